@@ -1,0 +1,172 @@
+/*
+ * pairec_gpu.h — C ABI of libpairec_gpu.so: the B200 (sm_100a) recall → feature → rank → sort/DPP hot path that
+ * drops in behind alibaba/pairec's Recall / IAlgorithm / ISort plugin contracts.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns an int status (PRG_OK == 0) and
+ * records a thread-local message readable through prg_last_error().  Nothing here aborts or throws across the
+ * boundary: the reference's callers treat an error as "log and keep the items unchanged"
+ * (sort/dpp_sort.go:304-307, service/rank/rank_service.go:274-277, service/recall/vector_recall.go:89-92).
+ *
+ * Reference interface each group replaces (paths relative to alibaba/pairec):
+ *   prg_recall_*    algorithm/faiss/vector_client.go:32-42 (VectorRetrieval.Search, vectorretrieval.proto:11-20),
+ *                   reached from service/recall/vector_recall.go:88 through algorithm.Run (algorithm/algorithm.go:126)
+ *   prg_rank        service/rank/rank_service.go:264-289 → algorithm.Run → eas/tfserving remote models
+ *                   (algorithm/eas/fm_response.go:28-34, algorithm/tfserving/response.go:51-63) and the item-side
+ *                   module.FeatureDao.FeatureFetch (module/feature_dao.go:24-26)
+ *   prg_sort_*      sort/item_rank_score.go:26-32, sort/item_score.go:15-18, sort/algo_score_sort.go:38-66
+ *   prg_dpp         sort/dpp_sort.go:271-351 (doSort), :372-475 (KernelMatrix), :477-551 (DPPWithWindow, DPP)
+ *   prg_lookup      algorithm/lookup.go:37-51
+ *   prg_set_*       the table loaders behind module/vector_*_dao.go, module/feature_*_dao.go and
+ *                   sort/dpp_sort.go:169-269 (loadEmbeddingCache): tables become HBM resident.
+ *
+ * Memory kinds: every data pointer is accompanied (per call) by `mem`: PRG_MEM_HOST = caller host memory, the
+ * call copies host<->device itself and returns when the outputs are valid; PRG_MEM_DEVICE = device pointers on
+ * this handle's device, the work is enqueued on the handle's stream and the caller orders against it with
+ * prg_sync() / prg_stream().  No pointer is retained after return, except tables adopted with PRG_MEM_DEVICE,
+ * which the caller must keep alive until prg_destroy or the next prg_set_* of the same table.
+ *
+ * Threading: any entry point may be called from any OS thread (cgo); calls on one handle are serialised by an
+ * internal mutex, different handles (one per GPU) run concurrently.
+ */
+#ifndef PAIREC_GPU_H
+#define PAIREC_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct prg_handle prg_handle;
+
+enum {
+  PRG_OK = 0,
+  PRG_EINVAL = 1,       /* bad argument */
+  PRG_ECUDA = 2,        /* CUDA runtime / driver failure (message carries the CUDA error string) */
+  PRG_ENOMEM = 3,
+  PRG_ESTATE = 4,       /* a table or model the call needs has not been set */
+  PRG_EUNSUPPORTED = 5, /* shape outside what the kernels are built for */
+  PRG_ENODEVICE = 6     /* no CUDA device: there is NO CPU fallback in this library */
+};
+
+enum { PRG_MEM_HOST = 0, PRG_MEM_DEVICE = 1 };
+enum { PRG_F32 = 0, PRG_F64 = 1 };
+
+/* rank model selector for prg_rank (what the replaced remote processor computed) */
+enum {
+  PRG_MODEL_FM = 0,     /* ALINK_FM-shaped: sigmoid(w0 + sum w + 1/2 sum_k((sum v)^2 - sum v^2)) */
+  PRG_MODEL_MLP = 1,    /* EasyRec/TF-Serving-shaped DNN: concat(field factors) -> dense layers (bf16) -> sigmoid */
+  PRG_MODEL_FM_MLP = 2  /* DeepFM-shaped: sigmoid(fm_logit + mlp_logit) */
+};
+
+/* ---------------------------------------------------------------- lifecycle */
+
+/* json_cfg: {"device":0,"max_batch":64,"max_k":1000,"max_candidates":1024} — all keys optional. */
+int prg_init(const char* json_cfg, prg_handle** out);
+void prg_destroy(prg_handle* h);
+const char* prg_last_error(void);
+const char* prg_version(void);
+/* Blocks until everything enqueued on the handle's stream has finished. */
+int prg_sync(prg_handle* h);
+/* The handle's cudaStream_t (as void*), for callers that order their own device work against ours. */
+void* prg_stream(prg_handle* h);
+
+/* ---------------------------------------------------------------- HBM-resident tables */
+
+/* Item embedding matrix scanned by recall: rows x dim f32 row-major, dim in {64,128}.  row_base is the global row
+ * id of local row 0 (non-zero on a row shard).  Replaces the index held by the remote faiss server. */
+int prg_set_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_t dim, uint64_t row_base, int mem);
+
+/* Per-item categorical field ids, rows x n_fields u32 row-major (what FeatureDao.FeatureFetch would have written
+ * into item.Properties, module/feature_hologres_dao.go:644-675, already id-encoded). */
+int prg_set_item_fields(prg_handle* h, const uint32_t* ids, uint64_t rows, uint32_t n_fields, int mem);
+
+/* Feature table `table` (0 <= table < n_fields): factors rows x fdim f32 (fdim == 16) and linear weights rows f32
+ * (may be NULL = zeros).  These are the embedding variables of the replaced remote model. */
+int prg_set_feature_table(prg_handle* h, int table, const float* factors, const float* linear, uint64_t rows,
+                          uint32_t fdim, int mem);
+int prg_set_fm_bias(prg_handle* h, float w0);
+
+/* Dense tower: n_layers weight matrices, dims[n_layers+1] (dims[0] == n_fields*fdim, dims[n_layers] == 1).
+ * W[l] is bf16 (raw uint16 bit patterns) [dims[l+1]][dims[l]] row-major (out-major), bias[l] f32 [dims[l+1]].
+ * Host pointers only. */
+int prg_set_mlp(prg_handle* h, int n_layers, const uint32_t* dims, const uint16_t* const* W, const float* const* bias);
+
+/* Diversity embeddings read by DPP: rows x dim, f32 or f64 row-major (the table behind
+ * sort/dpp_sort.go:169-269; rows are L2-normalised in fp64 at use when normalize != 0, :234-237). */
+int prg_set_diversity_matrix(prg_handle* h, const void* data, uint64_t rows, uint32_t dim, int dtype, int mem);
+
+/* ---------------------------------------------------------------- recall (faiss VectorRetrieval.Search replacement) */
+
+/* Exact inner-product top-k.  q: B x dim f32.  out_row: B x k u32 global row ids, out_score: B x k f32,
+ * out_n: B i32 (= min(k, rows)); rows beyond out_n are filled with 0xFFFFFFFF / -inf.
+ * Score(row,q) = fmaf chain over dims 0..dim-1 starting from +0 (one accumulator, IEEE RN).
+ * Order: score descending, ties by ascending row; NaN scores rank below -inf. */
+int prg_recall_topk(prg_handle* h, const float* q, int B, int k, uint32_t* out_row, float* out_score,
+                    int32_t* out_n, int mem);
+
+/* Row-sharded recall: local top-k as 64-bit order keys, device pointers only.
+ * key = (ordered_bits(score) << 32) | (0xFFFFFFFF - global_row); 0 = empty slot.  out_keys: B x k u64. */
+int prg_recall_local_keys(prg_handle* h, const float* q_dev, int B, int k, uint64_t* out_keys_dev);
+/* Merge G gathered key lists (keys_dev: G x B x k, the all-gather output) into the global top-k. */
+int prg_merge_keys(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint32_t* out_row,
+                   float* out_score, int32_t* out_n, int mem);
+
+/* ---------------------------------------------------------------- rank (feature gather + FM / MLP forward) */
+
+/* rows: B x n u32 item rows (0xFFFFFFFF = padding, scored 0).  out_score: B x n f64 (the AlgoResponse.GetScore()
+ * values, algorithm/response/resonse.go:3-7), f32 arithmetic widened exactly. */
+int prg_rank(prg_handle* h, int model, const uint32_t* rows, int B, int n, double* out_score, int mem);
+
+/* ---------------------------------------------------------------- sort */
+
+/* Order of sort.Sort(sort.Reverse(ItemScoreSlice)) (sort/item_rank_score.go:29): descending score.  Host-side
+ * emulation of Go's pdqsort so that tie order follows the reference for n <= a few thousand.  out_perm[i] = input
+ * index of the item at output position i.  Pure host code (no GPU involved). */
+int prg_sort_desc_host(const double* score, int n, int32_t* out_perm);
+/* Device batched variant: B independent lists of n scores; stable total order (score desc, input index asc). */
+int prg_sort_desc(prg_handle* h, const double* score, int B, int n, int32_t* out_perm, int mem);
+
+/* ---------------------------------------------------------------- DPP re-rank (sort/dpp_sort.go) */
+
+typedef struct prg_dpp_params {
+  double alpha;             /* DPPConf.Alpha / abtest dpp_alpha (dpp_sort.go:374) */
+  int32_t top_n;            /* ctx.Size */
+  int32_t window_size;      /* DPPConf.WindowSize, <=0 -> 10 (dpp_sort.go:89-91) */
+  int32_t norm_mode;        /* dpp_norm_relevance_score 0/1/2 (dpp_sort.go:382-405) */
+  int32_t normalize_emb;    /* NormalizeEmb (dpp_sort.go:234-237) */
+  int32_t candidate_count;  /* DPPConf.CandidateCount (dpp_sort.go:280-287) */
+  double min_score_percent; /* DPPConf.MinScorePercent (dpp_sort.go:288-298) */
+} prg_dpp_params;
+
+/* rows: B x n item rows into the diversity matrix; score: B x n f64 relevance (Item.Score) in the order the items
+ * reach doSort.  out_idx: B x top_n i32 indices into the request's input list, out_n: B i32 number written
+ * (min(top_n, n_after_truncation)), status: B i32 per-request (0 ok; 1 = reference would have returned the input
+ * unchanged, e.g. "all item score is zero", dpp_sort.go:385-388,397-400).  0xFFFFFFFF rows are padding. */
+int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_dpp_params* p,
+            int32_t* out_idx, int32_t* out_n, int32_t* status, int mem);
+
+/* ---------------------------------------------------------------- fused request path */
+
+/* recall -> gather+rank -> score sort -> DPP for B requests, everything device resident in between.
+ * q: B x dim f32.  out_row: B x top_n u32 item rows in final order, out_score: B x top_n f64 rank scores,
+ * out_n: B i32.  This is what one /api/recommend costs below the four plugin call sites. */
+int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params* p,
+                  uint32_t* out_row, double* out_score, int32_t* out_n, int mem);
+
+/* ---------------------------------------------------------------- LOOKUP algorithm (algorithm/lookup.go:37-51) */
+
+/* present[i] != 0 -> out[i] = value[i], else 0.5.  Pure host code. */
+int prg_lookup(const double* value, const uint8_t* present, int n, double* out);
+
+/* ---------------------------------------------------------------- instrumentation */
+
+/* Number of kernels launched by this handle since init (bench.py's gpu_launches). */
+uint64_t prg_launch_count(prg_handle* h);
+/* Last recall: how many queries took the dense re-scan path, and candidates collected per query (max). */
+int prg_recall_stats(prg_handle* h, int32_t* n_fallback, int32_t* max_candidates);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAIREC_GPU_H */

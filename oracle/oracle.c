@@ -1,0 +1,731 @@
+/*
+ * oracle.c — CPU restatement of the pairec recall -> feature -> rank -> sort/DPP hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load it; the product (libpairec_gpu.so) never does and has no CPU path of its own.
+ *
+ * PARITY STATUS
+ *   - DPP / KernelMatrix / DPPWithWindow, score sorts, LOOKUP restate code that IS in the reference
+ *     (sort/dpp_sort.go, sort/item_rank_score.go, sort/algo_score_sort.go, algorithm/lookup.go) line by line, but the
+ *     reference holds no test, golden vector or fixture for any of them and neither a Go toolchain
+ *     nor gonum v0.12.0 / the Go stdlib sources exist in the build container: "parity unpinned".  The gonum and
+ *     pdqsort internals below (summation orders, pivot rules) are restated from the published algorithms from
+ *     memory and are marked [UNVERIFIED-UPSTREAM] where results could differ in the last bit / in tie order.
+ *   - recall / gather+FM / MLP arithmetic is NOT in the reference (remote faiss / EAS / TF-Serving); the reference
+ *     pins only the wire contract.  The semantics are DEFINED here (and in DESIGN.md) and the CUDA path must
+ *     reproduce them: bit-exact for recall keys and FM logits, 1e-5 relative for MLP scores.
+ *   - The one known-answer test of the path the reference does hold, utils/ast/ast_test.go:12-27
+ *     (${ctr}+${click}+${price} with 0.1,0.3,0.1 -> 0.5), is checked against orc_rank_score_expr in tests/.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -mavx2 -mfma -ffp-contract=off, pthreads).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+/* minimal fork-join over pthreads (libgomp is not in the image) */
+typedef void (*orc_job_fn)(void* arg, int tid, int n_threads);
+typedef struct { orc_job_fn fn; void* arg; int tid, nt; } orc_job;
+static void* orc_job_main(void* p) { orc_job* j = (orc_job*)p; j->fn(j->arg, j->tid, j->nt); return NULL; }
+static int orc_hw_threads(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
+static void orc_parallel(int nt, orc_job_fn fn, void* arg) {
+  if (nt <= 1) { fn(arg, 0, 1); return; }
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nt);
+  orc_job* jobs = (orc_job*)malloc(sizeof(orc_job) * (size_t)nt);
+  for (int t = 0; t < nt; ++t) { jobs[t].fn = fn; jobs[t].arg = arg; jobs[t].tid = t; jobs[t].nt = nt; }
+  for (int t = 1; t < nt; ++t) pthread_create(&th[t], NULL, orc_job_main, &jobs[t]);
+  orc_job_main(&jobs[0]);
+  for (int t = 1; t < nt; ++t) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------ order keys */
+/* Same total order as pairec_b200/csrc/common.cuh: key = ord(score)<<32 | (0xFFFFFFFF-row); NaN -> ord 1. */
+static inline uint32_t f32_ord(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 1u;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static inline float ord_f32(uint32_t o) {
+  uint32_t u = (o == 1u) ? 0x7FC00000u : ((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline uint64_t make_key(float s, uint32_t row) { return ((uint64_t)f32_ord(s) << 32) | (uint64_t)(0xFFFFFFFFu - row); }
+
+ORC_API uint64_t orc_make_key(float s, uint32_t row) { return make_key(s, row); }
+ORC_API float orc_key_score(uint64_t key) { return ord_f32((uint32_t)(key >> 32)); }
+ORC_API uint32_t orc_key_row(uint64_t key) { return 0xFFFFFFFFu - (uint32_t)key; }
+
+static int cmp_key_desc(const void* a, const void* b) {
+  uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+  return (x < y) - (x > y);
+}
+
+/* ------------------------------------------------------------------------------------------------ recall */
+/*
+ * Exact inner-product top-k (the arithmetic the remote faiss VectorRetrieval.Search server performs for
+ * service/recall/vector_recall.go:88; metric/tie rule unspecified upstream, defined here):
+ *   score(row,q) = fmaf(E[row][d-1],Q[q][d-1], ... fmaf(E[row][0],Q[q][0], +0)) — one accumulator, dims ascending.
+ *   order: score descending, ties by ascending global row; NaN below -inf.
+ * out_keys: B x k, descending, 0-padded.  Threads: pthreads over row chunks with per-thread bounded buffers.
+ */
+typedef struct { uint64_t* v; int n, cap, k; uint64_t thr; } keybuf;
+
+static void kb_init(keybuf* b, int k) {
+  b->k = k; b->cap = 4 * k + 64; b->n = 0; b->thr = 0;
+  b->v = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)b->cap);
+}
+static void kb_shrink(keybuf* b) {
+  qsort(b->v, (size_t)b->n, sizeof(uint64_t), cmp_key_desc);
+  if (b->n > b->k) { b->n = b->k; b->thr = b->v[b->k - 1]; }
+}
+static inline void kb_push(keybuf* b, uint64_t key) {
+  if (key < b->thr) return;
+  b->v[b->n++] = key;
+  if (b->n == b->cap) kb_shrink(b);
+}
+
+typedef struct { const float* E; uint64_t rows; uint32_t dim; uint64_t row_base; const float* Qt; int nq; keybuf* bufs; } recall_job;
+static void recall_worker(void* arg, int tid, int nt) {
+  const recall_job* J = (const recall_job*)arg;
+  keybuf* mine = J->bufs + (size_t)tid * 64;
+  const uint64_t r0 = J->rows * (uint64_t)tid / (uint64_t)nt, r1 = J->rows * (uint64_t)(tid + 1) / (uint64_t)nt;
+  const uint32_t dim = J->dim;
+  for (uint64_t r = r0; r < r1; ++r) {
+    const float* x = J->E + (size_t)r * dim;
+    float acc[64] __attribute__((aligned(64)));
+    for (int q = 0; q < 64; ++q) acc[q] = 0.0f;
+    for (uint32_t d = 0; d < dim; ++d) {
+      const float xv = x[d];
+      const float* qt = J->Qt + (size_t)d * 64;
+      for (int q = 0; q < 64; ++q) acc[q] = __builtin_fmaf(xv, qt[q], acc[q]);
+    }
+    const uint32_t grow = (uint32_t)(J->row_base + r);
+    for (int q = 0; q < J->nq; ++q) kb_push(&mine[q], make_key(acc[q], grow));
+  }
+}
+
+ORC_API int orc_recall_topk(const float* E, uint64_t rows, uint32_t dim, uint64_t row_base, const float* Q, int B, int k,
+                            uint64_t* out_keys, int n_threads) {
+  if (!E || !Q || !out_keys || B <= 0 || k <= 0 || dim == 0) return 1;
+  if (n_threads <= 0) n_threads = orc_hw_threads();
+  for (int q0 = 0; q0 < B; q0 += 64) {
+    const int nq = (B - q0 < 64) ? (B - q0) : 64;
+    /* Qt[dd][q] so that the q loop vectorises; every lane is still one exact fmaf per dim */
+    float* Qt = (float*)aligned_alloc(64, sizeof(float) * (size_t)dim * 64);
+    memset(Qt, 0, sizeof(float) * (size_t)dim * 64);
+    for (int q = 0; q < nq; ++q)
+      for (uint32_t d = 0; d < dim; ++d) Qt[(size_t)d * 64 + q] = Q[(size_t)(q0 + q) * dim + d];
+    keybuf* bufs = (keybuf*)malloc(sizeof(keybuf) * (size_t)n_threads * 64);
+    for (int i = 0; i < n_threads * 64; ++i) kb_init(&bufs[i], k);
+    recall_job job = {E, rows, dim, row_base, Qt, nq, bufs};
+    orc_parallel(n_threads, recall_worker, &job);
+    for (int q = 0; q < nq; ++q) {
+      keybuf all;
+      kb_init(&all, k);
+      for (int t = 0; t < n_threads; ++t) {
+        keybuf* b = &bufs[(size_t)t * 64 + q];
+        for (int i = 0; i < b->n; ++i) kb_push(&all, b->v[i]);
+      }
+      kb_shrink(&all);
+      uint64_t* o = out_keys + (size_t)(q0 + q) * k;
+      for (int i = 0; i < k; ++i) o[i] = (i < all.n) ? all.v[i] : 0ull;
+      free(all.v);
+    }
+    for (int i = 0; i < n_threads * 64; ++i) free(bufs[i].v);
+    free(bufs);
+    free(Qt);
+  }
+  return 0;
+}
+
+/* scores only (for property checks): out[q*rows + r] */
+ORC_API int orc_recall_scores(const float* E, uint64_t rows, uint32_t dim, const float* Q, int B, float* out) {
+  for (int q = 0; q < B; ++q)
+    for (uint64_t r = 0; r < rows; ++r) {
+      float acc = 0.0f;
+      for (uint32_t d = 0; d < dim; ++d) acc = __builtin_fmaf(E[r * dim + d], Q[(size_t)q * dim + d], acc);
+      out[(size_t)q * rows + r] = acc;
+    }
+  return 0;
+}
+
+/* merge of G sorted shard lists: keys [G][B][k] -> [B][k] */
+ORC_API int orc_merge_keys(const uint64_t* keys, int G, int B, int k, uint64_t* out) {
+  uint64_t* tmp = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)G * k);
+  for (int b = 0; b < B; ++b) {
+    for (int g = 0; g < G; ++g) memcpy(tmp + (size_t)g * k, keys + ((size_t)g * B + b) * k, sizeof(uint64_t) * (size_t)k);
+    qsort(tmp, (size_t)G * k, sizeof(uint64_t), cmp_key_desc);
+    memcpy(out + (size_t)b * k, tmp, sizeof(uint64_t) * (size_t)k);
+  }
+  free(tmp);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ gather + FM */
+/*
+ * Item-side feature gather + FM second-order forward, the work module/feature_*_dao.go (FeatureFetch) and the remote
+ * ALINK_FM processor (algorithm/eas/fm_request.go:29-79, fm_response.go:28-34) do between them.  Defined semantics
+ * (f32, fixed order, every step one IEEE operation):
+ *   id_f = fields[row][f];  id_f >= table_rows[f]  -> the field contributes zeros
+ *   lin   = w0;            lin   = lin + w_f[id_f]                       f = 0..F-1
+ *   s_k   = 0;             s_k   = s_k + v_f[id_f][k]                    f = 0..F-1
+ *   ss_k  = 0;             ss_k  = fmaf(v, v, ss_k)
+ *   inter = 0;             inter = inter + fmaf(s_k, s_k, -ss_k)         k = 0..fdim-1
+ *   logit = fmaf(0.5f, inter, lin)
+ * x_out (optional): the F*fdim concatenated factors (MLP input), row-major [n][F*fdim].
+ * rows == 0xFFFFFFFF is padding: logit 0, x zeros.
+ */
+ORC_API int orc_gather_fm(const uint32_t* fields, uint64_t field_rows, uint32_t F, const float* const* factors,
+                          const float* const* linear, const uint64_t* table_rows, uint32_t fdim, float w0,
+                          const uint32_t* rows, int n, float* logit_out, float* x_out) {
+  if (fdim > 64) return 1;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t row = rows[i];
+    float* x = x_out ? x_out + (size_t)i * F * fdim : NULL;
+    if (row == 0xFFFFFFFFu || row >= field_rows) {
+      if (logit_out) logit_out[i] = 0.0f;
+      if (x) memset(x, 0, sizeof(float) * (size_t)F * fdim);
+      continue;
+    }
+    float lin = w0, s[64], ss[64];
+    for (uint32_t k = 0; k < fdim; ++k) { s[k] = 0.0f; ss[k] = 0.0f; }
+    for (uint32_t f = 0; f < F; ++f) {
+      const uint32_t id = fields[(size_t)row * F + f];
+      const int ok = id < table_rows[f];
+      const float w = (ok && linear[f]) ? linear[f][id] : 0.0f;
+      lin = lin + w;
+      for (uint32_t k = 0; k < fdim; ++k) {
+        const float v = ok ? factors[f][(size_t)id * fdim + k] : 0.0f;
+        s[k] = s[k] + v;
+        ss[k] = __builtin_fmaf(v, v, ss[k]);
+        if (x) x[f * fdim + k] = v;
+      }
+    }
+    float inter = 0.0f;
+    for (uint32_t k = 0; k < fdim; ++k) inter = inter + __builtin_fmaf(s[k], s[k], -ss[k]);
+    if (logit_out) logit_out[i] = __builtin_fmaf(0.5f, inter, lin);
+  }
+  return 0;
+}
+
+/* score = (float)(1 / (1 + exp(-(double)logit))): the f32 AlgoResponse score, evaluated through fp64 so that the
+ * CPU and GPU libm differences (<= 1 ulp of fp64) vanish in the f32 rounding. */
+ORC_API float orc_sigmoid(float logit) { return (float)(1.0 / (1.0 + exp(-(double)logit))); }
+
+/* ------------------------------------------------------------------------------------------------ MLP */
+static inline uint16_t f32_to_bf16(float f) { /* round to nearest even; NaN kept quiet */
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+ORC_API uint16_t orc_f32_to_bf16(float f) { return f32_to_bf16(f); }
+ORC_API float orc_bf16_to_f32(uint16_t h) { return bf16_to_f32(h); }
+
+/*
+ * Dense tower of the replaced remote DNN (algorithm/eas easyrec / algorithm/tfserving; wire contract
+ * easyrec_response.go:35-70, tfserving/response.go:51-63).  Defined semantics ("bf16x2" activations):
+ *   an activation a (f32) is carried as hi = bf16(a), lo = bf16(a - hi): the tensor cores see two bf16 operands,
+ *   the value carried is hi + lo (>= 16 significant bits), which keeps the result continuous under the 1e-6-level
+ *   accumulation-order differences between implementations (plain bf16 activations flip whole bf16 ulps).
+ *   z_j   = b_j + sum_i W[j][i] * (hi_i + lo_i)      W bf16, accumulation wide (oracle: fp64), z rounded to f32
+ *   hidden: a = max(z, 0) -> split again;   last layer (width 1): logit = z (f32)
+ * x: [n][dims[0]] f32.  W[l]: [dims[l+1]][dims[l]] bf16 bits.  logit_out: [n].
+ */
+typedef struct { const float* x; int n, n_layers; const uint32_t* dims; const uint16_t* const* W; const float* const* bias; float* logit_out; uint32_t maxd; } mlp_job;
+static void mlp_worker(void* arg, int tid, int nt) {
+  const mlp_job* J = (const mlp_job*)arg;
+  const uint32_t* dims = J->dims;
+  double* a = (double*)malloc(sizeof(double) * J->maxd);
+  float* z = (float*)malloc(sizeof(float) * J->maxd);
+  const int i0 = (int)((int64_t)J->n * tid / nt), i1 = (int)((int64_t)J->n * (tid + 1) / nt);
+  for (int i = i0; i < i1; ++i) {
+    for (uint32_t c = 0; c < dims[0]; ++c) {
+      const float v = J->x[(size_t)i * dims[0] + c];
+      const float hi = bf16_to_f32(f32_to_bf16(v));
+      const float lo = bf16_to_f32(f32_to_bf16(v - hi));
+      a[c] = (double)hi + (double)lo;
+    }
+    for (int l = 0; l < J->n_layers; ++l) {
+      const uint32_t K = dims[l], N = dims[l + 1];
+      for (uint32_t j = 0; j < N; ++j) {
+        double acc = 0.0;
+        const uint16_t* w = J->W[l] + (size_t)j * K;
+        for (uint32_t c = 0; c < K; ++c) acc += (double)bf16_to_f32(w[c]) * a[c];
+        z[j] = (float)(acc + (double)(J->bias[l] ? J->bias[l][j] : 0.0f));
+      }
+      if (l == J->n_layers - 1) {
+        J->logit_out[i] = z[0];
+      } else {
+        for (uint32_t j = 0; j < N; ++j) {
+          const float r = z[j] > 0.0f ? z[j] : 0.0f;
+          const float hi = bf16_to_f32(f32_to_bf16(r));
+          const float lo = bf16_to_f32(f32_to_bf16(r - hi));
+          a[j] = (double)hi + (double)lo;
+        }
+      }
+    }
+  }
+  free(a);
+  free(z);
+}
+
+ORC_API int orc_mlp_forward(const float* x, int n, int n_layers, const uint32_t* dims, const uint16_t* const* W,
+                            const float* const* bias, float* logit_out) {
+  uint32_t maxd = 0;
+  for (int l = 0; l <= n_layers; ++l)
+    if (dims[l] > maxd) maxd = dims[l];
+  if (dims[n_layers] != 1) return 1;
+  mlp_job job = {x, n, n_layers, dims, W, bias, logit_out, maxd};
+  orc_parallel(n > 256 ? orc_hw_threads() : 1, mlp_worker, &job);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ LOOKUP */
+/* algorithm/lookup.go:37-51: score = features[FieldName].(float64) when the key is present, else 0.5. */
+ORC_API void orc_lookup(const double* value, const uint8_t* present, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = present[i] ? value[i] : 0.5;
+}
+
+/* utils/ast: the simple "${a} + ${b} * w" RankScore expressions (service/rank/rank_service.go:339-363) reduce, for
+ * the sums-of-products the GPU path accepts, to left-to-right fp64 evaluation.  terms[i] = coef[i] * value[i]. */
+ORC_API double orc_rank_score_expr(const double* value, const double* coef, int n) {
+  double acc = 0.0;
+  for (int i = 0; i < n; ++i) acc = (i == 0) ? coef[i] * value[i] : acc + coef[i] * value[i];
+  return acc;
+}
+
+/* ------------------------------------------------------------------------------------------------ Go sort (pdqsort) */
+/*
+ * sort.Sort / sort.Slice of Go >= 1.19 (pattern-defeating quicksort, src/sort/zsortinterface.go) driving a
+ * permutation, so that the tie order of sort/item_rank_score.go:29, sort/algo_score_sort.go:51 and
+ * sort/dpp_sort.go:119,281 can be reproduced.  [UNVERIFIED-UPSTREAM]: restated from the published algorithm; the
+ * stdlib source is not in the container.  less(i,j) is evaluated on the CURRENT positions i,j like sort.Interface.
+ */
+typedef struct { const double* score; int32_t* perm; int descending; } sortctx;
+
+static inline int s_less(const sortctx* c, int i, int j) {
+  const double a = c->score[c->perm[i]], b = c->score[c->perm[j]];
+  return c->descending ? (b < a) : (a < b); /* sort.Reverse: Less(i,j) = inner.Less(j,i) */
+}
+static inline void s_swap(sortctx* c, int i, int j) { int32_t t = c->perm[i]; c->perm[i] = c->perm[j]; c->perm[j] = t; }
+
+static void s_insertion(sortctx* c, int a, int b) {
+  for (int i = a + 1; i < b; ++i)
+    for (int j = i; j > a && s_less(c, j, j - 1); --j) s_swap(c, j, j - 1);
+}
+static void s_sift_down(sortctx* c, int lo, int hi, int first) {
+  int root = lo;
+  for (;;) {
+    int child = 2 * root + 1;
+    if (child >= hi) return;
+    if (child + 1 < hi && s_less(c, first + child, first + child + 1)) child++;
+    if (!s_less(c, first + root, first + child)) return;
+    s_swap(c, first + root, first + child);
+    root = child;
+  }
+}
+static void s_heapsort(sortctx* c, int a, int b) {
+  const int first = a, lo = 0, hi = b - a;
+  for (int i = (hi - 1) / 2; i >= 0; --i) s_sift_down(c, i, hi, first);
+  for (int i = hi - 1; i >= 0; --i) { s_swap(c, first, first + i); s_sift_down(c, lo, i, first); }
+}
+static int bits_len(unsigned x) { int n = 0; while (x) { ++n; x >>= 1; } return n; }
+static void s_break_patterns(sortctx* c, int a, int b) {
+  const int length = b - a;
+  if (length >= 8) {
+    uint64_t r = (uint64_t)length;
+    const unsigned modulus = 1u << bits_len((unsigned)length);
+    const int idx = a + (length / 4) * 2 - 1;
+    for (int i = 0; i < 3; ++i) {
+      r ^= r << 13; r ^= r >> 7; r ^= r << 17;
+      int other = (int)((unsigned)r & (modulus - 1));
+      if (other >= length) other -= length;
+      s_swap(c, idx - 1 + i, a + other);
+    }
+  }
+}
+static void s_order2(sortctx* c, int* a, int* b, int* swaps) {
+  if (s_less(c, *b, *a)) { int t = *a; *a = *b; *b = t; (*swaps)++; }
+}
+static int s_median(sortctx* c, int a, int b, int cc, int* swaps) {
+  s_order2(c, &a, &b, swaps);
+  s_order2(c, &b, &cc, swaps);
+  s_order2(c, &a, &b, swaps);
+  return b;
+}
+enum { HINT_UNKNOWN = 0, HINT_INCREASING = 1, HINT_DECREASING = 2 };
+static int s_choose_pivot(sortctx* c, int a, int b, int* hint) {
+  const int l = b - a;
+  int swaps = 0, i = a + l / 4 * 1, j = a + l / 4 * 2, k = a + l / 4 * 3;
+  if (l >= 8) {
+    if (l >= 50) {
+      i = s_median(c, i - 1, i, i + 1, &swaps);
+      j = s_median(c, j - 1, j, j + 1, &swaps);
+      k = s_median(c, k - 1, k, k + 1, &swaps);
+    }
+    j = s_median(c, i, j, k, &swaps);
+  }
+  *hint = (swaps == 0) ? HINT_INCREASING : (swaps == 12) ? HINT_DECREASING : HINT_UNKNOWN;
+  return j;
+}
+static void s_reverse(sortctx* c, int a, int b) {
+  int i = a, j = b - 1;
+  while (i < j) { s_swap(c, i, j); ++i; --j; }
+}
+static int s_partial_insertion(sortctx* c, int a, int b) {
+  int i = a + 1;
+  for (int step = 0; step < 5; ++step) {
+    while (i < b && !s_less(c, i, i - 1)) ++i;
+    if (i == b) return 1;
+    if (b - a < 50) return 0;
+    s_swap(c, i, i - 1);
+    if (i - a >= 2)
+      for (int j = i - 1; j >= 1; --j) { if (!s_less(c, j, j - 1)) break; s_swap(c, j, j - 1); }
+    if (b - i >= 2)
+      for (int j = i + 1; j < b; ++j) { if (!s_less(c, j, j - 1)) break; s_swap(c, j, j - 1); }
+  }
+  return 0;
+}
+static int s_partition_equal(sortctx* c, int a, int b, int pivot) {
+  s_swap(c, a, pivot);
+  int i = a + 1, j = b - 1;
+  for (;;) {
+    while (i <= j && !s_less(c, a, i)) ++i;
+    while (i <= j && s_less(c, a, j)) --j;
+    if (i > j) break;
+    s_swap(c, i, j); ++i; --j;
+  }
+  return i;
+}
+static int s_partition(sortctx* c, int a, int b, int pivot, int* already) {
+  s_swap(c, a, pivot);
+  int i = a + 1, j = b - 1;
+  while (i <= j && s_less(c, i, a)) ++i;
+  while (i <= j && !s_less(c, j, a)) --j;
+  if (i > j) { s_swap(c, j, a); *already = 1; return j; }
+  s_swap(c, i, j); ++i; --j;
+  for (;;) {
+    while (i <= j && s_less(c, i, a)) ++i;
+    while (i <= j && !s_less(c, j, a)) --j;
+    if (i > j) break;
+    s_swap(c, i, j); ++i; --j;
+  }
+  s_swap(c, j, a);
+  *already = 0;
+  return j;
+}
+static void s_pdqsort(sortctx* c, int a, int b, int limit) {
+  int was_balanced = 1, was_partitioned = 1;
+  for (;;) {
+    const int length = b - a;
+    if (length <= 12) { s_insertion(c, a, b); return; }
+    if (limit == 0) { s_heapsort(c, a, b); return; }
+    if (!was_balanced) { s_break_patterns(c, a, b); --limit; }
+    int hint;
+    int pivot = s_choose_pivot(c, a, b, &hint);
+    if (hint == HINT_DECREASING) {
+      s_reverse(c, a, b);
+      pivot = (b - 1) - (pivot - a);
+      hint = HINT_INCREASING;
+    }
+    if (was_balanced && was_partitioned && hint == HINT_INCREASING) {
+      if (s_partial_insertion(c, a, b)) return;
+    }
+    if (a > 0 && !s_less(c, a - 1, pivot)) { a = s_partition_equal(c, a, b, pivot); continue; }
+    int already;
+    const int mid = s_partition(c, a, b, pivot, &already);
+    was_partitioned = already;
+    const int left = mid - a, right = b - mid, thr = length / 8;
+    if (left < right) {
+      was_balanced = left >= thr;
+      s_pdqsort(c, a, mid, limit);
+      a = mid + 1;
+    } else {
+      was_balanced = right >= thr;
+      s_pdqsort(c, mid + 1, b, limit);
+      b = mid;
+    }
+  }
+}
+/* perm_out[i] = input index placed at position i.  descending != 0: sort.Sort(sort.Reverse(ItemScoreSlice)). */
+ORC_API void orc_go_sort(const double* score, int n, int descending, int32_t* perm_out) {
+  for (int i = 0; i < n; ++i) perm_out[i] = i;
+  if (n <= 1) return;
+  sortctx c = {score, perm_out, descending};
+  s_pdqsort(&c, 0, n, bits_len((unsigned)n));
+}
+/* The stable total order the GPU sort defines: score descending, then input index ascending. */
+ORC_API void orc_stable_sort_desc(const double* score, int n, int32_t* perm_out) {
+  for (int i = 0; i < n; ++i) perm_out[i] = i;
+  for (int i = 1; i < n; ++i) { /* insertion sort: n is a few thousand at most */
+    const int32_t p = perm_out[i];
+    int j = i - 1;
+    while (j >= 0 && score[perm_out[j]] < score[p]) { perm_out[j + 1] = perm_out[j]; --j; }
+    perm_out[j + 1] = p;
+  }
+}
+/* sort/algo_score_sort.go:28-66: max(Score) > SwitchThreshold -> sort by current score, else by the field;
+ * sort.Slice(less = iScore > jScore).  (The :59 bug only triggers on a missing field, not modelled.) */
+ORC_API void orc_algo_score_sort(const double* score, const double* field, int n, double switch_threshold,
+                                 int32_t* perm_out) {
+  double mx = -1e300;
+  for (int i = 0; i < n; ++i)
+    if (score[i] > mx) mx = score[i];
+  orc_go_sort(mx > switch_threshold ? score : field, n, 1, perm_out);
+}
+
+/* ------------------------------------------------------------------------------------------------ DPP */
+/* gonum floats.Norm(v, 2) -> f64.L2NormUnitary, scaled form (internal/asm/f64 l2norm noasm variant).
+ * [UNVERIFIED-UPSTREAM]: the amd64 assembly variant may sum in a different order (last-bit differences). */
+static double g_norm2(const double* x, int n) {
+  double scale = 0.0, sumsq = 1.0;
+  for (int i = 0; i < n; ++i) {
+    const double v = x[i];
+    if (v == 0) continue;
+    const double a = fabs(v);
+    if (isnan(a)) return NAN;
+    if (scale < a) { const double s = scale / a; sumsq = 1 + sumsq * s * s; scale = a; }
+    else { const double s = a / scale; sumsq += s * s; }
+  }
+  if (isinf(scale)) return INFINITY;
+  return scale * sqrt(sumsq);
+}
+/* gonum f64.DotUnitary (amd64 SSE2): four partial sums by index mod 4, tail into lane 0, (s0+s2)+(s1+s3); separate
+ * multiply and add roundings.  [UNVERIFIED-UPSTREAM] */
+static double g_dot_unitary(const double* x, const double* y, int n) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  int i = 0;
+  for (; i + 4 <= n; i += 4) {
+    s0 += x[i] * y[i];
+    s1 += x[i + 1] * y[i + 1];
+    s2 += x[i + 2] * y[i + 2];
+    s3 += x[i + 3] * y[i + 3];
+  }
+  for (; i < n; ++i) s0 += x[i] * y[i];
+  return (s0 + s2) + (s1 + s3);
+}
+/* gonum blas Dgemm(NoTrans, Trans) element: k is processed in blocks of 64, each block one DotUnitary, block
+ * results added to C in order.  [UNVERIFIED-UPSTREAM] */
+static double g_gemm_nt_elem(const double* a, const double* b, int k) {
+  double c = 0.0;
+  for (int k0 = 0; k0 < k; k0 += 64) {
+    const int len = (k - k0 < 64) ? (k - k0) : 64;
+    c += g_dot_unitary(a + k0, b + k0, len);
+  }
+  return c;
+}
+static int g_max_idx(const double* s, int n) { /* floats.MaxIdx: NaN skipped, first maximum wins, 0 if all NaN */
+  double mx = NAN;
+  int ind = 0;
+  for (int i = 0; i < n; ++i) {
+    const double v = s[i];
+    if (isnan(v)) continue;
+    if (v > mx || isnan(mx)) { mx = v; ind = i; }
+  }
+  return ind;
+}
+static int index_of(const int32_t* a, int n, int e) {
+  for (int i = 0; i < n; ++i)
+    if (a[i] == e) return i;
+  return -1;
+}
+
+typedef struct {
+  double alpha;
+  int32_t top_n, window_size, norm_mode, normalize_emb, candidate_count;
+  double min_score_percent;
+} orc_dpp_params;
+
+/* sort/dpp_sort.go:493-551.  L accessed through rows computed on demand (Lrow) — mathematically the dense kernel
+ * matrix of :372-475, element for element.  F: n x (D+1) features, r: n quality terms. */
+static void dpp_L_row(const double* F, const double* r, int n, int D1, int j, double* out) {
+  for (int i = 0; i < n; ++i) {
+    const double s = g_gemm_nt_elem(F + (size_t)j * D1, F + (size_t)i * D1, D1); /* S[j][i] */
+    out[i] = (r[j] * s) * r[i];                                                   /* diag(r) S diag(r), :466-472 */
+  }
+}
+static int dpp_once(const double* F, const double* r, int n, int D1, int top_n, const int32_t* existed, int n_existed,
+                    int32_t* Y) {
+  const double eps = 1e-10;
+  if (top_n > n) top_n = n;
+  double* d2 = (double*)malloc(sizeof(double) * (size_t)n);
+  double* C = (double*)calloc((size_t)(top_n > 0 ? top_n : 1) * n, sizeof(double));
+  double* Lj = (double*)malloc(sizeof(double) * (size_t)n);
+  double* e = (double*)malloc(sizeof(double) * (size_t)n);
+  int ny = 0;
+  for (int i = 0; i < n; ++i) {
+    if (index_of(existed, n_existed, i) < 0) {
+      const double s = g_gemm_nt_elem(F + (size_t)i * D1, F + (size_t)i * D1, D1);
+      d2[i] = (r[i] * s) * r[i];
+    } else d2[i] = NAN;
+  }
+  int j = g_max_idx(d2, n);
+  Y[ny++] = j;
+  while (ny < top_n) {
+    double dj = d2[j];
+    if (dj < eps) break;
+    dj = sqrt(dj);
+    const int k = ny - 1;
+    const double inv = 1 / dj;
+    dpp_L_row(F, r, n, D1, j, Lj);
+    if (k == 0) {
+      for (int i = 0; i < n; ++i) e[i] = inv * Lj[i]; /* e.Scale(1/dj, Lj) */
+    } else {
+      /* ss = cj^T * C[0:k] : Dgemm(Trans,NoTrans), l ascending, AxpyUnitary (mul then add), skipped when tmp == 0 */
+      for (int i = 0; i < n; ++i) e[i] = 0.0;
+      for (int l = 0; l < k; ++l) {
+        const double tmp = C[(size_t)l * n + j];
+        if (tmp != 0)
+          for (int i = 0; i < n; ++i) e[i] += tmp * C[(size_t)l * n + i];
+      }
+      for (int i = 0; i < n; ++i) e[i] = inv * (Lj[i] - e[i]); /* e.Sub(Lj, ss); e.Scale(1/dj, e) */
+    }
+    memcpy(C + (size_t)k * n, e, sizeof(double) * (size_t)n);
+    for (int i = 0; i < n; ++i) d2[i] = d2[i] - e[i] * e[i]; /* MulElem then SubVec */
+    d2[j] = NAN;
+    j = g_max_idx(d2, n);
+    Y[ny++] = j;
+  }
+  if (ny < top_n) {
+    for (int i = 0; i < n; ++i) {
+      if (index_of(existed, n_existed, i) < 0 && index_of(Y, ny, i) < 0) {
+        Y[ny++] = i;
+        if (ny == top_n) break;
+      }
+    }
+  }
+  free(d2); free(C); free(Lj); free(e);
+  return ny;
+}
+
+/*
+ * One request through DPPSort.doSort (sort/dpp_sort.go:271-351), table path (hasTable, no hooks).
+ *   emb: n x D embeddings of the candidates in input order (f64; an f32 table row widened exactly).
+ *   score: Item.Score in input order.
+ * out_idx: indices into the INPUT list, in output order; returns the count (ctx.Size entries in windowed mode, even
+ * when that repeats index 0 — the reference does, :477-491 with :497-499).  *status = 1 when the reference logs an
+ * error and returns the items unchanged (out_idx = identity over the truncated list).
+ */
+ORC_API int orc_dpp_request(const double* emb, const double* score, int n, int D, const orc_dpp_params* p,
+                            int32_t* out_idx, int32_t* status) {
+  *status = 0;
+  if (n == 0) return 0;
+  int window = p->window_size > 0 ? p->window_size : 10;
+  const int T = p->top_n;
+  int32_t* order = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+  int m = n;
+  for (int i = 0; i < n; ++i) order[i] = i;
+  /* :280-300 presort + truncation */
+  if ((p->candidate_count > 0 || p->min_score_percent > 0) && n > T) {
+    orc_go_sort(score, n, 1, order);
+    if (p->candidate_count > 0) {
+      const int cnt = T > p->candidate_count ? T : p->candidate_count;
+      if (cnt < m) m = cnt;
+    }
+    if (p->min_score_percent > 0 && m > T) {
+      int idx = T;
+      const double mx = score[order[0]];
+      for (; idx < m; ++idx)
+        if (score[order[idx]] / mx < p->min_score_percent) break;
+      m = idx;
+    }
+  }
+  /* KernelMatrix :372-475 */
+  double* rel = (double*)malloc(sizeof(double) * (size_t)m);
+  for (int i = 0; i < m; ++i) rel[i] = score[order[i]];
+  int err = 0;
+  if (p->norm_mode == 1) { /* stat.PopMeanVariance + StdScore */
+    double mean = 0;
+    for (int i = 0; i < m; ++i) mean += rel[i];
+    mean /= (double)m;
+    double ss = 0, comp = 0; /* gonum PopMeanVariance -> MeanVariance two-pass with compensation, / n */
+    for (int i = 0; i < m; ++i) { const double d = rel[i] - mean; ss += d * d; comp += d; }
+    const double var = (ss - comp * comp / (double)m) / (double)m;
+    if (mean == 0 || var == 0) err = 1;
+    else { const double sd = sqrt(var); for (int i = 0; i < m; ++i) rel[i] = (rel[i] - mean) / sd; }
+  } else if (p->norm_mode == 2) {
+    const double mx = rel[0], mn = rel[m - 1], span = mx - mn;
+    if (span == 0) err = 1;
+    else for (int i = 0; i < m; ++i) rel[i] = ((rel[i] - mn) / span) * (1 - 1e-6) + 1e-6;
+  }
+  int ny = 0;
+  if (err) {
+    *status = 1;
+    for (int i = 0; i < m; ++i) out_idx[i] = order[i];
+    ny = m;
+  } else {
+    const int D1 = D + 1;
+    double* F = (double*)malloc(sizeof(double) * (size_t)m * D1);
+    double* r = (double*)malloc(sizeof(double) * (size_t)m);
+    const double inv_sqrt2 = 0.70710678118654752440; /* 1/math.Sqrt2 as a Go constant expression */
+    for (int i = 0; i < m; ++i) {
+      double* f = F + (size_t)i * D1;
+      memcpy(f, emb + (size_t)order[i] * D, sizeof(double) * (size_t)D);
+      if (p->normalize_emb) { /* :234-237 floats.Scale(1/normV, vector) */
+        const double s = 1 / g_norm2(f, D);
+        for (int d = 0; d < D; ++d) f[d] *= s;
+      }
+      f[D] = 1;
+      for (int d = 0; d < D1; ++d) f[d] *= inv_sqrt2; /* :428-429 */
+      r[i] = exp(p->alpha * rel[i]);                  /* :431 */
+    }
+    int32_t* res = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T > 0 ? T : 1));
+    if (T <= window) {
+      ny = dpp_once(F, r, m, D1, T, res, 0, res);
+    } else {
+      int32_t* sub = (int32_t*)malloc(sizeof(int32_t) * (size_t)window);
+      for (int w = 0; w < T / window; ++w) {
+        const int c = dpp_once(F, r, m, D1, window, res, ny, sub);
+        memcpy(res + ny, sub, sizeof(int32_t) * (size_t)c);
+        ny += c;
+      }
+      if (T % window > 0) {
+        const int c = dpp_once(F, r, m, D1, T % window, res, ny, sub);
+        memcpy(res + ny, sub, sizeof(int32_t) * (size_t)c);
+        ny += c;
+      }
+      free(sub);
+    }
+    for (int i = 0; i < ny; ++i) out_idx[i] = order[res[i]];
+    free(res); free(F); free(r);
+  }
+  free(rel); free(order);
+  return ny;
+}
+
+/* Dense kernel matrix exactly as KernelMatrix materialises it (for tests of the row-on-demand form). */
+ORC_API void orc_dpp_kernel_matrix(const double* emb, const double* rel, int n, int D, double alpha, int normalize,
+                                   double* L) {
+  const int D1 = D + 1;
+  double* F = (double*)malloc(sizeof(double) * (size_t)n * D1);
+  double* r = (double*)malloc(sizeof(double) * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    double* f = F + (size_t)i * D1;
+    memcpy(f, emb + (size_t)i * D, sizeof(double) * (size_t)D);
+    if (normalize) { const double s = 1 / g_norm2(f, D); for (int d = 0; d < D; ++d) f[d] *= s; }
+    f[D] = 1;
+    for (int d = 0; d < D1; ++d) f[d] *= 0.70710678118654752440;
+    r[i] = exp(alpha * rel[i]);
+  }
+  for (int j = 0; j < n; ++j) dpp_L_row(F, r, n, D1, j, L + (size_t)j * n);
+  free(F); free(r);
+}
+
+ORC_API int orc_num_threads(void) { return orc_hw_threads(); }

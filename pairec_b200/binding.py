@@ -1,0 +1,270 @@
+"""ctypes binding of libpairec_gpu.so (include/pairec_gpu.h) — what the cgo stub in INTEGRATION.md does from Go.
+
+Arrays cross the boundary as raw pointers: numpy arrays for PRG_MEM_HOST, integer device addresses
+(`tensor.data_ptr()`) for PRG_MEM_DEVICE.  torch is never imported here.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+MEM_HOST, MEM_DEVICE = 0, 1
+F32, F64 = 0, 1
+MODEL_FM, MODEL_MLP, MODEL_FM_MLP = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+EXPORTS = [
+    "prg_init", "prg_destroy", "prg_last_error", "prg_version", "prg_sync", "prg_stream", "prg_set_item_matrix",
+    "prg_set_item_fields", "prg_set_feature_table", "prg_set_fm_bias", "prg_set_mlp", "prg_set_diversity_matrix",
+    "prg_recall_topk", "prg_recall_local_keys", "prg_merge_keys", "prg_rank", "prg_sort_desc_host", "prg_sort_desc",
+    "prg_dpp", "prg_recommend", "prg_lookup", "prg_launch_count", "prg_recall_stats",
+]
+
+
+class PrgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpairec_gpu error {code}: {msg}")
+        self.code = code
+
+
+class DppParams(C.Structure):
+    """prg_dpp_params (DPPSortConfig / abtest knobs of sort/dpp_sort.go)."""
+    _fields_ = [("alpha", C.c_double), ("top_n", C.c_int32), ("window_size", C.c_int32), ("norm_mode", C.c_int32),
+                ("normalize_emb", C.c_int32), ("candidate_count", C.c_int32), ("min_score_percent", C.c_double)]
+
+    def __init__(self, alpha=1.0, top_n=50, window_size=10, norm_mode=0, normalize_emb=1, candidate_count=0,
+                 min_score_percent=0.0):
+        super().__init__(alpha, top_n, window_size, norm_mode, normalize_emb, candidate_count, min_score_percent)
+
+
+def lib_path():
+    return os.path.join(_HERE, "libpairec_gpu.so")
+
+
+def load_library():
+    """Loads the CUDA library; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise OSError(f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C pairec_b200/csrc). pairec_b200 has no CPU fallback.")
+        _lib = C.CDLL(p)
+        _lib.prg_last_error.restype = C.c_char_p
+        _lib.prg_version.restype = C.c_char_p
+        _lib.prg_stream.restype = C.c_void_p
+        _lib.prg_launch_count.restype = C.c_uint64
+        _lib.prg_destroy.restype = None
+        for name in EXPORTS:
+            getattr(_lib, name)  # raises AttributeError if a declared symbol is not exported
+    return _lib
+
+
+def _ptr(a):
+    """numpy array -> void*, int (device address) -> void*, None -> NULL."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(int(a))
+
+
+def _np(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class Engine:
+    """One prg_handle (one GPU)."""
+
+    def __init__(self, device=0, **cfg):
+        self._lib = load_library()
+        self._h = C.c_void_p(0)
+        import json
+        cfg = dict(cfg, device=device)
+        rc = self._lib.prg_init(json.dumps(cfg).encode(), C.byref(self._h))
+        if rc != 0:
+            raise PrgError(rc, self._lib.prg_last_error().decode())
+        self.dim = 0
+        self.n_fields = 0
+        self.fdim = 0
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PrgError(rc, self._lib.prg_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self._lib.prg_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._ck(self._lib.prg_sync(self._h))
+
+    @property
+    def stream(self):
+        return self._lib.prg_stream(self._h)
+
+    @property
+    def launches(self):
+        return int(self._lib.prg_launch_count(self._h))
+
+    def recall_stats(self):
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._ck(self._lib.prg_recall_stats(self._h, C.byref(a), C.byref(b)))
+        return {"fallback_queries": a.value, "max_candidates": b.value}
+
+    # ---------------------------------------------------------------- tables
+    def set_item_matrix(self, data, rows=None, dim=None, row_base=0, mem=MEM_HOST):
+        if mem == MEM_HOST:
+            data = _np(data, np.float32)
+            rows, dim = data.shape
+        self._ck(self._lib.prg_set_item_matrix(self._h, _ptr(data), C.c_uint64(rows), C.c_uint32(dim),
+                                               C.c_uint64(row_base), C.c_int(mem)))
+        self.dim = dim
+
+    def set_item_fields(self, ids, rows=None, n_fields=None, mem=MEM_HOST):
+        if mem == MEM_HOST:
+            ids = _np(ids, np.uint32)
+            rows, n_fields = ids.shape
+        self._ck(self._lib.prg_set_item_fields(self._h, _ptr(ids), C.c_uint64(rows), C.c_uint32(n_fields), C.c_int(mem)))
+        self.n_fields = n_fields
+
+    def set_feature_table(self, table, factors, linear=None, rows=None, fdim=None, mem=MEM_HOST):
+        if mem == MEM_HOST:
+            factors = _np(factors, np.float32)
+            rows, fdim = factors.shape
+            linear = None if linear is None else _np(linear, np.float32)
+        self._ck(self._lib.prg_set_feature_table(self._h, C.c_int(table), _ptr(factors), _ptr(linear), C.c_uint64(rows),
+                                                 C.c_uint32(fdim), C.c_int(mem)))
+        self.fdim = fdim
+
+    def set_fm_bias(self, w0):
+        self._ck(self._lib.prg_set_fm_bias(self._h, C.c_float(w0)))
+
+    def set_mlp(self, dims, W, bias):
+        L = len(W)
+        Wc = [_np(w, np.uint16) for w in W]
+        bc = [_np(b, np.float32) for b in bias]
+        wp = (C.c_void_p * L)(*[w.ctypes.data for w in Wc])
+        bp = (C.c_void_p * L)(*[b.ctypes.data for b in bc])
+        d = np.array(dims, dtype=np.uint32)
+        self._ck(self._lib.prg_set_mlp(self._h, C.c_int(L), _ptr(d), wp, bp))
+
+    def set_diversity_matrix(self, data, rows=None, dim=None, dtype=None, mem=MEM_HOST):
+        if mem == MEM_HOST:
+            data = np.ascontiguousarray(data)
+            assert data.dtype in (np.float32, np.float64)
+            dtype = F32 if data.dtype == np.float32 else F64
+            rows, dim = data.shape
+        self._ck(self._lib.prg_set_diversity_matrix(self._h, _ptr(data), C.c_uint64(rows), C.c_uint32(dim),
+                                                    C.c_int(dtype), C.c_int(mem)))
+
+    # ---------------------------------------------------------------- recall
+    def recall_topk(self, q, k):
+        """Host buffers in/out (the e2e path).  Returns rows u32 [B,k], scores f32 [B,k], n i32 [B]."""
+        q = _np(q, np.float32)
+        B = q.shape[0]
+        rows = np.empty((B, k), dtype=np.uint32)
+        scores = np.empty((B, k), dtype=np.float32)
+        n = np.empty(B, dtype=np.int32)
+        self._ck(self._lib.prg_recall_topk(self._h, _ptr(q), C.c_int(B), C.c_int(k), _ptr(rows), _ptr(scores), _ptr(n),
+                                           C.c_int(MEM_HOST)))
+        return rows, scores, n
+
+    def recall_topk_dev(self, q_ptr, B, k, rows_ptr, scores_ptr, n_ptr):
+        self._ck(self._lib.prg_recall_topk(self._h, _ptr(q_ptr), C.c_int(B), C.c_int(k), _ptr(rows_ptr),
+                                           _ptr(scores_ptr), _ptr(n_ptr), C.c_int(MEM_DEVICE)))
+
+    def recall_local_keys_dev(self, q_ptr, B, k, keys_ptr):
+        self._ck(self._lib.prg_recall_local_keys(self._h, _ptr(q_ptr), C.c_int(B), C.c_int(k), _ptr(keys_ptr)))
+
+    def merge_keys(self, keys_ptr, G, B, k, rows=None, scores=None, n=None, mem=MEM_HOST):
+        if mem == MEM_HOST:
+            rows = np.empty((B, k), dtype=np.uint32)
+            scores = np.empty((B, k), dtype=np.float32)
+            n = np.empty(B, dtype=np.int32)
+        self._ck(self._lib.prg_merge_keys(self._h, _ptr(keys_ptr), C.c_int(G), C.c_int(B), C.c_int(k), _ptr(rows),
+                                          _ptr(scores), _ptr(n), C.c_int(mem)))
+        return rows, scores, n
+
+    # ---------------------------------------------------------------- rank
+    def rank(self, model, rows):
+        rows = _np(rows, np.uint32)
+        B, n = rows.shape
+        out = np.empty((B, n), dtype=np.float64)
+        self._ck(self._lib.prg_rank(self._h, C.c_int(model), _ptr(rows), C.c_int(B), C.c_int(n), _ptr(out),
+                                    C.c_int(MEM_HOST)))
+        return out
+
+    def rank_dev(self, model, rows_ptr, B, n, out_ptr):
+        self._ck(self._lib.prg_rank(self._h, C.c_int(model), _ptr(rows_ptr), C.c_int(B), C.c_int(n), _ptr(out_ptr),
+                                    C.c_int(MEM_DEVICE)))
+
+    # ---------------------------------------------------------------- sort
+    def sort_desc(self, score):
+        score = _np(score, np.float64)
+        B, n = score.shape
+        perm = np.empty((B, n), dtype=np.int32)
+        self._ck(self._lib.prg_sort_desc(self._h, _ptr(score), C.c_int(B), C.c_int(n), _ptr(perm), C.c_int(MEM_HOST)))
+        return perm
+
+    # ---------------------------------------------------------------- DPP
+    def dpp(self, rows, score, params):
+        rows = _np(rows, np.uint32)
+        score = _np(score, np.float64)
+        B, n = rows.shape
+        T = params.top_n
+        idx = np.full((B, T), -1, dtype=np.int32)
+        cnt = np.zeros(B, dtype=np.int32)
+        st = np.zeros(B, dtype=np.int32)
+        self._ck(self._lib.prg_dpp(self._h, _ptr(rows), _ptr(score), C.c_int(B), C.c_int(n), C.byref(params), _ptr(idx),
+                                   _ptr(cnt), _ptr(st), C.c_int(MEM_HOST)))
+        return idx, cnt, st
+
+    # ---------------------------------------------------------------- fused
+    def recommend(self, q, recall_k, model, params):
+        q = _np(q, np.float32)
+        B = q.shape[0]
+        T = params.top_n
+        rows = np.empty((B, T), dtype=np.uint32)
+        scores = np.empty((B, T), dtype=np.float64)
+        n = np.empty(B, dtype=np.int32)
+        self._ck(self._lib.prg_recommend(self._h, _ptr(q), C.c_int(B), C.c_int(recall_k), C.c_int(model),
+                                         C.byref(params), _ptr(rows), _ptr(scores), _ptr(n), C.c_int(MEM_HOST)))
+        return rows, scores, n
+
+    def recommend_dev(self, q_ptr, B, recall_k, model, params, rows_ptr, scores_ptr, n_ptr):
+        self._ck(self._lib.prg_recommend(self._h, _ptr(q_ptr), C.c_int(B), C.c_int(recall_k), C.c_int(model),
+                                         C.byref(params), _ptr(rows_ptr), _ptr(scores_ptr), _ptr(n_ptr),
+                                         C.c_int(MEM_DEVICE)))
+
+
+def sort_desc_host(score):
+    """prg_sort_desc_host: Go pdqsort tie order, host only."""
+    lib = load_library()
+    score = _np(score, np.float64)
+    perm = np.empty(score.shape[0], dtype=np.int32)
+    rc = lib.prg_sort_desc_host(_ptr(score), C.c_int(score.shape[0]), _ptr(perm))
+    if rc != 0:
+        raise PrgError(rc, lib.prg_last_error().decode())
+    return perm
+
+
+def lookup(value, present):
+    lib = load_library()
+    value = _np(value, np.float64)
+    present = _np(present, np.uint8)
+    out = np.empty_like(value)
+    rc = lib.prg_lookup(_ptr(value), _ptr(present), C.c_int(value.shape[0]), _ptr(out))
+    if rc != 0:
+        raise PrgError(rc, lib.prg_last_error().decode())
+    return out

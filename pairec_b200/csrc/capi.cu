@@ -1,0 +1,271 @@
+// capi.cu — the extern "C" surface declared in include/pairec_gpu.h: handle lifecycle, table residency, and the
+// host-buffer / device-buffer wrappers around the kernels.  No CPU compute path exists here: without a CUDA device
+// prg_init fails with PRG_ENODEVICE.
+#include "handle.h"
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <new>
+
+namespace prg {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+int DevBuf::ensure(size_t need) {
+  if (need <= bytes && p) return PRG_OK;
+  if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+  if (need == 0) need = 16;
+  cudaError_t e = cudaMalloc(&p, need);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    return fail(PRG_ENOMEM, std::string("cudaMalloc(") + std::to_string(need) + "): " + cudaGetErrorString(e));
+  }
+  bytes = need;
+  return PRG_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// minimal "key": integer lookup in a flat JSON object (prg_init's config is a handful of integers)
+static bool json_int(const char* js, const char* key, long* out) {
+  if (!js) return false;
+  std::string pat = std::string("\"") + key + "\"";
+  const char* p = strstr(js, pat.c_str());
+  if (!p) return false;
+  p += pat.size();
+  while (*p == ' ' || *p == '\t' || *p == '\n' || *p == ':') ++p;
+  char* end = nullptr;
+  long v = strtol(p, &end, 10);
+  if (end == p) return false;
+  *out = v;
+  return true;
+}
+
+struct Guard {
+  prg_handle* h;
+  std::unique_lock<std::mutex> lk;
+  int prev = -1;
+  explicit Guard(prg_handle* hh) : h(hh), lk(hh->mu) {
+    cudaGetDevice(&prev);
+    if (prev != h->device) cudaSetDevice(h->device);
+  }
+  ~Guard() {
+    if (prev >= 0 && prev != h->device) cudaSetDevice(prev);
+  }
+};
+
+// copy-or-adopt helper for tables
+static int take_table(const void* src, size_t bytes, int mem, const void** dst, bool* owned) {
+  if (*owned && *dst) cudaFree(const_cast<void*>(*dst));
+  *dst = nullptr;
+  *owned = false;
+  if (mem == PRG_MEM_DEVICE) {
+    *dst = src;
+    return PRG_OK;
+  }
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, bytes ? bytes : 16);
+  if (e != cudaSuccess) return fail(PRG_ENOMEM, std::string("cudaMalloc table: ") + cudaGetErrorString(e));
+  e = cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(PRG_ECUDA, std::string("cudaMemcpy table: ") + cudaGetErrorString(e));
+  }
+  *dst = d;
+  *owned = true;
+  return PRG_OK;
+}
+
+}  // namespace prg
+
+using namespace prg;
+
+#define CHECK_H(h) \
+  if (!(h)) return prg::fail(PRG_EINVAL, "null handle")
+
+extern "C" {
+
+const char* prg_last_error(void) { return prg::g_err.c_str(); }
+const char* prg_version(void) { return "pairec_b200 0.1 (sm_100a)"; }
+
+int prg_init(const char* json_cfg, prg_handle** out) {
+  if (!out) return fail(PRG_EINVAL, "out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PRG_ENODEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) +
+                                   "); libpairec_gpu has no CPU fallback");
+  long v;
+  int dev = 0;
+  if (json_int(json_cfg, "device", &v)) dev = (int)v;
+  if (dev < 0 || dev >= ndev) return fail(PRG_EINVAL, "device index out of range");
+  PRG_CUDA(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  PRG_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(PRG_EUNSUPPORTED, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                      ", this library is built for sm_100a only");
+  prg_handle* h = new (std::nothrow) prg_handle();
+  if (!h) return fail(PRG_ENOMEM, "handle allocation failed");
+  h->device = dev;
+  h->sm_count = prop.multiProcessorCount;
+  if (json_int(json_cfg, "max_batch", &v) && v > 0) h->max_batch = (int)v;
+  if (json_int(json_cfg, "max_k", &v) && v > 0) h->max_k = (int)v;
+  if (json_int(json_cfg, "sm_limit", &v) && v > 0 && v < h->sm_count) h->sm_count = (int)v;
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(PRG_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  }
+  *out = h;
+  return PRG_OK;
+}
+
+void prg_destroy(prg_handle* h) {
+  if (!h) return;
+  {
+    Guard g(h);
+    cudaStreamSynchronize(h->stream);
+    if (h->E_owned && h->E) cudaFree(const_cast<float*>(h->E));
+    if (h->fields_owned && h->fields) cudaFree(const_cast<uint32_t*>(h->fields));
+    if (h->D_owned && h->D) cudaFree(const_cast<void*>(h->D));
+    for (int t = 0; t < kMaxFields; ++t) {
+      if (h->tables[t].owned) {
+        if (h->tables[t].factors) cudaFree(const_cast<float*>(h->tables[t].factors));
+        if (h->tables[t].linear) cudaFree(const_cast<float*>(h->tables[t].linear));
+      }
+    }
+    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
+                      &h->out_row, &h->out_score, &h->out_n, &h->flags, &h->table_ptrs, &h->act[0], &h->act[1],
+                      &h->fm_logit, &h->rank_rows, &h->rank_out, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
+                      &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->sort_in, &h->sort_perm, &h->rec_rows,
+                      &h->rec_scores, &h->rec_perm, &h->rec_sorted_rows, &h->rec_sorted_scores};
+    for (DevBuf* b : bufs) b->release();
+    for (int l = 0; l < kMaxLayers; ++l) { h->mlp_W[l].release(); h->mlp_b[l].release(); }
+    cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+int prg_sync(prg_handle* h) {
+  CHECK_H(h);
+  Guard g(h);
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+void* prg_stream(prg_handle* h) { return h ? (void*)h->stream : nullptr; }
+uint64_t prg_launch_count(prg_handle* h) { return h ? h->launches : 0; }
+
+int prg_recall_stats(prg_handle* h, int32_t* n_fallback, int32_t* max_candidates) {
+  CHECK_H(h);
+  if (n_fallback) *n_fallback = h->last_fallback;
+  if (max_candidates) *max_candidates = h->last_max_cand;
+  return PRG_OK;
+}
+
+// ------------------------------------------------------------------ tables
+int prg_set_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_t dim, uint64_t row_base, int mem) {
+  CHECK_H(h);
+  if (!data || rows == 0) return fail(PRG_EINVAL, "empty item matrix");
+  if (dim != 64 && dim != 128) return fail(PRG_EUNSUPPORTED, "item matrix dim must be 64 or 128");
+  if ((reinterpret_cast<uintptr_t>(data) & 15) && mem == PRG_MEM_DEVICE)
+    return fail(PRG_EINVAL, "device item matrix must be 16-byte aligned");
+  Guard g(h);
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  const void* d = h->E;
+  PRG_TRY(take_table(data, (size_t)rows * dim * 4, mem, &d, &h->E_owned));
+  h->E = (const float*)d;
+  h->E_rows = rows;
+  h->E_dim = dim;
+  h->E_row_base = row_base;
+  return recall_build_map(h);
+}
+
+// ------------------------------------------------------------------ recall
+int prg_recall_topk(prg_handle* h, const float* q, int B, int k, uint32_t* out_row, float* out_score, int32_t* out_n,
+                    int mem) {
+  CHECK_H(h);
+  if (!q || !out_row || !out_score || !out_n) return fail(PRG_EINVAL, "null buffer");
+  if (B <= 0 || k <= 0) return fail(PRG_EINVAL, "B and k must be positive");
+  Guard g(h);
+  if (!h->E) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
+  const size_t nk = (size_t)B * k;
+  PRG_TRY(h->topk_keys.ensure(nk * 8));
+  if (mem == PRG_MEM_DEVICE) {
+    PRG_TRY(recall_topk_device(h, q, B, k, (uint64_t*)h->topk_keys.p));
+    return keys_to_outputs(h, (const uint64_t*)h->topk_keys.p, B, k, out_row, out_score, out_n);
+  }
+  PRG_TRY(h->q_dev.ensure((size_t)B * h->E_dim * 4));
+  PRG_TRY(h->out_row.ensure(nk * 4));
+  PRG_TRY(h->out_score.ensure(nk * 4));
+  PRG_TRY(h->out_n.ensure((size_t)B * 4));
+  PRG_CUDA(cudaMemcpyAsync(h->q_dev.p, q, (size_t)B * h->E_dim * 4, cudaMemcpyHostToDevice, h->stream));
+  PRG_TRY(recall_topk_device(h, (const float*)h->q_dev.p, B, k, (uint64_t*)h->topk_keys.p));
+  PRG_TRY(keys_to_outputs(h, (const uint64_t*)h->topk_keys.p, B, k, (uint32_t*)h->out_row.p, (float*)h->out_score.p,
+                          (int32_t*)h->out_n.p));
+  PRG_CUDA(cudaMemcpyAsync(out_row, h->out_row.p, nk * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_score, h->out_score.p, nk * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_n, h->out_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+
+int prg_recall_local_keys(prg_handle* h, const float* q_dev, int B, int k, uint64_t* out_keys_dev) {
+  CHECK_H(h);
+  if (!q_dev || !out_keys_dev) return fail(PRG_EINVAL, "null buffer");
+  Guard g(h);
+  return recall_topk_device(h, q_dev, B, k, out_keys_dev);
+}
+
+int prg_merge_keys(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint32_t* out_row, float* out_score,
+                   int32_t* out_n, int mem) {
+  CHECK_H(h);
+  if (!keys_dev || !out_row || !out_score || !out_n) return fail(PRG_EINVAL, "null buffer");
+  Guard g(h);
+  const size_t nk = (size_t)B * k;
+  PRG_TRY(h->topk_keys.ensure(nk * 8));
+  PRG_TRY(merge_keys_device(h, keys_dev, G, B, k, (uint64_t*)h->topk_keys.p));
+  if (mem == PRG_MEM_DEVICE) return keys_to_outputs(h, (const uint64_t*)h->topk_keys.p, B, k, out_row, out_score, out_n);
+  PRG_TRY(h->out_row.ensure(nk * 4));
+  PRG_TRY(h->out_score.ensure(nk * 4));
+  PRG_TRY(h->out_n.ensure((size_t)B * 4));
+  PRG_TRY(keys_to_outputs(h, (const uint64_t*)h->topk_keys.p, B, k, (uint32_t*)h->out_row.p, (float*)h->out_score.p,
+                          (int32_t*)h->out_n.p));
+  PRG_CUDA(cudaMemcpyAsync(out_row, h->out_row.p, nk * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_score, h->out_score.p, nk * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_n, h->out_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+
+// ------------------------------------------------------------------ host-only entries
+int prg_lookup(const double* value, const uint8_t* present, int n, double* out) {
+  if (n < 0 || (n > 0 && (!value || !present || !out))) return fail(PRG_EINVAL, "null buffer");
+  for (int i = 0; i < n; ++i) out[i] = present[i] ? value[i] : 0.5;  // algorithm/lookup.go:44-49
+  return PRG_OK;
+}
+
+}  // extern "C"

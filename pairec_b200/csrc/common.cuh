@@ -1,0 +1,119 @@
+// common.cuh — shared device/host helpers for libpairec_gpu.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <mutex>
+#include <vector>
+#include "../../include/pairec_gpu.h"
+
+namespace prg {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define PRG_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      return ::prg::fail(PRG_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    }                                                                                             \
+  } while (0)
+
+#define PRG_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != PRG_OK) return _s; \
+  } while (0)
+
+// ---------------------------------------------------------------- order keys
+// Total order used everywhere a "top-k by score" is taken (recall, shard merge):
+//   key = (ord(score) << 32) | (0xFFFFFFFF - row),  larger key == better, key 0 == empty slot.
+// ord() is the usual monotone map of IEEE-754 binary32 onto u32, with every NaN sent to 1 (below -inf, above the
+// empty-slot sentinel).  -0.0 orders just below +0.0.
+__host__ __device__ __forceinline__ uint32_t f32_ord(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return 1u;  // NaN
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord_f32(uint32_t o) {
+  uint32_t u;
+  if (o == 1u) u = 0x7FC00000u;  // canonical NaN
+  else u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+  return ((uint64_t)f32_ord(score) << 32) | (uint64_t)(0xFFFFFFFFu - row);
+}
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t key) { return 0xFFFFFFFFu - (uint32_t)key; }
+__host__ __device__ __forceinline__ float key_score(uint64_t key) { return ord_f32((uint32_t)(key >> 32)); }
+
+// ---------------------------------------------------------------- small device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA: 2-D tiled load global -> shared, completion on an mbarrier (SASS: UTMALDG).
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// Packed fp32x2 FMA (sm_100+): two independent IEEE-RN fused multiply-adds per instruction (SASS: FFMA2).
+__device__ __forceinline__ void ffma2(float2& acc, const float2& a, const float2& b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(reinterpret_cast<unsigned long long&>(acc))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+}
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // L2 cache-hint policy words (createpolicy equivalents)
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------- driver entry (no libcuda link dependency)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+
+}  // namespace prg

@@ -1,0 +1,102 @@
+// handle.h — the per-GPU state behind a prg_handle.
+#pragma once
+#include "common.cuh"
+
+namespace prg {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need);  // grows (never shrinks); contents are NOT preserved
+  void release();
+};
+
+constexpr int kMaxFields = 64;
+constexpr int kMaxLayers = 8;
+
+struct Table {
+  const float* factors = nullptr;
+  const float* linear = nullptr;
+  uint64_t rows = 0;
+  bool owned = false;
+};
+
+}  // namespace prg
+
+struct prg_handle {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  uint64_t launches = 0;
+
+  int max_batch = 64;
+  int max_k = 1000;
+
+  // ---- recall: item matrix + scratch
+  const float* E = nullptr;
+  bool E_owned = false;
+  uint64_t E_rows = 0;
+  uint32_t E_dim = 0;
+  uint64_t E_row_base = 0;
+  CUtensorMap E_map;
+  bool E_map_ok = false;
+
+  prg::DevBuf q_dev;        // B x dim f32 (host-call staging)
+  prg::DevBuf sample_keys;  // QB x sample_slots u64
+  prg::DevBuf cand_keys;    // B x cand_cap u64
+  prg::DevBuf cand_cnt;     // B u32
+  prg::DevBuf tau;          // B u64
+  prg::DevBuf dense_keys;   // fallback / small-N: nq x slots u64
+  prg::DevBuf topk_keys;    // B x k u64
+  prg::DevBuf out_row, out_score, out_n;  // device staging for host calls
+  prg::DevBuf flags;        // B i32 per-query status from select
+  int32_t last_fallback = 0;
+  int32_t last_max_cand = 0;
+
+  // ---- rank: fields, tables, models
+  const uint32_t* fields = nullptr;
+  bool fields_owned = false;
+  uint64_t fields_rows = 0;
+  uint32_t n_fields = 0;
+  prg::Table tables[prg::kMaxFields];
+  uint32_t fdim = 0;
+  float fm_w0 = 0.f;
+  prg::DevBuf table_ptrs;  // device array of {factors*, linear*, rows}
+  bool table_ptrs_dirty = true;
+
+  int mlp_layers = 0;
+  uint32_t mlp_dims[prg::kMaxLayers + 1] = {0};
+  prg::DevBuf mlp_W[prg::kMaxLayers];  // bf16, layout chosen by mlp.cu
+  prg::DevBuf mlp_b[prg::kMaxLayers];
+  CUtensorMap mlp_Wmap[prg::kMaxLayers];
+  prg::DevBuf act[2];   // activations ping-pong (bf16)
+  prg::DevBuf fm_logit; // B*n f32
+  prg::DevBuf rank_rows, rank_out;
+
+  // ---- DPP
+  const void* D = nullptr;
+  bool D_owned = false;
+  uint64_t D_rows = 0;
+  uint32_t D_dim = 0;
+  int D_dtype = PRG_F32;
+  prg::DevBuf dpp_scratch, dpp_rows, dpp_score, dpp_idx, dpp_n, dpp_status;
+
+  // ---- sort
+  prg::DevBuf sort_in, sort_perm;
+
+  // ---- fused path
+  prg::DevBuf rec_rows, rec_scores, rec_perm, rec_sorted_rows, rec_sorted_scores;
+};
+
+namespace prg {
+// launch bookkeeping
+inline void count_launch(prg_handle* h, int n = 1) { h->launches += (uint64_t)n; }
+
+// recall.cu
+int recall_build_map(prg_handle* h);
+int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t* keys_out /*B x k*/);
+int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint32_t* out_row, float* out_score,
+                    int32_t* out_n);
+int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint64_t* keys_out);
+}  // namespace prg

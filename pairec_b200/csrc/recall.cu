@@ -1,0 +1,573 @@
+// recall.cu — exact inner-product top-k over the HBM-resident item matrix.
+//
+// Replaces the remote faiss VectorRetrieval.Search behind algorithm/faiss/vector_client.go:32-42 that
+// service/recall/vector_recall.go:88 reaches through algorithm.Run.  Arithmetic contract (defined here, mirrored by
+// oracle/oracle.c orc_recall_topk): score(row,q) = fmaf chain over dims 0..d-1 from +0, one accumulator; total
+// order = 64-bit key (score desc, row asc).
+//
+// Pipeline per block of <=64 queries:
+//   1. scan<DENSE> over a strided sample of tiles      -> sample keys
+//   2. select (r-th largest of the sample)             -> per-query threshold key tau
+//   3. scan<THRESH> over the whole matrix              -> candidates with key >= tau (expected ~4k per query)
+//   4. select (exact top-k of the candidates, sorted)  -> keys / rows / scores
+// A query whose candidate list under- or overflows (adversarial row order) is redone through the dense path
+// (all keys materialised, same select), so the result is exact for every input.
+//
+// The scan kernel is persistent (one CTA per SM): one producer warp streams 256-row tiles through a 3-stage
+// TMA/mbarrier ring (SWIZZLE_128B so the per-row LDS.128 reads are bank-conflict free), eight consumer warps hold a
+// 4-row x 16-query register tile per thread and issue packed FFMA2; the threshold test is fused into the tile
+// epilogue, so the only HBM traffic is the matrix itself (algorithmic bytes = rows*dim*4 per <=64-query block).
+#include "handle.h"
+
+namespace prg {
+
+constexpr int TM = 4, TQ = 16, WR = 2, WQ = 4;
+constexpr int kTileRows = WR * 32 * TM;              // 256
+constexpr int kQB = WQ * TQ;                         // 64 queries per pass
+constexpr int kConsumerWarps = WR * WQ;              // 8
+constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
+constexpr int kStageFloats = kTileRows * 64;         // one stage = 256 rows x 64 dims
+constexpr int kStageBytes = kStageFloats * 4;        // 64 KiB
+constexpr int kStages = 3;
+constexpr int kSubTileFloats = kTileRows * 32;       // one TMA box: 256 rows x 32 floats (128 B)
+
+enum { SCAN_THRESH = 0, SCAN_DENSE = 1 };
+
+struct ScanParams {
+  const float* Q;          // [nq][dim]
+  int nq;
+  uint64_t n_rows;         // local rows in the matrix
+  uint64_t row_base;       // global id of local row 0
+  uint32_t n_tiles;        // tiles covered by this launch
+  uint32_t tile_stride;    // launch tile t reads matrix tile t*tile_stride
+  const uint64_t* tau;     // THRESH: [nq]
+  uint64_t* cand;          // THRESH: [nq][cand_cap]
+  uint32_t cand_cap;
+  uint32_t* cand_cnt;      // THRESH: [nq]
+  uint64_t* dense;         // DENSE: [nq][dense_stride], slot = t*256 + r
+  uint64_t dense_stride;
+};
+
+template <int DIM>
+constexpr size_t scan_smem_bytes() {
+  return (size_t)kStages * kStageBytes + (size_t)DIM * kQB * 4 + kQB * 4 + kQB * 8 +
+         2 * kStages * 8;
+}
+
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(kScanThreads, 1)
+recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B boxes need 1024-B aligned destinations
+  float* stage_base = reinterpret_cast<float*>(smem);
+  float* Qs = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);  // [DIM][64]
+  float* tauf = Qs + DIM * kQB;                                                // [64]
+  uint64_t* tau64 = reinterpret_cast<uint64_t*>(tauf + kQB);                   // [64]
+  uint64_t* full = tau64 + kQB;
+  uint64_t* empty = full + kStages;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int KH = DIM / 64;
+
+  for (int i = tid; i < DIM * kQB; i += kScanThreads) {
+    const int q = i / DIM, dd = i - q * DIM;
+    Qs[dd * kQB + q] = (q < p.nq) ? p.Q[(size_t)q * DIM + dd] : 0.f;
+  }
+  if (tid < kQB) {
+    uint64_t t = 0;
+    float tf = __int_as_float(0x7F800000);  // +inf: padded queries never pass the pre-test
+    if (tid < p.nq) {
+      if (MODE == SCAN_THRESH) t = p.tau[tid];
+      tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
+    }
+    tau64[tid] = t;
+    tauf[tid] = tf;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const uint32_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == kConsumerWarps) {
+    // ------------------------------------------------------------ producer: one lane drives TMA
+    if (lane == 0) {
+      tma_prefetch_desc(&emap);
+      uint32_t it = 0;
+      for (uint32_t i = 0; i < my_tiles; ++i) {
+        const uint32_t t = blockIdx.x + i * gridDim.x;
+        const int row0 = (int)(t * p.tile_stride * (uint32_t)kTileRows);
+        for (int h = 0; h < KH; ++h, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          float* dst = stage_base + (size_t)s * kStageFloats;
+          tma_load_2d(dst, &emap, h * 64, row0, &full[s], kEvictFirst);
+          tma_load_2d(dst + kSubTileFloats, &emap, h * 64 + 32, row0, &full[s], kEvictFirst);
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- consumers
+  const int wr = warp / WQ, wq = warp - wr * WQ;
+  const int rloc0 = wr * (32 * TM) + lane;  // this thread's rows: rloc0 + 32*m
+  const int qbase = wq * TQ;
+  const int sw = lane & 7;                  // == row & 7 for every row of this thread (swizzle phase)
+  uint32_t it = 0;
+
+  for (uint32_t i = 0; i < my_tiles; ++i) {
+    float2 acc[TM][TQ / 2];
+#pragma unroll
+    for (int m = 0; m < TM; ++m)
+#pragma unroll
+      for (int c = 0; c < TQ / 2; ++c) acc[m][c] = make_float2(0.f, 0.f);
+
+    for (int h = 0; h < KH; ++h, ++it) {
+      const uint32_t s = it % kStages, ph = (it / kStages) & 1u;
+      mbar_wait(&full[s], ph);
+      const float* st = stage_base + (size_t)s * kStageFloats;
+      const float* qs = Qs + (size_t)h * 64 * kQB + qbase;
+#pragma unroll 2
+      for (int c = 0; c < 16; ++c) {
+        const int sub = c >> 3, ch = c & 7;
+        float4 xv[TM];
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+          const int r = rloc0 + 32 * m;
+          xv[m] = *reinterpret_cast<const float4*>(st + sub * kSubTileFloats + r * 32 + ((ch ^ sw) << 2));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4* qrow = reinterpret_cast<const float4*>(qs + (c * 4 + j) * kQB);
+          float2 qv[TQ / 2];
+#pragma unroll
+          for (int v = 0; v < TQ / 4; ++v) {
+            const float4 t4 = qrow[v];
+            qv[2 * v] = make_float2(t4.x, t4.y);
+            qv[2 * v + 1] = make_float2(t4.z, t4.w);
+          }
+#pragma unroll
+          for (int m = 0; m < TM; ++m) {
+            const float x = (j == 0) ? xv[m].x : (j == 1) ? xv[m].y : (j == 2) ? xv[m].z : xv[m].w;
+            const float2 xd = make_float2(x, x);
+#pragma unroll
+            for (int c2 = 0; c2 < TQ / 2; ++c2) ffma2(acc[m][c2], xd, qv[c2]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+    // ------------------------------------------------------------ tile epilogue
+    const uint32_t t = blockIdx.x + i * gridDim.x;
+    const uint64_t tile_row0 = (uint64_t)t * p.tile_stride * kTileRows;
+    if (MODE == SCAN_THRESH) {
+      bool any = false;
+#pragma unroll
+      for (int c2 = 0; c2 < TQ / 2; ++c2) {
+        const float t0 = tauf[qbase + 2 * c2], t1 = tauf[qbase + 2 * c2 + 1];
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+          any |= !(acc[m][c2].x < t0);
+          any |= !(acc[m][c2].y < t1);
+        }
+      }
+      if (any) {
+#pragma unroll
+        for (int m = 0; m < TM; ++m) {
+          const uint64_t lrow = tile_row0 + (uint64_t)(rloc0 + 32 * m);
+          if (lrow < p.n_rows) {
+            const uint32_t grow = (uint32_t)(p.row_base + lrow);
+#pragma unroll
+            for (int c2 = 0; c2 < TQ / 2; ++c2) {
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int q = qbase + 2 * c2 + e;
+                const float sc = e ? acc[m][c2].y : acc[m][c2].x;
+                if (!(sc < tauf[q])) {
+                  const uint64_t key = make_key(sc, grow);
+                  if (q < p.nq && key >= tau64[q]) {
+                    const uint32_t pos = atomicAdd(&p.cand_cnt[q], 1u);
+                    if (pos < p.cand_cap) p.cand[(size_t)q * p.cand_cap + pos] = key;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < TM; ++m) {
+        const uint64_t lrow = tile_row0 + (uint64_t)(rloc0 + 32 * m);
+        const bool valid = lrow < p.n_rows;
+        const uint32_t grow = (uint32_t)(p.row_base + lrow);
+        const uint64_t slot = (uint64_t)t * kTileRows + (uint64_t)(rloc0 + 32 * m);
+#pragma unroll
+        for (int c2 = 0; c2 < TQ / 2; ++c2) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int q = qbase + 2 * c2 + e;
+            if (q < p.nq) {
+              const float sc = e ? acc[m][c2].y : acc[m][c2].x;
+              p.dense[(size_t)q * p.dense_stride + slot] = valid ? make_key(sc, grow) : 0ull;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ select: exact k-th / sorted top-k of a key list
+struct SelectParams {
+  const uint64_t* keys;    // query q reads keys + q*stride
+  uint64_t stride;
+  const uint32_t* counts;  // per-query list length (nullable -> fixed_m); clamped to cap, overflow flagged
+  uint32_t fixed_m;
+  uint32_t cap;
+  int k;                   // rank wanted
+  int k_out;               // row stride of the outputs (== caller's k)
+  uint32_t expect;         // MODE_TOPK: number of results that must exist (min(k, total rows)), else flag 2
+  uint64_t* out_keys;      // MODE_TOPK: [q][k_out] sorted descending, 0-padded (nullable)
+  uint32_t* out_row;       // nullable
+  float* out_score;        // nullable
+  int32_t* out_n;          // nullable
+  uint64_t* tau;           // MODE_KTH: [q] the k-th largest key (0 if fewer than k valid keys)
+  int32_t* flags;          // nullable; 0 ok, 1 overflow, 2 underflow
+  uint32_t* max_count;     // nullable: atomicMax of the list lengths seen
+};
+enum { SEL_TOPK = 0, SEL_KTH = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1) select_kernel(const SelectParams p) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint64_t s_prefix;
+  __shared__ uint32_t s_want, s_fill, s_zero;
+  extern __shared__ uint64_t sk[];  // MODE_TOPK: K2 keys
+
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t* keys = p.keys + (size_t)q * p.stride;
+  uint32_t m = p.counts ? p.counts[q] : p.fixed_m;
+  const bool overflow = m > p.cap;
+  if (p.max_count && tid == 0) atomicMax(p.max_count, m);
+  if (overflow) m = p.cap;
+
+  if (tid == 0) { s_zero = 0; s_fill = 0; }
+  __syncthreads();
+  {
+    uint32_t z = 0;
+    for (uint32_t i = tid; i < m; i += 1024) z += (keys[i] == 0ull);
+    if (z) atomicAdd(&s_zero, z);
+  }
+  __syncthreads();
+  const uint32_t valid = m - s_zero;
+  const uint32_t k = (uint32_t)p.k;
+
+  uint64_t kth = 1;  // every valid key is >= 1
+  if (valid > k || (MODE == SEL_KTH && valid == k)) {
+    uint64_t prefix = 0, mask = 0;
+    uint32_t want = k;
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < m; i += 1024) {
+        const uint64_t key = keys[i];
+        if (key != 0ull && (key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (warp == 0) {
+        // lane l owns digits [8l, 8l+8); suffix sums from the top digit down
+        uint32_t c[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
+        uint32_t above = 0;  // keys in digits strictly above this lane's block
+        {
+          uint32_t run = tot;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_down_sync(0xffffffffu, run, off);
+            if (lane + off < 32) run += v;
+          }
+          above = run - tot;
+        }
+        if (above < want && above + tot >= want) {
+          uint32_t a = above;
+          int d = 7;
+          for (; d >= 0; --d) {
+            if (a + c[d] >= want) break;
+            a += c[d];
+          }
+          s_prefix = prefix | ((uint64_t)(lane * 8 + d) << shift);
+          s_want = want - a;
+        }
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      want = s_want;
+      mask |= (0xFFull << shift);
+      __syncthreads();
+    }
+    kth = prefix;
+  } else if (MODE == SEL_KTH) {
+    kth = 0;  // fewer than k valid keys: no threshold
+  }
+
+  if (MODE == SEL_KTH) {
+    if (tid == 0) p.tau[q] = kth;
+    return;
+  }
+
+  // compaction of keys >= kth (exactly min(k, valid) of them: keys are distinct) and bitonic sort, descending
+  uint32_t K2 = 32;
+  while (K2 < k) K2 <<= 1;
+  for (uint32_t i = tid; i < K2; i += 1024) sk[i] = 0ull;
+  __syncthreads();
+  for (uint32_t i = tid; i < m; i += 1024) {
+    const uint64_t key = keys[i];
+    if (key != 0ull && key >= kth) {
+      const uint32_t pos = atomicAdd(&s_fill, 1u);
+      if (pos < K2) sk[pos] = key;
+    }
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= K2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = tid; i < (K2 >> 1); i += 1024) {
+        const uint32_t pos = 2 * i - (i & (stride - 1));
+        const uint64_t a = sk[pos], b = sk[pos + stride];
+        const bool desc = (pos & size) == 0;
+        if ((a < b) == desc) { sk[pos] = b; sk[pos + stride] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t n_out = valid < k ? valid : k;
+  for (uint32_t i = tid; i < (uint32_t)p.k_out; i += 1024) {
+    const uint64_t key = (i < n_out) ? sk[i] : 0ull;
+    const size_t o = (size_t)q * p.k_out + i;
+    if (p.out_keys) p.out_keys[o] = key;
+    if (p.out_row) p.out_row[o] = key ? key_row(key) : 0xFFFFFFFFu;
+    if (p.out_score) p.out_score[o] = key ? key_score(key) : __int_as_float(0xFF800000);
+  }
+  if (tid == 0) {
+    if (p.out_n) p.out_n[q] = (int32_t)n_out;
+    if (p.flags) p.flags[q] = overflow ? 1 : (n_out < p.expect ? 2 : 0);
+  }
+}
+
+// keys -> rows / scores / counts (used by the shard-merge path where keys already are sorted)
+__global__ void keys_unpack_kernel(const uint64_t* keys, int total, int k, uint32_t* out_row, float* out_score,
+                                   int32_t* out_n, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    const uint64_t key = keys[i];
+    out_row[i] = key ? key_row(key) : 0xFFFFFFFFu;
+    out_score[i] = key ? key_score(key) : __int_as_float(0xFF800000);
+  }
+  if (i < B) {
+    int n = 0;
+    for (int j = 0; j < k; ++j) n += (keys[(size_t)i * k + j] != 0ull);
+    out_n[i] = n;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+int recall_build_map(prg_handle* h) {
+  h->E_map_ok = false;
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)h->E_dim, (cuuint64_t)h->E_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)h->E_dim * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)kTileRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&h->E_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(h->E), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  h->E_map_ok = true;
+  return PRG_OK;
+}
+
+template <int DIM, int MODE>
+static int launch_scan(prg_handle* h, const ScanParams& p) {
+  const size_t smem = scan_smem_bytes<DIM>();
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_kernel<DIM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.n_tiles == 0) return PRG_OK;
+  const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
+  recall_scan_kernel<DIM, MODE><<<grid, kScanThreads, smem, h->stream>>>(h->E_map, p);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+static int scan(prg_handle* h, int mode, const ScanParams& p) {
+  if (h->E_dim == 64) return mode == SCAN_THRESH ? launch_scan<64, SCAN_THRESH>(h, p) : launch_scan<64, SCAN_DENSE>(h, p);
+  if (h->E_dim == 128)
+    return mode == SCAN_THRESH ? launch_scan<128, SCAN_THRESH>(h, p) : launch_scan<128, SCAN_DENSE>(h, p);
+  return fail(PRG_EUNSUPPORTED, "item matrix dim must be 64 or 128");
+}
+
+static int launch_select(prg_handle* h, int mode, const SelectParams& p, int nq) {
+  if (mode == SEL_KTH) {
+    select_kernel<SEL_KTH><<<nq, 1024, 0, h->stream>>>(p);
+  } else {
+    uint32_t K2 = 32;
+    while (K2 < (uint32_t)p.k) K2 <<= 1;
+    select_kernel<SEL_TOPK><<<nq, 1024, K2 * 8, h->stream>>>(p);
+  }
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+// Dense path for query block [q0, q0+nq): all keys materialised, then the same select.
+static int recall_dense(prg_handle* h, const float* q_dev, int nq, int k, int k_out, uint64_t* keys_out) {
+  const uint32_t n_tiles = (uint32_t)((h->E_rows + kTileRows - 1) / kTileRows);
+  const uint64_t slots = (uint64_t)n_tiles * kTileRows;
+  PRG_TRY(h->dense_keys.ensure((size_t)nq * slots * 8));
+  ScanParams sp{};
+  sp.Q = q_dev; sp.nq = nq; sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
+  sp.n_tiles = n_tiles; sp.tile_stride = 1;
+  sp.dense = (uint64_t*)h->dense_keys.p; sp.dense_stride = slots;
+  PRG_TRY(scan(h, SCAN_DENSE, sp));
+  SelectParams se{};
+  se.keys = (const uint64_t*)h->dense_keys.p; se.stride = slots; se.counts = nullptr;
+  se.fixed_m = (uint32_t)slots; se.cap = (uint32_t)slots; se.k = k; se.k_out = k_out;
+  se.expect = 0; se.out_keys = keys_out;
+  PRG_TRY(launch_select(h, SEL_TOPK, se, nq));
+  return PRG_OK;
+}
+
+constexpr uint64_t kSampledMinRows = 1u << 18;  // below this the dense path is cheaper than sampling
+
+int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t* keys_out) {
+  if (!h->E || !h->E_map_ok) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
+  if (B <= 0 || k <= 0) return fail(PRG_EINVAL, "B and k must be positive");
+  if (k > 4096) return fail(PRG_EUNSUPPORTED, "k > 4096");
+  if (h->E_rows + h->E_row_base > 0xFFFFFFFFull) return fail(PRG_EUNSUPPORTED, "global row ids must fit u32");
+  if (h->E_rows >= (1ull << 31)) return fail(PRG_EUNSUPPORTED, "more than 2^31 rows per shard");
+  const uint32_t dim = h->E_dim;
+  h->last_fallback = 0;
+  h->last_max_cand = 0;
+
+  const uint32_t n_tiles = (uint32_t)((h->E_rows + kTileRows - 1) / kTileRows);
+  const bool sampled = h->E_rows >= kSampledMinRows && (uint64_t)k * 64 <= h->E_rows;
+
+  // sampling plan: ~1/128 of the tiles, strided across the whole matrix
+  uint32_t sample_tiles = 0, tile_stride = 1, r_rank = 0, cand_cap = 0;
+  if (sampled) {
+    sample_tiles = n_tiles / 128;
+    if (sample_tiles < 64) sample_tiles = 64;
+    if (sample_tiles > 2048) sample_tiles = 2048;
+    tile_stride = n_tiles / sample_tiles;
+    const double f = (double)sample_tiles * kTileRows / (double)h->E_rows;
+    const double target = 4.0 * (k < 1024 ? 1024 : k);
+    r_rank = (uint32_t)(target * f + 0.999);
+    if (r_rank < 24) r_rank = 24;
+    cand_cap = (uint32_t)(4.0 * (double)r_rank / f);
+    cand_cap = (cand_cap + 1023) & ~1023u;
+    PRG_TRY(h->sample_keys.ensure((size_t)kQB * sample_tiles * kTileRows * 8));
+    PRG_TRY(h->cand_keys.ensure((size_t)kQB * cand_cap * 8));
+    PRG_TRY(h->cand_cnt.ensure((size_t)kQB * 4 + 4));
+    PRG_TRY(h->tau.ensure((size_t)kQB * 8));
+    PRG_TRY(h->flags.ensure((size_t)kQB * 4));
+  }
+
+  for (int q0 = 0; q0 < B; q0 += kQB) {
+    const int nq = (B - q0 < kQB) ? (B - q0) : kQB;
+    const float* qb = q_dev + (size_t)q0 * dim;
+    uint64_t* kout = keys_out + (size_t)q0 * k;
+    if (!sampled) {
+      PRG_TRY(recall_dense(h, qb, nq, k, k, kout));
+      continue;
+    }
+    // 1. sample
+    ScanParams sp{};
+    sp.Q = qb; sp.nq = nq; sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
+    sp.n_tiles = sample_tiles; sp.tile_stride = tile_stride;
+    sp.dense = (uint64_t*)h->sample_keys.p; sp.dense_stride = (uint64_t)sample_tiles * kTileRows;
+    PRG_TRY(scan(h, SCAN_DENSE, sp));
+    // 2. threshold = r-th largest sample key
+    SelectParams st{};
+    st.keys = (const uint64_t*)h->sample_keys.p; st.stride = sp.dense_stride; st.fixed_m = (uint32_t)sp.dense_stride;
+    st.cap = st.fixed_m; st.k = (int)r_rank; st.tau = (uint64_t*)h->tau.p;
+    PRG_TRY(launch_select(h, SEL_KTH, st, nq));
+    // 3. full scan with fused threshold test
+    PRG_CUDA(cudaMemsetAsync(h->cand_cnt.p, 0, (size_t)kQB * 4 + 4, h->stream));
+    ScanParams sc{};
+    sc.Q = qb; sc.nq = nq; sc.n_rows = h->E_rows; sc.row_base = h->E_row_base;
+    sc.n_tiles = n_tiles; sc.tile_stride = 1;
+    sc.tau = (const uint64_t*)h->tau.p; sc.cand = (uint64_t*)h->cand_keys.p; sc.cand_cap = cand_cap;
+    sc.cand_cnt = (uint32_t*)h->cand_cnt.p;
+    PRG_TRY(scan(h, SCAN_THRESH, sc));
+    // 4. exact top-k of the candidates
+    SelectParams se{};
+    se.keys = (const uint64_t*)h->cand_keys.p; se.stride = cand_cap; se.counts = (const uint32_t*)h->cand_cnt.p;
+    se.cap = cand_cap; se.k = k; se.k_out = k;
+    se.expect = (uint32_t)((uint64_t)k < h->E_rows ? (uint64_t)k : h->E_rows);
+    se.out_keys = kout; se.flags = (int32_t*)h->flags.p;
+    se.max_count = (uint32_t*)h->cand_cnt.p + kQB;
+    PRG_TRY(launch_select(h, SEL_TOPK, se, nq));
+    // 5. per-query status; redo the rare failures through the dense path
+    int32_t hf[kQB + 1];
+    PRG_CUDA(cudaMemcpyAsync(hf, h->flags.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
+    PRG_CUDA(cudaMemcpyAsync(&hf[kQB], (uint32_t*)h->cand_cnt.p + kQB, 4, cudaMemcpyDeviceToHost, h->stream));
+    PRG_CUDA(cudaStreamSynchronize(h->stream));
+    if (hf[kQB] > h->last_max_cand) h->last_max_cand = hf[kQB];
+    for (int q = 0; q < nq; ++q) {
+      if (hf[q] != 0) {
+        ++h->last_fallback;
+        PRG_TRY(recall_dense(h, qb + (size_t)q * dim, 1, k, k, kout + (size_t)q * k));
+      }
+    }
+  }
+  return PRG_OK;
+}
+
+int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint32_t* out_row, float* out_score,
+                    int32_t* out_n) {
+  const int total = B * k;
+  const int n = total > B ? total : B;
+  keys_unpack_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(keys_dev, total, k, out_row, out_score, out_n, B);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+// Shard merge: keys_dev is the all-gather output [G][B][k]; per query the G*k keys are distinct
+// (global rows), so the same exact select yields the replica-identical global top-k.
+__global__ void regroup_kernel(const uint64_t* in, uint64_t* out, int G, int B, int k) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)G * B * k;
+  if (i >= total) return;
+  const int j = (int)(i % k);
+  const int b = (int)((i / k) % B);
+  const int g = (int)(i / ((size_t)k * B));
+  out[((size_t)b * G + g) * k + j] = in[i];
+}
+
+int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint64_t* keys_out) {
+  if (G <= 0 || B <= 0 || k <= 0) return fail(PRG_EINVAL, "G, B, k must be positive");
+  if (k > 4096) return fail(PRG_EUNSUPPORTED, "k > 4096");
+  const size_t total = (size_t)G * B * k;
+  PRG_TRY(h->dense_keys.ensure(total * 8));
+  regroup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(keys_dev, (uint64_t*)h->dense_keys.p, G, B, k);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  SelectParams se{};
+  se.keys = (const uint64_t*)h->dense_keys.p; se.stride = (uint64_t)G * k; se.fixed_m = (uint32_t)(G * k);
+  se.cap = se.fixed_m; se.k = k; se.k_out = k; se.out_keys = keys_out;
+  PRG_TRY(launch_select(h, SEL_TOPK, se, B));
+  return PRG_OK;
+}
+
+}  // namespace prg

@@ -1,0 +1,87 @@
+"""GPU parity of the recall path against the CPU oracle, through the C ABI (prg_recall_topk)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, d, b, seed):
+    rng = np.random.default_rng(seed)
+    E = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    Q = (rng.standard_normal((b, d)) / np.sqrt(d)).astype(np.float32)
+    return E, Q
+
+
+def _check(engine, oracle, E, Q, k, row_base=0):
+    engine.set_item_matrix(E, row_base=row_base)
+    rows, scores, n = engine.recall_topk(Q, k)
+    keys = oracle.recall_topk(E, Q, k, row_base=row_base)
+    orows, oscores, on = oracle.keys_split(keys)
+    assert (n == on).all()
+    assert (rows == orows).all(), "recalled row ids differ from the oracle"
+    assert (scores.view(np.uint32) == oscores.view(np.uint32)).all(), "scores are not bit-identical"
+
+
+@pytest.mark.parametrize("n,d,b,k", [(1000, 64, 1, 10), (5000, 64, 7, 100), (4097, 128, 64, 50), (300, 64, 3, 1000),
+                                      (70000, 64, 65, 100)])
+def test_dense_path_matches_oracle(engine, oracle_lib, n, d, b, k):
+    E, Q = _data(n, d, b, seed=n + b)
+    _check(engine, oracle_lib, E, Q, k)
+
+
+@pytest.mark.parametrize("n,d,b,k", [(400_000, 64, 64, 1000), (300_001, 128, 5, 200), (1_000_000, 64, 17, 1000)])
+def test_sampled_path_matches_oracle(engine, oracle_lib, n, d, b, k):
+    E, Q = _data(n, d, b, seed=7)
+    _check(engine, oracle_lib, E, Q, k, row_base=12345)
+    st = engine.recall_stats()
+    assert st["fallback_queries"] == 0
+    assert st["max_candidates"] >= k
+
+
+def test_ties_zero_query_and_duplicates(engine, oracle_lib):
+    # zero query: every score ties at +0 -> rows 0..k-1; duplicated rows tie pairwise
+    E, Q = _data(300_000, 64, 4, seed=3)
+    E[150_000:] = E[:150_000]
+    Q[0] = 0
+    _check(engine, oracle_lib, E, Q, 100)
+
+
+def test_adversarial_order_falls_back_exactly(engine, oracle_lib):
+    # rows sorted by score of query 0: the strided sample is still fine, but force a pathological layout where
+    # all large scores sit in rows the sample never visits
+    n, d = 400_000, 64
+    rng = np.random.default_rng(11)
+    E = (rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    Q = np.zeros((2, d), dtype=np.float32)
+    Q[0, 0] = 1.0
+    Q[1, 1] = -1.0
+    E[:, 0] = 0.0
+    hot = np.arange(256 * 3, 256 * 3 + 2000)  # tiles 3..10 are never sampled (stride >= 12)
+    E[hot, 0] = np.linspace(1, 2, hot.size, dtype=np.float32)
+    _check(engine, oracle_lib, E, Q, 1000)
+    assert engine.recall_stats()["fallback_queries"] >= 1
+
+
+def test_nan_and_inf_scores(engine, oracle_lib):
+    E, Q = _data(3000, 64, 2, seed=5)
+    E[10, 0] = np.nan
+    E[20, 1] = np.inf
+    E[30, 2] = -np.inf
+    _check(engine, oracle_lib, E, Q, 3000)
+
+
+def test_k_larger_than_rows(engine, oracle_lib):
+    E, Q = _data(100, 64, 2, seed=9)
+    engine.set_item_matrix(E)
+    rows, scores, n = engine.recall_topk(Q, 256)
+    assert (n == 100).all()
+    assert (rows[:, 100:] == 0xFFFFFFFF).all() and np.isneginf(scores[:, 100:]).all()
+    keys = oracle_lib.recall_topk(E, Q, 256)
+    orows, _, _ = oracle_lib.keys_split(keys)
+    assert (rows == orows).all()
+
+
+def test_errors_do_not_abort(engine):
+    from pairec_b200 import PrgError
+    with pytest.raises(PrgError):
+        engine.set_item_matrix(np.zeros((10, 48), dtype=np.float32))  # unsupported dim
