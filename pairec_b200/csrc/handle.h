@@ -70,6 +70,7 @@ struct prg_handle {
   prg::DevBuf mlp_W[prg::kMaxLayers];  // bf16, layout chosen by mlp.cu
   prg::DevBuf mlp_b[prg::kMaxLayers];
   CUtensorMap mlp_Wmap[prg::kMaxLayers];
+  float mlp_b_last = 0.f;
   prg::DevBuf act[2];   // activations ping-pong (bf16)
   prg::DevBuf fm_logit; // B*n f32
   prg::DevBuf rank_rows, rank_out;

@@ -1,0 +1,320 @@
+// mlp.cu — dense tower of the rank model on the 5th-gen tensor cores.
+//
+// Replaces the remote EasyRec / TF-Serving DNN behind algorithm/eas/easyrec_request.go:20-73 and
+// algorithm/tfserving/client.go:77-115 (wire contract: one score per item, easyrec_response.go:35-70,
+// tfserving/response.go:51-63).  This is the one GEMM-shaped stage of the path, so it is the one stage on
+// tcgen05: per layer  out[M x N] = relu(A[M x K] * W^T + b)  with
+//   A   = the activations as bf16 hi/lo pairs ("bf16x2": a = hi + lo, hi = bf16(a), lo = bf16(a - hi)), stored
+//         [M][2K] (hi | lo), so one layer is 2*K/64 k-blocks against the same W tile,
+//   W   = bf16 [N][K] (K-major B operand), fp32 accumulation in TMEM.
+// The hi/lo split is what makes the result reproducible to 1e-5 against oracle/oracle.c orc_mlp_forward: with plain
+// bf16 activations a 1e-6 accumulation-order difference flips whole bf16 ulps of hidden units.
+//
+// One CTA per 128 x BN output tile, 6 warps: warp 0 = TMA producer (SWIZZLE_128B boxes, 4-stage mbarrier ring),
+// warp 1 = TMEM allocator + the single MMA-issuing thread (tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16),
+// warps 2-5 = epilogue (tcgen05.ld 32x32b.x32 -> bias + ReLU -> hi/lo split -> global, or for the last hidden layer
+// the fused N=1 output layer: logit = b + sum_j w_j * a_j in fp32).
+#include "handle.h"
+#include <cuda_bf16.h>
+#include <cstring>
+#include <vector>
+
+namespace prg {
+
+constexpr int kMlpBM = 128;
+constexpr int kMlpBK = 64;       // bf16 elements per k-block = one 128-B swizzle row
+constexpr int kMlpStages = 4;
+constexpr int kMlpThreads = 192;
+
+struct MlpLayerParams {
+  int M;                 // valid rows
+  int K;                 // input width (the A tensor has 2K columns)
+  int N;                 // output width
+  const float* bias;     // [N]
+  uint16_t* out;         // [Mp][2N] bf16 (hi | lo)                 (hidden layers)
+  const float* w_last;   // [N] f32 (bf16 values widened)           (FINAL)
+  float b_last;          //                                         (FINAL)
+  float* logit_out;      // [M]                                     (FINAL)
+};
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B canonical layout: 8-row groups of 128-B rows, group stride (SBO) 1024 B, version 1 (sm_100)
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN>
+constexpr size_t mlp_smem_bytes() {
+  return (size_t)kMlpStages * (kMlpBM * 128 + BN * 128) + 2 * BN * 4 + (2 * kMlpStages + 1) * 8 + 16;
+}
+
+template <int BN, bool FINAL>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+mlp_layer_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                 const MlpLayerParams p) {
+  extern __shared__ __align__(1024) uint8_t msm[];
+  constexpr int kABytes = kMlpBM * 128, kBBytes = BN * 128, kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  float* bias_s = reinterpret_cast<float*>(msm + (size_t)kMlpStages * kStageBytes);
+  float* wl_s = bias_s + BN;
+  uint64_t* full = reinterpret_cast<uint64_t*>(wl_s + BN);
+  uint64_t* empty = full + kMlpStages;
+  uint64_t* tmem_full = empty + kMlpStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_blk = blockIdx.x, n_blk = blockIdx.y;
+  const int num_kb = 2 * p.K / kMlpBK;
+
+  for (int i = tid; i < BN; i += kMlpThreads) {
+    bias_s[i] = p.bias ? p.bias[n_blk * BN + i] : 0.f;
+    wl_s[i] = FINAL ? p.w_last[n_blk * BN + i] : 0.f;
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < kMlpStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kMlpStages;
+        const uint32_t ph = (uint32_t)(kb / kMlpStages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], kStageBytes);
+        uint8_t* a_dst = msm + (size_t)s * kStageBytes;
+        tma_load_2d(a_dst, &mapA, kb * kMlpBK, m_blk * kMlpBM, &full[s], kEvictNormal);
+        tma_load_2d(a_dst + kABytes, &mapW, (kb * kMlpBK) % p.K, n_blk * BN, &full[s], kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kMlpBM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kMlpStages;
+        const uint32_t ph = (uint32_t)(kb / kMlpStages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(msm + (size_t)s * kStageBytes);
+        const uint64_t adesc = umma_desc_k_sw128(a_addr), bdesc = umma_desc_k_sw128(a_addr + kABytes);
+#pragma unroll
+        for (int k = 0; k < kMlpBK / 16; ++k)  // UMMA_K = 16 bf16 = 32 B: advance the start address by 2 (16-B units)
+          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&empty[s]);  // frees the stage when these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: 4 warps x 32 TMEM lanes
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int row = m_blk * kMlpBM + quarter * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    float logit = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      uint32_t hi_w[16], lo_w[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        float r0 = fmaxf(__fadd_rn(__uint_as_float(v[c]), bias_s[c0 + c]), 0.f);
+        float r1 = fmaxf(__fadd_rn(__uint_as_float(v[c + 1]), bias_s[c0 + c + 1]), 0.f);
+        const uint16_t h0 = __bfloat16_as_ushort(__float2bfloat16_rn(r0)), h1 = __bfloat16_as_ushort(__float2bfloat16_rn(r1));
+        const float h0f = __uint_as_float((uint32_t)h0 << 16), h1f = __uint_as_float((uint32_t)h1 << 16);
+        const uint16_t l0 = __bfloat16_as_ushort(__float2bfloat16_rn(__fsub_rn(r0, h0f)));
+        const uint16_t l1 = __bfloat16_as_ushort(__float2bfloat16_rn(__fsub_rn(r1, h1f)));
+        if (FINAL) {
+          const float a0 = __fadd_rn(h0f, __uint_as_float((uint32_t)l0 << 16));
+          const float a1 = __fadd_rn(h1f, __uint_as_float((uint32_t)l1 << 16));
+          logit = __fmaf_rn(wl_s[c0 + c], a0, logit);
+          logit = __fmaf_rn(wl_s[c0 + c + 1], a1, logit);
+        } else {
+          hi_w[c >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          lo_w[c >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+      }
+      if (!FINAL) {
+        uint16_t* o = p.out + (size_t)row * (2 * p.N) + (size_t)n_blk * BN + c0;
+        uint4* oh = reinterpret_cast<uint4*>(o);
+        uint4* ol = reinterpret_cast<uint4*>(o + p.N);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          oh[w] = make_uint4(hi_w[4 * w], hi_w[4 * w + 1], hi_w[4 * w + 2], hi_w[4 * w + 3]);
+          ol[w] = make_uint4(lo_w[4 * w], lo_w[4 * w + 1], lo_w[4 * w + 2], lo_w[4 * w + 3]);
+        }
+      }
+    }
+    if (FINAL && row < p.M) p.logit_out[row] = __fadd_rn(logit, p.b_last);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int encode_bf16_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kMlpBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled(bf16) failed: " + std::to_string((int)r));
+  return PRG_OK;
+}
+
+static int tile_n(uint32_t N) {
+  if (N <= 256) return (N % 16 == 0 && N >= 16) ? (int)N : 0;
+  return (N % 256 == 0) ? 256 : 0;
+}
+
+template <int BN, bool FINAL>
+static int launch_layer(prg_handle* h, const CUtensorMap& mapA, const CUtensorMap& mapW, const MlpLayerParams& p, int Mp) {
+  const size_t smem = mlp_smem_bytes<BN>();
+  PRG_CUDA(cudaFuncSetAttribute(mlp_layer_kernel<BN, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)(Mp / kMlpBM), (unsigned)(p.N / BN));
+  mlp_layer_kernel<BN, FINAL><<<grid, kMlpThreads, smem, h->stream>>>(mapA, mapW, p);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+template <bool FINAL>
+static int launch_layer_bn(prg_handle* h, int BN, const CUtensorMap& a, const CUtensorMap& w, const MlpLayerParams& p, int Mp) {
+  switch (BN) {
+    case 64: return launch_layer<64, FINAL>(h, a, w, p, Mp);
+    case 128: return launch_layer<128, FINAL>(h, a, w, p, Mp);
+    case 192: return launch_layer<192, FINAL>(h, a, w, p, Mp);
+    case 256: return launch_layer<256, FINAL>(h, a, w, p, Mp);
+    default: return fail(PRG_EUNSUPPORTED, "MLP hidden width must be 64, 128, 192, 256 or a multiple of 256");
+  }
+}
+
+// x_dev: [Mp][2*dims[0]] bf16 hi|lo in h->act[0];  logit_dev: [M]
+int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit_dev) {
+  const int L = h->mlp_layers;
+  if (L < 2) return fail(PRG_ESTATE, "MLP weights not set (prg_set_mlp)");
+  const int Mp = (M + kMlpBM - 1) / kMlpBM * kMlpBM;
+  const uint16_t* in = x_dev;
+  for (int l = 0; l < L - 1; ++l) {
+    const uint32_t K = h->mlp_dims[l], N = h->mlp_dims[l + 1];
+    const bool final_layer = (l == L - 2);
+    const int BN = tile_n(N);
+    CUtensorMap mapA;
+    PRG_TRY(encode_bf16_map(&mapA, in, 2ull * K, (uint64_t)Mp, kMlpBM));
+    MlpLayerParams p{};
+    p.M = M; p.K = (int)K; p.N = (int)N; p.bias = (const float*)h->mlp_b[l].p;
+    if (final_layer) {
+      p.w_last = (const float*)h->mlp_W[L - 1].p;
+      p.b_last = h->mlp_b_last;
+      p.logit_out = logit_dev;
+      PRG_TRY(launch_layer_bn<true>(h, BN, mapA, h->mlp_Wmap[l], p, Mp));
+    } else {
+      uint16_t* out = (uint16_t*)h->act[(l + 1) & 1].p;
+      p.out = out;
+      PRG_TRY(launch_layer_bn<false>(h, BN, mapA, h->mlp_Wmap[l], p, Mp));
+      in = out;
+    }
+  }
+  return PRG_OK;
+}
+
+size_t mlp_act_bytes(const prg_handle* h, int M) {
+  uint32_t wmax = 0;
+  for (int l = 0; l < h->mlp_layers; ++l) wmax = h->mlp_dims[l] > wmax ? h->mlp_dims[l] : wmax;
+  const size_t Mp = ((size_t)M + kMlpBM - 1) / kMlpBM * kMlpBM;
+  return Mp * 2 * wmax * 2;
+}
+
+}  // namespace prg
+
+using namespace prg;
+
+extern "C" int prg_set_mlp(prg_handle* h, int n_layers, const uint32_t* dims, const uint16_t* const* W,
+                           const float* const* bias) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (n_layers < 2 || n_layers > kMaxLayers || !dims || !W || !bias) return fail(PRG_EINVAL, "bad MLP description");
+  if (dims[n_layers] != 1) return fail(PRG_EUNSUPPORTED, "MLP output width must be 1");
+  if (dims[0] % kMlpBK != 0) return fail(PRG_EUNSUPPORTED, "MLP input width must be a multiple of 64");
+  for (int l = 1; l < n_layers; ++l) {
+    if (tile_n(dims[l]) == 0 || dims[l] % kMlpBK != 0)
+      return fail(PRG_EUNSUPPORTED, "MLP hidden widths must be 64, 128, 192, 256 or a multiple of 256");
+  }
+  if (dims[n_layers - 1] > 256) return fail(PRG_EUNSUPPORTED, "last hidden width must be <= 256 (fused output layer)");
+  std::lock_guard<std::mutex> lk(h->mu);
+  PRG_CUDA(cudaSetDevice(h->device));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  h->mlp_layers = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const size_t K = dims[l], N = dims[l + 1];
+    if (!W[l]) return fail(PRG_EINVAL, "null weight matrix");
+    if (l < n_layers - 1) {
+      PRG_TRY(h->mlp_W[l].ensure(N * K * 2));
+      PRG_CUDA(cudaMemcpy(h->mlp_W[l].p, W[l], N * K * 2, cudaMemcpyHostToDevice));
+      PRG_TRY(h->mlp_b[l].ensure(N * 4));
+      if (bias[l]) PRG_CUDA(cudaMemcpy(h->mlp_b[l].p, bias[l], N * 4, cudaMemcpyHostToDevice));
+      else PRG_CUDA(cudaMemset(h->mlp_b[l].p, 0, N * 4));
+      PRG_TRY(encode_bf16_map(&h->mlp_Wmap[l], h->mlp_W[l].p, K, N, (uint32_t)tile_n((uint32_t)N)));
+    } else {
+      std::vector<float> wl(K);
+      for (size_t i = 0; i < K; ++i) {
+        uint32_t u = (uint32_t)W[l][i] << 16;
+        memcpy(&wl[i], &u, 4);
+      }
+      PRG_TRY(h->mlp_W[l].ensure(K * 4));
+      PRG_CUDA(cudaMemcpy(h->mlp_W[l].p, wl.data(), K * 4, cudaMemcpyHostToDevice));
+      h->mlp_b_last = bias[l] ? bias[l][0] : 0.f;
+    }
+  }
+  for (int l = 0; l <= n_layers; ++l) h->mlp_dims[l] = dims[l];
+  h->mlp_layers = n_layers;
+  return PRG_OK;
+}

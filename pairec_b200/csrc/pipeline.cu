@@ -1,0 +1,266 @@
+// pipeline.cu — C-ABI entry points for the rank / DPP stages and the fused request path
+// (recall -> gather+rank -> score sort -> DPP, everything device resident in between).
+#include "handle.h"
+
+namespace prg {
+// gather_fm.cu
+int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logit_dev, uint16_t* x_dev);
+int logits_to_scores_device(prg_handle* h, const float* a, const float* b, const uint32_t* rows_dev, int M, double* out);
+// mlp.cu
+int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit_dev);
+size_t mlp_act_bytes(const prg_handle* h, int M);
+// sort.cu
+int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32_t* perm_dev);
+// dpp.cu
+int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
+               int32_t* out_idx, int32_t* out_n, int32_t* status);
+
+struct DevGuard {
+  std::unique_lock<std::mutex> lk;
+  explicit DevGuard(prg_handle* h) : lk(h->mu) { cudaSetDevice(h->device); }
+};
+
+static int adopt(const void* src, size_t bytes, int mem, const void** dst, bool* owned) {
+  if (*owned && *dst) cudaFree(const_cast<void*>(*dst));
+  *dst = nullptr;
+  *owned = false;
+  if (mem == PRG_MEM_DEVICE) { *dst = src; return PRG_OK; }
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, bytes ? bytes : 16);
+  if (e != cudaSuccess) return fail(PRG_ENOMEM, std::string("cudaMalloc table: ") + cudaGetErrorString(e));
+  e = cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return fail(PRG_ECUDA, std::string("cudaMemcpy table: ") + cudaGetErrorString(e)); }
+  *dst = d;
+  *owned = true;
+  return PRG_OK;
+}
+
+// rank on device buffers: rows_dev [M] -> score_dev [M] f64
+static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int M, double* score_dev) {
+  if (model != PRG_MODEL_FM && model != PRG_MODEL_MLP && model != PRG_MODEL_FM_MLP)
+    return fail(PRG_EINVAL, "unknown rank model");
+  const bool need_mlp = model != PRG_MODEL_FM;
+  const bool need_fm = model != PRG_MODEL_MLP;
+  if (need_mlp && h->mlp_layers == 0) return fail(PRG_ESTATE, "MLP weights not set (prg_set_mlp)");
+  PRG_TRY(h->fm_logit.ensure((size_t)M * 4 * 2));
+  float* fm_logit = (float*)h->fm_logit.p;
+  float* mlp_logit = fm_logit + M;
+  uint16_t* x = nullptr;
+  if (need_mlp) {
+    if ((size_t)h->n_fields * 16 != h->mlp_dims[0])
+      return fail(PRG_ESTATE, "MLP input width != n_fields * 16");
+    PRG_TRY(h->act[0].ensure(mlp_act_bytes(h, M)));
+    PRG_TRY(h->act[1].ensure(mlp_act_bytes(h, M)));
+    x = (uint16_t*)h->act[0].p;
+  }
+  PRG_TRY(gather_fm_device(h, rows_dev, M, fm_logit, x));
+  if (need_mlp) PRG_TRY(mlp_forward_device(h, x, M, mlp_logit));
+  return logits_to_scores_device(h, need_fm ? fm_logit : mlp_logit, (need_fm && need_mlp) ? mlp_logit : nullptr, rows_dev,
+                                 M, score_dev);
+}
+
+__global__ void apply_perm_kernel(const uint32_t* rows, const double* scores, const int32_t* perm, int total,
+                                  uint32_t* rows_o, double* scores_o, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = i / n;
+  const int src = b * n + perm[i];
+  rows_o[i] = rows[src];
+  scores_o[i] = scores[src];
+}
+__global__ void final_gather_kernel(const uint32_t* rows, const double* scores, const int32_t* idx, const int32_t* cnt,
+                                    const int32_t* status, int B, int n, int T, uint32_t* out_row, double* out_score,
+                                    int32_t* out_n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * T) return;
+  const int b = i / T, t = i - b * T;
+  // status 1: the reference returns the items unchanged (sort/dpp_sort.go:317-320) -> first T of the sorted list
+  const bool unchanged = status[b] != 0;
+  int c = unchanged ? (n < T ? n : T) : cnt[b];
+  if (t == 0) out_n[b] = c;
+  if (t < c) {
+    const int src = b * n + (unchanged ? t : idx[i]);
+    out_row[i] = rows[src];
+    out_score[i] = scores[src];
+  } else {
+    out_row[i] = 0xFFFFFFFFu;
+    out_score[i] = 0.0;
+  }
+}
+
+static int recommend_device(prg_handle* h, const float* q_dev, int B, int k, int model, const prg_dpp_params& p,
+                            uint32_t* out_row, double* out_score, int32_t* out_n) {
+  const int M = B * k;
+  PRG_TRY(h->topk_keys.ensure((size_t)M * 8));
+  PRG_TRY(h->rec_rows.ensure((size_t)M * 4));
+  PRG_TRY(h->out_score.ensure((size_t)M * 4));
+  PRG_TRY(h->out_n.ensure((size_t)B * 4));
+  PRG_TRY(h->rec_scores.ensure((size_t)M * 8));
+  PRG_TRY(h->rec_perm.ensure((size_t)M * 4));
+  PRG_TRY(h->rec_sorted_rows.ensure((size_t)M * 4));
+  PRG_TRY(h->rec_sorted_scores.ensure((size_t)M * 8));
+  PRG_TRY(h->dpp_idx.ensure((size_t)B * p.top_n * 4));
+  PRG_TRY(h->dpp_n.ensure((size_t)B * 4));
+  PRG_TRY(h->dpp_status.ensure((size_t)B * 4));
+  // 1. recall
+  PRG_TRY(recall_topk_device(h, q_dev, B, k, (uint64_t*)h->topk_keys.p));
+  PRG_TRY(keys_to_outputs(h, (const uint64_t*)h->topk_keys.p, B, k, (uint32_t*)h->rec_rows.p, (float*)h->out_score.p,
+                          (int32_t*)h->out_n.p));
+  // 2. gather + rank
+  PRG_TRY(rank_device(h, model, (const uint32_t*)h->rec_rows.p, M, (double*)h->rec_scores.p));
+  // 3. ItemRankScore sort
+  PRG_TRY(sort_desc_device(h, (const double*)h->rec_scores.p, B, k, (int32_t*)h->rec_perm.p));
+  apply_perm_kernel<<<(M + 255) / 256, 256, 0, h->stream>>>((const uint32_t*)h->rec_rows.p, (const double*)h->rec_scores.p,
+                                                            (const int32_t*)h->rec_perm.p, M,
+                                                            (uint32_t*)h->rec_sorted_rows.p,
+                                                            (double*)h->rec_sorted_scores.p, k);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  // 4. DPP
+  PRG_TRY(dpp_device(h, (const uint32_t*)h->rec_sorted_rows.p, (const double*)h->rec_sorted_scores.p, B, k, p,
+                     (int32_t*)h->dpp_idx.p, (int32_t*)h->dpp_n.p, (int32_t*)h->dpp_status.p));
+  const int tot = B * p.top_n;
+  final_gather_kernel<<<(tot + 255) / 256, 256, 0, h->stream>>>(
+      (const uint32_t*)h->rec_sorted_rows.p, (const double*)h->rec_sorted_scores.p, (const int32_t*)h->dpp_idx.p,
+      (const int32_t*)h->dpp_n.p, (const int32_t*)h->dpp_status.p, B, k, p.top_n, out_row, out_score, out_n);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+}  // namespace prg
+
+using namespace prg;
+
+extern "C" {
+
+int prg_set_item_fields(prg_handle* h, const uint32_t* ids, uint64_t rows, uint32_t n_fields, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!ids || rows == 0 || n_fields == 0 || n_fields > (uint32_t)kMaxFields)
+    return fail(PRG_EINVAL, "bad item fields (1 <= n_fields <= 64)");
+  DevGuard g(h);
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  const void* d = h->fields;
+  PRG_TRY(adopt(ids, (size_t)rows * n_fields * 4, mem, &d, &h->fields_owned));
+  h->fields = (const uint32_t*)d;
+  h->fields_rows = rows;
+  h->n_fields = n_fields;
+  return PRG_OK;
+}
+
+int prg_set_feature_table(prg_handle* h, int table, const float* factors, const float* linear, uint64_t rows,
+                          uint32_t fdim, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (table < 0 || table >= kMaxFields) return fail(PRG_EINVAL, "table index out of range");
+  if (!factors || rows == 0) return fail(PRG_EINVAL, "empty feature table");
+  if (fdim != 16) return fail(PRG_EUNSUPPORTED, "feature tables must have fdim == 16");
+  if (rows > 0xFFFFFFFFull) return fail(PRG_EUNSUPPORTED, "feature table rows must fit u32");
+  DevGuard g(h);
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  Table& t = h->tables[table];
+  bool own_f = t.owned, own_l = t.owned && t.linear;
+  const void* f = t.factors;
+  const void* l = t.linear;
+  PRG_TRY(adopt(factors, (size_t)rows * fdim * 4, mem, &f, &own_f));
+  if (linear) {
+    PRG_TRY(adopt(linear, (size_t)rows * 4, mem, &l, &own_l));
+  } else {
+    if (own_l && l) cudaFree(const_cast<void*>(l));
+    l = nullptr;
+  }
+  t.factors = (const float*)f;
+  t.linear = (const float*)l;
+  t.rows = rows;
+  t.owned = own_f;
+  h->fdim = fdim;
+  return PRG_OK;
+}
+
+int prg_set_fm_bias(prg_handle* h, float w0) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  DevGuard g(h);
+  h->fm_w0 = w0;
+  return PRG_OK;
+}
+
+int prg_set_diversity_matrix(prg_handle* h, const void* data, uint64_t rows, uint32_t dim, int dtype, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!data || rows == 0 || dim == 0) return fail(PRG_EINVAL, "empty diversity matrix");
+  if (dtype != PRG_F32 && dtype != PRG_F64) return fail(PRG_EINVAL, "dtype must be PRG_F32 or PRG_F64");
+  if (dim > 512) return fail(PRG_EUNSUPPORTED, "diversity dim > 512");
+  DevGuard g(h);
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  const void* d = h->D;
+  PRG_TRY(adopt(data, (size_t)rows * dim * (dtype == PRG_F64 ? 8 : 4), mem, &d, &h->D_owned));
+  h->D = d;
+  h->D_rows = rows;
+  h->D_dim = dim;
+  h->D_dtype = dtype;
+  return PRG_OK;
+}
+
+int prg_rank(prg_handle* h, int model, const uint32_t* rows, int B, int n, double* out_score, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!rows || !out_score || B <= 0 || n <= 0) return fail(PRG_EINVAL, "bad arguments");
+  DevGuard g(h);
+  const int M = B * n;
+  if (mem == PRG_MEM_DEVICE) return rank_device(h, model, rows, M, out_score);
+  PRG_TRY(h->rank_rows.ensure((size_t)M * 4));
+  PRG_TRY(h->rank_out.ensure((size_t)M * 8));
+  PRG_CUDA(cudaMemcpyAsync(h->rank_rows.p, rows, (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
+  PRG_TRY(rank_device(h, model, (const uint32_t*)h->rank_rows.p, M, (double*)h->rank_out.p));
+  PRG_CUDA(cudaMemcpyAsync(out_score, h->rank_out.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+
+int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_dpp_params* p,
+            int32_t* out_idx, int32_t* out_n, int32_t* status, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!rows || !score || !p || !out_idx || !out_n || !status) return fail(PRG_EINVAL, "null buffer");
+  if (B <= 0 || n <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "B, n, top_n must be positive");
+  DevGuard g(h);
+  if (mem == PRG_MEM_DEVICE) return dpp_device(h, rows, score, B, n, *p, out_idx, out_n, status);
+  const size_t M = (size_t)B * n, TT = (size_t)B * p->top_n;
+  PRG_TRY(h->dpp_rows.ensure(M * 4));
+  PRG_TRY(h->dpp_score.ensure(M * 8));
+  PRG_TRY(h->dpp_idx.ensure(TT * 4));
+  PRG_TRY(h->dpp_n.ensure((size_t)B * 4));
+  PRG_TRY(h->dpp_status.ensure((size_t)B * 4));
+  PRG_CUDA(cudaMemcpyAsync(h->dpp_rows.p, rows, M * 4, cudaMemcpyHostToDevice, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(h->dpp_score.p, score, M * 8, cudaMemcpyHostToDevice, h->stream));
+  PRG_CUDA(cudaMemsetAsync(h->dpp_idx.p, 0xFF, TT * 4, h->stream));
+  PRG_TRY(dpp_device(h, (const uint32_t*)h->dpp_rows.p, (const double*)h->dpp_score.p, B, n, *p, (int32_t*)h->dpp_idx.p,
+                     (int32_t*)h->dpp_n.p, (int32_t*)h->dpp_status.p));
+  PRG_CUDA(cudaMemcpyAsync(out_idx, h->dpp_idx.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_n, h->dpp_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(status, h->dpp_status.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+
+int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params* p,
+                  uint32_t* out_row, double* out_score, int32_t* out_n, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!q || !p || !out_row || !out_score || !out_n) return fail(PRG_EINVAL, "null buffer");
+  if (B <= 0 || recall_k <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "B, recall_k, top_n must be positive");
+  DevGuard g(h);
+  if (!h->E) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
+  if (mem == PRG_MEM_DEVICE) return recommend_device(h, q, B, recall_k, model, *p, out_row, out_score, out_n);
+  const size_t TT = (size_t)B * p->top_n;
+  PRG_TRY(h->q_dev.ensure((size_t)B * h->E_dim * 4));
+  PRG_TRY(h->out_row.ensure(TT * 4 > (size_t)B * recall_k * 4 ? TT * 4 : (size_t)B * recall_k * 4));
+  PRG_TRY(h->rank_out.ensure(TT * 8));
+  PRG_TRY(h->flags.ensure((size_t)(B > 64 ? B : 64) * 4));
+  PRG_CUDA(cudaMemcpyAsync(h->q_dev.p, q, (size_t)B * h->E_dim * 4, cudaMemcpyHostToDevice, h->stream));
+  PRG_TRY(h->sort_perm.ensure((size_t)B * 4));
+  PRG_TRY(recommend_device(h, (const float*)h->q_dev.p, B, recall_k, model, *p, (uint32_t*)h->out_row.p,
+                           (double*)h->rank_out.p, (int32_t*)h->sort_perm.p));
+  PRG_CUDA(cudaMemcpyAsync(out_row, h->out_row.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_score, h->rank_out.p, TT * 8, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_n, h->sort_perm.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+
+}  // extern "C"

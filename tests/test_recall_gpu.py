@@ -47,17 +47,18 @@ def test_ties_zero_query_and_duplicates(engine, oracle_lib):
 
 
 def test_adversarial_order_falls_back_exactly(engine, oracle_lib):
-    # rows sorted by score of query 0: the strided sample is still fine, but force a pathological layout where
-    # all large scores sit in rows the sample never visits
+    # every large score sits in a tile the strided sample never visits -> the candidate list overflows and the
+    # query is redone through the dense path; the result must still be exact
     n, d = 400_000, 64
     rng = np.random.default_rng(11)
     E = (rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    n_tiles = (n + 255) // 256
+    stride = n_tiles // max(64, n_tiles // 128)        # sampling plan of recall.cu
+    tile = np.arange(n) // 256
+    E[:, 0] = np.where(tile % stride == 0, 0.0, 1.0 + rng.random(n) * 0.5).astype(np.float32)
     Q = np.zeros((2, d), dtype=np.float32)
     Q[0, 0] = 1.0
     Q[1, 1] = -1.0
-    E[:, 0] = 0.0
-    hot = np.arange(256 * 3, 256 * 3 + 2000)  # tiles 3..10 are never sampled (stride >= 12)
-    E[hot, 0] = np.linspace(1, 2, hot.size, dtype=np.float32)
     _check(engine, oracle_lib, E, Q, 1000)
     assert engine.recall_stats()["fallback_queries"] >= 1
 
