@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — requests/s and p99 ms of the recall -> gather+rank -> sort -> DPP hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one batch of synthetic requests.
+
+  python bench.py --gpus 1 --steps K --warmup W            the CUDA path (libpairec_gpu.so through its C ABI)
+  python bench.py --impl reference --gpus N ...            the reference's CPU path (oracle port) on the host cores
+
+N=1 workload ("c4"): BASELINE.json configs[3] — 10 M items x 64-d f32 recall top-1000, 32 categorical tables
+(1 M rows x 16-d) gather + FM + MLP 512-512-256-128-1 (bf16 tensor cores) rank, score sort, DPP top-50 (window 10) on
+128-d diversity embeddings, batch 64 requests.  The recall stage alone is configs[1]; it is the dominant kernel and
+the one the roofline object describes.
+
+N>1 (torchrun, one rank per GPU): the item matrix is row-sharded (10 M / N rows per rank), every rank scans its shard
+for the global batch of 64*N queries, ONE all-gather (NCCL) exchanges the per-shard top-k keys, and each rank merges,
+ranks and re-ranks its own 64 requests with replicated feature/diversity tables: per-GPU work is constant -> "weak".
+
+Timing: W >= 3 warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the library's
+stream, max over ranks.  The 2.56 GB item matrix is far larger than the 126 MB L2, so every step streams it from
+HBM (config.l2 = "inputs larger than L2").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (items, dim, k, batch, n_fields, table_rows, mlp dims, div_dim, top_n, window)
+    "c4": dict(items=10_000_000, dim=64, k=1000, batch=64, n_fields=32, table_rows=1_000_000,
+               mlp=[512, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
+    "small": dict(items=400_000, dim=64, k=1000, batch=64, n_fields=32, table_rows=50_000,
+                  mlp=[512, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
+}
+METRIC = "requests/sec (10M-item recall->rank->DPP)"
+UNIT = "requests/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- synthetic tables
+def make_tables_torch(w, dev, rank, world):
+    """Synthetic tables generated ON the device with torch (plumbing).  Seeds follow SURVEY §8d."""
+    import torch
+    g = torch.Generator(device=dev)
+    items, dim = w["items"], w["dim"]
+    shard = items // world
+    row_base = rank * shard
+    if rank == world - 1:
+        shard = items - row_base
+    g.manual_seed(2 + 1000 * rank)
+    E = torch.randn(shard, dim, device=dev, generator=g) / dim ** 0.5
+    g.manual_seed(5)
+    F, R = w["n_fields"], w["table_rows"]
+    u = torch.rand(items, F, device=dev, generator=g)
+    fields = (u * u * u * R).to(torch.int32).clamp_(0, R - 1)  # skewed ids (hot head), replicated on every rank
+    del u
+    g.manual_seed(4)
+    factors = torch.randn(F, R, 16, device=dev, generator=g) * 0.4
+    linear = torch.randn(F, R, device=dev, generator=g) * 0.05
+    g.manual_seed(7)
+    D = torch.randn(items, w["div_dim"], device=dev, generator=g)
+    D /= D.norm(dim=1, keepdim=True)
+    return dict(E=E, row_base=row_base, fields=fields, factors=factors, linear=linear, D=D)
+
+
+def mlp_weights(dims, seed=6):
+    import oracle
+    rng = np.random.default_rng(seed)
+    W, b = [], []
+    for l in range(len(dims) - 1):
+        lim = np.sqrt(6.0 / (dims[l] + dims[l + 1]))
+        W.append(oracle.f32_to_bf16(rng.uniform(-lim, lim, size=(dims[l + 1], dims[l])).astype(np.float32)))
+        b.append((rng.standard_normal(dims[l + 1]) * 0.01).astype(np.float32))
+    return W, b
+
+
+def bf16_bits(a):
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+def mlp_weights_np(dims, seed=6):
+    rng = np.random.default_rng(seed)
+    W, b = [], []
+    for l in range(len(dims) - 1):
+        lim = np.sqrt(6.0 / (dims[l] + dims[l + 1]))
+        W.append(bf16_bits(rng.uniform(-lim, lim, size=(dims[l + 1], dims[l])).astype(np.float32)))
+        b.append((rng.standard_normal(dims[l + 1]) * 0.01).astype(np.float32))
+    return W, b
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_pipeline(w, T, Q, sample_rows, threads):
+    """The oracle port of the path on the host cores, over the first `sample_rows` catalog rows; returns seconds per
+    stage for one batch.  Recall time scales linearly with rows, the other stages do not depend on the catalog size."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    B, k = Q.shape[0], w["k"]
+    E = T["E"][:sample_rows]
+    t0 = time.perf_counter()
+    keys = oracle.recall_topk(E, Q, k, n_threads=threads)
+    t_recall = time.perf_counter() - t0
+    rows, _, _ = oracle.keys_split(keys)
+    t0 = time.perf_counter()
+    fm, x = oracle.gather_fm(T["fields"], T["factors"], T["linear"], 0.05, rows.reshape(-1), want_x=True)
+    t_gather = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ml = oracle.mlp_forward(x, w["mlp"], T["W"], T["b"])
+    sc = oracle.sigmoid((fm + ml).astype(np.float32)).astype(np.float64).reshape(B, k)
+    t_mlp = time.perf_counter() - t0
+
+    def one(b):
+        perm = oracle.stable_sort_desc(sc[b])
+        r = rows[b][perm]
+        idx, st = oracle.dpp_request(T["D"][r].astype(np.float64), sc[b][perm], w["top_n"], alpha=1.0,
+                                     window_size=w["window"])
+        return r[idx]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=max(1, min(threads, B))) as ex:
+        out = list(ex.map(one, range(B)))
+    t_dpp = time.perf_counter() - t0
+    return dict(recall=t_recall, gather_fm=t_gather, mlp=t_mlp, sort_dpp=t_dpp), out
+
+
+def cpu_tables(w, sample_rows):
+    """Host tables for the CPU arm (numpy, same distributions as the device tables; the CPU arm is a timing arm)."""
+    rng = np.random.default_rng(2)
+    F, R = w["n_fields"], min(w["table_rows"], 200_000)
+    E = (rng.standard_normal((sample_rows, w["dim"]), dtype=np.float32) / np.float32(w["dim"] ** 0.5))
+    u = rng.random((sample_rows, F), dtype=np.float32)
+    fields = np.minimum((u * u * u * R).astype(np.uint32), R - 1)
+    factors = [(rng.standard_normal((R, 16), dtype=np.float32) * np.float32(0.4)) for _ in range(F)]
+    linear = [(rng.standard_normal(R, dtype=np.float32) * np.float32(0.05)) for _ in range(F)]
+    D = rng.standard_normal((sample_rows, w["div_dim"]), dtype=np.float32)
+    D /= np.linalg.norm(D, axis=1, keepdims=True)
+    W, b = mlp_weights_np(w["mlp"])
+    return dict(E=E, fields=fields, factors=factors, linear=linear, D=D, W=W, b=b)
+
+
+def cpu_measure(w, steps, warmup, sample_rows):
+    import oracle
+    oracle.build()
+    threads = oracle.num_threads()
+    T = cpu_tables(w, sample_rows)
+    rng = np.random.default_rng(3)
+    Q = (rng.standard_normal((w["batch"], w["dim"]), dtype=np.float32) / np.float32(w["dim"] ** 0.5))
+    per = []
+    for i in range(warmup + steps):
+        st, _ = cpu_pipeline(w, T, Q, sample_rows, threads)
+        if i >= warmup:
+            per.append(st)
+    scale = w["items"] / sample_rows
+    tot = [p["recall"] * scale + p["gather_fm"] + p["mlp"] + p["sort_dpp"] for p in per]
+    med = float(np.median(tot))
+    stages = {k: float(np.median([p[k] for p in per])) for k in per[0]}
+    stages["recall_scaled_to_full_catalog"] = stages["recall"] * scale
+    return dict(value=w["batch"] / med, ms_per_step=med * 1e3, cores=threads, stages_s=stages,
+                sample=f"batch {w['batch']} requests; recall over the first {sample_rows} of {w['items']} rows "
+                       f"(time scaled x{scale:.1f}), gather+FM / MLP / sort+DPP at full size on tables of "
+                       f"{min(w['table_rows'], 200_000)} rows; oracle port (C, AVX2 FMA), all host threads")
+
+
+# ---------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("PRG_WORKLOAD", "c4"), choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+    config = {"workload": f"{args.workload}: {w['items']} items x {w['dim']}-d f32 recall top-{w['k']} -> "
+                          f"{w['n_fields']}-table gather + FM + MLP {'-'.join(map(str, w['mlp']))} (bf16x2 act, bf16 W) "
+                          f"rank -> score sort -> DPP top-{w['top_n']} (window {w['window']}, {w['div_dim']}-d f32 table, "
+                          f"fp64 arithmetic)",
+              "batch_per_gpu": w["batch"], "global_batch": w["batch"] * world,
+              "sharding": "item matrix row-sharded, one all-gather of per-shard top-k keys" if world > 1 else "none",
+              "l2": "inputs larger than L2 (2.56 GB item matrix streamed per step)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample_rows = min(args.cpu_sample_rows, w["items"])
+        r = cpu_measure(w, max(1, min(args.steps, 3)), 1, sample_rows)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 recall/FM, f64 MLP-acc/DPP",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"], "stages_s": r["stages_s"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pairec_b200 import DppParams, Engine
+    from pairec_b200.binding import MEM_DEVICE, MODEL_FM_MLP
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local_rank)
+    T = make_tables_torch(w, dev, rank, world)
+    eng.set_item_matrix(T["E"].data_ptr(), rows=T["E"].shape[0], dim=w["dim"], row_base=T["row_base"], mem=MEM_DEVICE)
+    eng.set_item_fields(T["fields"].data_ptr(), rows=w["items"], n_fields=w["n_fields"], mem=MEM_DEVICE)
+    for t in range(w["n_fields"]):
+        eng.set_feature_table(t, T["factors"][t].data_ptr(), T["linear"][t].data_ptr(), rows=w["table_rows"], fdim=16,
+                              mem=MEM_DEVICE)
+    eng.set_fm_bias(0.05)
+    W, b = mlp_weights_np(w["mlp"])
+    eng.set_mlp(w["mlp"], W, b)
+    eng.set_diversity_matrix(T["D"].data_ptr(), rows=w["items"], dim=w["div_dim"], dtype=0, mem=MEM_DEVICE)
+    p = DppParams(top_n=w["top_n"], alpha=1.0, window_size=w["window"])
+
+    B, k, Tn = w["batch"], w["k"], w["top_n"]
+    Bg = B * world
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(3)
+    Qg = torch.randn(Bg, w["dim"], device=dev, generator=gq) / w["dim"] ** 0.5   # same global batch on every rank
+    out_rows = torch.empty(B, Tn, dtype=torch.int32, device=dev)
+    out_scores = torch.empty(B, Tn, dtype=torch.float64, device=dev)
+    out_n = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+    if world > 1:
+        keys_local = torch.empty(Bg, k, dtype=torch.int64, device=dev)
+        keys_all = torch.empty(world, Bg, k, dtype=torch.int64, device=dev)
+
+    def step_device():
+        if world == 1:
+            eng.recommend_dev(Qg.data_ptr(), B, k, MODEL_FM_MLP, p, out_rows.data_ptr(), out_scores.data_ptr(),
+                              out_n.data_ptr())
+        else:
+            eng.recall_local_keys_dev(Qg.data_ptr(), Bg, k, keys_local.data_ptr())
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(keys_all, keys_local)
+            eng.recommend_from_keys_dev(keys_all.data_ptr() + rank * B * k * 8, world, Bg * k, B, k, MODEL_FM_MLP, p,
+                                        out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr())
+
+    def sync_all():
+        eng.sync()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    # ---- warm-up, then K timed steps (device-resident inputs): `value`
+    for _ in range(warmup):
+        step_device()
+    sync_all()
+    eng.timing(True)
+    eng.timing(True, read=True)  # reset accumulators
+    launches0 = eng.launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    sync_all()
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step_device()
+            ev[i + 1].record(stream)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    stage = eng.timing(False, read=True)
+    launches = eng.launches - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    value = Bg * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: the same step through the host-buffer C ABI (pinned host queries in, results out), 1 GPU path per rank
+    e2e = None
+    if world == 1:
+        q_host = torch.empty(B, w["dim"], dtype=torch.float32).pin_memory()
+        q_host.copy_(Qg.cpu())
+        rows_h = torch.empty(B, Tn, dtype=torch.int32).pin_memory()
+        sc_h = torch.empty(B, Tn, dtype=torch.float64).pin_memory()
+        n_h = torch.empty(B, dtype=torch.int32).pin_memory()
+        import ctypes as C
+        lib, h = eng._lib, eng._h
+        def step_host():
+            rc = lib.prg_recommend(h, C.c_void_p(q_host.data_ptr()), B, k, MODEL_FM_MLP, C.byref(p),
+                                   C.c_void_p(rows_h.data_ptr()), C.c_void_p(sc_h.data_ptr()),
+                                   C.c_void_p(n_h.data_ptr()), 0)
+            assert rc == 0, lib.prg_last_error()
+        for _ in range(3):
+            step_host()
+        lat = []
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            t1 = time.perf_counter()
+            step_host()
+            lat.append((time.perf_counter() - t1) * 1e3)
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": B * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * w["dim"] * 4,
+               "d2h_bytes_per_step": B * Tn * 12 + B * 4, "p50_ms": float(np.percentile(lat, 50)),
+               "p99_ms": float(np.percentile(lat, 99)),
+               "note": "prg_recommend with host buffers: H2D of the queries, all stages, D2H of rows/scores/counts, per step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_kind = peaks()
+    scan = stage["scan"]
+    scan_ms = scan["ms"] / max(1, scan["spans"])
+    rows_local = T["E"].shape[0]
+    alg_bytes = rows_local * w["dim"] * 4 + min(Bg, 64) * w["dim"] * 4   # per scan launch (<= 64 queries per pass)
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": total_ms / args.steps, "p50_ms_per_step": float(np.percentile(step_ms, 50)),
+            "p99_ms_per_step": float(np.percentile(step_ms, 99)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (recall, FM), bf16x2/bf16->f32 (MLP), f64 (sort, DPP)",
+            "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+            "stage_ms_per_step": {s: stage[s]["ms"] / args.steps for s in stage},
+            "roofline": {"kernel": "recall_scan_kernel<64,THRESH>", "bound": "hbm", "achieved": achieved,
+                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                         "peak_source": f"MEASURED_PEAKS.json ({pk_kind})", "launch_ms": scan_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "fp32_tflops": 2.0 * rows_local * w["dim"] * 64 / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0,
+                         "note": "at 64 queries per pass the scan is FP32-issue bound (FFMA2 peak measured 68.4 TFLOP/s), "
+                                 "not HBM bound; see DESIGN.md"},
+            "e2e": e2e}
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            r = cpu_measure(w, 1, 0, min(args.cpu_sample_rows, w["items"]))
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"], "stages_s": r["stages_s"]}
+        except Exception as ex:  # the baseline must not take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

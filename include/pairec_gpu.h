@@ -154,6 +154,13 @@ int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int
 int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params* p,
                   uint32_t* out_row, double* out_score, int32_t* out_n, int mem);
 
+/* Row-sharded variant: keys_dev points at this rank's slice of the all-gathered per-shard top-k keys —
+ * G lists of B x k keys, list g at keys_dev + g*g_stride (u64 elements) — which are merged (same total order, so the
+ * result is replica-identical) and then ranked / sorted / DPP-re-ranked as in prg_recommend.  Feature, field and
+ * diversity tables must hold every global row (replicated per GPU). */
+int prg_recommend_from_keys(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k, int model,
+                            const prg_dpp_params* p, uint32_t* out_row, double* out_score, int32_t* out_n, int mem);
+
 /* ---------------------------------------------------------------- LOOKUP algorithm (algorithm/lookup.go:37-51) */
 
 /* present[i] != 0 -> out[i] = value[i], else 0.5.  Pure host code. */
@@ -163,6 +170,11 @@ int prg_lookup(const double* value, const uint8_t* present, int n, double* out);
 
 /* Number of kernels launched by this handle since init (bench.py's gpu_launches). */
 uint64_t prg_launch_count(prg_handle* h);
+/* Per-stage device time: enable != 0 turns on CUDA-event spans around each stage's launches (on the handle's
+ * stream).  When ms_out / n_out are non-NULL the call synchronises, writes the accumulated milliseconds and span
+ * counts per stage (8 entries: 0 scan, 1 scan-dense/sample, 2 select, 3 gather+FM, 4 MLP, 5 sort, 6 DPP, 7 other)
+ * and resets the accumulators. */
+int prg_timing(prg_handle* h, int enable, double* ms_out, uint64_t* n_out);
 /* Last recall: how many queries took the dense re-scan path, and candidates collected per query (max). */
 int prg_recall_stats(prg_handle* h, int32_t* n_fallback, int32_t* max_candidates);
 

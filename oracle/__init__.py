@@ -29,7 +29,9 @@ def lib():
             build()
         _lib = C.CDLL(_LIB_PATH)
         _lib.orc_key_score.restype = C.c_float
+        _lib.orc_key_score.argtypes = [C.c_uint64]
         _lib.orc_key_row.restype = C.c_uint32
+        _lib.orc_key_row.argtypes = [C.c_uint64]
         _lib.orc_make_key.restype = C.c_uint64
         _lib.orc_make_key.argtypes = [C.c_float, C.c_uint32]
         _lib.orc_sigmoid.restype = C.c_float

@@ -19,7 +19,7 @@ EXPORTS = [
     "prg_init", "prg_destroy", "prg_last_error", "prg_version", "prg_sync", "prg_stream", "prg_set_item_matrix",
     "prg_set_item_fields", "prg_set_feature_table", "prg_set_fm_bias", "prg_set_mlp", "prg_set_diversity_matrix",
     "prg_recall_topk", "prg_recall_local_keys", "prg_merge_keys", "prg_rank", "prg_sort_desc_host", "prg_sort_desc",
-    "prg_dpp", "prg_recommend", "prg_lookup", "prg_launch_count", "prg_recall_stats",
+    "prg_dpp", "prg_recommend", "prg_recommend_from_keys", "prg_lookup", "prg_launch_count", "prg_recall_stats", "prg_timing",
 ]
 
 
@@ -40,7 +40,8 @@ class DppParams(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libpairec_gpu.so")
+    # PRG_LIB selects another build of the same library (kernel-variant experiments); never a different backend
+    return os.environ.get("PRG_LIB") or os.path.join(_HERE, "libpairec_gpu.so")
 
 
 def load_library():
@@ -121,6 +122,18 @@ class Engine:
         a, b = C.c_int32(0), C.c_int32(0)
         self._ck(self._lib.prg_recall_stats(self._h, C.byref(a), C.byref(b)))
         return {"fallback_queries": a.value, "max_candidates": b.value}
+
+    STAGES = ("scan", "scan_dense", "select", "gather_fm", "mlp", "sort", "dpp", "other")
+
+    def timing(self, enable, read=False):
+        """Per-stage device milliseconds / span counts measured with CUDA events inside the library."""
+        if not read:
+            self._ck(self._lib.prg_timing(self._h, C.c_int(int(enable)), None, None))
+            return None
+        ms = (C.c_double * 8)()
+        n = (C.c_uint64 * 8)()
+        self._ck(self._lib.prg_timing(self._h, C.c_int(int(enable)), ms, n))
+        return {s: {"ms": ms[i], "spans": int(n[i])} for i, s in enumerate(self.STAGES)}
 
     # ---------------------------------------------------------------- tables
     def set_item_matrix(self, data, rows=None, dim=None, row_base=0, mem=MEM_HOST):
@@ -246,6 +259,15 @@ class Engine:
         self._ck(self._lib.prg_recommend(self._h, _ptr(q_ptr), C.c_int(B), C.c_int(recall_k), C.c_int(model),
                                          C.byref(params), _ptr(rows_ptr), _ptr(scores_ptr), _ptr(n_ptr),
                                          C.c_int(MEM_DEVICE)))
+
+
+def _engine_recommend_from_keys_dev(self, keys_ptr, G, g_stride, B, k, model, params, rows_ptr, scores_ptr, n_ptr):
+    self._ck(self._lib.prg_recommend_from_keys(self._h, _ptr(keys_ptr), C.c_int(G), C.c_uint64(g_stride), C.c_int(B),
+                                               C.c_int(k), C.c_int(model), C.byref(params), _ptr(rows_ptr),
+                                               _ptr(scores_ptr), _ptr(n_ptr), C.c_int(MEM_DEVICE)))
+
+
+Engine.recommend_from_keys_dev = _engine_recommend_from_keys_dev
 
 
 def sort_desc_host(score):

@@ -158,13 +158,15 @@ void prg_destroy(prg_handle* h) {
         if (h->tables[t].linear) cudaFree(const_cast<float*>(h->tables[t].linear));
       }
     }
-    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
+    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
                       &h->out_row, &h->out_score, &h->out_n, &h->flags, &h->table_ptrs, &h->act[0], &h->act[1],
                       &h->fm_logit, &h->rank_rows, &h->rank_out, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
                       &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->sort_in, &h->sort_perm, &h->rec_rows,
                       &h->rec_scores, &h->rec_perm, &h->rec_sorted_rows, &h->rec_sorted_scores};
     for (DevBuf* b : bufs) b->release();
     for (int l = 0; l < kMaxLayers; ++l) { h->mlp_W[l].release(); h->mlp_b[l].release(); }
+    for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
   }
   delete h;
@@ -178,6 +180,29 @@ int prg_sync(prg_handle* h) {
 }
 void* prg_stream(prg_handle* h) { return h ? (void*)h->stream : nullptr; }
 uint64_t prg_launch_count(prg_handle* h) { return h ? h->launches : 0; }
+
+int prg_timing(prg_handle* h, int enable, double* ms_out, uint64_t* n_out) {
+  CHECK_H(h);
+  Guard g(h);
+  if (ms_out || n_out) {
+    PRG_CUDA(cudaStreamSynchronize(h->stream));
+    for (auto& sp : h->spans) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { h->stage_ms[sp.stage] += ms; h->stage_n[sp.stage] += 1; }
+      h->ev_pool.push_back(sp.a);
+      h->ev_pool.push_back(sp.b);
+    }
+    h->spans.clear();
+    for (int i = 0; i < 8; ++i) {
+      if (ms_out) ms_out[i] = h->stage_ms[i];
+      if (n_out) n_out[i] = h->stage_n[i];
+      h->stage_ms[i] = 0;
+      h->stage_n[i] = 0;
+    }
+  }
+  h->timing = enable != 0;
+  return PRG_OK;
+}
 
 int prg_recall_stats(prg_handle* h, int32_t* n_fallback, int32_t* max_candidates) {
   CHECK_H(h);
@@ -247,7 +272,7 @@ int prg_merge_keys(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k,
   Guard g(h);
   const size_t nk = (size_t)B * k;
   PRG_TRY(h->topk_keys.ensure(nk * 8));
-  PRG_TRY(merge_keys_device(h, keys_dev, G, B, k, (uint64_t*)h->topk_keys.p));
+  PRG_TRY(merge_keys_device(h, keys_dev, G, (uint64_t)B * k, B, k, (uint64_t*)h->topk_keys.p));
   if (mem == PRG_MEM_DEVICE) return keys_to_outputs(h, (const uint64_t*)h->topk_keys.p, B, k, out_row, out_score, out_n);
   PRG_TRY(h->out_row.ensure(nk * 4));
   PRG_TRY(h->out_score.ensure(nk * 4));

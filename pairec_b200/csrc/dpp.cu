@@ -384,6 +384,7 @@ int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev,
   a.rows = rows_dev; a.score = score_dev; a.n = n; a.D = h->D; a.D_rows = h->D_rows; a.D_dim = (int)h->D_dim;
   a.p = p; a.Et = h->dpp_scratch.p; a.out_idx = out_idx; a.out_n = out_n; a.status = status; a.c_rows = c_rows;
   const size_t smem = dpp_smem_bytes(c_rows, p.top_n);
+  StageScope span(h, ST_DPP);
   if (h->D_dtype == PRG_F64) {
     PRG_CUDA(cudaFuncSetAttribute(dpp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dpp_kernel<double><<<B, kDppMaxItems, smem, h->stream>>>(a);

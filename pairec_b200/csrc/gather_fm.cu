@@ -115,6 +115,7 @@ int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logi
     ts.linear[f] = h->tables[f].linear;
     ts.rows[f] = (uint32_t)h->tables[f].rows;
   }
+  StageScope span(h, ST_GATHER_FM);
   const int threads = 256;
   const long long total = (long long)M * 4;
   const unsigned grid = (unsigned)((total + threads - 1) / threads);

@@ -30,6 +30,14 @@ struct prg_handle {
   std::mutex mu;
   uint64_t launches = 0;
 
+  // optional per-stage device timing (CUDA events on this handle's stream around each stage's launches)
+  bool timing = false;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  double stage_ms[8] = {0};
+  uint64_t stage_n[8] = {0};
+
   int max_batch = 64;
   int max_k = 1000;
 
@@ -44,7 +52,8 @@ struct prg_handle {
 
   prg::DevBuf q_dev;        // B x dim f32 (host-call staging)
   prg::DevBuf sample_keys;  // QB x sample_slots u64
-  prg::DevBuf cand_keys;    // B x cand_cap u64
+  prg::DevBuf cand_keys;    // QB x cand_cap u64 (packed candidates)
+  prg::DevBuf seg_keys;     // QB x n_seg x seg_cap u64 (per-CTA candidate segments)
   prg::DevBuf cand_cnt;     // B u32
   prg::DevBuf tau;          // B u64
   prg::DevBuf dense_keys;   // fallback / small-N: nq x slots u64
@@ -94,10 +103,31 @@ namespace prg {
 // launch bookkeeping
 inline void count_launch(prg_handle* h, int n = 1) { h->launches += (uint64_t)n; }
 
+enum Stage { ST_SCAN = 0, ST_SCAN_DENSE = 1, ST_SELECT = 2, ST_GATHER_FM = 3, ST_MLP = 4, ST_SORT = 5, ST_DPP = 6, ST_OTHER = 7 };
+// RAII span: records an event before and after the enclosed launches when timing is on
+struct StageScope {
+  prg_handle* h;
+  int stage;
+  cudaEvent_t a = nullptr;
+  static cudaEvent_t get(prg_handle* h) {
+    cudaEvent_t e = nullptr;
+    if (!h->ev_pool.empty()) { e = h->ev_pool.back(); h->ev_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  }
+  StageScope(prg_handle* hh, int st) : h(hh), stage(st) {
+    if (h->timing) { a = get(h); cudaEventRecord(a, h->stream); }
+  }
+  ~StageScope() {
+    if (a) { cudaEvent_t b = get(h); cudaEventRecord(b, h->stream); h->spans.push_back({stage, a, b}); }
+  }
+};
+
 // recall.cu
 int recall_build_map(prg_handle* h);
 int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t* keys_out /*B x k*/);
 int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint32_t* out_row, float* out_score,
                     int32_t* out_n);
-int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint64_t* keys_out);
+int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k,
+                      uint64_t* keys_out);
 }  // namespace prg

@@ -243,6 +243,7 @@ int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit
   const int L = h->mlp_layers;
   if (L < 2) return fail(PRG_ESTATE, "MLP weights not set (prg_set_mlp)");
   const int Mp = (M + kMlpBM - 1) / kMlpBM * kMlpBM;
+  StageScope span(h, ST_MLP);
   const uint16_t* in = x_dev;
   for (int l = 0; l < L - 1; ++l) {
     const uint32_t K = h->mlp_dims[l], N = h->mlp_dims[l + 1];

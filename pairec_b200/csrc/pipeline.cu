@@ -88,10 +88,20 @@ __global__ void final_gather_kernel(const uint32_t* rows, const double* scores, 
   }
 }
 
+// stages after recall: topk_keys [B][k] (sorted, merged) -> rank -> sort -> DPP -> outputs
+static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
+                              double* out_score, int32_t* out_n);
+
 static int recommend_device(prg_handle* h, const float* q_dev, int B, int k, int model, const prg_dpp_params& p,
                             uint32_t* out_row, double* out_score, int32_t* out_n) {
+  PRG_TRY(h->topk_keys.ensure((size_t)B * k * 8));
+  PRG_TRY(recall_topk_device(h, q_dev, B, k, (uint64_t*)h->topk_keys.p));
+  return post_recall_device(h, B, k, model, p, out_row, out_score, out_n);
+}
+
+static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
+                              double* out_score, int32_t* out_n) {
   const int M = B * k;
-  PRG_TRY(h->topk_keys.ensure((size_t)M * 8));
   PRG_TRY(h->rec_rows.ensure((size_t)M * 4));
   PRG_TRY(h->out_score.ensure((size_t)M * 4));
   PRG_TRY(h->out_n.ensure((size_t)B * 4));
@@ -102,8 +112,6 @@ static int recommend_device(prg_handle* h, const float* q_dev, int B, int k, int
   PRG_TRY(h->dpp_idx.ensure((size_t)B * p.top_n * 4));
   PRG_TRY(h->dpp_n.ensure((size_t)B * 4));
   PRG_TRY(h->dpp_status.ensure((size_t)B * 4));
-  // 1. recall
-  PRG_TRY(recall_topk_device(h, q_dev, B, k, (uint64_t*)h->topk_keys.p));
   PRG_TRY(keys_to_outputs(h, (const uint64_t*)h->topk_keys.p, B, k, (uint32_t*)h->rec_rows.p, (float*)h->out_score.p,
                           (int32_t*)h->out_n.p));
   // 2. gather + rank
@@ -235,6 +243,27 @@ int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int
   PRG_CUDA(cudaMemcpyAsync(out_idx, h->dpp_idx.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaMemcpyAsync(out_n, h->dpp_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaMemcpyAsync(status, h->dpp_status.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+
+int prg_recommend_from_keys(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k, int model,
+                            const prg_dpp_params* p, uint32_t* out_row, double* out_score, int32_t* out_n, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!keys_dev || !p || !out_row || !out_score || !out_n) return fail(PRG_EINVAL, "null buffer");
+  if (G <= 0 || B <= 0 || k <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "G, B, k, top_n must be positive");
+  DevGuard g(h);
+  PRG_TRY(h->topk_keys.ensure((size_t)B * k * 8));
+  PRG_TRY(merge_keys_device(h, keys_dev, G, g_stride, B, k, (uint64_t*)h->topk_keys.p));
+  if (mem == PRG_MEM_DEVICE) return post_recall_device(h, B, k, model, *p, out_row, out_score, out_n);
+  const size_t TT = (size_t)B * p->top_n;
+  PRG_TRY(h->out_row.ensure(TT * 4 > (size_t)B * k * 4 ? TT * 4 : (size_t)B * k * 4));
+  PRG_TRY(h->rank_out.ensure(TT * 8));
+  PRG_TRY(h->sort_perm.ensure((size_t)B * 4));
+  PRG_TRY(post_recall_device(h, B, k, model, *p, (uint32_t*)h->out_row.p, (double*)h->rank_out.p, (int32_t*)h->sort_perm.p));
+  PRG_CUDA(cudaMemcpyAsync(out_row, h->out_row.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_score, h->rank_out.p, TT * 8, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_n, h->sort_perm.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaStreamSynchronize(h->stream));
   return PRG_OK;
 }

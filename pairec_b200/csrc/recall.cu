@@ -32,6 +32,10 @@ constexpr int kStages = 3;
 constexpr int kSubTileFloats = kTileRows * 32;       // one TMA box: 256 rows x 32 floats (128 B)
 
 enum { SCAN_THRESH = 0, SCAN_DENSE = 1 };
+#ifndef SCAN_UNROLL
+#define SCAN_UNROLL 2
+#endif
+constexpr int kScanUnroll = SCAN_UNROLL;
 
 struct ScanParams {
   const float* Q;          // [nq][dim]
@@ -41,9 +45,9 @@ struct ScanParams {
   uint32_t n_tiles;        // tiles covered by this launch
   uint32_t tile_stride;    // launch tile t reads matrix tile t*tile_stride
   const uint64_t* tau;     // THRESH: [nq]
-  uint64_t* cand;          // THRESH: [nq][cand_cap]
-  uint32_t cand_cap;
-  uint32_t* cand_cnt;      // THRESH: [nq]
+  uint64_t* cand;          // THRESH: [nq][gridDim.x][seg_cap] — one private segment per CTA and query
+  uint32_t seg_cap;
+  uint32_t* seg_cnt;       // THRESH: [nq][gridDim.x], written once per CTA at kernel end
   uint64_t* dense;         // DENSE: [nq][dense_stride], slot = t*256 + r
   uint64_t dense_stride;
 };
@@ -51,7 +55,7 @@ struct ScanParams {
 template <int DIM>
 constexpr size_t scan_smem_bytes() {
   return (size_t)kStages * kStageBytes + (size_t)DIM * kQB * 4 + kQB * 4 + kQB * 8 +
-         2 * kStages * 8;
+         2 * kStages * 8 + kQB * 4;
 }
 
 template <int DIM, int MODE>
@@ -64,6 +68,7 @@ recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p)
   uint64_t* tau64 = reinterpret_cast<uint64_t*>(tauf + kQB);                   // [64]
   uint64_t* full = tau64 + kQB;
   uint64_t* empty = full + kStages;
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(empty + kStages);                // [64] candidates appended by this CTA
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int KH = DIM / 64;
@@ -81,6 +86,7 @@ recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p)
     }
     tau64[tid] = t;
     tauf[tid] = tf;
+    s_cnt[tid] = 0;
   }
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -133,7 +139,7 @@ recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p)
       mbar_wait(&full[s], ph);
       const float* st = stage_base + (size_t)s * kStageFloats;
       const float* qs = Qs + (size_t)h * 64 * kQB + qbase;
-#pragma unroll 2
+#pragma unroll kScanUnroll
       for (int c = 0; c < 16; ++c) {
         const int sub = c >> 3, ch = c & 7;
         float4 xv[TM];
@@ -169,19 +175,24 @@ recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p)
     const uint32_t t = blockIdx.x + i * gridDim.x;
     const uint64_t tile_row0 = (uint64_t)t * p.tile_stride * kTileRows;
     if (MODE == SCAN_THRESH) {
-      bool any = false;
+      // pre-test: one predicate per row of the register tile (64 FSETP per thread-tile in total); a pass is rare
+      // (~1 score per warp-tile), and the append below costs one shared-memory atomic + one fire-and-forget store:
+      // no global round trip stalls the warp.
+      bool any_m[TM];
+#pragma unroll
+      for (int m = 0; m < TM; ++m) any_m[m] = false;
 #pragma unroll
       for (int c2 = 0; c2 < TQ / 2; ++c2) {
         const float t0 = tauf[qbase + 2 * c2], t1 = tauf[qbase + 2 * c2 + 1];
 #pragma unroll
         for (int m = 0; m < TM; ++m) {
-          any |= !(acc[m][c2].x < t0);
-          any |= !(acc[m][c2].y < t1);
+          any_m[m] |= !(acc[m][c2].x < t0);
+          any_m[m] |= !(acc[m][c2].y < t1);
         }
       }
-      if (any) {
 #pragma unroll
-        for (int m = 0; m < TM; ++m) {
+      for (int m = 0; m < TM; ++m) {
+        if (any_m[m]) {
           const uint64_t lrow = tile_row0 + (uint64_t)(rloc0 + 32 * m);
           if (lrow < p.n_rows) {
             const uint32_t grow = (uint32_t)(p.row_base + lrow);
@@ -194,8 +205,8 @@ recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p)
                 if (!(sc < tauf[q])) {
                   const uint64_t key = make_key(sc, grow);
                   if (q < p.nq && key >= tau64[q]) {
-                    const uint32_t pos = atomicAdd(&p.cand_cnt[q], 1u);
-                    if (pos < p.cand_cap) p.cand[(size_t)q * p.cand_cap + pos] = key;
+                    const uint32_t pos = atomicAdd(&s_cnt[q], 1u);
+                    if (pos < p.seg_cap) p.cand[((size_t)q * gridDim.x + blockIdx.x) * p.seg_cap + pos] = key;
                   }
                 }
               }
@@ -224,6 +235,10 @@ recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p)
       }
     }
   }
+  if (MODE == SCAN_THRESH) {
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");  // consumer warps only
+    if (tid < p.nq) p.seg_cnt[(size_t)tid * gridDim.x + blockIdx.x] = s_cnt[tid];
+  }
 }
 
 // ------------------------------------------------------------------ select: exact k-th / sorted top-k of a key list
@@ -233,6 +248,11 @@ struct SelectParams {
   const uint32_t* counts;  // per-query list length (nullable -> fixed_m); clamped to cap, overflow flagged
   uint32_t fixed_m;
   uint32_t cap;
+  // segmented input (scan<THRESH> output): query q owns n_seg segments of seg_cap keys at keys + (q*n_seg+s)*seg_cap,
+  // lengths seg_counts[q*n_seg+s]; they are first packed into compact + q*stride (cap = stride).
+  const uint32_t* seg_counts;
+  uint32_t n_seg, seg_cap;
+  uint64_t* compact;
   int k;                   // rank wanted
   int k_out;               // row stride of the outputs (== caller's k)
   uint32_t expect;         // MODE_TOPK: number of results that must exist (min(k, total rows)), else flag 2
@@ -256,9 +276,38 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const SelectParams p) {
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint64_t* keys = p.keys + (size_t)q * p.stride;
   uint32_t m = p.counts ? p.counts[q] : p.fixed_m;
-  const bool overflow = m > p.cap;
+  bool overflow = m > p.cap;
+  if (p.seg_counts) {
+    // pack the per-CTA segments: exclusive prefix of the (clamped) lengths, then a strided copy
+    __shared__ uint32_t seg_off[513];
+    if (tid == 0) {
+      uint32_t run = 0;
+      bool ov = false;
+      for (uint32_t sgi = 0; sgi < p.n_seg; ++sgi) {
+        uint32_t c = p.seg_counts[(size_t)q * p.n_seg + sgi];
+        if (c > p.seg_cap) { c = p.seg_cap; ov = true; }
+        seg_off[sgi] = run;
+        run += c;
+      }
+      seg_off[p.n_seg] = run;
+      s_want = ov ? 1u : 0u;
+    }
+    __syncthreads();
+    m = seg_off[p.n_seg];
+    overflow = (s_want != 0u) || m > p.cap;
+    if (m > p.cap) m = p.cap;
+    uint64_t* dst = p.compact + (size_t)q * p.stride;
+    for (uint32_t sgi = warp; sgi < p.n_seg; sgi += 32) {
+      const uint32_t o = seg_off[sgi], c = seg_off[sgi + 1] - o;
+      const uint64_t* src = p.keys + ((size_t)q * p.n_seg + sgi) * p.seg_cap;
+      for (uint32_t i = lane; i < c; i += 32)
+        if (o + i < p.cap) dst[o + i] = src[i];
+    }
+    __syncthreads();
+    keys = dst;
+  }
   if (p.max_count && tid == 0) atomicMax(p.max_count, m);
-  if (overflow) m = p.cap;
+  if (overflow && m > p.cap) m = p.cap;
 
   if (tid == 0) { s_zero = 0; s_fill = 0; }
   __syncthreads();
@@ -402,6 +451,7 @@ static int launch_scan(prg_handle* h, const ScanParams& p) {
   const size_t smem = scan_smem_bytes<DIM>();
   PRG_CUDA(cudaFuncSetAttribute(recall_scan_kernel<DIM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (p.n_tiles == 0) return PRG_OK;
+  StageScope span(h, MODE == SCAN_THRESH ? ST_SCAN : ST_SCAN_DENSE);
   const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
   recall_scan_kernel<DIM, MODE><<<grid, kScanThreads, smem, h->stream>>>(h->E_map, p);
   PRG_CUDA(cudaGetLastError());
@@ -417,6 +467,7 @@ static int scan(prg_handle* h, int mode, const ScanParams& p) {
 }
 
 static int launch_select(prg_handle* h, int mode, const SelectParams& p, int nq) {
+  StageScope span(h, ST_SELECT);
   if (mode == SEL_KTH) {
     select_kernel<SEL_KTH><<<nq, 1024, 0, h->stream>>>(p);
   } else {
@@ -463,7 +514,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   const bool sampled = h->E_rows >= kSampledMinRows && (uint64_t)k * 64 <= h->E_rows;
 
   // sampling plan: ~1/128 of the tiles, strided across the whole matrix
-  uint32_t sample_tiles = 0, tile_stride = 1, r_rank = 0, cand_cap = 0;
+  uint32_t sample_tiles = 0, tile_stride = 1, r_rank = 0, cand_cap = 0, n_seg = 0, seg_cap = 0;
   if (sampled) {
     sample_tiles = n_tiles / 128;
     if (sample_tiles < 64) sample_tiles = 64;
@@ -476,8 +527,12 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     cand_cap = (uint32_t)(4.0 * (double)r_rank / f);
     cand_cap = (cand_cap + 1023) & ~1023u;
     PRG_TRY(h->sample_keys.ensure((size_t)kQB * sample_tiles * kTileRows * 8));
+    n_seg = n_tiles < (uint32_t)h->sm_count ? n_tiles : (uint32_t)h->sm_count;
+    seg_cap = (uint32_t)(8.0 * ((double)r_rank / f) / n_seg) + 32;
+    seg_cap = (seg_cap + 15) & ~15u;
     PRG_TRY(h->cand_keys.ensure((size_t)kQB * cand_cap * 8));
-    PRG_TRY(h->cand_cnt.ensure((size_t)kQB * 4 + 4));
+    PRG_TRY(h->seg_keys.ensure((size_t)kQB * n_seg * seg_cap * 8));
+    PRG_TRY(h->cand_cnt.ensure((size_t)kQB * n_seg * 4 + 4));
     PRG_TRY(h->tau.ensure((size_t)kQB * 8));
     PRG_TRY(h->flags.ensure((size_t)kQB * 4));
   }
@@ -502,25 +557,28 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     st.cap = st.fixed_m; st.k = (int)r_rank; st.tau = (uint64_t*)h->tau.p;
     PRG_TRY(launch_select(h, SEL_KTH, st, nq));
     // 3. full scan with fused threshold test
-    PRG_CUDA(cudaMemsetAsync(h->cand_cnt.p, 0, (size_t)kQB * 4 + 4, h->stream));
+    uint32_t* max_cnt = (uint32_t*)h->cand_cnt.p + (size_t)kQB * n_seg;
+    PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
     ScanParams sc{};
     sc.Q = qb; sc.nq = nq; sc.n_rows = h->E_rows; sc.row_base = h->E_row_base;
     sc.n_tiles = n_tiles; sc.tile_stride = 1;
-    sc.tau = (const uint64_t*)h->tau.p; sc.cand = (uint64_t*)h->cand_keys.p; sc.cand_cap = cand_cap;
-    sc.cand_cnt = (uint32_t*)h->cand_cnt.p;
+    sc.tau = (const uint64_t*)h->tau.p; sc.cand = (uint64_t*)h->seg_keys.p; sc.seg_cap = seg_cap;
+    sc.seg_cnt = (uint32_t*)h->cand_cnt.p;
     PRG_TRY(scan(h, SCAN_THRESH, sc));
     // 4. exact top-k of the candidates
     SelectParams se{};
-    se.keys = (const uint64_t*)h->cand_keys.p; se.stride = cand_cap; se.counts = (const uint32_t*)h->cand_cnt.p;
+    se.keys = (const uint64_t*)h->seg_keys.p; se.stride = cand_cap; se.counts = nullptr;
+    se.seg_counts = (const uint32_t*)h->cand_cnt.p; se.n_seg = n_seg; se.seg_cap = seg_cap;
+    se.compact = (uint64_t*)h->cand_keys.p;
     se.cap = cand_cap; se.k = k; se.k_out = k;
     se.expect = (uint32_t)((uint64_t)k < h->E_rows ? (uint64_t)k : h->E_rows);
     se.out_keys = kout; se.flags = (int32_t*)h->flags.p;
-    se.max_count = (uint32_t*)h->cand_cnt.p + kQB;
+    se.max_count = max_cnt;
     PRG_TRY(launch_select(h, SEL_TOPK, se, nq));
     // 5. per-query status; redo the rare failures through the dense path
     int32_t hf[kQB + 1];
     PRG_CUDA(cudaMemcpyAsync(hf, h->flags.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
-    PRG_CUDA(cudaMemcpyAsync(&hf[kQB], (uint32_t*)h->cand_cnt.p + kQB, 4, cudaMemcpyDeviceToHost, h->stream));
+    PRG_CUDA(cudaMemcpyAsync(&hf[kQB], max_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
     PRG_CUDA(cudaStreamSynchronize(h->stream));
     if (hf[kQB] > h->last_max_cand) h->last_max_cand = hf[kQB];
     for (int q = 0; q < nq; ++q) {
@@ -545,22 +603,24 @@ int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint3
 
 // Shard merge: keys_dev is the all-gather output [G][B][k]; per query the G*k keys are distinct
 // (global rows), so the same exact select yields the replica-identical global top-k.
-__global__ void regroup_kernel(const uint64_t* in, uint64_t* out, int G, int B, int k) {
+__global__ void regroup_kernel(const uint64_t* in, uint64_t g_stride, uint64_t* out, int G, int B, int k) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)G * B * k;
   if (i >= total) return;
   const int j = (int)(i % k);
   const int b = (int)((i / k) % B);
   const int g = (int)(i / ((size_t)k * B));
-  out[((size_t)b * G + g) * k + j] = in[i];
+  out[((size_t)b * G + g) * k + j] = in[(size_t)g * g_stride + (size_t)b * k + j];
 }
 
-int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint64_t* keys_out) {
+int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k,
+                      uint64_t* keys_out) {
   if (G <= 0 || B <= 0 || k <= 0) return fail(PRG_EINVAL, "G, B, k must be positive");
   if (k > 4096) return fail(PRG_EUNSUPPORTED, "k > 4096");
   const size_t total = (size_t)G * B * k;
   PRG_TRY(h->dense_keys.ensure(total * 8));
-  regroup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(keys_dev, (uint64_t*)h->dense_keys.p, G, B, k);
+  regroup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(keys_dev, g_stride, (uint64_t*)h->dense_keys.p, G,
+                                                                          B, k);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   SelectParams se{};

@@ -185,6 +185,7 @@ int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32
   uint32_t P2 = 32;
   while (P2 < (uint32_t)n) P2 <<= 1;
   const size_t smem = (size_t)P2 * 12;
+  StageScope span(h, ST_SORT);
   if (smem > 48 * 1024)
     PRG_CUDA(cudaFuncSetAttribute(sort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sort_desc_kernel<<<B, P2 / 2 < 1024 ? (P2 / 2 < 32 ? 32 : P2 / 2) : 1024, smem, h->stream>>>(score_dev, n, perm_dev);

@@ -1,0 +1,187 @@
+"""CPU tests of the oracle (no GPU): the reference's one known-answer test for this path, the committed golden
+fixtures, an independent pure-Python restatement of DPP, and structural properties."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import ref_py, synth
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_rank_score_expression_kat(oracle_lib):
+    # utils/ast/ast_test.go:12-27 — "${ctr} + ${click} + ${price}" with ctr=0.1, click=0.3, price=0.1 evaluates to 0.5
+    assert oracle_lib.rank_score_expr([0.1, 0.3, 0.1], [1.0, 1.0, 1.0]) == 0.5
+
+
+def test_lookup_default(oracle_lib):
+    # algorithm/lookup.go:44-49
+    out = oracle_lib.lookup(np.array([0.2, 9.0, 0.7]), np.array([1, 0, 1]))
+    assert out.tolist() == [0.2, 0.5, 0.7]
+
+
+def test_golden_recall(oracle_lib):
+    g = np.load(os.path.join(G, "recall_small.npz"))
+    keys = oracle_lib.recall_topk(g["E"], g["Q"], int(g["k"]), row_base=int(g["row_base"]))
+    assert (keys == g["keys"]).all()
+    rows, scores, n = oracle_lib.keys_split(keys)
+    # independent check: numpy stable argsort of fp32 fmaf-chain scores
+    s = oracle_lib.recall_scores(g["E"], g["Q"])
+    ref = np.argsort(-s, axis=1, kind="stable")[:, :int(g["k"])]
+    assert (rows == ref + int(g["row_base"])).all()
+    assert (np.diff(keys.astype(np.uint64).view(np.int64), axis=1) < 0).all()  # strictly descending keys
+
+
+def test_recall_thread_count_does_not_change_result(oracle_lib):
+    rng = np.random.default_rng(1)
+    E = rng.standard_normal((20000, 64)).astype(np.float32)
+    Q = rng.standard_normal((3, 64)).astype(np.float32)
+    a = oracle_lib.recall_topk(E, Q, 50, n_threads=1)
+    b = oracle_lib.recall_topk(E, Q, 50, n_threads=5)
+    assert (a == b).all()
+
+
+def test_shard_merge_equals_unsharded(oracle_lib):
+    rng = np.random.default_rng(2)
+    E = rng.standard_normal((9000, 64)).astype(np.float32)
+    E[4000:4100] = E[:100]          # ties across shards
+    Q = rng.standard_normal((4, 64)).astype(np.float32)
+    full = oracle_lib.recall_topk(E, Q, 64)
+    parts = [oracle_lib.recall_topk(E[a:b], Q, 64, row_base=a) for a, b in ((0, 3000), (3000, 6000), (6000, 9000))]
+    merged = oracle_lib.merge_keys(np.stack(parts))
+    assert (merged == full).all()
+
+
+def test_golden_rank(oracle_lib):
+    g = np.load(os.path.join(G, "rank_small.npz"))
+    factors = [g[f"factors{t}"] for t in range(8)]
+    linear = [g[f"linear{t}"] for t in range(8)]
+    logit, x = oracle_lib.gather_fm(g["fields"], factors, linear, float(g["w0"]), g["rows"])
+    assert (logit.view(np.uint32) == g["fm_logit"].view(np.uint32)).all()
+    assert (x == g["x"]).all()
+    W = [g[f"W{l}"] for l in range(3)]
+    b = [g[f"b{l}"] for l in range(3)]
+    mlp = oracle_lib.mlp_forward(x, g["dims"].tolist(), W, b)
+    assert (mlp.view(np.uint32) == g["mlp_logit"].view(np.uint32)).all()
+    assert (oracle_lib.sigmoid(logit).view(np.uint32) == g["fm_score"].view(np.uint32)).all()
+
+
+def test_fm_against_numpy_float64(oracle_lib):
+    fields, factors, linear = synth.rank_tables(n_items=200, n_fields=6, max_rows=100)
+    rows = np.arange(200, dtype=np.uint32)
+    logit, x = oracle_lib.gather_fm(fields, factors, linear, 0.1, rows)
+    v = np.stack([factors[f][fields[:, f]] for f in range(6)], axis=1).astype(np.float64)   # [n, F, 16]
+    lin = 0.1 + sum(linear[f][fields[:, f]].astype(np.float64) for f in range(6))
+    inter = ((v.sum(1) ** 2) - (v ** 2).sum(1)).sum(1)
+    want = lin + 0.5 * inter
+    assert np.allclose(logit, want, rtol=0, atol=1e-6)
+    assert (x.reshape(200, 6, 16) == v.astype(np.float32)).all()
+
+
+def test_mlp_against_numpy_float64(oracle_lib):
+    dims = [64, 64, 1]
+    W, b = synth.mlp_weights(dims)
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((40, 64)) * 0.5).astype(np.float32)
+    got = oracle_lib.mlp_forward(x, dims, W, b)
+    a = x.astype(np.float64)
+    a = np.maximum(a @ oracle_lib.bf16_to_f32(W[0]).astype(np.float64).T + b[0], 0)
+    want = a @ oracle_lib.bf16_to_f32(W[1]).astype(np.float64).T + b[1]
+    # bf16x2 activations carry >= 16 significant bits
+    assert np.allclose(got, want[:, 0], rtol=0, atol=2e-5)
+
+
+def test_bf16_round_to_nearest_even(oracle_lib):
+    lib = oracle_lib.lib()
+    assert lib.orc_f32_to_bf16(1.0) == 0x3F80
+    assert lib.orc_f32_to_bf16(np.float32(1.0 + 2 ** -8)) == 0x3F80      # tie -> even
+    assert lib.orc_f32_to_bf16(np.float32(1.0 + 3 * 2 ** -8)) == 0x3F82  # tie -> even (up)
+    a = np.random.default_rng(0).standard_normal(1000).astype(np.float32)
+    assert (oracle_lib.f32_to_bf16(a) == np.array([lib.orc_f32_to_bf16(float(v)) for v in a], dtype=np.uint16)).all()
+
+
+def test_golden_dpp_and_python_restatement(oracle_lib):
+    g = np.load(os.path.join(G, "dpp_small.npz"))
+    emb = g["emb"].astype(np.float64)
+    idx, st = oracle_lib.dpp_request(emb, g["score"], 25, alpha=1.0, window_size=10)
+    assert st == int(g["status"]) and (idx == g["idx"]).all()
+    idx2, st2 = oracle_lib.dpp_request(emb, g["score2"], 12, alpha=2.0, window_size=5, norm_mode=2)
+    assert st2 == int(g["status2"]) and (idx2 == g["idx2"]).all()
+    # independent pure-Python float64 restatement (tests/ref_py.py)
+    L = ref_py.kernel_matrix(emb.tolist(), g["score"].tolist(), 1.0)
+    assert ref_py.dpp_with_window(L, 25, 10) == idx.tolist()
+    Lc = oracle_lib.dpp_kernel_matrix(emb, g["score"], alpha=1.0)
+    assert (np.array(L) == Lc).all(), "kernel matrix differs from the Python restatement"
+
+
+def test_dpp_kernel_matrix_matches_closed_form(oracle_lib):
+    rng = np.random.default_rng(5)
+    emb = rng.standard_normal((30, 12))
+    rel = rng.random(30)
+    L = oracle_lib.dpp_kernel_matrix(emb, rel, alpha=1.5)
+    e = emb / np.linalg.norm(emb, axis=1, keepdims=True)
+    S = (1 + e @ e.T) / 2
+    q = np.exp(1.5 * rel)
+    assert np.allclose(L, q[:, None] * S * q[None, :], rtol=1e-12)
+
+
+def test_dpp_edge_cases(oracle_lib):
+    rng = np.random.default_rng(6)
+    emb = rng.standard_normal((25, 8))
+    score = rng.random(25)
+    # ctx.Size > n in windowed mode: index 0 is repeated once the candidates run out (dpp_sort.go:477-499)
+    idx, st = oracle_lib.dpp_request(emb, score, 50, window_size=10)
+    assert st == 0 and len(idx) == 50 and sorted(set(idx[:25].tolist())) == list(range(25)) and (idx[25:] == 0).all()
+    # ctx.Size <= window: one call, clamped to n
+    idx, st = oracle_lib.dpp_request(emb[:5], score[:5], 8, window_size=10)
+    assert len(idx) == 5 and sorted(idx.tolist()) == list(range(5))
+    # duplicate embeddings + alpha 0: second copy has d2 ~ 0 -> early stop + lowest-index fill (:539-548)
+    emb2 = np.repeat(rng.standard_normal((1, 8)), 6, axis=0)
+    idx, st = oracle_lib.dpp_request(emb2, np.zeros(6), 4, alpha=0.0, window_size=10)
+    assert idx.tolist() == [0, 1, 2, 3]
+    # all-zero scores with z-score normalisation -> error path, items unchanged
+    idx, st = oracle_lib.dpp_request(emb, np.zeros(25), 10, norm_mode=1)
+    assert st == 1 and idx.tolist() == list(range(25))
+    # CandidateCount / MinScorePercent truncation (:280-300)
+    idx, st = oracle_lib.dpp_request(emb, score, 5, candidate_count=10)
+    top10 = set(np.argsort(-score)[:10].tolist())
+    assert set(idx.tolist()) <= top10
+
+
+def test_go_sort_properties(oracle_lib):
+    g = np.load(os.path.join(G, "sort_small.npz"))
+    assert (oracle_lib.go_sort(g["score"]) == g["go_perm"]).all()
+    assert (oracle_lib.stable_sort_desc(g["score"]) == g["stable_perm"]).all()
+    rng = np.random.default_rng(7)
+    for n in (0, 1, 2, 12, 13, 49, 50, 51, 333, 1000, 4097):
+        s = rng.random(n)
+        p = oracle_lib.go_sort(s)
+        assert sorted(p.tolist()) == list(range(n))
+        assert (np.diff(s[p]) <= 0).all()
+        assert (p == oracle_lib.stable_sort_desc(s)).all()     # distinct scores: every correct sort agrees
+    # already-sorted input (recall output feeding ItemRankScore) is left untouched, ties included
+    s = -np.sort(-np.round(rng.random(1000), 2))
+    assert (oracle_lib.go_sort(s) == np.arange(1000)).all()
+    # heavy ties: still a sorted permutation; tie groups are the same sets as the stable order
+    s = np.round(rng.random(500), 1)
+    p, q = oracle_lib.go_sort(s), oracle_lib.stable_sort_desc(s)
+    assert (s[p] == s[q]).all() and sorted(p.tolist()) == list(range(500))
+
+
+def test_algo_score_sort_switch(oracle_lib):
+    # sort/algo_score_sort.go:45-49
+    score = np.array([0.2, 0.9, 0.5])
+    field = np.array([3.0, 1.0, 2.0])
+    assert oracle_lib.algo_score_sort(score, field, switch_threshold=0.95).tolist() == [0, 2, 1]   # by field
+    assert oracle_lib.algo_score_sort(score, field, switch_threshold=0.5).tolist() == [1, 2, 0]    # by current score
+
+
+def test_key_order_properties(oracle_lib):
+    lib = oracle_lib.lib()
+    vals = [float("-inf"), -1.5, -0.0, 0.0, 1e-30, 2.5, float("inf")]
+    ks = [lib.orc_make_key(v, 10) for v in vals]
+    assert ks == sorted(ks) and len(set(ks)) == len(ks)
+    assert lib.orc_make_key(float("nan"), 10) < ks[0]           # NaN ranks below -inf
+    assert lib.orc_make_key(1.0, 3) > lib.orc_make_key(1.0, 4)  # ties: lower row first
+    assert lib.orc_key_row(lib.orc_make_key(1.0, 12345)) == 12345 and lib.orc_key_score(lib.orc_make_key(-2.5, 1)) == -2.5
