@@ -184,27 +184,30 @@ ORC_API int orc_merge_keys(const uint64_t* keys, int G, int B, int k, uint64_t* 
  * x_out (optional): the F*fdim concatenated factors (MLP input), row-major [n][F*fdim].
  * rows == 0xFFFFFFFF is padding: logit 0, x zeros.
  */
-ORC_API int orc_gather_fm(const uint32_t* fields, uint64_t field_rows, uint32_t F, const float* const* factors,
-                          const float* const* linear, const uint64_t* table_rows, uint32_t fdim, float w0,
-                          const uint32_t* rows, int n, float* logit_out, float* x_out) {
-  if (fdim > 64) return 1;
-  for (int i = 0; i < n; ++i) {
-    const uint32_t row = rows[i];
-    float* x = x_out ? x_out + (size_t)i * F * fdim : NULL;
-    if (row == 0xFFFFFFFFu || row >= field_rows) {
-      if (logit_out) logit_out[i] = 0.0f;
+typedef struct { const uint32_t* fields; uint64_t field_rows; uint32_t F; const float* const* factors;
+                 const float* const* linear; const uint64_t* table_rows; uint32_t fdim; float w0; const uint32_t* rows;
+                 int n; float* logit_out; float* x_out; } gfm_job;
+static void gfm_worker(void* arg, int tid, int nt) {
+  const gfm_job* J = (const gfm_job*)arg;
+  const uint32_t F = J->F, fdim = J->fdim;
+  const int i0 = (int)((int64_t)J->n * tid / nt), i1 = (int)((int64_t)J->n * (tid + 1) / nt);
+  for (int i = i0; i < i1; ++i) {
+    const uint32_t row = J->rows[i];
+    float* x = J->x_out ? J->x_out + (size_t)i * F * fdim : NULL;
+    if (row == 0xFFFFFFFFu || row >= J->field_rows) {
+      if (J->logit_out) J->logit_out[i] = 0.0f;
       if (x) memset(x, 0, sizeof(float) * (size_t)F * fdim);
       continue;
     }
-    float lin = w0, s[64], ss[64];
+    float lin = J->w0, s[64], ss[64];
     for (uint32_t k = 0; k < fdim; ++k) { s[k] = 0.0f; ss[k] = 0.0f; }
     for (uint32_t f = 0; f < F; ++f) {
-      const uint32_t id = fields[(size_t)row * F + f];
-      const int ok = id < table_rows[f];
-      const float w = (ok && linear[f]) ? linear[f][id] : 0.0f;
+      const uint32_t id = J->fields[(size_t)row * F + f];
+      const int ok = id < J->table_rows[f];
+      const float w = (ok && J->linear[f]) ? J->linear[f][id] : 0.0f;
       lin = lin + w;
       for (uint32_t k = 0; k < fdim; ++k) {
-        const float v = ok ? factors[f][(size_t)id * fdim + k] : 0.0f;
+        const float v = ok ? J->factors[f][(size_t)id * fdim + k] : 0.0f;
         s[k] = s[k] + v;
         ss[k] = __builtin_fmaf(v, v, ss[k]);
         if (x) x[f * fdim + k] = v;
@@ -212,8 +215,15 @@ ORC_API int orc_gather_fm(const uint32_t* fields, uint64_t field_rows, uint32_t 
     }
     float inter = 0.0f;
     for (uint32_t k = 0; k < fdim; ++k) inter = inter + __builtin_fmaf(s[k], s[k], -ss[k]);
-    if (logit_out) logit_out[i] = __builtin_fmaf(0.5f, inter, lin);
+    if (J->logit_out) J->logit_out[i] = __builtin_fmaf(0.5f, inter, lin);
   }
+}
+ORC_API int orc_gather_fm(const uint32_t* fields, uint64_t field_rows, uint32_t F, const float* const* factors,
+                          const float* const* linear, const uint64_t* table_rows, uint32_t fdim, float w0,
+                          const uint32_t* rows, int n, float* logit_out, float* x_out) {
+  if (fdim > 64) return 1;
+  gfm_job job = {fields, field_rows, F, factors, linear, table_rows, fdim, w0, rows, n, logit_out, x_out};
+  orc_parallel(n > 1024 ? orc_hw_threads() : 1, gfm_worker, &job);
   return 0;
 }
 
@@ -248,12 +258,12 @@ ORC_API float orc_bf16_to_f32(uint16_t h) { return bf16_to_f32(h); }
  *   hidden: a = max(z, 0) -> split again;   last layer (width 1): logit = z (f32)
  * x: [n][dims[0]] f32.  W[l]: [dims[l+1]][dims[l]] bf16 bits.  logit_out: [n].
  */
-typedef struct { const float* x; int n, n_layers; const uint32_t* dims; const uint16_t* const* W; const float* const* bias; float* logit_out; uint32_t maxd; } mlp_job;
+typedef struct { const float* x; int n, n_layers; const uint32_t* dims; double* const* Wt; const float* const* bias; float* logit_out; uint32_t maxd; } mlp_job;
 static void mlp_worker(void* arg, int tid, int nt) {
   const mlp_job* J = (const mlp_job*)arg;
   const uint32_t* dims = J->dims;
   double* a = (double*)malloc(sizeof(double) * J->maxd);
-  float* z = (float*)malloc(sizeof(float) * J->maxd);
+  double* acc = (double*)malloc(sizeof(double) * J->maxd);
   const int i0 = (int)((int64_t)J->n * tid / nt), i1 = (int)((int64_t)J->n * (tid + 1) / nt);
   for (int i = i0; i < i1; ++i) {
     for (uint32_t c = 0; c < dims[0]; ++c) {
@@ -264,17 +274,20 @@ static void mlp_worker(void* arg, int tid, int nt) {
     }
     for (int l = 0; l < J->n_layers; ++l) {
       const uint32_t K = dims[l], N = dims[l + 1];
-      for (uint32_t j = 0; j < N; ++j) {
-        double acc = 0.0;
-        const uint16_t* w = J->W[l] + (size_t)j * K;
-        for (uint32_t c = 0; c < K; ++c) acc += (double)bf16_to_f32(w[c]) * a[c];
-        z[j] = (float)(acc + (double)(J->bias[l] ? J->bias[l][j] : 0.0f));
+      /* acc_j = sum_c W[j][c] * a[c], c ascending, one accumulator per j (Wt is [c][j] so the j loop vectorises;
+       * the per-j summation order is unchanged) */
+      for (uint32_t j = 0; j < N; ++j) acc[j] = 0.0;
+      for (uint32_t c = 0; c < K; ++c) {
+        const double ac = a[c];
+        const double* w = J->Wt[l] + (size_t)c * N;
+        for (uint32_t j = 0; j < N; ++j) acc[j] += w[j] * ac;
       }
       if (l == J->n_layers - 1) {
-        J->logit_out[i] = z[0];
+        J->logit_out[i] = (float)(acc[0] + (double)(J->bias[l] ? J->bias[l][0] : 0.0f));
       } else {
         for (uint32_t j = 0; j < N; ++j) {
-          const float r = z[j] > 0.0f ? z[j] : 0.0f;
+          const float z = (float)(acc[j] + (double)(J->bias[l] ? J->bias[l][j] : 0.0f));
+          const float r = z > 0.0f ? z : 0.0f;
           const float hi = bf16_to_f32(f32_to_bf16(r));
           const float lo = bf16_to_f32(f32_to_bf16(r - hi));
           a[j] = (double)hi + (double)lo;
@@ -283,7 +296,7 @@ static void mlp_worker(void* arg, int tid, int nt) {
     }
   }
   free(a);
-  free(z);
+  free(acc);
 }
 
 ORC_API int orc_mlp_forward(const float* x, int n, int n_layers, const uint32_t* dims, const uint16_t* const* W,
@@ -292,8 +305,17 @@ ORC_API int orc_mlp_forward(const float* x, int n, int n_layers, const uint32_t*
   for (int l = 0; l <= n_layers; ++l)
     if (dims[l] > maxd) maxd = dims[l];
   if (dims[n_layers] != 1) return 1;
-  mlp_job job = {x, n, n_layers, dims, W, bias, logit_out, maxd};
+  double** Wt = (double**)malloc(sizeof(double*) * (size_t)n_layers);
+  for (int l = 0; l < n_layers; ++l) {
+    const uint32_t K = dims[l], N = dims[l + 1];
+    Wt[l] = (double*)malloc(sizeof(double) * (size_t)K * N);
+    for (uint32_t j = 0; j < N; ++j)
+      for (uint32_t c = 0; c < K; ++c) Wt[l][(size_t)c * N + j] = (double)bf16_to_f32(W[l][(size_t)j * K + c]);
+  }
+  mlp_job job = {x, n, n_layers, dims, Wt, bias, logit_out, maxd};
   orc_parallel(n > 256 ? orc_hw_threads() : 1, mlp_worker, &job);
+  for (int l = 0; l < n_layers; ++l) free(Wt[l]);
+  free(Wt);
   return 0;
 }
 

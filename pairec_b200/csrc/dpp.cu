@@ -358,6 +358,9 @@ __global__ void __launch_bounds__(kDppMaxItems, 1) dpp_kernel(const DppArgs a) {
   if (tid == 0) { a.out_n[b] = total; a.status[b] = 0; }
 }
 
+int dpp_cluster_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n,
+                       const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled);
+
 static size_t dpp_smem_bytes(int c_rows, int top_n) {
   return (size_t)c_rows * kDppMaxItems * 8 + 2 * kDppMaxItems * 8 + 520 * 8 + 32 * 8 + 32 * 4 + kDppMaxItems * 4 +
          (size_t)((top_n + 3) & ~3) * 4 + kDppMaxItems + 64;
@@ -378,6 +381,11 @@ int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev,
   int c_rows = p.top_n <= window ? p.top_n : window;
   if (c_rows < 6) c_rows = 6;  // the region doubles as presort staging (4096 x 12 B)
   if (c_rows > 24) return fail(PRG_EUNSUPPORTED, "prg_dpp: window (or top_n when <= window) > 24");
+  if (!h->dpp_generic) {  // fast path: 4-CTA cluster per request, embeddings in registers (dpp_cluster.cu)
+    bool handled = false;
+    PRG_TRY(dpp_cluster_device(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, &handled));
+    if (handled) return PRG_OK;
+  }
   const size_t esz = h->D_dtype == PRG_F64 ? 8 : 4;
   PRG_TRY(h->dpp_scratch.ensure((size_t)B * h->D_dim * kDppMaxItems * esz));
   DppArgs a{};

@@ -53,7 +53,9 @@ struct prg_handle {
   prg::DevBuf q_dev;        // B x dim f32 (host-call staging)
   prg::DevBuf sample_keys;  // QB x sample_slots u64
   prg::DevBuf cand_keys;    // QB x cand_cap u64 (packed candidates)
-  prg::DevBuf seg_keys;     // QB x n_seg x seg_cap u64 (per-CTA candidate segments)
+  prg::DevBuf seg_keys;     // QB x n_seg x seg_cap u64 keys (FFMA2 scan) or u32 rows (tensor-core filter)
+  prg::DevBuf row_norm;     // rows f32: upper bounds of the item row norms (tensor-core filter margin)
+  bool scan_ffma2 = false;  // config "scan_ffma2": use the exact FFMA2 scan for the full pass as well
   prg::DevBuf cand_cnt;     // B u32
   prg::DevBuf tau;          // B u64
   prg::DevBuf dense_keys;   // fallback / small-N: nq x slots u64
@@ -90,6 +92,7 @@ struct prg_handle {
   uint64_t D_rows = 0;
   uint32_t D_dim = 0;
   int D_dtype = PRG_F32;
+  bool dpp_generic = false;  // config "dpp_generic": force the one-CTA-per-request kernel (A/B measurements)
   prg::DevBuf dpp_scratch, dpp_rows, dpp_score, dpp_idx, dpp_n, dpp_status;
 
   // ---- sort

@@ -18,39 +18,9 @@
 // 4-row x 16-query register tile per thread and issue packed FFMA2; the threshold test is fused into the tile
 // epilogue, so the only HBM traffic is the matrix itself (algorithmic bytes = rows*dim*4 per <=64-query block).
 #include "handle.h"
+#include "recall.h"
 
 namespace prg {
-
-constexpr int TM = 4, TQ = 16, WR = 2, WQ = 4;
-constexpr int kTileRows = WR * 32 * TM;              // 256
-constexpr int kQB = WQ * TQ;                         // 64 queries per pass
-constexpr int kConsumerWarps = WR * WQ;              // 8
-constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
-constexpr int kStageFloats = kTileRows * 64;         // one stage = 256 rows x 64 dims
-constexpr int kStageBytes = kStageFloats * 4;        // 64 KiB
-constexpr int kStages = 3;
-constexpr int kSubTileFloats = kTileRows * 32;       // one TMA box: 256 rows x 32 floats (128 B)
-
-enum { SCAN_THRESH = 0, SCAN_DENSE = 1 };
-#ifndef SCAN_UNROLL
-#define SCAN_UNROLL 2
-#endif
-constexpr int kScanUnroll = SCAN_UNROLL;
-
-struct ScanParams {
-  const float* Q;          // [nq][dim]
-  int nq;
-  uint64_t n_rows;         // local rows in the matrix
-  uint64_t row_base;       // global id of local row 0
-  uint32_t n_tiles;        // tiles covered by this launch
-  uint32_t tile_stride;    // launch tile t reads matrix tile t*tile_stride
-  const uint64_t* tau;     // THRESH: [nq]
-  uint64_t* cand;          // THRESH: [nq][gridDim.x][seg_cap] — one private segment per CTA and query
-  uint32_t seg_cap;
-  uint32_t* seg_cnt;       // THRESH: [nq][gridDim.x], written once per CTA at kernel end
-  uint64_t* dense;         // DENSE: [nq][dense_stride], slot = t*256 + r
-  uint64_t dense_stride;
-};
 
 template <int DIM>
 constexpr size_t scan_smem_bytes() {
@@ -242,30 +212,6 @@ recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p)
 }
 
 // ------------------------------------------------------------------ select: exact k-th / sorted top-k of a key list
-struct SelectParams {
-  const uint64_t* keys;    // query q reads keys + q*stride
-  uint64_t stride;
-  const uint32_t* counts;  // per-query list length (nullable -> fixed_m); clamped to cap, overflow flagged
-  uint32_t fixed_m;
-  uint32_t cap;
-  // segmented input (scan<THRESH> output): query q owns n_seg segments of seg_cap keys at keys + (q*n_seg+s)*seg_cap,
-  // lengths seg_counts[q*n_seg+s]; they are first packed into compact + q*stride (cap = stride).
-  const uint32_t* seg_counts;
-  uint32_t n_seg, seg_cap;
-  uint64_t* compact;
-  int k;                   // rank wanted
-  int k_out;               // row stride of the outputs (== caller's k)
-  uint32_t expect;         // MODE_TOPK: number of results that must exist (min(k, total rows)), else flag 2
-  uint64_t* out_keys;      // MODE_TOPK: [q][k_out] sorted descending, 0-padded (nullable)
-  uint32_t* out_row;       // nullable
-  float* out_score;        // nullable
-  int32_t* out_n;          // nullable
-  uint64_t* tau;           // MODE_KTH: [q] the k-th largest key (0 if fewer than k valid keys)
-  int32_t* flags;          // nullable; 0 ok, 1 overflow, 2 underflow
-  uint32_t* max_count;     // nullable: atomicMax of the list lengths seen
-};
-enum { SEL_TOPK = 0, SEL_KTH = 1 };
-
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) select_kernel(const SelectParams p) {
   __shared__ uint32_t hist[256];
@@ -297,11 +243,37 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const SelectParams p) {
     overflow = (s_want != 0u) || m > p.cap;
     if (m > p.cap) m = p.cap;
     uint64_t* dst = p.compact + (size_t)q * p.stride;
-    for (uint32_t sgi = warp; sgi < p.n_seg; sgi += 32) {
-      const uint32_t o = seg_off[sgi], c = seg_off[sgi + 1] - o;
-      const uint64_t* src = p.keys + ((size_t)q * p.n_seg + sgi) * p.seg_cap;
-      for (uint32_t i = lane; i < c; i += 32)
-        if (o + i < p.cap) dst[o + i] = src[i];
+    if (p.seg_rows) {
+      // tensor-core survivors: re-score with the exact fmaf chain of the arithmetic contract (dims ascending, one
+      // accumulator) — the approximate score never reaches the output
+      __shared__ float qv[128];
+      for (uint32_t d = tid; d < p.dim; d += 1024) qv[d] = p.Q[(size_t)q * p.dim + d];
+      __syncthreads();
+      for (uint32_t sgi = warp; sgi < p.n_seg; sgi += 32) {
+        const uint32_t o = seg_off[sgi], c = seg_off[sgi + 1] - o;
+        const uint32_t* src = p.seg_rows + ((size_t)q * p.n_seg + sgi) * p.seg_cap;
+        for (uint32_t i = lane; i < c; i += 32) {
+          if (o + i >= p.cap) break;
+          const uint32_t grow = src[i];
+          const float4* x = reinterpret_cast<const float4*>(p.E + ((size_t)grow - p.row_base) * p.dim);
+          float acc = 0.f;
+          for (uint32_t d4 = 0; d4 < p.dim / 4; ++d4) {
+            const float4 xv = x[d4];
+            acc = __fmaf_rn(xv.x, qv[4 * d4], acc);
+            acc = __fmaf_rn(xv.y, qv[4 * d4 + 1], acc);
+            acc = __fmaf_rn(xv.z, qv[4 * d4 + 2], acc);
+            acc = __fmaf_rn(xv.w, qv[4 * d4 + 3], acc);
+          }
+          dst[o + i] = make_key(acc, grow);
+        }
+      }
+    } else {
+      for (uint32_t sgi = warp; sgi < p.n_seg; sgi += 32) {
+        const uint32_t o = seg_off[sgi], c = seg_off[sgi + 1] - o;
+        const uint64_t* src = p.keys + ((size_t)q * p.n_seg + sgi) * p.seg_cap;
+        for (uint32_t i = lane; i < c; i += 32)
+          if (o + i < p.cap) dst[o + i] = src[i];
+      }
     }
     __syncthreads();
     keys = dst;
@@ -409,7 +381,9 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const SelectParams p) {
   }
   if (tid == 0) {
     if (p.out_n) p.out_n[q] = (int32_t)n_out;
-    if (p.flags) p.flags[q] = overflow ? 1 : (n_out < p.expect ? 2 : 0);
+    int fl = overflow ? 1 : (n_out < p.expect ? 2 : 0);
+    if (!fl && p.tau_check && n_out > 0 && sk[n_out - 1] < p.tau_check[q]) fl = 2;  // a row outside the list could win
+    if (p.flags) p.flags[q] = fl;
   }
 }
 
@@ -515,6 +489,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
 
   // sampling plan: ~1/128 of the tiles, strided across the whole matrix
   uint32_t sample_tiles = 0, tile_stride = 1, r_rank = 0, cand_cap = 0, n_seg = 0, seg_cap = 0;
+  bool use_tc = false;
   if (sampled) {
     sample_tiles = n_tiles / 128;
     if (sample_tiles < 64) sample_tiles = 64;
@@ -532,6 +507,8 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     seg_cap = (seg_cap + 15) & ~15u;
     PRG_TRY(h->cand_keys.ensure((size_t)kQB * cand_cap * 8));
     PRG_TRY(h->seg_keys.ensure((size_t)kQB * n_seg * seg_cap * 8));
+    use_tc = !h->scan_ffma2;
+    if (use_tc && !h->row_norm.p) PRG_TRY(build_row_norms(h));
     PRG_TRY(h->cand_cnt.ensure((size_t)kQB * n_seg * 4 + 4));
     PRG_TRY(h->tau.ensure((size_t)kQB * 8));
     PRG_TRY(h->flags.ensure((size_t)kQB * 4));
@@ -564,12 +541,18 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     sc.n_tiles = n_tiles; sc.tile_stride = 1;
     sc.tau = (const uint64_t*)h->tau.p; sc.cand = (uint64_t*)h->seg_keys.p; sc.seg_cap = seg_cap;
     sc.seg_cnt = (uint32_t*)h->cand_cnt.p;
-    PRG_TRY(scan(h, SCAN_THRESH, sc));
+    sc.row_norm = (const float*)h->row_norm.p; sc.cand_rows = (uint32_t*)h->seg_keys.p;
+    if (use_tc) PRG_TRY(launch_scan_tc(h, sc));
+    else PRG_TRY(scan(h, SCAN_THRESH, sc));
     // 4. exact top-k of the candidates
     SelectParams se{};
     se.keys = (const uint64_t*)h->seg_keys.p; se.stride = cand_cap; se.counts = nullptr;
     se.seg_counts = (const uint32_t*)h->cand_cnt.p; se.n_seg = n_seg; se.seg_cap = seg_cap;
     se.compact = (uint64_t*)h->cand_keys.p;
+    if (use_tc) {
+      se.seg_rows = (const uint32_t*)h->seg_keys.p; se.E = h->E; se.Q = qb; se.dim = dim; se.row_base = h->E_row_base;
+      se.tau_check = (const uint64_t*)h->tau.p;
+    }
     se.cap = cand_cap; se.k = k; se.k_out = k;
     se.expect = (uint32_t)((uint64_t)k < h->E_rows ? (uint64_t)k : h->E_rows);
     se.out_keys = kout; se.flags = (int32_t*)h->flags.p;

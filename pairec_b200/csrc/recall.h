@@ -1,0 +1,77 @@
+// recall.h — constants and parameter blocks shared by recall.cu (FFMA2 exact scan, select) and recall_tc.cu
+// (tensor-core candidate filter).
+#pragma once
+#include "handle.h"
+
+namespace prg {
+
+constexpr int TM = 4, TQ = 16, WR = 2, WQ = 4;
+constexpr int kTileRows = WR * 32 * TM;              // 256
+constexpr int kQB = WQ * TQ;                         // 64 queries per pass
+constexpr int kConsumerWarps = WR * WQ;              // 8
+constexpr int kScanThreads = (kConsumerWarps + 1) * 32;
+constexpr int kStageFloats = kTileRows * 64;         // one stage = 256 rows x 64 dims
+constexpr int kStageBytes = kStageFloats * 4;        // 64 KiB
+constexpr int kStages = 3;
+constexpr int kSubTileFloats = kTileRows * 32;       // one TMA box: 256 rows x 32 floats (128 B)
+
+enum { SCAN_THRESH = 0, SCAN_DENSE = 1 };
+#ifndef SCAN_UNROLL
+#define SCAN_UNROLL 2
+#endif
+constexpr int kScanUnroll = SCAN_UNROLL;
+
+struct ScanParams {
+  const float* Q;          // [nq][dim]
+  int nq;
+  uint64_t n_rows;         // local rows in the matrix
+  uint64_t row_base;       // global id of local row 0
+  uint32_t n_tiles;        // tiles covered by this launch
+  uint32_t tile_stride;    // launch tile t reads matrix tile t*tile_stride
+  const uint64_t* tau;     // THRESH: [nq]
+  uint64_t* cand;          // THRESH: [nq][gridDim.x][seg_cap] — one private segment per CTA and query
+  uint32_t seg_cap;
+  uint32_t* seg_cnt;       // THRESH: [nq][gridDim.x], written once per CTA at kernel end
+  const float* row_norm;   // TC filter: [n_rows] upper bounds of the row norms
+  uint32_t* cand_rows;     // TC filter: [nq][gridDim.x][seg_cap] surviving global rows (re-scored exactly by select)
+  uint64_t* dense;         // DENSE: [nq][dense_stride], slot = t*256 + r
+  uint64_t dense_stride;
+};
+
+struct SelectParams {
+  const uint64_t* keys;    // query q reads keys + q*stride
+  uint64_t stride;
+  const uint32_t* counts;  // per-query list length (nullable -> fixed_m); clamped to cap, overflow flagged
+  uint32_t fixed_m;
+  uint32_t cap;
+  // segmented input (scan<THRESH> output): query q owns n_seg segments of seg_cap keys at keys + (q*n_seg+s)*seg_cap,
+  // lengths seg_counts[q*n_seg+s]; they are first packed into compact + q*stride (cap = stride).
+  const uint32_t* seg_counts;
+  uint32_t n_seg, seg_cap;
+  uint64_t* compact;
+  // exact re-score of tensor-core survivors while packing: segments hold u32 global rows instead of keys
+  const uint32_t* seg_rows;
+  const float* E;          // item matrix (local rows)
+  const float* Q;          // [nq][dim]
+  uint32_t dim;
+  uint64_t row_base;
+  const uint64_t* tau_check;  // per-query sampled threshold: the k-th exact key must reach it (else flag 2)
+  int k;                   // rank wanted
+  int k_out;               // row stride of the outputs (== caller's k)
+  uint32_t expect;         // MODE_TOPK: number of results that must exist (min(k, total rows)), else flag 2
+  uint64_t* out_keys;      // MODE_TOPK: [q][k_out] sorted descending, 0-padded (nullable)
+  uint32_t* out_row;       // nullable
+  float* out_score;        // nullable
+  int32_t* out_n;          // nullable
+  uint64_t* tau;           // MODE_KTH: [q] the k-th largest key (0 if fewer than k valid keys)
+  int32_t* flags;          // nullable; 0 ok, 1 overflow, 2 underflow
+  uint32_t* max_count;     // nullable: atomicMax of the list lengths seen
+};
+enum { SEL_TOPK = 0, SEL_KTH = 1 };
+
+
+// recall_tc.cu
+int launch_scan_tc(prg_handle* h, const ScanParams& p);
+int build_row_norms(prg_handle* h);
+
+}  // namespace prg

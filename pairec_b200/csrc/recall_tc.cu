@@ -1,0 +1,260 @@
+// recall_tc.cu — tensor-core candidate filter for the recall scan: moves the full-matrix pass
+// from the FP32-issue limit (recall.cu, 64 queries/pass: 81.9 GFLOP of FFMA2 per 2.56 GB) to the HBM roofline while
+// the RESULT stays bit-exact.
+//
+//   filter (this kernel):  approx(row,q) = TF32 tcgen05.mma of the item tile against the query block, fp32 accum in
+//                          TMEM; a row is kept for query q unless  approx < tau_f[q] - c*||x_row||*||q||,  where
+//                          tau_f is the exact sampled threshold (recall.cu steps 1-2), ||x_row|| a precomputed upper
+//                          bound of the row norm and c = 1.05 * 2^-9 bounds |approx - exact| (two TF32 operand
+//                          truncations of <= 2^-10 each, Cauchy-Schwarz, fp32 accumulation slack).  Every row whose
+//                          EXACT key reaches tau therefore survives; a few percent extra rows survive too.
+//   refine (select_kernel): survivors (~4.5k rows per query) are re-scored with the exact fmaf chain of the arithmetic
+//                          contract while they are packed, then the exact radix select / sort runs as before, and
+//                          the k-th exact key is checked against tau (else the query falls back to the dense path).
+//
+// Structure: persistent, one CTA per SM, 10 warps: warp 0 = TMA producer (same 256-row x 64-dim SWIZZLE_128B stages
+// as the FFMA2 scan — the fp32 rows are consumed by kind::tf32 as they lie in HBM, no conversion pass), warp 1 = TMEM
+// allocator + the single MMA-issuing thread (M=128, N=64, K=8; two 128-row halves per stage, accumulators double
+// buffered in 256 TMEM columns), warps 2-9 = epilogue (tcgen05.ld 32x32b.x32 -> 64 FFMA + 64 FSETP per row).
+// Survivor rows go to the per-CTA, per-query segments with one shared-memory atomic + one store.
+#include "recall.h"
+
+namespace prg {
+
+constexpr int kTcThreads = 320;
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcStages = 3;
+constexpr float kTcMargin = 1.05f / 512.f;  // c = 1.05 * 2^-9
+
+template <int DIM>
+constexpr size_t scan_tc_smem_bytes() {
+  return (size_t)kTcStages * kStageBytes + (size_t)DIM * kQB * 4 /*Q operand*/ + 3 * kQB * 4 /*tauf, qn, s_cnt*/ +
+         (2 * kTcStages + 4) * 8 + 16;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kTcThreads, 1)
+recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int KH = DIM / 64;
+  float* stage_base = reinterpret_cast<float*>(smem);
+  float* Qb = reinterpret_cast<float*>(smem + (size_t)kTcStages * kStageBytes);  // B operand: [DIM/32][64 q][32] swizzled
+  float2* tq = reinterpret_cast<float2*>(Qb + DIM * kQB);  // [64] {tau_f, c*||q||}
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tq + kQB);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + kQB);
+  uint64_t* empty = full + kTcStages;
+  uint64_t* tfull = empty + kTcStages;   // [2] accumulator buffer ready
+  uint64_t* tempty = tfull + 2;          // [2] accumulator buffer drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // query block -> K-major SWIZZLE_128B B operand; padded queries are zero rows
+  for (int i = tid; i < DIM * kQB; i += kTcThreads) {
+    const int q = i / DIM, dd = i - q * DIM;
+    const float v = (q < p.nq) ? p.Q[(size_t)q * DIM + dd] : 0.f;
+    const int sub = dd >> 5, ch = (dd & 31) >> 2;
+    Qb[sub * (kQB * 32) + q * 32 + ((ch ^ (q & 7)) << 2) + (dd & 3)] = v;
+  }
+  if (tid < kQB) {
+    float tf = __int_as_float(0x7F800000), nq2 = 0.f;
+    if (tid < p.nq) {
+      const uint64_t t = p.tau[tid];
+      tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
+      float ss = 0.f;
+      for (int dd = 0; dd < DIM; ++dd) { const float v = p.Q[(size_t)tid * DIM + dd]; ss = fmaf(v, v, ss); }
+      nq2 = sqrtf(ss) * 1.0001f * kTcMargin;
+    }
+    tq[tid] = make_float2(tf, nq2);
+    s_cnt[tid] = 0;
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&emap);
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kTcEpiWarps); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // the generic-proxy writes of Qb must be visible to the tensor core (async proxy) before the first MMA
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (uint32_t i = 0; i < my_tiles; ++i) {
+        const uint32_t t = blockIdx.x + i * gridDim.x;
+        const int row0 = (int)(t * p.tile_stride * (uint32_t)kTileRows);
+        for (int h = 0; h < KH; ++h, ++it) {
+          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          float* dst = stage_base + (size_t)s * kStageFloats;
+          tma_load_2d(dst, &emap, h * 64, row0, &full[s], kEvictFirst);
+          tma_load_2d(dst + kSubTileFloats, &emap, h * 64 + 32, row0, &full[s], kEvictFirst);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      // D=f32, A=B=tf32, both K-major, N=64, M=128
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kQB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t qb_addr = smem_u32(Qb);
+      uint32_t it = 0;
+      for (uint32_t i = 0; i < my_tiles; ++i) {
+        const uint32_t buf = i & 1u;
+        mbar_wait(&tempty[buf], ((i >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        for (int h = 0; h < KH; ++h, ++it) {
+          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st_addr = smem_u32(stage_base + (size_t)s * kStageFloats);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t d_addr = tmem_base + buf * 128u + (uint32_t)half * 64u;
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kSubTileFloats * 4) + (uint32_t)half * (128 * 128));
+              const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)(h * 2 + sub) * (kQB * 128));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 B -> +2 in 16-B units
+                umma_tf32(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                          (h | sub | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: 8 warps, 256 rows
+    const int ew = warp - 2;
+    const int half = ew >> 2, quarter = warp & 3;  // TMEM lanes [32*(warp%4), +32) of half-tile `half`
+    const int row_local = half * 128 + quarter * 32 + lane;
+    for (uint32_t i = 0; i < my_tiles; ++i) {
+      const uint32_t buf = i & 1u;
+      const uint32_t t = blockIdx.x + i * gridDim.x;
+      const uint64_t lrow = (uint64_t)t * p.tile_stride * kTileRows + (uint64_t)row_local;
+      const bool valid = lrow < p.n_rows;
+      const float nr = valid ? p.row_norm[lrow] : 0.f;
+      mbar_wait(&tfull[buf], (i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128u + (uint32_t)half * 64u;
+      uint32_t v0[32], v1[32];
+      tmem_ld32(taddr, v0);
+      tmem_ld32(taddr + 32u, v1);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);  // accumulators are in registers: the MMA warp may overwrite them
+      // thresholds are re-read from shared memory per tile (volatile: keeping 128 loop-invariant values live would
+      // spill); thr_q = tau_f[q] - ||x_row|| * c*||q||
+      const volatile float4* tq4 = reinterpret_cast<const volatile float4*>(tq);
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < 32; q += 2) {
+        const float4 a4 = make_float4(tq4[q >> 1].x, tq4[q >> 1].y, tq4[q >> 1].z, tq4[q >> 1].w);
+        const float4 b4 = make_float4(tq4[16 + (q >> 1)].x, tq4[16 + (q >> 1)].y, tq4[16 + (q >> 1)].z, tq4[16 + (q >> 1)].w);
+        any |= !(__uint_as_float(v0[q]) < fmaf(-nr, a4.y, a4.x));
+        any |= !(__uint_as_float(v0[q + 1]) < fmaf(-nr, a4.w, a4.z));
+        any |= !(__uint_as_float(v1[q]) < fmaf(-nr, b4.y, b4.x));
+        any |= !(__uint_as_float(v1[q + 1]) < fmaf(-nr, b4.w, b4.z));
+      }
+      if (any && valid) {
+        const uint32_t grow = (uint32_t)(p.row_base + lrow);
+        const volatile float2* tqv = reinterpret_cast<const volatile float2*>(tq);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          if (q < p.nq && !(__uint_as_float(v0[q]) < fmaf(-nr, tqv[q].y, tqv[q].x))) {
+            const uint32_t pos = atomicAdd(&s_cnt[q], 1u);
+            if (pos < p.seg_cap) p.cand_rows[((size_t)q * gridDim.x + blockIdx.x) * p.seg_cap + pos] = grow;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          if (q + 32 < p.nq && !(__uint_as_float(v1[q]) < fmaf(-nr, tqv[q + 32].y, tqv[q + 32].x))) {
+            const uint32_t pos = atomicAdd(&s_cnt[q + 32], 1u);
+            if (pos < p.seg_cap) p.cand_rows[((size_t)(q + 32) * gridDim.x + blockIdx.x) * p.seg_cap + pos] = grow;
+          }
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
+    if (tid - 64 < p.nq) p.seg_cnt[(size_t)(tid - 64) * gridDim.x + blockIdx.x] = s_cnt[tid - 64];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+  }
+}
+
+// upper bounds of the row norms: sqrt in fp64, inflated, rounded up to f32
+__global__ void row_norm_kernel(const float* __restrict__ E, uint64_t rows, int dim, float* __restrict__ out) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float4* x = reinterpret_cast<const float4*>(E + r * dim);
+  double ss = 0.0;
+  for (int i = 0; i < dim / 4; ++i) {
+    const float4 v = x[i];
+    ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  float f = (float)(sqrt(ss) * (1.0 + 1e-6));
+  f = (f == f && f < __int_as_float(0x7F800000)) ? __uint_as_float(__float_as_uint(f) + 1u) : __int_as_float(0x7F800000);
+  out[r] = f;  // NaN / inf rows get +inf: they always survive the filter and are settled by the exact re-score
+}
+
+int build_row_norms(prg_handle* h) {
+  PRG_TRY(h->row_norm.ensure((size_t)h->E_rows * 4));
+  const unsigned grid = (unsigned)((h->E_rows + 255) / 256);
+  row_norm_kernel<<<grid, 256, 0, h->stream>>>(h->E, h->E_rows, (int)h->E_dim, (float*)h->row_norm.p);
+  PRG_CUDA(cudaGetLastError());
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  count_launch(h);
+  return PRG_OK;
+}
+
+template <int DIM>
+static int launch_tc(prg_handle* h, const ScanParams& p) {
+  const size_t smem = scan_tc_smem_bytes<DIM>();
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.n_tiles == 0) return PRG_OK;
+  StageScope span(h, ST_SCAN);
+  const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
+  recall_scan_tc_kernel<DIM><<<grid, kTcThreads, smem, h->stream>>>(h->E_map, p);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+int launch_scan_tc(prg_handle* h, const ScanParams& p) {
+  if (h->E_dim == 64) return launch_tc<64>(h, p);
+  if (h->E_dim == 128) return launch_tc<128>(h, p);
+  return fail(PRG_EUNSUPPORTED, "item matrix dim must be 64 or 128");
+}
+
+}  // namespace prg

@@ -86,3 +86,28 @@ def test_errors_do_not_abort(engine):
     from pairec_b200 import PrgError
     with pytest.raises(PrgError):
         engine.set_item_matrix(np.zeros((10, 48), dtype=np.float32))  # unsupported dim
+
+
+def test_exact_ffma2_scan_path_matches_oracle(oracle_lib):
+    # the full pass through the exact FFMA2 scan (config scan_ffma2) instead of the tensor-core filter + re-score
+    from pairec_b200 import Engine
+    eng = Engine(0, scan_ffma2=1)
+    try:
+        E, Q = _data(500_000, 64, 33, seed=21)
+        _check(eng, oracle_lib, E, Q, 500)
+        assert eng.recall_stats()["fallback_queries"] == 0
+    finally:
+        eng.close()
+
+
+def test_filter_margin_holds_for_scaled_rows(engine, oracle_lib):
+    # rows with very different norms (1e-3 .. 1e3): the TF32 filter margin is per row, the result stays exact
+    E, Q = _data(400_000, 64, 8, seed=23)
+    rng = np.random.default_rng(5)
+    E *= (10.0 ** rng.uniform(-3, 3, size=(E.shape[0], 1))).astype(np.float32)
+    _check(engine, oracle_lib, E, Q, 300)
+
+
+def test_dim128_sampled_path(engine, oracle_lib):
+    E, Q = _data(300_000, 128, 64, seed=29)
+    _check(engine, oracle_lib, E, Q, 1000)

@@ -73,3 +73,21 @@ def test_dpp_all_zero_scores_is_flagged(engine, oracle_lib):
     score = np.zeros((1, 100))
     idx, cnt, st = engine.dpp(rows, score, DppParams(top_n=10, norm_mode=1))
     assert st[0] == 1    # "all item score is zero": caller keeps the items unchanged (dpp_sort.go:385-388)
+
+
+def test_dpp_generic_kernel_still_matches(oracle_lib):
+    # the one-CTA-per-request kernel (any dim, f64 tables) behind config dpp_generic
+    from pairec_b200 import Engine
+    eng = Engine(0, dpp_generic=1)
+    try:
+        _dpp_case(eng, oracle_lib, n=700, dim=128, top_n=30, alpha=1.0, window_size=10)
+        _dpp_case(eng, oracle_lib, n=200, dim=24, top_n=12, alpha=1.0, window_size=5)
+    finally:
+        eng.close()
+
+
+def test_dpp_cluster_dims(engine, oracle_lib):
+    for dim in (32, 64, 128):
+        _dpp_case(engine, oracle_lib, n=1000, dim=dim, top_n=50, alpha=1.0, window_size=10)
+    _dpp_case(engine, oracle_lib, n=1024, dim=64, top_n=24, alpha=0.7, window_size=24)
+    _dpp_case(engine, oracle_lib, n=5, dim=32, top_n=3, alpha=1.0, window_size=10)

@@ -10,7 +10,7 @@ torch.manual_seed(2)
 dev = torch.device("cuda:0")
 E = torch.randn(N, D, device=dev) / D ** 0.5
 Q = torch.randn(B, D, device=dev) / D ** 0.5
-eng = Engine(0)
+eng = Engine(0, scan_ffma2=int(os.environ.get('FFMA2', 0)))
 eng.set_item_matrix(E.data_ptr(), rows=N, dim=D, mem=MEM_DEVICE)
 rows = torch.empty(B, K, dtype=torch.int32, device=dev); sc = torch.empty(B, K, device=dev); n = torch.empty(B, dtype=torch.int32, device=dev)
 for _ in range(3):
