@@ -1,0 +1,166 @@
+// host_capi.cpp — C ABI over the host mirror so that tests (ctypes) can drive it the way /api/recommend drives the
+// reference: one recconf JSON in, RecommendParam JSON in, RecommendResponse JSON out
+// (web/recommend_controller.go:24-31,51-60,112-157).  "score" is added to each item for the parity checks.
+#include <cstring>
+
+#include "pairec_host.hpp"
+
+using namespace pairec;
+
+namespace {
+thread_local std::string g_err;
+struct UserVectors : recall::VectorDao {
+  std::map<std::string, std::string> m;
+  Error VectorString(const std::string& id, std::string* out) override {
+    auto it = m.find(id);
+    if (it == m.end()) return recall::VectoryEmptyError;
+    *out = it->second;
+    return "";
+  }
+};
+}  // namespace
+
+struct ph_server {
+  recconf::RecommendConfig conf;
+  std::shared_ptr<GpuCatalog> catalog = std::make_shared<GpuCatalog>();
+  std::map<std::string, std::vector<module::ItemPtr>> context_items;  // recall name -> items
+  std::shared_ptr<UserVectors> vectors = std::make_shared<UserVectors>();
+  uint64_t next_id = 1;
+};
+
+extern "C" {
+
+const char* ph_last_error(void) { return g_err.c_str(); }
+
+int ph_create(const char* recconf_json, ph_server** out) {
+  if (!recconf_json || !out) { g_err = "null argument"; return 1; }
+  auto* s = new ph_server();
+  Error e = recconf::LoadConfig(recconf_json, &s->conf);
+  if (!e.empty()) { g_err = e; delete s; return 1; }
+  ResetRegistries();
+  algorithm::Load(s->conf);   // pairec.go:88-109 runBeforeStart order: algorithm.Load, then register(conf)
+  recall::Load(s->conf);
+  sort::Load(s->conf);
+  *out = s;
+  return 0;
+}
+void ph_destroy(ph_server* s) { delete s; }
+
+int ph_attach_engine(ph_server* s, void* prg) {
+  if (!s) { g_err = "null server"; return 1; }
+  s->catalog->h = static_cast<prg_handle*>(prg);
+  return 0;
+}
+int ph_set_catalog_ids(ph_server* s, const char* const* ids, uint64_t n) {
+  if (!s || (!ids && n)) { g_err = "null argument"; return 1; }
+  std::vector<std::string> v;
+  v.reserve(n);
+  for (uint64_t i = 0; i < n; ++i) v.emplace_back(ids[i]);
+  s->catalog->SetIds(std::move(v));
+  return 0;
+}
+// items of an in-memory recall (config 1); properties_json = {"score": 0.3, "brand": "x", ...}
+int ph_add_context_item(ph_server* s, const char* recall_name, const char* item_id, double score, const char* properties_json) {
+  if (!s || !recall_name || !item_id) { g_err = "null argument"; return 1; }
+  auto item = module::NewItem(item_id);
+  item->Score = score;
+  if (properties_json && *properties_json) {
+    Json j;
+    std::string err;
+    if (!Json::parse(properties_json, &j, &err) || j.type != Json::Object) { g_err = "bad properties JSON: " + err; return 1; }
+    for (auto& kv : j.obj) {
+      if (kv.second.type == Json::Number) {
+        if (kv.second.is_int) item->Properties[kv.first] = (int64_t)kv.second.num;
+        else item->Properties[kv.first] = kv.second.num;
+      } else if (kv.second.type == Json::String) item->Properties[kv.first] = kv.second.str;
+    }
+  }
+  s->context_items[recall_name].push_back(item);
+  return 0;
+}
+// makes the in-memory recalls and the sort strategies visible (call after the items are added)
+int ph_commit(ph_server* s) {
+  if (!s) { g_err = "null server"; return 1; }
+  for (auto& kv : s->context_items)
+    recall::RegisterRecall(kv.first, std::make_shared<recall::ContextItemRecall>(kv.first, kv.second));
+  sort::Load(s->conf);
+  return 0;
+}
+// GPU plugins, registered the way a user start hook would (pairec.go:58): names must match the recconf
+int ph_register_gpu_plugins(ph_server* s, const char* recall_algo, const char* rank_algo, int model, const char* dpp_sort) {
+  if (!s || !s->catalog->h) { g_err = "no engine attached"; return 1; }
+  if (recall_algo && *recall_algo)
+    algorithm::RegisterAlgorithm(recall_algo, std::make_shared<algorithm::GpuVectorAlgorithm>(s->catalog));
+  if (rank_algo && *rank_algo)
+    algorithm::RegisterAlgorithm(rank_algo, std::make_shared<algorithm::GpuRankAlgorithm>(s->catalog, model));
+  if (dpp_sort && *dpp_sort) {
+    recconf::DPPSortConfig dc;
+    dc.Alpha = 1.0;
+    for (auto& sc : s->conf.SortConfs)
+      if (sc.Name == dpp_sort) dc = sc.DPPConf;
+    sort::RegisterSort(dpp_sort, std::make_shared<sort::GpuDPPSort>(dc, s->catalog));
+  }
+  for (auto& rc : s->conf.RecallConfs)
+    if (rc.RecallType == "VectorRecall") recall::RegisterRecall(rc.Name, std::make_shared<recall::VectorRecall>(rc, s->vectors));
+  sort::Load(s->conf);
+  return 0;
+}
+int ph_set_user_vector(ph_server* s, const char* uid, const char* vector_string) {
+  if (!s || !uid || !vector_string) { g_err = "null argument"; return 1; }
+  s->vectors->m[uid] = vector_string;
+  return 0;
+}
+
+// POST /api/recommend body -> response body.  Returns the number of bytes needed (incl. NUL); writes when it fits.
+long long ph_recommend(ph_server* s, const char* request_json, char* out, unsigned long long cap) {
+  if (!s || !request_json) { g_err = "null argument"; return -1; }
+  Json req;
+  std::string err;
+  if (!Json::parse(request_json, &req, &err)) { g_err = "bad request JSON: " + err; return -1; }
+  context::RecommendContext ctx;
+  ctx.Config = &s->conf;
+  ctx.RecommendId = "req-" + std::to_string(s->next_id++);
+  ctx.Size = req["size"].as_int(10);  // Default_Size (recommend_controller.go:20-22)
+  if (ctx.Size <= 0) ctx.Size = 10;
+  ctx.Debug = req["debug"].as_bool(false);
+  ctx.Param["scene"] = req["scene_id"].as_string();
+  ctx.Param["category"] = req["category"].as_string().empty() ? "default" : req["category"].as_string();
+  module::User user;
+  user.Id = req["uid"].as_string();
+  for (auto& kv : req["features"].obj) {
+    if (kv.second.type == Json::Number) user.Properties[kv.first] = kv.second.num;
+    else if (kv.second.type == Json::String) user.Properties[kv.first] = kv.second.str;
+  }
+  auto items = service::Recommend(&user, &ctx);
+  std::string o = "{\"request_id\":" + Json::quote(ctx.RecommendId);
+  if ((int)items.size() < ctx.Size) o += ",\"code\":299,\"msg\":\"items size not enough\"";
+  else o += ",\"code\":200,\"msg\":\"success\"";
+  o += ",\"size\":" + std::to_string(items.size()) + ",\"items\":[";
+  for (size_t i = 0; i < items.size(); ++i) {
+    if (i) o += ",";
+    o += "{\"item_id\":" + Json::quote(items[i]->Id) + ",\"item_type\":" + Json::quote(items[i]->ItemType) +
+         ",\"retrieve_id\":" + Json::quote(items[i]->RetrieveId) + ",\"score\":" + Json::number(items[i]->Score) + "}";
+  }
+  o += "],\"log\":[";
+  for (size_t i = 0; i < ctx.Log.size(); ++i) { if (i) o += ","; o += Json::quote(ctx.Log[i]); }
+  o += "]}";
+  const long long need = (long long)o.size() + 1;
+  if (out && cap >= (unsigned long long)need) memcpy(out, o.c_str(), (size_t)need);
+  return need;
+}
+
+// utils/ast known-answer entry: evaluates an expression over named values (names[i] -> values[i])
+int ph_eval_expr(const char* expr, const char* const* names, const double* values, int n, double* out) {
+  std::shared_ptr<ast::Expr> e;
+  Error er = ast::Parse(expr ? expr : "", &e);
+  if (!er.empty()) { g_err = er; return 1; }
+  er = ast::Eval(*e, [&](const std::string& nm, double* o) {
+    for (int i = 0; i < n; ++i)
+      if (nm == names[i]) { *o = values[i]; return true; }
+    return false;
+  }, out);
+  if (!er.empty()) { g_err = er; return 1; }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,713 @@
+// pairec_host.cpp — implementation of the host-side mirror declared in pairec_host.hpp.
+#include "pairec_host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+
+namespace pairec {
+
+// ================================================================================================ recconf
+namespace recconf {
+static std::vector<std::string> str_list(const Json& j) {
+  std::vector<std::string> v;
+  if (j.type == Json::Array)
+    for (auto& e : j.arr)
+      if (e.type == Json::String) v.push_back(e.str);
+  return v;
+}
+Error LoadConfig(const std::string& json, RecommendConfig* out) {
+  Json root;
+  std::string err;
+  if (!Json::parse(json, &root, &err)) return "invalid recconf JSON: " + err;
+  if (root.type != Json::Object) return "recconf JSON must be an object";
+  *out = RecommendConfig();
+  out->RunMode = root["RunMode"].as_string();
+  for (auto& a : root["AlgoConfs"].arr) {
+    AlgoConfig c;
+    c.Name = a["Name"].as_string();
+    c.Type = a["Type"].as_string();
+    c.LookupConf.FieldName = a["LookupConf"]["FieldName"].as_string();
+    out->AlgoConfs.push_back(c);
+  }
+  for (auto& r : root["RecallConfs"].arr) {
+    RecallConfig c;
+    c.Name = r["Name"].as_string();
+    c.RecallType = r["RecallType"].as_string();
+    c.RecallAlgo = r["RecallAlgo"].as_string();
+    c.ItemType = r["ItemType"].as_string();
+    c.RecallCount = r["RecallCount"].as_int();
+    out->RecallConfs.push_back(c);
+  }
+  for (auto& sc : root["SceneConfs"].obj)
+    for (auto& cat : sc.second.obj) out->SceneConfs[sc.first][cat.first].RecallNames = str_list(cat.second["RecallNames"]);
+  for (auto& rc : root["RankConf"].obj) {
+    RankConfig c;
+    c.RankAlgoList = str_list(rc.second["RankAlgoList"]);
+    c.RankScore = rc.second["RankScore"].as_string();
+    c.Processor = rc.second["Processor"].as_string();
+    c.BatchCount = rc.second["BatchCount"].as_int();
+    out->RankConf[rc.first] = c;
+  }
+  for (auto& s : root["SortNames"].obj) out->SortNames[s.first] = str_list(s.second);
+  for (auto& s : root["FilterNames"].obj) out->FilterNames[s.first] = str_list(s.second);
+  for (auto& s : root["SortConfs"].arr) {
+    SortConfig c;
+    c.Name = s["Name"].as_string();
+    c.SortType = s["SortType"].as_string();
+    c.SortByField = s["SortByField"].as_string();
+    c.SwitchThreshold = s["SwitchThreshold"].as_number();
+    const Json& d = s["DPPConf"];
+    c.DPPConf.Name = d["Name"].as_string();
+    c.DPPConf.Alpha = d["Alpha"].as_number();
+    c.DPPConf.WindowSize = d["WindowSize"].as_int();
+    c.DPPConf.AbortRunCount = d["AbortRunCount"].as_int();
+    c.DPPConf.CandidateCount = d["CandidateCount"].as_int();
+    c.DPPConf.MinScorePercent = d["MinScorePercent"].as_number();
+    c.DPPConf.NormalizeEmb = d["NormalizeEmb"].as_string();
+    c.DPPConf.EnsurePositiveSim = d["EnsurePositiveSim"].as_string();
+    c.DPPConf.FilterRetrieveIds = str_list(d["FilterRetrieveIds"]);
+    out->SortConfs.push_back(c);
+  }
+  out->UserDefineConfs = root["UserDefineConfs"];
+  return "";
+}
+}  // namespace recconf
+
+// ================================================================================================ module
+namespace module {
+double ToFloat(const Value& v, double def) {
+  if (auto p = std::get_if<double>(&v)) return *p;
+  if (auto p = std::get_if<int64_t>(&v)) return (double)*p;
+  if (auto p = std::get_if<std::string>(&v)) {
+    char* end = nullptr;
+    const double d = strtod(p->c_str(), &end);
+    return (end && *end == 0 && end != p->c_str()) ? d : def;
+  }
+  return def;
+}
+ItemPtr NewItem(const std::string& id) { return std::make_shared<Item>(id); }
+void Item::AddProperty(const std::string& k, Value v) {
+  std::lock_guard<std::mutex> g(mutex);
+  Properties[k] = std::move(v);
+}
+void Item::AddAlgoScore(const std::string& name, double score) {
+  std::lock_guard<std::mutex> g(mutex);
+  algoScores[name] = score;
+}
+Features Item::GetFeatures() {
+  std::lock_guard<std::mutex> g(mutex);
+  if (!RetrieveId.empty() && !Properties.count(RetrieveId)) {  // module/item.go:233-239
+    Properties[RetrieveId] = Score;
+    Properties["recall_name"] = RetrieveId;
+    Properties["recall_score"] = Score;
+  }
+  return Properties;
+}
+Error Item::FloatExprData(const std::string& name, double* out) {
+  std::lock_guard<std::mutex> g(mutex);
+  if (name == "current_score") {  // :190-198
+    algoScores["recall_score"] = Score;
+    *out = Score;
+    return "";
+  }
+  auto it = algoScores.find(name);
+  if (it != algoScores.end()) { *out = it->second; return ""; }
+  auto pt = Properties.find(name);
+  if (pt != Properties.end()) { *out = ToFloat(pt->second, 0); return ""; }
+  *out = 0;
+  return "not found,name:" + name;
+}
+}  // namespace module
+
+// ================================================================================================ algorithm
+namespace algorithm {
+namespace {
+struct ScoreResponse : response::AlgoResponse {
+  double score;
+  explicit ScoreResponse(double s) : score(s) {}
+  double GetScore() const override { return score; }
+};
+}  // namespace
+
+AlgorithmFactory& Factory() {
+  static AlgorithmFactory f;
+  return f;
+}
+void AlgorithmFactory::Init(const std::vector<recconf::AlgoConfig>& confs) {
+  std::unique_lock<std::shared_mutex> g(mutex_);
+  for (auto& conf : confs) {
+    std::shared_ptr<IAlgorithm> algo;
+    if (conf.Type == "LOOKUP") algo = std::make_shared<LookupPolicy>();
+    else continue;  // EAS / FAISS / TFSERVING / SELDON are the remote backends this repo replaces; GPU algos register in code
+    if (algo->Init(&conf).empty()) algorithms_[conf.Name] = algo;
+  }
+}
+Error AlgorithmFactory::Run(const std::string& name, const AlgoData& data, AlgoResult* out) {
+  std::shared_ptr<IAlgorithm> algo;
+  {
+    std::shared_lock<std::shared_mutex> g(mutex_);
+    auto it = algorithms_.find(name);
+    if (it != algorithms_.end()) algo = it->second;
+  }
+  if (!algo) return "not found algorithm, name:" + name;  // algorithm/algorithm.go:113
+  return algo->Run(data, out);
+}
+void AlgorithmFactory::RegisterAlgorithm(const std::string& name, std::shared_ptr<IAlgorithm> a) {
+  std::unique_lock<std::shared_mutex> g(mutex_);
+  algorithms_[name] = std::move(a);
+}
+
+Error LookupPolicy::Init(const recconf::AlgoConfig* conf) {
+  conf_ = conf->LookupConf;
+  return "";
+}
+Error LookupPolicy::Run(const AlgoData& algoData, AlgoResult* out) {
+  auto pp = std::get_if<const FeatureList*>(&algoData);
+  if (!pp || !*pp) return "LookupPolicy: algoData is not []map[string]interface{}";
+  const FeatureList& list = **pp;
+  if (list.empty()) { *out = std::monostate{}; return ""; }  // algorithm/lookup.go:39-41 returns nil, nil
+  AlgoResponses res(list.size());
+  for (size_t i = 0; i < list.size(); ++i) {
+    auto it = list[i].find(conf_.FieldName);
+    if (it == list[i].end()) { res[i] = std::make_shared<ScoreResponse>(0.5); continue; }  // :47-49
+    auto d = std::get_if<double>(&it->second);
+    if (!d) return "LookupPolicy: field " + conf_.FieldName + " is not float64";  // the reference panics (:45)
+    res[i] = std::make_shared<ScoreResponse>(*d);
+  }
+  *out = std::move(res);
+  return "";
+}
+
+Error GpuVectorAlgorithm::Run(const AlgoData& algoData, AlgoResult* out) {
+  auto pp = std::get_if<const pai_web::VectorRequest*>(&algoData);
+  if (!pp || !*pp) return "GpuVectorAlgorithm: algoData is not *pai_web.VectorRequest";
+  const pai_web::VectorRequest& req = **pp;
+  if (req.K == 0 || req.Vector.empty()) return "GpuVectorAlgorithm: empty request";
+  const int k = (int)req.K;
+  std::vector<uint32_t> rows((size_t)k);
+  std::vector<float> scores((size_t)k);
+  int32_t n = 0;
+  if (prg_recall_topk(cat_->h, req.Vector.data(), 1, k, rows.data(), scores.data(), &n, PRG_MEM_HOST) != PRG_OK)
+    return std::string("prg_recall_topk: ") + prg_last_error();
+  pai_web::VectorReply reply;
+  for (int i = 0; i < n; ++i) {
+    if (rows[i] >= cat_->ids.size()) continue;
+    reply.Retval.push_back(rows[i]);
+    reply.Labels.push_back(cat_->ids[rows[i]]);
+    reply.Scores.push_back(scores[i]);
+  }
+  *out = std::move(reply);
+  return "";
+}
+
+Error GpuRankAlgorithm::Run(const AlgoData& algoData, AlgoResult* out) {
+  auto pp = std::get_if<const FeatureList*>(&algoData);
+  if (!pp || !*pp) return "GpuRankAlgorithm: algoData is not []map[string]interface{}";
+  const FeatureList& list = **pp;
+  if (list.empty()) { *out = std::monostate{}; return ""; }
+  std::vector<uint32_t> rows(list.size(), 0xFFFFFFFFu);
+  for (size_t i = 0; i < list.size(); ++i) {
+    auto it = list[i].find("item_id");
+    if (it == list[i].end()) continue;
+    if (auto s = std::get_if<std::string>(&it->second)) {
+      auto r = cat_->row_of.find(*s);
+      if (r != cat_->row_of.end()) rows[i] = r->second;
+    }
+  }
+  std::vector<double> sc(list.size());
+  if (prg_rank(cat_->h, model_, rows.data(), 1, (int)rows.size(), sc.data(), PRG_MEM_HOST) != PRG_OK)
+    return std::string("prg_rank: ") + prg_last_error();
+  AlgoResponses res(list.size());
+  for (size_t i = 0; i < list.size(); ++i) res[i] = std::make_shared<ScoreResponse>(sc[i]);
+  *out = std::move(res);
+  return "";
+}
+}  // namespace algorithm
+
+void GpuCatalog::SetIds(std::vector<std::string> v) {
+  ids = std::move(v);
+  row_of.clear();
+  row_of.reserve(ids.size() * 2);
+  for (size_t i = 0; i < ids.size(); ++i) row_of.emplace(ids[i], (uint32_t)i);
+}
+
+// ================================================================================================ recall
+namespace recall {
+namespace {
+std::map<std::string, std::shared_ptr<Recall>>& registry() {
+  static std::map<std::string, std::shared_ptr<Recall>> m;
+  return m;
+}
+// VectorDao reading the "i:v i:v ..." string from a user property (stands in for the Redis/Hologres DAOs)
+struct PropertyVectorDao : VectorDao {
+  std::function<bool(const std::string&, std::string*)> fn;
+  Error VectorString(const std::string& id, std::string* out) override { return fn && fn(id, out) ? "" : VectoryEmptyError; }
+};
+}  // namespace
+const Error VectoryEmptyError = "vector empty";
+void RegisterRecall(const std::string& name, std::shared_ptr<Recall> r) { registry()[name] = std::move(r); }
+std::shared_ptr<Recall> GetRecall(const std::string& name) {
+  auto it = registry().find(name);
+  return it == registry().end() ? nullptr : it->second;
+}
+void Load(const recconf::RecommendConfig&) {}  // config-selectable recall types are registered by the embedding program
+
+VectorRecall::VectorRecall(const recconf::RecallConfig& conf, std::shared_ptr<VectorDao> dao)
+    : modelName_(conf.Name), itemType_(conf.ItemType), recallAlgo_(conf.RecallAlgo), recallCount_(conf.RecallCount),
+      dao_(std::move(dao)) {}
+
+std::vector<module::ItemPtr> VectorRecall::GetCandidateItems(module::User* user, context::RecommendContext* ctx) {
+  std::vector<module::ItemPtr> ret;
+  std::string value;
+  Error err = dao_->VectorString(user->Id, &value);  // vector_recall.go:59
+  if (!err.empty()) {
+    if (err != VectoryEmptyError) ctx->LogError("module=VectorRecall\tname=" + modelName_ + "\terr=" + err);
+    return ret;
+  }
+  pai_web::VectorRequest request;
+  request.K = (uint32_t)recallCount_;
+  std::istringstream ss(value);  // "idx:val idx:val" (:70-82)
+  std::string vc;
+  while (std::getline(ss, vc, ' ')) {
+    const size_t c = vc.find(':');
+    if (c == std::string::npos || vc.find(':', c + 1) != std::string::npos) continue;
+    request.Vector.push_back((float)strtod(vc.c_str() + c + 1, nullptr));
+  }
+  if (request.Vector.empty()) {
+    ctx->LogError("module=VectorRecall\terror=user Vector empty");
+    return ret;
+  }
+  algorithm::AlgoResult result;
+  err = algorithm::Run(recallAlgo_, &request, &result);  // :88
+  if (!err.empty()) {
+    ctx->LogError("module=VectorRecall\terror=" + err);
+    return ret;
+  }
+  auto reply = std::get_if<pai_web::VectorReply>(&result);
+  if (!reply) return ret;
+  for (size_t i = 0; i < reply->Labels.size(); ++i) {  // :93-102
+    auto item = module::NewItem(reply->Labels[i]);
+    item->RetrieveId = modelName_;
+    item->ItemType = itemType_;
+    item->Score = (double)reply->Scores[i];
+    ret.push_back(item);
+  }
+  return ret;
+}
+
+std::vector<module::ItemPtr> ContextItemRecall::GetCandidateItems(module::User*, context::RecommendContext*) {
+  std::vector<module::ItemPtr> out;
+  out.reserve(items_.size());
+  for (auto& it : items_) {  // fresh Items per request, like the reference's recalls
+    auto n = module::NewItem(it->Id);
+    n->Score = it->Score;
+    n->RetrieveId = name_;
+    n->ItemType = it->ItemType;
+    n->Properties = it->Properties;
+    out.push_back(n);
+  }
+  return out;
+}
+}  // namespace recall
+
+// ================================================================================================ ast (utils/ast)
+namespace ast {
+struct Expr {
+  enum Kind { Num, Param, Bin } kind = Num;
+  double val = 0;
+  std::string name;  // Param name or operator
+  std::shared_ptr<Expr> lhs, rhs;
+};
+namespace {
+struct Tok { std::string tok; int type; };  // 0 literal, 1 operator, 2 parameter (utils/ast/parse.go)
+Error tokenize(const std::string& s, std::vector<Tok>* out) {
+  size_t i = 0;
+  while (i < s.size()) {
+    const char c = s[i];
+    if (c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r') { ++i; continue; }
+    if (strchr("#()+-*/^%", c)) { out->push_back({std::string(1, c), 1}); ++i; continue; }
+    if (c >= '0' && c <= '9') {
+      const size_t st = i;
+      while (i < s.size() && ((s[i] >= '0' && s[i] <= '9') || s[i] == '.' || s[i] == '_' || s[i] == 'e')) ++i;
+      std::string t = s.substr(st, i - st);
+      t.erase(std::remove(t.begin(), t.end(), '_'), t.end());
+      out->push_back({t, 0});
+      continue;
+    }
+    if (c == '$' && i + 1 < s.size() && s[i + 1] == '{') {
+      const size_t e = s.find('}', i);
+      if (e == std::string::npos) return "unterminated ${";
+      out->push_back({s.substr(i + 2, e - i - 2), 2});
+      i = e + 1;
+      continue;
+    }
+    return std::string("symbol error: unkown '") + c + "'";
+  }
+  return "";
+}
+int prec(const std::string& op) {
+  if (op == "+" || op == "-") return 20;
+  if (op == "*" || op == "/" || op == "%") return 40;
+  if (op == "^") return 60;
+  if (op == "#") return 80;
+  return -1;
+}
+struct Parser {
+  const std::vector<Tok>& t;
+  size_t i = 0;
+  Error err;
+  const Tok* cur() const { return i < t.size() ? &t[i] : nullptr; }
+  std::shared_ptr<Expr> primary() {
+    const Tok* c = cur();
+    if (!c) return nullptr;
+    if (c->type == 0 || (c->type == 1 && c->tok != "(")) {
+      if (c->type == 1) { err = "want '(' or '0-9' but get '" + c->tok + "'"; return nullptr; }
+      auto e = std::make_shared<Expr>();
+      e->kind = Expr::Num;
+      e->val = strtod(c->tok.c_str(), nullptr);
+      ++i;
+      return e;
+    }
+    if (c->type == 2) {
+      auto e = std::make_shared<Expr>();
+      e->kind = Expr::Param;
+      e->name = c->tok;
+      ++i;
+      return e;
+    }
+    ++i;  // "("
+    auto e = expression();
+    if (!e) return nullptr;
+    if (!cur() || cur()->tok != ")") { err = "want ')'"; return nullptr; }
+    ++i;
+    return e;
+  }
+  int cur_prec() const { return (cur() && cur()->type == 1) ? prec(cur()->tok) : -1; }
+  std::shared_ptr<Expr> binop_rhs(int exec_prec, std::shared_ptr<Expr> lhs) {  // ast.go:167-196
+    for (;;) {
+      const int tok_prec = cur_prec();
+      if (tok_prec < exec_prec) return lhs;
+      const std::string op = cur()->tok;
+      ++i;
+      if (!cur()) return lhs;
+      auto rhs = primary();
+      if (!rhs) return nullptr;
+      if (tok_prec < cur_prec()) {
+        rhs = binop_rhs(tok_prec + 1, rhs);
+        if (!rhs) return nullptr;
+      }
+      auto b = std::make_shared<Expr>();
+      b->kind = Expr::Bin;
+      b->name = op;
+      b->lhs = lhs;
+      b->rhs = rhs;
+      lhs = b;
+    }
+  }
+  std::shared_ptr<Expr> expression() {
+    auto l = primary();
+    if (!l) return nullptr;
+    return binop_rhs(0, l);
+  }
+};
+}  // namespace
+Error Parse(const std::string& src, std::shared_ptr<Expr>* out) {
+  std::vector<Tok> toks;
+  Error e = tokenize(src, &toks);
+  if (!e.empty()) return e;
+  if (toks.empty()) return "empty token";
+  Parser p{toks, 0, ""};
+  auto r = p.expression();
+  if (!r) return p.err.empty() ? "parse error" : p.err;
+  *out = r;
+  return "";
+}
+Error Eval(const Expr& e, const std::function<bool(const std::string&, double*)>& param, double* out) {
+  switch (e.kind) {
+    case Expr::Num: *out = e.val; return "";
+    case Expr::Param: if (!param(e.name, out)) *out = 0.0; return "";  // ast.go:256-262 (unknown -> 0)
+    case Expr::Bin: {
+      double l = 0, r = 0;
+      Error er = Eval(*e.lhs, param, &l);
+      if (!er.empty()) return er;
+      er = Eval(*e.rhs, param, &r);
+      if (!er.empty()) return er;
+      const std::string& op = e.name;
+      if (op == "#") *out = (l != 0.0) ? l : r;
+      else if (op == "^") *out = std::pow(l, r);
+      else if (op == "+") *out = l + r;
+      else if (op == "-") *out = l - r;
+      else if (op == "*") *out = l * r;
+      else if (op == "/") {
+        if (r == 0) return "violation of arithmetic specification: a division by zero in ExprASTResult";  // panics upstream
+        *out = l / r;
+      } else if (op == "%") {
+        if ((long long)r == 0) return "integer divide by zero";
+        *out = (double)((long long)l % (long long)r);
+      } else *out = 0;
+      return "";
+    }
+  }
+  return "";
+}
+}  // namespace ast
+
+// ================================================================================================ rank
+namespace rank {
+void Rank(module::User* user, std::vector<module::ItemPtr>& items, context::RecommendContext* ctx) {
+  const std::string scene = ctx->GetParameter("scene");
+  if (!ctx->Config) return;
+  auto rc = ctx->Config->RankConf.find(scene);
+  if (rc == ctx->Config->RankConf.end()) return;  // rank_service.go:153-157: no config -> no rank
+  const recconf::RankConfig& rankConfig = rc->second;
+  int batchCount = rankConfig.BatchCount > 0 ? rankConfig.BatchCount : 100;  // :163-166
+  if (rankConfig.RankAlgoList.empty() && rankConfig.RankScore.empty()) return;
+  const module::Features userFeatures = user ? user->MakeUserFeatures() : module::Features();
+  std::shared_ptr<ast::Expr> exprAst;
+  if (!rankConfig.RankScore.empty()) {
+    Error e = ast::Parse(rankConfig.RankScore, &exprAst);
+    if (!e.empty()) { ctx->LogError("module=rank\trankscore=" + rankConfig.RankScore + "\terror=" + e); exprAst = nullptr; }
+  }
+  for (size_t b0 = 0; b0 < items.size(); b0 += (size_t)batchCount) {
+    const size_t b1 = std::min(items.size(), b0 + (size_t)batchCount);
+    algorithm::FeatureList feats;
+    feats.reserve(b1 - b0);
+    for (size_t i = b0; i < b1; ++i) {  // AlgoDataGenerator.AddFeatures (algo_data.go:104-118): user ∪ item features
+      module::Features f = userFeatures;
+      for (auto& kv : items[i]->GetFeatures()) f[kv.first] = kv.second;
+      f["item_id"] = items[i]->Id;
+      feats.push_back(std::move(f));
+    }
+    for (auto& algoName : rankConfig.RankAlgoList) {  // :264-289 (one goroutine per batch x algo upstream)
+      algorithm::AlgoResult result;
+      Error e = algorithm::Run(algoName, &feats, &result);
+      if (!e.empty()) { ctx->LogError("module=rank\terror=run algorithm error(" + e + ")"); continue; }  // :274-277
+      auto res = std::get_if<algorithm::AlgoResponses>(&result);
+      if (!res) continue;
+      for (size_t j = 0; j < res->size() && b0 + j < b1; ++j) {  // :313-334
+        auto& it = items[b0 + j];
+        if ((*res)[j]->GetModuleType())
+          for (auto& kv : (*res)[j]->GetScoreMap()) it->AddAlgoScore(algoName + "_" + kv.first, kv.second);
+        else it->AddAlgoScore(algoName, (*res)[j]->GetScore());
+      }
+    }
+    if (exprAst) {  // :339-363
+      for (size_t i = b0; i < b1; ++i) {
+        auto& it = items[i];
+        double v = 0;
+        Error e = ast::Eval(*exprAst, [&](const std::string& n, double* o) { return it->FloatExprData(n, o).empty(); }, &v);
+        if (!e.empty()) { ctx->LogError("module=rank\terror=" + e); continue; }
+        it->Score = v;
+      }
+    }
+  }
+}
+}  // namespace rank
+
+// ================================================================================================ sort
+namespace sort {
+namespace {
+std::map<std::string, std::shared_ptr<ISort>>& mapping() {
+  static std::map<std::string, std::shared_ptr<ISort>> m;
+  return m;
+}
+std::map<std::string, std::vector<std::shared_ptr<ISort>>>& strategies() {
+  static std::map<std::string, std::vector<std::shared_ptr<ISort>>> m;
+  return m;
+}
+// sort.Sort(sort.Reverse(ItemScoreSlice(items))) with Go's pdqsort tie order (prg_sort_desc_host)
+void go_sort_desc(std::vector<module::ItemPtr>& items, const std::vector<double>& key) {
+  const int n = (int)items.size();
+  if (n <= 1) return;
+  std::vector<int32_t> perm((size_t)n);
+  prg_sort_desc_host(key.data(), n, perm.data());
+  std::vector<module::ItemPtr> out((size_t)n);
+  for (int i = 0; i < n; ++i) out[(size_t)i] = items[(size_t)perm[(size_t)i]];
+  items.swap(out);
+}
+}  // namespace
+void RegisterSort(const std::string& name, std::shared_ptr<ISort> s) {
+  if (!mapping().count(name)) mapping()[name] = std::move(s);
+}
+Error GetSort(const std::string& name, std::shared_ptr<ISort>* out) {
+  auto it = mapping().find(name);
+  if (it == mapping().end()) return "ISort not found, name:" + name;
+  *out = it->second;
+  return "";
+}
+void Load(const recconf::RecommendConfig& c) {
+  RegisterSort("ItemRankScore", std::make_shared<ItemRankScoreSort>());  // sort/item_rank_score.go:34-36 init()
+  for (auto& sc : c.SortConfs)
+    if (sc.SortType == "AlgoScoreSort") RegisterSort(sc.Name, std::make_shared<AlgoScoreSort>(sc));
+  for (auto& kv : c.SortNames) {
+    std::vector<std::shared_ptr<ISort>> v;
+    for (auto& n : kv.second) {
+      auto it = mapping().find(n);
+      if (it != mapping().end()) v.push_back(it->second);
+    }
+    strategies()[kv.first] = v;
+  }
+}
+void Sort(SortData* data, const std::string& tag) {
+  context::RecommendContext* ctx = data->Context;
+  std::string scene = ctx->GetParameter("scene") + tag;
+  std::string category = ctx->GetParameter("category");
+  if (category.empty()) category = "default";
+  std::vector<std::shared_ptr<ISort>> sorts;
+  auto it = strategies().find(scene);
+  if (it == strategies().end()) it = strategies().find(category);
+  if (it != strategies().end()) sorts = it->second;
+  if (sorts.empty()) {
+    sorts.push_back(std::make_shared<ItemRankScoreSort>());
+    ctx->LogInfo("defaultSort=ItemRankScore\tscene=" + scene);
+  }
+  for (auto& s : sorts) s->Sort(data);  // the return value is ignored upstream (sort.go:123)
+}
+
+Error ItemRankScoreSort::Sort(SortData* d) {
+  std::vector<double> key(d->Data.size());
+  for (size_t i = 0; i < key.size(); ++i) key[i] = d->Data[i]->Score;
+  go_sort_desc(d->Data, key);
+  return "";
+}
+AlgoScoreSort::AlgoScoreSort(const recconf::SortConfig& c)
+    : sortByField_(c.SortByField.empty() ? "current_score" : c.SortByField), switchThreshold_(c.SwitchThreshold) {}
+Error AlgoScoreSort::Sort(SortData* d) {
+  double maxScore = -1e300;  // GetMaxScore (:28-36)
+  for (auto& it : d->Data) maxScore = std::max(maxScore, it->Score);
+  const std::string field = maxScore > switchThreshold_ ? "current_score" : sortByField_;
+  std::vector<double> key(d->Data.size());
+  for (size_t i = 0; i < key.size(); ++i) {
+    if (!d->Data[i]->FloatExprData(field, &key[i]).empty()) {
+      key[i] = d->Data[i]->Score;
+      d->Context->LogInfo("get sort field " + field + " from item " + d->Data[i]->Id + " failed");
+    }
+  }
+  go_sort_desc(d->Data, key);  // sort.Slice(less = iScore > jScore) — same pdqsort
+  return "";
+}
+
+GpuDPPSort::GpuDPPSort(const recconf::DPPSortConfig& c, std::shared_ptr<GpuCatalog> cat) : conf_(c), cat_(std::move(cat)) {
+  if (conf_.WindowSize <= 0) conf_.WindowSize = 10;  // dpp_sort.go:89-91
+}
+Error GpuDPPSort::Sort(SortData* d) {
+  auto& candidates = d->Data;
+  if (candidates.empty()) return "";
+  context::RecommendContext* ctx = d->Context;
+  if (conf_.AbortRunCount > 0 && (int)candidates.size() <= conf_.AbortRunCount) {  // :118-123
+    ItemRankScoreSort().Sort(d);
+    return "";
+  }
+  std::vector<module::ItemPtr> selected, backup;  // :145-158
+  for (auto& it : candidates) {
+    if (std::find(conf_.FilterRetrieveIds.begin(), conf_.FilterRetrieveIds.end(), it->RetrieveId) != conf_.FilterRetrieveIds.end())
+      backup.push_back(it);
+    else selected.push_back(it);
+  }
+  std::vector<module::ItemPtr> result = selected;
+  if (!selected.empty()) {
+    std::vector<uint32_t> rows(selected.size());
+    std::vector<double> score(selected.size());
+    for (size_t i = 0; i < selected.size(); ++i) {
+      auto r = cat_->row_of.find(selected[i]->Id);
+      rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFEu : r->second;  // unknown id: out-of-table row -> zero embedding
+      score[i] = selected[i]->Score;
+    }
+    prg_dpp_params p{};
+    p.alpha = conf_.Alpha;
+    p.top_n = ctx->Size;
+    p.window_size = conf_.WindowSize;
+    p.norm_mode = 0;
+    p.normalize_emb = (conf_.NormalizeEmb == "false" || conf_.NormalizeEmb == "False") ? 0 : 1;
+    p.candidate_count = conf_.CandidateCount;
+    p.min_score_percent = conf_.MinScorePercent;
+    std::vector<int32_t> idx((size_t)std::max(1, ctx->Size), -1);
+    int32_t n = 0, st = 0;
+    if (prg_dpp(cat_->h, rows.data(), score.data(), 1, (int)rows.size(), &p, idx.data(), &n, &st, PRG_MEM_HOST) != PRG_OK) {
+      ctx->LogError(std::string("build kernel matrix failed ") + prg_last_error());  // :317-320: items unchanged
+    } else if (st == 0) {
+      result.clear();
+      for (int i = 0; i < n; ++i) {
+        selected[(size_t)idx[(size_t)i]]->AddAlgoScore("dpp_relevance_score", score[(size_t)idx[(size_t)i]]);  // :411
+        result.push_back(selected[(size_t)idx[(size_t)i]]);
+      }
+    }
+  }
+  result.insert(result.end(), backup.begin(), backup.end());
+  candidates.swap(result);
+  return "";
+}
+}  // namespace sort
+
+// ================================================================================================ filter
+namespace filter {
+void UniqueFilter(std::vector<module::ItemPtr>* items) {
+  std::vector<module::ItemPtr> out;
+  std::unordered_map<std::string, module::ItemPtr> uniq;
+  for (auto& item : *items) {
+    auto it = uniq.find(item->Id);
+    if (it == uniq.end()) {
+      uniq[item->Id] = item;
+      out.push_back(item);
+    } else {
+      for (auto& kv : item->algoScores) it->second->AddAlgoScore(kv.first, kv.second);
+      if (it->second->RecallScores.empty()) it->second->RecallScores[it->second->RetrieveId] = it->second->Score;
+      it->second->RecallScores[item->RetrieveId] = item->Score;
+    }
+  }
+  items->swap(out);
+}
+}  // namespace filter
+
+// ================================================================================================ service
+namespace service {
+std::vector<module::ItemPtr> Recommend(module::User* user, context::RecommendContext* ctx) {
+  std::vector<module::ItemPtr> items;
+  const recconf::RecommendConfig* conf = ctx->Config;
+  if (!conf) return items;
+  const std::string scene = ctx->GetParameter("scene");
+  std::string category = ctx->GetParameter("category");
+  if (category.empty()) category = "default";
+  // RecallService.GetItems (service/recall.go:53-151): scene -> category -> recall names
+  auto sc = conf->SceneConfs.find(scene);
+  if (sc != conf->SceneConfs.end()) {
+    auto cat = sc->second.find(category);
+    if (cat == sc->second.end()) cat = sc->second.find("default");
+    if (cat != sc->second.end()) {
+      for (auto& name : cat->second.RecallNames) {
+        auto r = recall::GetRecall(name);
+        if (!r) { ctx->LogError("recall not found, name:" + name); continue; }
+        auto got = r->GetCandidateItems(user, ctx);
+        items.insert(items.end(), got.begin(), got.end());
+      }
+    }
+  }
+  // Filter (service/recommend.go:28-35): FilterNames[scene] or ["default"]
+  auto fn = conf->FilterNames.find(scene);
+  if (fn == conf->FilterNames.end()) fn = conf->FilterNames.find("default");
+  if (fn != conf->FilterNames.end())
+    for (auto& f : fn->second)
+      if (f == "UniqueFilter") filter::UniqueFilter(&items);
+  rank::Rank(user, items, ctx);
+  sort::SortData sd;
+  sd.Data = items;
+  sd.Context = ctx;
+  sd.User = user;
+  sort::Sort(&sd, "");
+  items = sd.Data;
+  if ((int)items.size() > ctx->Size) items.resize((size_t)ctx->Size);  // user_recommend.go:168
+  return items;
+}
+}  // namespace service
+
+void ResetRegistries() {
+  sort::mapping().clear();
+  sort::strategies().clear();
+  recall::registry().clear();
+  algorithm::Factory().~AlgorithmFactory();
+  new (&algorithm::Factory()) algorithm::AlgorithmFactory();
+}
+
+}  // namespace pairec

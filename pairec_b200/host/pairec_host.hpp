@@ -1,0 +1,294 @@
+// pairec_host.hpp — host-side mirror (C++17) of the reference's operator / plugin interfaces for the hot path.
+//
+// The reference host is Go; no Go toolchain exists in the build image or on the GPU box, so the layer that sits above
+// the C ABI (include/pairec_gpu.h) is written in C++ with the SAME names, argument meaning and error behaviour as the
+// Go interfaces it stands in for, so that tests/test_host_plugin*.py read like the reference's own plugin tests
+// (construct Items + a RecommendContext, run the plugin, assert order/count):
+//
+//   recconf::RecommendConfig        recconf/recconf.go:48-93 (subset: AlgoConfs, RecallConfs, SceneConfs, RankConf,
+//                                   SortNames, SortConfs{SortByField,SwitchThreshold,DPPConf}, FilterNames, UserDefineConfs)
+//   module::Item / User             module/item.go:15-27,168-248 ; module/user.go
+//   context::RecommendContext       context/recommend_context.go
+//   algorithm::IAlgorithm, factory  algorithm/algorithm.go:28-31,107-168 ; LookupPolicy algorithm/lookup.go:37-51
+//   pai_web::VectorRequest/Reply    algorithm/faiss/vectorretrieval.proto:11-20
+//   recall::Recall, VectorRecall    service/recall/recall.go:18-34 ; service/recall/vector_recall.go:32-123
+//   rank::RankService               service/rank/rank_service.go:102-372 (generic processor), utils/ast/ast.go:215-269
+//   sort::ISort, SortService        sort/sort.go:27-35,65-150 ; ItemRankScoreSort sort/item_rank_score.go:26-32 ;
+//                                   AlgoScoreSort sort/algo_score_sort.go:38-66 ; DPPSort sort/dpp_sort.go:108-167
+//   filter::UniqueFilter            filter/unique_filter.go:26-49
+//   service::UserRecommendService   service/user_recommend.go:46-183 (recall -> filter -> rank -> sort -> truncate)
+//
+// GPU-backed plugins (GpuVectorAlgorithm, GpuRankAlgorithm, GpuDPPSort) call libpairec_gpu.so through its C ABI only.
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <variant>
+#include <vector>
+
+#include "../../include/pairec_gpu.h"
+#include "json.hpp"
+
+namespace pairec {
+
+using Error = std::string;  // "" == nil
+
+// ------------------------------------------------------------------------------------------------ recconf
+namespace recconf {
+struct LookupConfig { std::string FieldName; };
+struct AlgoConfig { std::string Name, Type; LookupConfig LookupConf; };
+struct RecallConfig { std::string Name, RecallType, RecallAlgo, ItemType; int RecallCount = 0; };
+struct RankConfig { std::vector<std::string> RankAlgoList; std::string RankScore, Processor; int BatchCount = 0; };
+struct DPPSortConfig {
+  std::string Name, NormalizeEmb, EnsurePositiveSim;
+  double Alpha = 0, MinScorePercent = 0;
+  int WindowSize = 0, AbortRunCount = 0, CandidateCount = 0;
+  std::vector<std::string> FilterRetrieveIds;
+};
+struct SortConfig { std::string Name, SortType, SortByField; double SwitchThreshold = 0; DPPSortConfig DPPConf; };
+struct SceneCategory { std::vector<std::string> RecallNames; };
+struct RecommendConfig {
+  std::string RunMode;
+  std::vector<AlgoConfig> AlgoConfs;
+  std::vector<RecallConfig> RecallConfs;
+  std::map<std::string, std::map<std::string, SceneCategory>> SceneConfs;
+  std::map<std::string, RankConfig> RankConf;
+  std::map<std::string, std::vector<std::string>> SortNames, FilterNames;
+  std::vector<SortConfig> SortConfs;
+  Json UserDefineConfs;
+};
+// recconf.LoadConfig (recconf/recconf.go:1089-1100) from a JSON string
+Error LoadConfig(const std::string& json, RecommendConfig* out);
+}  // namespace recconf
+
+// ------------------------------------------------------------------------------------------------ module
+namespace module {
+using Value = std::variant<double, int64_t, std::string>;
+using Features = std::map<std::string, Value>;
+double ToFloat(const Value& v, double def);  // utils.ToFloat
+
+struct Item {
+  std::string Id;
+  double Score = 0;
+  std::string RetrieveId, ItemType;
+  std::vector<double> Embedding;
+  Features Properties;
+  std::map<std::string, double> algoScores;
+  std::map<std::string, double> RecallScores;
+  mutable std::mutex mutex;
+
+  explicit Item(std::string id) : Id(std::move(id)) {}
+  void AddProperty(const std::string& k, Value v);
+  void AddAlgoScore(const std::string& name, double score);                  // module/item.go:168-176
+  Features GetFeatures();                                                     // :229-248 (injects recall_name/score)
+  Error FloatExprData(const std::string& name, double* out);                  // :189-212
+};
+using ItemPtr = std::shared_ptr<Item>;
+ItemPtr NewItem(const std::string& id);
+
+struct User {
+  std::string Id;
+  Features Properties;
+  Features MakeUserFeatures() const { return Properties; }
+};
+}  // namespace module
+
+// ------------------------------------------------------------------------------------------------ context
+namespace context {
+struct RecommendContext {
+  std::string RecommendId;
+  int Size = 10;
+  bool Debug = false;
+  std::map<std::string, std::string> Param;  // "scene", "category", ...
+  const recconf::RecommendConfig* Config = nullptr;
+  std::vector<std::string> Log;               // LogInfo / LogError sink (the reference writes to glog)
+  std::string GetParameter(const std::string& k) const { auto it = Param.find(k); return it == Param.end() ? "" : it->second; }
+  void LogInfo(const std::string& m) { Log.push_back("INFO " + m); }
+  void LogError(const std::string& m) { Log.push_back("ERROR " + m); }
+};
+}  // namespace context
+
+// ------------------------------------------------------------------------------------------------ algorithm
+namespace pai_web {
+struct VectorRequest { uint32_t K = 0; std::vector<float> Vector; };
+struct VectorReply { std::vector<uint64_t> Retval; std::vector<float> Scores; std::vector<std::string> Labels; };
+}  // namespace pai_web
+
+namespace algorithm {
+namespace response {
+struct AlgoResponse {  // algorithm/response/resonse.go:3-7
+  virtual ~AlgoResponse() = default;
+  virtual double GetScore() const = 0;
+  virtual std::map<std::string, double> GetScoreMap() const { return {}; }
+  virtual bool GetModuleType() const { return false; }
+};
+}  // namespace response
+using FeatureList = std::vector<module::Features>;
+using AlgoResponses = std::vector<std::shared_ptr<response::AlgoResponse>>;
+// Go's interface{} payloads on this path: generic-processor feature maps or a faiss VectorRequest
+using AlgoData = std::variant<std::monostate, const FeatureList*, const pai_web::VectorRequest*>;
+using AlgoResult = std::variant<std::monostate, AlgoResponses, pai_web::VectorReply>;
+
+struct IAlgorithm {  // algorithm/algorithm.go:28-31
+  virtual ~IAlgorithm() = default;
+  virtual Error Init(const recconf::AlgoConfig* conf) = 0;
+  virtual Error Run(const AlgoData& algoData, AlgoResult* out) = 0;
+};
+class AlgorithmFactory {
+ public:
+  void Init(const std::vector<recconf::AlgoConfig>& confs);                       // :48-67
+  Error Run(const std::string& name, const AlgoData& data, AlgoResult* out);     // :107-120
+  void RegisterAlgorithm(const std::string& name, std::shared_ptr<IAlgorithm> a);  // :164-168
+ private:
+  std::shared_mutex mutex_;
+  std::map<std::string, std::shared_ptr<IAlgorithm>> algorithms_;
+};
+AlgorithmFactory& Factory();
+inline void Load(const recconf::RecommendConfig& c) { Factory().Init(c.AlgoConfs); }
+inline Error Run(const std::string& name, const AlgoData& d, AlgoResult* out) { return Factory().Run(name, d, out); }
+inline void RegisterAlgorithm(const std::string& n, std::shared_ptr<IAlgorithm> a) { Factory().RegisterAlgorithm(n, std::move(a)); }
+
+class LookupPolicy : public IAlgorithm {  // algorithm/lookup.go
+ public:
+  Error Init(const recconf::AlgoConfig* conf) override;
+  Error Run(const AlgoData& algoData, AlgoResult* out) override;
+ private:
+  recconf::LookupConfig conf_;
+};
+}  // namespace algorithm
+
+// ------------------------------------------------------------------------------------------------ the GPU catalog
+// Item identity in the reference is a string; the kernels work on u32 rows.  One catalog per engine: row i <-> ids[i].
+struct GpuCatalog {
+  prg_handle* h = nullptr;
+  std::vector<std::string> ids;
+  std::unordered_map<std::string, uint32_t> row_of;
+  void SetIds(std::vector<std::string> v);
+};
+
+namespace algorithm {
+// IAlgorithm behind a RecallAlgo name: VectorRequest -> VectorReply through prg_recall_topk (replaces algorithm/faiss)
+class GpuVectorAlgorithm : public IAlgorithm {
+ public:
+  explicit GpuVectorAlgorithm(std::shared_ptr<GpuCatalog> c) : cat_(std::move(c)) {}
+  Error Init(const recconf::AlgoConfig*) override { return ""; }
+  Error Run(const AlgoData& algoData, AlgoResult* out) override;
+ private:
+  std::shared_ptr<GpuCatalog> cat_;
+};
+// IAlgorithm behind a RankAlgoList name: feature maps (carrying "item_id") -> scores through prg_rank
+class GpuRankAlgorithm : public IAlgorithm {
+ public:
+  GpuRankAlgorithm(std::shared_ptr<GpuCatalog> c, int model) : cat_(std::move(c)), model_(model) {}
+  Error Init(const recconf::AlgoConfig*) override { return ""; }
+  Error Run(const AlgoData& algoData, AlgoResult* out) override;
+ private:
+  std::shared_ptr<GpuCatalog> cat_;
+  int model_;
+};
+}  // namespace algorithm
+
+// ------------------------------------------------------------------------------------------------ recall
+namespace recall {
+struct Recall {  // service/recall/recall.go:18-20
+  virtual ~Recall() = default;
+  virtual std::vector<module::ItemPtr> GetCandidateItems(module::User* user, context::RecommendContext* ctx) = 0;
+};
+void RegisterRecall(const std::string& name, std::shared_ptr<Recall> r);  // :32-34
+std::shared_ptr<Recall> GetRecall(const std::string& name);
+void Load(const recconf::RecommendConfig& c);  // builds the config-selectable recalls it knows (VectorRecall)
+
+struct VectorDao {  // module/vector_dao.go:13-15
+  virtual ~VectorDao() = default;
+  virtual Error VectorString(const std::string& id, std::string* out) = 0;
+};
+extern const Error VectoryEmptyError;
+class VectorRecall : public Recall {  // service/recall/vector_recall.go
+ public:
+  VectorRecall(const recconf::RecallConfig& conf, std::shared_ptr<VectorDao> dao);
+  std::vector<module::ItemPtr> GetCandidateItems(module::User* user, context::RecommendContext* ctx) override;
+ private:
+  std::string modelName_, itemType_, recallAlgo_;
+  int recallCount_;
+  std::shared_ptr<VectorDao> dao_;
+};
+// in-memory recall of a fixed item list (the role MockRecall / ContextItemRecall play for config 1)
+class ContextItemRecall : public Recall {
+ public:
+  ContextItemRecall(std::string name, std::vector<module::ItemPtr> items) : name_(std::move(name)), items_(std::move(items)) {}
+  std::vector<module::ItemPtr> GetCandidateItems(module::User*, context::RecommendContext*) override;
+ private:
+  std::string name_;
+  std::vector<module::ItemPtr> items_;
+};
+}  // namespace recall
+
+// ------------------------------------------------------------------------------------------------ rank
+namespace ast {
+// utils/ast: "${a} * 2 + ${b}" with ops # ^ + - * / % and parentheses; division by zero is an error (the reference panics)
+struct Expr;
+Error Parse(const std::string& src, std::shared_ptr<Expr>* out);
+Error Eval(const Expr& e, const std::function<bool(const std::string&, double*)>& param, double* out);
+}  // namespace ast
+namespace rank {
+void Rank(module::User* user, std::vector<module::ItemPtr>& items, context::RecommendContext* ctx);  // RankService.Rank
+}
+
+// ------------------------------------------------------------------------------------------------ sort
+namespace sort {
+struct SortData {  // sort/sort.go:27-31
+  std::vector<module::ItemPtr> Data;
+  context::RecommendContext* Context = nullptr;
+  module::User* User = nullptr;
+  std::string PipelineName;
+};
+struct ISort {  // :33-35
+  virtual ~ISort() = default;
+  virtual Error Sort(SortData* sortData) = 0;
+};
+void RegisterSort(const std::string& name, std::shared_ptr<ISort> s);  // first registration wins (:143-150)
+Error GetSort(const std::string& name, std::shared_ptr<ISort>* out);
+void Load(const recconf::RecommendConfig& c);                            // SortNames -> strategies (:127-137)
+void Sort(SortData* sortData, const std::string& tag);                  // SortService.Sort (:65-125)
+
+class ItemRankScoreSort : public ISort {  // sort/item_rank_score.go: sort.Sort(sort.Reverse(ItemScoreSlice))
+ public:
+  Error Sort(SortData* d) override;
+};
+class AlgoScoreSort : public ISort {  // sort/algo_score_sort.go
+ public:
+  explicit AlgoScoreSort(const recconf::SortConfig& c);
+  Error Sort(SortData* d) override;
+ private:
+  std::string sortByField_;
+  double switchThreshold_;
+};
+// DPPSort.Sort (sort/dpp_sort.go:108-167) with the kernel-matrix + greedy part on the GPU (prg_dpp)
+class GpuDPPSort : public ISort {
+ public:
+  GpuDPPSort(const recconf::DPPSortConfig& c, std::shared_ptr<GpuCatalog> cat);
+  Error Sort(SortData* d) override;
+ private:
+  recconf::DPPSortConfig conf_;
+  std::shared_ptr<GpuCatalog> cat_;
+};
+}  // namespace sort
+
+namespace filter {
+void UniqueFilter(std::vector<module::ItemPtr>* items);  // filter/unique_filter.go:26-49
+}
+
+// ------------------------------------------------------------------------------------------------ service
+namespace service {
+// UserRecommendService.Recommend (service/user_recommend.go:46-183): recall -> filter -> rank -> sort -> items[:size]
+std::vector<module::ItemPtr> Recommend(module::User* user, context::RecommendContext* ctx);
+}
+
+// Process-wide registries are reset between test cases.
+void ResetRegistries();
+
+}  // namespace pairec

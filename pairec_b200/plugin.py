@@ -1,0 +1,90 @@
+"""ctypes front-end of libpairec_host.so — the C++ mirror of the reference's plugin interfaces (pairec_b200/host/).
+
+`HostServer` plays the role of the pairec process for the hot path: it loads ONE recconf JSON, registers the
+in-memory / GPU-backed plugins under the names the JSON binds, and answers /api/recommend-shaped requests.
+"""
+import ctypes as C
+import json
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def load_host_library():
+    global _lib
+    if _lib is None:
+        p = os.path.join(_HERE, "libpairec_host.so")
+        if not os.path.exists(p):
+            raise OSError(f"{p} is missing: run __graft_entry__.build() (make -C pairec_b200/host)")
+        # the host library links libpairec_gpu.so ($ORIGIN rpath)
+        _lib = C.CDLL(p)
+        _lib.ph_last_error.restype = C.c_char_p
+        _lib.ph_recommend.restype = C.c_longlong
+        _lib.ph_destroy.restype = None
+    return _lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+class HostServer:
+    def __init__(self, recconf):
+        self._lib = load_host_library()
+        self._h = C.c_void_p(0)
+        js = recconf if isinstance(recconf, str) else json.dumps(recconf)
+        if self._lib.ph_create(js.encode(), C.byref(self._h)) != 0:
+            raise HostError(self._lib.ph_last_error().decode())
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HostError(self._lib.ph_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self._lib.ph_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def add_context_item(self, recall_name, item_id, score=0.0, properties=None):
+        self._ck(self._lib.ph_add_context_item(self._h, recall_name.encode(), item_id.encode(), C.c_double(score),
+                                               json.dumps(properties or {}).encode()))
+
+    def commit(self):
+        self._ck(self._lib.ph_commit(self._h))
+
+    def attach_engine(self, engine, ids):
+        """Binds a pairec_b200.Engine (GPU) and the row -> item-id catalog."""
+        self._ck(self._lib.ph_attach_engine(self._h, engine._h))
+        arr = (C.c_char_p * len(ids))(*[s.encode() for s in ids])
+        self._ck(self._lib.ph_set_catalog_ids(self._h, arr, C.c_uint64(len(ids))))
+
+    def register_gpu_plugins(self, recall_algo="", rank_algo="", model=0, dpp_sort=""):
+        self._ck(self._lib.ph_register_gpu_plugins(self._h, recall_algo.encode(), rank_algo.encode(), C.c_int(model),
+                                                   dpp_sort.encode()))
+
+    def set_user_vector(self, uid, vector):
+        s = " ".join(f"{i}:{float(v)!r}" for i, v in enumerate(vector))
+        self._ck(self._lib.ph_set_user_vector(self._h, uid.encode(), s.encode()))
+
+    def recommend(self, **param):
+        """RecommendParam (scene_id, category, uid, size, debug, features) -> RecommendResponse dict."""
+        req = json.dumps(param).encode()
+        need = self._lib.ph_recommend(self._h, req, None, C.c_ulonglong(0))
+        if need < 0:
+            raise HostError(self._lib.ph_last_error().decode())
+        buf = C.create_string_buffer(int(need))
+        self._lib.ph_recommend(self._h, req, buf, C.c_ulonglong(need))
+        return json.loads(buf.value.decode())
+
+
+def eval_expr(expr, values):
+    """utils/ast expression over named values."""
+    lib = load_host_library()
+    names = list(values)
+    arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    vals = (C.c_double * len(names))(*[float(values[n]) for n in names])
+    out = C.c_double(0)
+    if lib.ph_eval_expr(expr.encode(), arr, vals, C.c_int(len(names)), C.byref(out)) != 0:
+        raise HostError(lib.ph_last_error().decode())
+    return out.value

@@ -1,0 +1,115 @@
+"""Config 1 (BASELINE.json configs[0]): single-scene recconf JSON, 1k-item in-memory catalog, LOOKUP scoring +
+AlgoScoreSort / ItemRankScore ordering on the host (plumbing, no GPU) through the C++ mirror of the reference's
+plugin interfaces.  Written in the style of the reference's own plugin tests (sort/custom_field_sort_test.go:56-80:
+build items + context, run the plugin, assert order/count)."""
+import json
+
+import numpy as np
+import pytest
+
+# the sample config the reference's scaffolder emits (commands/commands/project_data.go:40-94), with the LOOKUP
+# algorithm bound as the scene's rank model
+RECCONF = {
+    "RunMode": "product",
+    "ListenConf": {"HttpAddr": "", "HttpPort": 8000},
+    "RecallConfs": [],
+    "SortNames": {"default": ["ItemRankScore"], "by_field": ["field_sort"]},
+    "FilterNames": {"default": ["UniqueFilter"]},
+    "AlgoConfs": [{"Name": "lookup_score", "Type": "LOOKUP", "LookupConf": {"FieldName": "score"}}],
+    "SceneConfs": {"home_feed": {"default": {"RecallNames": ["mem_recall"]}},
+                   "by_field": {"default": {"RecallNames": ["mem_recall"]}}},
+    "RankConf": {"home_feed": {"RankAlgoList": ["lookup_score"], "RankScore": "${lookup_score}", "BatchCount": 100},
+                 "by_field": {"RankAlgoList": ["lookup_score"], "RankScore": "${lookup_score} * 2 + ${bonus}"}},
+    "SortConfs": [{"Name": "field_sort", "SortType": "AlgoScoreSort", "SortByField": "freshness", "SwitchThreshold": 10.0}],
+}
+
+
+@pytest.fixture()
+def server():
+    from pairec_b200.plugin import HostServer
+    s = HostServer(RECCONF)
+    yield s
+    s.close()
+
+
+def _catalog(server, n=1000, seed=1, ties=False):
+    rng = np.random.default_rng(seed)
+    score = rng.random(n)
+    if ties:
+        score = np.round(score, 2)
+    fresh = rng.random(n)
+    for i in range(n):
+        props = {"score": float(score[i]), "freshness": float(fresh[i]), "bonus": 0.25}
+        if i % 97 == 0:
+            del props["score"]          # LOOKUP default 0.5 (algorithm/lookup.go:47-49)
+            score[i] = 0.5
+        server.add_context_item("mem_recall", "i%07d" % i, 0.0, props)
+    server.add_context_item("mem_recall", "i%07d" % 3, 0.0, {"score": 0.9})   # duplicate id -> UniqueFilter drops it
+    server.commit()
+    return score, fresh
+
+
+def test_config1_lookup_rank_item_rank_score_sort(server, oracle_lib):
+    score, _ = _catalog(server)
+    resp = server.recommend(scene_id="home_feed", uid="u1", size=50)
+    assert resp["code"] == 200 and resp["size"] == 50
+    got = [it["item_id"] for it in resp["items"]]
+    want = oracle_lib.go_sort(oracle_lib.lookup(score, np.ones_like(score, dtype=np.uint8)))[:50]
+    assert got == ["i%07d" % i for i in want]
+    assert [it["score"] for it in resp["items"]] == [float(score[i]) for i in want]
+    assert all(it["retrieve_id"] == "mem_recall" for it in resp["items"])
+
+
+def test_config1_tie_order_follows_go_sort(server, oracle_lib):
+    score, _ = _catalog(server, ties=True)
+    resp = server.recommend(scene_id="home_feed", uid="u1", size=1000)
+    got = [int(it["item_id"][1:]) for it in resp["items"]]
+    assert got == oracle_lib.go_sort(score).tolist()
+
+
+def test_config1_rank_score_expression_and_algo_score_sort(server, oracle_lib):
+    score, fresh = _catalog(server, n=300)
+    resp = server.recommend(scene_id="by_field", uid="u1", size=20)
+    # RankScore "${lookup_score} * 2 + ${bonus}" -> Item.Score; max(Score) <= SwitchThreshold -> sort by the field
+    final = score * 2 + 0.25
+    want = oracle_lib.algo_score_sort(final, fresh, 10.0)[:20]
+    assert [int(it["item_id"][1:]) for it in resp["items"]] == want.tolist()
+    assert [it["score"] for it in resp["items"]] == [float(final[i]) for i in want]
+
+
+def test_size_larger_than_catalog_is_code_299(server):
+    _catalog(server, n=30)
+    resp = server.recommend(scene_id="home_feed", uid="u1", size=100)
+    assert resp["code"] == 299 and resp["size"] == 30    # web/recommend_controller.go:131-142
+
+
+def test_unknown_scene_and_missing_algorithm_do_not_abort():
+    from pairec_b200.plugin import HostServer
+    conf = dict(RECCONF, RankConf={"home_feed": {"RankAlgoList": ["nope"], "RankScore": "${nope}"}})
+    s = HostServer(conf)
+    try:
+        s.add_context_item("mem_recall", "a", 0.0, {"score": 0.3})
+        s.commit()
+        r = s.recommend(scene_id="home_feed", uid="u", size=1)
+        assert r["size"] == 1 and any("not found algorithm, name:nope" in l for l in r["log"])
+        assert s.recommend(scene_id="no_such_scene", uid="u", size=1)["size"] == 0
+    finally:
+        s.close()
+
+
+def test_ast_known_answer_and_operators():
+    from pairec_b200.plugin import HostError, eval_expr
+    # utils/ast/ast_test.go:12-27
+    assert eval_expr("${ctr} + ${click} + ${price}", {"ctr": 0.1, "click": 0.3, "price": 0.1}) == 0.5
+    assert eval_expr("${a} * 2 + ${b} ^ 2", {"a": 3, "b": 4}) == 22.0
+    assert eval_expr("(${a} + 1) * (${b} - 1) / 2", {"a": 3, "b": 4}) == 6.0
+    assert eval_expr("${missing} # 7", {}) == 7.0          # '#': first non-zero operand
+    assert eval_expr("7 % 4", {}) == 3.0
+    with pytest.raises(HostError):
+        eval_expr("1 / ${z}", {"z": 0.0})                  # the reference panics (utils/ast/ast.go:243-249)
+
+
+def test_bad_recconf_is_an_error_not_a_crash():
+    from pairec_b200.plugin import HostError, HostServer
+    with pytest.raises(HostError):
+        HostServer("{not json")
