@@ -160,7 +160,7 @@ void prg_destroy(prg_handle* h) {
         if (h->tables[t].linear) cudaFree(const_cast<float*>(h->tables[t].linear));
       }
     }
-    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->row_norm, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
+    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->row_norm, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
                       &h->out_row, &h->out_score, &h->out_n, &h->flags, &h->table_ptrs, &h->act[0], &h->act[1],
                       &h->fm_logit, &h->rank_rows, &h->rank_out, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
                       &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->sort_in, &h->sort_perm, &h->rec_rows,

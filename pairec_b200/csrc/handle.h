@@ -54,6 +54,7 @@ struct prg_handle {
   prg::DevBuf sample_keys;  // QB x sample_slots u64
   prg::DevBuf cand_keys;    // QB x cand_cap u64 (packed candidates)
   prg::DevBuf seg_keys;     // QB x n_seg x seg_cap u64 keys (FFMA2 scan) or u32 rows (tensor-core filter)
+  prg::DevBuf seg_rows;     // QB x n_seg x seg_cap u32 survivor rows of the tensor-core filter
   prg::DevBuf row_norm;     // rows f32: upper bounds of the item row norms (tensor-core filter margin)
   bool scan_ffma2 = false;  // config "scan_ffma2": use the exact FFMA2 scan for the full pass as well
   prg::DevBuf cand_cnt;     // B u32

@@ -23,7 +23,10 @@ namespace prg {
 
 constexpr int kMlpBM = 128;
 constexpr int kMlpBK = 64;       // bf16 elements per k-block = one 128-B swizzle row
-constexpr int kMlpStages = 4;
+#ifndef MLP_STAGES
+#define MLP_STAGES 4
+#endif
+constexpr int kMlpStages = MLP_STAGES;
 constexpr int kMlpThreads = 192;
 
 struct MlpLayerParams {
@@ -43,7 +46,7 @@ constexpr size_t mlp_smem_bytes() {
 }
 
 template <int BN, bool FINAL>
-__global__ void __launch_bounds__(kMlpThreads, 1)
+__global__ void __launch_bounds__(kMlpThreads, MLP_STAGES <= 2 ? 2 : 1)
 mlp_layer_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                  const MlpLayerParams p) {
   extern __shared__ __align__(1024) uint8_t msm[];

@@ -387,6 +387,35 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const SelectParams p) {
   }
 }
 
+// Exact re-score of the tensor-core survivors: one block per (segment, query); every candidate row gets the fmaf chain
+// of the arithmetic contract (dims ascending, one accumulator) — the approximate score never reaches an output.
+__global__ void __launch_bounds__(64) rescore_kernel(const uint32_t* __restrict__ seg_rows, const uint32_t* __restrict__ seg_cnt,
+                                                     uint32_t seg_cap, const float* __restrict__ E, const float* __restrict__ Q,
+                                                     uint32_t dim, uint64_t row_base, uint64_t* __restrict__ seg_keys) {
+  __shared__ float qv[128];
+  const uint32_t sgi = blockIdx.x, q = blockIdx.y, n_seg = gridDim.x;
+  uint32_t c = seg_cnt[(size_t)q * n_seg + sgi];
+  if (c == 0) return;
+  if (c > seg_cap) c = seg_cap;
+  for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) qv[d] = Q[(size_t)q * dim + d];
+  __syncthreads();
+  const uint32_t* src = seg_rows + ((size_t)q * n_seg + sgi) * seg_cap;
+  uint64_t* dst = seg_keys + ((size_t)q * n_seg + sgi) * seg_cap;
+  for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+    const uint32_t grow = src[i];
+    const float4* x = reinterpret_cast<const float4*>(E + ((size_t)grow - row_base) * dim);
+    float acc = 0.f;
+    for (uint32_t d4 = 0; d4 < dim / 4; ++d4) {
+      const float4 xv = x[d4];
+      acc = __fmaf_rn(xv.x, qv[4 * d4], acc);
+      acc = __fmaf_rn(xv.y, qv[4 * d4 + 1], acc);
+      acc = __fmaf_rn(xv.z, qv[4 * d4 + 2], acc);
+      acc = __fmaf_rn(xv.w, qv[4 * d4 + 3], acc);
+    }
+    dst[i] = make_key(acc, grow);
+  }
+}
+
 // keys -> rows / scores / counts (used by the shard-merge path where keys already are sorted)
 __global__ void keys_unpack_kernel(const uint64_t* keys, int total, int k, uint32_t* out_row, float* out_score,
                                    int32_t* out_n, int B) {
@@ -508,6 +537,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     PRG_TRY(h->cand_keys.ensure((size_t)kQB * cand_cap * 8));
     PRG_TRY(h->seg_keys.ensure((size_t)kQB * n_seg * seg_cap * 8));
     use_tc = !h->scan_ffma2;
+    if (use_tc) PRG_TRY(h->seg_rows.ensure((size_t)kQB * n_seg * seg_cap * 4));
     if (use_tc && !h->row_norm.p) PRG_TRY(build_row_norms(h));
     PRG_TRY(h->cand_cnt.ensure((size_t)kQB * n_seg * 4 + 4));
     PRG_TRY(h->tau.ensure((size_t)kQB * 8));
@@ -542,17 +572,24 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     sc.tau = (const uint64_t*)h->tau.p; sc.cand = (uint64_t*)h->seg_keys.p; sc.seg_cap = seg_cap;
     sc.seg_cnt = (uint32_t*)h->cand_cnt.p;
     sc.row_norm = (const float*)h->row_norm.p; sc.cand_rows = (uint32_t*)h->seg_keys.p;
-    if (use_tc) PRG_TRY(launch_scan_tc(h, sc));
-    else PRG_TRY(scan(h, SCAN_THRESH, sc));
+    if (use_tc) {
+      sc.cand_rows = (uint32_t*)h->seg_rows.p;
+      PRG_TRY(launch_scan_tc(h, sc));
+      StageScope span(h, ST_SELECT);
+      rescore_kernel<<<dim3(n_seg, (unsigned)nq), 64, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
+                                                                      (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, qb,
+                                                                      dim, h->E_row_base, (uint64_t*)h->seg_keys.p);
+      PRG_CUDA(cudaGetLastError());
+      count_launch(h);
+    } else {
+      PRG_TRY(scan(h, SCAN_THRESH, sc));
+    }
     // 4. exact top-k of the candidates
     SelectParams se{};
     se.keys = (const uint64_t*)h->seg_keys.p; se.stride = cand_cap; se.counts = nullptr;
     se.seg_counts = (const uint32_t*)h->cand_cnt.p; se.n_seg = n_seg; se.seg_cap = seg_cap;
     se.compact = (uint64_t*)h->cand_keys.p;
-    if (use_tc) {
-      se.seg_rows = (const uint32_t*)h->seg_keys.p; se.E = h->E; se.Q = qb; se.dim = dim; se.row_base = h->E_row_base;
-      se.tau_check = (const uint64_t*)h->tau.p;
-    }
+    if (use_tc) se.tau_check = (const uint64_t*)h->tau.p;
     se.cap = cand_cap; se.k = k; se.k_out = k;
     se.expect = (uint32_t)((uint64_t)k < h->E_rows ? (uint64_t)k : h->E_rows);
     se.out_keys = kout; se.flags = (int32_t*)h->flags.p;

@@ -154,12 +154,18 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     const int ew = warp - 2;
     const int half = ew >> 2, quarter = warp & 3;  // TMEM lanes [32*(warp%4), +32) of half-tile `half`
     const int row_local = half * 128 + quarter * 32 + lane;
+    // row norms are prefetched one tile ahead: the global-load latency must not sit between the accumulator read
+    // and the compares (ncu r2: that exposed ~1 us per tile)
+    auto tile_row = [&](uint32_t i) -> uint64_t {
+      return (uint64_t)(blockIdx.x + i * gridDim.x) * p.tile_stride * kTileRows + (uint64_t)row_local;
+    };
+    float nr_next = (my_tiles > 0 && tile_row(0) < p.n_rows) ? p.row_norm[tile_row(0)] : 0.f;
     for (uint32_t i = 0; i < my_tiles; ++i) {
       const uint32_t buf = i & 1u;
-      const uint32_t t = blockIdx.x + i * gridDim.x;
-      const uint64_t lrow = (uint64_t)t * p.tile_stride * kTileRows + (uint64_t)row_local;
+      const uint64_t lrow = tile_row(i);
       const bool valid = lrow < p.n_rows;
-      const float nr = valid ? p.row_norm[lrow] : 0.f;
+      const float nr = nr_next;
+      nr_next = (i + 1 < my_tiles && tile_row(i + 1) < p.n_rows) ? p.row_norm[tile_row(i + 1)] : 0.f;
       mbar_wait(&tfull[buf], (i >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128u + (uint32_t)half * 64u;
@@ -169,34 +175,38 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);  // accumulators are in registers: the MMA warp may overwrite them
-      // thresholds are re-read from shared memory per tile (volatile: keeping 128 loop-invariant values live would
-      // spill); thr_q = tau_f[q] - ||x_row|| * c*||q||
-      const volatile float4* tq4 = reinterpret_cast<const volatile float4*>(tq);
-      bool any = false;
+      // thr_q = tau_f[q] - ||x_row|| * c*||q||; {tau_f, c||q||} pairs are re-read from shared memory per tile (the
+      // mbarrier wait above is a compiler memory barrier, so nothing is hoisted into 128 live registers)
+      const float4* tq4 = reinterpret_cast<const float4*>(tq);
+      bool any0 = false, any1 = false;
 #pragma unroll
       for (int q = 0; q < 32; q += 2) {
-        const float4 a4 = make_float4(tq4[q >> 1].x, tq4[q >> 1].y, tq4[q >> 1].z, tq4[q >> 1].w);
-        const float4 b4 = make_float4(tq4[16 + (q >> 1)].x, tq4[16 + (q >> 1)].y, tq4[16 + (q >> 1)].z, tq4[16 + (q >> 1)].w);
-        any |= !(__uint_as_float(v0[q]) < fmaf(-nr, a4.y, a4.x));
-        any |= !(__uint_as_float(v0[q + 1]) < fmaf(-nr, a4.w, a4.z));
-        any |= !(__uint_as_float(v1[q]) < fmaf(-nr, b4.y, b4.x));
-        any |= !(__uint_as_float(v1[q + 1]) < fmaf(-nr, b4.w, b4.z));
+        const float4 a4 = tq4[q >> 1];
+        const float4 b4 = tq4[16 + (q >> 1)];
+        any0 |= !(__uint_as_float(v0[q]) < fmaf(-nr, a4.y, a4.x));
+        any0 |= !(__uint_as_float(v0[q + 1]) < fmaf(-nr, a4.w, a4.z));
+        any1 |= !(__uint_as_float(v1[q]) < fmaf(-nr, b4.y, b4.x));
+        any1 |= !(__uint_as_float(v1[q + 1]) < fmaf(-nr, b4.w, b4.z));
       }
-      if (any && valid) {
+      if (valid && (any0 || any1)) {
         const uint32_t grow = (uint32_t)(p.row_base + lrow);
-        const volatile float2* tqv = reinterpret_cast<const volatile float2*>(tq);
+        const uint32_t seg_stride = gridDim.x * p.seg_cap, seg_base = blockIdx.x * p.seg_cap;
+        if (any0) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          if (q < p.nq && !(__uint_as_float(v0[q]) < fmaf(-nr, tqv[q].y, tqv[q].x))) {
-            const uint32_t pos = atomicAdd(&s_cnt[q], 1u);
-            if (pos < p.seg_cap) p.cand_rows[((size_t)q * gridDim.x + blockIdx.x) * p.seg_cap + pos] = grow;
+          for (int q = 0; q < 32; ++q) {
+            if (q < p.nq && !(__uint_as_float(v0[q]) < fmaf(-nr, tq[q].y, tq[q].x))) {
+              const uint32_t pos = atomicAdd(&s_cnt[q], 1u);
+              if (pos < p.seg_cap) p.cand_rows[(uint32_t)q * seg_stride + seg_base + pos] = grow;
+            }
           }
         }
+        if (any1) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          if (q + 32 < p.nq && !(__uint_as_float(v1[q]) < fmaf(-nr, tqv[q + 32].y, tqv[q + 32].x))) {
-            const uint32_t pos = atomicAdd(&s_cnt[q + 32], 1u);
-            if (pos < p.seg_cap) p.cand_rows[((size_t)(q + 32) * gridDim.x + blockIdx.x) * p.seg_cap + pos] = grow;
+          for (int q = 0; q < 32; ++q) {
+            if (q + 32 < p.nq && !(__uint_as_float(v1[q]) < fmaf(-nr, tq[q + 32].y, tq[q + 32].x))) {
+              const uint32_t pos = atomicAdd(&s_cnt[q + 32], 1u);
+              if (pos < p.seg_cap) p.cand_rows[(uint32_t)(q + 32) * seg_stride + seg_base + pos] = grow;
+            }
           }
         }
       }
