@@ -387,6 +387,95 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const SelectParams p) {
   }
 }
 
+// r-th largest key of a long list when r is small (the sampled threshold: r ~ 32 of ~78k keys).  One histogram pass
+// over 11-bit digits, refined until the bucket holding the answer fits in shared memory, then that bucket is sorted:
+// typically 2 passes over the keys instead of the 9 of the generic radix select.  Exact (keys are distinct).
+constexpr uint32_t kKthCap = 4096;
+__global__ void __launch_bounds__(1024, 1) select_kth_kernel(const SelectParams p) {
+  __shared__ uint32_t hist[2048];
+  __shared__ uint64_t s_prefix, s_mask;
+  __shared__ uint32_t s_want, s_bucket, s_fill;
+  extern __shared__ uint64_t sk[];  // kKthCap keys
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const uint64_t* keys = p.keys + (size_t)q * p.stride;
+  const uint32_t m = p.fixed_m;
+  uint64_t prefix = 0, mask = 0;
+  uint32_t want = (uint32_t)p.k;
+  uint64_t answer = 0;
+  bool done = false;
+  for (int level = 0; level < 6 && !done; ++level) {
+    const int bits = (level < 5) ? 11 : 9;
+    const int shift = (level < 5) ? (53 - 11 * level) : 0;
+    for (int i = tid; i < 2048; i += 1024) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < m; i += 1024) {
+      const uint64_t key = keys[i];
+      if (key != 0ull && (key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & ((1u << bits) - 1u)], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {  // digits from the top: lane l owns [64l, 64l+64)
+      uint32_t tot = 0;
+      for (int j = 0; j < 64; ++j) tot += hist[tid * 64 + j];
+      uint32_t run = tot;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, run, off);
+        if (tid + off < 32) run += v;
+      }
+      const uint32_t above = run - tot;
+      const uint32_t grand = __shfl_sync(0xffffffffu, run, 0);
+      if (grand < want) {
+        if (tid == 0) s_bucket = 0xFFFFFFFFu;  // fewer than r valid keys: no threshold
+      } else if (tot > 0 && above < want && above + tot >= want) {
+        uint32_t a = above;
+        int d = 63;
+        for (; d >= 0; --d) {
+          const uint32_t c = hist[tid * 64 + d];
+          if (a + c >= want) break;
+          a += c;
+        }
+        s_prefix = prefix | ((uint64_t)(tid * 64 + d) << shift);
+        s_mask = mask | ((uint64_t)((1u << bits) - 1u) << shift);
+        s_want = want - a;
+        s_bucket = hist[tid * 64 + d];
+      }
+      if (tid == 0) s_fill = 0;
+    }
+    __syncthreads();
+    if (s_bucket == 0xFFFFFFFFu) { answer = 0; done = true; break; }
+    prefix = s_prefix; mask = s_mask; want = s_want;
+    const uint32_t bucket = s_bucket;
+    __syncthreads();
+    if (bucket <= kKthCap || level == 5) {
+      for (uint32_t i = tid; i < kKthCap; i += 1024) sk[i] = 0ull;
+      __syncthreads();
+      for (uint32_t i = tid; i < m; i += 1024) {
+        const uint64_t key = keys[i];
+        if (key != 0ull && (key & mask) == prefix) {
+          const uint32_t pos = atomicAdd(&s_fill, 1u);
+          if (pos < kKthCap) sk[pos] = key;
+        }
+      }
+      __syncthreads();
+      uint32_t K2 = 32;
+      while (K2 < bucket && K2 < kKthCap) K2 <<= 1;
+      for (uint32_t size = 2; size <= K2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+          for (uint32_t i = tid; i < (K2 >> 1); i += 1024) {
+            const uint32_t pos = 2 * i - (i & (stride - 1));
+            const uint64_t a = sk[pos], b = sk[pos + stride];
+            if ((a < b) == ((pos & size) == 0)) { sk[pos] = b; sk[pos + stride] = a; }
+          }
+          __syncthreads();
+        }
+      }
+      answer = sk[want - 1];
+      done = true;
+    }
+  }
+  if (tid == 0) p.tau[q] = answer;
+}
+
 // Exact re-score of the tensor-core survivors: one block per (segment, query); every candidate row gets the fmaf chain
 // of the arithmetic contract (dims ascending, one accumulator) — the approximate score never reaches an output.
 __global__ void __launch_bounds__(64) rescore_kernel(const uint32_t* __restrict__ seg_rows, const uint32_t* __restrict__ seg_cnt,
@@ -472,7 +561,7 @@ static int scan(prg_handle* h, int mode, const ScanParams& p) {
 static int launch_select(prg_handle* h, int mode, const SelectParams& p, int nq) {
   StageScope span(h, ST_SELECT);
   if (mode == SEL_KTH) {
-    select_kernel<SEL_KTH><<<nq, 1024, 0, h->stream>>>(p);
+    select_kth_kernel<<<nq, 1024, kKthCap * 8, h->stream>>>(p);
   } else {
     uint32_t K2 = 32;
     while (K2 < (uint32_t)p.k) K2 <<= 1;
