@@ -85,6 +85,8 @@ class Engine:
         self._h = C.c_void_p(0)
         import json
         cfg = dict(cfg, device=device)
+        if os.environ.get("PRG_CFG"):  # experiment switches (A/B of kernel variants), e.g. '{"mlp_one_tile":1}'
+            cfg.update(json.loads(os.environ["PRG_CFG"]))
         rc = self._lib.prg_init(json.dumps(cfg).encode(), C.byref(self._h))
         if rc != 0:
             raise PrgError(rc, self._lib.prg_last_error().decode())

@@ -137,6 +137,7 @@ int prg_init(const char* json_cfg, prg_handle** out) {
   if (json_int(json_cfg, "sm_limit", &v) && v > 0 && v < h->sm_count) h->sm_count = (int)v;
   if (json_int(json_cfg, "scan_ffma2", &v) && v != 0) h->scan_ffma2 = true;
   if (json_int(json_cfg, "dpp_generic", &v) && v != 0) h->dpp_generic = true;
+  if (json_int(json_cfg, "mlp_one_tile", &v) && v != 0) h->mlp_one_tile_per_cta = true;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete h;

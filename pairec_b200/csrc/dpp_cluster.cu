@@ -1,18 +1,22 @@
 // dpp_cluster.cu — the fast path of DPPSort.doSort (sort/dpp_sort.go:271-351, :372-475, :477-551) for f32 diversity
-// tables with dim 32 / 64 / 128: one thread-block CLUSTER of 4 CTAs per request, one thread per candidate, the
-// candidate's embedding held in REGISTERS.
+// tables with dim 32 / 64 / 128: one thread-block CLUSTER of 4 CTAs per request, 256 candidates per CTA, the
+// candidates' embeddings resident in SHARED MEMORY ([dim][item], conflict-free), two threads per candidate.
 //
 // Why: the selection loop is 50 dependent steps of "row of L for the chosen item against every candidate" — n x (D+1)
 // fp64 multiply-adds per step with nothing reused between steps.  With one CTA per request (dpp.cu) every step
-// re-reads the request's embeddings through L2 and stalls on that latency (ncu: 62 % long-scoreboard, 1.56 ms per
-// 64-request batch).  Spreading a request over 4 SMs lets 1024 candidates keep their 128 floats in registers, so a
-// step is pure fp64 issue + one cluster barrier; all 148 SMs work on 37 requests at a time instead of 64 SMs on 64.
+// re-reads the request's embeddings through L2 and stalls on that latency (ncu r1: 62 % long-scoreboard, 1.56 ms per
+// 64-request batch).  Spreading a request over 4 SMs keeps the embeddings on chip; the two 64-wide k blocks of the
+// gonum dot product go to two threads (their partial sums are independent by construction), so a step is one pass of
+// fp64 issue over 16 warps + ONE cluster barrier.  v2 of this kernel kept the embedding in 128 registers per thread
+// (0.45 ms per batch; ncu r2: 63 % of issue slots lost to instruction fetch of the fully unrolled 129-term loops and
+// ~45 % of the step spent in barriers and the winner's row fetch); v3 loops over shared memory instead and ships
+// the winner's embedding inside the published record, so no global load sits on the critical path.
 //
 // Arithmetic is exactly dpp.cu's (and oracle/oracle.c's): fp64, gonum operation order, separate multiply/add
 // roundings, first-maximum argmax (rank order == index order), NaN masking, 1e-10 early stop + lowest-index fill.
 // Per step each CTA publishes its local arg-max candidate TOGETHER with everything the others need about it
-// (d2, 1/norm, quality, table row, its column of C) into every CTA's shared memory (DSMEM), so one cluster barrier
-// per step suffices; the records are double buffered so a fast CTA never overwrites what a slow one still reads.
+// (d2, 1/norm, quality, its embedding, its column of C) into every CTA's shared memory (DSMEM); the records are
+// double buffered so a fast CTA never overwrites what a slow one still reads.
 #include "handle.h"
 #include <cooperative_groups.h>
 #include <math_constants.h>
@@ -22,8 +26,9 @@ namespace cg = cooperative_groups;
 namespace prg {
 
 constexpr int kClCtas = 4;
-constexpr int kClThreads = 256;
-constexpr int kClMaxItems = kClCtas * kClThreads;  // 1024
+constexpr int kClItems = 256;                      // candidates per CTA
+constexpr int kClThreads = 2 * kClItems;           // two threads per candidate (k blocks split)
+constexpr int kClMaxItems = kClCtas * kClItems;    // 1024
 constexpr int kClMaxN = 4096;
 constexpr int kClCRows = 24;
 constexpr double kInvSqrt2c = 0.70710678118654752440;
@@ -40,13 +45,15 @@ struct DppClArgs {
   int32_t* status;
 };
 
-struct __align__(16) CandRec {
+template <int D>
+struct __align__(16) CandRecT {
   double v;       // d2 of the candidate (NaN if the CTA has none)
   double inv;     // 1 / ||e||
   double q;       // exp(alpha * rel)
   int32_t idx;    // index in the truncated list
-  uint32_t row;   // diversity-table row
+  uint32_t row;   // diversity-table row (diagnostics)
   double cj[kClCRows];
+  float x[D];     // the candidate's embedding
 };
 
 __device__ __forceinline__ uint64_t f64_ord_c(double d) {
@@ -62,51 +69,59 @@ __device__ __forceinline__ AmC amc(AmC a, AmC b) {
   return a;
 }
 
-// S[j][i] in gonum Dgemm(NoTrans,Trans) order over D+1 features; x in registers, `other` = f_j in shared memory or
-// nullptr for the diagonal.  Feature d < D is (x*inv)*c (or x*c), feature D is c.
+// One 64-wide k block of gonum's DotUnitary for candidate `it`: positions [k0, k0+len) of the D+1 features, four
+// partial sums by position mod 4 over the full groups, the tail (always the constant feature D) into s0, then
+// (s0+s2)+(s1+s3).  xs = embeddings [d][256] in shared memory; other = f_j (nullptr: the diagonal, g == f).
 template <int D>
-__device__ __forceinline__ double gram_reg(const float (&x)[D], double inv, bool do_norm, const double* other) {
-  // (interleaving the 64-wide blocks for more ILP was tried and measured slower: 0.507 vs 0.449 ms per batch)
-  constexpr int D1 = D + 1;
-  double acc = 0.0;
-#pragma unroll
-  for (int k0 = 0; k0 < D1; k0 += 64) {
-    const int len = (D1 - k0 < 64) ? (D1 - k0) : 64;
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int t = 0; t < 64; ++t) {
-      if (t < len) {
-        const int d = k0 + t;
-        double f;
-        if (d == D) f = kInvSqrt2c;
-        else {
-          const double xv = (double)x[d < D ? d : 0];
-          f = do_norm ? __dmul_rn(__dmul_rn(xv, inv), kInvSqrt2c) : __dmul_rn(xv, kInvSqrt2c);
-        }
-        const double g = other ? other[d] : f;
-        const int lane4 = (t < (len & ~3)) ? (t & 3) : 0;  // full groups of 4 -> 4 partial sums, tail -> s0
-        s[lane4] = __dadd_rn(s[lane4], __dmul_rn(g, f));
-      }
-    }
-    acc = __dadd_rn(acc, __dadd_rn(__dadd_rn(s[0], s[2]), __dadd_rn(s[1], s[3])));
+__device__ __forceinline__ double block_dot(const float* xs, int it, int k0, int len, double inv, bool do_norm,
+                                            const double* other) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const int full = len & ~3;
+  auto feat = [&](int d) -> double {
+    const double xv = (double)xs[d * kClItems + it];
+    return do_norm ? __dmul_rn(__dmul_rn(xv, inv), kInvSqrt2c) : __dmul_rn(xv, kInvSqrt2c);
+  };
+#pragma unroll 2
+  for (int t = 0; t < full; t += 4) {
+    const int d = k0 + t;
+    const double f0 = feat(d), f1 = feat(d + 1), f2 = feat(d + 2), f3 = feat(d + 3);
+    const double g0 = other ? other[d] : f0, g1 = other ? other[d + 1] : f1, g2 = other ? other[d + 2] : f2,
+                 g3 = other ? other[d + 3] : f3;
+    s0 = __dadd_rn(s0, __dmul_rn(g0, f0));
+    s1 = __dadd_rn(s1, __dmul_rn(g1, f1));
+    s2 = __dadd_rn(s2, __dmul_rn(g2, f2));
+    s3 = __dadd_rn(s3, __dmul_rn(g3, f3));
   }
-  return acc;
+  for (int t = full; t < len; ++t) {  // at most one element: the constant feature (position D)
+    const int d = k0 + t;
+    const double f = (d == D) ? kInvSqrt2c : feat(d);
+    const double g = other ? other[d] : f;
+    s0 = __dadd_rn(s0, __dmul_rn(g, f));
+  }
+  return __dadd_rn(__dadd_rn(s0, s2), __dadd_rn(s1, s3));
 }
 
 template <int D>
 __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClArgs a) {
+  using CandRec = CandRecT<D>;
+  constexpr int D1 = D + 1;
+  constexpr int NB = (D1 + 63) / 64;  // k blocks: part 0 owns block 0, part 1 the rest
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
   const int b = blockIdx.x / kClCtas;
   extern __shared__ __align__(16) uint8_t csm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int it = tid & (kClItems - 1), part = tid >> 8;
   const int n = a.n, T_out = a.p.top_n;
   const int window = a.p.window_size > 0 ? a.p.window_size : 10;
 
   double* C = reinterpret_cast<double*>(csm);                                   // [24][256]  (48 KiB, also presort staging)
-  CandRec* pub = reinterpret_cast<CandRec*>(C + kClCRows * kClThreads);         // [2][4]
+  float* xs = reinterpret_cast<float*>(C + kClCRows * kClItems);                // [D][256]
+  CandRec* pub = reinterpret_cast<CandRec*>(xs + D * kClItems);                 // [2][4]
   double* fj = reinterpret_cast<double*>(pub + 2 * kClCtas);                    // [D+1] padded to 136
-  double* red_v = fj + 136;                                                     // [8]
+  double* blk_s = fj + 136;                                                     // [2][256] partial block sums of part 1
+  double* inv_s = blk_s + 2 * kClItems;                                         // [256]
+  double* red_v = inv_s + kClItems;                                             // [8]
   int32_t* red_i = reinterpret_cast<int32_t*>(red_v + 8);                       // [8]
   int32_t* order = red_i + 8;                                                   // [1024]
   int32_t* res = order + kClMaxItems;                                           // [T_out]
@@ -181,8 +196,9 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   }
   __syncthreads();
 
-  const int gi = (int)rank * kClThreads + tid;  // this thread's candidate (index in the truncated list)
+  const int gi = (int)rank * kClItems + it;  // this thread's candidate (index in the truncated list)
   const bool active = gi < m;
+  const bool owner = part == 0;               // part 0 owns d2, C, the publication; part 1 only adds block sums
   const int my_in = active ? order[gi] : 0;
 
   // ---- 1. relevance + abtest normalisation modes (:382-405), redundantly per CTA
@@ -221,59 +237,89 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
     return;
   }
 
-  // ---- 2. the candidate's embedding -> registers; norm (gonum floats.Norm scaled form), quality
-  float x[D];
+  // ---- 2. embeddings -> shared memory [d][item]; norm (gonum floats.Norm scaled form) and quality by the owner
   uint32_t my_row = 0;
   double inv = 1.0, qi = 0.0;
-  {
+  if (owner) {
     my_row = active ? rows[my_in] : 0u;
     const bool have = active && (uint64_t)my_row < a.D_rows;
     if (!have) my_row = 0;
     const float4* src = reinterpret_cast<const float4*>(a.D + (size_t)my_row * D);
-#pragma unroll
-    for (int d4 = 0; d4 < D / 4; ++d4) {
-      const float4 v = have ? src[d4] : make_float4(0.f, 0.f, 0.f, 0.f);
-      x[4 * d4] = v.x; x[4 * d4 + 1] = v.y; x[4 * d4 + 2] = v.z; x[4 * d4 + 3] = v.w;
-    }
     double scale = 0.0, sumsq = 1.0;
+#pragma unroll 4
+    for (int d4 = 0; d4 < D / 4; ++d4) {
+      const float4 v4 = have ? src[d4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float e4[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const double v = (double)x[d];
-      if (v != 0.0) {
-        const double av = fabs(v);
-        if (scale < av) {
-          const double s = scale / av;
-          sumsq = __dadd_rn(1.0, __dmul_rn(__dmul_rn(sumsq, s), s));
-          scale = av;
-        } else {
-          const double s = av / scale;
-          sumsq = __dadd_rn(sumsq, __dmul_rn(s, s));
+      for (int c = 0; c < 4; ++c) {
+        xs[(4 * d4 + c) * kClItems + it] = e4[c];
+        const double v = (double)e4[c];
+        if (v != 0.0) {
+          const double av = fabs(v);
+          if (scale < av) {
+            const double sc = scale / av;
+            sumsq = __dadd_rn(1.0, __dmul_rn(__dmul_rn(sumsq, sc), sc));
+            scale = av;
+          } else {
+            const double sc = av / scale;
+            sumsq = __dadd_rn(sumsq, __dmul_rn(sc, sc));
+          }
         }
       }
     }
     if (a.p.normalize_emb) inv = 1.0 / __dmul_rn(scale, sqrt(sumsq));
     if (active) qi = exp(__dmul_rn(a.p.alpha, rel));
+    inv_s[it] = inv;
   }
   for (int i = tid; i < kClMaxItems; i += kClThreads) existed[i] = 0;
   const bool do_norm = a.p.normalize_emb != 0;
-  const double diag = active ? __dmul_rn(__dmul_rn(qi, gram_reg<D>(x, inv, do_norm, nullptr)), qi) : CUDART_NAN;
+  __syncthreads();
+  inv = inv_s[it];
+
+  // S[j][i] in gonum Dgemm(NoTrans,Trans) order: block sums added to C in block order (0 + b0) + b1 + b2.
+  // part 0 computes block 0, part 1 the remaining blocks -> blk_s; one barrier; the owner finishes.
+  auto gram = [&](const double* other) -> double {
+    double acc = 0.0;
+    if (owner) {
+      acc = __dadd_rn(0.0, block_dot<D>(xs, it, 0, D1 < 64 ? D1 : 64, inv, do_norm, other));
+    } else {
+#pragma unroll
+      for (int bb = 1; bb < NB; ++bb) {
+        const int k0 = bb * 64;
+        blk_s[(bb - 1) * kClItems + it] = block_dot<D>(xs, it, k0, (D1 - k0 < 64) ? (D1 - k0) : 64, inv, do_norm, other);
+      }
+    }
+    if (NB > 1) {
+      __syncthreads();
+      if (owner) {
+#pragma unroll
+        for (int bb = 1; bb < NB; ++bb) acc = __dadd_rn(acc, blk_s[(bb - 1) * kClItems + it]);
+      }
+    }
+    return acc;
+  };
+
+  const double g0 = gram(nullptr);
+  const double diag = (owner && active) ? __dmul_rn(__dmul_rn(qi, g0), qi) : CUDART_NAN;
   __syncthreads();
 
-  // cluster-wide first-maximum argmax; every CTA ends up with the winner's record in pub[par][w]
+  // cluster-wide first-maximum argmax over the owners; every CTA ends up with the winner's record in pub[par][w]
   int par = 0;
   auto cluster_argmax = [&](double v, int krows) -> int {
-    AmC am{v, tid};
+    if (warp < kClItems / 32) {  // owner warps
+      AmC am{v, it};
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      AmC o;
-      o.v = __shfl_xor_sync(0xffffffffu, am.v, off);
-      o.i = __shfl_xor_sync(0xffffffffu, am.i, off);
-      am = amc(am, o);
+      for (int off = 16; off > 0; off >>= 1) {
+        AmC o;
+        o.v = __shfl_xor_sync(0xffffffffu, am.v, off);
+        o.i = __shfl_xor_sync(0xffffffffu, am.i, off);
+        am = amc(am, o);
+      }
+      if (lane == 0) { red_v[warp] = am.v; red_i[warp] = am.i; }
     }
-    if (lane == 0) { red_v[warp] = am.v; red_i[warp] = am.i; }
-    __syncthreads();
+    __syncthreads();  // also: row k of C (written by the owners just before) is complete
     if (warp == 0) {
-      AmC xx{lane < (kClThreads / 32) ? red_v[lane] : CUDART_NAN, lane < (kClThreads / 32) ? red_i[lane] : 0};
+      AmC xx{lane < (kClItems / 32) ? red_v[lane & 7] : CUDART_NAN, lane < (kClItems / 32) ? red_i[lane & 7] : 0};
 #pragma unroll
       for (int off = 4; off > 0; off >>= 1) {
         AmC o;
@@ -285,8 +331,9 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
     }
     __syncthreads();
     const int li = s_li;
-    // publish this CTA's candidate into every CTA's pub[par][rank]
-    if (tid == li) {
+    // publish this CTA's candidate into every CTA's pub[par][rank]: scalars by its owner thread, its column of C by
+    // threads 0..krows-1, its embedding by threads 256..256+D-1 (part 1 is otherwise idle here)
+    if (owner && it == li) {
 #pragma unroll
       for (int r = 0; r < kClCtas; ++r) {
         CandRec* dst = cluster.map_shared_rank(&pub[par * kClCtas + rank], r);
@@ -298,20 +345,23 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
       }
     }
     if (tid < krows) {
-      const double cv = C[tid * kClThreads + li];
+      const double cv = C[tid * kClItems + li];
 #pragma unroll
       for (int r = 0; r < kClCtas; ++r) cluster.map_shared_rank(&pub[par * kClCtas + rank], r)->cj[tid] = cv;
     }
+    if (tid >= kClItems && tid - kClItems < D) {
+      const float xv = xs[(tid - kClItems) * kClItems + li];
+#pragma unroll
+      for (int r = 0; r < kClCtas; ++r) cluster.map_shared_rank(&pub[par * kClCtas + rank], r)->x[tid - kClItems] = xv;
+    }
     cluster.sync();
-    int w = 0;
     AmC best{pub[par * kClCtas].v, 0};
 #pragma unroll
     for (int r = 1; r < kClCtas; ++r) {
       const double rv = pub[par * kClCtas + r].v;
       if (!isnan(rv) && (isnan(best.v) || rv > best.v)) { best.v = rv; best.i = r; }  // lower rank == lower index wins ties
     }
-    w = best.i;
-    const int used = par * kClCtas + w;
+    const int used = par * kClCtas + best.i;
     par ^= 1;
     return used;
   };
@@ -322,7 +372,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   for (int call = 0; call < n_calls; ++call) {
     int top = (T_out <= window) ? T_out : ((call < T_out / window) ? window : T_out % window);
     if (top > m) top = m;
-    double d2 = (active && !existed[gi]) ? diag : CUDART_NAN;
+    double d2 = (owner && active && !existed[gi]) ? diag : CUDART_NAN;
     int wrec = cluster_argmax(d2, 0);
     int j = isnan(pub[wrec].v) ? 0 : pub[wrec].idx;
     if (tid == 0) res[total] = j;
@@ -336,35 +386,33 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
       const double inv_dj = 1.0 / dj;
       const int k = ny - 1;
       const double inv_j = W.inv, q_j = W.q;
-      {
-        const float* rj = a.D + (size_t)W.row * D;
-        if (tid < D) {
-          const double xv = (double)rj[tid];
-          fj[tid] = do_norm ? __dmul_rn(__dmul_rn(xv, inv_j), kInvSqrt2c) : __dmul_rn(xv, kInvSqrt2c);
-        }
-        if (tid == D % kClThreads && D < kClThreads) fj[D] = kInvSqrt2c;
-        if (D >= kClThreads && tid == 0) fj[D] = kInvSqrt2c;
+      if (tid < D) {
+        const double xv = (double)W.x[tid];
+        fj[tid] = do_norm ? __dmul_rn(__dmul_rn(xv, inv_j), kInvSqrt2c) : __dmul_rn(xv, kInvSqrt2c);
       }
+      if (tid == D) fj[D] = kInvSqrt2c;
       __syncthreads();
-      double e = CUDART_NAN;
-      if (active) {
-        const double Lji = __dmul_rn(__dmul_rn(q_j, gram_reg<D>(x, inv, do_norm, fj)), qi);
-        if (k == 0) {
-          e = __dmul_rn(inv_dj, Lji);
-        } else {
-          double ss = 0.0;
-          for (int l = 0; l < k; ++l) {
-            const double tmp = W.cj[l];
-            if (tmp != 0) ss = __dadd_rn(ss, __dmul_rn(tmp, C[l * kClThreads + tid]));
+      const double S = gram(fj);
+      if (owner) {
+        if (active) {
+          const double Lji = __dmul_rn(__dmul_rn(q_j, S), qi);
+          double e;
+          if (k == 0) {
+            e = __dmul_rn(inv_dj, Lji);
+          } else {
+            double ss = 0.0;
+            for (int l = 0; l < k; ++l) {
+              const double tmp = W.cj[l];
+              if (tmp != 0) ss = __dadd_rn(ss, __dmul_rn(tmp, C[l * kClItems + it]));
+            }
+            e = __dmul_rn(inv_dj, __dsub_rn(Lji, ss));
           }
-          e = __dmul_rn(inv_dj, __dsub_rn(Lji, ss));
+          C[k * kClItems + it] = e;
+          d2 = __dsub_rn(d2, __dmul_rn(e, e));
         }
-        C[k * kClThreads + tid] = e;
-        d2 = __dsub_rn(d2, __dmul_rn(e, e));
+        if (gi == j) d2 = CUDART_NAN;
       }
-      if (gi == j) d2 = CUDART_NAN;
-      __syncthreads();  // C row k complete before the next candidate's column is read; fj free for reuse
-      wrec = cluster_argmax(d2, ny);
+      wrec = cluster_argmax(d2, ny);  // its first barrier also orders the C[k] writes before the column reads
       j = isnan(pub[wrec].v) ? 0 : pub[wrec].idx;
       if (tid == 0) res[total + ny] = j;
       ++ny;
@@ -396,14 +444,15 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   cluster.sync();  // no CTA may exit while peers can still write into its shared memory
 }
 
+template <int D>
 static size_t dpp_cluster_smem(int top_n) {
-  return (size_t)kClCRows * kClThreads * 8 + 2 * kClCtas * sizeof(CandRec) + 136 * 8 + 8 * 8 + 8 * 4 + kClMaxItems * 4 +
-         (size_t)((top_n + 3) & ~3) * 4 + kClMaxItems + 64;
+  return (size_t)kClCRows * kClItems * 8 + (size_t)D * kClItems * 4 + 2 * kClCtas * sizeof(CandRecT<D>) + 136 * 8 +
+         2 * kClItems * 8 + kClItems * 8 + 8 * 8 + 8 * 4 + kClMaxItems * 4 + (size_t)((top_n + 3) & ~3) * 4 + kClMaxItems + 64;
 }
 
 template <int D>
 static int launch_cluster(prg_handle* h, const DppClArgs& a, int B) {
-  const size_t smem = dpp_cluster_smem(a.p.top_n);
+  const size_t smem = dpp_cluster_smem<D>(a.p.top_n);
   PRG_CUDA(cudaFuncSetAttribute(dpp_cluster_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(B * kClCtas));

@@ -83,6 +83,7 @@ struct prg_handle {
   prg::DevBuf mlp_b[prg::kMaxLayers];
   CUtensorMap mlp_Wmap[prg::kMaxLayers];
   float mlp_b_last = 0.f;
+  bool mlp_one_tile_per_cta = false;  // config "mlp_one_tile": the non-persistent layer kernel (A/B measurements)
   prg::DevBuf act[2];   // activations ping-pong (bf16)
   prg::DevBuf fm_logit; // B*n f32
   prg::DevBuf rank_rows, rank_out;

@@ -166,6 +166,172 @@ mlp_layer_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------ persistent variant (used by mlp_forward_device)
+// One CTA per SM loops over output tiles; the accumulator is double buffered in TMEM (2 x BN columns) so the epilogue
+// of tile i (8 warps: two per TMEM lane quarter, each taking half of the columns) overlaps the MMAs of tile i+1, and
+// the per-CTA prologue (TMEM alloc, barrier init, first TMA round trip) is paid once per SM instead of once per tile.
+// ncu r1 of the one-tile-per-CTA kernel above: tensor pipe 30 % active — MMA and epilogue were serialised.
+constexpr int kMlpPThreads = 320;
+constexpr int kMlpEpiWarps = 8;
+
+template <int BN>
+constexpr size_t mlp_p_smem_bytes() {
+  return (size_t)kMlpStages * (kMlpBM * 128 + BN * 128) + 2 * 1024 * 4 /*bias, w_last*/ + 2 * 2 * kMlpBM * 4 /*partials*/ +
+         (2 * kMlpStages + 4) * 8 + 16;
+}
+
+template <int BN, bool FINAL>
+__global__ void __launch_bounds__(kMlpPThreads, 1)
+mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                            const MlpLayerParams p, const int n_mblk) {
+  extern __shared__ __align__(1024) uint8_t msm[];
+  constexpr int kABytes = kMlpBM * 128, kBBytes = BN * 128, kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  float* bias_s = reinterpret_cast<float*>(msm + (size_t)kMlpStages * kStageBytes);  // [1024]
+  float* wl_s = bias_s + 1024;                                                       // [1024]
+  float* part_s = wl_s + 1024;                                                       // [2 buf][2 halves][128]
+  uint64_t* full = reinterpret_cast<uint64_t*>(part_s + 4 * kMlpBM);
+  uint64_t* empty = full + kMlpStages;
+  uint64_t* tfull = empty + kMlpStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_nblk = p.N / BN;
+  const int n_tiles = n_mblk * n_nblk;
+  const int num_kb = 2 * p.K / kMlpBK;
+  const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  for (int i = tid; i < p.N; i += kMlpPThreads) {
+    bias_s[i] = p.bias ? p.bias[i] : 0.f;
+    wl_s[i] = FINAL ? p.w_last[i] : 0.f;
+  }
+  if (tid == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < kMlpStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kMlpEpiWarps); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int t = (int)blockIdx.x + i * (int)gridDim.x;
+        const int m_blk = t / n_nblk, n_blk = t - m_blk * n_nblk;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % kMlpStages, ph = (it / kMlpStages) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], kStageBytes);
+          uint8_t* a_dst = msm + (size_t)s * kStageBytes;
+          tma_load_2d(a_dst, &mapA, kb * kMlpBK, m_blk * kMlpBM, &full[s], kEvictNormal);
+          tma_load_2d(a_dst + kABytes, &mapW, (kb * kMlpBK) % p.K, n_blk * BN, &full[s], kEvictLast);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kMlpBM >> 4) << 24);
+      uint32_t it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const uint32_t buf = (uint32_t)i & 1u;
+        mbar_wait(&tempty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + buf * (uint32_t)BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % kMlpStages, ph = (it / kMlpStages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(msm + (size_t)s * kStageBytes);
+          const uint64_t adesc = umma_desc_k_sw128(a_addr), bdesc = umma_desc_k_sw128(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kMlpBK / 16; ++k)
+            umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    const int ew = warp - 2;
+    const int quarter = warp & 3, chalf = ew >> 2;
+    constexpr int kHalf = BN / 2;
+    for (int i = 0; i < my_tiles; ++i) {
+      const uint32_t buf = (uint32_t)i & 1u;
+      const int t = (int)blockIdx.x + i * (int)gridDim.x;
+      const int m_blk = t / n_nblk, n_blk = t - m_blk * n_nblk;
+      const int row = m_blk * kMlpBM + quarter * 32 + lane;
+      mbar_wait(&tfull[buf], ((uint32_t)i >> 1) & 1u);
+      tc_fence_after();
+      float logit = 0.f;
+#pragma unroll 1
+      for (int c0 = chalf * kHalf; c0 < (chalf + 1) * kHalf; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)BN + (uint32_t)c0, v);
+        if (c0 + 32 >= (chalf + 1) * kHalf) {  // last read of this tile by this warp: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+        const int nb = n_blk * BN + c0;  // column in the layer's output
+        uint32_t hi_w[16], lo_w[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float r0 = fmaxf(__fadd_rn(__uint_as_float(v[c]), bias_s[nb + c]), 0.f);
+          float r1 = fmaxf(__fadd_rn(__uint_as_float(v[c + 1]), bias_s[nb + c + 1]), 0.f);
+          const uint16_t h0 = __bfloat16_as_ushort(__float2bfloat16_rn(r0)), h1 = __bfloat16_as_ushort(__float2bfloat16_rn(r1));
+          const float h0f = __uint_as_float((uint32_t)h0 << 16), h1f = __uint_as_float((uint32_t)h1 << 16);
+          const uint16_t l0 = __bfloat16_as_ushort(__float2bfloat16_rn(__fsub_rn(r0, h0f)));
+          const uint16_t l1 = __bfloat16_as_ushort(__float2bfloat16_rn(__fsub_rn(r1, h1f)));
+          if (FINAL) {
+            const float a0 = __fadd_rn(h0f, __uint_as_float((uint32_t)l0 << 16));
+            const float a1 = __fadd_rn(h1f, __uint_as_float((uint32_t)l1 << 16));
+            logit = __fmaf_rn(wl_s[nb + c], a0, logit);
+            logit = __fmaf_rn(wl_s[nb + c + 1], a1, logit);
+          } else {
+            hi_w[c >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            lo_w[c >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+          }
+        }
+        if (!FINAL) {
+          uint16_t* o = p.out + (size_t)row * (2 * p.N) + (size_t)nb;
+          uint4* oh = reinterpret_cast<uint4*>(o);
+          uint4* ol = reinterpret_cast<uint4*>(o + p.N);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            oh[w] = make_uint4(hi_w[4 * w], hi_w[4 * w + 1], hi_w[4 * w + 2], hi_w[4 * w + 3]);
+            ol[w] = make_uint4(lo_w[4 * w], lo_w[4 * w + 1], lo_w[4 * w + 2], lo_w[4 * w + 3]);
+          }
+        }
+      }
+      if (FINAL) {  // logit = b + (columns of half 0) + (columns of half 1): the two warps of a lane quarter combine
+        part_s[(buf * 2 + chalf) * kMlpBM + quarter * 32 + lane] = logit;
+        asm volatile("bar.sync 1, %0;" ::"n"(kMlpEpiWarps * 32) : "memory");
+        if (chalf == 0 && row < p.M)
+          p.logit_out[row] = __fadd_rn(__fadd_rn(part_s[(buf * 2) * kMlpBM + quarter * 32 + lane],
+                                                 part_s[(buf * 2 + 1) * kMlpBM + quarter * 32 + lane]), p.b_last);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
 // ------------------------------------------------------------------ host side
 static int encode_bf16_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode_tiled();
@@ -188,6 +354,17 @@ static int tile_n(uint32_t N) {
 
 template <int BN, bool FINAL>
 static int launch_layer(prg_handle* h, const CUtensorMap& mapA, const CUtensorMap& mapW, const MlpLayerParams& p, int Mp) {
+  if (!h->mlp_one_tile_per_cta && p.N <= 1024) {
+    const size_t smem = mlp_p_smem_bytes<BN>();
+    PRG_CUDA(cudaFuncSetAttribute(mlp_layer_persistent_kernel<BN, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    const int n_mblk = Mp / kMlpBM, tiles = n_mblk * (p.N / BN);
+    const unsigned grid = (unsigned)(tiles < h->sm_count ? tiles : h->sm_count);
+    mlp_layer_persistent_kernel<BN, FINAL><<<grid, kMlpPThreads, smem, h->stream>>>(mapA, mapW, p, n_mblk);
+    PRG_CUDA(cudaGetLastError());
+    count_launch(h);
+    return PRG_OK;
+  }
   const size_t smem = mlp_smem_bytes<BN>();
   PRG_CUDA(cudaFuncSetAttribute(mlp_layer_kernel<BN, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)(Mp / kMlpBM), (unsigned)(p.N / BN));
