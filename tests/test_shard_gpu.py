@@ -1,0 +1,70 @@
+"""Row-sharded path on ONE GPU: two engines hold the two shards (row_base 0 / N/2), their local top-k key
+lists are concatenated exactly as the all-gather would lay them out, and prg_merge_keys / prg_recommend_from_keys must
+give the unsharded result.  (bench.py --gpus N runs the same entry points with torch.distributed/NCCL in between.)"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_shards_merge_to_unsharded_result(oracle_lib):
+    import torch
+    from pairec_b200 import DppParams, Engine
+    from pairec_b200.binding import MEM_DEVICE, MODEL_FM
+    n, d, B, k, T = 600_000, 64, 70, 300, 15     # B = 70: two query blocks of <= 64
+    rng = np.random.default_rng(31)
+    E = (rng.standard_normal((n, d)) / 8).astype(np.float32)
+    E[n // 2:n // 2 + 500] = E[:500]              # ties across the shard boundary
+    Q = (rng.standard_normal((B, d)) / 8).astype(np.float32)
+    dev = torch.device("cuda:0")
+    half = n // 2
+    engs = [Engine(0), Engine(0)]
+    try:
+        engs[0].set_item_matrix(E[:half], row_base=0)
+        engs[1].set_item_matrix(E[half:], row_base=half)
+        q_dev = torch.from_numpy(Q).to(dev)
+        keys_all = torch.zeros(2, B, k, dtype=torch.int64, device=dev)       # the all-gather output layout [G][B][k]
+        for g in range(2):
+            engs[g].recall_local_keys_dev(q_dev.data_ptr(), B, k, keys_all[g].data_ptr())
+            engs[g].sync()
+        full = oracle_lib.recall_topk(E, Q, k)
+        # per-shard lists equal the oracle's per-shard lists
+        for g, (lo, hi) in enumerate(((0, half), (half, n))):
+            want = oracle_lib.recall_topk(E[lo:hi], Q, k, row_base=lo)
+            assert (keys_all[g].cpu().numpy().view(np.uint64) == want).all()
+        rows, scores, cnt = engs[0].merge_keys(keys_all.data_ptr(), 2, B, k)
+        orows, oscores, on = oracle_lib.keys_split(full)
+        assert (rows == orows).all() and (scores.view(np.uint32) == oscores.view(np.uint32)).all() and (cnt == on).all()
+
+        # downstream of the merge on a slice of the requests (what each rank does for its own 64)
+        fields, factors, linear = synth.rank_tables(n_items=n, n_fields=32)
+        Dm = synth.diversity(n_items=n, dim=32)
+        e = engs[1]
+        e.set_item_fields(fields)
+        for t, (f, l) in enumerate(zip(factors, linear)):
+            e.set_feature_table(t, f, l)
+        e.set_fm_bias(0.05)
+        e.set_diversity_matrix(Dm)
+        b0, nb = 6, 5                                                         # requests 6..10 of the global batch
+        out_rows = torch.empty(nb, T, dtype=torch.int32, device=dev)
+        out_sc = torch.empty(nb, T, dtype=torch.float64, device=dev)
+        out_n = torch.empty(nb, dtype=torch.int32, device=dev)
+        p = DppParams(top_n=T, alpha=1.0, window_size=10)
+        e.recommend_from_keys_dev(keys_all.data_ptr() + b0 * k * 8, 2, B * k, nb, k, MODEL_FM, p, out_rows.data_ptr(),
+                                  out_sc.data_ptr(), out_n.data_ptr())
+        e.sync()
+        got_rows = out_rows.cpu().numpy().view(np.uint32)
+        for i in range(nb):
+            r = orows[b0 + i]
+            logit, _ = oracle_lib.gather_fm(fields, factors, linear, 0.05, r, want_x=False)
+            sc = oracle_lib.sigmoid(logit).astype(np.float64)
+            perm = oracle_lib.stable_sort_desc(sc)
+            idx, st = oracle_lib.dpp_request(Dm[r[perm]].astype(np.float64), sc[perm], T, alpha=1.0, window_size=10)
+            assert st == 0 and (got_rows[i, :len(idx)] == r[perm][idx]).all()
+    finally:
+        for g in engs:
+            g.close()
