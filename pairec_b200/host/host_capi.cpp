@@ -40,6 +40,7 @@ int ph_create(const char* recconf_json, ph_server** out) {
   ResetRegistries();
   algorithm::Load(s->conf);   // pairec.go:88-109 runBeforeStart order: algorithm.Load, then register(conf)
   recall::Load(s->conf);
+  filter::Load(s->conf);
   sort::Load(s->conf);
   *out = s;
   return 0;
@@ -147,6 +148,31 @@ long long ph_recommend(ph_server* s, const char* request_json, char* out, unsign
   const long long need = (long long)o.size() + 1;
   if (out && cap >= (unsigned long long)need) memcpy(out, o.c_str(), (size_t)need);
   return need;
+}
+
+// sort/dpp_sort.go:224-233 embedding text -> doubles; returns the element count (writes up to cap)
+long long ph_parse_embedding(const char* text, const char* sep, double* out, unsigned long long cap) {
+  auto v = ingest::ParseEmbeddingText(text ? text : "", sep ? sep : "");
+  for (size_t i = 0; i < v.size() && i < cap; ++i) out[i] = v[i];
+  return (long long)v.size();
+}
+// recall cache round trip (vector_recall.go:35-58,103-110): ids/scores -> string -> JSON list of {item_id, score}
+long long ph_recall_cache_roundtrip(const char* const* ids, const double* scores, int n, const char* model, char* out,
+                                    unsigned long long cap, char* cache_out, unsigned long long cache_cap) {
+  std::vector<module::ItemPtr> items;
+  for (int i = 0; i < n; ++i) { auto it = module::NewItem(ids[i]); it->Score = scores[i]; items.push_back(it); }
+  const std::string cache = ingest::FormatRecallCache(items, model);
+  if (cache_out && cache_cap > cache.size()) memcpy(cache_out, cache.c_str(), cache.size() + 1);
+  auto back = ingest::ParseRecallCache(cache, model, "");
+  std::string o = "[";
+  for (size_t i = 0; i < back.size(); ++i) {
+    if (i) o += ",";
+    o += "{\"item_id\":" + Json::quote(back[i]->Id) + ",\"score\":" + Json::number(back[i]->Score) + ",\"retrieve_id\":" +
+         Json::quote(back[i]->RetrieveId) + "}";
+  }
+  o += "]";
+  if (out && cap > o.size()) memcpy(out, o.c_str(), o.size() + 1);
+  return (long long)o.size() + 1;
 }
 
 // utils/ast known-answer entry: evaluates an expression over named values (names[i] -> values[i])

@@ -70,6 +70,24 @@ Error LoadConfig(const std::string& json, RecommendConfig* out) {
     c.DPPConf.FilterRetrieveIds = str_list(d["FilterRetrieveIds"]);
     out->SortConfs.push_back(c);
   }
+  for (auto& f : root["FilterConfs"].arr) {
+    FilterConfig c;
+    c.Name = f["Name"].as_string();
+    c.FilterType = f["FilterType"].as_string();
+    c.RetainNum = f["RetainNum"].as_int();
+    c.ShuffleItem = f["ShuffleItem"].as_bool(false);
+    out->FilterConfs.push_back(c);
+  }
+  for (auto& g : root["GeneralRankConfs"].obj) {
+    GeneralRankConfig c;
+    const Json& rc = g.second["RankConf"];
+    c.RankConf.RankAlgoList = str_list(rc["RankAlgoList"]);
+    c.RankConf.RankScore = rc["RankScore"].as_string();
+    c.RankConf.Processor = rc["Processor"].as_string();
+    c.RankConf.BatchCount = rc["BatchCount"].as_int();
+    for (auto& a : g.second["ActionConfs"].arr) c.ActionConfs.push_back({a["ActionType"].as_string(), a["ActionName"].as_string()});
+    out->GeneralRankConfs[g.first] = c;
+  }
   out->UserDefineConfs = root["UserDefineConfs"];
   return "";
 }
@@ -461,7 +479,10 @@ void Rank(module::User* user, std::vector<module::ItemPtr>& items, context::Reco
   if (!ctx->Config) return;
   auto rc = ctx->Config->RankConf.find(scene);
   if (rc == ctx->Config->RankConf.end()) return;  // rank_service.go:153-157: no config -> no rank
-  const recconf::RankConfig& rankConfig = rc->second;
+  RankWithConfig(rc->second, user, items, ctx);
+}
+void RankWithConfig(const recconf::RankConfig& rankConfig, module::User* user, std::vector<module::ItemPtr>& items,
+                    context::RecommendContext* ctx) {
   int batchCount = rankConfig.BatchCount > 0 ? rankConfig.BatchCount : 100;  // :163-166
   if (rankConfig.RankAlgoList.empty() && rankConfig.RankScore.empty()) return;
   const module::Features userFeatures = user ? user->MakeUserFeatures() : module::Features();
@@ -661,6 +682,152 @@ void UniqueFilter(std::vector<module::ItemPtr>* items) {
 }
 }  // namespace filter
 
+namespace filter {
+namespace {
+std::map<std::string, std::shared_ptr<IFilter>>& fregistry() {
+  static std::map<std::string, std::shared_ptr<IFilter>> m;
+  return m;
+}
+struct UniqueFilterImpl : IFilter {
+  Error Filter(FilterData* d) override { UniqueFilter(&d->Data); return ""; }
+};
+struct AdjustCountFilter : IFilter {  // filter/adjust_count_filter.go:37-77
+  int retainNum;
+  bool shuffleItem;
+  Error Filter(FilterData* d) override {
+    if ((int)d->Data.size() <= retainNum) return "";
+    if (shuffleItem) return "AdjustCountFilter: ShuffleItem uses an unseeded math/rand upstream; not reproducible here";
+    d->Data.resize((size_t)retainNum);
+    return "";
+  }
+};
+}  // namespace
+void RegisterFilter(const std::string& name, std::shared_ptr<IFilter> f) { fregistry()[name] = std::move(f); }
+Error GetFilter(const std::string& name, std::shared_ptr<IFilter>* out) {
+  auto it = fregistry().find(name);
+  if (it == fregistry().end()) return "Filter not found, name:" + name;
+  *out = it->second;
+  return "";
+}
+void Load(const recconf::RecommendConfig& c) {
+  RegisterFilter("UniqueFilter", std::make_shared<UniqueFilterImpl>());
+  for (auto& fc : c.FilterConfs) {
+    if (fc.FilterType == "AdjustCountFilter") {
+      auto f = std::make_shared<AdjustCountFilter>();
+      f->retainNum = fc.RetainNum;
+      f->shuffleItem = fc.ShuffleItem;
+      RegisterFilter(fc.Name, f);
+    }
+  }
+}
+void ResetFilters() { fregistry().clear(); }
+}  // namespace filter
+
+// ================================================================================================ general rank
+namespace general_rank {
+std::vector<module::ItemPtr> Rank(module::User* user, std::vector<module::ItemPtr> items, context::RecommendContext* ctx) {
+  if (!ctx->Config) return items;
+  auto gc = ctx->Config->GeneralRankConfs.find(ctx->GetParameter("scene"));
+  if (gc == ctx->Config->GeneralRankConfs.end()) return items;  // general_rank.go:216-262: no config, items pass through
+  recconf::RankConfig rc = gc->second.RankConf;
+  if (rc.BatchCount <= 0) rc.BatchCount = 100;                  // base_general_rank.go:58-60
+  if (!rc.RankAlgoList.empty()) rank::RankWithConfig(rc, user, items, ctx);
+  for (auto& ac : gc->second.ActionConfs) {                     // action.go:40-83
+    if (ac.ActionType == "sort") {
+      std::shared_ptr<sort::ISort> s;
+      Error e = sort::GetSort(ac.ActionName, &s);
+      if (!e.empty()) { ctx->LogError("create action error:" + e); continue; }
+      sort::SortData sd;
+      sd.Data = items; sd.Context = ctx; sd.User = user;
+      s->Sort(&sd);
+      items = sd.Data;
+    } else if (ac.ActionType == "filter") {
+      std::shared_ptr<filter::IFilter> f;
+      Error e = filter::GetFilter(ac.ActionName, &f);
+      if (!e.empty()) { ctx->LogError("create action error:" + e); continue; }
+      filter::FilterData fd;
+      fd.Data = items; fd.Uid = user ? user->Id : ""; fd.Context = ctx;
+      e = f->Filter(&fd);
+      if (!e.empty()) ctx->LogError("module=general_rank\tfilter error=" + e);
+      items = fd.Data;
+    } else {
+      ctx->LogError("create action error:error to find actionType:" + ac.ActionType);
+    }
+  }
+  return items;
+}
+}  // namespace general_rank
+
+// ================================================================================================ ingest
+namespace ingest {
+std::vector<double> ParseEmbeddingText(const std::string& text, const std::string& sep_in) {
+  const std::string sep = sep_in.empty() ? "," : sep_in;  // dpp_sort.go:92-94
+  size_t a = 0, b = text.size();
+  while (a < b && (text[a] == '{' || text[a] == '}')) ++a;   // strings.Trim(s, "{}")
+  while (b > a && (text[b - 1] == '{' || text[b - 1] == '}')) --b;
+  std::vector<double> out;
+  const std::string body = text.substr(a, b - a);
+  size_t pos = 0;
+  for (;;) {
+    const size_t nx = body.find(sep, pos);
+    const std::string tok = body.substr(pos, nx == std::string::npos ? std::string::npos : nx - pos);
+    char* end = nullptr;
+    const double v = strtod(tok.c_str(), &end);
+    out.push_back((end && end != tok.c_str() && *end == 0) ? v : 0.0);  // ParseFloat error -> element stays 0
+    if (nx == std::string::npos) break;
+    pos = nx + sep.size();
+  }
+  return out;
+}
+std::string FormatRecallCache(const std::vector<module::ItemPtr>& items, const std::string& modelName) {
+  std::string s;
+  for (size_t i = 0; i < items.size(); ++i) {
+    if (i) s += ",";
+    char buf[64];
+    // fmt.Sprintf("%s:%s:%v", id, modelName, score): %v of a float64 is strconv 'g' with the shortest repr
+    snprintf(buf, sizeof buf, "%.17g", items[i]->Score);
+    double back = strtod(buf, nullptr);
+    for (int prec = 1; prec < 17; ++prec) {  // shortest round-tripping representation
+      char b2[64];
+      snprintf(b2, sizeof b2, "%.*g", prec, items[i]->Score);
+      if (strtod(b2, nullptr) == items[i]->Score) { snprintf(buf, sizeof buf, "%s", b2); break; }
+    }
+    (void)back;
+    s += items[i]->Id + ":" + modelName + ":" + buf;
+  }
+  return s;
+}
+std::vector<module::ItemPtr> ParseRecallCache(const std::string& s, const std::string& modelName, const std::string& itemType) {
+  std::vector<module::ItemPtr> ret;
+  size_t pos = 0;
+  while (pos <= s.size()) {
+    const size_t nx = s.find(',', pos);
+    const std::string id = s.substr(pos, nx == std::string::npos ? std::string::npos : nx - pos);
+    module::ItemPtr item;
+    if (id.find(':') != std::string::npos) {  // vector_recall.go:42-48: vars[0] = id, vars[2] = score
+      std::vector<std::string> vars;
+      size_t p = 0;
+      for (;;) {
+        const size_t c = id.find(':', p);
+        vars.push_back(id.substr(p, c == std::string::npos ? std::string::npos : c - p));
+        if (c == std::string::npos) break;
+        p = c + 1;
+      }
+      item = module::NewItem(vars[0]);
+      if (vars.size() > 2) item->Score = strtod(vars[2].c_str(), nullptr);
+    } else {
+      item = module::NewItem(id);
+    }
+    item->RetrieveId = modelName;
+    item->ItemType = itemType;
+    ret.push_back(item);
+    if (nx == std::string::npos) break;
+    pos = nx + 1;
+  }
+  return ret;
+}
+}  // namespace ingest
+
 // ================================================================================================ service
 namespace service {
 std::vector<module::ItemPtr> Recommend(module::User* user, context::RecommendContext* ctx) {
@@ -687,10 +854,18 @@ std::vector<module::ItemPtr> Recommend(module::User* user, context::RecommendCon
   // Filter (service/recommend.go:28-35): FilterNames[scene] or ["default"]
   auto fn = conf->FilterNames.find(scene);
   if (fn == conf->FilterNames.end()) fn = conf->FilterNames.find("default");
-  if (fn != conf->FilterNames.end())
-    for (auto& f : fn->second)
-      if (f == "UniqueFilter") filter::UniqueFilter(&items);
-  rank::Rank(user, items, ctx);
+  if (fn != conf->FilterNames.end()) {
+    for (auto& name : fn->second) {
+      std::shared_ptr<filter::IFilter> f;
+      if (!filter::GetFilter(name, &f).empty()) continue;
+      filter::FilterData fd;
+      fd.Data = items; fd.Uid = user ? user->Id : ""; fd.Context = ctx;
+      f->Filter(&fd);
+      items = fd.Data;
+    }
+  }
+  items = general_rank::Rank(user, items, ctx);   // user_recommend.go:116
+  rank::Rank(user, items, ctx);                   // :137
   sort::SortData sd;
   sd.Data = items;
   sd.Context = ctx;
@@ -702,7 +877,9 @@ std::vector<module::ItemPtr> Recommend(module::User* user, context::RecommendCon
 }
 }  // namespace service
 
+namespace filter { void ResetFilters(); }
 void ResetRegistries() {
+  filter::ResetFilters();
   sort::mapping().clear();
   sort::strategies().clear();
   recall::registry().clear();

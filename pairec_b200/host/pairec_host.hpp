@@ -51,6 +51,9 @@ struct DPPSortConfig {
 };
 struct SortConfig { std::string Name, SortType, SortByField; double SwitchThreshold = 0; DPPSortConfig DPPConf; };
 struct SceneCategory { std::vector<std::string> RecallNames; };
+struct FilterConfig { std::string Name, FilterType; int RetainNum = 0; bool ShuffleItem = false; };   // recconf.go FilterConfig
+struct ActionConfig { std::string ActionType, ActionName; };                                          // :746-749
+struct GeneralRankConfig { RankConfig RankConf; std::vector<ActionConfig> ActionConfs; };             // :934-938
 struct RecommendConfig {
   std::string RunMode;
   std::vector<AlgoConfig> AlgoConfs;
@@ -59,6 +62,8 @@ struct RecommendConfig {
   std::map<std::string, RankConfig> RankConf;
   std::map<std::string, std::vector<std::string>> SortNames, FilterNames;
   std::vector<SortConfig> SortConfs;
+  std::vector<FilterConfig> FilterConfs;
+  std::map<std::string, GeneralRankConfig> GeneralRankConfs;
   Json UserDefineConfs;
 };
 // recconf.LoadConfig (recconf/recconf.go:1089-1100) from a JSON string
@@ -236,6 +241,15 @@ Error Eval(const Expr& e, const std::function<bool(const std::string&, double*)>
 }  // namespace ast
 namespace rank {
 void Rank(module::User* user, std::vector<module::ItemPtr>& items, context::RecommendContext* ctx);  // RankService.Rank
+// the shared core: batches -> algorithm.Run -> AddAlgoScore -> RankScore expression (rank_service.go:163-363)
+void RankWithConfig(const recconf::RankConfig& rankConfig, module::User* user, std::vector<module::ItemPtr>& items,
+                    context::RecommendContext* ctx);
+}
+namespace general_rank {
+// GeneralRankService.Rank (service/general_rank/general_rank.go:216) -> BaseGeneralRank.DoRank
+// (base_general_rank.go:66-109): pre-rank with GeneralRankConfs[scene].RankConf, then the Actions (sort / filter by
+// registered name, action.go:61-83) — the second caller of the same rank kernels, over the whole recall set.
+std::vector<module::ItemPtr> Rank(module::User* user, std::vector<module::ItemPtr> items, context::RecommendContext* ctx);
 }
 
 // ------------------------------------------------------------------------------------------------ sort
@@ -279,7 +293,25 @@ class GpuDPPSort : public ISort {
 }  // namespace sort
 
 namespace filter {
+struct FilterData { std::vector<module::ItemPtr> Data; std::string Uid; context::RecommendContext* Context = nullptr; };
+struct IFilter {  // filter/filter.go:32-34
+  virtual ~IFilter() = default;
+  virtual Error Filter(FilterData* d) = 0;
+};
+void RegisterFilter(const std::string& name, std::shared_ptr<IFilter> f);
+Error GetFilter(const std::string& name, std::shared_ptr<IFilter>* out);
+void Load(const recconf::RecommendConfig& c);            // UniqueFilter + FilterConfs (AdjustCountFilter)
 void UniqueFilter(std::vector<module::ItemPtr>* items);  // filter/unique_filter.go:26-49
+}
+
+// ------------------------------------------------------------------------------------------------ table ingest formats
+namespace ingest {
+// "{v1,v2,...}" embedding text of the Hologres tables DPP reads (sort/dpp_sort.go:224-233): Trim "{}", Split by
+// the separator, ParseFloat each element (an unparsable element stays 0, as upstream logs and continues).
+std::vector<double> ParseEmbeddingText(const std::string& text, const std::string& sep);
+// recall result cache "id:name:score,id:name:score" (service/recall/vector_recall.go:35-58 read, :103-110 write)
+std::string FormatRecallCache(const std::vector<module::ItemPtr>& items, const std::string& modelName);
+std::vector<module::ItemPtr> ParseRecallCache(const std::string& s, const std::string& modelName, const std::string& itemType);
 }
 
 // ------------------------------------------------------------------------------------------------ service

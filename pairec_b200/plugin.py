@@ -88,3 +88,26 @@ def eval_expr(expr, values):
     if lib.ph_eval_expr(expr.encode(), arr, vals, C.c_int(len(names)), C.byref(out)) != 0:
         raise HostError(lib.ph_last_error().decode())
     return out.value
+
+
+def parse_embedding(text, sep=","):
+    """sort/dpp_sort.go:224-233 embedding text ("{v1,v2,...}") -> list of float."""
+    lib = load_host_library()
+    lib.ph_parse_embedding.restype = C.c_longlong
+    n = lib.ph_parse_embedding(text.encode(), sep.encode(), None, C.c_ulonglong(0))
+    buf = (C.c_double * int(n))()
+    lib.ph_parse_embedding(text.encode(), sep.encode(), buf, C.c_ulonglong(n))
+    return list(buf)
+
+
+def recall_cache_roundtrip(ids, scores, model):
+    """Formats the recall-result cache string (vector_recall.go:103-110) and parses it back (:35-58)."""
+    lib = load_host_library()
+    lib.ph_recall_cache_roundtrip.restype = C.c_longlong
+    arr = (C.c_char_p * len(ids))(*[i.encode() for i in ids])
+    sc = (C.c_double * len(ids))(*[float(s) for s in scores])
+    out = C.create_string_buffer(1 << 20)
+    cache = C.create_string_buffer(1 << 20)
+    lib.ph_recall_cache_roundtrip(arr, sc, C.c_int(len(ids)), model.encode(), out, C.c_ulonglong(1 << 20), cache,
+                                  C.c_ulonglong(1 << 20))
+    return cache.value.decode(), json.loads(out.value.decode())

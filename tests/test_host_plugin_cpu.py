@@ -113,3 +113,42 @@ def test_bad_recconf_is_an_error_not_a_crash():
     from pairec_b200.plugin import HostError, HostServer
     with pytest.raises(HostError):
         HostServer("{not json")
+
+
+def test_general_rank_prerank_then_actions(oracle_lib):
+    # service/general_rank: pre-rank the whole recall set with the scene's GeneralRankConfs.RankConf, then the actions
+    # (sort by a registered ISort, truncate with AdjustCountFilter) before the main rank (user_recommend.go:116,137)
+    from pairec_b200.plugin import HostServer
+    conf = dict(RECCONF)
+    conf["FilterConfs"] = [{"Name": "keep100", "FilterType": "AdjustCountFilter", "RetainNum": 100, "ShuffleItem": False}]
+    conf["GeneralRankConfs"] = {"home_feed": {"RankConf": {"RankAlgoList": ["lookup_score"], "RankScore": "${lookup_score}"},
+                                              "ActionConfs": [{"ActionType": "sort", "ActionName": "ItemRankScore"},
+                                                              {"ActionType": "filter", "ActionName": "keep100"},
+                                                              {"ActionType": "bogus", "ActionName": "x"}]}}
+    conf["RankConf"] = {"home_feed": {"RankAlgoList": ["lookup_score"], "RankScore": "1 - ${lookup_score}"}}
+    s = HostServer(conf)
+    try:
+        rng = np.random.default_rng(5)
+        score = rng.random(400)
+        for i in range(400):
+            s.add_context_item("mem_recall", "i%07d" % i, 0.0, {"score": float(score[i])})
+        s.commit()
+        r = s.recommend(scene_id="home_feed", uid="u", size=100)
+        # pre-rank keeps the 100 best by score; the main rank then inverts the score, so the final order is ascending
+        keep = oracle_lib.go_sort(score)[:100]
+        final = 1 - score[keep]
+        want = keep[oracle_lib.go_sort(final)]
+        assert [int(it["item_id"][1:]) for it in r["items"]] == want.tolist()
+        assert any("error to find actionType:bogus" in l for l in r["log"])
+    finally:
+        s.close()
+
+
+def test_ingest_formats():
+    from pairec_b200.plugin import parse_embedding, recall_cache_roundtrip
+    assert parse_embedding("{0.25,-1.5,3e-2}") == [0.25, -1.5, 0.03]
+    assert parse_embedding("{1|2|x|4}", "|") == [1.0, 2.0, 0.0, 4.0]      # ParseFloat error -> 0 (dpp_sort.go:228-232)
+    cache, back = recall_cache_roundtrip(["a", "b", "c"], [0.5, 0.123456789, 1e-7], "u2i")
+    assert cache == "a:u2i:0.5,b:u2i:0.123456789,c:u2i:1e-07"             # fmt %v of float64 (vector_recall.go:107)
+    assert [(d["item_id"], d["score"], d["retrieve_id"]) for d in back] == [("a", 0.5, "u2i"), ("b", 0.123456789, "u2i"),
+                                                                           ("c", 1e-7, "u2i")]
