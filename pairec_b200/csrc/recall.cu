@@ -19,6 +19,7 @@
 // epilogue, so the only HBM traffic is the matrix itself (algorithmic bytes = rows*dim*4 per <=64-query block).
 #include "handle.h"
 #include "recall.h"
+#include <vector>
 
 namespace prg {
 
@@ -606,95 +607,101 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   const bool sampled = h->E_rows >= kSampledMinRows && (uint64_t)k * 64 <= h->E_rows;
 
   // sampling plan: ~1/128 of the tiles, strided across the whole matrix
-  uint32_t sample_tiles = 0, tile_stride = 1, r_rank = 0, cand_cap = 0, n_seg = 0, seg_cap = 0;
-  bool use_tc = false;
-  if (sampled) {
-    sample_tiles = n_tiles / 128;
-    if (sample_tiles < 64) sample_tiles = 64;
-    if (sample_tiles > 2048) sample_tiles = 2048;
-    tile_stride = n_tiles / sample_tiles;
-    const double f = (double)sample_tiles * kTileRows / (double)h->E_rows;
-    const double target = 4.0 * (k < 1024 ? 1024 : k);
-    r_rank = (uint32_t)(target * f + 0.999);
-    if (r_rank < 24) r_rank = 24;
-    cand_cap = (uint32_t)(4.0 * (double)r_rank / f);
-    cand_cap = (cand_cap + 1023) & ~1023u;
-    PRG_TRY(h->sample_keys.ensure((size_t)kQB * sample_tiles * kTileRows * 8));
-    n_seg = n_tiles < (uint32_t)h->sm_count ? n_tiles : (uint32_t)h->sm_count;
-    seg_cap = (uint32_t)(8.0 * ((double)r_rank / f) / n_seg) + 32;
-    seg_cap = (seg_cap + 15) & ~15u;
-    PRG_TRY(h->cand_keys.ensure((size_t)kQB * cand_cap * 8));
-    PRG_TRY(h->seg_keys.ensure((size_t)kQB * n_seg * seg_cap * 8));
-    use_tc = !h->scan_ffma2;
-    if (use_tc) PRG_TRY(h->seg_rows.ensure((size_t)kQB * n_seg * seg_cap * 4));
-    if (use_tc && !h->row_norm.p) PRG_TRY(build_row_norms(h));
-    PRG_TRY(h->cand_cnt.ensure((size_t)kQB * n_seg * 4 + 4));
-    PRG_TRY(h->tau.ensure((size_t)kQB * 8));
-    PRG_TRY(h->flags.ensure((size_t)kQB * 4));
+  const int nblk = (B + kQB - 1) / kQB;
+  const size_t QT = (size_t)nblk * kQB;  // query slots (blocks of 64)
+  if (!sampled) {
+    for (int q0 = 0; q0 < B; q0 += kQB) {
+      const int nq = (B - q0 < kQB) ? (B - q0) : kQB;
+      PRG_TRY(recall_dense(h, q_dev + (size_t)q0 * dim, nq, k, k, keys_out + (size_t)q0 * k));
+    }
+    return PRG_OK;
   }
+  uint32_t sample_tiles = n_tiles / 128;
+  if (sample_tiles < 64) sample_tiles = 64;
+  if (sample_tiles > 2048) sample_tiles = 2048;
+  const uint32_t tile_stride = n_tiles / sample_tiles;
+  const uint64_t slots = (uint64_t)sample_tiles * kTileRows;
+  const double f = (double)slots / (double)h->E_rows;
+  const double target = 4.0 * (k < 1024 ? 1024 : k);
+  uint32_t r_rank = (uint32_t)(target * f + 0.999);
+  if (r_rank < 24) r_rank = 24;
+  uint32_t cand_cap = (uint32_t)(4.0 * (double)r_rank / f);
+  cand_cap = (cand_cap + 1023) & ~1023u;
+  const uint32_t n_seg = n_tiles < (uint32_t)h->sm_count ? n_tiles : (uint32_t)h->sm_count;
+  uint32_t seg_cap = (uint32_t)(8.0 * ((double)r_rank / f) / n_seg) + 32;
+  seg_cap = (seg_cap + 15) & ~15u;
+  const bool use_tc = !h->scan_ffma2;
+  PRG_TRY(h->sample_keys.ensure(QT * slots * 8));
+  PRG_TRY(h->cand_keys.ensure(QT * cand_cap * 8));
+  PRG_TRY(h->seg_keys.ensure(QT * n_seg * seg_cap * 8));
+  if (use_tc) PRG_TRY(h->seg_rows.ensure(QT * n_seg * seg_cap * 4));
+  if (use_tc && !h->row_norm.p) PRG_TRY(build_row_norms(h));
+  PRG_TRY(h->cand_cnt.ensure(QT * n_seg * 4 + 4));
+  PRG_TRY(h->tau.ensure(QT * 8));
+  PRG_TRY(h->flags.ensure(QT * 4));
+  const size_t seg_q = (size_t)n_seg * seg_cap;  // segment slots per query
 
+  // All query blocks go through each phase together: the scans run once per block of <= 64 queries, the selects
+  // and the re-score once for the whole batch (one CTA per query), and there is ONE status read-back.
+  // 1. sample
   for (int q0 = 0; q0 < B; q0 += kQB) {
-    const int nq = (B - q0 < kQB) ? (B - q0) : kQB;
-    const float* qb = q_dev + (size_t)q0 * dim;
-    uint64_t* kout = keys_out + (size_t)q0 * k;
-    if (!sampled) {
-      PRG_TRY(recall_dense(h, qb, nq, k, k, kout));
-      continue;
-    }
-    // 1. sample
     ScanParams sp{};
-    sp.Q = qb; sp.nq = nq; sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
+    sp.Q = q_dev + (size_t)q0 * dim; sp.nq = (B - q0 < kQB) ? (B - q0) : kQB;
+    sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
     sp.n_tiles = sample_tiles; sp.tile_stride = tile_stride;
-    sp.dense = (uint64_t*)h->sample_keys.p; sp.dense_stride = (uint64_t)sample_tiles * kTileRows;
+    sp.dense = (uint64_t*)h->sample_keys.p + (size_t)q0 * slots; sp.dense_stride = slots;
     PRG_TRY(scan(h, SCAN_DENSE, sp));
-    // 2. threshold = r-th largest sample key
-    SelectParams st{};
-    st.keys = (const uint64_t*)h->sample_keys.p; st.stride = sp.dense_stride; st.fixed_m = (uint32_t)sp.dense_stride;
-    st.cap = st.fixed_m; st.k = (int)r_rank; st.tau = (uint64_t*)h->tau.p;
-    PRG_TRY(launch_select(h, SEL_KTH, st, nq));
-    // 3. full scan with fused threshold test
-    uint32_t* max_cnt = (uint32_t*)h->cand_cnt.p + (size_t)kQB * n_seg;
-    PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
+  }
+  // 2. threshold = r-th largest sample key
+  SelectParams st{};
+  st.keys = (const uint64_t*)h->sample_keys.p; st.stride = slots; st.fixed_m = (uint32_t)slots;
+  st.cap = st.fixed_m; st.k = (int)r_rank; st.tau = (uint64_t*)h->tau.p;
+  PRG_TRY(launch_select(h, SEL_KTH, st, B));
+  // 3. full pass with the threshold test fused into the tile epilogue
+  uint32_t* max_cnt = (uint32_t*)h->cand_cnt.p + QT * n_seg;
+  PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
+  const int pass_q = use_tc ? scan_tc_max_queries(h) : kQB;  // queries per pass over the matrix
+  for (int q0 = 0; q0 < B; q0 += pass_q) {
     ScanParams sc{};
-    sc.Q = qb; sc.nq = nq; sc.n_rows = h->E_rows; sc.row_base = h->E_row_base;
+    sc.Q = q_dev + (size_t)q0 * dim; sc.nq = (B - q0 < pass_q) ? (B - q0) : pass_q;
+    sc.n_rows = h->E_rows; sc.row_base = h->E_row_base;
     sc.n_tiles = n_tiles; sc.tile_stride = 1;
-    sc.tau = (const uint64_t*)h->tau.p; sc.cand = (uint64_t*)h->seg_keys.p; sc.seg_cap = seg_cap;
-    sc.seg_cnt = (uint32_t*)h->cand_cnt.p;
-    sc.row_norm = (const float*)h->row_norm.p; sc.cand_rows = (uint32_t*)h->seg_keys.p;
-    if (use_tc) {
-      sc.cand_rows = (uint32_t*)h->seg_rows.p;
-      PRG_TRY(launch_scan_tc(h, sc));
-      StageScope span(h, ST_SELECT);
-      rescore_kernel<<<dim3(n_seg, (unsigned)nq), 64, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
-                                                                      (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, qb,
-                                                                      dim, h->E_row_base, (uint64_t*)h->seg_keys.p);
-      PRG_CUDA(cudaGetLastError());
-      count_launch(h);
-    } else {
-      PRG_TRY(scan(h, SCAN_THRESH, sc));
-    }
-    // 4. exact top-k of the candidates
-    SelectParams se{};
-    se.keys = (const uint64_t*)h->seg_keys.p; se.stride = cand_cap; se.counts = nullptr;
-    se.seg_counts = (const uint32_t*)h->cand_cnt.p; se.n_seg = n_seg; se.seg_cap = seg_cap;
-    se.compact = (uint64_t*)h->cand_keys.p;
-    if (use_tc) se.tau_check = (const uint64_t*)h->tau.p;
-    se.cap = cand_cap; se.k = k; se.k_out = k;
-    se.expect = (uint32_t)((uint64_t)k < h->E_rows ? (uint64_t)k : h->E_rows);
-    se.out_keys = kout; se.flags = (int32_t*)h->flags.p;
-    se.max_count = max_cnt;
-    PRG_TRY(launch_select(h, SEL_TOPK, se, nq));
-    // 5. per-query status; redo the rare failures through the dense path
-    int32_t hf[kQB + 1];
-    PRG_CUDA(cudaMemcpyAsync(hf, h->flags.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, h->stream));
-    PRG_CUDA(cudaMemcpyAsync(&hf[kQB], max_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
-    PRG_CUDA(cudaStreamSynchronize(h->stream));
-    if (hf[kQB] > h->last_max_cand) h->last_max_cand = hf[kQB];
-    for (int q = 0; q < nq; ++q) {
-      if (hf[q] != 0) {
-        ++h->last_fallback;
-        PRG_TRY(recall_dense(h, qb + (size_t)q * dim, 1, k, k, kout + (size_t)q * k));
-      }
+    sc.tau = (const uint64_t*)h->tau.p + q0; sc.cand = (uint64_t*)h->seg_keys.p + (size_t)q0 * seg_q; sc.seg_cap = seg_cap;
+    sc.seg_cnt = (uint32_t*)h->cand_cnt.p + (size_t)q0 * n_seg;
+    sc.row_norm = (const float*)h->row_norm.p;
+    sc.cand_rows = use_tc ? (uint32_t*)h->seg_rows.p + (size_t)q0 * seg_q : nullptr;
+    if (use_tc) PRG_TRY(launch_scan_tc(h, sc));
+    else PRG_TRY(scan(h, SCAN_THRESH, sc));
+  }
+  if (use_tc) {  // exact re-score of the tensor-core survivors, all queries at once
+    StageScope span(h, ST_SELECT);
+    rescore_kernel<<<dim3(n_seg, (unsigned)B), 64, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
+                                                                   (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, q_dev, dim,
+                                                                   h->E_row_base, (uint64_t*)h->seg_keys.p);
+    PRG_CUDA(cudaGetLastError());
+    count_launch(h);
+  }
+  // 4. exact top-k of the candidates
+  SelectParams se{};
+  se.keys = (const uint64_t*)h->seg_keys.p; se.stride = cand_cap; se.counts = nullptr;
+  se.seg_counts = (const uint32_t*)h->cand_cnt.p; se.n_seg = n_seg; se.seg_cap = seg_cap;
+  se.compact = (uint64_t*)h->cand_keys.p;
+  if (use_tc) se.tau_check = (const uint64_t*)h->tau.p;
+  se.cap = cand_cap; se.k = k; se.k_out = k;
+  se.expect = (uint32_t)((uint64_t)k < h->E_rows ? (uint64_t)k : h->E_rows);
+  se.out_keys = keys_out; se.flags = (int32_t*)h->flags.p;
+  se.max_count = max_cnt;
+  PRG_TRY(launch_select(h, SEL_TOPK, se, B));
+  // 5. per-query status; redo the rare failures through the dense path
+  std::vector<int32_t> hf((size_t)B + 1);
+  PRG_CUDA(cudaMemcpyAsync(hf.data(), h->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(&hf[(size_t)B], max_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  if (hf[(size_t)B] > h->last_max_cand) h->last_max_cand = hf[(size_t)B];
+  for (int q = 0; q < B; ++q) {
+    if (hf[(size_t)q] != 0) {
+      ++h->last_fallback;
+      PRG_TRY(recall_dense(h, q_dev + (size_t)q * dim, 1, k, k, keys_out + (size_t)q * k));
     }
   }
   return PRG_OK;

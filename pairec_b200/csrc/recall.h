@@ -72,6 +72,7 @@ enum { SEL_TOPK = 0, SEL_KTH = 1 };
 
 // recall_tc.cu
 int launch_scan_tc(prg_handle* h, const ScanParams& p);
+int scan_tc_max_queries(const prg_handle* h);
 int build_row_norms(prg_handle* h);
 
 }  // namespace prg

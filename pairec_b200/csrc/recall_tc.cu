@@ -26,10 +26,14 @@ constexpr int kTcEpiWarps = 8;
 constexpr int kTcStages = 3;
 constexpr float kTcMargin = 1.05f / 512.f;  // c = 1.05 * 2^-9
 
-template <int DIM>
+// NQB = query blocks (of 64) handled per pass over the matrix: the tile is read from HBM once and multiplied against
+// every block (the shard of a G-GPU run sees 64*G queries per step: one pass instead of G).
+template <int NQB>
+constexpr int tc_stages() { return NQB <= 2 ? 3 : 2; }
+template <int DIM, int NQB>
 constexpr size_t scan_tc_smem_bytes() {
-  return (size_t)kTcStages * kStageBytes + (size_t)DIM * kQB * 4 /*Q operand*/ + 3 * kQB * 4 /*tauf, qn, s_cnt*/ +
-         (2 * kTcStages + 4) * 8 + 16;
+  return (size_t)tc_stages<NQB>() * kStageBytes + (size_t)NQB * DIM * kQB * 4 /*Q operands*/ +
+         (size_t)NQB * 3 * kQB * 4 /*tauf, qn, s_cnt*/ + (2 * tc_stages<NQB>() + 4) * 8 + 16;
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -43,16 +47,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
-template <int DIM>
+template <int DIM, int NQB>
 __global__ void __launch_bounds__(kTcThreads, 1)
 recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int KH = DIM / 64;
+  constexpr int kTcStages = tc_stages<NQB>();
+  constexpr int NBUF = NQB <= 2 ? 2 : 1;                   // accumulator buffers (128 TMEM columns per block and buffer)
+  constexpr uint32_t kTmemCols = NQB == 1 ? 256 : 512;
+  constexpr int QTOT = NQB * kQB;
   float* stage_base = reinterpret_cast<float*>(smem);
-  float* Qb = reinterpret_cast<float*>(smem + (size_t)kTcStages * kStageBytes);  // B operand: [DIM/32][64 q][32] swizzled
-  float2* tq = reinterpret_cast<float2*>(Qb + DIM * kQB);  // [64] {tau_f, c*||q||}
-  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tq + kQB);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + kQB);
+  float* Qb = reinterpret_cast<float*>(smem + (size_t)kTcStages * kStageBytes);  // B operands: [NQB][DIM/32][64 q][32] swizzled
+  float2* tq = reinterpret_cast<float2*>(Qb + (size_t)NQB * DIM * kQB);         // [NQB*64] {tau_f, c*||q||}
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tq + QTOT);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + QTOT);
   uint64_t* empty = full + kTcStages;
   uint64_t* tfull = empty + kTcStages;   // [2] accumulator buffer ready
   uint64_t* tempty = tfull + 2;          // [2] accumulator buffer drained
@@ -60,24 +68,25 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // query block -> K-major SWIZZLE_128B B operand; padded queries are zero rows
-  for (int i = tid; i < DIM * kQB; i += kTcThreads) {
+  // query blocks -> K-major SWIZZLE_128B B operands; padded queries are zero rows
+  for (int i = tid; i < DIM * QTOT; i += kTcThreads) {
     const int q = i / DIM, dd = i - q * DIM;
     const float v = (q < p.nq) ? p.Q[(size_t)q * DIM + dd] : 0.f;
+    const int blk = q >> 6, ql = q & 63;
     const int sub = dd >> 5, ch = (dd & 31) >> 2;
-    Qb[sub * (kQB * 32) + q * 32 + ((ch ^ (q & 7)) << 2) + (dd & 3)] = v;
+    Qb[(size_t)blk * DIM * kQB + sub * (kQB * 32) + ql * 32 + ((ch ^ (ql & 7)) << 2) + (dd & 3)] = v;
   }
-  if (tid < kQB) {
+  for (int q = tid; q < QTOT; q += kTcThreads) {
     float tf = __int_as_float(0x7F800000), nq2 = 0.f;
-    if (tid < p.nq) {
-      const uint64_t t = p.tau[tid];
+    if (q < p.nq) {
+      const uint64_t t = p.tau[q];
       tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
       float ss = 0.f;
-      for (int dd = 0; dd < DIM; ++dd) { const float v = p.Q[(size_t)tid * DIM + dd]; ss = fmaf(v, v, ss); }
+      for (int dd = 0; dd < DIM; ++dd) { const float v = p.Q[(size_t)q * DIM + dd]; ss = fmaf(v, v, ss); }
       nq2 = sqrtf(ss) * 1.0001f * kTcMargin;
     }
-    tq[tid] = make_float2(tf, nq2);
-    s_cnt[tid] = 0;
+    tq[q] = make_float2(tf, nq2);
+    s_cnt[q] = 0;
   }
   if (tid == 0) {
     tma_prefetch_desc(&emap);
@@ -86,7 +95,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // the generic-proxy writes of Qb must be visible to the tensor core (async proxy) before the first MMA
@@ -123,8 +132,9 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       const uint32_t qb_addr = smem_u32(Qb);
       uint32_t it = 0;
       for (uint32_t i = 0; i < my_tiles; ++i) {
-        const uint32_t buf = i & 1u;
-        mbar_wait(&tempty[buf], ((i >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator buffer
+        const uint32_t buf = (NBUF == 2) ? (i & 1u) : 0u;
+        const uint32_t use = (NBUF == 2) ? (i >> 1) : i;  // how often this buffer has been used before
+        mbar_wait(&tempty[buf], (use & 1u) ^ 1u);         // epilogue has drained this accumulator buffer
         tc_fence_after();
         for (int h = 0; h < KH; ++h, ++it) {
           const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
@@ -132,16 +142,19 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
           tc_fence_after();
           const uint32_t st_addr = smem_u32(stage_base + (size_t)s * kStageFloats);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint32_t d_addr = tmem_base + buf * 128u + (uint32_t)half * 64u;
+          for (int blk = 0; blk < NQB; ++blk) {
 #pragma unroll
-            for (int sub = 0; sub < 2; ++sub) {
-              const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kSubTileFloats * 4) + (uint32_t)half * (128 * 128));
-              const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)(h * 2 + sub) * (kQB * 128));
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t d_addr = tmem_base + (buf * (uint32_t)NQB + (uint32_t)blk) * 128u + (uint32_t)half * 64u;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 B -> +2 in 16-B units
-                umma_tf32(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                          (h | sub | k) != 0 ? 1u : 0u);
+              for (int sub = 0; sub < 2; ++sub) {
+                const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kSubTileFloats * 4) + (uint32_t)half * (128 * 128));
+                const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)blk * (DIM * kQB * 4) + (uint32_t)(h * 2 + sub) * (kQB * 128));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 B -> +2 in 16-B units
+                  umma_tf32(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                            (h | sub | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty[s]);
@@ -161,65 +174,76 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     };
     float nr_next = (my_tiles > 0 && tile_row(0) < p.n_rows) ? p.row_norm[tile_row(0)] : 0.f;
     for (uint32_t i = 0; i < my_tiles; ++i) {
-      const uint32_t buf = i & 1u;
+      const uint32_t buf = (NBUF == 2) ? (i & 1u) : 0u;
+      const uint32_t use = (NBUF == 2) ? (i >> 1) : i;
       const uint64_t lrow = tile_row(i);
       const bool valid = lrow < p.n_rows;
       const float nr = nr_next;
       nr_next = (i + 1 < my_tiles && tile_row(i + 1) < p.n_rows) ? p.row_norm[tile_row(i + 1)] : 0.f;
-      mbar_wait(&tfull[buf], (i >> 1) & 1u);
+      const uint32_t grow = (uint32_t)(p.row_base + lrow);
+      const uint32_t seg_stride = gridDim.x * p.seg_cap, seg_base = blockIdx.x * p.seg_cap;
+      mbar_wait(&tfull[buf], use & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 128u + (uint32_t)half * 64u;
-      uint32_t v0[32], v1[32];
-      tmem_ld32(taddr, v0);
-      tmem_ld32(taddr + 32u, v1);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);  // accumulators are in registers: the MMA warp may overwrite them
-      // thr_q = tau_f[q] - ||x_row|| * c*||q||; {tau_f, c||q||} pairs are re-read from shared memory per tile (the
-      // mbarrier wait above is a compiler memory barrier, so nothing is hoisted into 128 live registers)
-      const float4* tq4 = reinterpret_cast<const float4*>(tq);
-      bool any0 = false, any1 = false;
+#pragma unroll 1
+      for (int blk = 0; blk < NQB; ++blk) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * (uint32_t)NQB + (uint32_t)blk) * 128u +
+                               (uint32_t)half * 64u;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32u, v1);
+        if (blk == NQB - 1) {  // last accumulator read of this tile: the MMA warp may overwrite the buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[buf]);
+        }
+        // thr_q = tau_f[q] - ||x_row|| * c*||q||; {tau_f, c||q||} pairs are re-read from shared memory per tile (the
+        // mbarrier wait above is a compiler memory barrier, so nothing is hoisted into 128 live registers)
+        const float2* tqb = tq + blk * kQB;
+        const float4* tq4 = reinterpret_cast<const float4*>(tqb);
+        const int nqb = p.nq - blk * kQB;  // queries of this block (may exceed 64; <= 0 for an unused block)
+        bool any0 = false, any1 = false;
 #pragma unroll
-      for (int q = 0; q < 32; q += 2) {
-        const float4 a4 = tq4[q >> 1];
-        const float4 b4 = tq4[16 + (q >> 1)];
-        any0 |= !(__uint_as_float(v0[q]) < fmaf(-nr, a4.y, a4.x));
-        any0 |= !(__uint_as_float(v0[q + 1]) < fmaf(-nr, a4.w, a4.z));
-        any1 |= !(__uint_as_float(v1[q]) < fmaf(-nr, b4.y, b4.x));
-        any1 |= !(__uint_as_float(v1[q + 1]) < fmaf(-nr, b4.w, b4.z));
-      }
-      if (valid && (any0 || any1)) {
-        const uint32_t grow = (uint32_t)(p.row_base + lrow);
-        const uint32_t seg_stride = gridDim.x * p.seg_cap, seg_base = blockIdx.x * p.seg_cap;
-        if (any0) {
+        for (int q = 0; q < 32; q += 2) {
+          const float4 a4 = tq4[q >> 1];
+          const float4 b4 = tq4[16 + (q >> 1)];
+          any0 |= !(__uint_as_float(v0[q]) < fmaf(-nr, a4.y, a4.x));
+          any0 |= !(__uint_as_float(v0[q + 1]) < fmaf(-nr, a4.w, a4.z));
+          any1 |= !(__uint_as_float(v1[q]) < fmaf(-nr, b4.y, b4.x));
+          any1 |= !(__uint_as_float(v1[q + 1]) < fmaf(-nr, b4.w, b4.z));
+        }
+        if (valid && (any0 || any1)) {
+          uint32_t* scb = s_cnt + blk * kQB;
+          const uint32_t qoff = (uint32_t)(blk * kQB);
+          if (any0) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            if (q < p.nq && !(__uint_as_float(v0[q]) < fmaf(-nr, tq[q].y, tq[q].x))) {
-              const uint32_t pos = atomicAdd(&s_cnt[q], 1u);
-              if (pos < p.seg_cap) p.cand_rows[(uint32_t)q * seg_stride + seg_base + pos] = grow;
+            for (int q = 0; q < 32; ++q) {
+              if (q < nqb && !(__uint_as_float(v0[q]) < fmaf(-nr, tqb[q].y, tqb[q].x))) {
+                const uint32_t pos = atomicAdd(&scb[q], 1u);
+                if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)q) * seg_stride + seg_base + pos] = grow;
+              }
             }
           }
-        }
-        if (any1) {
+          if (any1) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            if (q + 32 < p.nq && !(__uint_as_float(v1[q]) < fmaf(-nr, tq[q + 32].y, tq[q + 32].x))) {
-              const uint32_t pos = atomicAdd(&s_cnt[q + 32], 1u);
-              if (pos < p.seg_cap) p.cand_rows[(uint32_t)(q + 32) * seg_stride + seg_base + pos] = grow;
+            for (int q = 0; q < 32; ++q) {
+              if (q + 32 < nqb && !(__uint_as_float(v1[q]) < fmaf(-nr, tqb[q + 32].y, tqb[q + 32].x))) {
+                const uint32_t pos = atomicAdd(&scb[q + 32], 1u);
+                if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)(q + 32)) * seg_stride + seg_base + pos] = grow;
+              }
             }
           }
         }
       }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
-    if (tid - 64 < p.nq) p.seg_cnt[(size_t)(tid - 64) * gridDim.x + blockIdx.x] = s_cnt[tid - 64];
+    for (int q = tid - 64; q < p.nq; q += kTcEpiWarps * 32) p.seg_cnt[(size_t)q * gridDim.x + blockIdx.x] = s_cnt[q];
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
   }
 }
 
@@ -248,22 +272,33 @@ int build_row_norms(prg_handle* h) {
   return PRG_OK;
 }
 
-template <int DIM>
+template <int DIM, int NQB>
 static int launch_tc(prg_handle* h, const ScanParams& p) {
-  const size_t smem = scan_tc_smem_bytes<DIM>();
-  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = scan_tc_smem_bytes<DIM, NQB>();
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM, NQB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (p.n_tiles == 0) return PRG_OK;
   StageScope span(h, ST_SCAN);
   const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
-  recall_scan_tc_kernel<DIM><<<grid, kTcThreads, smem, h->stream>>>(h->E_map, p);
+  recall_scan_tc_kernel<DIM, NQB><<<grid, kTcThreads, smem, h->stream>>>(h->E_map, p);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;
 }
 
+// queries per pass the kernel is built for: 64/128/256 at dim 64, 64 at dim 128 (shared-memory budget)
+int scan_tc_max_queries(const prg_handle* h) { return h->E_dim == 64 ? 256 : 64; }
+
 int launch_scan_tc(prg_handle* h, const ScanParams& p) {
-  if (h->E_dim == 64) return launch_tc<64>(h, p);
-  if (h->E_dim == 128) return launch_tc<128>(h, p);
+  if (h->E_dim == 64) {
+    if (p.nq <= 64) return launch_tc<64, 1>(h, p);
+    if (p.nq <= 128) return launch_tc<64, 2>(h, p);
+    if (p.nq <= 256) return launch_tc<64, 4>(h, p);
+    return fail(PRG_EINVAL, "launch_scan_tc: more than 256 queries per pass");
+  }
+  if (h->E_dim == 128) {
+    if (p.nq <= 64) return launch_tc<128, 1>(h, p);
+    return fail(PRG_EINVAL, "launch_scan_tc: more than 64 queries per pass at dim 128");
+  }
   return fail(PRG_EUNSUPPORTED, "item matrix dim must be 64 or 128");
 }
 

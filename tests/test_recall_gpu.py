@@ -111,3 +111,11 @@ def test_filter_margin_holds_for_scaled_rows(engine, oracle_lib):
 def test_dim128_sampled_path(engine, oracle_lib):
     E, Q = _data(300_000, 128, 64, seed=29)
     _check(engine, oracle_lib, E, Q, 1000)
+
+
+@pytest.mark.parametrize("b", [100, 200, 300])
+def test_many_queries_per_pass(engine, oracle_lib, b):
+    # 2 / 4 query blocks per pass of the tensor-core filter (one read of the matrix), and more than one pass
+    E, Q = _data(350_000, 64, b, seed=41 + b)
+    _check(engine, oracle_lib, E, Q, 200)
+    assert engine.recall_stats()["fallback_queries"] == 0
