@@ -70,6 +70,7 @@ struct Guard {
   explicit Guard(prg_handle* hh) : h(hh), lk(hh->mu) {
     cudaGetDevice(&prev);
     if (prev != h->device) cudaSetDevice(h->device);
+    resolve_pending(h);  // deferred recall check of a previous fused call
   }
   ~Guard() {
     if (prev >= 0 && prev != h->device) cudaSetDevice(prev);
@@ -168,6 +169,8 @@ void prg_destroy(prg_handle* h) {
                       &h->rec_scores, &h->rec_perm, &h->rec_sorted_rows, &h->rec_sorted_scores};
     for (DevBuf* b : bufs) b->release();
     for (int l = 0; l < kMaxLayers; ++l) { h->mlp_W[l].release(); h->mlp_b[l].release(); }
+    if (h->flags_ev) cudaEventDestroy(h->flags_ev);
+    if (h->host_flags) cudaFreeHost(h->host_flags);
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->stream);
@@ -177,8 +180,13 @@ void prg_destroy(prg_handle* h) {
 
 int prg_sync(prg_handle* h) {
   CHECK_H(h);
-  Guard g(h);
+  Guard g(h);  // resolves a deferred recall check (and re-runs the fused downstream if a query had to be repaired)
   PRG_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->deferred_status != PRG_OK) {
+    const int rc = h->deferred_status;
+    h->deferred_status = PRG_OK;
+    return fail(rc, "deferred: " + h->deferred_msg);
+  }
   return PRG_OK;
 }
 void* prg_stream(prg_handle* h) { return h ? (void*)h->stream : nullptr; }

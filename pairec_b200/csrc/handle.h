@@ -65,6 +65,24 @@ struct prg_handle {
   prg::DevBuf flags;        // B i32 per-query status from select
   int32_t last_fallback = 0;
   int32_t last_max_cand = 0;
+  // deferred validation of the sampled recall (fused path): the per-query status is copied to pinned host memory
+  // asynchronously and checked later, so the steady state has no host round trip in the middle of a step
+  struct Pending {
+    bool active = false;        // recall status not checked yet
+    bool fused = false;         // downstream (rank/sort/DPP) outputs depend on it: re-run them after a repair
+    int B = 0, k = 0, model = 0;
+    const float* q_dev = nullptr;
+    uint64_t* keys_out = nullptr;
+    prg_dpp_params p{};
+    uint32_t* out_row = nullptr;
+    double* out_score = nullptr;
+    int32_t* out_n = nullptr;
+  } pending;
+  cudaEvent_t flags_ev = nullptr;
+  int32_t* host_flags = nullptr;  // pinned, host_flags_cap + 1 ints
+  size_t host_flags_cap = 0;
+  int deferred_status = PRG_OK;   // error met while resolving a deferred check (reported by the next call)
+  std::string deferred_msg;
 
   // ---- rank: fields, tables, models
   const uint32_t* fields = nullptr;
@@ -130,7 +148,9 @@ struct StageScope {
 
 // recall.cu
 int recall_build_map(prg_handle* h);
-int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t* keys_out /*B x k*/);
+int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t* keys_out /*B x k*/, bool defer = false);
+int recall_resolve(prg_handle* h, bool* repaired);   // waits for the deferred status, redoes failed queries densely
+int resolve_pending(prg_handle* h);                  // pipeline.cu: recall_resolve + re-run of the fused downstream
 int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint32_t* out_row, float* out_score,
                     int32_t* out_n);
 int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k,

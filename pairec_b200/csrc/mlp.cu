@@ -439,6 +439,7 @@ extern "C" int prg_set_mlp(prg_handle* h, int n_layers, const uint32_t* dims, co
   if (dims[n_layers - 1] > 256) return fail(PRG_EUNSUPPORTED, "last hidden width must be <= 256 (fused output layer)");
   std::lock_guard<std::mutex> lk(h->mu);
   PRG_CUDA(cudaSetDevice(h->device));
+  prg::resolve_pending(h);
   PRG_CUDA(cudaStreamSynchronize(h->stream));
   h->mlp_layers = 0;
   for (int l = 0; l < n_layers; ++l) {

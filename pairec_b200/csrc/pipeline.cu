@@ -17,7 +17,10 @@ int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev,
 
 struct DevGuard {
   std::unique_lock<std::mutex> lk;
-  explicit DevGuard(prg_handle* h) : lk(h->mu) { cudaSetDevice(h->device); }
+  explicit DevGuard(prg_handle* h) : lk(h->mu) {
+    cudaSetDevice(h->device);
+    resolve_pending(h);  // a deferred recall check of the previous fused call (errors surface through deferred_status)
+  }
 };
 
 static int adopt(const void* src, size_t bytes, int mem, const void** dst, bool* owned) {
@@ -92,11 +95,20 @@ __global__ void final_gather_kernel(const uint32_t* rows, const double* scores, 
 static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
                               double* out_score, int32_t* out_n);
 
+// The recall's per-query status is validated AFTER the downstream stages have been enqueued (resolve_pending): in the
+// steady state the host never waits in the middle of a step; a failed query (adversarial row order) is redone densely
+// and the downstream stages are simply run again.
 static int recommend_device(prg_handle* h, const float* q_dev, int B, int k, int model, const prg_dpp_params& p,
-                            uint32_t* out_row, double* out_score, int32_t* out_n) {
+                            uint32_t* out_row, double* out_score, int32_t* out_n, bool resolve_now) {
   PRG_TRY(h->topk_keys.ensure((size_t)B * k * 8));
-  PRG_TRY(recall_topk_device(h, q_dev, B, k, (uint64_t*)h->topk_keys.p));
-  return post_recall_device(h, B, k, model, p, out_row, out_score, out_n);
+  PRG_TRY(recall_topk_device(h, q_dev, B, k, (uint64_t*)h->topk_keys.p, /*defer=*/true));
+  PRG_TRY(post_recall_device(h, B, k, model, p, out_row, out_score, out_n));
+  if (h->pending.active) {
+    h->pending.fused = true;
+    h->pending.model = model; h->pending.p = p;
+    h->pending.out_row = out_row; h->pending.out_score = out_score; h->pending.out_n = out_n;
+  }
+  return resolve_now ? resolve_pending(h) : PRG_OK;
 }
 
 static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
@@ -134,6 +146,18 @@ static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;
+}
+
+int resolve_pending(prg_handle* h) {
+  if (!h->pending.active) return PRG_OK;
+  const bool fused = h->pending.fused;
+  bool repaired = false;
+  int rc = recall_resolve(h, &repaired);
+  if (rc == PRG_OK && repaired && fused)
+    rc = post_recall_device(h, h->pending.B, h->pending.k, h->pending.model, h->pending.p, h->pending.out_row,
+                            h->pending.out_score, h->pending.out_n);
+  if (rc != PRG_OK) { h->deferred_status = rc; h->deferred_msg = prg_last_error(); }
+  return rc;
 }
 
 }  // namespace prg
@@ -275,7 +299,8 @@ int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model,
   if (B <= 0 || recall_k <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "B, recall_k, top_n must be positive");
   DevGuard g(h);
   if (!h->E) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
-  if (mem == PRG_MEM_DEVICE) return recommend_device(h, q, B, recall_k, model, *p, out_row, out_score, out_n);
+  if (h->deferred_status != PRG_OK) { const int rc = h->deferred_status; h->deferred_status = PRG_OK; return fail(rc, "deferred: " + h->deferred_msg); }
+  if (mem == PRG_MEM_DEVICE) return recommend_device(h, q, B, recall_k, model, *p, out_row, out_score, out_n, /*resolve_now=*/false);
   const size_t TT = (size_t)B * p->top_n;
   PRG_TRY(h->q_dev.ensure((size_t)B * h->E_dim * 4));
   PRG_TRY(h->out_row.ensure(TT * 4 > (size_t)B * recall_k * 4 ? TT * 4 : (size_t)B * recall_k * 4));
@@ -284,7 +309,7 @@ int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model,
   PRG_CUDA(cudaMemcpyAsync(h->q_dev.p, q, (size_t)B * h->E_dim * 4, cudaMemcpyHostToDevice, h->stream));
   PRG_TRY(h->sort_perm.ensure((size_t)B * 4));
   PRG_TRY(recommend_device(h, (const float*)h->q_dev.p, B, recall_k, model, *p, (uint32_t*)h->out_row.p,
-                           (double*)h->rank_out.p, (int32_t*)h->sort_perm.p));
+                           (double*)h->rank_out.p, (int32_t*)h->sort_perm.p, /*resolve_now=*/true));
   PRG_CUDA(cudaMemcpyAsync(out_row, h->out_row.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaMemcpyAsync(out_score, h->rank_out.p, TT * 8, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaMemcpyAsync(out_n, h->sort_perm.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));

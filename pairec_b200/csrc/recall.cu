@@ -593,7 +593,7 @@ static int recall_dense(prg_handle* h, const float* q_dev, int nq, int k, int k_
 
 constexpr uint64_t kSampledMinRows = 1u << 18;  // below this the dense path is cheaper than sampling
 
-int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t* keys_out) {
+int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t* keys_out, bool defer) {
   if (!h->E || !h->E_map_ok) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
   if (B <= 0 || k <= 0) return fail(PRG_EINVAL, "B and k must be positive");
   if (k > 4096) return fail(PRG_EUNSUPPORTED, "k > 4096");
@@ -609,6 +609,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   // sampling plan: ~1/128 of the tiles, strided across the whole matrix
   const int nblk = (B + kQB - 1) / kQB;
   const size_t QT = (size_t)nblk * kQB;  // query slots (blocks of 64)
+  h->pending.active = false;
   if (!sampled) {
     for (int q0 = 0; q0 < B; q0 += kQB) {
       const int nq = (B - q0 < kQB) ? (B - q0) : kQB;
@@ -692,16 +693,40 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   se.out_keys = keys_out; se.flags = (int32_t*)h->flags.p;
   se.max_count = max_cnt;
   PRG_TRY(launch_select(h, SEL_TOPK, se, B));
-  // 5. per-query status; redo the rare failures through the dense path
-  std::vector<int32_t> hf((size_t)B + 1);
-  PRG_CUDA(cudaMemcpyAsync(hf.data(), h->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
-  PRG_CUDA(cudaMemcpyAsync(&hf[(size_t)B], max_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
-  PRG_CUDA(cudaStreamSynchronize(h->stream));
-  if (hf[(size_t)B] > h->last_max_cand) h->last_max_cand = hf[(size_t)B];
+  // 5. per-query status -> pinned host memory; checked now, or later when deferred (fused path)
+  if (h->host_flags_cap < (size_t)B) {
+    if (h->host_flags) cudaFreeHost(h->host_flags);
+    h->host_flags = nullptr;
+    h->host_flags_cap = 0;
+    const size_t cap = (size_t)B < 1024 ? 1024 : (size_t)B;
+    PRG_CUDA(cudaHostAlloc((void**)&h->host_flags, (cap + 1) * 4, cudaHostAllocDefault));
+    h->host_flags_cap = cap;
+  }
+  if (!h->flags_ev) PRG_CUDA(cudaEventCreateWithFlags(&h->flags_ev, cudaEventDisableTiming));
+  PRG_CUDA(cudaMemcpyAsync(h->host_flags, h->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(h->host_flags + h->host_flags_cap, max_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaEventRecord(h->flags_ev, h->stream));
+  h->pending.active = true;
+  h->pending.fused = false;
+  h->pending.B = B; h->pending.k = k; h->pending.q_dev = q_dev; h->pending.keys_out = keys_out;
+  if (defer) return PRG_OK;
+  bool repaired = false;
+  return recall_resolve(h, &repaired);
+}
+
+int recall_resolve(prg_handle* h, bool* repaired) {
+  *repaired = false;
+  if (!h->pending.active) return PRG_OK;
+  h->pending.active = false;
+  PRG_CUDA(cudaEventSynchronize(h->flags_ev));
+  const int B = h->pending.B, k = h->pending.k;
+  const int32_t mx = h->host_flags[h->host_flags_cap];
+  if (mx > h->last_max_cand) h->last_max_cand = mx;
   for (int q = 0; q < B; ++q) {
-    if (hf[(size_t)q] != 0) {
+    if (h->host_flags[q] != 0) {  // candidate list under/overflowed: redo this query through the dense path
       ++h->last_fallback;
-      PRG_TRY(recall_dense(h, q_dev + (size_t)q * dim, 1, k, k, keys_out + (size_t)q * k));
+      *repaired = true;
+      PRG_TRY(recall_dense(h, h->pending.q_dev + (size_t)q * h->E_dim, 1, k, k, h->pending.keys_out + (size_t)q * k));
     }
   }
   return PRG_OK;

@@ -214,6 +214,7 @@ int prg_sort_desc(prg_handle* h, const double* score, int B, int n, int32_t* out
   if (!score || !out_perm || B <= 0 || n <= 0) return fail(PRG_EINVAL, "bad arguments");
   std::lock_guard<std::mutex> lk(h->mu);
   PRG_CUDA(cudaSetDevice(h->device));
+  prg::resolve_pending(h);
   if (mem == PRG_MEM_DEVICE) return sort_desc_device(h, score, B, n, out_perm);
   const size_t cnt = (size_t)B * n;
   PRG_TRY(h->sort_in.ensure(cnt * 8));
