@@ -315,8 +315,8 @@ def main():
     for _ in range(warmup):
         step_device()
     sync_all()
-    eng.timing(True)
-    eng.timing(True, read=True)  # reset accumulators
+    eng.timing(2)             # CUDA-event spans around the recall scan only while the step is timed
+    eng.timing(2, read=True)  # reset accumulators
     launches0 = eng.launches
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -330,8 +330,12 @@ def main():
             ev[i + 1].record(stream)
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
-    stage = eng.timing(False, read=True)
+    stage = eng.timing(1, read=True)   # scan spans of the timed region; now switch to all stages
     launches = eng.launches - launches0
+    for _ in range(20):                # untimed: per-stage breakdown (the extra events perturb the step slightly)
+        step_device()
+    sync_all()
+    stage_all = eng.timing(0, read=True)
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
@@ -416,7 +420,7 @@ def main():
             "p99_ms_per_step": float(np.percentile(step_ms, 99)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (recall, FM), bf16x2/bf16->f32 (MLP), f64 (sort, DPP)",
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
-            "stage_ms_per_step": {s: stage[s]["ms"] / args.steps for s in stage},
+            "stage_ms_per_step": {s: stage_all[s]["ms"] / 20 for s in stage_all},
             "roofline": {"kernel": "recall_scan_kernel<64,THRESH>", "bound": "hbm", "achieved": achieved,
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                          "peak_source": f"MEASURED_PEAKS.json ({pk_kind})", "launch_ms": scan_ms,

@@ -146,6 +146,25 @@ typedef struct prg_dpp_params {
 int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_dpp_params* p,
             int32_t* out_idx, int32_t* out_n, int32_t* status, int mem);
 
+/* ---------------------------------------------------------------- SSD re-rank (sort/ssd_sort.go) */
+
+typedef struct prg_ssd_params {
+  double gamma;             /* SSDConf.Gamma (<=0 in the config -> 0.25, ssd_sort.go:62,81-83); abtest ssd_gamma; 0 = skip */
+  int32_t top_n;            /* ctx.Size */
+  int32_t window_size;      /* SSDConf.WindowSize, <=1 -> 5 (ssd_sort.go:358-361) */
+  int32_t norm_mode;        /* ssd_norm_quality_score 0/1/2 (ssd_sort.go:368-391) */
+  int32_t normalize_emb;    /* NormalizeEmb */
+  int32_t use_ssd_star;     /* SSDConf.UseSSDStar */
+  int32_t candidate_count;  /* SSDConf.CandidateCount */
+  double min_score_percent; /* SSDConf.MinScorePercent */
+} prg_ssd_params;
+
+/* Same calling convention as prg_dpp.  doSort sorts the candidates by score first (ssd_sort.go:301; stable order on
+ * the device), then SSDWithSlidingWindow picks min(n', top_n) items.  status 1 = upstream returned the sorted
+ * (truncated) list without re-ranking (gamma == 0, "all item score are zeros"): out_idx holds its first top_n. */
+int prg_ssd(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_ssd_params* p,
+            int32_t* out_idx, int32_t* out_n, int32_t* status, int mem);
+
 /* ---------------------------------------------------------------- fused request path */
 
 /* recall -> gather+rank -> score sort -> DPP for B requests, everything device resident in between.
@@ -170,8 +189,8 @@ int prg_lookup(const double* value, const uint8_t* present, int n, double* out);
 
 /* Number of kernels launched by this handle since init (bench.py's gpu_launches). */
 uint64_t prg_launch_count(prg_handle* h);
-/* Per-stage device time: enable != 0 turns on CUDA-event spans around each stage's launches (on the handle's
- * stream).  When ms_out / n_out are non-NULL the call synchronises, writes the accumulated milliseconds and span
+/* Per-stage device time: enable = 1 turns on CUDA-event spans around each stage's launches (on the handle's
+ * stream), enable = 2 only around the recall scan (the dominant kernel; least perturbation), 0 turns them off.  When ms_out / n_out are non-NULL the call synchronises, writes the accumulated milliseconds and span
  * counts per stage (8 entries: 0 scan, 1 scan-dense/sample, 2 select, 3 gather+FM, 4 MLP, 5 sort, 6 DPP, 7 other)
  * and resets the accumulators. */
 int prg_timing(prg_handle* h, int enable, double* ms_out, uint64_t* n_out);

@@ -206,6 +206,25 @@ def dpp_request(emb, score, top_n, alpha=1.0, window_size=10, norm_mode=0, norma
     return out[:ny].copy(), int(st.value)
 
 
+class SsdParams(C.Structure):
+    _fields_ = [("gamma", C.c_double), ("top_n", C.c_int32), ("window_size", C.c_int32), ("norm_mode", C.c_int32),
+                ("normalize_emb", C.c_int32), ("use_ssd_star", C.c_int32), ("candidate_count", C.c_int32),
+                ("min_score_percent", C.c_double)]
+
+
+def ssd_request(emb, score, top_n, gamma=0.25, window_size=5, norm_mode=0, normalize_emb=1, use_ssd_star=0,
+                candidate_count=0, min_score_percent=0.0):
+    emb = np.ascontiguousarray(emb, dtype=np.float64)
+    score = np.ascontiguousarray(score, dtype=np.float64)
+    n, D = emb.shape
+    p = SsdParams(gamma, top_n, window_size, norm_mode, normalize_emb, use_ssd_star, candidate_count, min_score_percent)
+    out = np.full(max(top_n, n), -1, dtype=np.int32)
+    st = C.c_int32(0)
+    ny = lib().orc_ssd_request(_p(emb, C.c_double), _p(score, C.c_double), C.c_int(n), C.c_int(D), C.byref(p),
+                               _p(out, C.c_int32), C.byref(st))
+    return out[:ny].copy(), int(st.value)
+
+
 def dpp_kernel_matrix(emb, rel, alpha=1.0, normalize=1):
     emb = np.ascontiguousarray(emb, dtype=np.float64)
     rel = np.ascontiguousarray(rel, dtype=np.float64)

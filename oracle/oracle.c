@@ -750,4 +750,140 @@ ORC_API void orc_dpp_kernel_matrix(const double* emb, const double* rel, int n, 
   free(F); free(r);
 }
 
+/* ------------------------------------------------------------------------------------------------ SSD */
+/*
+ * SSDSort.doSort + SSDWithSlidingWindow (sort/ssd_sort.go:297-343, :346-486), table path, one request with FRESH
+ * embeddings (upstream mutates the cached slices in place, :423-431,447-449, so its result depends on what earlier
+ * requests did to the cache; the first-request behaviour is the one restated).
+ *   emb: n x D (f64), score: Item.Score in input order.  doSort always sorts descending first (:301, Go pdqsort).
+ * gonum pieces: floats.Dot = f64.DotUnitary (4 partial sums), floats.Norm (scaled), floats.Add/Sub elementwise,
+ * VecDense.ScaleVec (dst = alpha * x).  [UNVERIFIED-UPSTREAM] as for DPP.
+ * out_idx: indices into the INPUT list.  *status: 0 = re-ranked (T = min(n', ctx.Size) entries), 1 = upstream returned
+ * the (sorted, truncated) items unchanged (gamma == 0, or all-zero scores with normalisation) -> identity over them.
+ */
+typedef struct {
+  double gamma;
+  int32_t top_n, window_size, norm_mode, normalize_emb, use_ssd_star, candidate_count;
+  double min_score_percent;
+} orc_ssd_params;
+
+ORC_API int orc_ssd_request(const double* emb_in, const double* score, int n, int D, const orc_ssd_params* p, int32_t* out_idx,
+                            int32_t* status) {
+  *status = 0;
+  if (n == 0) return 0;
+  const int Tsz = p->top_n;
+  int32_t* order = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+  orc_go_sort(score, n, 1, order); /* :301 */
+  int m = n;
+  if (p->gamma == 0) { /* :304-307 */
+    for (int i = 0; i < n; ++i) out_idx[i] = order[i];
+    *status = 1;
+    free(order);
+    return n;
+  }
+  if ((p->candidate_count > 0 || p->min_score_percent > 0) && n > Tsz) { /* :311-330 */
+    if (p->candidate_count > 0) {
+      const int cnt = Tsz > p->candidate_count ? Tsz : p->candidate_count;
+      if (cnt < m) m = cnt;
+    }
+    if (p->min_score_percent > 0 && m > Tsz) {
+      int idx = Tsz;
+      const double mx = score[order[0]];
+      for (; idx < m; ++idx)
+        if (score[order[idx]] / mx < p->min_score_percent) break;
+      m = idx;
+    }
+  }
+  int window = p->window_size;
+  if (window <= 1) window = 5; /* :358-361 (NewSSDSort defaults <=0 to 5 as well, :89-91) */
+  double* rel = (double*)malloc(sizeof(double) * (size_t)m);
+  for (int i = 0; i < m; ++i) rel[i] = score[order[i]];
+  if (p->norm_mode == 1) {
+    double mean = 0;
+    for (int i = 0; i < m; ++i) mean += rel[i];
+    mean /= (double)m;
+    double ss = 0, comp = 0;
+    for (int i = 0; i < m; ++i) { const double d = rel[i] - mean; ss += d * d; comp += d; }
+    const double var = (ss - comp * comp / (double)m) / (double)m;
+    if (mean == 0 || var == 0) *status = 1;
+    else { const double sd = sqrt(var); for (int i = 0; i < m; ++i) rel[i] = (rel[i] - mean) / sd; }
+  } else if (p->norm_mode == 2) {
+    const double mx = rel[0], mn = rel[m - 1], span = mx - mn;
+    if (span == 0) *status = 1;
+    else for (int i = 0; i < m; ++i) rel[i] = ((rel[i] - mn) / span) * (1 - 1e-6) + 1e-6;
+  }
+  if (*status) {
+    for (int i = 0; i < m; ++i) out_idx[i] = order[i];
+    free(rel); free(order);
+    return m;
+  }
+  double* E = (double*)malloc(sizeof(double) * (size_t)m * D);
+  for (int i = 0; i < m; ++i) {
+    double* e = E + (size_t)i * D;
+    memcpy(e, emb_in + (size_t)order[i] * D, sizeof(double) * (size_t)D);
+    if (p->normalize_emb) { const double s = 1 / g_norm2(e, D); for (int d = 0; d < D; ++d) e[d] *= s; }
+  }
+  const int T = m < Tsz ? m : Tsz;
+  uint8_t* selected = (uint8_t*)calloc((size_t)m, 1);
+  int32_t* indices = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T > 0 ? T : 1));
+  int* qB = (int*)malloc(sizeof(int) * (size_t)window);            /* CycleQueue of capacity window */
+  double* qP = (double*)malloc(sizeof(double) * (size_t)window * m);
+  int q_front = 0, q_len = 0;
+  double* qual = (double*)malloc(sizeof(double) * (size_t)m);
+  int t = 1, ni = 0;
+  int idx = g_max_idx(rel, m);
+  selected[idx] = 1;
+  indices[ni++] = idx;
+  double volume = p->gamma;
+  if (!p->use_ssd_star) {
+    const double l2 = g_norm2(E + (size_t)idx * D, D);
+    if (!(isnan(l2) || isinf(l2))) volume *= l2;
+  }
+  while (t < T) {
+    if (t > window) { /* :415-432: give back the projection on the item leaving the window */
+      const int i = qB[q_front];
+      const double* proj = qP + (size_t)q_front * m;
+      q_front = (q_front + 1) % window; --q_len;
+      const double* ei = E + (size_t)i * D;
+      for (int j = 0; j < m; ++j) {
+        if (selected[j]) continue;
+        double* ej = E + (size_t)j * D;
+        for (int d = 0; d < D; ++d) ej[d] = ej[d] + proj[j] * ei[d]; /* ScaleVec then floats.Add */
+      }
+    }
+    const int slot = (q_front + q_len) % window; /* B.Push(idx), P.Push(projections) */
+    qB[slot] = idx; ++q_len;
+    double* proj = qP + (size_t)slot * m;
+    const double* ei = E + (size_t)idx * D;
+    for (int j = 0; j < m; ++j) {
+      proj[j] = 0.0;
+      if (selected[j]) continue;
+      double* ej = E + (size_t)j * D;
+      double pj = g_dot_unitary(ej, ei, D);
+      pj /= g_dot_unitary(ei, ei, D);
+      if (isnan(pj) || isinf(pj)) pj = 1.0;
+      proj[j] = pj;
+      for (int d = 0; d < D; ++d) ej[d] = ej[d] - pj * ei[d]; /* ScaleVec then floats.Sub */
+    }
+    ++t;
+    for (int i = 0; i < m; ++i) {
+      if (selected[i]) qual[i] = -1.7976931348623157e308;
+      else {
+        const double l2 = g_norm2(E + (size_t)i * D, D);
+        qual[i] = (isnan(l2) || isinf(l2)) ? rel[i] + volume * 0.5 : rel[i] + volume * l2;
+      }
+    }
+    idx = g_max_idx(qual, m);
+    selected[idx] = 1;
+    indices[ni++] = idx;
+    if (!p->use_ssd_star) {
+      const double l2 = g_norm2(E + (size_t)idx * D, D);
+      if (!(isnan(l2) || isinf(l2))) volume *= l2;
+    }
+  }
+  for (int i = 0; i < ni; ++i) out_idx[i] = order[indices[i]];
+  free(rel); free(order); free(E); free(selected); free(indices); free(qB); free(qP); free(qual);
+  return ni;
+}
+
 ORC_API int orc_num_threads(void) { return orc_hw_threads(); }

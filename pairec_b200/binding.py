@@ -19,7 +19,7 @@ EXPORTS = [
     "prg_init", "prg_destroy", "prg_last_error", "prg_version", "prg_sync", "prg_stream", "prg_set_item_matrix",
     "prg_set_item_fields", "prg_set_feature_table", "prg_set_fm_bias", "prg_set_mlp", "prg_set_diversity_matrix",
     "prg_recall_topk", "prg_recall_local_keys", "prg_merge_keys", "prg_rank", "prg_sort_desc_host", "prg_sort_desc",
-    "prg_dpp", "prg_recommend", "prg_recommend_from_keys", "prg_lookup", "prg_launch_count", "prg_recall_stats", "prg_timing",
+    "prg_dpp", "prg_ssd", "prg_recommend", "prg_recommend_from_keys", "prg_lookup", "prg_launch_count", "prg_recall_stats", "prg_timing",
 ]
 
 
@@ -37,6 +37,18 @@ class DppParams(C.Structure):
     def __init__(self, alpha=1.0, top_n=50, window_size=10, norm_mode=0, normalize_emb=1, candidate_count=0,
                  min_score_percent=0.0):
         super().__init__(alpha, top_n, window_size, norm_mode, normalize_emb, candidate_count, min_score_percent)
+
+
+class SsdParams(C.Structure):
+    """prg_ssd_params (SSDSortConfig / abtest knobs of sort/ssd_sort.go)."""
+    _fields_ = [("gamma", C.c_double), ("top_n", C.c_int32), ("window_size", C.c_int32), ("norm_mode", C.c_int32),
+                ("normalize_emb", C.c_int32), ("use_ssd_star", C.c_int32), ("candidate_count", C.c_int32),
+                ("min_score_percent", C.c_double)]
+
+    def __init__(self, gamma=0.25, top_n=50, window_size=5, norm_mode=0, normalize_emb=1, use_ssd_star=0,
+                 candidate_count=0, min_score_percent=0.0):
+        super().__init__(gamma, top_n, window_size, norm_mode, normalize_emb, use_ssd_star, candidate_count,
+                         min_score_percent)
 
 
 def lib_path():
@@ -242,6 +254,18 @@ class Engine:
         cnt = np.zeros(B, dtype=np.int32)
         st = np.zeros(B, dtype=np.int32)
         self._ck(self._lib.prg_dpp(self._h, _ptr(rows), _ptr(score), C.c_int(B), C.c_int(n), C.byref(params), _ptr(idx),
+                                   _ptr(cnt), _ptr(st), C.c_int(MEM_HOST)))
+        return idx, cnt, st
+
+    def ssd(self, rows, score, params):
+        rows = _np(rows, np.uint32)
+        score = _np(score, np.float64)
+        B, n = rows.shape
+        T = params.top_n
+        idx = np.full((B, T), -1, dtype=np.int32)
+        cnt = np.zeros(B, dtype=np.int32)
+        st = np.zeros(B, dtype=np.int32)
+        self._ck(self._lib.prg_ssd(self._h, _ptr(rows), _ptr(score), C.c_int(B), C.c_int(n), C.byref(params), _ptr(idx),
                                    _ptr(cnt), _ptr(st), C.c_int(MEM_HOST)))
         return idx, cnt, st
 

@@ -165,7 +165,7 @@ void prg_destroy(prg_handle* h) {
     DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->row_norm, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
                       &h->out_row, &h->out_score, &h->out_n, &h->flags, &h->table_ptrs, &h->act[0], &h->act[1],
                       &h->fm_logit, &h->rank_rows, &h->rank_out, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
-                      &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->sort_in, &h->sort_perm, &h->rec_rows,
+                      &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->ssd_E, &h->ssd_P, &h->sort_in, &h->sort_perm, &h->rec_rows,
                       &h->rec_scores, &h->rec_perm, &h->rec_sorted_rows, &h->rec_sorted_scores};
     for (DevBuf* b : bufs) b->release();
     for (int l = 0; l < kMaxLayers; ++l) { h->mlp_W[l].release(); h->mlp_b[l].release(); }
@@ -211,7 +211,7 @@ int prg_timing(prg_handle* h, int enable, double* ms_out, uint64_t* n_out) {
       h->stage_n[i] = 0;
     }
   }
-  h->timing = enable != 0;
+  h->timing = enable;
   return PRG_OK;
 }
 

@@ -31,7 +31,7 @@ struct prg_handle {
   uint64_t launches = 0;
 
   // optional per-stage device timing (CUDA events on this handle's stream around each stage's launches)
-  bool timing = false;
+  int timing = 0;  // 0 off, 1 every stage, 2 only the recall scan (least perturbation of the step)
   struct Span { int stage; cudaEvent_t a, b; };
   std::vector<Span> spans;
   std::vector<cudaEvent_t> ev_pool;
@@ -115,6 +115,8 @@ struct prg_handle {
   bool dpp_generic = false;  // config "dpp_generic": force the one-CTA-per-request kernel (A/B measurements)
   prg::DevBuf dpp_scratch, dpp_rows, dpp_score, dpp_idx, dpp_n, dpp_status;
 
+  prg::DevBuf ssd_E, ssd_P;  // SSD: mutable fp64 embeddings [B][D][1024], projection history [B][w][1024]
+
   // ---- sort
   prg::DevBuf sort_in, sort_perm;
 
@@ -139,7 +141,7 @@ struct StageScope {
     return e;
   }
   StageScope(prg_handle* hh, int st) : h(hh), stage(st) {
-    if (h->timing) { a = get(h); cudaEventRecord(a, h->stream); }
+    if (h->timing == 1 || (h->timing == 2 && st == ST_SCAN)) { a = get(h); cudaEventRecord(a, h->stream); }
   }
   ~StageScope() {
     if (a) { cudaEvent_t b = get(h); cudaEventRecord(b, h->stream); h->spans.push_back({stage, a, b}); }

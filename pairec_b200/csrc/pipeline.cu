@@ -15,6 +15,10 @@ int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32
 int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
                int32_t* out_idx, int32_t* out_n, int32_t* status);
 
+// ssd.cu
+int ssd_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_ssd_params& p,
+               int32_t* out_idx, int32_t* out_n, int32_t* status);
+
 struct DevGuard {
   std::unique_lock<std::mutex> lk;
   explicit DevGuard(prg_handle* h) : lk(h->mu) {
@@ -263,6 +267,31 @@ int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int
   PRG_CUDA(cudaMemcpyAsync(h->dpp_score.p, score, M * 8, cudaMemcpyHostToDevice, h->stream));
   PRG_CUDA(cudaMemsetAsync(h->dpp_idx.p, 0xFF, TT * 4, h->stream));
   PRG_TRY(dpp_device(h, (const uint32_t*)h->dpp_rows.p, (const double*)h->dpp_score.p, B, n, *p, (int32_t*)h->dpp_idx.p,
+                     (int32_t*)h->dpp_n.p, (int32_t*)h->dpp_status.p));
+  PRG_CUDA(cudaMemcpyAsync(out_idx, h->dpp_idx.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_n, h->dpp_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(status, h->dpp_status.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+
+int prg_ssd(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_ssd_params* p,
+            int32_t* out_idx, int32_t* out_n, int32_t* status, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!rows || !score || !p || !out_idx || !out_n || !status) return fail(PRG_EINVAL, "null buffer");
+  if (B <= 0 || n <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "B, n, top_n must be positive");
+  DevGuard g(h);
+  if (mem == PRG_MEM_DEVICE) return ssd_device(h, rows, score, B, n, *p, out_idx, out_n, status);
+  const size_t M = (size_t)B * n, TT = (size_t)B * p->top_n;
+  PRG_TRY(h->dpp_rows.ensure(M * 4));
+  PRG_TRY(h->dpp_score.ensure(M * 8));
+  PRG_TRY(h->dpp_idx.ensure(TT * 4));
+  PRG_TRY(h->dpp_n.ensure((size_t)B * 4));
+  PRG_TRY(h->dpp_status.ensure((size_t)B * 4));
+  PRG_CUDA(cudaMemcpyAsync(h->dpp_rows.p, rows, M * 4, cudaMemcpyHostToDevice, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(h->dpp_score.p, score, M * 8, cudaMemcpyHostToDevice, h->stream));
+  PRG_CUDA(cudaMemsetAsync(h->dpp_idx.p, 0xFF, TT * 4, h->stream));
+  PRG_TRY(ssd_device(h, (const uint32_t*)h->dpp_rows.p, (const double*)h->dpp_score.p, B, n, *p, (int32_t*)h->dpp_idx.p,
                      (int32_t*)h->dpp_n.p, (int32_t*)h->dpp_status.p));
   PRG_CUDA(cudaMemcpyAsync(out_idx, h->dpp_idx.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaMemcpyAsync(out_n, h->dpp_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));

@@ -101,6 +101,8 @@ int ph_register_gpu_plugins(ph_server* s, const char* recall_algo, const char* r
       if (sc.Name == dpp_sort) dc = sc.DPPConf;
     sort::RegisterSort(dpp_sort, std::make_shared<sort::GpuDPPSort>(dc, s->catalog));
   }
+  for (auto& sc : s->conf.SortConfs)  // SortType "SSDSort" entries become GPU-backed sorts under their own names
+    if (sc.SortType == "SSDSort") sort::RegisterSort(sc.Name, std::make_shared<sort::GpuSSDSort>(sc.SSDConf, s->catalog));
   for (auto& rc : s->conf.RecallConfs)
     if (rc.RecallType == "VectorRecall") recall::RegisterRecall(rc.Name, std::make_shared<recall::VectorRecall>(rc, s->vectors));
   sort::Load(s->conf);

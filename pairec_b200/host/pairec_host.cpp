@@ -68,6 +68,16 @@ Error LoadConfig(const std::string& json, RecommendConfig* out) {
     c.DPPConf.NormalizeEmb = d["NormalizeEmb"].as_string();
     c.DPPConf.EnsurePositiveSim = d["EnsurePositiveSim"].as_string();
     c.DPPConf.FilterRetrieveIds = str_list(d["FilterRetrieveIds"]);
+    const Json& sd = s["SSDConf"];
+    c.SSDConf.Name = sd["Name"].as_string();
+    c.SSDConf.Gamma = sd["Gamma"].as_number();
+    c.SSDConf.UseSSDStar = sd["UseSSDStar"].as_bool(false);
+    c.SSDConf.WindowSize = sd["WindowSize"].as_int();
+    c.SSDConf.AbortRunCount = sd["AbortRunCount"].as_int();
+    c.SSDConf.CandidateCount = sd["CandidateCount"].as_int();
+    c.SSDConf.MinScorePercent = sd["MinScorePercent"].as_number();
+    c.SSDConf.NormalizeEmb = sd["NormalizeEmb"].as_string();
+    c.SSDConf.FilterRetrieveIds = str_list(sd["FilterRetrieveIds"]);
     out->SortConfs.push_back(c);
   }
   for (auto& f : root["FilterConfs"].arr) {
@@ -654,6 +664,55 @@ Error GpuDPPSort::Sort(SortData* d) {
         selected[(size_t)idx[(size_t)i]]->AddAlgoScore("dpp_relevance_score", score[(size_t)idx[(size_t)i]]);  // :411
         result.push_back(selected[(size_t)idx[(size_t)i]]);
       }
+    }
+  }
+  result.insert(result.end(), backup.begin(), backup.end());
+  candidates.swap(result);
+  return "";
+}
+GpuSSDSort::GpuSSDSort(const recconf::SSDSortConfig& c, std::shared_ptr<GpuCatalog> cat) : conf_(c), cat_(std::move(cat)) {
+  if (conf_.Gamma <= 0) conf_.Gamma = 0.25;     // ssd_sort.go:62,81-83
+  if (conf_.WindowSize <= 0) conf_.WindowSize = 5;  // :84-86
+}
+Error GpuSSDSort::Sort(SortData* d) {
+  auto& candidates = d->Data;
+  if (candidates.empty()) return "";
+  context::RecommendContext* ctx = d->Context;
+  if (conf_.AbortRunCount > 0 && (int)candidates.size() <= conf_.AbortRunCount) {  // :129-134
+    ItemRankScoreSort().Sort(d);
+    return "";
+  }
+  std::vector<module::ItemPtr> selected, backup;  // :158-176
+  for (auto& it : candidates) {
+    if (std::find(conf_.FilterRetrieveIds.begin(), conf_.FilterRetrieveIds.end(), it->RetrieveId) != conf_.FilterRetrieveIds.end())
+      backup.push_back(it);
+    else selected.push_back(it);
+  }
+  std::vector<module::ItemPtr> result = selected;
+  if (!selected.empty()) {
+    std::vector<uint32_t> rows(selected.size());
+    std::vector<double> score(selected.size());
+    for (size_t i = 0; i < selected.size(); ++i) {
+      auto r = cat_->row_of.find(selected[i]->Id);
+      rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFEu : r->second;
+      score[i] = selected[i]->Score;
+    }
+    prg_ssd_params p{};
+    p.gamma = conf_.Gamma;
+    p.top_n = ctx->Size;
+    p.window_size = conf_.WindowSize;
+    p.norm_mode = 0;
+    p.normalize_emb = (conf_.NormalizeEmb == "false" || conf_.NormalizeEmb == "False") ? 0 : 1;
+    p.use_ssd_star = conf_.UseSSDStar ? 1 : 0;
+    p.candidate_count = conf_.CandidateCount;
+    p.min_score_percent = conf_.MinScorePercent;
+    std::vector<int32_t> idx((size_t)std::max(1, ctx->Size), -1);
+    int32_t n = 0, st = 0;
+    if (prg_ssd(cat_->h, rows.data(), score.data(), 1, (int)rows.size(), &p, idx.data(), &n, &st, PRG_MEM_HOST) != PRG_OK) {
+      ctx->LogError(std::string("module=SSDSort\terror=") + prg_last_error());  // items unchanged, as upstream on errors
+    } else {
+      result.clear();
+      for (int i = 0; i < n; ++i) result.push_back(selected[(size_t)idx[(size_t)i]]);
     }
   }
   result.insert(result.end(), backup.begin(), backup.end());

@@ -49,7 +49,14 @@ struct DPPSortConfig {
   int WindowSize = 0, AbortRunCount = 0, CandidateCount = 0;
   std::vector<std::string> FilterRetrieveIds;
 };
-struct SortConfig { std::string Name, SortType, SortByField; double SwitchThreshold = 0; DPPSortConfig DPPConf; };
+struct SSDSortConfig {  // recconf/recconf.go:980-1000
+  std::string Name, NormalizeEmb;
+  double Gamma = 0, MinScorePercent = 0;
+  bool UseSSDStar = false;
+  int WindowSize = 0, AbortRunCount = 0, CandidateCount = 0;
+  std::vector<std::string> FilterRetrieveIds;
+};
+struct SortConfig { std::string Name, SortType, SortByField; double SwitchThreshold = 0; DPPSortConfig DPPConf; SSDSortConfig SSDConf; };
 struct SceneCategory { std::vector<std::string> RecallNames; };
 struct FilterConfig { std::string Name, FilterType; int RetainNum = 0; bool ShuffleItem = false; };   // recconf.go FilterConfig
 struct ActionConfig { std::string ActionType, ActionName; };                                          // :746-749
@@ -288,6 +295,15 @@ class GpuDPPSort : public ISort {
   Error Sort(SortData* d) override;
  private:
   recconf::DPPSortConfig conf_;
+  std::shared_ptr<GpuCatalog> cat_;
+};
+// SSDSort.Sort (sort/ssd_sort.go:108-190) with doSort + SSDWithSlidingWindow on the GPU (prg_ssd)
+class GpuSSDSort : public ISort {
+ public:
+  GpuSSDSort(const recconf::SSDSortConfig& c, std::shared_ptr<GpuCatalog> cat);
+  Error Sort(SortData* d) override;
+ private:
+  recconf::SSDSortConfig conf_;
   std::shared_ptr<GpuCatalog> cat_;
 };
 }  // namespace sort

@@ -185,3 +185,22 @@ def test_key_order_properties(oracle_lib):
     assert lib.orc_make_key(float("nan"), 10) < ks[0]           # NaN ranks below -inf
     assert lib.orc_make_key(1.0, 3) > lib.orc_make_key(1.0, 4)  # ties: lower row first
     assert lib.orc_key_row(lib.orc_make_key(1.0, 12345)) == 12345 and lib.orc_key_score(lib.orc_make_key(-2.5, 1)) == -2.5
+
+
+def test_ssd_edge_cases(oracle_lib):
+    rng = np.random.default_rng(8)
+    emb = rng.standard_normal((40, 12))
+    score = rng.random(40)
+    idx, st = oracle_lib.ssd_request(emb, score, 15, gamma=0.25, window_size=5)
+    assert st == 0 and len(idx) == 15 and len(set(idx.tolist())) == 15
+    assert idx[0] == int(np.argmax(score))                       # first pick = best score (ssd_sort.go:394)
+    # gamma == 0: sorted list returned unchanged (:304-307)
+    idx0, st0 = oracle_lib.ssd_request(emb, score, 15, gamma=0.0)
+    assert st0 == 1 and idx0.tolist() == oracle_lib.go_sort(score).tolist()
+    # ctx.Size > n: T = min(N, ctx.Size) (:395)
+    idx1, st1 = oracle_lib.ssd_request(emb[:6], score[:6], 30, gamma=0.25)
+    assert st1 == 0 and sorted(idx1.tolist()) == list(range(6))
+    # a large gamma makes the pick sequence diversity driven: orthogonal-ish items first
+    e2 = np.eye(4)[[0, 0, 1, 2]] + 1e-3 * rng.standard_normal((4, 4))
+    idx2, _ = oracle_lib.ssd_request(e2, np.array([0.9, 0.8, 0.1, 0.1]), 3, gamma=10.0, window_size=5)
+    assert idx2[0] == 0 and 1 not in idx2.tolist()[:3]          # the near-duplicate of item 0 is not picked

@@ -91,3 +91,43 @@ def test_dpp_cluster_dims(engine, oracle_lib):
         _dpp_case(engine, oracle_lib, n=1000, dim=dim, top_n=50, alpha=1.0, window_size=10)
     _dpp_case(engine, oracle_lib, n=1024, dim=64, top_n=24, alpha=0.7, window_size=24)
     _dpp_case(engine, oracle_lib, n=5, dim=32, top_n=3, alpha=1.0, window_size=10)
+
+
+def _ssd_case(engine, oracle_lib, n, dim, top_n, dtype=np.float32, **kw):
+    from pairec_b200 import SsdParams
+    D = synth.diversity(n_items=3000, dim=dim, dtype=dtype)
+    # not unit-norm on purpose: SSD's quality term uses the residual norms
+    D = (D * (1.0 + 0.3 * np.sin(np.arange(3000))[:, None])).astype(dtype)
+    engine.set_diversity_matrix(D)
+    rng = np.random.default_rng(n * 7 + top_n)
+    B = 3
+    rows = np.stack([rng.choice(3000, size=n, replace=False) for _ in range(B)]).astype(np.uint32)
+    score = rng.random((B, n))
+    p = SsdParams(top_n=top_n, **kw)
+    idx, cnt, st = engine.ssd(rows, score, p)
+    for b in range(B):
+        want, wst = oracle_lib.ssd_request(D[rows[b]].astype(np.float64), score[b], top_n, gamma=p.gamma,
+                                           window_size=p.window_size, norm_mode=p.norm_mode,
+                                           normalize_emb=p.normalize_emb, use_ssd_star=p.use_ssd_star,
+                                           candidate_count=p.candidate_count, min_score_percent=p.min_score_percent)
+        assert st[b] == wst
+        take = min(len(want), top_n)
+        assert cnt[b] == take
+        assert (idx[b, :take] == want[:take]).all(), f"request {b}: SSD pick sequence differs"
+
+
+def test_ssd_config4_shape(engine, oracle_lib):
+    _ssd_case(engine, oracle_lib, n=1000, dim=128, top_n=50, gamma=0.25, window_size=5)
+
+
+@pytest.mark.parametrize("kw", [dict(gamma=0.5, window_size=3), dict(gamma=0.25, window_size=5, normalize_emb=0),
+                                dict(gamma=0.25, window_size=8, use_ssd_star=1), dict(gamma=0.25, window_size=5, norm_mode=1),
+                                dict(gamma=0.25, window_size=5, norm_mode=2), dict(gamma=0.25, window_size=4, candidate_count=150),
+                                dict(gamma=0.0, window_size=5)])
+def test_ssd_variants(engine, oracle_lib, kw):
+    _ssd_case(engine, oracle_lib, n=300, dim=32, top_n=21, **kw)
+
+
+def test_ssd_f64_table_and_small_inputs(engine, oracle_lib):
+    _ssd_case(engine, oracle_lib, n=200, dim=24, top_n=10, dtype=np.float64, gamma=0.25, window_size=5)
+    _ssd_case(engine, oracle_lib, n=7, dim=16, top_n=20, gamma=0.25, window_size=5)   # ctx.Size > n: T = n
