@@ -1,25 +1,29 @@
 // dpp_cluster.cu — the fast path of DPPSort.doSort (sort/dpp_sort.go:271-351, :372-475, :477-551) for f32 diversity
-// tables with dim 32 / 64 / 128: one thread-block CLUSTER of 4 CTAs per request, 256 candidates per CTA, the
-// candidates' embeddings resident in SHARED MEMORY ([dim][item], conflict-free), two threads per candidate.
+// tables with dim 32 / 64 / 128: one thread-block CLUSTER of 4 CTAs per request, 256 candidates per CTA, two threads
+// (a lane pair) per candidate, the candidates' fp64 FEATURES resident on chip (registers + shared memory).
 //
 // Why: the selection loop is 50 dependent steps of "row of L for the chosen item against every candidate" — n x (D+1)
 // fp64 multiply-adds per step with nothing reused between steps.  With one CTA per request (dpp.cu) every step
 // re-reads the request's embeddings through L2 and stalls on that latency (ncu r1: 62 % long-scoreboard, 1.56 ms per
-// 64-request batch).  Spreading a request over 4 SMs keeps the embeddings on chip; the two 64-wide k blocks of the
-// gonum dot product go to two threads (their partial sums are independent by construction), so a step is one pass of
-// fp64 issue over 16 warps + ONE cluster barrier.  v2 of this kernel kept the embedding in 128 registers per thread
-// (0.45 ms per batch; ncu r2: 63 % of issue slots lost to instruction fetch of the fully unrolled 129-term loops and
-// ~45 % of the step spent in barriers and the winner's row fetch); v3 loops over shared memory instead and ships
-// the winner's embedding inside the published record, so no global load sits on the critical path.
+// 64-request batch).  History of this kernel (64 requests x 1000 candidates x 128-d, top 50, window 10):
+//   v2  embeddings as f32 in 128 registers per thread: 0.45 ms; 63 % of issue slots lost to instruction fetch.
+//   v3  embeddings as f32 in shared memory, features rebuilt every step (cvt + 2 dmul per element before the
+//       multiply-add): 0.46 ms; ncu (profiles/r01_dpp_v3_ncu_full_summary.txt): fp64 pipe 33 %, 5 fp64 ops + one
+//       F2F.F64.F32 per element, 20 % of samples in CTA barriers (unbalanced k-block split, 4 barriers per step).
+//   v4  (this file) the rounded fp64 feature f = rn(rn(x*inv)*2^-1/2) is computed ONCE and kept — the winner's record
+//       carries its features, so a step is exactly one dmul + one dadd per element; gonum's four DotUnitary chains
+//       are split by parity over the lane pair (lane 0: s0,s2; lane 1: s1,s3; one shuffle per 64-wide block), which
+//       balances the two lanes for every dim and needs no barrier; one CTA barrier + one cluster barrier per step.
 //
 // Arithmetic is exactly dpp.cu's (and oracle/oracle.c's): fp64, gonum operation order, separate multiply/add
 // roundings, first-maximum argmax (rank order == index order), NaN masking, 1e-10 early stop + lowest-index fill.
 // Per step each CTA publishes its local arg-max candidate TOGETHER with everything the others need about it
-// (d2, 1/norm, quality, its embedding, its column of C) into every CTA's shared memory (DSMEM); the records are
+// (d2, quality, its features, its column of C) into every CTA's shared memory (DSMEM); the records are
 // double buffered so a fast CTA never overwrites what a slow one still reads.
 #include "handle.h"
 #include <cooperative_groups.h>
 #include <math_constants.h>
+#include <type_traits>
 
 namespace cg = cooperative_groups;
 
@@ -38,6 +42,7 @@ struct DppClArgs {
   const double* score;
   int n;
   const float* D;
+  const double* D_inv;  // 1 / ||row|| per table row (dpp_inv_norm_kernel)
   uint64_t D_rows;
   prg_dpp_params p;
   int32_t* out_idx;
@@ -46,14 +51,30 @@ struct DppClArgs {
 };
 
 template <int D>
+struct ClCfg {
+  static constexpr int kBlocks = (D + 63) / 64;             // gonum 64-wide k blocks that hold embedding features
+  static constexpr int kLPC = 4 * kBlocks;                  // lanes per candidate group: one per (block, DotUnitary chain)
+  static constexpr int kR = kLPC / 2;                       // candidates per group (and per thread)
+  static constexpr int kCL = D >= 64 ? 16 : D / 4;          // chain length: features per (candidate, lane)
+  static constexpr int kTR = (D == 128) ? 8 : kCL;          // of those, kept in registers
+  static constexpr int kSlots = kR * (kCL - kTR);           // shared-memory feature slots per thread ([slot][512] doubles)
+  static constexpr int kFDoubles = (kSlots * 512 > 128 * D) ? kSlots * 512 : 128 * D;  // F region; first holds the f32 staging [256][D]
+  static constexpr int kFS = kCL + 2;                       // lane stride (doubles) of a feature record: 16-B accesses of the
+                                                            // 4 / 8 lanes of a group fall into distinct banks
+  static constexpr bool kConstOwnBlock = (D % 64) == 0;     // the constant feature D opens a block of its own
+};
+
+template <int D>
 struct __align__(16) CandRecT {
   double v;       // d2 of the candidate (NaN if the CTA has none)
-  double inv;     // 1 / ||e||
+  uint64_t key;   // its order key (0 = none)
   double q;       // exp(alpha * rel)
+  double inv_dj;  // 1 / sqrt(d2): computed by the publishing thread while the winner's warp ships the features
   int32_t idx;    // index in the truncated list
   uint32_t row;   // diversity-table row (diagnostics)
+  double pad_;
   double cj[kClCRows];
-  float x[D];     // the candidate's embedding
+  double f[ClCfg<D>::kLPC * ClCfg<D>::kFS];  // features by (lane of the group, chain position); the constant feature is implied
 };
 
 __device__ __forceinline__ uint64_t f64_ord_c(double d) {
@@ -61,76 +82,110 @@ __device__ __forceinline__ uint64_t f64_ord_c(double d) {
   if ((u & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return 0ull;
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
-struct AmC { double v; int i; };
-__device__ __forceinline__ AmC amc(AmC a, AmC b) {
-  if (isnan(b.v)) return a;
-  if (isnan(a.v)) return b;
-  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
-  return a;
+// order key of a d2 value for the first-maximum search: NaN -> 0 (never wins), -0 == +0 (gonum compares with >)
+__device__ __forceinline__ uint64_t d2_key(double d) {
+  uint64_t u = (uint64_t)__double_as_longlong(d);
+  if ((u << 1) == 0) u = 0;
+  if ((u & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return 0ull;
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double d2_from_key(uint64_t k) {
+  if (k == 0) return CUDART_NAN;
+  const uint64_t u = (k >> 63) ? (k ^ 0x8000000000000000ull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+// warp-wide (max key, lowest index among equals) with three REDUX ops instead of five 64-bit shuffle rounds
+__device__ __forceinline__ void warp_first_max(uint64_t key, int idx, uint64_t* kout, int* iout) {
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned H = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned L = __reduce_max_sync(0xffffffffu, hi == H ? lo : 0u);
+  const unsigned I = __reduce_min_sync(0xffffffffu, (hi == H && lo == L) ? (unsigned)idx : 0x7FFFFFFFu);
+  *kout = ((uint64_t)H << 32) | L;
+  *iout = (int)I;
+}
+// cluster publication primitives: smem -> peer smem bulk copy (async proxy) completing on the PEER's mbarrier
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (long long spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && spins > (1ll << 26)) __trap();
+  }
+}
+__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
+  return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
-// One 64-wide k block of gonum's DotUnitary for candidate `it`: positions [k0, k0+len) of the D+1 features, four
-// partial sums by position mod 4 over the full groups, the tail (always the constant feature D) into s0, then
-// (s0+s2)+(s1+s3).  xs = embeddings [d][256] in shared memory; other = f_j (nullptr: the diagonal, g == f).
-template <int D>
-__device__ __forceinline__ double block_dot(const float* xs, int it, int k0, int len, double inv, bool do_norm,
-                                            const double* other) {
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  const int full = len & ~3;
-  auto feat = [&](int d) -> double {
-    const double xv = (double)xs[d * kClItems + it];
-    return do_norm ? __dmul_rn(__dmul_rn(xv, inv), kInvSqrt2c) : __dmul_rn(xv, kInvSqrt2c);
-  };
-#pragma unroll 2
-  for (int t = 0; t < full; t += 4) {
-    const int d = k0 + t;
-    const double f0 = feat(d), f1 = feat(d + 1), f2 = feat(d + 2), f3 = feat(d + 3);
-    const double g0 = other ? other[d] : f0, g1 = other ? other[d + 1] : f1, g2 = other ? other[d + 2] : f2,
-                 g3 = other ? other[d + 3] : f3;
-    s0 = __dadd_rn(s0, __dmul_rn(g0, f0));
-    s1 = __dadd_rn(s1, __dmul_rn(g1, f1));
-    s2 = __dadd_rn(s2, __dmul_rn(g2, f2));
-    s3 = __dadd_rn(s3, __dmul_rn(g3, f3));
-  }
-  for (int t = full; t < len; ++t) {  // at most one element: the constant feature (position D)
-    const int d = k0 + t;
-    const double f = (d == D) ? kInvSqrt2c : feat(d);
-    const double g = other ? other[d] : f;
-    s0 = __dadd_rn(s0, __dmul_rn(g, f));
-  }
-  return __dadd_rn(__dadd_rn(s0, s2), __dadd_rn(s1, s3));
-}
+#ifdef PRG_DPP_PROFILE
+__device__ long long g_dpp_clk[16];
+// per-segment cycle sums of thread 0 of CTA 0, accumulated in shared memory (a global read-modify-write per probe would
+// add its own L2 round trip to every segment) and flushed once at the end
+#define DPP_CLK(slot) do { if (tid == 0) { const long long t_ = clock64(); s_clk[slot] += t_ - t_last; t_last = t_; } } while (0)
+#else
+#define DPP_CLK(slot) do { } while (0)
+#endif
 
 template <int D>
 __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClArgs a) {
   using CandRec = CandRecT<D>;
-  constexpr int D1 = D + 1;
-  constexpr int NB = (D1 + 63) / 64;  // k blocks: part 0 owns block 0, part 1 the rest
+  using Cfg = ClCfg<D>;
+  constexpr int LPC = Cfg::kLPC, R = Cfg::kR, CL = Cfg::kCL, TR = Cfg::kTR, FS = Cfg::kFS;
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
   const int b = blockIdx.x / kClCtas;
   extern __shared__ __align__(16) uint8_t csm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int it = tid & (kClItems - 1), part = tid >> 8;
+  const int grp = tid / LPC, lam = tid % LPC;   // group of LPC lanes serves candidates grp*R .. grp*R+R-1 of this CTA
+  const int q = lam & 3, bb = lam >> 2;         // this lane: DotUnitary chain q of k block bb, for each of the R candidates
   const int n = a.n, T_out = a.p.top_n;
   const int window = a.p.window_size > 0 ? a.p.window_size : 10;
+  const int c_rows = T_out <= window ? T_out : window;
+  const bool small_window = c_rows <= 10;  // then k <= 8: the <c_j, c_i> sum is fused into the Gram row code
 
-  double* C = reinterpret_cast<double*>(csm);                                   // [24][256]  (48 KiB, also presort staging)
-  float* xs = reinterpret_cast<float*>(C + kClCRows * kClItems);                // [D][256]
-  CandRec* pub = reinterpret_cast<CandRec*>(xs + D * kClItems);                 // [2][4]
-  double* fj = reinterpret_cast<double*>(pub + 2 * kClCtas);                    // [D+1] padded to 136
-  double* blk_s = fj + 136;                                                     // [2][256] partial block sums of part 1
-  double* inv_s = blk_s + 2 * kClItems;                                         // [256]
-  double* red_v = inv_s + kClItems;                                             // [8]
-  int32_t* red_i = reinterpret_cast<int32_t*>(red_v + 8);                       // [8]
-  int32_t* order = red_i + 8;                                                   // [1024]
+  double* C = reinterpret_cast<double*>(csm);                                   // [c_rows][256]
+  double* F = C + (size_t)c_rows * kClItems;                                    // [kSlots][512] features kept in smem
+  CandRec* pub = reinterpret_cast<CandRec*>(F + Cfg::kFDoubles);                // [2][4]
+  CandRec* srec = pub + 2 * kClCtas;                                            // [2] this CTA's own record, staged for the copy
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(srec + 2);                       // [2] one per record buffer
+  double* inv_s = reinterpret_cast<double*>(mbar + 2);                          // [256]
+  double* q_s = inv_s + kClItems;                                               // [256]
+  uint64_t* red_k = reinterpret_cast<uint64_t*>(q_s + kClItems);                // [16]
+  int32_t* red_i = reinterpret_cast<int32_t*>(red_k + 16);                      // [16]
+  uint32_t* row_s = reinterpret_cast<uint32_t*>(red_i + 16);                    // [256]
+  int32_t* order = reinterpret_cast<int32_t*>(row_s + kClItems);                // [1024]
   int32_t* res = order + kClMaxItems;                                           // [T_out]
   uint8_t* existed = reinterpret_cast<uint8_t*>(res + ((T_out + 3) & ~3));      // [1024]
-  __shared__ int s_m, s_err, s_ny, s_li;
+  __shared__ int s_m, s_err, s_ny;
   __shared__ double s_p0, s_p1;
 
   const uint32_t* rows = a.rows + (size_t)b * n;
   const double* score = a.score + (size_t)b * n;
+#ifdef PRG_DPP_PROFILE
+  __shared__ long long s_clk[16];
+  if (tid == 0)
+    for (int i = 0; i < 16; ++i) s_clk[i] = 0;
+  long long t_last = clock64();
+#endif
 
   // ---- 0. valid count, optional presort + truncation (:280-300); done redundantly by every CTA of the cluster
   if (tid == 0) { s_m = 0; s_err = 0; }
@@ -148,7 +203,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   if (nv > 0 && presort) {
     uint32_t P2 = 32;
     while (P2 < (uint32_t)nv) P2 <<= 1;
-    uint64_t* key = reinterpret_cast<uint64_t*>(csm);
+    uint64_t* key = reinterpret_cast<uint64_t*>(csm);  // staging over C / F (not live yet); 12 B x P2 <= 48 KiB
     int32_t* idx = reinterpret_cast<int32_t*>(key + P2);
     for (uint32_t i = tid; i < P2; i += kClThreads) {
       key[i] = (i < (uint32_t)nv) ? f64_ord_c(score[i]) : 0ull;
@@ -196,13 +251,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   }
   __syncthreads();
 
-  const int gi = (int)rank * kClItems + it;  // this thread's candidate (index in the truncated list)
-  const bool active = gi < m;
-  const bool owner = part == 0;               // part 0 owns d2, C, the publication; part 1 only adds block sums
-  const int my_in = active ? order[gi] : 0;
-
-  // ---- 1. relevance + abtest normalisation modes (:382-405), redundantly per CTA
-  double rel = active ? score[my_in] : 0.0;
+  // ---- 1. abtest normalisation parameters (:382-405), redundantly per CTA
   if (a.p.norm_mode == 1 || a.p.norm_mode == 2) {
     if (tid == 0) {
       if (a.p.norm_mode == 1) {
@@ -228,140 +277,252 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
       }
     }
     __syncthreads();
-    if (a.p.norm_mode == 1) rel = __dsub_rn(rel, s_p0) / s_p1;
-    else rel = __dadd_rn(__dmul_rn(__dsub_rn(rel, s_p0) / s_p1, 1 - 1e-6), 1e-6);
   }
-  __syncthreads();
   if (s_err) {
     if (rank == 0 && tid == 0) { a.out_n[b] = 0; a.status[b] = 1; }
     return;
   }
+  DPP_CLK(0);
 
-  // ---- 2. embeddings -> shared memory [d][item]; norm (gonum floats.Norm scaled form) and quality by the owner
-  uint32_t my_row = 0;
-  double inv = 1.0, qi = 0.0;
-  if (owner) {
-    my_row = active ? rows[my_in] : 0u;
-    const bool have = active && (uint64_t)my_row < a.D_rows;
-    if (!have) my_row = 0;
-    const float4* src = reinterpret_cast<const float4*>(a.D + (size_t)my_row * D);
-    double scale = 0.0, sumsq = 1.0;
-#pragma unroll 4
-    for (int d4 = 0; d4 < D / 4; ++d4) {
-      const float4 v4 = have ? src[d4] : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float e4[4] = {v4.x, v4.y, v4.z, v4.w};
+  // ---- 2a. rows -> coalesced staging of the 256 embeddings in shared memory -> one thread per candidate: relevance,
+  //          1/norm (table lookup), quality.
+  //          * staging: thread-per-row reads of 512-B rows were 16 dependent HBM round trips; here every warp loads
+  //            whole rows (16 independent 16-B loads per thread) into XS (over the F region, 16-B chunks XOR-swizzled
+  //            by row so both the row-wise reads of 2a and the chain-wise reads of 2b are conflict-light).
+  constexpr int CH = D / 4;  // 16-B chunks per embedding
+  float* XS = reinterpret_cast<float*>(F);
+  if (tid == 0) {  // (past the last early return: every CTA of the cluster gets here)
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+  }
+  cluster.barrier_arrive();  // peers may signal our mbarriers only after this; waited for before the first publication
+  if (tid < kClItems) {
+    const int c = (int)rank * kClItems + tid;
+    const bool act = c < m;
+    const uint32_t r = act ? rows[order[c]] : 0u;
+    row_s[tid] = (act && (uint64_t)r < a.D_rows) ? r : 0xFFFFFFFFu;
+  }
+  for (int i = tid; i < kClMaxItems; i += kClThreads) existed[i] = 0;
+  __syncthreads();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        xs[(4 * d4 + c) * kClItems + it] = e4[c];
-        const double v = (double)e4[c];
-        if (v != 0.0) {
-          const double av = fabs(v);
-          if (scale < av) {
-            const double sc = scale / av;
-            sumsq = __dadd_rn(1.0, __dmul_rn(__dmul_rn(sumsq, sc), sc));
-            scale = av;
-          } else {
-            const double sc = av / scale;
-            sumsq = __dadd_rn(sumsq, __dmul_rn(sc, sc));
-          }
+  for (int g = tid; g < kClItems * CH; g += kClThreads) {
+    const int row = g / CH, c = g % CH;
+    const uint32_t rw = row_s[row];
+    const float4 v = (rw != 0xFFFFFFFFu) ? reinterpret_cast<const float4*>(a.D + (size_t)rw * D)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(XS + (size_t)row * D + 4 * (c ^ (row & (CH - 1)))) = v;
+  }
+  __syncthreads();
+  if (tid < kClItems) {
+    const int c = (int)rank * kClItems + tid;
+    const bool act = c < m;
+    double rel = act ? score[order[c]] : 0.0;
+    if (a.p.norm_mode == 1) rel = __dsub_rn(rel, s_p0) / s_p1;
+    else if (a.p.norm_mode == 2) rel = __dadd_rn(__dmul_rn(__dsub_rn(rel, s_p0) / s_p1, 1 - 1e-6), 1e-6);
+    // 1 / ||e|| comes from the per-row table built when the matrix was set (dpp_inv_norm_kernel: gonum floats.Norm in
+    // its exact operation order).  Computing it here cost 44k cycles per request — 128 dependent divide/accumulate steps
+    // per candidate with only half the warps busy — for a value that is a pure function of the table row.  A row
+    // outside the table stands for a zero embedding: norm 0, inverse +inf, NaN features, exactly as computed before.
+    const uint32_t rw = row_s[tid];
+    const double inv = !a.p.normalize_emb ? 1.0 : (rw != 0xFFFFFFFFu ? a.D_inv[rw] : 1.0 / __dmul_rn(0.0, 1.0));
+    inv_s[tid] = inv;
+    q_s[tid] = act ? exp(__dmul_rn(a.p.alpha, rel)) : 0.0;
+  }
+  __syncthreads();
+  DPP_CLK(1);
+
+  // ---- 2b. the rounded fp64 features, built once.  Lane (bb, q) of a group holds, for each of the group's R
+  //          candidates, chain q of block bb: features 64*bb + 4*t + q, t < CL; the first TR in registers, the rest
+  //          in shared memory slots [r*(CL-TR) + t-TR][tid] (written after every thread has read its staged values:
+  //          the slots overlay XS).
+  double fr[R][TR];
+  // shared-memory features: chain positions (t, t+1), t >= TR even, of candidate r form one 16-byte element [pair][tid]
+  auto f_idx = [&](int r, int t) -> size_t {
+    return ((size_t)(r * ((CL - TR) / 2) + ((t - TR) >> 1)) * kClThreads + tid) * 2 + ((t - TR) & 1);
+  };
+  {
+    const bool do_norm = a.p.normalize_emb != 0;
+    float xt[R][CL - TR > 0 ? CL - TR : 1];
+    double invr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int cand = grp * R + r;
+      invr[r] = inv_s[cand];
+      const float* src = XS + (size_t)cand * D + q;
+#pragma unroll
+      for (int t = 0; t < CL; ++t) {
+        const float xf = src[4 * ((16 * bb + t) ^ (cand & (CH - 1)))];
+        if (t < TR) {
+          const double x = (double)xf;
+          fr[r][t < TR ? t : 0] = do_norm ? __dmul_rn(__dmul_rn(x, invr[r]), kInvSqrt2c) : __dmul_rn(x, kInvSqrt2c);
+        } else {
+          xt[r][t >= TR ? t - TR : 0] = xf;
         }
       }
     }
-    if (a.p.normalize_emb) inv = 1.0 / __dmul_rn(scale, sqrt(sumsq));
-    if (active) qi = exp(__dmul_rn(a.p.alpha, rel));
-    inv_s[it] = inv;
-  }
-  for (int i = tid; i < kClMaxItems; i += kClThreads) existed[i] = 0;
-  const bool do_norm = a.p.normalize_emb != 0;
-  __syncthreads();
-  inv = inv_s[it];
-
-  // S[j][i] in gonum Dgemm(NoTrans,Trans) order: block sums added to C in block order (0 + b0) + b1 + b2.
-  // part 0 computes block 0, part 1 the remaining blocks -> blk_s; one barrier; the owner finishes.
-  auto gram = [&](const double* other) -> double {
-    double acc = 0.0;
-    if (owner) {
-      acc = __dadd_rn(0.0, block_dot<D>(xs, it, 0, D1 < 64 ? D1 : 64, inv, do_norm, other));
-    } else {
-#pragma unroll
-      for (int bb = 1; bb < NB; ++bb) {
-        const int k0 = bb * 64;
-        blk_s[(bb - 1) * kClItems + it] = block_dot<D>(xs, it, k0, (D1 - k0 < 64) ? (D1 - k0) : 64, inv, do_norm, other);
-      }
-    }
-    if (NB > 1) {
+    if (Cfg::kSlots > 0) {
       __syncthreads();
-      if (owner) {
 #pragma unroll
-        for (int bb = 1; bb < NB; ++bb) acc = __dadd_rn(acc, blk_s[(bb - 1) * kClItems + it]);
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int t = TR; t < CL; ++t) {
+          const double x = (double)xt[r][t - TR];
+          F[f_idx(r, t)] = do_norm ? __dmul_rn(__dmul_rn(x, invr[r]), kInvSqrt2c) : __dmul_rn(x, kInvSqrt2c);
+        }
       }
     }
-    return acc;
+  }
+  const double cc = __dmul_rn(kInvSqrt2c, kInvSqrt2c);  // product of the constant feature with itself
+
+  // S[j][i] in gonum Dgemm(NoTrans,Trans) order: per 64-wide k block DotUnitary = (s0+s2)+(s1+s3), block sums added to
+  // C in block order from +0.  g = the other item's feature record (nullptr: the diagonal).  Every lane of the group
+  // ends with the R dot products in S[0..R).
+  //
+  // WITH_SS (windows of at most 10, i.e. k <= 8): the k-term sequential sum <c_j, c_i> of the update step rides in the
+  // same straight-line code, one row per loop step, so its latency hides under the Gram row instead of preceding it.
+  double S[R];
+  auto gram = [&](const double* g, auto with_ss, const double* wcj, int k, int c_it, double& ss) {
+    constexpr bool WITH_SS = decltype(with_ss)::value;
+    constexpr int LPI = 8 / (CL / 2);  // rows of C per loop step (1 for chains of 16, 2 for chains of 8)
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+#pragma unroll
+    for (int t = 0; t < CL; t += 2) {
+      double2 g2 = make_double2(0.0, 0.0);
+      if (g) g2 = *reinterpret_cast<const double2*>(g + lam * FS + t);
+      if (WITH_SS) {
+#pragma unroll
+        for (int u = 0; u < LPI; ++u) {
+          const int l = (t / 2) * LPI + u;
+          const double tm = (l < k) ? wcj[l] : 0.0;
+          const double pr = __dmul_rn(tm, C[l * kClItems + c_it]);
+          ss = (tm != 0) ? __dadd_rn(ss, pr) : ss;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        double fa, fb;
+        if (t < TR) {
+          fa = fr[r][t < TR ? t : 0];
+          fb = fr[r][t + 1 < TR ? t + 1 : 0];
+        } else {
+          const double2 f2 = *reinterpret_cast<const double2*>(F + f_idx(r, t));
+          fa = f2.x;
+          fb = f2.y;
+        }
+        acc[r] = __dadd_rn(acc[r], __dmul_rn(g ? g2.x : fa, fa));
+        acc[r] = __dadd_rn(acc[r], __dmul_rn(g ? g2.y : fb, fb));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double u = acc[r];
+      if (!Cfg::kConstOwnBlock && q == 0 && bb == Cfg::kBlocks - 1) u = __dadd_rn(u, cc);  // tail element -> s0
+      double o = shfl_xor_f64(u, 2);
+      const double pr = (q & 2) ? __dadd_rn(o, u) : __dadd_rn(u, o);      // s0+s2 | s1+s3
+      o = shfl_xor_f64(pr, 1);
+      const double bs = (q & 1) ? __dadd_rn(o, pr) : __dadd_rn(pr, o);    // (s0+s2)+(s1+s3)
+      double tot;
+      if (Cfg::kBlocks == 2) {
+        o = shfl_xor_f64(bs, 4);
+        tot = __dadd_rn(__dadd_rn(0.0, bb ? o : bs), bb ? bs : o);
+      } else {
+        tot = __dadd_rn(0.0, bs);
+      }
+      if (Cfg::kConstOwnBlock) tot = __dadd_rn(tot, cc);
+      S[r] = tot;
+    }
+  };
+  auto pick_own = [&]() -> double {  // the dot product of the candidate this lane owns (lam < R)
+    double v = S[0];
+#pragma unroll
+    for (int r = 1; r < R; ++r) v = (lam == r) ? S[r] : v;
+    return v;
   };
 
-  const double g0 = gram(nullptr);
-  const double diag = (owner && active) ? __dmul_rn(__dmul_rn(qi, g0), qi) : CUDART_NAN;
-  __syncthreads();
+  const bool owner = lam < R;                      // lane r of a group owns candidate grp*R + r: d2, C, quality
+  const int it = grp * R + (owner ? lam : 0);
+  const int gi = (int)rank * kClItems + it;        // index in the truncated list
+  const bool active = owner && gi < m;
+  const double qi = q_s[it];
+  DPP_CLK(2);
+  {
+    double unused = 0.0;
+    gram(nullptr, std::false_type{}, nullptr, 0, 0, unused);
+  }
+  const double diag = active ? __dmul_rn(__dmul_rn(qi, pick_own()), qi) : CUDART_NAN;
+  DPP_CLK(3);
 
-  // cluster-wide first-maximum argmax over the owners; every CTA ends up with the winner's record in pub[par][w]
+  // cluster-wide first-maximum argmax over the owners; every CTA ends up with the winner's record in pub[par][w].
+  // Two CTA barriers (per-warp maxima -> every warp reduces them redundantly; record staged) + one mbarrier wait.
   int par = 0;
+  uint32_t mb_phase = 0;      // bit p: parity to wait for on mbar[p]
+  cluster.barrier_wait();     // every CTA's mbarriers are initialised (arrive was before phase 2a)
   auto cluster_argmax = [&](double v, int krows) -> int {
-    if (warp < kClItems / 32) {  // owner warps
-      AmC am{v, it};
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        AmC o;
-        o.v = __shfl_xor_sync(0xffffffffu, am.v, off);
-        o.i = __shfl_xor_sync(0xffffffffu, am.i, off);
-        am = amc(am, o);
-      }
-      if (lane == 0) { red_v[warp] = am.v; red_i[warp] = am.i; }
-    }
+    uint64_t wk;
+    int wi;
+    warp_first_max(owner ? d2_key(v) : 0ull, it, &wk, &wi);
+    if (lane == 0) { red_k[warp] = wk; red_i[warp] = wi; }
+    DPP_CLK(6);
     __syncthreads();  // also: row k of C (written by the owners just before) is complete
-    if (warp == 0) {
-      AmC xx{lane < (kClItems / 32) ? red_v[lane & 7] : CUDART_NAN, lane < (kClItems / 32) ? red_i[lane & 7] : 0};
+    DPP_CLK(7);
+    uint64_t bk;
+    int li;
+    warp_first_max(red_k[lane & 15], red_i[lane & 15], &bk, &li);
+    if (bk == 0) li = 0;
+    // publish this CTA's candidate `li`: the record is assembled in srec[par] (features by the winner's group straight
+    // from registers / shared memory, its column of C by warp 15, the scalars by one thread), then ONE thread sends it to
+    // the four CTAs as bulk copies that complete on the receivers' mbarriers — no remote stores, no release fence, no
+    // cluster barrier on the critical path (the st.shared::cluster + cluster.sync version spent 23 % of the kernel in
+    // UCGABAR / membar stalls).
+    CandRec* mine = &srec[par];
+    const int wg = li / R, wr = li - wg * R;
+    if (grp == wg) {
 #pragma unroll
-      for (int off = 4; off > 0; off >>= 1) {
-        AmC o;
-        o.v = __shfl_xor_sync(0xffffffffu, xx.v, off);
-        o.i = __shfl_xor_sync(0xffffffffu, xx.i, off);
-        xx = amc(xx, o);
-      }
-      if (lane == 0) s_li = isnan(xx.v) ? 0 : xx.i;
+      for (int r = 0; r < R; ++r)
+        if (r == wr) {
+#pragma unroll
+          for (int t = 0; t < TR; t += 2) *reinterpret_cast<double2*>(mine->f + lam * FS + t) = make_double2(fr[r][t], fr[r][t + 1]);
+        }
+#pragma unroll
+      for (int t = TR; t < CL; t += 2)
+        *reinterpret_cast<double2*>(mine->f + lam * FS + t) = *reinterpret_cast<const double2*>(F + f_idx(wr, t));
     }
+    if (tid >= kClThreads - 32 && tid - (kClThreads - 32) < krows) {  // the candidate's column of C
+      const int l = tid - (kClThreads - 32);
+      mine->cj[l] = C[l * kClItems + li];
+    }
+    if (tid == kClThreads - 33) {
+      const double dv = d2_from_key(bk);
+      mine->v = dv;
+      mine->inv_dj = 1.0 / sqrt(dv);
+      mine->key = bk;
+      mine->q = q_s[li];
+      mine->idx = (int)rank * kClItems + li;
+      mine->row = row_s[li];
+    }
+    DPP_CLK(8);
     __syncthreads();
-    const int li = s_li;
-    // publish this CTA's candidate into every CTA's pub[par][rank]: scalars by its owner thread, its column of C by
-    // threads 0..krows-1, its embedding by threads 256..256+D-1 (part 1 is otherwise idle here)
-    if (owner && it == li) {
+    if (tid == 0) {
+      fence_proxy_async_smem();
+      mbar_arrive_expect_tx(&mbar[par], (uint32_t)(kClCtas * sizeof(CandRec)));
+      const uint32_t src = smem_u32(mine), dst = smem_u32(&pub[par * kClCtas + rank]), bar = smem_u32(&mbar[par]);
 #pragma unroll
-      for (int r = 0; r < kClCtas; ++r) {
-        CandRec* dst = cluster.map_shared_rank(&pub[par * kClCtas + rank], r);
-        dst->v = v;
-        dst->inv = inv;
-        dst->q = qi;
-        dst->idx = gi;
-        dst->row = my_row;
-      }
+      for (int r = 0; r < kClCtas; ++r)
+        bulk_copy_to_peer(mapa_u32(dst, r), src, (uint32_t)sizeof(CandRec), mapa_u32(bar, r));
     }
-    if (tid < krows) {
-      const double cv = C[tid * kClItems + li];
-#pragma unroll
-      for (int r = 0; r < kClCtas; ++r) cluster.map_shared_rank(&pub[par * kClCtas + rank], r)->cj[tid] = cv;
-    }
-    if (tid >= kClItems && tid - kClItems < D) {
-      const float xv = xs[(tid - kClItems) * kClItems + li];
-#pragma unroll
-      for (int r = 0; r < kClCtas; ++r) cluster.map_shared_rank(&pub[par * kClCtas + rank], r)->x[tid - kClItems] = xv;
-    }
-    cluster.sync();
-    AmC best{pub[par * kClCtas].v, 0};
+    mbar_wait_bounded(&mbar[par], (mb_phase >> par) & 1);
+    mb_phase ^= 1u << par;
+    DPP_CLK(9);
+    uint64_t best_k = pub[par * kClCtas].key;
+    int best_r = 0;
 #pragma unroll
     for (int r = 1; r < kClCtas; ++r) {
-      const double rv = pub[par * kClCtas + r].v;
-      if (!isnan(rv) && (isnan(best.v) || rv > best.v)) { best.v = rv; best.i = r; }  // lower rank == lower index wins ties
+      const uint64_t rk = pub[par * kClCtas + r].key;
+      if (rk > best_k) { best_k = rk; best_r = r; }  // lower rank == lower index wins ties
     }
-    const int used = par * kClCtas + best.i;
+    const int used = par * kClCtas + best_r;
     par ^= 1;
     return used;
   };
@@ -372,7 +533,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   for (int call = 0; call < n_calls; ++call) {
     int top = (T_out <= window) ? T_out : ((call < T_out / window) ? window : T_out % window);
     if (top > m) top = m;
-    double d2 = (owner && active && !existed[gi]) ? diag : CUDART_NAN;
+    double d2 = (active && !existed[gi]) ? diag : CUDART_NAN;
     int wrec = cluster_argmax(d2, 0);
     int j = isnan(pub[wrec].v) ? 0 : pub[wrec].idx;
     if (tid == 0) res[total] = j;
@@ -382,37 +543,46 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
       const CandRec& W = pub[wrec];
       double dj = W.v;  // == d2[j]; NaN when every candidate is used up (the reference then repeats index 0)
       if (dj < 1e-10) { broke = true; break; }
-      dj = sqrt(dj);
-      const double inv_dj = 1.0 / dj;
       const int k = ny - 1;
-      const double inv_j = W.inv, q_j = W.q;
-      if (tid < D) {
-        const double xv = (double)W.x[tid];
-        fj[tid] = do_norm ? __dmul_rn(__dmul_rn(xv, inv_j), kInvSqrt2c) : __dmul_rn(xv, kInvSqrt2c);
+      // <c_j, c_i> over the k rows so far: sequential adds, zero terms skipped as in the reference
+      double ss = 0.0;
+      const double inv_dj = W.inv_dj;
+      const double q_j = W.q;
+      DPP_CLK(10);
+      if (small_window) {
+        gram(W.f, std::true_type{}, W.cj, k, it, ss);
+      } else {
+        if (active) {
+#pragma unroll 1
+          for (int l0 = 0; l0 < k; l0 += 4) {
+            double tm[4], cv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const bool in = l0 + u < k;
+              tm[u] = in ? W.cj[l0 + u] : 0.0;
+              cv[u] = in ? C[(l0 + u) * kClItems + it] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const double pr = __dmul_rn(tm[u], cv[u]);
+              ss = (tm[u] != 0) ? __dadd_rn(ss, pr) : ss;
+            }
+          }
+        }
+        gram(W.f, std::false_type{}, nullptr, 0, 0, ss);
       }
-      if (tid == D) fj[D] = kInvSqrt2c;
-      __syncthreads();
-      const double S = gram(fj);
+      DPP_CLK(4);
       if (owner) {
         if (active) {
-          const double Lji = __dmul_rn(__dmul_rn(q_j, S), qi);
-          double e;
-          if (k == 0) {
-            e = __dmul_rn(inv_dj, Lji);
-          } else {
-            double ss = 0.0;
-            for (int l = 0; l < k; ++l) {
-              const double tmp = W.cj[l];
-              if (tmp != 0) ss = __dadd_rn(ss, __dmul_rn(tmp, C[l * kClItems + it]));
-            }
-            e = __dmul_rn(inv_dj, __dsub_rn(Lji, ss));
-          }
+          const double Lji = __dmul_rn(__dmul_rn(q_j, pick_own()), qi);
+          const double e = (k == 0) ? __dmul_rn(inv_dj, Lji) : __dmul_rn(inv_dj, __dsub_rn(Lji, ss));
           C[k * kClItems + it] = e;
           d2 = __dsub_rn(d2, __dmul_rn(e, e));
         }
         if (gi == j) d2 = CUDART_NAN;
       }
-      wrec = cluster_argmax(d2, ny);  // its first barrier also orders the C[k] writes before the column reads
+      DPP_CLK(5);
+      wrec = cluster_argmax(d2, ny);  // its CTA barrier also orders the C[k] writes before the column reads
       j = isnan(pub[wrec].v) ? 0 : pub[wrec].idx;
       if (tid == 0) res[total + ny] = j;
       ++ny;
@@ -437,6 +607,11 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
     total += ny;
     __syncthreads();
   }
+  DPP_CLK(11);
+#ifdef PRG_DPP_PROFILE
+  if (blockIdx.x == 0 && tid == 0)
+    for (int i = 0; i < 16; ++i) g_dpp_clk[i] += s_clk[i];
+#endif
   if (rank == 0) {
     for (int t = tid; t < total; t += kClThreads) a.out_idx[(size_t)b * T_out + t] = order[res[t]];
     if (tid == 0) { a.out_n[b] = total; a.status[b] = 0; }
@@ -444,15 +619,55 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   cluster.sync();  // no CTA may exit while peers can still write into its shared memory
 }
 
+// 1 / ||row|| for every row of an f32 table, gonum floats.Norm (scaled sum of squares, true divisions) then
+// 1 / (scale * sqrt(sumsq)) — the value DPPSort's normalisation divides by (sort/dpp_sort.go:372-381).  One thread per row;
+// runs once per prg_set_diversity_matrix.
+__global__ void dpp_inv_norm_kernel(const float* __restrict__ D, uint64_t rows, int dim, double* __restrict__ out) {
+  const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* x = D + r * dim;
+  double scale = 0.0, sumsq = 1.0;
+  for (int d = 0; d < dim; ++d) {
+    const double v = (double)x[d];
+    if (v != 0.0) {
+      const double av = fabs(v);
+      if (scale < av) {
+        const double sc = scale / av;
+        sumsq = __dadd_rn(1.0, __dmul_rn(__dmul_rn(sumsq, sc), sc));
+        scale = av;
+      } else {
+        const double sc = av / scale;
+        sumsq = __dadd_rn(sumsq, __dmul_rn(sc, sc));
+      }
+    }
+  }
+  out[r] = 1.0 / __dmul_rn(scale, sqrt(sumsq));
+}
+
+int dpp_cluster_prepare(prg_handle* h) {
+  if (h->D_dtype != PRG_F32) return PRG_OK;  // f64 tables take the generic kernel, which normalises on the fly
+  PRG_TRY(h->D_inv.ensure((size_t)h->D_rows * 8));
+  const unsigned blocks = (unsigned)((h->D_rows + 255) / 256);
+  dpp_inv_norm_kernel<<<blocks, 256, 0, h->stream>>>((const float*)h->D, h->D_rows, (int)h->D_dim, (double*)h->D_inv.p);
+  PRG_CUDA(cudaGetLastError());
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+
 template <int D>
-static size_t dpp_cluster_smem(int top_n) {
-  return (size_t)kClCRows * kClItems * 8 + (size_t)D * kClItems * 4 + 2 * kClCtas * sizeof(CandRecT<D>) + 136 * 8 +
-         2 * kClItems * 8 + kClItems * 8 + 8 * 8 + 8 * 4 + kClMaxItems * 4 + (size_t)((top_n + 3) & ~3) * 4 + kClMaxItems + 64;
+static size_t dpp_cluster_smem(int top_n, int c_rows) {
+  using Cfg = ClCfg<D>;
+  size_t live = (size_t)c_rows * kClItems * 8 + (size_t)Cfg::kFDoubles * 8 + (2 * kClCtas + 2) * sizeof(CandRecT<D>) + 16 +
+                2 * kClItems * 8 + 16 * 8 + 16 * 4 + kClItems * 4 + kClMaxItems * 4 +
+                (size_t)((top_n + 3) & ~3) * 4 + kClMaxItems + 64;
+  const size_t presort_staging = (size_t)kClMaxN * 12;
+  return live > presort_staging ? live : presort_staging;
 }
 
 template <int D>
 static int launch_cluster(prg_handle* h, const DppClArgs& a, int B) {
-  const size_t smem = dpp_cluster_smem<D>(a.p.top_n);
+  const int window = a.p.window_size > 0 ? a.p.window_size : 10;
+  const size_t smem = dpp_cluster_smem<D>(a.p.top_n, a.p.top_n <= window ? a.p.top_n : window);
   PRG_CUDA(cudaFuncSetAttribute(dpp_cluster_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(B * kClCtas));
@@ -483,7 +698,7 @@ int dpp_cluster_device(prg_handle* h, const uint32_t* rows_dev, const double* sc
   const int c_rows = p.top_n <= window ? p.top_n : window;
   if (c_rows > kClCRows) return PRG_OK;
   DppClArgs a{};
-  a.rows = rows_dev; a.score = score_dev; a.n = n; a.D = (const float*)h->D; a.D_rows = h->D_rows; a.p = p;
+  a.rows = rows_dev; a.score = score_dev; a.n = n; a.D = (const float*)h->D; a.D_inv = (const double*)h->D_inv.p; a.D_rows = h->D_rows; a.p = p;
   a.out_idx = out_idx; a.out_n = out_n; a.status = status;
   StageScope span(h, ST_DPP);
   int rc = PRG_OK;
@@ -493,5 +708,13 @@ int dpp_cluster_device(prg_handle* h, const uint32_t* rows_dev, const double* sc
   if (rc == PRG_OK) *handled = true;
   return rc;
 }
+
+#ifdef PRG_DPP_PROFILE
+extern "C" void prg_debug_dpp_clocks(long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_dpp_clk, sizeof(long long) * 16);
+  if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(g_dpp_clk, z, sizeof(z)); }
+}
+#endif
 
 }  // namespace prg

@@ -110,6 +110,7 @@ struct prg_handle {
   const void* D = nullptr;
   bool D_owned = false;
   uint64_t D_rows = 0;
+  prg::DevBuf D_inv;        // D_rows f64: 1 / ||row|| (gonum floats.Norm order) of an f32 diversity table, built once at set time
   uint32_t D_dim = 0;
   int D_dtype = PRG_F32;
   bool dpp_generic = false;  // config "dpp_generic": force the one-CTA-per-request kernel (A/B measurements)

@@ -15,6 +15,8 @@ int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32
 int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
                int32_t* out_idx, int32_t* out_n, int32_t* status);
 
+// dpp_cluster.cu
+int dpp_cluster_prepare(prg_handle* h);
 // ssd.cu
 int ssd_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_ssd_params& p,
                int32_t* out_idx, int32_t* out_n, int32_t* status);
@@ -232,6 +234,7 @@ int prg_set_diversity_matrix(prg_handle* h, const void* data, uint64_t rows, uin
   h->D_rows = rows;
   h->D_dim = dim;
   h->D_dtype = dtype;
+  PRG_TRY(dpp_cluster_prepare(h));
   return PRG_OK;
 }
 

@@ -204,3 +204,36 @@ def test_ssd_edge_cases(oracle_lib):
     e2 = np.eye(4)[[0, 0, 1, 2]] + 1e-3 * rng.standard_normal((4, 4))
     idx2, _ = oracle_lib.ssd_request(e2, np.array([0.9, 0.8, 0.1, 0.1]), 3, gamma=10.0, window_size=5)
     assert idx2[0] == 0 and 1 not in idx2.tolist()[:3]          # the near-duplicate of item 0 is not picked
+
+
+def test_reciprocal_division_is_correctly_rounded_for_f32_operands():
+    """dpp_cluster.cu phase 2a replaces av/scale (both f32 values widened to f64) by q0 = av*y, rem = fma(-q0, scale, av),
+    q = fma(rem, y, q0) with y = RN(1/scale).  Check against exact rational arithmetic that q == RN(av/scale)."""
+    import random
+    import struct
+    from fractions import Fraction
+
+    def fma(x, y, z):
+        return float(Fraction(x) * Fraction(y) + Fraction(z))
+
+    def f32(x):
+        return struct.unpack("f", struct.pack("f", x))[0]
+
+    rng = random.Random(7)
+    cases = []
+    for i in range(20000):
+        if i % 3 == 0:
+            a = float(rng.getrandbits(23) | (1 << 23))
+            b = float(rng.getrandbits(23) | (1 << 23)) * 2.0 ** rng.randint(0, 3)
+        else:
+            a = f32(abs(rng.gauss(0, 1)) * 10 ** rng.uniform(-6, 6))
+            b = f32(abs(rng.gauss(0, 1)) * 10 ** rng.uniform(-6, 6))
+        if a == 0 or b == 0:
+            continue
+        cases.append((min(a, b), max(a, b)))
+    cases += [(1.0, 1.0), (f32(1e-45), f32(3e38)), (f32(1.17549435e-38), f32(3.4028235e38)), (3.0, 3.0), (1.0, 3.0)]
+    for a, b in cases:
+        y = float(Fraction(1) / Fraction(b))
+        q0 = a * y
+        q = fma(fma(-q0, b, a), y, q0)
+        assert q == float(Fraction(a) / Fraction(b)), (a, b)
