@@ -17,23 +17,38 @@
 // allocator + the single MMA-issuing thread (M=128, N=64, K=8; two 128-row halves per stage, accumulators double
 // buffered in 256 TMEM columns), warps 2-9 = epilogue (tcgen05.ld 32x32b.x32 -> 64 FFMA + 64 FSETP per row).
 // Survivor rows go to the per-CTA, per-query segments with one shared-memory atomic + one store.
+//
+// BF16 filter index (default): the same filter over a bf16 SHADOW of the item matrix (round-to-nearest copy built once
+// when the matrix is set, next to the row norms): the full pass then streams rows*dim*2 bytes instead of rows*dim*4
+// (kind::f16 MMA, one 128-B swizzle row per 64 dims).  The bound grows to c = 1.05 * 2^-8: |bf16(x)-x| <= 2^-9 |x|
+// for both operands, so |approx - exact| <= (2^-8 + 2^-18) * sum|x_d||q_d| <= ... * ||x|| * ||q||; products of two
+// bf16 are exact in fp32, the 5 % slack covers the fp32 accumulation of either side, and both norm bounds carry a
+// +1e-30 absolute term for subnormal elements.  The fp32 matrix stays the authority: survivors are re-scored from
+// it, so every emitted row and score is still bit-identical to the oracle.  Config "scan_filter":"tf32" selects the
+// fp32-operand filter above.
 #include "recall.h"
+#include <cuda_bf16.h>
 
 namespace prg {
 
 constexpr int kTcThreads = 320;
 constexpr int kTcEpiWarps = 8;
 constexpr int kTcStages = 3;
-constexpr float kTcMargin = 1.05f / 512.f;  // c = 1.05 * 2^-9
+constexpr float kTcMarginTf32 = 1.05f / 512.f;  // c = 1.05 * 2^-9
+constexpr float kTcMarginBf16 = 1.05f / 256.f;  // c = 1.05 * 2^-8
 
 // NQB = query blocks (of 64) handled per pass over the matrix: the tile is read from HBM once and multiplied against
 // every block (the shard of a G-GPU run sees 64*G queries per step: one pass instead of G).
-template <int NQB>
-constexpr int tc_stages() { return NQB <= 2 ? 3 : 2; }
-template <int DIM, int NQB>
+// A stage is 256 rows x 64 dims of fp32 (64 KiB, two 32-float TMA boxes) for the tf32 filter and 256 rows x DIM of
+// bf16 (DIM/64 boxes of 32 KiB) for the bf16 filter.
+template <int DIM, bool BF>
+constexpr int tc_stage_bytes() { return BF ? kTileRows * DIM * 2 : kStageBytes; }
+template <int DIM, int NQB, bool BF>
+constexpr int tc_stages() { return BF ? (DIM == 64 ? (NQB <= 2 ? 5 : 4) : 3) : (NQB <= 2 ? 3 : 2); }
+template <int DIM, int NQB, bool BF>
 constexpr size_t scan_tc_smem_bytes() {
-  return (size_t)tc_stages<NQB>() * kStageBytes + (size_t)NQB * DIM * kQB * 4 /*Q operands*/ +
-         (size_t)NQB * 3 * kQB * 4 /*tauf, qn, s_cnt*/ + (2 * tc_stages<NQB>() + 4) * 8 + 16;
+  return (size_t)tc_stages<DIM, NQB, BF>() * tc_stage_bytes<DIM, BF>() + (size_t)NQB * DIM * kQB * (BF ? 2 : 4) /*Q operands*/ +
+         (size_t)NQB * 3 * kQB * 4 /*tauf, qn, s_cnt*/ + (2 * tc_stages<DIM, NQB, BF>() + 4) * 8 + 16;
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
