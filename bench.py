@@ -285,7 +285,7 @@ def main():
                           f"fp64 arithmetic)",
               "batch_per_gpu": w["batch"], "global_batch": w["batch"] * world,
               "sharding": "item matrix row-sharded, one all-gather of per-shard top-k keys" if world > 1 else "none",
-              "l2": "inputs larger than L2 (2.56 GB item matrix streamed per step)"}
+              "l2": "inputs larger than L2 (item matrix / its 1.28 GB bf16 filter index streamed per step)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -448,13 +448,23 @@ def main():
     scan = stage["scan"]
     scan_ms = scan["ms"] / max(1, scan["spans"])
     rows_local = T["E"].shape[0]
-    alg_bytes = rows_local * w["dim"] * 4 + min(Bg, 64) * w["dim"] * 4   # per scan launch (<= 64 queries per pass)
+    # the full-matrix pass: tensor-core filter over the bf16 shadow index (default), the fp32 rows (scan_tf32) or the
+    # exact FFMA2 scan (scan_ffma2); algorithmic bytes per launch = the operand the pass must stream + the row norms
+    cfg_env = json.loads(os.environ.get("PRG_CFG", "{}"))
+    filt = "ffma2" if cfg_env.get("scan_ffma2") else ("tf32" if cfg_env.get("scan_tf32") else "bf16")
+    q_pass = min(Bg, 256 if filt != "ffma2" else 64)
+    elem = 2 if filt == "bf16" else 4
+    alg_bytes = rows_local * w["dim"] * elem + (rows_local * 4 if filt != "ffma2" else 0) + q_pass * w["dim"] * 4
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    kernel = {"bf16": f"recall_scan_tc_kernel<{w['dim']},NQB,bf16 shadow index>",
+              "tf32": f"recall_scan_tc_kernel<{w['dim']},NQB,tf32 on fp32 rows>",
+              "ffma2": f"recall_scan_kernel<{w['dim']},THRESH>"}[filt]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch") if tj.get("filter", "tf32") == filt else None
         except Exception:
             traffic = None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -463,13 +473,14 @@ def main():
             "vs_baseline": None, "dtype": "f32 (recall, FM), bf16x2/bf16->f32 (MLP), f64 (sort, DPP)",
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
             "stage_ms_per_step": {s: stage_all[s]["ms"] / 20 for s in stage_all},
-            "roofline": {"kernel": "recall_scan_kernel<64,THRESH>", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": kernel, "bound": "hbm", "achieved": achieved,
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                          "peak_source": f"MEASURED_PEAKS.json ({pk_kind})", "launch_ms": scan_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "fp32_tflops": 2.0 * rows_local * w["dim"] * 64 / (scan_ms * 1e-3) / 1e12 if scan_ms > 0 else 0.0,
-                         "note": "at 64 queries per pass the scan is FP32-issue bound (FFMA2 peak measured 68.4 TFLOP/s), "
-                                 "not HBM bound; see DESIGN.md"},
+                         "algorithmic_bytes_per_launch": alg_bytes, "queries_per_pass": q_pass,
+                         "fp32_matrix_bytes_per_ms": rows_local * w["dim"] * 4 / scan_ms if scan_ms > 0 else 0.0,
+                         "note": "algorithmic bytes = what this pass must stream: rows*dim*2 (bf16 filter index) or "
+                                 "rows*dim*4 (tf32 / ffma2 over the fp32 rows) + rows*4 row norms + queries; the fp32 "
+                                 "matrix is only touched for the ~5 k survivors per query (exact re-score); see DESIGN.md 3.1"},
             "e2e": e2e}
     if not args.no_cpu_baseline and world == 1:
         try:

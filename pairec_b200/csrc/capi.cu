@@ -137,6 +137,7 @@ int prg_init(const char* json_cfg, prg_handle** out) {
   if (json_int(json_cfg, "max_k", &v) && v > 0) h->max_k = (int)v;
   if (json_int(json_cfg, "sm_limit", &v) && v > 0 && v < h->sm_count) h->sm_count = (int)v;
   if (json_int(json_cfg, "scan_ffma2", &v) && v != 0) h->scan_ffma2 = true;
+  if (json_int(json_cfg, "scan_tf32", &v) && v != 0) h->scan_filter = SCAN_FILTER_TF32;
   if (json_int(json_cfg, "dpp_generic", &v) && v != 0) h->dpp_generic = true;
   if (json_int(json_cfg, "mlp_one_tile", &v) && v != 0) h->mlp_one_tile_per_cta = true;
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -162,7 +163,7 @@ void prg_destroy(prg_handle* h) {
         if (h->tables[t].linear) cudaFree(const_cast<float*>(h->tables[t].linear));
       }
     }
-    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->row_norm, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
+    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->row_norm, &h->E16, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
                       &h->out_row, &h->out_score, &h->out_n, &h->flags, &h->table_ptrs, &h->act[0], &h->act[1],
                       &h->fm_logit, &h->rank_rows, &h->rank_out, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
                       &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->ssd_E, &h->ssd_P, &h->sort_in, &h->sort_perm, &h->rec_rows,
@@ -237,7 +238,8 @@ int prg_set_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_
   h->E_rows = rows;
   h->E_dim = dim;
   h->E_row_base = row_base;
-  h->row_norm.release();  // rebuilt lazily for the new matrix
+  h->row_norm.release();  // norms and the bf16 filter index are rebuilt lazily for the new matrix
+  h->E16_map_ok = false;
   return recall_build_map(h);
 }
 

@@ -57,6 +57,10 @@ struct prg_handle {
   prg::DevBuf seg_rows;     // QB x n_seg x seg_cap u32 survivor rows of the tensor-core filter
   prg::DevBuf row_norm;     // rows f32: upper bounds of the item row norms (tensor-core filter margin)
   bool scan_ffma2 = false;  // config "scan_ffma2": use the exact FFMA2 scan for the full pass as well
+  int scan_filter = 0;      // config "scan_filter": 0 = bf16 shadow index (default), 1 = tf32 on the fp32 rows
+  prg::DevBuf E16;          // rows x dim bf16: round-to-nearest shadow of the item matrix (bf16 filter operand)
+  CUtensorMap E16_map;
+  bool E16_map_ok = false;
   prg::DevBuf cand_cnt;     // B u32
   prg::DevBuf tau;          // B u64
   prg::DevBuf dense_keys;   // fallback / small-N: nq x slots u64
@@ -129,6 +133,7 @@ namespace prg {
 // launch bookkeeping
 inline void count_launch(prg_handle* h, int n = 1) { h->launches += (uint64_t)n; }
 
+enum { SCAN_FILTER_BF16 = 0, SCAN_FILTER_TF32 = 1 };
 enum Stage { ST_SCAN = 0, ST_SCAN_DENSE = 1, ST_SELECT = 2, ST_GATHER_FM = 3, ST_MLP = 4, ST_SORT = 5, ST_DPP = 6, ST_OTHER = 7 };
 // RAII span: records an event before and after the enclosed launches when timing is on
 struct StageScope {

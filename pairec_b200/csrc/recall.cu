@@ -479,47 +479,58 @@ __global__ void __launch_bounds__(1024, 1) select_kth_kernel(const SelectParams 
 
 // Exact re-score of the tensor-core survivors: one block per (segment, query); every candidate row gets the fmaf chain
 // of the arithmetic contract (dims ascending, one accumulator) — the approximate score never reaches an output.
+// DIM is a template parameter so that the DIM/4 row loads of a candidate are all in flight before the (serial) fmaf
+// chain starts: with a runtime trip count every 16-B load sat in front of its four FMAs (ncu: 82 long-scoreboard
+// stalls per issue, 55 us for ~290 k rows).
+template <int DIM>
 __global__ void __launch_bounds__(64) rescore_kernel(const uint32_t* __restrict__ seg_rows, const uint32_t* __restrict__ seg_cnt,
                                                      uint32_t seg_cap, const float* __restrict__ E, const float* __restrict__ Q,
-                                                     uint32_t dim, uint64_t row_base, uint64_t* __restrict__ seg_keys) {
-  __shared__ float qv[128];
+                                                     uint64_t row_base, uint64_t* __restrict__ seg_keys) {
+  __shared__ float qv[DIM];
   const uint32_t sgi = blockIdx.x, q = blockIdx.y, n_seg = gridDim.x;
   uint32_t c = seg_cnt[(size_t)q * n_seg + sgi];
   if (c == 0) return;
   if (c > seg_cap) c = seg_cap;
-  for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) qv[d] = Q[(size_t)q * dim + d];
-  __syncthreads();
   const uint32_t* src = seg_rows + ((size_t)q * n_seg + sgi) * seg_cap;
+  uint32_t grow = threadIdx.x < c ? src[threadIdx.x] : 0u;   // issued together with the query load
+  for (uint32_t d = threadIdx.x; d < DIM; d += blockDim.x) qv[d] = Q[(size_t)q * DIM + d];
+  __syncthreads();
   uint64_t* dst = seg_keys + ((size_t)q * n_seg + sgi) * seg_cap;
   for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
-    const uint32_t grow = src[i];
-    const float4* x = reinterpret_cast<const float4*>(E + ((size_t)grow - row_base) * dim);
+    if (i != threadIdx.x) grow = src[i];
+    const float4* x = reinterpret_cast<const float4*>(E + ((size_t)grow - row_base) * DIM);
+    float4 xv[DIM / 4];
+#pragma unroll
+    for (int d4 = 0; d4 < DIM / 4; ++d4) xv[d4] = __ldg(x + d4);
     float acc = 0.f;
-    for (uint32_t d4 = 0; d4 < dim / 4; ++d4) {
-      const float4 xv = x[d4];
-      acc = __fmaf_rn(xv.x, qv[4 * d4], acc);
-      acc = __fmaf_rn(xv.y, qv[4 * d4 + 1], acc);
-      acc = __fmaf_rn(xv.z, qv[4 * d4 + 2], acc);
-      acc = __fmaf_rn(xv.w, qv[4 * d4 + 3], acc);
+#pragma unroll
+    for (int d4 = 0; d4 < DIM / 4; ++d4) {
+      acc = __fmaf_rn(xv[d4].x, qv[4 * d4], acc);
+      acc = __fmaf_rn(xv[d4].y, qv[4 * d4 + 1], acc);
+      acc = __fmaf_rn(xv[d4].z, qv[4 * d4 + 2], acc);
+      acc = __fmaf_rn(xv[d4].w, qv[4 * d4 + 3], acc);
     }
     dst[i] = make_key(acc, grow);
   }
 }
 
-// keys -> rows / scores / counts (used by the shard-merge path where keys already are sorted)
+// keys -> rows / scores / counts (used by the shard-merge path where keys already are sorted): one warp per 32 keys,
+// the per-request count is a ballot + one atomic per warp (out_n is zeroed by the launcher)
 __global__ void keys_unpack_kernel(const uint64_t* keys, int total, int k, uint32_t* out_row, float* out_score,
-                                   int32_t* out_n, int B) {
+                                   int32_t* out_n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) {
-    const uint64_t key = keys[i];
+  const bool in = i < total;
+  const uint64_t key = in ? keys[i] : 0ull;
+  if (in) {
     out_row[i] = key ? key_row(key) : 0xFFFFFFFFu;
     out_score[i] = key ? key_score(key) : __int_as_float(0xFF800000);
   }
-  if (i < B) {
-    int n = 0;
-    for (int j = 0; j < k; ++j) n += (keys[(size_t)i * k + j] != 0ull);
-    out_n[i] = n;
-  }
+  // lanes of a warp may straddle requests (k is not a multiple of 32 in general): group the lanes by request
+  const int b = in ? i / k : -1;
+  const unsigned same = __match_any_sync(0xffffffffu, b);
+  const unsigned nz = __ballot_sync(0xffffffffu, key != 0ull);
+  const int lane = threadIdx.x & 31;
+  if (in && lane == __ffs(same) - 1 && (same & nz)) atomicAdd(&out_n[b], __popc(same & nz));
 }
 
 // ------------------------------------------------------------------ host side
@@ -676,9 +687,14 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   }
   if (use_tc) {  // exact re-score of the tensor-core survivors, all queries at once
     StageScope span(h, ST_SELECT);
-    rescore_kernel<<<dim3(n_seg, (unsigned)B), 64, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
-                                                                   (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, q_dev, dim,
-                                                                   h->E_row_base, (uint64_t*)h->seg_keys.p);
+    if (dim == 64)
+      rescore_kernel<64><<<dim3(n_seg, (unsigned)B), 64, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
+                                                                         (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, q_dev,
+                                                                         h->E_row_base, (uint64_t*)h->seg_keys.p);
+    else
+      rescore_kernel<128><<<dim3(n_seg, (unsigned)B), 64, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
+                                                                          (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, q_dev,
+                                                                          h->E_row_base, (uint64_t*)h->seg_keys.p);
     PRG_CUDA(cudaGetLastError());
     count_launch(h);
   }
@@ -735,8 +751,8 @@ int recall_resolve(prg_handle* h, bool* repaired) {
 int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint32_t* out_row, float* out_score,
                     int32_t* out_n) {
   const int total = B * k;
-  const int n = total > B ? total : B;
-  keys_unpack_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(keys_dev, total, k, out_row, out_score, out_n, B);
+  PRG_CUDA(cudaMemsetAsync(out_n, 0, (size_t)B * 4, h->stream));
+  keys_unpack_kernel<<<(total + 255) / 256, 256, 0, h->stream>>>(keys_dev, total, k, out_row, out_score, out_n);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;

@@ -24,16 +24,16 @@
 // for both operands, so |approx - exact| <= (2^-8 + 2^-18) * sum|x_d||q_d| <= ... * ||x|| * ||q||; products of two
 // bf16 are exact in fp32, the 5 % slack covers the fp32 accumulation of either side, and both norm bounds carry a
 // +1e-30 absolute term for subnormal elements.  The fp32 matrix stays the authority: survivors are re-scored from
-// it, so every emitted row and score is still bit-identical to the oracle.  Config "scan_filter":"tf32" selects the
+// it, so every emitted row and score is still bit-identical to the oracle.  Config "scan_tf32":1 selects the
 // fp32-operand filter above.
 #include "recall.h"
 #include <cuda_bf16.h>
+#include <type_traits>
 
 namespace prg {
 
 constexpr int kTcThreads = 320;
 constexpr int kTcEpiWarps = 8;
-constexpr int kTcStages = 3;
 constexpr float kTcMarginTf32 = 1.05f / 512.f;  // c = 1.05 * 2^-9
 constexpr float kTcMarginBf16 = 1.05f / 256.f;  // c = 1.05 * 2^-8
 
@@ -62,18 +62,32 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
-template <int DIM, int NQB>
+// Epilogue survivor test, shared by both operand types: keep row r for query q unless approx < tau_f[q] - nr * c||q||.
+// The 64 queries of a block are tested in four groups of 16 and only a group with a survivor is walked again to append
+// rows: ~5 k survivors per query and 10 M rows make a survivor a 3 % event per row but a 60 % event per WARP and tile,
+// and walking all 64 queries for each of those was half of the epilogue's instructions.
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // SASS FMNMX3; NaN operands are ignored
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+template <int DIM, int NQB, bool BF>
 __global__ void __launch_bounds__(kTcThreads, 1)
 recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int KH = DIM / 64;
-  constexpr int kTcStages = tc_stages<NQB>();
+  constexpr int KH = BF ? 1 : DIM / 64;                    // stages per tile
+  constexpr int kTcStages = tc_stages<DIM, NQB, BF>();
+  constexpr int kStageB = tc_stage_bytes<DIM, BF>();
+  constexpr int kQBytes = DIM * kQB * (BF ? 2 : 4);        // one query block as a B operand
   constexpr int NBUF = NQB <= 2 ? 2 : 1;                   // accumulator buffers (128 TMEM columns per block and buffer)
   constexpr uint32_t kTmemCols = NQB == 1 ? 256 : 512;
   constexpr int QTOT = NQB * kQB;
-  float* stage_base = reinterpret_cast<float*>(smem);
-  float* Qb = reinterpret_cast<float*>(smem + (size_t)kTcStages * kStageBytes);  // B operands: [NQB][DIM/32][64 q][32] swizzled
-  float2* tq = reinterpret_cast<float2*>(Qb + (size_t)NQB * DIM * kQB);         // [NQB*64] {tau_f, c*||q||}
+  constexpr float kMargin = BF ? kTcMarginBf16 : kTcMarginTf32;
+  uint8_t* stage_base = smem;
+  uint8_t* Qb = smem + (size_t)kTcStages * kStageB;  // B operands, K-major SWIZZLE_128B: tf32 [NQB][DIM/32][64 q][32 f32],
+                                                     // bf16 [NQB][DIM/64][64 q][64 bf16]
+  float2* tq = reinterpret_cast<float2*>(Qb + (size_t)NQB * kQBytes);           // [NQB*64] {tau_f, c*||q||}
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tq + QTOT);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + QTOT);
   uint64_t* empty = full + kTcStages;
@@ -83,22 +97,53 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // query blocks -> K-major SWIZZLE_128B B operands; padded queries are zero rows
+  // Uniform threshold: when every query of the pass has a positive, well-scaled threshold the B operand is staged as
+  // q / tau_q, so "exact >= tau_q" becomes "exact' >= 1" for every query and the survivor test needs ONE per-row
+  // scalar, t_r = (1 - 1e-6) - ||x_r|| * max_q(c ||q'_q||): the epilogue is then a running maximum (FMNMX3) over the
+  // accumulators plus one compare per 16 queries instead of an FFMA + FSETP per accumulator (the bf16 pass was
+  // epilogue-bound at 0.40 ms with the per-query form).  The 1e-6 covers fl(1/tau)*tau != 1; taking the largest
+  // c||q'|| for all queries only lets a few more rows through.  Otherwise (a threshold <= 0, none, or extreme) the
+  // per-query form below is used for the whole pass.
+  __shared__ float s_scale[NQB * kQB];
+  __shared__ uint32_t s_cmax;
+  if (tid == 0) s_cmax = 0u;
+  int bad = 0;
+  for (int q = tid; q < QTOT; q += kTcThreads) {
+    float sc = 0.f;
+    if (q < p.nq) {
+      const uint64_t t = p.tau[q];
+      const float tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
+      if (tf > 0x1p-60f && tf < 0x1p60f) sc = 1.0f / tf; else bad = 1;
+    }
+    s_scale[q] = sc;
+  }
+  const bool scaled = __syncthreads_or(bad) == 0;
+
+  // query blocks -> K-major SWIZZLE_128B B operands (16-B chunk index XOR row-in-group); padded queries are zero rows
   for (int i = tid; i < DIM * QTOT; i += kTcThreads) {
     const int q = i / DIM, dd = i - q * DIM;
-    const float v = (q < p.nq) ? p.Q[(size_t)q * DIM + dd] : 0.f;
+    float v = (q < p.nq) ? p.Q[(size_t)q * DIM + dd] : 0.f;
+    if (scaled) v *= s_scale[q];
     const int blk = q >> 6, ql = q & 63;
-    const int sub = dd >> 5, ch = (dd & 31) >> 2;
-    Qb[(size_t)blk * DIM * kQB + sub * (kQB * 32) + ql * 32 + ((ch ^ (ql & 7)) << 2) + (dd & 3)] = v;
+    if constexpr (BF) {
+      const int sub = dd >> 6, e = dd & 63, ch = e >> 3;
+      reinterpret_cast<__nv_bfloat16*>(Qb)[(size_t)blk * DIM * kQB + sub * (kQB * 64) + ql * 64 + ((ch ^ (ql & 7)) << 3) + (e & 7)] =
+          __float2bfloat16_rn(v);
+    } else {
+      const int sub = dd >> 5, ch = (dd & 31) >> 2;
+      reinterpret_cast<float*>(Qb)[(size_t)blk * DIM * kQB + sub * (kQB * 32) + ql * 32 + ((ch ^ (ql & 7)) << 2) + (dd & 3)] = v;
+    }
   }
   for (int q = tid; q < QTOT; q += kTcThreads) {
     float tf = __int_as_float(0x7F800000), nq2 = 0.f;
     if (q < p.nq) {
       const uint64_t t = p.tau[q];
       tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
+      const float sc = scaled ? s_scale[q] : 1.0f;
       float ss = 0.f;
-      for (int dd = 0; dd < DIM; ++dd) { const float v = p.Q[(size_t)q * DIM + dd]; ss = fmaf(v, v, ss); }
-      nq2 = sqrtf(ss) * 1.0001f * kTcMargin;
+      for (int dd = 0; dd < DIM; ++dd) { const float v = p.Q[(size_t)q * DIM + dd] * sc; ss = fmaf(v, v, ss); }
+      nq2 = (sqrtf(ss) * 1.0001f + 1e-30f) * kMargin;
+      if (scaled) atomicMax(&s_cmax, __float_as_uint(nq2));  // non-negative floats order like their bit patterns
     }
     tq[q] = make_float2(tf, nq2);
     s_cnt[q] = 0;
@@ -132,18 +177,26 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
         for (int h = 0; h < KH; ++h, ++it) {
           const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], kStageBytes);
-          float* dst = stage_base + (size_t)s * kStageFloats;
-          tma_load_2d(dst, &emap, h * 64, row0, &full[s], kEvictFirst);
-          tma_load_2d(dst + kSubTileFloats, &emap, h * 64 + 32, row0, &full[s], kEvictFirst);
+          mbar_arrive_expect_tx(&full[s], kStageB);
+          uint8_t* dst = stage_base + (size_t)s * kStageB;
+          if constexpr (BF) {
+#pragma unroll
+            for (int sub = 0; sub < DIM / 64; ++sub)   // one box = 256 rows x 64 bf16 (128 B)
+              tma_load_2d(dst + sub * (kTileRows * 128), &emap, sub * 64, row0, &full[s], kEvictFirst);
+          } else {
+            tma_load_2d(dst, &emap, h * 64, row0, &full[s], kEvictFirst);
+            tma_load_2d(dst + kSubTileFloats * 4, &emap, h * 64 + 32, row0, &full[s], kEvictFirst);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      // D=f32, A=B=tf32, both K-major, N=64, M=128
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kQB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // D=f32, A=B=tf32 (format 2) or bf16 (format 1), both K-major, N=64, M=128
+      constexpr uint32_t fmt = BF ? 1u : 2u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kQB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr int kSubs = BF ? DIM / 64 : 2;           // 128-B-wide sub-tiles per stage
       const uint32_t qb_addr = smem_u32(Qb);
       uint32_t it = 0;
       for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -155,20 +208,25 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
           const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t st_addr = smem_u32(stage_base + (size_t)s * kStageFloats);
+          const uint32_t st_addr = smem_u32(stage_base + (size_t)s * kStageB);
 #pragma unroll
           for (int blk = 0; blk < NQB; ++blk) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               const uint32_t d_addr = tmem_base + (buf * (uint32_t)NQB + (uint32_t)blk) * 128u + (uint32_t)half * 64u;
 #pragma unroll
-              for (int sub = 0; sub < 2; ++sub) {
-                const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kSubTileFloats * 4) + (uint32_t)half * (128 * 128));
-                const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)blk * (DIM * kQB * 4) + (uint32_t)(h * 2 + sub) * (kQB * 128));
+              for (int sub = 0; sub < kSubs; ++sub) {
+                // a sub-tile is 256 rows of 128 B; rows [128*half, +128) start 16 KiB in; the matching slice of the
+                // query block is 64 rows of 128 B (8 KiB)
+                const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kTileRows * 128) + (uint32_t)half * (128 * 128));
+                const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)blk * kQBytes + (uint32_t)(h * kSubs + sub) * (kQB * 128));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 B -> +2 in 16-B units
-                  umma_tf32(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                            (h | sub | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {  // UMMA_K = 32 B (8 tf32 / 16 bf16) -> +2 in 16-B units
+                  if constexpr (BF)
+                    umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (sub | k) != 0 ? 1u : 0u);
+                  else
+                    umma_tf32(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (h | sub | k) != 0 ? 1u : 0u);
+                }
               }
             }
           }
@@ -188,6 +246,12 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       return (uint64_t)(blockIdx.x + i * gridDim.x) * p.tile_stride * kTileRows + (uint64_t)row_local;
     };
     float nr_next = (my_tiles > 0 && tile_row(0) < p.n_rows) ? p.row_norm[tile_row(0)] : 0.f;
+    const uint32_t seg_stride = gridDim.x * p.seg_cap, seg_base = blockIdx.x * p.seg_cap;
+    const float cmax = __uint_as_float(s_cmax);
+    // the tile loop is instantiated once per threshold form (the choice is uniform for the launch), so that neither
+    // form pays registers for the other
+    auto run = [&](auto scaled_tag) {
+    constexpr bool kScaled = decltype(scaled_tag)::value;
     for (uint32_t i = 0; i < my_tiles; ++i) {
       const uint32_t buf = (NBUF == 2) ? (i & 1u) : 0u;
       const uint32_t use = (NBUF == 2) ? (i >> 1) : i;
@@ -196,7 +260,6 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       const float nr = nr_next;
       nr_next = (i + 1 < my_tiles && tile_row(i + 1) < p.n_rows) ? p.row_norm[tile_row(i + 1)] : 0.f;
       const uint32_t grow = (uint32_t)(p.row_base + lrow);
-      const uint32_t seg_stride = gridDim.x * p.seg_cap, seg_base = blockIdx.x * p.seg_cap;
       mbar_wait(&tfull[buf], use & 1u);
       tc_fence_after();
 #pragma unroll 1
@@ -211,45 +274,76 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[buf]);
         }
-        // thr_q = tau_f[q] - ||x_row|| * c*||q||; {tau_f, c||q||} pairs are re-read from shared memory per tile (the
-        // mbarrier wait above is a compiler memory barrier, so nothing is hoisted into 128 live registers)
-        const float2* tqb = tq + blk * kQB;
-        const float4* tq4 = reinterpret_cast<const float4*>(tqb);
         const int nqb = p.nq - blk * kQB;  // queries of this block (may exceed 64; <= 0 for an unused block)
-        bool any0 = false, any1 = false;
+        uint32_t* scb = s_cnt + blk * kQB;
+        const uint32_t qoff = (uint32_t)(blk * kQB);
+        if constexpr (kScaled) {
+          // one threshold for the whole row: running maxima over four groups of 16 queries (NaN accumulators are
+          // ignored by max; a row whose norm bound is +inf has t_r = -inf or NaN and always survives)
+          const float t_r = fmaf(-nr, cmax, 1.0f - 1e-6f);
+          float m[4];
 #pragma unroll
-        for (int q = 0; q < 32; q += 2) {
-          const float4 a4 = tq4[q >> 1];
-          const float4 b4 = tq4[16 + (q >> 1)];
-          any0 |= !(__uint_as_float(v0[q]) < fmaf(-nr, a4.y, a4.x));
-          any0 |= !(__uint_as_float(v0[q + 1]) < fmaf(-nr, a4.w, a4.z));
-          any1 |= !(__uint_as_float(v1[q]) < fmaf(-nr, b4.y, b4.x));
-          any1 |= !(__uint_as_float(v1[q + 1]) < fmaf(-nr, b4.w, b4.z));
-        }
-        if (valid && (any0 || any1)) {
-          uint32_t* scb = s_cnt + blk * kQB;
-          const uint32_t qoff = (uint32_t)(blk * kQB);
-          if (any0) {
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t* v = g < 2 ? v0 : v1;
+            const int o = (g & 1) * 16;
+            float a = fmax3(__uint_as_float(v[o]), __uint_as_float(v[o + 1]), __uint_as_float(v[o + 2]));
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              if (q < nqb && !(__uint_as_float(v0[q]) < fmaf(-nr, tqb[q].y, tqb[q].x))) {
-                const uint32_t pos = atomicAdd(&scb[q], 1u);
-                if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)q) * seg_stride + seg_base + pos] = grow;
+            for (int j = 3; j < 15; j += 2) a = fmax3(a, __uint_as_float(v[o + j]), __uint_as_float(v[o + j + 1]));
+            m[g] = fmaxf(a, __uint_as_float(v[o + 15]));
+          }
+          const bool any0 = !(m[0] < t_r), any1 = !(m[1] < t_r), any2 = !(m[2] < t_r), any3 = !(m[3] < t_r);
+          if (valid && (any0 || any1 || any2 || any3)) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g == 0 ? any0 : g == 1 ? any1 : g == 2 ? any2 : any3) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int q = g * 16 + j;
+                  const float sc = __uint_as_float(g < 2 ? v0[q & 31] : v1[q & 31]);
+                  if (q < nqb && !(sc < t_r)) {
+                    const uint32_t pos = atomicAdd(&scb[q], 1u);
+                    if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)q) * seg_stride + seg_base + pos] = grow;
+                  }
+                }
               }
             }
           }
-          if (any1) {
+        } else {
+          // thr_q = tau_f[q] - ||x_row|| * c*||q||; {tau_f, c||q||} pairs are re-read from shared memory per tile (the
+          // mbarrier wait above is a compiler memory barrier, so nothing is hoisted into 128 live registers)
+          const float2* tqb = tq + blk * kQB;
+          const float4* tq4 = reinterpret_cast<const float4*>(tqb);
+          bool any[4] = {false, false, false, false};  // queries [0,16) [16,32) [32,48) [48,64)
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              if (q + 32 < nqb && !(__uint_as_float(v1[q]) < fmaf(-nr, tqb[q + 32].y, tqb[q + 32].x))) {
-                const uint32_t pos = atomicAdd(&scb[q + 32], 1u);
-                if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)(q + 32)) * seg_stride + seg_base + pos] = grow;
+          for (int q = 0; q < 32; q += 2) {
+            const float4 a4 = tq4[q >> 1];
+            const float4 b4 = tq4[16 + (q >> 1)];
+            any[q >> 4] |= !(__uint_as_float(v0[q]) < fmaf(-nr, a4.y, a4.x));
+            any[q >> 4] |= !(__uint_as_float(v0[q + 1]) < fmaf(-nr, a4.w, a4.z));
+            any[2 + (q >> 4)] |= !(__uint_as_float(v1[q]) < fmaf(-nr, b4.y, b4.x));
+            any[2 + (q >> 4)] |= !(__uint_as_float(v1[q + 1]) < fmaf(-nr, b4.w, b4.z));
+          }
+          if (valid && (any[0] || any[1] || any[2] || any[3])) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (any[g]) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int q = g * 16 + j;
+                  const float sc = __uint_as_float(g < 2 ? v0[q & 31] : v1[q & 31]);
+                  if (q < nqb && !(sc < fmaf(-nr, tqb[q].y, tqb[q].x))) {
+                    const uint32_t pos = atomicAdd(&scb[q], 1u);
+                    if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)q) * seg_stride + seg_base + pos] = grow;
+                  }
+                }
               }
             }
           }
         }
       }
     }
+    };
+    if (scaled) run(std::true_type{}); else run(std::false_type{});
     asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
     for (int q = tid - 64; q < p.nq; q += kTcEpiWarps * 32) p.seg_cnt[(size_t)q * gridDim.x + blockIdx.x] = s_cnt[q];
   }
@@ -262,8 +356,10 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   }
 }
 
-// upper bounds of the row norms: sqrt in fp64, inflated, rounded up to f32
-__global__ void row_norm_kernel(const float* __restrict__ E, uint64_t rows, int dim, float* __restrict__ out) {
+// upper bounds of the row norms (sqrt in fp64, inflated, rounded up to f32, plus an absolute term that covers subnormal
+// elements) and, for the bf16 filter, the round-to-nearest bf16 shadow of the row
+__global__ void row_norm_kernel(const float* __restrict__ E, uint64_t rows, int dim, float* __restrict__ out,
+                                __nv_bfloat16* __restrict__ shadow) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   const float4* x = reinterpret_cast<const float4*>(E + r * dim);
@@ -271,30 +367,57 @@ __global__ void row_norm_kernel(const float* __restrict__ E, uint64_t rows, int 
   for (int i = 0; i < dim / 4; ++i) {
     const float4 v = x[i];
     ss += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    if (shadow) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(shadow + r * dim)[i] = pk;
+    }
   }
-  float f = (float)(sqrt(ss) * (1.0 + 1e-6));
+  float f = (float)(sqrt(ss) * (1.0 + 1e-6) + 1e-30);
   f = (f == f && f < __int_as_float(0x7F800000)) ? __uint_as_float(__float_as_uint(f) + 1u) : __int_as_float(0x7F800000);
   out[r] = f;  // NaN / inf rows get +inf: they always survive the filter and are settled by the exact re-score
 }
 
+// Built lazily by the first recall after prg_set_item_matrix (which releases row_norm): norms, and the bf16 shadow +
+// its tensor map unless the tf32 filter is configured.
 int build_row_norms(prg_handle* h) {
+  const bool bf = h->scan_filter == SCAN_FILTER_BF16;
+  h->E16_map_ok = false;
+  if (bf) PRG_TRY(h->E16.ensure((size_t)h->E_rows * h->E_dim * 2));
   PRG_TRY(h->row_norm.ensure((size_t)h->E_rows * 4));
   const unsigned grid = (unsigned)((h->E_rows + 255) / 256);
-  row_norm_kernel<<<grid, 256, 0, h->stream>>>(h->E, h->E_rows, (int)h->E_dim, (float*)h->row_norm.p);
+  row_norm_kernel<<<grid, 256, 0, h->stream>>>(h->E, h->E_rows, (int)h->E_dim, (float*)h->row_norm.p,
+                                               bf ? (__nv_bfloat16*)h->E16.p : nullptr);
   PRG_CUDA(cudaGetLastError());
   PRG_CUDA(cudaStreamSynchronize(h->stream));
   count_launch(h);
+  if (bf) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)h->E_dim, (cuuint64_t)h->E_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)h->E_dim * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)kTileRows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&h->E16_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->E16.p, gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled (bf16 shadow) failed: " + std::to_string((int)r));
+    h->E16_map_ok = true;
+  }
   return PRG_OK;
 }
 
-template <int DIM, int NQB>
+template <int DIM, int NQB, bool BF>
 static int launch_tc(prg_handle* h, const ScanParams& p) {
-  const size_t smem = scan_tc_smem_bytes<DIM, NQB>();
-  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM, NQB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = scan_tc_smem_bytes<DIM, NQB, BF>();
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM, NQB, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (p.n_tiles == 0) return PRG_OK;
+  if (BF && !h->E16_map_ok) return fail(PRG_ESTATE, "bf16 filter index not built");
   StageScope span(h, ST_SCAN);
   const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
-  recall_scan_tc_kernel<DIM, NQB><<<grid, kTcThreads, smem, h->stream>>>(h->E_map, p);
+  recall_scan_tc_kernel<DIM, NQB, BF><<<grid, kTcThreads, smem, h->stream>>>(BF ? h->E16_map : h->E_map, p);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;
@@ -303,18 +426,23 @@ static int launch_tc(prg_handle* h, const ScanParams& p) {
 // queries per pass the kernel is built for: 64/128/256 at dim 64, 64 at dim 128 (shared-memory budget)
 int scan_tc_max_queries(const prg_handle* h) { return h->E_dim == 64 ? 256 : 64; }
 
-int launch_scan_tc(prg_handle* h, const ScanParams& p) {
+template <bool BF>
+static int launch_scan_tc_t(prg_handle* h, const ScanParams& p) {
   if (h->E_dim == 64) {
-    if (p.nq <= 64) return launch_tc<64, 1>(h, p);
-    if (p.nq <= 128) return launch_tc<64, 2>(h, p);
-    if (p.nq <= 256) return launch_tc<64, 4>(h, p);
+    if (p.nq <= 64) return launch_tc<64, 1, BF>(h, p);
+    if (p.nq <= 128) return launch_tc<64, 2, BF>(h, p);
+    if (p.nq <= 256) return launch_tc<64, 4, BF>(h, p);
     return fail(PRG_EINVAL, "launch_scan_tc: more than 256 queries per pass");
   }
   if (h->E_dim == 128) {
-    if (p.nq <= 64) return launch_tc<128, 1>(h, p);
+    if (p.nq <= 64) return launch_tc<128, 1, BF>(h, p);
     return fail(PRG_EINVAL, "launch_scan_tc: more than 64 queries per pass at dim 128");
   }
   return fail(PRG_EUNSUPPORTED, "item matrix dim must be 64 or 128");
+}
+
+int launch_scan_tc(prg_handle* h, const ScanParams& p) {
+  return h->scan_filter == SCAN_FILTER_BF16 ? launch_scan_tc_t<true>(h, p) : launch_scan_tc_t<false>(h, p);
 }
 
 }  // namespace prg

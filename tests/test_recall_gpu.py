@@ -119,3 +119,54 @@ def test_many_queries_per_pass(engine, oracle_lib, b):
     E, Q = _data(350_000, 64, b, seed=41 + b)
     _check(engine, oracle_lib, E, Q, 200)
     assert engine.recall_stats()["fallback_queries"] == 0
+
+
+@pytest.mark.parametrize("d,b", [(64, 70), (128, 9)])
+def test_tf32_filter_variant_matches_oracle(oracle_lib, d, b):
+    # config scan_tf32: the tensor-core filter over the fp32 rows themselves (no bf16 shadow index)
+    from pairec_b200 import Engine
+    eng = Engine(0, scan_tf32=1)
+    try:
+        E, Q = _data(400_000, d, b, seed=51)
+        _check(eng, oracle_lib, E, Q, 400)
+        assert eng.recall_stats()["fallback_queries"] == 0
+    finally:
+        eng.close()
+
+
+def test_bf16_filter_worst_case_rounding(engine, oracle_lib):
+    # elements that sit exactly between two bf16 values (largest rounding error of the shadow index), positive rows
+    # and a positive query so that no cancellation hides the error: the margin must still keep every true winner
+    n, d = 400_000, 64
+    rng = np.random.default_rng(61)
+    base = (rng.integers(128, 256, size=(n, d)).astype(np.float32)) / 256.0       # 8 significant bits
+    E = (base * (1.0 + 2.0 ** -8) * (2.0 ** rng.integers(-3, 3, size=(n, 1)))).astype(np.float32)  # half-way cases
+    Q = (rng.integers(128, 256, size=(5, d)).astype(np.float32) / 256.0 * (1.0 + 2.0 ** -8)).astype(np.float32)
+    _check(engine, oracle_lib, E, Q, 1000)
+
+
+def test_subnormal_rows_and_queries(engine, oracle_lib):
+    E, Q = _data(300_000, 64, 3, seed=67)
+    E[::3] *= np.float32(1e-38)          # subnormal / near-subnormal rows
+    Q[1] *= np.float32(1e-30)
+    Q[2] *= np.float32(1e-40)
+    _check(engine, oracle_lib, E, Q, 500)
+
+
+def test_matrix_replaced_rebuilds_filter_index(engine, oracle_lib):
+    E1, Q = _data(300_000, 64, 4, seed=71)
+    _check(engine, oracle_lib, E1, Q, 100)
+    E2, _ = _data(350_000, 64, 4, seed=73)
+    _check(engine, oracle_lib, E2, Q, 100)
+
+
+def test_negative_thresholds_use_the_per_query_filter(engine, oracle_lib):
+    # every score is negative (positive rows, negative queries): the sampled threshold is < 0, so the uniform
+    # (query / tau) form of the filter does not apply and the per-query form must give the same exact result
+    n, d = 400_000, 64
+    rng = np.random.default_rng(83)
+    E = rng.random((n, d), dtype=np.float32) + np.float32(0.1)
+    Q = -(rng.random((6, d), dtype=np.float32) + np.float32(0.1))
+    Q[3] = -Q[3]    # one query with positive scores in the same pass
+    _check(engine, oracle_lib, E, Q, 700)
+    assert engine.recall_stats()["fallback_queries"] == 0
