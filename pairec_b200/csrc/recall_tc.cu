@@ -44,11 +44,17 @@ constexpr float kTcMarginBf16 = 1.05f / 256.f;  // c = 1.05 * 2^-8
 template <int DIM, bool BF>
 constexpr int tc_stage_bytes() { return BF ? kTileRows * DIM * 2 : kStageBytes; }
 template <int DIM, int NQB, bool BF>
-constexpr int tc_stages() { return BF ? (DIM == 64 ? (NQB <= 2 ? 5 : 4) : 3) : (NQB <= 2 ? 3 : 2); }
+constexpr int tc_stages() { return BF ? (DIM == 64 ? (NQB <= 2 ? 5 : 4) : 3) : ((NQB == 1 && DIM == 64) ? 3 : 2); }
+// The row norms of a tile travel with it (one 1 KiB bulk copy completing on the tile's `full` barrier) into a ring of
+// S + 3 slots: the producer may run S tiles ahead of the MMA warp and the MMA warp 2 tiles (accumulator buffers) ahead
+// of the epilogue, which reads the norms.
+template <int DIM, int NQB, bool BF>
+constexpr int tc_norm_ring() { return tc_stages<DIM, NQB, BF>() + 3; }
 template <int DIM, int NQB, bool BF>
 constexpr size_t scan_tc_smem_bytes() {
   return (size_t)tc_stages<DIM, NQB, BF>() * tc_stage_bytes<DIM, BF>() + (size_t)NQB * DIM * kQB * (BF ? 2 : 4) /*Q operands*/ +
-         (size_t)NQB * 3 * kQB * 4 /*tauf, qn, s_cnt*/ + (2 * tc_stages<DIM, NQB, BF>() + 4) * 8 + 16;
+         (size_t)NQB * 3 * kQB * 4 /*tauf, qn, s_cnt*/ + (2 * tc_stages<DIM, NQB, BF>() + 4) * 8 + 16 +
+         (size_t)tc_norm_ring<DIM, NQB, BF>() * kTileRows * 4 /*row-norm ring*/;
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -94,6 +100,8 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   uint64_t* tfull = empty + kTcStages;   // [2] accumulator buffer ready
   uint64_t* tempty = tfull + 2;          // [2] accumulator buffer drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  constexpr int kNormRing = tc_norm_ring<DIM, NQB, BF>();
+  float* nrm = reinterpret_cast<float*>(tmem_slot + 4);   // [kNormRing][256], 16-B aligned
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -106,7 +114,13 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   // per-query form below is used for the whole pass.
   __shared__ float s_scale[NQB * kQB];
   __shared__ uint32_t s_cmax;
-  if (tid == 0) s_cmax = 0u;
+  if (tid == 0) {
+    s_cmax = 0u;
+    tma_prefetch_desc(&emap);
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kTcEpiWarps); }
+    mbar_fence_init();
+  }
   int bad = 0;
   for (int q = tid; q < QTOT; q += kTcThreads) {
     float sc = 0.f;
@@ -117,7 +131,35 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     }
     s_scale[q] = sc;
   }
-  const bool scaled = __syncthreads_or(bad) == 0;
+  const bool scaled = __syncthreads_or(bad) == 0;   // (also publishes the mbarrier initialisation)
+
+  const uint32_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // one tile = KH stages of data + its row norms
+  auto issue_tile = [&](uint32_t i, uint32_t it) {
+    const uint32_t t = blockIdx.x + i * gridDim.x;
+    const int row0 = (int)(t * p.tile_stride * (uint32_t)kTileRows);
+    for (int h = 0; h < KH; ++h, ++it) {
+      const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      mbar_arrive_expect_tx(&full[s], kStageB + (h == 0 ? kTileRows * 4 : 0));
+      uint8_t* dst = stage_base + (size_t)s * kStageB;
+      if (h == 0)   // the norm array is padded to whole tiles (build_row_norms), so the copy never runs past it
+        bulk_load_1d(nrm + (size_t)(i % kNormRing) * kTileRows, p.row_norm + (size_t)row0, kTileRows * 4, &full[s]);
+      if constexpr (BF) {
+#pragma unroll
+        for (int sub = 0; sub < DIM / 64; ++sub)   // one box = 256 rows x 64 bf16 (128 B)
+          tma_load_2d(dst + sub * (kTileRows * 128), &emap, sub * 64, row0, &full[s], kEvictFirst);
+      } else {
+        tma_load_2d(dst, &emap, h * 64, row0, &full[s], kEvictFirst);
+        tma_load_2d(dst + kSubTileFloats * 4, &emap, h * 64 + 32, row0, &full[s], kEvictFirst);
+      }
+    }
+  };
+  // the first tiles are requested before the query operands are staged: the ring fills while the prologue runs
+  constexpr uint32_t kPrefetchTiles = kTcStages / KH;
+  const uint32_t n_pre = my_tiles < kPrefetchTiles ? my_tiles : kPrefetchTiles;
+  if (tid == 0)
+    for (uint32_t i = 0; i < n_pre; ++i) issue_tile(i, i * KH);
 
   // query blocks -> K-major SWIZZLE_128B B operands (16-B chunk index XOR row-in-group); padded queries are zero rows
   for (int i = tid; i < DIM * QTOT; i += kTcThreads) {
@@ -148,12 +190,6 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     tq[q] = make_float2(tf, nq2);
     s_cnt[q] = 0;
   }
-  if (tid == 0) {
-    tma_prefetch_desc(&emap);
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kTcEpiWarps); }
-    mbar_fence_init();
-  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -165,31 +201,10 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (uint32_t i = 0; i < my_tiles; ++i) {
-        const uint32_t t = blockIdx.x + i * gridDim.x;
-        const int row0 = (int)(t * p.tile_stride * (uint32_t)kTileRows);
-        for (int h = 0; h < KH; ++h, ++it) {
-          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], kStageB);
-          uint8_t* dst = stage_base + (size_t)s * kStageB;
-          if constexpr (BF) {
-#pragma unroll
-            for (int sub = 0; sub < DIM / 64; ++sub)   // one box = 256 rows x 64 bf16 (128 B)
-              tma_load_2d(dst + sub * (kTileRows * 128), &emap, sub * 64, row0, &full[s], kEvictFirst);
-          } else {
-            tma_load_2d(dst, &emap, h * 64, row0, &full[s], kEvictFirst);
-            tma_load_2d(dst + kSubTileFloats * 4, &emap, h * 64 + 32, row0, &full[s], kEvictFirst);
-          }
-        }
-      }
-    }
+    if (lane == 0)
+      for (uint32_t i = n_pre; i < my_tiles; ++i) issue_tile(i, i * KH);
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
@@ -240,12 +255,9 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     const int ew = warp - 2;
     const int half = ew >> 2, quarter = warp & 3;  // TMEM lanes [32*(warp%4), +32) of half-tile `half`
     const int row_local = half * 128 + quarter * 32 + lane;
-    // row norms are prefetched one tile ahead: the global-load latency must not sit between the accumulator read
-    // and the compares (ncu r2: that exposed ~1 us per tile)
     auto tile_row = [&](uint32_t i) -> uint64_t {
       return (uint64_t)(blockIdx.x + i * gridDim.x) * p.tile_stride * kTileRows + (uint64_t)row_local;
     };
-    float nr_next = (my_tiles > 0 && tile_row(0) < p.n_rows) ? p.row_norm[tile_row(0)] : 0.f;
     const uint32_t seg_stride = gridDim.x * p.seg_cap, seg_base = blockIdx.x * p.seg_cap;
     const float cmax = __uint_as_float(s_cmax);
     // the tile loop is instantiated once per threshold form (the choice is uniform for the launch), so that neither
@@ -257,18 +269,22 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       const uint32_t use = (NBUF == 2) ? (i >> 1) : i;
       const uint64_t lrow = tile_row(i);
       const bool valid = lrow < p.n_rows;
-      const float nr = nr_next;
-      nr_next = (i + 1 < my_tiles && tile_row(i + 1) < p.n_rows) ? p.row_norm[tile_row(i + 1)] : 0.f;
       const uint32_t grow = (uint32_t)(p.row_base + lrow);
       mbar_wait(&tfull[buf], use & 1u);
       tc_fence_after();
+      // The norms landed before the tile's `full` barrier completed, which the MMA thread observed before it issued the
+      // MMAs whose commit completes `tfull`: reading them after the tfull wait is ordered behind the copy.  (Waiting on
+      // `full` itself from here would be wrong: that barrier may already be a whole phase further, the epilogue being
+      // up to two tiles behind the MMA warp.)
+      const float nr = nrm[(size_t)(i % kNormRing) * kTileRows + row_local];
 #pragma unroll 1
       for (int blk = 0; blk < NQB; ++blk) {
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * (uint32_t)NQB + (uint32_t)blk) * 128u +
                                (uint32_t)half * 64u;
         uint32_t v0[32], v1[32];
-        tmem_ld32(taddr, v0);
-        tmem_ld32(taddr + 32u, v1);
+        tmem_ld32_nowait(taddr, v0);
+        tmem_ld32_nowait(taddr + 32u, v1);
+        tmem_ld_wait();
         if (blk == NQB - 1) {  // last accumulator read of this tile: the MMA warp may overwrite the buffer
           tc_fence_before();
           __syncwarp();
@@ -296,14 +312,22 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (g == 0 ? any0 : g == 1 ? any1 : g == 2 ? any2 : any3) {
+                // only the lanes that own a survivor get here (typically one per warp): collect the group's survivors
+                // in a bit mask and append them one by one — a per-query loop over all 16 would be executed by the
+                // whole warp with a (compiler-aggregated) shared-memory atomic per query
+                uint32_t mask = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  const int q = g * 16 + j;
-                  const float sc = __uint_as_float(g < 2 ? v0[q & 31] : v1[q & 31]);
-                  if (q < nqb && !(sc < t_r)) {
-                    const uint32_t pos = atomicAdd(&scb[q], 1u);
-                    if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)q) * seg_stride + seg_base + pos] = grow;
-                  }
+                  const float sc = __uint_as_float(g < 2 ? v0[(g & 1) * 16 + j] : v1[(g & 1) * 16 + j]);
+                  if (!(sc < t_r)) mask |= 1u << j;
+                }
+                const int left = nqb - g * 16;   // real queries in this group
+                if (left < 16) mask &= left > 0 ? ((1u << left) - 1u) : 0u;
+                while (mask) {
+                  const int q = g * 16 + __ffs(mask) - 1;
+                  mask &= mask - 1;
+                  const uint32_t pos = atomicAdd(&scb[q], 1u);
+                  if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)q) * seg_stride + seg_base + pos] = grow;
                 }
               }
             }
@@ -327,14 +351,20 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (any[g]) {
+                uint32_t mask = 0;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const int q = g * 16 + j;
                   const float sc = __uint_as_float(g < 2 ? v0[q & 31] : v1[q & 31]);
-                  if (q < nqb && !(sc < fmaf(-nr, tqb[q].y, tqb[q].x))) {
-                    const uint32_t pos = atomicAdd(&scb[q], 1u);
-                    if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)q) * seg_stride + seg_base + pos] = grow;
-                  }
+                  if (!(sc < fmaf(-nr, tqb[q].y, tqb[q].x))) mask |= 1u << j;
+                }
+                const int left = nqb - g * 16;
+                if (left < 16) mask &= left > 0 ? ((1u << left) - 1u) : 0u;
+                while (mask) {
+                  const int q = g * 16 + __ffs(mask) - 1;
+                  mask &= mask - 1;
+                  const uint32_t pos = atomicAdd(&scb[q], 1u);
+                  if (pos < p.seg_cap) p.cand_rows[(qoff + (uint32_t)q) * seg_stride + seg_base + pos] = grow;
                 }
               }
             }
@@ -386,7 +416,9 @@ int build_row_norms(prg_handle* h) {
   const bool bf = h->scan_filter == SCAN_FILTER_BF16;
   h->E16_map_ok = false;
   if (bf) PRG_TRY(h->E16.ensure((size_t)h->E_rows * h->E_dim * 2));
-  PRG_TRY(h->row_norm.ensure((size_t)h->E_rows * 4));
+  const size_t padded = (size_t)((h->E_rows + kTileRows - 1) / kTileRows) * kTileRows;
+  PRG_TRY(h->row_norm.ensure(padded * 4));
+  PRG_CUDA(cudaMemsetAsync(h->row_norm.p, 0, padded * 4, h->stream));   // whole tiles: the scan copies 256 norms per tile
   const unsigned grid = (unsigned)((h->E_rows + 255) / 256);
   row_norm_kernel<<<grid, 256, 0, h->stream>>>(h->E, h->E_rows, (int)h->E_dim, (float*)h->row_norm.p,
                                                bf ? (__nv_bfloat16*)h->E16.p : nullptr);
