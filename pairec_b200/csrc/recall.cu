@@ -477,40 +477,238 @@ __global__ void __launch_bounds__(1024, 1) select_kth_kernel(const SelectParams 
   if (tid == 0) p.tau[q] = answer;
 }
 
-// Exact re-score of the tensor-core survivors: one block per (segment, query); every candidate row gets the fmaf chain
+// Exact re-score of the tensor-core survivors: one WARP per (segment, query); every candidate row gets the fmaf chain
 // of the arithmetic contract (dims ascending, one accumulator) — the approximate score never reaches an output.
-// DIM is a template parameter so that the DIM/4 row loads of a candidate are all in flight before the (serial) fmaf
-// chain starts: with a runtime trip count every 16-B load sat in front of its four FMAs (ncu: 82 long-scoreboard
-// stalls per issue, 55 us for ~290 k rows).
+// Rows are fetched COALESCED (a half-warp reads one 256-B row per instruction, 16 x 16 B) into a padded shared-memory
+// tile and each lane then walks its own row from there: with one thread per row every 16-B load touched 32 different
+// lines and the LSU, not DRAM, bounded the kernel (ncu r5: 55 us for ~290 k rows = 9 GB/s per SM, mio/lg throttle).
 template <int DIM>
-__global__ void __launch_bounds__(64) rescore_kernel(const uint32_t* __restrict__ seg_rows, const uint32_t* __restrict__ seg_cnt,
+__global__ void __launch_bounds__(32) rescore_kernel(const uint32_t* __restrict__ seg_rows, const uint32_t* __restrict__ seg_cnt,
                                                      uint32_t seg_cap, const float* __restrict__ E, const float* __restrict__ Q,
                                                      uint64_t row_base, uint64_t* __restrict__ seg_keys) {
+  constexpr int F4 = DIM / 4;            // 16-B pieces per row
+  constexpr int RPI = 32 / F4;           // rows fetched per load instruction (2 at dim 64, 1 at dim 128)
+  constexpr int PITCH = DIM + 4;         // floats; keeps both the row-wise stores and the lane-per-row loads conflict free
+  __shared__ __align__(16) float tile[32 * PITCH];
   __shared__ float qv[DIM];
-  const uint32_t sgi = blockIdx.x, q = blockIdx.y, n_seg = gridDim.x;
+  const uint32_t sgi = blockIdx.x, q = blockIdx.y, n_seg = gridDim.x, lane = threadIdx.x;
   uint32_t c = seg_cnt[(size_t)q * n_seg + sgi];
   if (c == 0) return;
   if (c > seg_cap) c = seg_cap;
   const uint32_t* src = seg_rows + ((size_t)q * n_seg + sgi) * seg_cap;
-  uint32_t grow = threadIdx.x < c ? src[threadIdx.x] : 0u;   // issued together with the query load
-  for (uint32_t d = threadIdx.x; d < DIM; d += blockDim.x) qv[d] = Q[(size_t)q * DIM + d];
-  __syncthreads();
   uint64_t* dst = seg_keys + ((size_t)q * n_seg + sgi) * seg_cap;
-  for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
-    if (i != threadIdx.x) grow = src[i];
-    const float4* x = reinterpret_cast<const float4*>(E + ((size_t)grow - row_base) * DIM);
-    float4 xv[DIM / 4];
+  for (uint32_t d = lane; d < DIM; d += 32) qv[d] = Q[(size_t)q * DIM + d];
+  const uint32_t sub = lane / F4, piece = lane % F4;
+  for (uint32_t base = 0; base < c; base += 32) {
+    const uint32_t n = c - base < 32 ? c - base : 32;
+    const uint32_t my_row = lane < n ? src[base + lane] : 0u;
+    __syncwarp();
+    float4 xv[32 / RPI];
 #pragma unroll
-    for (int d4 = 0; d4 < DIM / 4; ++d4) xv[d4] = __ldg(x + d4);
-    float acc = 0.f;
-#pragma unroll
-    for (int d4 = 0; d4 < DIM / 4; ++d4) {
-      acc = __fmaf_rn(xv[d4].x, qv[4 * d4], acc);
-      acc = __fmaf_rn(xv[d4].y, qv[4 * d4 + 1], acc);
-      acc = __fmaf_rn(xv[d4].z, qv[4 * d4 + 2], acc);
-      acc = __fmaf_rn(xv[d4].w, qv[4 * d4 + 3], acc);
+    for (int r = 0; r < 32 / RPI; ++r) {
+      const uint32_t row_in_chunk = r * RPI + sub;
+      const uint32_t grow = __shfl_sync(0xffffffffu, my_row, row_in_chunk);
+      xv[r] = row_in_chunk < n ? __ldg(reinterpret_cast<const float4*>(E + ((size_t)grow - row_base) * DIM) + piece)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    dst[i] = make_key(acc, grow);
+#pragma unroll
+    for (int r = 0; r < 32 / RPI; ++r)
+      *reinterpret_cast<float4*>(&tile[(r * RPI + sub) * PITCH + piece * 4]) = xv[r];
+    __syncwarp();
+    if (lane < n) {
+      const float4* x = reinterpret_cast<const float4*>(&tile[lane * PITCH]);
+      float acc = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < F4; ++d4) {
+        const float4 v = x[d4];
+        acc = __fmaf_rn(v.x, qv[4 * d4], acc);
+        acc = __fmaf_rn(v.y, qv[4 * d4 + 1], acc);
+        acc = __fmaf_rn(v.z, qv[4 * d4 + 2], acc);
+        acc = __fmaf_rn(v.w, qv[4 * d4 + 3], acc);
+      }
+      dst[base + lane] = make_key(acc, my_row);
+    }
+  }
+}
+
+// Select step of the tensor-core filter: one CTA per query packs the query's exact (re-scored) survivor keys into
+// SHARED memory, selects and sorts the top k there.  Replaces select_kernel<TOPK> on that path (ncu r5: 35 us per 64
+// queries: a tid-0 serial walk over the 148 segment counts, ten passes over the keys through L2, and an 8-pass radix
+// select whose first passes all hit one histogram bin).
+//   1. exclusive scan of the (clamped) per-CTA segment lengths -> m survivors, m <= cap (else overflow, flag 1)
+//   2. survivor i: segment by binary search, key from the re-scored segment
+//   3. radix select that starts at the highest bit in which the keys differ and stops as soon as the keys above
+//      the current bucket plus the bucket fit the sort buffer (typically one or two 8-bit passes for ~5 k keys)
+//   4. bitonic sort of that buffer, first k out (keys are distinct: no tie handling left)
+struct RefineParams {
+  const uint64_t* seg_keys;    // [nq][n_seg][seg_cap] exact keys (rescore_kernel)
+  const uint32_t* seg_counts;  // [nq][n_seg]
+  uint32_t n_seg, seg_cap, cap;  // cap = keys the shared buffer holds
+  const uint64_t* tau_check;   // the k-th exact key must reach the sampled threshold (else flag 2)
+  int k, k_out;
+  uint32_t expect;
+  uint32_t sort_cap;           // power of two >= 2 * pow2ceil(k)
+  uint64_t* out_keys;          // [nq][k_out]
+  int32_t* flags;
+  uint32_t* max_count;
+};
+
+__global__ void __launch_bounds__(1024, 1) refine_select_kernel(const RefineParams p) {
+  extern __shared__ uint64_t rs_keys[];          // [cap] exact keys, then [sort_cap] sort buffer
+  __shared__ uint32_t seg_off[520];
+  __shared__ uint32_t hist[256];
+  __shared__ unsigned long long s_or;
+  __shared__ uint64_t s_prefix;
+  __shared__ uint32_t s_want, s_above, s_bucket, s_fill, s_ov;
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint64_t* keys = rs_keys;
+  uint64_t* sk = rs_keys + p.cap;
+
+  // ---- 1. segment offsets
+  if (tid == 0) { s_ov = 0; s_or = 0ull; s_fill = 0; }
+  __syncthreads();
+  for (uint32_t sgi = tid; sgi < p.n_seg; sgi += 1024) {
+    uint32_t c = p.seg_counts[(size_t)q * p.n_seg + sgi];
+    if (c > p.seg_cap) { c = p.seg_cap; s_ov = 1; }
+    seg_off[sgi + 1] = c;
+  }
+  __syncthreads();
+  if (warp == 0) {  // inclusive scan of seg_off[1..n_seg] (n_seg <= 512): 16 entries per lane
+    const uint32_t per = (p.n_seg + 31) / 32;
+    uint32_t sum = 0;
+    for (uint32_t j = 0; j < per; ++j) { const uint32_t i = lane * per + j; if (i < p.n_seg) sum += seg_off[i + 1]; }
+    uint32_t run = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, run, off);
+      if (lane >= off) run += v;
+    }
+    uint32_t base = run - sum;
+    for (uint32_t j = 0; j < per; ++j) {
+      const uint32_t i = lane * per + j;
+      if (i < p.n_seg) { const uint32_t c = seg_off[i + 1]; seg_off[i + 1] = base + c; base += c; }
+    }
+    if (lane == 0) seg_off[0] = 0;
+  }
+  __syncthreads();
+  uint32_t m = seg_off[p.n_seg];
+  bool overflow = s_ov != 0u;
+  if (m > p.cap) { m = p.cap; overflow = true; }
+  if (p.max_count && tid == 0) atomicMax(p.max_count, m);
+
+  // ---- 2. pack the exact keys into shared memory
+  unsigned long long my_or = 0ull;
+  uint64_t key0 = 0ull;
+  for (uint32_t i = tid; i < m; i += 1024) {
+    uint32_t lo = 0, hi = p.n_seg;       // last segment with seg_off[s] <= i
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
+    const uint64_t key = p.seg_keys[((size_t)q * p.n_seg + lo) * p.seg_cap + (i - seg_off[lo])];
+    keys[i] = key;
+    if (i == tid) key0 = key;
+    my_or |= key ^ key0;
+  }
+  __syncthreads();
+  // bits in which any two keys differ: OR over (key ^ keys[0])
+  if (tid < m) my_or |= key0 ^ keys[0];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) my_or |= __shfl_xor_sync(0xffffffffu, my_or, off);
+  if (lane == 0 && my_or) atomicOr(&s_or, my_or);
+  __syncthreads();
+
+  // ---- 3. radix select from the highest differing bit; stop when (keys above the bucket) + bucket fit sort_cap
+  const uint32_t k = (uint32_t)p.k;
+  uint64_t lo_key = 1ull;  // keys >= lo_key go to the sort buffer
+  if (m > p.sort_cap) {
+    const int top0 = 64 - __clzll((long long)s_or);   // bits [top0, 64) are common to all keys (s_or != 0: m > 1 distinct)
+    int top = top0;
+    uint64_t prefix = 0ull, mask = 0ull;
+    uint32_t want = k, above_total = 0;
+    while (true) {
+      const int shift = top > 8 ? top - 8 : 0;
+      const uint32_t dmask = (1u << (top - shift)) - 1u;
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < m; i += 1024) {
+        const uint64_t key = keys[i];
+        const bool in = (key & mask) == prefix;
+        const uint32_t dg = (uint32_t)(key >> shift) & dmask;
+        // warp-aggregated histogram: one atomic per distinct digit and warp
+        const unsigned act = __ballot_sync(__activemask(), in);
+        if (in) {
+          const unsigned same = __match_any_sync(act, dg);
+          if (lane == __ffs(same) - 1) atomicAdd(&hist[dg], __popc(same));
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {  // lane l owns digits [8l, 8l+8); suffix sums from the top digit down
+        uint32_t c[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
+        uint32_t run = tot;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t v = __shfl_down_sync(0xffffffffu, run, off);
+          if (lane + off < 32) run += v;
+        }
+        const uint32_t above = run - tot;
+        if (above < want && above + tot >= want) {
+          uint32_t a = above;
+          int d = 7;
+          for (; d >= 0; --d) {
+            if (a + c[d] >= want) break;
+            a += c[d];
+          }
+          s_prefix = prefix | ((uint64_t)(lane * 8 + d) << shift);
+          s_want = want - a;
+          s_above = a;
+          s_bucket = c[d];
+        }
+      }
+      __syncthreads();
+      prefix = s_prefix;
+      want = s_want;
+      above_total += s_above;
+      mask |= ((uint64_t)dmask << shift);
+      const uint32_t bucket = s_bucket;
+      top = shift;
+      __syncthreads();
+      if (above_total + bucket <= p.sort_cap || shift == 0) break;
+    }
+    // every key shares the bits at and above top0, so "in the bucket or above it" is a plain comparison
+    lo_key = (top0 >= 64 ? 0ull : ((keys[0] >> top0) << top0)) | prefix;
+  }
+  for (uint32_t i = tid; i < p.sort_cap; i += 1024) sk[i] = 0ull;
+  __syncthreads();
+  for (uint32_t i = tid; i < m; i += 1024) {
+    const uint64_t key = keys[i];
+    if (key >= lo_key) {
+      const uint32_t pos = atomicAdd(&s_fill, 1u);
+      if (pos < p.sort_cap) sk[pos] = key;
+    }
+  }
+  __syncthreads();
+  const uint32_t filled = s_fill < p.sort_cap ? s_fill : p.sort_cap;
+  uint32_t K2 = 32;
+  while (K2 < filled) K2 <<= 1;
+  // ---- 4. bitonic sort, descending
+  for (uint32_t size = 2; size <= K2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = tid; i < (K2 >> 1); i += 1024) {
+        const uint32_t pos = 2 * i - (i & (stride - 1));
+        const uint64_t a = sk[pos], b = sk[pos + stride];
+        const bool desc = (pos & size) == 0;
+        if ((a < b) == desc) { sk[pos] = b; sk[pos + stride] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  const uint32_t n_out = m < k ? m : k;
+  for (uint32_t i = tid; i < (uint32_t)p.k_out; i += 1024)
+    p.out_keys[(size_t)q * p.k_out + i] = (i < n_out) ? sk[i] : 0ull;
+  if (tid == 0) {
+    int fl = overflow ? 1 : (n_out < p.expect ? 2 : 0);
+    if (!fl && p.tau_check && n_out > 0 && sk[n_out - 1] < p.tau_check[q]) fl = 2;  // a row outside the list could win
+    if (p.flags) p.flags[q] = fl;
   }
 }
 
@@ -685,19 +883,40 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     if (use_tc) PRG_TRY(launch_scan_tc(h, sc));
     else PRG_TRY(scan(h, SCAN_THRESH, sc));
   }
-  if (use_tc) {  // exact re-score of the tensor-core survivors, all queries at once
+  uint32_t k_pow2 = 32;
+  while (k_pow2 < (uint32_t)k) k_pow2 <<= 1;
+  const uint32_t sort_cap = (k_pow2 - (uint32_t)k >= 16) ? k_pow2 : 2 * k_pow2;
+  const size_t refine_smem = ((size_t)cand_cap + sort_cap) * 8;
+  auto launch_rescore = [&]() -> int {   // exact re-score of the tensor-core survivors, all queries at once
     StageScope span(h, ST_SELECT);
     if (dim == 64)
-      rescore_kernel<64><<<dim3(n_seg, (unsigned)B), 64, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
+      rescore_kernel<64><<<dim3(n_seg, (unsigned)B), 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
                                                                          (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, q_dev,
                                                                          h->E_row_base, (uint64_t*)h->seg_keys.p);
     else
-      rescore_kernel<128><<<dim3(n_seg, (unsigned)B), 64, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
+      rescore_kernel<128><<<dim3(n_seg, (unsigned)B), 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
                                                                           (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, q_dev,
                                                                           h->E_row_base, (uint64_t*)h->seg_keys.p);
     PRG_CUDA(cudaGetLastError());
     count_launch(h);
-  }
+    return PRG_OK;
+  };
+  if (use_tc && n_seg <= 512 && refine_smem <= 200 * 1024) {
+    // 4. exact re-score, then the top-k of the exact keys in shared memory
+    PRG_TRY(launch_rescore());
+    RefineParams rp{};
+    rp.seg_keys = (const uint64_t*)h->seg_keys.p; rp.seg_counts = (const uint32_t*)h->cand_cnt.p;
+    rp.n_seg = n_seg; rp.seg_cap = seg_cap; rp.cap = cand_cap;
+    rp.tau_check = (const uint64_t*)h->tau.p;
+    rp.k = k; rp.k_out = k; rp.expect = (uint32_t)((uint64_t)k < h->E_rows ? (uint64_t)k : h->E_rows);
+    rp.sort_cap = sort_cap; rp.out_keys = keys_out; rp.flags = (int32_t*)h->flags.p; rp.max_count = max_cnt;
+    StageScope span(h, ST_SELECT);
+    PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
+    refine_select_kernel<<<B, 1024, refine_smem, h->stream>>>(rp);
+    PRG_CUDA(cudaGetLastError());
+    count_launch(h);
+  } else {
+  if (use_tc) PRG_TRY(launch_rescore());   // large k: the keys do not fit on chip
   // 4. exact top-k of the candidates
   SelectParams se{};
   se.keys = (const uint64_t*)h->seg_keys.p; se.stride = cand_cap; se.counts = nullptr;
@@ -709,6 +928,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   se.out_keys = keys_out; se.flags = (int32_t*)h->flags.p;
   se.max_count = max_cnt;
   PRG_TRY(launch_select(h, SEL_TOPK, se, B));
+  }
   // 5. per-query status -> pinned host memory; checked now, or later when deferred (fused path)
   if (h->host_flags_cap < (size_t)B) {
     if (h->host_flags) cudaFreeHost(h->host_flags);

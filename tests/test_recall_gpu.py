@@ -170,3 +170,20 @@ def test_negative_thresholds_use_the_per_query_filter(engine, oracle_lib):
     Q[3] = -Q[3]    # one query with positive scores in the same pass
     _check(engine, oracle_lib, E, Q, 700)
     assert engine.recall_stats()["fallback_queries"] == 0
+
+
+def test_large_k_uses_the_split_refine_path(engine, oracle_lib):
+    # k = 3000: the survivors' exact keys do not fit in shared memory, so re-score and select run as separate kernels
+    E, Q = _data(400_000, 64, 5, seed=91)
+    _check(engine, oracle_lib, E, Q, 3000)
+    assert engine.recall_stats()["fallback_queries"] == 0
+
+
+def test_clustered_scores_refine_select(engine, oracle_lib):
+    # many near-identical scores: the radix select of the refine kernel has to walk several digit passes
+    n, d = 400_000, 64
+    rng = np.random.default_rng(97)
+    base = (rng.standard_normal((1, d)) / np.sqrt(d)).astype(np.float32)
+    E = (base + rng.standard_normal((n, d)).astype(np.float32) * np.float32(1e-4)).astype(np.float32)
+    Q = (base * np.float32(1.0) + rng.standard_normal((3, d)).astype(np.float32) * np.float32(1e-3)).astype(np.float32)
+    _check(engine, oracle_lib, E, Q, 1000)
