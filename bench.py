@@ -53,91 +53,112 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+_NVML_POLLER = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+d = n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print("max", n.nvmlDeviceGetMaxClockInfo(d, n.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(d)
+    except Exception:
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(d)
+    print(time.time(), n.nvmlDeviceGetClockInfo(d, n.NVML_CLOCK_SM), int(r), flush=True)
+    time.sleep(0.002)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region: NVML polled from a thread every ~2 ms (a short timed
-    region still gets samples); `nvidia-smi -lms 50` only when NVML cannot be loaded."""
+    """SM clock and throttle reasons DURING the timed region.  A separate PROCESS polls NVML every ~2 ms for the whole
+    run (a thread in this process starves behind the GIL while the timed loop issues ctypes calls back to back);
+    begin()/end() bracket the timed region and only the samples stamped inside it are reported.  Falls back to
+    `nvidia-smi -lms 50` when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.rows = []       # nvidia-smi fallback: csv rows
-        self.sm = []         # NVML: SM MHz samples
-        self.reason_bits = 0
+        self.rows = []
+        self.lines = []
         self.sm_max = None
         self.proc = None
-        self.nvml = None
-        self.stop_flag = threading.Event()
-        self.t = None
+        self.kind = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.dev = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
-            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
-            self.nvml = pynvml
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
-            return
+            self.proc = subprocess.Popen([sys.executable, "-c", _NVML_POLLER, str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            first = self.proc.stdout.readline().split()
+            if len(first) == 2 and first[0] == "max":
+                self.sm_max = float(first[1])
+                self.kind = "nvml"
+                self.t = threading.Thread(target=self._read_nvml, daemon=True)
+                self.t.start()
+                return
+            self.proc.kill()
         except Exception:
-            self.nvml = None
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.kind = "nvidia-smi"
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _poll(self):
-        n = self.nvml
-        while not self.stop_flag.is_set():
-            try:
-                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM)))
-                self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
-            except Exception:
-                try:
-                    self.reason_bits |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
-                except Exception:
-                    pass
-            time.sleep(0.002)
-
-    def _read(self):
+    def _read_nvml(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            f = line.split()
+            if len(f) == 3:
+                self.lines.append((float(f[0]), float(f[1]), int(f[2])))
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        if self.nvml is not None:
-            self.stop_flag.set()
-            self.t.join(timeout=2)
-            n = self.nvml
-            names = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                     "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                     "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                     "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-            reasons = sorted(k for k, bit in names.items() if self.reason_bits & bit)
-            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
-                    "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source"], "samples": 0}
+        time.sleep(0.01)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        t0 = self.t0 or 0.0
+        t1 = self.t1 or time.time()
+        if self.kind == "nvml":
+            inside = [(c, r) for (t, c, r) in self.lines if t0 <= t <= t1]
+            if not inside:  # region shorter than one poll: take the nearest samples around it
+                inside = [(c, r) for (t, c, r) in self.lines if t0 - 0.01 <= t <= t1 + 0.01]
+            bits = 0
+            for _, r in inside:
+                bits |= r
+            return {"sm_mhz": float(np.median([c for c, _ in inside])) if inside else None, "sm_max_mhz": self.sm_max,
+                    "reasons": sorted(k for k, b in self.BITS.items() if bits & b), "samples": len(inside),
+                    "source": "nvml poller process, 2 ms"}
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.05 and len(r) >= 8]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 50"}
 
 
 # ---------------------------------------------------------------------------------------------- synthetic tables
@@ -354,23 +375,27 @@ def main():
             dist.barrier()
 
     # ---- warm-up, then K timed steps (device-resident inputs): `value`
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()   # the poller process needs a moment to come up: start it before the warm-up
     for _ in range(warmup):
         step_device()
     sync_all()
     eng.timing(2)             # CUDA-event spans around the recall scan only while the step is timed
     eng.timing(2, read=True)  # reset accumulators
     launches0 = eng.launches
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     sync_all()
+    if rank == 0:
+        sampler.begin()
     with torch.cuda.stream(stream):
         ev[0].record(stream)
         for i in range(args.steps):
             step_device()
             ev[i + 1].record(stream)
     sync_all()
+    if rank == 0:
+        sampler.end()
     clocks = sampler.stop() if rank == 0 else None
     stage = eng.timing(1, read=True)   # scan spans of the timed region; now switch to all stages
     launches = eng.launches - launches0

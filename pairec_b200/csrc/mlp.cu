@@ -171,13 +171,18 @@ mlp_layer_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // of tile i (8 warps: two per TMEM lane quarter, each taking half of the columns) overlaps the MMAs of tile i+1, and
 // the per-CTA prologue (TMEM alloc, barrier init, first TMA round trip) is paid once per SM instead of once per tile.
 // ncu r1 of the one-tile-per-CTA kernel above: tensor pipe 30 % active — MMA and epilogue were serialised.
+// A stage holds the hi AND the lo block of the activations for one 64-wide slice of K together with the ONE W block
+// both are multiplied with (a = hi + lo, so hi*W and lo*W use the same weights): per slice the CTA pulls
+// 16 + 16 + BN/8 KiB instead of 2 x (16 + BN/8) KiB.  Layer 1 at 128 x 256 tiles ran at the L2 bandwidth limit
+// (768 MB of operand reads in 92 us = 8.3 TB/s, tensor pipe 39 % active); this takes a third of that traffic away.
 constexpr int kMlpPThreads = 320;
 constexpr int kMlpEpiWarps = 8;
+constexpr int kMlpPStages = 3;
 
 template <int BN>
 constexpr size_t mlp_p_smem_bytes() {
-  return (size_t)kMlpStages * (kMlpBM * 128 + BN * 128) + 2 * 1024 * 4 /*bias, w_last*/ + 2 * 2 * kMlpBM * 4 /*partials*/ +
-         (2 * kMlpStages + 4) * 8 + 16;
+  return (size_t)kMlpPStages * (2 * kMlpBM * 128 + BN * 128) + 2 * 1024 * 4 /*bias, w_last*/ + 2 * 2 * kMlpBM * 4 /*partials*/ +
+         (2 * kMlpPStages + 4) * 8 + 16;
 }
 
 template <int BN, bool FINAL>
@@ -185,7 +190,8 @@ __global__ void __launch_bounds__(kMlpPThreads, 1)
 mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                             const MlpLayerParams p, const int n_mblk) {
   extern __shared__ __align__(1024) uint8_t msm[];
-  constexpr int kABytes = kMlpBM * 128, kBBytes = BN * 128, kStageBytes = kABytes + kBBytes;
+  constexpr int kABytes = kMlpBM * 128, kBBytes = BN * 128, kStageBytes = 2 * kABytes + kBBytes;  // A_hi | A_lo | W
+  constexpr int kMlpStages = kMlpPStages;
   constexpr uint32_t kTmemCols = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   float* bias_s = reinterpret_cast<float*>(msm + (size_t)kMlpStages * kStageBytes);  // [1024]
   float* wl_s = bias_s + 1024;                                                       // [1024]
@@ -199,7 +205,7 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_nblk = p.N / BN;
   const int n_tiles = n_mblk * n_nblk;
-  const int num_kb = 2 * p.K / kMlpBK;
+  const int num_kb = p.K / kMlpBK;   // 64-wide slices of K; each brings its hi and its lo activations
   const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   for (int i = tid; i < p.N; i += kMlpPThreads) {
@@ -235,7 +241,8 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
           mbar_arrive_expect_tx(&full[s], kStageBytes);
           uint8_t* a_dst = msm + (size_t)s * kStageBytes;
           tma_load_2d(a_dst, &mapA, kb * kMlpBK, m_blk * kMlpBM, &full[s], kEvictNormal);
-          tma_load_2d(a_dst + kABytes, &mapW, (kb * kMlpBK) % p.K, n_blk * BN, &full[s], kEvictLast);
+          tma_load_2d(a_dst + kABytes, &mapA, p.K + kb * kMlpBK, m_blk * kMlpBM, &full[s], kEvictNormal);
+          tma_load_2d(a_dst + 2 * kABytes, &mapW, kb * kMlpBK, n_blk * BN, &full[s], kEvictLast);
         }
       }
     }
@@ -253,10 +260,14 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(msm + (size_t)s * kStageBytes);
-          const uint64_t adesc = umma_desc_k_sw128(a_addr), bdesc = umma_desc_k_sw128(a_addr + kABytes);
+          const uint64_t bdesc = umma_desc_k_sw128(a_addr + 2 * kABytes);
 #pragma unroll
-          for (int k = 0; k < kMlpBK / 16; ++k)
-            umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int part = 0; part < 2; ++part) {   // hi, then lo, against the same W block
+            const uint64_t adesc = umma_desc_k_sw128(a_addr + (uint32_t)part * kABytes);
+#pragma unroll
+            for (int k = 0; k < kMlpBK / 16; ++k)
+              umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | part | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty[s]);
         }
         umma_commit(&tfull[buf]);
