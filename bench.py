@@ -305,7 +305,10 @@ def main():
                           f"rank -> score sort -> DPP top-{w['top_n']} (window {w['window']}, {w['div_dim']}-d f32 table, "
                           f"fp64 arithmetic)",
               "batch_per_gpu": w["batch"], "global_batch": w["batch"] * world,
-              "sharding": "item matrix row-sharded, one all-gather of per-shard top-k keys" if world > 1 else "none",
+              "sharding": ("item matrix row-sharded; " + ("all-gather of per-shard top-k keys"
+                           if os.environ.get("PRG_SHARD_PROTOCOL", "global") == "local" else
+                           "global threshold: all-gather of per-shard sample keys, then all-gather of the candidates "
+                           "that reach it") if world > 1 else "none"),
               "l2": "inputs larger than L2 (item matrix / its 1.28 GB bf16 filter index streamed per step)"}
 
     if args.impl == "reference":
@@ -353,19 +356,38 @@ def main():
     out_scores = torch.empty(B, Tn, dtype=torch.float64, device=dev)
     out_n = torch.empty(B, dtype=torch.int32, device=dev)
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
-    if world > 1:
+    protocol = os.environ.get("PRG_SHARD_PROTOCOL", "global")   # "global": one threshold per query across shards
+    if world > 1 and protocol == "local":
         keys_local = torch.empty(Bg, k, dtype=torch.int64, device=dev)
         keys_all = torch.empty(world, Bg, k, dtype=torch.int64, device=dev)
+    elif world > 1:
+        r_s = eng.shard_sample_len(k)
+        samp_local = torch.empty(Bg, r_s, dtype=torch.int64, device=dev)
+        samp_all = torch.empty(world, Bg, r_s, dtype=torch.int64, device=dev)
+        blk = Bg * k + Bg                                        # per rank: Bg x k keys + Bg status words
+        cand_local = torch.empty(blk, dtype=torch.int64, device=dev)
+        cand_all = torch.empty(world, blk, dtype=torch.int64, device=dev)
+        retry = torch.zeros(2, dtype=torch.int32, device=dev)
 
     def step_device():
         if world == 1:
             eng.recommend_dev(Qg.data_ptr(), B, k, MODEL_FM_MLP, p, out_rows.data_ptr(), out_scores.data_ptr(),
                               out_n.data_ptr())
-        else:
+        elif protocol == "local":
             eng.recall_local_keys_dev(Qg.data_ptr(), Bg, k, keys_local.data_ptr())
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(keys_all, keys_local)
             eng.recommend_from_keys_dev(keys_all.data_ptr() + rank * B * k * 8, world, Bg * k, B, k, MODEL_FM_MLP, p,
+                                        out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr())
+        else:
+            eng.shard_sample_dev(Qg.data_ptr(), Bg, k, world, samp_local.data_ptr())
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(samp_all, samp_local)          # exchange 1: G x Bg x r sample keys
+            eng.shard_candidates_dev(Qg.data_ptr(), Bg, k, world, samp_all.data_ptr(), cand_local.data_ptr())
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(cand_all, cand_local)          # exchange 2: candidates that reach tau
+            eng.shard_check_dev(cand_all.data_ptr(), world, Bg, k, retry.data_ptr())
+            eng.recommend_from_keys_dev(cand_all.data_ptr() + rank * B * k * 8, world, blk, B, k, MODEL_FM_MLP, p,
                                         out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr())
 
     def sync_all():
@@ -464,6 +486,10 @@ def main():
            "d2h_bytes_per_step": B * Tn * 12 + B * 4, "p50_ms": float(np.percentile(lat, 50)),
            "p99_ms": float(np.percentile(lat, 99)), "note": note}
 
+    shard_retries = None
+    if world > 1 and protocol == "global":
+        eng.sync()
+        shard_retries = int(retry.cpu()[1].item())   # queries that asked for the exact protocol (expected: 0)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -507,6 +533,8 @@ def main():
                                  "rows*dim*4 (tf32 / ffma2 over the fp32 rows) + rows*4 row norms + queries; the fp32 "
                                  "matrix is only touched for the ~5 k survivors per query (exact re-score); see DESIGN.md 3.1"},
             "e2e": e2e}
+    if shard_retries is not None:
+        line["shard_retry_queries"] = shard_retries
     if not args.no_cpu_baseline and world == 1:
         try:
             r = cpu_measure(w, 1, 0, min(args.cpu_sample_rows, w["items"]))

@@ -108,6 +108,27 @@ int prg_recall_topk(prg_handle* h, const float* q, int B, int k, uint32_t* out_r
 /* Row-sharded recall: local top-k as 64-bit order keys, device pointers only.
  * key = (ordered_bits(score) << 32) | (0xFFFFFFFF - global_row); 0 = empty slot.  out_keys: B x k u64. */
 int prg_recall_local_keys(prg_handle* h, const float* q_dev, int B, int k, uint64_t* out_keys_dev);
+/* Row-sharded recall with ONE global threshold per query: the refine work of a rank no longer grows with the shard
+ * count G (with prg_recall_local_keys every shard refines ~4k survivors per query to a local top-k for all B*G queries).
+ * All pointers are device pointers; Bg = B*G queries, identical on every rank; the two exchanges are the host's
+ * (ncclAllGather / torch.distributed.all_gather_into_tensor).
+ *   1. prg_shard_sample:     out_sample[Bg][r] = the r = prg_shard_sample_len(k) best keys of this shard's 1/128 row
+ *                            sample per query (sorted, 0-padded)                              -> all-gather #1 (G x Bg x r)
+ *   2. prg_shard_candidates: tau[q] = r-th largest of the G*r gathered sample keys; out[Bg*k + Bg] = per query the
+ *                            exact keys of this shard's rows that reach tau (sorted, at most k, 0-padded), then Bg
+ *                            status words (non-zero: the shard's candidate list overflowed)    -> all-gather #2
+ *   3. prg_shard_check:      retry[0] |= 1 and retry[1] += 1 for every query that needs the exact protocol (a shard
+ *                            overflowed, or fewer than k gathered keys reach tau: both < 1e-10 per query unless the
+ *                            row order defeats the strided sample).  Every rank computes the same answer from the
+ *                            same gathered buffer, so all ranks redo the batch together with prg_recall_local_keys.
+ *                            Then prg_recommend_from_keys with g_stride = Bg*k + Bg merges as before.
+ * The union of the gathered lists holds every row whose exact key reaches tau; with >= k of them the merged top-k is the
+ * global top-k, bit-identical to prg_recall_topk over the unsharded matrix. */
+int prg_shard_sample_len(int k);
+int prg_shard_sample(prg_handle* h, const float* q_dev, int Bg, int k, int G, uint64_t* out_sample_dev);
+int prg_shard_candidates(prg_handle* h, const float* q_dev, int Bg, int k, int G, const uint64_t* all_samples_dev,
+                         uint64_t* out_keys_dev);
+int prg_shard_check(prg_handle* h, const uint64_t* gathered_dev, int G, int Bg, int k, int32_t* retry_dev);
 /* Merge G gathered key lists (keys_dev: G x B x k, the all-gather output) into the global top-k. */
 int prg_merge_keys(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint32_t* out_row,
                    float* out_score, int32_t* out_n, int mem);

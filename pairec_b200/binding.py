@@ -18,7 +18,8 @@ _lib = None
 EXPORTS = [
     "prg_init", "prg_destroy", "prg_last_error", "prg_version", "prg_sync", "prg_stream", "prg_set_item_matrix",
     "prg_set_item_fields", "prg_set_feature_table", "prg_set_fm_bias", "prg_set_mlp", "prg_set_diversity_matrix",
-    "prg_recall_topk", "prg_recall_local_keys", "prg_merge_keys", "prg_rank", "prg_sort_desc_host", "prg_sort_desc",
+    "prg_recall_topk", "prg_recall_local_keys", "prg_merge_keys", "prg_shard_sample_len", "prg_shard_sample",
+    "prg_shard_candidates", "prg_shard_check", "prg_rank", "prg_sort_desc_host", "prg_sort_desc",
     "prg_dpp", "prg_ssd", "prg_recommend", "prg_recommend_from_keys", "prg_lookup", "prg_launch_count", "prg_recall_stats", "prg_timing",
 ]
 
@@ -213,6 +214,21 @@ class Engine:
 
     def recall_local_keys_dev(self, q_ptr, B, k, keys_ptr):
         self._ck(self._lib.prg_recall_local_keys(self._h, _ptr(q_ptr), C.c_int(B), C.c_int(k), _ptr(keys_ptr)))
+
+    # global-threshold sharded recall (device pointers; the two all-gathers are the caller's)
+    def shard_sample_len(self, k):
+        return int(self._lib.prg_shard_sample_len(C.c_int(k)))
+
+    def shard_sample_dev(self, q_ptr, Bg, k, G, out_ptr):
+        self._ck(self._lib.prg_shard_sample(self._h, _ptr(q_ptr), C.c_int(Bg), C.c_int(k), C.c_int(G), _ptr(out_ptr)))
+
+    def shard_candidates_dev(self, q_ptr, Bg, k, G, all_samples_ptr, out_ptr):
+        self._ck(self._lib.prg_shard_candidates(self._h, _ptr(q_ptr), C.c_int(Bg), C.c_int(k), C.c_int(G),
+                                                _ptr(all_samples_ptr), _ptr(out_ptr)))
+
+    def shard_check_dev(self, gathered_ptr, G, Bg, k, retry_ptr):
+        self._ck(self._lib.prg_shard_check(self._h, _ptr(gathered_ptr), C.c_int(G), C.c_int(Bg), C.c_int(k),
+                                           _ptr(retry_ptr)))
 
     def merge_keys(self, keys_ptr, G, B, k, rows=None, scores=None, n=None, mem=MEM_HOST):
         if mem == MEM_HOST:

@@ -279,6 +279,31 @@ int prg_recall_local_keys(prg_handle* h, const float* q_dev, int B, int k, uint6
   return recall_topk_device(h, q_dev, B, k, out_keys_dev);
 }
 
+int prg_shard_sample_len(int k) { return k > 0 ? shard_sample_len(k) : 0; }
+
+int prg_shard_sample(prg_handle* h, const float* q_dev, int Bg, int k, int G, uint64_t* out_sample_dev) {
+  CHECK_H(h);
+  if (!q_dev || !out_sample_dev) return fail(PRG_EINVAL, "null buffer");
+  Guard g(h);
+  return recall_shard_sample_device(h, q_dev, Bg, k, G, out_sample_dev);
+}
+
+int prg_shard_candidates(prg_handle* h, const float* q_dev, int Bg, int k, int G, const uint64_t* all_samples_dev,
+                         uint64_t* out_keys_dev) {
+  CHECK_H(h);
+  if (!q_dev || !all_samples_dev || !out_keys_dev) return fail(PRG_EINVAL, "null buffer");
+  Guard g(h);
+  return recall_shard_candidates_device(h, q_dev, Bg, k, G, all_samples_dev, out_keys_dev);
+}
+
+int prg_shard_check(prg_handle* h, const uint64_t* gathered_dev, int G, int Bg, int k, int32_t* retry_dev) {
+  CHECK_H(h);
+  if (!gathered_dev || !retry_dev) return fail(PRG_EINVAL, "null buffer");
+  if (G <= 0 || Bg <= 0 || k <= 0) return fail(PRG_EINVAL, "G, Bg, k must be positive");
+  Guard g(h);
+  return shard_check_device(h, gathered_dev, G, Bg, k, retry_dev);
+}
+
 int prg_merge_keys(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint32_t* out_row, float* out_score,
                    int32_t* out_n, int mem) {
   CHECK_H(h);

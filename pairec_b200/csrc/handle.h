@@ -161,6 +161,11 @@ int recall_resolve(prg_handle* h, bool* repaired);   // waits for the deferred s
 int resolve_pending(prg_handle* h);                  // pipeline.cu: recall_resolve + re-run of the fused downstream
 int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint32_t* out_row, float* out_score,
                     int32_t* out_n);
+int shard_sample_len(int k);
+int recall_shard_sample_device(prg_handle* h, const float* q_dev, int Bg, int k, int G, uint64_t* out);
+int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, int k, int G, const uint64_t* all_samples,
+                                   uint64_t* out);
+int shard_check_device(prg_handle* h, const uint64_t* gathered, int G, int Bg, int k, int32_t* retry_dev);
 int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k,
                       uint64_t* keys_out);
 }  // namespace prg

@@ -1007,4 +1007,225 @@ int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g
   return PRG_OK;
 }
 
+// ------------------------------------------------------------------ sharded recall with ONE global threshold per query
+// (SURVEY §8e).  With the protocol above (prg_recall_local_keys) every shard refines its own ~4k survivors per query
+// to a local top-k, so the refine work of a rank grows with the number of shards G (it sees all B*G queries).  Here
+// the threshold is global: each shard samples 1/128 of its rows and contributes its r best sample keys per query; after
+// a first, tiny all-gather every rank takes the r-th largest of the G*r keys as tau (r/f ~ 4k rows of the WHOLE
+// catalog reach it), filters its shard against that tau (~4k/G survivors per query), re-scores them exactly and emits
+// them sorted (at most k).  The second all-gather carries those lists plus one status word per query; the union of the
+// lists holds every row whose exact key reaches tau, so if at least k of them exist the merged top-k is the global
+// top-k.  The two failure modes — a list that overflowed (tau too low) and fewer than k rows reaching tau (tau too
+// high), both < 1e-10 per query for row orders a strided sample represents — are detected identically on every rank
+// from the gathered data (shard_check), and the host then redoes the batch with the exact local protocol.
+constexpr int kShardSampleStride = 128;   // one tile in 128 is sampled
+constexpr uint32_t kShardMaxSampleKeys = 2048;
+
+struct ShardPlan {
+  bool sampled;
+  uint32_t n_tiles, sample_tiles, tile_stride, r;
+  uint64_t slots;
+  uint32_t n_seg, seg_cap, cand_cap, sort_cap;
+  size_t refine_smem;
+};
+
+static uint32_t shard_r(int k) {   // sample keys per query and shard; depends on k only, so every rank agrees on it
+  const uint32_t target = 4u * (uint32_t)(k < 1024 ? 1024 : k);
+  return (target + kShardSampleStride - 1) / kShardSampleStride;
+}
+
+static ShardPlan shard_plan(const prg_handle* h, int k, int G) {
+  ShardPlan pl{};
+  pl.n_tiles = (uint32_t)((h->E_rows + kTileRows - 1) / kTileRows);
+  pl.r = shard_r(k);
+  pl.sample_tiles = pl.n_tiles / kShardSampleStride;
+  // a shard joins the sampled protocol when its sample can hold r keys per query; G equal shards decide alike
+  pl.sampled = !h->scan_ffma2 && pl.sample_tiles >= 8 && (uint64_t)pl.sample_tiles * kTileRows >= 4ull * pl.r &&
+               (uint64_t)k * 64 <= h->E_rows * (uint64_t)G;
+  if (!pl.sampled) return pl;
+  pl.tile_stride = pl.n_tiles / pl.sample_tiles;
+  pl.slots = (uint64_t)pl.sample_tiles * kTileRows;
+  const double expect = (double)pl.r * kShardSampleStride / (double)G;   // survivors per query on this shard
+  pl.cand_cap = ((uint32_t)(4.0 * expect) + 1024 + 1023) & ~1023u;
+  pl.n_seg = pl.n_tiles < (uint32_t)h->sm_count ? pl.n_tiles : (uint32_t)h->sm_count;
+  pl.seg_cap = ((uint32_t)(8.0 * expect / pl.n_seg) + 32 + 15) & ~15u;
+  uint32_t k_pow2 = 32;
+  while (k_pow2 < (uint32_t)k) k_pow2 <<= 1;
+  pl.sort_cap = (k_pow2 - (uint32_t)k >= 16) ? k_pow2 : 2 * k_pow2;
+  pl.refine_smem = ((size_t)pl.cand_cap + pl.sort_cap) * 8;
+  return pl;
+}
+
+int shard_sample_len(int k) { return (int)shard_r(k); }
+
+// phase 1: the r best keys of this shard's sample, per query (sorted, 0-padded); zeros if the shard is not sampled
+int recall_shard_sample_device(prg_handle* h, const float* q_dev, int Bg, int k, int G, uint64_t* out) {
+  if (!h->E || !h->E_map_ok) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
+  if (Bg <= 0 || k <= 0 || G <= 0) return fail(PRG_EINVAL, "Bg, k, G must be positive");
+  if (k > 4096) return fail(PRG_EUNSUPPORTED, "k > 4096");
+  const ShardPlan pl = shard_plan(h, k, G);
+  if ((uint64_t)pl.r * (uint64_t)G > kShardMaxSampleKeys) return fail(PRG_EUNSUPPORTED, "G * sample keys per query > 2048");
+  if (!pl.sampled) {
+    PRG_CUDA(cudaMemsetAsync(out, 0, (size_t)Bg * pl.r * 8, h->stream));
+    return PRG_OK;
+  }
+  const uint32_t dim = h->E_dim;
+  const int nblk = (Bg + kQB - 1) / kQB;
+  PRG_TRY(h->sample_keys.ensure((size_t)nblk * kQB * pl.slots * 8));
+  for (int q0 = 0; q0 < Bg; q0 += kQB) {
+    ScanParams sp{};
+    sp.Q = q_dev + (size_t)q0 * dim; sp.nq = (Bg - q0 < kQB) ? (Bg - q0) : kQB;
+    sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
+    sp.n_tiles = pl.sample_tiles; sp.tile_stride = pl.tile_stride;
+    sp.dense = (uint64_t*)h->sample_keys.p + (size_t)q0 * pl.slots; sp.dense_stride = pl.slots;
+    PRG_TRY(scan(h, SCAN_DENSE, sp));
+  }
+  SelectParams st{};
+  st.keys = (const uint64_t*)h->sample_keys.p; st.stride = pl.slots; st.fixed_m = (uint32_t)pl.slots;
+  st.cap = st.fixed_m; st.k = (int)pl.r; st.k_out = (int)pl.r; st.out_keys = out;
+  return launch_select(h, SEL_TOPK, st, Bg);
+}
+
+// tau[q] = r-th largest of the G*r gathered sample keys (0 = no threshold when fewer than r are valid)
+__global__ void __launch_bounds__(256) shard_tau_kernel(const uint64_t* __restrict__ all, int G, int Bg, uint32_t r,
+                                                        uint64_t* __restrict__ tau) {
+  __shared__ uint64_t sk[kShardMaxSampleKeys];
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const uint32_t m = (uint32_t)G * r;
+  uint32_t K2 = 32;
+  while (K2 < m) K2 <<= 1;
+  for (uint32_t i = tid; i < K2; i += 256) {
+    const uint32_t g = i / r, j = i - g * r;
+    sk[i] = i < m ? all[((size_t)g * Bg + q) * r + j] : 0ull;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= K2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = tid; i < (K2 >> 1); i += 256) {
+        const uint32_t pos = 2 * i - (i & (stride - 1));
+        const uint64_t a = sk[pos], b = sk[pos + stride];
+        if ((a < b) == ((pos & size) == 0)) { sk[pos] = b; sk[pos + stride] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) tau[q] = sk[r - 1];
+}
+
+__global__ void shard_status_kernel(const int32_t* __restrict__ flags, int Bg, uint64_t* __restrict__ status) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Bg) status[q] = flags ? (uint64_t)(uint32_t)flags[q] : 0ull;
+}
+
+// phase 2: out = [Bg][k] exact keys of this shard's rows that reach the global tau (sorted, at most k, 0-padded)
+// followed by Bg status words (0 ok, 1 = the candidate list overflowed)
+int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, int k, int G, const uint64_t* all_samples,
+                                   uint64_t* out) {
+  if (!h->E || !h->E_map_ok) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
+  if (Bg <= 0 || k <= 0 || G <= 0) return fail(PRG_EINVAL, "Bg, k, G must be positive");
+  if (k > 4096) return fail(PRG_EUNSUPPORTED, "k > 4096");
+  if (h->E_rows + h->E_row_base > 0xFFFFFFFFull) return fail(PRG_EUNSUPPORTED, "global row ids must fit u32");
+  const ShardPlan pl = shard_plan(h, k, G);
+  if ((uint64_t)pl.r * (uint64_t)G > kShardMaxSampleKeys) return fail(PRG_EUNSUPPORTED, "G * sample keys per query > 2048");
+  uint64_t* status = out + (size_t)Bg * k;
+  const uint32_t dim = h->E_dim;
+  const size_t QT = (size_t)((Bg + kQB - 1) / kQB) * kQB;
+  PRG_TRY(h->tau.ensure(QT * 8));
+  PRG_TRY(h->flags.ensure(QT * 4));
+  h->pending.active = false;
+  {
+    StageScope span(h, ST_SELECT);
+    shard_tau_kernel<<<Bg, 256, 0, h->stream>>>(all_samples, G, Bg, pl.r, (uint64_t*)h->tau.p);
+    PRG_CUDA(cudaGetLastError());
+    count_launch(h);
+  }
+  if (!pl.sampled) {   // small shard: its exact local top-k is a superset of what the protocol needs
+    for (int q0 = 0; q0 < Bg; q0 += kQB) {
+      const int nq = (Bg - q0 < kQB) ? (Bg - q0) : kQB;
+      PRG_TRY(recall_dense(h, q_dev + (size_t)q0 * dim, nq, k, k, out + (size_t)q0 * k));
+    }
+    shard_status_kernel<<<(Bg + 255) / 256, 256, 0, h->stream>>>(nullptr, Bg, status);
+    PRG_CUDA(cudaGetLastError());
+    count_launch(h);
+    return PRG_OK;
+  }
+  if (pl.n_seg > 512 || pl.refine_smem > 200 * 1024) return fail(PRG_EUNSUPPORTED, "k too large for the global-threshold protocol");
+  const size_t seg_q = (size_t)pl.n_seg * pl.seg_cap;
+  PRG_TRY(h->seg_keys.ensure(QT * seg_q * 8));
+  PRG_TRY(h->seg_rows.ensure(QT * seg_q * 4));
+  if (!h->row_norm.p) PRG_TRY(build_row_norms(h));
+  PRG_TRY(h->cand_cnt.ensure(QT * pl.n_seg * 4 + 4));
+  uint32_t* max_cnt = (uint32_t*)h->cand_cnt.p + QT * pl.n_seg;
+  PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
+  const int pass_q = scan_tc_max_queries(h);
+  for (int q0 = 0; q0 < Bg; q0 += pass_q) {
+    ScanParams sc{};
+    sc.Q = q_dev + (size_t)q0 * dim; sc.nq = (Bg - q0 < pass_q) ? (Bg - q0) : pass_q;
+    sc.n_rows = h->E_rows; sc.row_base = h->E_row_base;
+    sc.n_tiles = pl.n_tiles; sc.tile_stride = 1;
+    sc.tau = (const uint64_t*)h->tau.p + q0; sc.seg_cap = pl.seg_cap;
+    sc.seg_cnt = (uint32_t*)h->cand_cnt.p + (size_t)q0 * pl.n_seg;
+    sc.row_norm = (const float*)h->row_norm.p;
+    sc.cand_rows = (uint32_t*)h->seg_rows.p + (size_t)q0 * seg_q;
+    PRG_TRY(launch_scan_tc(h, sc));
+  }
+  {
+    StageScope span(h, ST_SELECT);
+    if (dim == 64)
+      rescore_kernel<64><<<dim3(pl.n_seg, (unsigned)Bg), 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
+                                                                            (const uint32_t*)h->cand_cnt.p, pl.seg_cap, h->E,
+                                                                            q_dev, h->E_row_base, (uint64_t*)h->seg_keys.p);
+    else
+      rescore_kernel<128><<<dim3(pl.n_seg, (unsigned)Bg), 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
+                                                                             (const uint32_t*)h->cand_cnt.p, pl.seg_cap, h->E,
+                                                                             q_dev, h->E_row_base, (uint64_t*)h->seg_keys.p);
+    PRG_CUDA(cudaGetLastError());
+    count_launch(h);
+    RefineParams rp{};
+    rp.seg_keys = (const uint64_t*)h->seg_keys.p; rp.seg_counts = (const uint32_t*)h->cand_cnt.p;
+    rp.n_seg = pl.n_seg; rp.seg_cap = pl.seg_cap; rp.cap = pl.cand_cap;
+    rp.k = k; rp.k_out = k; rp.expect = 0; rp.sort_cap = pl.sort_cap;
+    rp.out_keys = out; rp.flags = (int32_t*)h->flags.p; rp.max_count = max_cnt;
+    PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.refine_smem));
+    refine_select_kernel<<<Bg, 1024, pl.refine_smem, h->stream>>>(rp);
+    PRG_CUDA(cudaGetLastError());
+    count_launch(h);
+    shard_status_kernel<<<(Bg + 255) / 256, 256, 0, h->stream>>>((const int32_t*)h->flags.p, Bg, status);
+    PRG_CUDA(cudaGetLastError());
+    count_launch(h);
+  }
+  return PRG_OK;
+}
+
+// phase 3 check, identical on every rank: gathered = G blocks of [Bg*k keys | Bg status words]; a query needs the exact
+// protocol if a shard reported an overflow or fewer than k gathered keys reach its tau.  retry[0] |= 1, retry[1] += count.
+__global__ void shard_check_kernel(const uint64_t* __restrict__ gathered, int G, int Bg, int k, const uint64_t* __restrict__ tau,
+                                   int32_t* __restrict__ retry) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Bg) return;
+  const size_t blk = (size_t)Bg * k + Bg;
+  const uint64_t t = tau[q];
+  bool bad = false;
+  uint32_t reach = 0;
+  for (int g = 0; g < G; ++g) {
+    const uint64_t* base = gathered + (size_t)g * blk;
+    if (base[(size_t)Bg * k + q] != 0ull) bad = true;
+    const uint64_t* list = base + (size_t)q * k;   // sorted descending, 0-padded: count keys >= max(t, 1)
+    const uint64_t lim = t ? t : 1ull;
+    int lo = 0, hi = k;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (list[mid] >= lim) lo = mid + 1; else hi = mid; }
+    reach += (uint32_t)lo;
+  }
+  if (t != 0ull && reach < (uint32_t)k) bad = true;
+  if (bad) { atomicOr(&retry[0], 1); atomicAdd(&retry[1], 1); }
+}
+
+int shard_check_device(prg_handle* h, const uint64_t* gathered, int G, int Bg, int k, int32_t* retry_dev) {
+  if (!h->tau.p) return fail(PRG_ESTATE, "prg_shard_candidates has not run on this handle");
+  shard_check_kernel<<<(Bg + 127) / 128, 128, 0, h->stream>>>(gathered, G, Bg, k, (const uint64_t*)h->tau.p, retry_dev);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
 }  // namespace prg

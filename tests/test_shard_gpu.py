@@ -68,3 +68,85 @@ def test_two_shards_merge_to_unsharded_result(oracle_lib):
     finally:
         for g in engs:
             g.close()
+
+
+def _global_protocol(engs, Q, k, dev):
+    """The global-threshold protocol on one GPU: G engines hold the shards; the two all-gathers are emulated by writing
+    every shard's output into its slot of the gathered tensor."""
+    import torch
+    G, Bg = len(engs), Q.shape[0]
+    r = engs[0].shard_sample_len(k)
+    q_dev = torch.from_numpy(Q).to(dev)
+    samples = torch.zeros(G, Bg, r, dtype=torch.int64, device=dev)
+    for g, e in enumerate(engs):
+        e.shard_sample_dev(q_dev.data_ptr(), Bg, k, G, samples[g].data_ptr())
+        e.sync()
+    blk = Bg * k + Bg
+    gathered = torch.zeros(G, blk, dtype=torch.int64, device=dev)
+    for g, e in enumerate(engs):
+        e.shard_candidates_dev(q_dev.data_ptr(), Bg, k, G, samples.data_ptr(), gathered[g].data_ptr())
+        e.sync()
+    retry = torch.zeros(2, dtype=torch.int32, device=dev)
+    engs[0].shard_check_dev(gathered.data_ptr(), G, Bg, k, retry.data_ptr())
+    engs[0].sync()
+    return gathered, retry.cpu().numpy()
+
+
+@pytest.mark.parametrize("G,d,B,k", [(2, 64, 70, 300), (4, 64, 130, 1000), (2, 128, 9, 200)])
+def test_global_threshold_protocol_matches_unsharded_oracle(oracle_lib, G, d, B, k):
+    import torch
+    from pairec_b200 import Engine
+    n = 1_200_000
+    rng = np.random.default_rng(37 + G)
+    E = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    E[n // G:n // G + 300] = E[:300]              # ties across a shard boundary
+    Q = (rng.standard_normal((B, d)) / np.sqrt(d)).astype(np.float32)
+    dev = torch.device("cuda:0")
+    bounds = [g * (n // G) for g in range(G)] + [n]
+    engs = [Engine(0) for _ in range(G)]
+    try:
+        for g, e in enumerate(engs):
+            e.set_item_matrix(E[bounds[g]:bounds[g + 1]], row_base=bounds[g])
+        gathered, retry = _global_protocol(engs, Q, k, dev)
+        assert retry[0] == 0 and retry[1] == 0, "a query asked for the exact protocol on well-mixed data"
+        lists = gathered[:, :B * k].reshape(G, B, k)
+        status = gathered[:, B * k:]
+        assert (status == 0).all()
+        # a shard only emits rows that reach the global threshold: ~4*max(k,1024)/G of them (capped at k)
+        per = (lists != 0).sum(dim=2).float().mean().item()
+        assert per <= min(k, 1.5 * 4 * max(k, 1024) / G)
+        compact = lists.contiguous()
+        rows, scores, cnt = engs[0].merge_keys(compact.data_ptr(), G, B, k)
+        full = oracle_lib.recall_topk(E, Q, k)
+        orows, oscores, on = oracle_lib.keys_split(full)
+        assert (cnt == on).all()
+        assert (rows == orows).all(), "merged rows differ from the unsharded oracle"
+        assert (scores.view(np.uint32) == oscores.view(np.uint32)).all()
+    finally:
+        for e in engs:
+            e.close()
+
+
+def test_global_threshold_protocol_flags_adversarial_order(oracle_lib):
+    # every large score sits in tiles the strided sample never visits: tau is far too low, candidate lists overflow,
+    # and the check must ask for the exact protocol (on every rank alike) instead of returning a wrong list
+    import torch
+    from pairec_b200 import Engine
+    n, d, G, k = 800_000, 64, 2, 500
+    rng = np.random.default_rng(43)
+    E = (rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    tile = np.arange(n) // 256
+    E[:, 0] = np.where(tile % 128 == 0, 0.0, 1.0 + rng.random(n) * 0.5).astype(np.float32)
+    Q = np.zeros((3, d), dtype=np.float32)
+    Q[:, 0] = 1.0
+    dev = torch.device("cuda:0")
+    engs = [Engine(0) for _ in range(G)]
+    try:
+        half = n // 2
+        engs[0].set_item_matrix(E[:half], row_base=0)
+        engs[1].set_item_matrix(E[half:], row_base=half)
+        _, retry = _global_protocol(engs, Q, k, dev)
+        assert retry[0] == 1 and retry[1] == 3
+    finally:
+        for e in engs:
+            e.close()
