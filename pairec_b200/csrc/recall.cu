@@ -31,8 +31,15 @@ constexpr size_t scan_smem_bytes() {
 
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(kScanThreads, 1)
-recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p) {
+recall_scan_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams pin) {
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B boxes need 1024-B aligned destinations
+  ScanParams p = pin;
+  if (MODE == SCAN_DENSE && gridDim.y > 1) {  // one grid row per block of 64 queries (the sample of a large batch)
+    const int y = (int)blockIdx.y;
+    p.Q = pin.Q + (size_t)y * kQB * DIM;
+    p.nq = pin.nq - y * kQB < kQB ? pin.nq - y * kQB : kQB;
+    p.dense = pin.dense + (size_t)y * kQB * pin.dense_stride;
+  }
   float* stage_base = reinterpret_cast<float*>(smem);
   float* Qs = reinterpret_cast<float*>(smem + (size_t)kStages * kStageBytes);  // [DIM][64]
   float* tauf = Qs + DIM * kQB;                                                // [64]
@@ -754,7 +761,8 @@ static int launch_scan(prg_handle* h, const ScanParams& p) {
   PRG_CUDA(cudaFuncSetAttribute(recall_scan_kernel<DIM, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (p.n_tiles == 0) return PRG_OK;
   StageScope span(h, MODE == SCAN_THRESH ? ST_SCAN : ST_SCAN_DENSE);
-  const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
+  const unsigned gx = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
+  const dim3 grid(gx, (MODE == SCAN_DENSE && p.q_blocks > 1) ? (unsigned)p.q_blocks : 1u);
   recall_scan_kernel<DIM, MODE><<<grid, kScanThreads, smem, h->stream>>>(h->E_map, p);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
@@ -854,12 +862,12 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   // All query blocks go through each phase together: the scans run once per block of <= 64 queries, the selects
   // and the re-score once for the whole batch (one CTA per query), and there is ONE status read-back.
   // 1. sample
-  for (int q0 = 0; q0 < B; q0 += kQB) {
+  {  // one launch, one grid row per block of 64 queries
     ScanParams sp{};
-    sp.Q = q_dev + (size_t)q0 * dim; sp.nq = (B - q0 < kQB) ? (B - q0) : kQB;
+    sp.Q = q_dev; sp.nq = B; sp.q_blocks = nblk;
     sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
     sp.n_tiles = sample_tiles; sp.tile_stride = tile_stride;
-    sp.dense = (uint64_t*)h->sample_keys.p + (size_t)q0 * slots; sp.dense_stride = slots;
+    sp.dense = (uint64_t*)h->sample_keys.p; sp.dense_stride = slots;
     PRG_TRY(scan(h, SCAN_DENSE, sp));
   }
   // 2. threshold = r-th largest sample key
@@ -1072,12 +1080,12 @@ int recall_shard_sample_device(prg_handle* h, const float* q_dev, int Bg, int k,
   const uint32_t dim = h->E_dim;
   const int nblk = (Bg + kQB - 1) / kQB;
   PRG_TRY(h->sample_keys.ensure((size_t)nblk * kQB * pl.slots * 8));
-  for (int q0 = 0; q0 < Bg; q0 += kQB) {
+  {  // one launch, one grid row per block of 64 queries
     ScanParams sp{};
-    sp.Q = q_dev + (size_t)q0 * dim; sp.nq = (Bg - q0 < kQB) ? (Bg - q0) : kQB;
+    sp.Q = q_dev; sp.nq = Bg; sp.q_blocks = nblk;
     sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
     sp.n_tiles = pl.sample_tiles; sp.tile_stride = pl.tile_stride;
-    sp.dense = (uint64_t*)h->sample_keys.p + (size_t)q0 * pl.slots; sp.dense_stride = pl.slots;
+    sp.dense = (uint64_t*)h->sample_keys.p; sp.dense_stride = pl.slots;
     PRG_TRY(scan(h, SCAN_DENSE, sp));
   }
   SelectParams st{};

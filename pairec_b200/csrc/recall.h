@@ -36,6 +36,7 @@ struct ScanParams {
   uint32_t* cand_rows;     // TC filter: [nq][gridDim.x][seg_cap] surviving global rows (re-scored exactly by select)
   uint64_t* dense;         // DENSE: [nq][dense_stride], slot = t*256 + r
   uint64_t dense_stride;
+  int q_blocks;            // DENSE: > 1 = nq spans that many blocks of 64 queries, one grid row (blockIdx.y) each
 };
 
 struct SelectParams {
