@@ -790,6 +790,30 @@ static int launch_select(prg_handle* h, int mode, const SelectParams& p, int nq)
   return PRG_OK;
 }
 
+// Scores of the strided tile sample for B queries -> h->sample_keys [B][slots].  With the bf16 filter index the
+// tensor-core kernel scores it (approximate keys: tau is only a pruning hint); otherwise the exact FFMA2 kernel, one
+// launch with one grid row per block of 64 queries.
+static int score_sample(prg_handle* h, const float* q_dev, int B, uint32_t sample_tiles, uint32_t tile_stride,
+                        uint64_t slots, bool use_tc) {
+  ScanParams sp{};
+  sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
+  sp.n_tiles = sample_tiles; sp.tile_stride = tile_stride;
+  sp.dense_stride = slots;
+  if (use_tc && scan_tc_dense_available(h)) {
+    const int pass_q = scan_tc_max_queries(h);
+    sp.row_norm = (const float*)h->row_norm.p;   // the producer copies the tile's norms although DENSE does not use them
+    for (int q0 = 0; q0 < B; q0 += pass_q) {
+      sp.Q = q_dev + (size_t)q0 * h->E_dim; sp.nq = (B - q0 < pass_q) ? (B - q0) : pass_q;
+      sp.dense = (uint64_t*)h->sample_keys.p + (size_t)q0 * slots;
+      PRG_TRY(launch_scan_tc_dense(h, sp));
+    }
+    return PRG_OK;
+  }
+  sp.Q = q_dev; sp.nq = B; sp.q_blocks = (B + kQB - 1) / kQB;
+  sp.dense = (uint64_t*)h->sample_keys.p;
+  return scan(h, SCAN_DENSE, sp);
+}
+
 // Dense path for query block [q0, q0+nq): all keys materialised, then the same select.
 static int recall_dense(prg_handle* h, const float* q_dev, int nq, int k, int k_out, uint64_t* keys_out) {
   const uint32_t n_tiles = (uint32_t)((h->E_rows + kTileRows - 1) / kTileRows);
@@ -862,14 +886,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   // All query blocks go through each phase together: the scans run once per block of <= 64 queries, the selects
   // and the re-score once for the whole batch (one CTA per query), and there is ONE status read-back.
   // 1. sample
-  {  // one launch, one grid row per block of 64 queries
-    ScanParams sp{};
-    sp.Q = q_dev; sp.nq = B; sp.q_blocks = nblk;
-    sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
-    sp.n_tiles = sample_tiles; sp.tile_stride = tile_stride;
-    sp.dense = (uint64_t*)h->sample_keys.p; sp.dense_stride = slots;
-    PRG_TRY(scan(h, SCAN_DENSE, sp));
-  }
+  PRG_TRY(score_sample(h, q_dev, B, sample_tiles, tile_stride, slots, use_tc));
   // 2. threshold = r-th largest sample key
   SelectParams st{};
   st.keys = (const uint64_t*)h->sample_keys.p; st.stride = slots; st.fixed_m = (uint32_t)slots;
@@ -1080,14 +1097,8 @@ int recall_shard_sample_device(prg_handle* h, const float* q_dev, int Bg, int k,
   const uint32_t dim = h->E_dim;
   const int nblk = (Bg + kQB - 1) / kQB;
   PRG_TRY(h->sample_keys.ensure((size_t)nblk * kQB * pl.slots * 8));
-  {  // one launch, one grid row per block of 64 queries
-    ScanParams sp{};
-    sp.Q = q_dev; sp.nq = Bg; sp.q_blocks = nblk;
-    sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
-    sp.n_tiles = pl.sample_tiles; sp.tile_stride = pl.tile_stride;
-    sp.dense = (uint64_t*)h->sample_keys.p; sp.dense_stride = pl.slots;
-    PRG_TRY(scan(h, SCAN_DENSE, sp));
-  }
+  if (!h->row_norm.p) PRG_TRY(build_row_norms(h));
+  PRG_TRY(score_sample(h, q_dev, Bg, pl.sample_tiles, pl.tile_stride, pl.slots, true));
   SelectParams st{};
   st.keys = (const uint64_t*)h->sample_keys.p; st.stride = pl.slots; st.fixed_m = (uint32_t)pl.slots;
   st.cap = st.fixed_m; st.k = (int)pl.r; st.k_out = (int)pl.r; st.out_keys = out;

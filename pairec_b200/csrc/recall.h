@@ -75,5 +75,7 @@ enum { SEL_TOPK = 0, SEL_KTH = 1 };
 int launch_scan_tc(prg_handle* h, const ScanParams& p);
 int scan_tc_max_queries(const prg_handle* h);
 int build_row_norms(prg_handle* h);
+bool scan_tc_dense_available(const prg_handle* h);
+int launch_scan_tc_dense(prg_handle* h, const ScanParams& p);   // sample scoring (approximate keys) on the tensor cores
 
 }  // namespace prg

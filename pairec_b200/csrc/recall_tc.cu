@@ -78,7 +78,11 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {  // SASS FMN
   return r;
 }
 
-template <int DIM, int NQB, bool BF>
+// MODE = SCAN_DENSE: no threshold — every accumulator is written out as an order key (approximate score, row) into
+// p.dense[q][launch tile * 256 + r].  Used for the strided SAMPLE from which the threshold is estimated: tau is a pruning
+// hint only (the filter keeps a superset of {exact >= tau} for any tau and the refine step checks that set), so the
+// sample does not need exact scores, and the tensor cores score it in a fraction of the FFMA2 kernel's time.
+template <int DIM, int NQB, bool BF, int MODE = SCAN_THRESH>
 __global__ void __launch_bounds__(kTcThreads, 1)
 recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -90,6 +94,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   constexpr uint32_t kTmemCols = NQB == 1 ? 256 : 512;
   constexpr int QTOT = NQB * kQB;
   constexpr float kMargin = BF ? kTcMarginBf16 : kTcMarginTf32;
+  constexpr bool kDense = MODE == SCAN_DENSE;
   uint8_t* stage_base = smem;
   uint8_t* Qb = smem + (size_t)kTcStages * kStageB;  // B operands, K-major SWIZZLE_128B: tf32 [NQB][DIM/32][64 q][32 f32],
                                                      // bf16 [NQB][DIM/64][64 q][64 bf16]
@@ -124,14 +129,15 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   int bad = 0;
   for (int q = tid; q < QTOT; q += kTcThreads) {
     float sc = 0.f;
-    if (q < p.nq) {
+    if (kDense) bad = 1;
+    else if (q < p.nq) {
       const uint64_t t = p.tau[q];
       const float tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
       if (tf > 0x1p-60f && tf < 0x1p60f) sc = 1.0f / tf; else bad = 1;
     }
     s_scale[q] = sc;
   }
-  const bool scaled = __syncthreads_or(bad) == 0;   // (also publishes the mbarrier initialisation)
+  const bool scaled = __syncthreads_or(bad) == 0 && !kDense;   // (also publishes the mbarrier initialisation)
 
   const uint32_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   // one tile = KH stages of data + its row norms
@@ -178,7 +184,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   }
   for (int q = tid; q < QTOT; q += kTcThreads) {
     float tf = __int_as_float(0x7F800000), nq2 = 0.f;
-    if (q < p.nq) {
+    if (q < p.nq && !kDense) {
       const uint64_t t = p.tau[q];
       tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
       const float sc = scaled ? s_scale[q] : 1.0f;
@@ -293,7 +299,17 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
         const int nqb = p.nq - blk * kQB;  // queries of this block (may exceed 64; <= 0 for an unused block)
         uint32_t* scb = s_cnt + blk * kQB;
         const uint32_t qoff = (uint32_t)(blk * kQB);
-        if constexpr (kScaled) {
+        if constexpr (kDense) {
+          // lanes of a warp hold consecutive rows: for a fixed query the 32 keys are one contiguous 256-B store
+          const uint64_t slot = (uint64_t)(blockIdx.x + i * gridDim.x) * kTileRows + (uint64_t)row_local;
+#pragma unroll
+          for (int q = 0; q < 64; ++q) {
+            if (q < nqb) {
+              const float sc = __uint_as_float(q < 32 ? v0[q & 31] : v1[q & 31]);
+              p.dense[(size_t)(qoff + (uint32_t)q) * p.dense_stride + slot] = valid ? make_key(sc, grow) : 0ull;
+            }
+          }
+        } else if constexpr (kScaled) {
           // one threshold for the whole row: running maxima over four groups of 16 queries (NaN accumulators are
           // ignored by max; a row whose norm bound is +inf has t_r = -inf or NaN and always survives)
           const float t_r = fmaf(-nr, cmax, 1.0f - 1e-6f);
@@ -375,7 +391,8 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     };
     if (scaled) run(std::true_type{}); else run(std::false_type{});
     asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
-    for (int q = tid - 64; q < p.nq; q += kTcEpiWarps * 32) p.seg_cnt[(size_t)q * gridDim.x + blockIdx.x] = s_cnt[q];
+    if (!kDense)
+      for (int q = tid - 64; q < p.nq; q += kTcEpiWarps * 32) p.seg_cnt[(size_t)q * gridDim.x + blockIdx.x] = s_cnt[q];
   }
 
   tc_fence_before();
@@ -453,6 +470,35 @@ static int launch_tc(prg_handle* h, const ScanParams& p) {
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;
+}
+
+// sample scoring on the tensor cores (bf16 index): nq <= 256 queries at dim 64, <= 64 at dim 128, per launch
+template <int DIM, int NQB>
+static int launch_tc_dense(prg_handle* h, const ScanParams& p) {
+  const size_t smem = scan_tc_smem_bytes<DIM, NQB, true>();
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM, NQB, true, SCAN_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  if (p.n_tiles == 0) return PRG_OK;
+  StageScope span(h, ST_SCAN_DENSE);
+  const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
+  recall_scan_tc_kernel<DIM, NQB, true, SCAN_DENSE><<<grid, kTcThreads, smem, h->stream>>>(h->E16_map, p);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+bool scan_tc_dense_available(const prg_handle* h) { return h->scan_filter == SCAN_FILTER_BF16 && h->E16_map_ok; }
+
+int launch_scan_tc_dense(prg_handle* h, const ScanParams& p) {
+  if (!scan_tc_dense_available(h)) return fail(PRG_ESTATE, "bf16 filter index not built");
+  if (h->E_dim == 64) {
+    if (p.nq <= 64) return launch_tc_dense<64, 1>(h, p);
+    if (p.nq <= 128) return launch_tc_dense<64, 2>(h, p);
+    if (p.nq <= 256) return launch_tc_dense<64, 4>(h, p);
+    return fail(PRG_EINVAL, "launch_scan_tc_dense: more than 256 queries per launch");
+  }
+  if (h->E_dim == 128 && p.nq <= 64) return launch_tc_dense<128, 1>(h, p);
+  return fail(PRG_EINVAL, "launch_scan_tc_dense: unsupported shape");
 }
 
 // queries per pass the kernel is built for: 64/128/256 at dim 64, 64 at dim 128 (shared-memory budget)
