@@ -294,6 +294,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("PRG_WORKLOAD", "c4"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batcher", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -486,6 +487,33 @@ def main():
            "d2h_bytes_per_step": B * Tn * 12 + B * 4, "p50_ms": float(np.percentile(lat, 50)),
            "p99_ms": float(np.percentile(lat, 99)), "note": note}
 
+    # ---- the same path entered ONE REQUEST PER HOST THREAD (what the reference's request goroutines do) through the
+    #      cross-call batcher: closed loop of 3*B native client threads, each a blocking prg_batcher_recommend call
+    batcher = None
+    if world == 1 and not args.no_batcher:
+        from pairec_b200.binding import Batcher
+        bat = Batcher(eng, k, MODEL_FM_MLP, p, max_batch=B, max_wait_us=0)
+        q_pool = q_host.numpy().copy()
+        n_thr = 3 * B
+        per = max(4, (args.steps * B) // n_thr)
+        bat.drive(q_pool, n_thr, 2)                      # warm-up
+        st0 = bat.stats()
+        lat_us, wall, rows_b, n_b = bat.drive(q_pool, n_thr, per)
+        st1 = bat.stats()
+        step_host()                                       # the direct batch call on the same queries, for the check
+        same = bool((rows_b.view(np.int32)[:, :] == rows_h.numpy()).all() and (n_b == n_h.numpy()).all())
+        lat1, _, _, _ = bat.drive(q_pool, 1, 50)          # one caller at a time: unloaded single-request latency
+        bat.close()
+        nb = st1["batches"] - st0["batches"]
+        batcher = {"value": n_thr * per / wall, "unit": UNIT, "client_threads": n_thr, "requests": n_thr * per,
+                   "p50_ms": float(np.percentile(lat_us, 50)) / 1e3, "p99_ms": float(np.percentile(lat_us, 99)) / 1e3,
+                   "mean_batch": (st1["requests"] - st0["requests"]) / max(1, nb),
+                   "unloaded_request_p50_ms": float(np.percentile(lat1, 50)) / 1e3,
+                   "unloaded_request_p99_ms": float(np.percentile(lat1, 99)) / 1e3,
+                   "answers_equal_direct_batch_call": same,
+                   "note": "prg_batcher_recommend: one request per host thread, coalesced into prg_recommend batches "
+                           "(host buffers, copies inside); latency = per request, queueing included"}
+
     shard_retries = None
     if world > 1 and protocol == "global":
         eng.sync()
@@ -533,6 +561,8 @@ def main():
                                  "rows*dim*4 (tf32 / ffma2 over the fp32 rows) + rows*4 row norms + queries; the fp32 "
                                  "matrix is only touched for the ~5 k survivors per query (exact re-score); see DESIGN.md 3.1"},
             "e2e": e2e}
+    if batcher is not None:
+        line["e2e_batcher"] = batcher
     if shard_retries is not None:
         line["shard_retry_queries"] = shard_retries
     if not args.no_cpu_baseline and world == 1:

@@ -201,6 +201,37 @@ int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model,
 int prg_recommend_from_keys(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k, int model,
                             const prg_dpp_params* p, uint32_t* out_row, double* out_score, int32_t* out_n, int mem);
 
+/* ---------------------------------------------------------------- cross-call request batcher */
+
+/* The reference handles ONE request per goroutine (service/user_recommend.go:46; the rank stage then fans out into
+ * BatchCount-sized RPCs, service/rank/rank_service.go:163-166, :264-289); the kernels serve up to 256 queries with one
+ * pass over the item matrix.  The batcher coalesces concurrent single-request calls into prg_recommend batches:
+ * it dispatches as soon as the GPU is free and a request waits (no added delay on an idle server); while a batch
+ * runs, the next one fills.  max_wait_us > 0 lets a non-full batch wait that long after its first request. */
+typedef struct prg_batcher prg_batcher;
+typedef struct prg_batcher_config {
+  int32_t max_batch;    /* 1..256 requests per prg_recommend call */
+  int32_t max_wait_us;  /* 0 = dispatch immediately when the GPU is free */
+  int32_t recall_k;     /* RecallConfs[].RecallCount */
+  int32_t model;        /* PRG_MODEL_* */
+  prg_dpp_params dpp;   /* shared by all requests of the scene */
+} prg_batcher_config;
+int prg_batcher_start(prg_handle* h, const prg_batcher_config* cfg, prg_batcher** out);
+/* Blocks the calling thread until its request has been served.  q: dim f32 (host); out_row / out_score: top_n
+ * entries, out_n: 1 entry (host).  Callable concurrently from any number of threads.  Results are those of
+ * prg_recommend for the same query, whatever batch it lands in. */
+int prg_batcher_recommend(prg_batcher* b, const float* q, uint32_t* out_row, double* out_score, int32_t* out_n);
+/* size_hist9: batches by size 1, 2, 3-4, 5-8, 9-16, 17-32, 33-64, 65-128, 129+ (any pointer may be NULL). */
+int prg_batcher_stats(prg_batcher* b, uint64_t* n_requests, uint64_t* n_batches, uint64_t* size_hist9);
+/* Closed-loop load generator (measurement aid; what a pool of request goroutines does): n_threads host threads each
+ * issue per_thread blocking prg_batcher_recommend calls, request i = thread*per_thread + j taking query i % n_pool of
+ * q_pool (n_pool x dim f32).  latency_us[n_threads*per_thread]: per-request latency; wall_s: the whole run;
+ * rows_out[n_pool x top_n] / n_out[n_pool]: the answers of requests 0..n_pool-1 (any output may be NULL). */
+int prg_batcher_drive(prg_batcher* b, const float* q_pool, int n_pool, int n_threads, int per_thread, float* latency_us,
+                      double* wall_s, uint32_t* rows_out, int32_t* n_out);
+/* Serves what is queued, makes late callers return PRG_ESTATE, joins the worker and frees the batcher. */
+void prg_batcher_stop(prg_batcher* b);
+
 /* ---------------------------------------------------------------- LOOKUP algorithm (algorithm/lookup.go:37-51) */
 
 /* present[i] != 0 -> out[i] = value[i], else 0.5.  Pure host code. */

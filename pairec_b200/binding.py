@@ -21,6 +21,7 @@ EXPORTS = [
     "prg_recall_topk", "prg_recall_local_keys", "prg_merge_keys", "prg_shard_sample_len", "prg_shard_sample",
     "prg_shard_candidates", "prg_shard_check", "prg_rank", "prg_sort_desc_host", "prg_sort_desc",
     "prg_dpp", "prg_ssd", "prg_recommend", "prg_recommend_from_keys", "prg_lookup", "prg_launch_count", "prg_recall_stats", "prg_timing",
+    "prg_batcher_start", "prg_batcher_recommend", "prg_batcher_stats", "prg_batcher_stop", "prg_batcher_drive",
 ]
 
 
@@ -52,6 +53,12 @@ class SsdParams(C.Structure):
                          min_score_percent)
 
 
+class BatcherConfig(C.Structure):
+    """prg_batcher_config."""
+    _fields_ = [("max_batch", C.c_int32), ("max_wait_us", C.c_int32), ("recall_k", C.c_int32), ("model", C.c_int32),
+                ("dpp", DppParams)]
+
+
 def lib_path():
     # PRG_LIB selects another build of the same library (kernel-variant experiments); never a different backend
     return os.environ.get("PRG_LIB") or os.path.join(_HERE, "libpairec_gpu.so")
@@ -71,6 +78,7 @@ def load_library():
         _lib.prg_stream.restype = C.c_void_p
         _lib.prg_launch_count.restype = C.c_uint64
         _lib.prg_destroy.restype = None
+        _lib.prg_batcher_stop.restype = None
         for name in EXPORTS:
             getattr(_lib, name)  # raises AttributeError if a declared symbol is not exported
     return _lib
@@ -332,3 +340,62 @@ def lookup(value, present):
     if rc != 0:
         raise PrgError(rc, lib.prg_last_error().decode())
     return out
+
+
+class Batcher:
+    """prg_batcher: coalesces concurrent single-request calls (one per host thread) into prg_recommend batches.
+    ctypes releases the GIL during the call, so Python threads behave like the reference's request goroutines."""
+
+    def __init__(self, engine, recall_k, model, dpp, max_batch=64, max_wait_us=0):
+        self._lib = engine._lib
+        self._eng = engine
+        self.dim = engine.dim
+        self.top_n = int(dpp.top_n)
+        cfg = BatcherConfig(max_batch, max_wait_us, recall_k, model, dpp)
+        self._b = C.c_void_p(0)
+        rc = self._lib.prg_batcher_start(engine._h, C.byref(cfg), C.byref(self._b))
+        if rc != 0:
+            raise PrgError(rc, self._lib.prg_last_error().decode())
+
+    def recommend(self, q):
+        """One request: q [dim] f32 -> (rows [n] u32, scores [n] f64).  Blocks until served."""
+        q = _np(q, np.float32)
+        assert q.shape == (self.dim,)
+        rows = np.empty(self.top_n, dtype=np.uint32)
+        scores = np.empty(self.top_n, dtype=np.float64)
+        n = C.c_int32(0)
+        rc = self._lib.prg_batcher_recommend(self._b, _ptr(q), _ptr(rows), _ptr(scores), C.byref(n))
+        if rc != 0:
+            raise PrgError(rc, self._lib.prg_last_error().decode())
+        return rows[:n.value], scores[:n.value]
+
+    def drive(self, q_pool, n_threads, per_thread):
+        """Closed-loop load from n_threads native client threads -> (latency_us [n], wall_s, rows [n_pool, top_n], n)."""
+        q_pool = _np(q_pool, np.float32)
+        n_pool = q_pool.shape[0]
+        lat = np.zeros(n_threads * per_thread, dtype=np.float32)
+        rows = np.full((n_pool, self.top_n), 0xFFFFFFFF, dtype=np.uint32)
+        n = np.zeros(n_pool, dtype=np.int32)
+        wall = C.c_double(0)
+        rc = self._lib.prg_batcher_drive(self._b, _ptr(q_pool), C.c_int(n_pool), C.c_int(n_threads), C.c_int(per_thread),
+                                         _ptr(lat), C.byref(wall), _ptr(rows), _ptr(n))
+        if rc != 0:
+            raise PrgError(rc, self._lib.prg_last_error().decode())
+        return lat, wall.value, rows, n
+
+    def stats(self):
+        nr, nb = C.c_uint64(0), C.c_uint64(0)
+        hist = (C.c_uint64 * 9)()
+        self._lib.prg_batcher_stats(self._b, C.byref(nr), C.byref(nb), hist)
+        return {"requests": nr.value, "batches": nb.value, "size_hist": list(hist)}
+
+    def close(self):
+        if self._b:
+            self._lib.prg_batcher_stop(self._b)
+            self._b = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

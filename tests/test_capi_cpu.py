@@ -62,3 +62,15 @@ def test_error_strings_are_thread_local_and_null_safe():
     assert lib.prg_sync(None) != 0
     assert b"null handle" in lib.prg_last_error()
     assert lib.prg_sort_desc_host(None, 5, None) != 0
+
+
+def test_batcher_entry_points_reject_bad_arguments_without_a_gpu():
+    from pairec_b200.binding import BatcherConfig, load_library
+    lib = load_library()
+    out = C.c_void_p(0)
+    cfg = BatcherConfig(64, 0, 1000, 0)
+    assert lib.prg_batcher_start(None, C.byref(cfg), C.byref(out)) != 0 and not out.value
+    n = C.c_int32(0)
+    assert lib.prg_batcher_recommend(None, None, None, None, C.byref(n)) != 0
+    assert lib.prg_batcher_stats(None, None, None, None) != 0
+    lib.prg_batcher_stop(None)   # no-op

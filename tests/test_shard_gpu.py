@@ -92,11 +92,13 @@ def _global_protocol(engs, Q, k, dev):
     return gathered, retry.cpu().numpy()
 
 
-@pytest.mark.parametrize("G,d,B,k", [(2, 64, 70, 300), (4, 64, 130, 1000), (2, 128, 9, 200)])
+# (8, 64, 512, 1000) is the shape of the 8-GPU bench: 64 requests per rank, two filter passes of 256 queries per shard
+@pytest.mark.parametrize("G,d,B,k", [(2, 64, 70, 300), (4, 64, 130, 1000), (2, 128, 9, 200), (8, 64, 512, 1000),
+                                     (8, 128, 130, 1000)])
 def test_global_threshold_protocol_matches_unsharded_oracle(oracle_lib, G, d, B, k):
     import torch
     from pairec_b200 import Engine
-    n = 1_200_000
+    n = max(1_200_000, 300_000 * G)   # every shard large enough to join the sampled protocol (>= 8 sample tiles)
     rng = np.random.default_rng(37 + G)
     E = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
     E[n // G:n // G + 300] = E[:300]              # ties across a shard boundary

@@ -5,7 +5,7 @@ set -u
 TAG=${1:-step}
 NCU="ncu --clock-control none --kernel-name-base demangled -k regex:prg::"
 timeout 600 $NCU --metrics gpu__time_duration.sum -s 47 -c 90 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launches_bench.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-batcher > gpurun_out/${TAG}_launches_bench.log 2>&1
 timeout 900 $NCU --set full --import-source on -s 47 -c 15 -f -o gpurun_out/${TAG}_full \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_full_bench.log 2>&1
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-batcher > gpurun_out/${TAG}_full_bench.log 2>&1
 ls -la gpurun_out/
