@@ -11,31 +11,37 @@
 // Policy (continuous batching): the worker dispatches as soon as the GPU is free and at least one request waits, so
 // an idle server adds no queueing delay; while a batch runs (≈ 1 ms) the next one fills.  `max_wait_us` > 0 lets a
 // batch that is not yet full wait that long (measured from its first request) for more requests to join.
-// Slots: two pinned host staging areas; a slot is FILLING (callers copy their query in), RUNNING (owned by the
-// worker), DRAINING (callers copy their results out) or FREE.
+// Requests wait in ONE FIFO queue (arrival order == service order); each caller sleeps on its own condition variable,
+// so finishing a batch wakes exactly its callers.
 #include "handle.h"
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <thread>
 
 using namespace prg;
 
 namespace {
-enum SlotState { SLOT_FREE = 0, SLOT_FILLING = 1, SLOT_RUNNING = 2, SLOT_DRAINING = 3 };
-
-struct Slot {
-  int state = SLOT_FREE;
-  int count = 0;     // requests in the slot
-  int readers = 0;   // callers that still have to copy their result out (DRAINING)
+// one blocked caller; lives on that caller's stack for the duration of prg_batcher_recommend
+struct Request {
+  const float* q;
+  uint32_t* out_row;
+  double* out_score;
+  int32_t* out_n;
   int rc = PRG_OK;
+  bool done = false;
   std::string err;
-  uint64_t ticket = 0;  // generation: a caller waits for ITS batch, not for whatever occupies the slot later
-  std::chrono::steady_clock::time_point first;
-  float* q = nullptr;          // pinned [max_batch][dim]
-  uint32_t* rows = nullptr;    // pinned [max_batch][top_n]
-  double* scores = nullptr;    // pinned [max_batch][top_n]
-  int32_t* n = nullptr;        // pinned [max_batch]
+  std::condition_variable cv;
+  std::chrono::steady_clock::time_point arrived;
+};
+
+struct Staging {  // pinned host buffers of one worker
+  float* q = nullptr;          // [max_batch][dim]
+  uint32_t* rows = nullptr;    // [max_batch][top_n]
+  double* scores = nullptr;    // [max_batch][top_n]
+  int32_t* n = nullptr;        // [max_batch]
+  void release() { cudaFreeHost(q); cudaFreeHost(rows); cudaFreeHost(scores); cudaFreeHost(n); }
 };
 }  // namespace
 
@@ -43,49 +49,71 @@ struct prg_batcher {
   prg_handle* h = nullptr;
   prg_batcher_config cfg{};
   uint32_t dim = 0;
-  std::mutex mu;
+  std::mutex mu;                       // queue, flags, statistics
+  std::mutex gpu_turn;                 // held by the worker that forms and runs the next batch
   std::condition_variable cv_worker;   // a request arrived / stop
-  std::condition_variable cv_callers;  // a batch finished / a slot became free
-  Slot slot[2];
-  int filling = -1;  // index of the FILLING slot, -1 if none
+  std::condition_variable cv_idle;     // inflight dropped to 0 after stop
+  std::deque<Request*> queue;          // FIFO: requests are served in arrival order
   bool stop = false;
   int inflight = 0;  // callers inside prg_batcher_recommend (prg_batcher_stop waits for them before freeing)
-  std::thread worker;
-  uint64_t n_requests = 0, n_batches = 0, next_ticket = 1;
+  std::thread worker[2];
+  Staging stage[2];
+  std::string last_err[2];
+  uint64_t n_requests = 0, n_batches = 0;
   uint64_t hist[9] = {0};  // batch sizes: 1, 2, 3-4, 5-8, 9-16, 17-32, 33-64, 65-128, 129+
 
-  void run();
+  void run(int w);
 };
 
-void prg_batcher::run() {
+// Two workers take turns: the one holding `gpu_turn` forms its batch at the last moment (when the previous batch has
+// left the GPU, so everything that arrived meanwhile joins), runs it, passes the turn on and only then hands out the
+// results — the other worker's batch is already on the GPU while the callers of this one are being woken.
+void prg_batcher::run(int w) {
   cudaSetDevice(h->device);
-  std::unique_lock<std::mutex> lk(mu);
+  Staging& st = stage[w];
+  const size_t T = (size_t)cfg.dpp.top_n;
+  std::vector<Request*> batch;
+  batch.reserve((size_t)cfg.max_batch);
   for (;;) {
-    cv_worker.wait(lk, [&] { return stop || (filling >= 0 && slot[filling].count > 0); });
-    if (stop && (filling < 0 || slot[filling].count == 0)) return;
-    Slot& s = slot[filling];
-    if (cfg.max_wait_us > 0 && s.count < cfg.max_batch && !stop) {
-      const auto deadline = s.first + std::chrono::microseconds(cfg.max_wait_us);
-      cv_worker.wait_until(lk, deadline, [&] { return stop || s.count >= cfg.max_batch; });
+    std::unique_lock<std::mutex> turn(gpu_turn);
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv_worker.wait(lk, [&] { return stop || !queue.empty(); });
+      if (queue.empty()) return;  // stop, and nothing left to serve
+      if (cfg.max_wait_us > 0 && (int)queue.size() < cfg.max_batch && !stop) {
+        const auto deadline = queue.front()->arrived + std::chrono::microseconds(cfg.max_wait_us);
+        cv_worker.wait_until(lk, deadline, [&] { return stop || (int)queue.size() >= cfg.max_batch; });
+      }
+      batch.clear();
+      while (!queue.empty() && (int)batch.size() < cfg.max_batch) {
+        batch.push_back(queue.front());
+        queue.pop_front();
+      }
     }
-    s.state = SLOT_RUNNING;
-    filling = -1;
-    const int B = s.count;
-    cv_callers.notify_all();  // callers waiting for a slot to fill may now open the other one
-    lk.unlock();
-    const int rc = prg_recommend(h, s.q, B, cfg.recall_k, cfg.model, &cfg.dpp, s.rows, s.scores, s.n, PRG_MEM_HOST);
-    std::string err = rc == PRG_OK ? std::string() : std::string(prg_last_error());
-    lk.lock();
-    s.rc = rc;
-    s.err = std::move(err);
-    s.readers = B;
-    s.state = SLOT_DRAINING;
+    const int B = (int)batch.size();
+    for (int i = 0; i < B; ++i) std::memcpy(st.q + (size_t)i * dim, batch[i]->q, (size_t)dim * 4);
+    const int rc = prg_recommend(h, st.q, B, cfg.recall_k, cfg.model, &cfg.dpp, st.rows, st.scores, st.n, PRG_MEM_HOST);
+    if (rc != PRG_OK) last_err[w] = prg_last_error();
+    turn.unlock();
+    if (rc == PRG_OK) {  // the callers are blocked: their output buffers are ours to fill
+      for (int i = 0; i < B; ++i) {
+        std::memcpy(batch[i]->out_row, st.rows + (size_t)i * T, T * 4);
+        std::memcpy(batch[i]->out_score, st.scores + (size_t)i * T, T * 8);
+        *batch[i]->out_n = st.n[i];
+      }
+    }
+    std::lock_guard<std::mutex> lk(mu);
     n_batches += 1;
     n_requests += (uint64_t)B;
     int bin = 0;
     for (int v = B - 1; v > 0 && bin < 8; v >>= 1) ++bin;
     hist[bin] += 1;
-    cv_callers.notify_all();
+    for (int i = 0; i < B; ++i) {  // notify under the lock: a Request may be destroyed as soon as its owner sees `done`
+      batch[i]->rc = rc;
+      if (rc != PRG_OK) batch[i]->err = last_err[w];
+      batch[i]->done = true;
+      batch[i]->cv.notify_one();
+    }
   }
 }
 
@@ -107,71 +135,36 @@ int prg_batcher_start(prg_handle* h, const prg_batcher_config* cfg, prg_batcher*
   b->cfg = *cfg;
   b->dim = dim;
   const size_t T = (size_t)cfg->dpp.top_n, M = (size_t)cfg->max_batch;
-  for (Slot& s : b->slot) {
+  for (Staging& s : b->stage) {
     cudaError_t e = cudaHostAlloc((void**)&s.q, M * dim * 4, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.rows, M * T * 4, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.scores, M * T * 8, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.n, M * 4, cudaHostAllocDefault);
     if (e != cudaSuccess) {
-      for (Slot& t : b->slot) { cudaFreeHost(t.q); cudaFreeHost(t.rows); cudaFreeHost(t.scores); cudaFreeHost(t.n); }
+      for (Staging& t : b->stage) t.release();
       delete b;
       return fail(PRG_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
     }
   }
-  b->worker = std::thread([b] { b->run(); });
+  for (int w = 0; w < 2; ++w) b->worker[w] = std::thread([b, w] { b->run(w); });
   *out = b;
   return PRG_OK;
 }
 
 int prg_batcher_recommend(prg_batcher* b, const float* q, uint32_t* out_row, double* out_score, int32_t* out_n) {
   if (!b || !q || !out_row || !out_score || !out_n) return fail(PRG_EINVAL, "null argument");
-  const size_t T = (size_t)b->cfg.dpp.top_n;
+  Request r;
+  r.q = q; r.out_row = out_row; r.out_score = out_score; r.out_n = out_n;
   std::unique_lock<std::mutex> lk(b->mu);
-  struct InFlight {  // constructed and destroyed under the lock
-    prg_batcher* b;
-    explicit InFlight(prg_batcher* bb) : b(bb) { ++b->inflight; }
-    ~InFlight() { if (--b->inflight == 0 && b->stop) b->cv_callers.notify_all(); }
-  } inflight_guard(b);
-  // 1. a place in the filling slot (open a FREE slot if there is none)
-  int si = -1;
-  for (;;) {
-    if (b->stop) return fail(PRG_ESTATE, "batcher stopped");
-    if (b->filling >= 0 && b->slot[b->filling].count < b->cfg.max_batch) { si = b->filling; break; }
-    if (b->filling < 0) {
-      for (int i = 0; i < 2; ++i)
-        if (b->slot[i].state == SLOT_FREE) { si = i; break; }
-      if (si >= 0) {
-        Slot& s = b->slot[si];
-        s.state = SLOT_FILLING;
-        s.count = 0;
-        s.ticket = b->next_ticket++;
-        s.first = std::chrono::steady_clock::now();
-        b->filling = si;
-        break;
-      }
-    }
-    b->cv_callers.wait(lk);
-  }
-  Slot& s = b->slot[si];
-  const int me = s.count++;
-  const uint64_t ticket = s.ticket;
-  std::memcpy(s.q + (size_t)me * b->dim, q, (size_t)b->dim * 4);  // short copy under the lock: 256-512 bytes
-  if (me == 0 || s.count >= b->cfg.max_batch) b->cv_worker.notify_one();
-  // 2. wait for this batch
-  b->cv_callers.wait(lk, [&] { return s.ticket == ticket && s.state == SLOT_DRAINING; });
-  const int rc = s.rc;
-  if (rc == PRG_OK) {
-    std::memcpy(out_row, s.rows + (size_t)me * T, T * 4);
-    std::memcpy(out_score, s.scores + (size_t)me * T, T * 8);
-    *out_n = s.n[me];
-  } else {
-    set_error("batched prg_recommend: " + s.err);
-  }
-  if (--s.readers == 0) {
-    s.state = SLOT_FREE;
-    s.count = 0;
-    b->cv_callers.notify_all();
-  }
+  if (b->stop) return fail(PRG_ESTATE, "batcher stopped");
+  ++b->inflight;
+  r.arrived = std::chrono::steady_clock::now();
+  b->queue.push_back(&r);
+  if (b->queue.size() == 1 || (int)b->queue.size() == b->cfg.max_batch) b->cv_worker.notify_all();
+  r.cv.wait(lk, [&] { return r.done; });
+  const int rc = r.rc;
+  if (rc != PRG_OK) set_error("batched prg_recommend: " + r.err);
+  if (--b->inflight == 0 && b->stop) b->cv_idle.notify_all();
   return rc;
 }
 
@@ -224,17 +217,17 @@ void prg_batcher_stop(prg_batcher* b) {
   if (!b) return;
   {
     std::lock_guard<std::mutex> g(b->mu);
-    b->stop = true;
+    b->stop = true;   // late callers leave with PRG_ESTATE; what is queued is still served
   }
   b->cv_worker.notify_all();
-  b->cv_callers.notify_all();
-  if (b->worker.joinable()) b->worker.join();
-  {  // callers of the last batch may still be copying their results out; late arrivals leave with PRG_ESTATE
+  for (auto& w : b->worker)
+    if (w.joinable()) w.join();
+  {
     std::unique_lock<std::mutex> lk(b->mu);
-    b->cv_callers.wait(lk, [&] { return b->inflight == 0; });
+    b->cv_idle.wait(lk, [&] { return b->inflight == 0; });
   }
   cudaSetDevice(b->h->device);
-  for (Slot& t : b->slot) { cudaFreeHost(t.q); cudaFreeHost(t.rows); cudaFreeHost(t.scores); cudaFreeHost(t.n); }
+  for (Staging& t : b->stage) t.release();
   delete b;
 }
 
