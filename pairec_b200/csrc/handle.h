@@ -67,6 +67,7 @@ struct prg_handle {
   prg::DevBuf topk_keys;    // B x k u64
   prg::DevBuf out_row, out_score, out_n;  // device staging for host calls
   prg::DevBuf flags;        // B i32 per-query status from select
+  prg::DevBuf topr_done;    // B i32: sample_topr_kernel served the query (else the generic select runs for it)
   int32_t last_fallback = 0;
   int32_t last_max_cand = 0;
   // deferred validation of the sampled recall (fused path): the per-query status is copied to pinned host memory

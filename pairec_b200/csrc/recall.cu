@@ -19,6 +19,7 @@
 // epilogue, so the only HBM traffic is the matrix itself (algorithmic bytes = rows*dim*4 per <=64-query block).
 #include "handle.h"
 #include "recall.h"
+#include <cstdlib>
 #include <vector>
 
 namespace prg {
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const SelectParams p) {
   extern __shared__ uint64_t sk[];  // MODE_TOPK: K2 keys
 
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (p.skip && p.skip[q]) return;
   const uint64_t* keys = p.keys + (size_t)q * p.stride;
   uint32_t m = p.counts ? p.counts[q] : p.fixed_m;
   bool overflow = m > p.cap;
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(1024, 1) select_kth_kernel(const SelectParams 
   __shared__ uint32_t s_want, s_bucket, s_fill;
   extern __shared__ uint64_t sk[];  // kKthCap keys
   const int q = blockIdx.x, tid = threadIdx.x;
+  if (p.skip && p.skip[q]) return;
   const uint64_t* keys = p.keys + (size_t)q * p.stride;
   const uint32_t m = p.fixed_m;
   uint64_t prefix = 0, mask = 0;
@@ -489,26 +492,52 @@ __global__ void __launch_bounds__(1024, 1) select_kth_kernel(const SelectParams 
 // Rows are fetched COALESCED (a half-warp reads one 256-B row per instruction, 16 x 16 B) into a padded shared-memory
 // tile and each lane then walks its own row from there: with one thread per row every 16-B load touched 32 different
 // lines and the LSU, not DRAM, bounded the kernel (ncu r5: 55 us for ~290 k rows = 9 GB/s per SM, mio/lg throttle).
+//
+// One warp walks a GROUP of `seg_group` consecutive segments of one query as one flattened list: a row shard of a
+// G-GPU run sees G times the queries with 1/G of the survivors each, and a warp per (segment, query) then holds ~4
+// rows — 28 idle lanes and 75 k tiny CTAs (71 us at G = 8 against 25 us for the same number of rows at G = 1).
 template <int DIM>
 __global__ void __launch_bounds__(32) rescore_kernel(const uint32_t* __restrict__ seg_rows, const uint32_t* __restrict__ seg_cnt,
-                                                     uint32_t seg_cap, const float* __restrict__ E, const float* __restrict__ Q,
+                                                     uint32_t n_seg, uint32_t seg_cap, uint32_t seg_group,
+                                                     const float* __restrict__ E, const float* __restrict__ Q,
                                                      uint64_t row_base, uint64_t* __restrict__ seg_keys) {
   constexpr int F4 = DIM / 4;            // 16-B pieces per row
   constexpr int RPI = 32 / F4;           // rows fetched per load instruction (2 at dim 64, 1 at dim 128)
   constexpr int PITCH = DIM + 4;         // floats; keeps both the row-wise stores and the lane-per-row loads conflict free
   __shared__ __align__(16) float tile[32 * PITCH];
   __shared__ float qv[DIM];
-  const uint32_t sgi = blockIdx.x, q = blockIdx.y, n_seg = gridDim.x, lane = threadIdx.x;
-  uint32_t c = seg_cnt[(size_t)q * n_seg + sgi];
-  if (c == 0) return;
-  if (c > seg_cap) c = seg_cap;
-  const uint32_t* src = seg_rows + ((size_t)q * n_seg + sgi) * seg_cap;
-  uint64_t* dst = seg_keys + ((size_t)q * n_seg + sgi) * seg_cap;
+  const uint32_t q = blockIdx.y, lane = threadIdx.x;
+  const uint32_t s0 = blockIdx.x * seg_group;             // first segment of this warp's group (seg_group <= 32)
+  // lane j < seg_group: length of segment s0 + j; inclusive scan -> the flattened list's offsets
+  uint32_t c = 0;
+  if (lane < seg_group && s0 + lane < n_seg) {
+    c = seg_cnt[(size_t)q * n_seg + s0 + lane];
+    if (c > seg_cap) c = seg_cap;
+  }
+  uint32_t incl = c;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= (uint32_t)off) incl += v;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  const size_t seg0 = ((size_t)q * n_seg + s0) * seg_cap;
+  const uint32_t* src = seg_rows + seg0;
+  uint64_t* dst = seg_keys + seg0;
   for (uint32_t d = lane; d < DIM; d += 32) qv[d] = Q[(size_t)q * DIM + d];
   const uint32_t sub = lane / F4, piece = lane % F4;
-  for (uint32_t base = 0; base < c; base += 32) {
-    const uint32_t n = c - base < 32 ? c - base : 32;
-    const uint32_t my_row = lane < n ? src[base + lane] : 0u;
+  for (uint32_t base = 0; base < total; base += 32) {
+    const uint32_t n = total - base < 32 ? total - base : 32;
+    // item base + lane lives in segment sg = #{j : incl_j <= item}, at position item - excl_sg
+    const uint32_t item = base + lane;
+    uint32_t sg = 0, excl = 0;
+    for (uint32_t j = 0; j < seg_group; ++j) {
+      const uint32_t e = __shfl_sync(0xffffffffu, incl, j);
+      if (e <= item) { sg = j + 1; excl = e; }
+    }
+    const uint32_t slot = sg * seg_cap + (item - excl);   // offset from the group's first segment
+    const uint32_t my_row = lane < n ? src[slot] : 0u;
     __syncwarp();
     float4 xv[32 / RPI];
 #pragma unroll
@@ -533,7 +562,7 @@ __global__ void __launch_bounds__(32) rescore_kernel(const uint32_t* __restrict_
         acc = __fmaf_rn(v.z, qv[4 * d4 + 2], acc);
         acc = __fmaf_rn(v.w, qv[4 * d4 + 3], acc);
       }
-      dst[base + lane] = make_key(acc, my_row);
+      dst[slot] = make_key(acc, my_row);
     }
   }
 }
@@ -560,7 +589,10 @@ struct RefineParams {
   uint32_t* max_count;
 };
 
-__global__ void __launch_bounds__(1024, 1) refine_select_kernel(const RefineParams p) {
+// NT threads per CTA: 1024 for the single-GPU shape (64 queries x ~4.6 k survivors, one CTA per SM), 256 for row shards
+// (G times the queries, 1/G of the survivors each: several CTAs per SM instead of 3.5 waves of one).
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) refine_select_kernel(const RefineParams p) {
   extern __shared__ uint64_t rs_keys[];          // [cap] exact keys, then [sort_cap] sort buffer
   __shared__ uint32_t seg_off[520];
   __shared__ uint32_t hist[256];
@@ -574,7 +606,7 @@ __global__ void __launch_bounds__(1024, 1) refine_select_kernel(const RefinePara
   // ---- 1. segment offsets
   if (tid == 0) { s_ov = 0; s_or = 0ull; s_fill = 0; }
   __syncthreads();
-  for (uint32_t sgi = tid; sgi < p.n_seg; sgi += 1024) {
+  for (uint32_t sgi = tid; sgi < p.n_seg; sgi += NT) {
     uint32_t c = p.seg_counts[(size_t)q * p.n_seg + sgi];
     if (c > p.seg_cap) { c = p.seg_cap; s_ov = 1; }
     seg_off[sgi + 1] = c;
@@ -606,7 +638,7 @@ __global__ void __launch_bounds__(1024, 1) refine_select_kernel(const RefinePara
   // ---- 2. pack the exact keys into shared memory
   unsigned long long my_or = 0ull;
   uint64_t key0 = 0ull;
-  for (uint32_t i = tid; i < m; i += 1024) {
+  for (uint32_t i = tid; i < m; i += NT) {
     uint32_t lo = 0, hi = p.n_seg;       // last segment with seg_off[s] <= i
     while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (seg_off[mid] <= i) lo = mid; else hi = mid; }
     const uint64_t key = p.seg_keys[((size_t)q * p.n_seg + lo) * p.seg_cap + (i - seg_off[lo])];
@@ -635,7 +667,7 @@ __global__ void __launch_bounds__(1024, 1) refine_select_kernel(const RefinePara
       const uint32_t dmask = (1u << (top - shift)) - 1u;
       if (tid < 256) hist[tid] = 0;
       __syncthreads();
-      for (uint32_t i = tid; i < m; i += 1024) {
+      for (uint32_t i = tid; i < m; i += NT) {
         const uint64_t key = keys[i];
         const bool in = (key & mask) == prefix;
         const uint32_t dg = (uint32_t)(key >> shift) & dmask;
@@ -684,9 +716,9 @@ __global__ void __launch_bounds__(1024, 1) refine_select_kernel(const RefinePara
     // every key shares the bits at and above top0, so "in the bucket or above it" is a plain comparison
     lo_key = (top0 >= 64 ? 0ull : ((keys[0] >> top0) << top0)) | prefix;
   }
-  for (uint32_t i = tid; i < p.sort_cap; i += 1024) sk[i] = 0ull;
+  for (uint32_t i = tid; i < p.sort_cap; i += NT) sk[i] = 0ull;
   __syncthreads();
-  for (uint32_t i = tid; i < m; i += 1024) {
+  for (uint32_t i = tid; i < m; i += NT) {
     const uint64_t key = keys[i];
     if (key >= lo_key) {
       const uint32_t pos = atomicAdd(&s_fill, 1u);
@@ -700,7 +732,7 @@ __global__ void __launch_bounds__(1024, 1) refine_select_kernel(const RefinePara
   // ---- 4. bitonic sort, descending
   for (uint32_t size = 2; size <= K2; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-      for (uint32_t i = tid; i < (K2 >> 1); i += 1024) {
+      for (uint32_t i = tid; i < (K2 >> 1); i += NT) {
         const uint32_t pos = 2 * i - (i & (stride - 1));
         const uint64_t a = sk[pos], b = sk[pos + stride];
         const bool desc = (pos & size) == 0;
@@ -710,7 +742,7 @@ __global__ void __launch_bounds__(1024, 1) refine_select_kernel(const RefinePara
     }
   }
   const uint32_t n_out = m < k ? m : k;
-  for (uint32_t i = tid; i < (uint32_t)p.k_out; i += 1024)
+  for (uint32_t i = tid; i < (uint32_t)p.k_out; i += NT)
     p.out_keys[(size_t)q * p.k_out + i] = (i < n_out) ? sk[i] : 0ull;
   if (tid == 0) {
     int fl = overflow ? 1 : (n_out < p.expect ? 2 : 0);
@@ -776,6 +808,156 @@ static int scan(prg_handle* h, int mode, const ScanParams& p) {
   return fail(PRG_EUNSUPPORTED, "item matrix dim must be 64 or 128");
 }
 
+// The r best keys of a sample (r ~ 32 of 10 k - 80 k keys), sorted — or just the r-th — in two passes over the keys:
+//   1. every thread takes the maximum of its strided share; T0 = the r-th largest of the NT maxima (rank counting in
+//      shared memory).  The maxima are distinct keys, so at least r keys reach T0 and the r-th largest key is >= T0;
+//   2. the keys >= T0 (r plus a handful when the large keys are spread over the threads) are collected in shared
+//      memory, sorted, and the first r written out.
+// If more than kTopRCap keys reach T0 (the large keys sit in a few threads' shares) the query is left to the generic
+// select (done[q] = 0).  The generic kernels cost 29 us (KTH, 64 x 78 k keys) and 73 us (TOPK, 512 x 9.7 k keys).
+constexpr uint32_t kTopRCap = 2048;
+struct TopRParams {
+  const uint64_t* keys;   // [q][stride]
+  uint64_t stride;
+  uint32_t m, r;
+  uint64_t* out_keys;     // nullable: [q][r] sorted descending, 0-padded
+  uint64_t* tau;          // nullable: [q] the r-th largest (0 if fewer than r valid keys)
+  int32_t* done;          // [q]
+};
+template <int NT>
+__global__ void __launch_bounds__(NT) sample_topr_kernel(const TopRParams p) {
+  __shared__ uint64_t mx[256];
+  __shared__ uint64_t cand[kTopRCap];
+  __shared__ uint64_t s_t0;
+  __shared__ uint32_t s_cnt;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const uint64_t* keys = p.keys + (size_t)q * p.stride;
+  const ulonglong2* keys2 = reinterpret_cast<const ulonglong2*>(keys);   // rows of the sample are 2 KiB multiples
+  const uint32_t m2 = p.m >> 1;
+  if (tid == 0) { s_cnt = 0; s_t0 = 0ull; }
+  uint64_t best = 0ull;
+  constexpr int U = 8;   // independent 16-B loads in flight per thread (64 CTAs x 78 k keys: latency-, not bandwidth-bound)
+  {
+    uint32_t i = tid;
+    for (; i + (U - 1) * NT < m2; i += U * NT) {
+      ulonglong2 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = keys2[i + u * NT];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint64_t a = v[u].x > v[u].y ? v[u].x : v[u].y;
+        best = a > best ? a : best;
+      }
+    }
+    for (; i < m2; i += NT) {
+      const ulonglong2 v = keys2[i];
+      const uint64_t a = v.x > v.y ? v.x : v.y;
+      best = a > best ? a : best;
+    }
+  }
+  if ((p.m & 1u) && tid == 0) { const uint64_t a = keys[p.m - 1]; best = a > best ? a : best; }
+  // 256 group maxima (groups of NT/256 adjacent threads): ranking NT values against each other is O(NT^2) — with 1024
+  // threads almost every warp holds one of the larger maxima and walks all 1024 (33 us)
+  constexpr int GS = NT / 256;
+  uint64_t gbest = best;
+#pragma unroll
+  for (int off = 1; off < GS; off <<= 1) {
+    const uint64_t o = __shfl_xor_sync(0xffffffffu, gbest, off);
+    gbest = o > gbest ? o : gbest;
+  }
+  if ((tid & (GS - 1)) == 0) mx[tid / GS] = gbest;
+  __syncthreads();
+  if (tid < 256) {
+    const uint64_t mine = mx[tid];
+    uint32_t rank = 0;   // only a maximum that can be among the r largest needs its exact rank: stop counting at r
+    for (int u0 = 0; u0 < 256 && rank < p.r; u0 += 8) {
+#pragma unroll
+      for (int u = u0; u < u0 + 8; ++u) {
+        const uint64_t v = mx[u];
+        rank += (v > mine || (v == mine && u < tid)) ? 1u : 0u;
+      }
+    }
+    if (rank == p.r - 1) s_t0 = mine;
+  }
+  __syncthreads();
+  const uint64_t lim = s_t0 ? s_t0 : 1ull;
+  auto take = [&](uint64_t key) {
+    if (key >= lim) { const uint32_t pos = atomicAdd(&s_cnt, 1u); if (pos < kTopRCap) cand[pos] = key; }
+  };
+  {
+    uint32_t i = tid;
+    for (; i + (U - 1) * NT < m2; i += U * NT) {
+      ulonglong2 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = keys2[i + u * NT];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { take(v[u].x); take(v[u].y); }
+    }
+    for (; i < m2; i += NT) { const ulonglong2 v = keys2[i]; take(v.x); take(v.y); }
+  }
+  if ((p.m & 1u) && tid == 0) {
+    const uint64_t a = keys[p.m - 1];
+    if (a >= lim) { const uint32_t pos = atomicAdd(&s_cnt, 1u); if (pos < kTopRCap) cand[pos] = a; }
+  }
+  __syncthreads();
+  const uint32_t c = s_cnt;
+  if (c > kTopRCap) { if (tid == 0) p.done[q] = 0; return; }
+  uint32_t K2 = 32;
+  while (K2 < c) K2 <<= 1;
+  for (uint32_t i = c + tid; i < K2; i += NT) cand[i] = 0ull;
+  __syncthreads();
+  for (uint32_t size = 2; size <= K2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t i = tid; i < (K2 >> 1); i += NT) {
+        const uint32_t pos = 2 * i - (i & (stride - 1));
+        const uint64_t a = cand[pos], b = cand[pos + stride];
+        if ((a < b) == ((pos & size) == 0)) { cand[pos] = b; cand[pos + stride] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (p.out_keys)
+    for (uint32_t i = tid; i < p.r; i += NT) p.out_keys[(size_t)q * p.r + i] = i < c ? cand[i] : 0ull;
+  if (tid == 0) {
+    if (p.tau) p.tau[q] = c >= p.r ? cand[p.r - 1] : 0ull;
+    p.done[q] = 1;
+  }
+}
+
+// Exact re-score of the filter survivors of nq queries.  `per_seg` = expected survivors per (segment, query): a warp takes
+// as many consecutive segments as give it about two chunks of 32 rows.
+static int launch_rescore(prg_handle* h, const float* q_dev, int nq, uint32_t n_seg, uint32_t seg_cap, double per_seg) {
+  StageScope span(h, ST_SELECT);
+  uint32_t group = 1;
+  while (group < 32 && per_seg * group < 24.0) group <<= 1;
+  const dim3 grid((n_seg + group - 1) / group, (unsigned)nq);
+  if (h->E_dim == 64)
+    rescore_kernel<64><<<grid, 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p, (const uint32_t*)h->cand_cnt.p, n_seg, seg_cap,
+                                                   group, h->E, q_dev, h->E_row_base, (uint64_t*)h->seg_keys.p);
+  else
+    rescore_kernel<128><<<grid, 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p, (const uint32_t*)h->cand_cnt.p, n_seg, seg_cap,
+                                                    group, h->E, q_dev, h->E_row_base, (uint64_t*)h->seg_keys.p);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+// Top-k of the exact keys, one CTA per query: 1024 threads when every query gets an SM of its own, 256 (several CTAs
+// per SM) when there are more queries than SMs.
+static int launch_refine(prg_handle* h, const RefineParams& rp, int nq, size_t smem) {
+  StageScope span(h, ST_SELECT);
+  if (nq > h->sm_count && smem <= 100 * 1024) {
+    PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    refine_select_kernel<256><<<nq, 256, smem, h->stream>>>(rp);
+  } else {
+    PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    refine_select_kernel<1024><<<nq, 1024, smem, h->stream>>>(rp);
+  }
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
 static int launch_select(prg_handle* h, int mode, const SelectParams& p, int nq) {
   StageScope span(h, ST_SELECT);
   if (mode == SEL_KTH) {
@@ -790,6 +972,32 @@ static int launch_select(prg_handle* h, int mode, const SelectParams& p, int nq)
   return PRG_OK;
 }
 
+// Threshold / best-r selection over the sample: the two-pass kernel first, the generic select only for the queries it
+// declined (none on well-mixed data).  mode SEL_KTH writes st.tau, SEL_TOPK st.out_keys (k_out == k == r).
+static int launch_sample_select(prg_handle* h, int mode, SelectParams st, int nq) {
+  const uint32_t r = (uint32_t)st.k;
+  if (r == 0 || r > 256 || (st.stride & 1ull) || (reinterpret_cast<uintptr_t>(st.keys) & 15))
+    return launch_select(h, mode, st, nq);
+  PRG_TRY(h->topr_done.ensure((size_t)nq * 4));
+  {
+    StageScope span(h, ST_SELECT);
+    TopRParams tp{};
+    tp.keys = st.keys; tp.stride = st.stride; tp.m = st.fixed_m; tp.r = r;
+    tp.out_keys = mode == SEL_TOPK ? st.out_keys : nullptr;
+    tp.tau = mode == SEL_KTH ? st.tau : nullptr;
+    tp.done = (int32_t*)h->topr_done.p;
+    static const int force_nt = getenv("PRG_TOPR_NT") ? atoi(getenv("PRG_TOPR_NT")) : 0;   // experiments only
+    const int nt = force_nt ? force_nt : (((uint64_t)st.fixed_m >= 32768 && nq <= 2 * h->sm_count) ? 1024 : 256);
+    if (nt == 1024) sample_topr_kernel<1024><<<nq, 1024, 0, h->stream>>>(tp);
+    else if (nt == 512) sample_topr_kernel<512><<<nq, 512, 0, h->stream>>>(tp);
+    else sample_topr_kernel<256><<<nq, 256, 0, h->stream>>>(tp);
+    PRG_CUDA(cudaGetLastError());
+    count_launch(h);
+  }
+  st.skip = (const int32_t*)h->topr_done.p;
+  return launch_select(h, mode, st, nq);
+}
+
 // Scores of the strided tile sample for B queries -> h->sample_keys [B][slots].  With the bf16 filter index the
 // tensor-core kernel scores it (approximate keys: tau is only a pruning hint); otherwise the exact FFMA2 kernel, one
 // launch with one grid row per block of 64 queries.
@@ -800,14 +1008,10 @@ static int score_sample(prg_handle* h, const float* q_dev, int B, uint32_t sampl
   sp.n_tiles = sample_tiles; sp.tile_stride = tile_stride;
   sp.dense_stride = slots;
   if (use_tc && scan_tc_dense_available(h)) {
-    const int pass_q = scan_tc_max_queries(h);
     sp.row_norm = (const float*)h->row_norm.p;   // the producer copies the tile's norms although DENSE does not use them
-    for (int q0 = 0; q0 < B; q0 += pass_q) {
-      sp.Q = q_dev + (size_t)q0 * h->E_dim; sp.nq = (B - q0 < pass_q) ? (B - q0) : pass_q;
-      sp.dense = (uint64_t*)h->sample_keys.p + (size_t)q0 * slots;
-      PRG_TRY(launch_scan_tc_dense(h, sp));
-    }
-    return PRG_OK;
+    sp.Q = q_dev; sp.nq = B;
+    sp.dense = (uint64_t*)h->sample_keys.p;
+    return launch_scan_tc_dense(h, sp);          // one launch: grid = sample tiles x blocks of 64 queries
   }
   sp.Q = q_dev; sp.nq = B; sp.q_blocks = (B + kQB - 1) / kQB;
   sp.dense = (uint64_t*)h->sample_keys.p;
@@ -891,7 +1095,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   SelectParams st{};
   st.keys = (const uint64_t*)h->sample_keys.p; st.stride = slots; st.fixed_m = (uint32_t)slots;
   st.cap = st.fixed_m; st.k = (int)r_rank; st.tau = (uint64_t*)h->tau.p;
-  PRG_TRY(launch_select(h, SEL_KTH, st, B));
+  PRG_TRY(launch_sample_select(h, SEL_KTH, st, B));
   // 3. full pass with the threshold test fused into the tile epilogue
   uint32_t* max_cnt = (uint32_t*)h->cand_cnt.p + QT * n_seg;
   PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
@@ -912,36 +1116,19 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   while (k_pow2 < (uint32_t)k) k_pow2 <<= 1;
   const uint32_t sort_cap = (k_pow2 - (uint32_t)k >= 16) ? k_pow2 : 2 * k_pow2;
   const size_t refine_smem = ((size_t)cand_cap + sort_cap) * 8;
-  auto launch_rescore = [&]() -> int {   // exact re-score of the tensor-core survivors, all queries at once
-    StageScope span(h, ST_SELECT);
-    if (dim == 64)
-      rescore_kernel<64><<<dim3(n_seg, (unsigned)B), 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
-                                                                         (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, q_dev,
-                                                                         h->E_row_base, (uint64_t*)h->seg_keys.p);
-    else
-      rescore_kernel<128><<<dim3(n_seg, (unsigned)B), 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
-                                                                          (const uint32_t*)h->cand_cnt.p, seg_cap, h->E, q_dev,
-                                                                          h->E_row_base, (uint64_t*)h->seg_keys.p);
-    PRG_CUDA(cudaGetLastError());
-    count_launch(h);
-    return PRG_OK;
-  };
+  const double per_seg = ((double)r_rank / f) / n_seg;   // expected survivors per (segment, query)
   if (use_tc && n_seg <= 512 && refine_smem <= 200 * 1024) {
     // 4. exact re-score, then the top-k of the exact keys in shared memory
-    PRG_TRY(launch_rescore());
+    PRG_TRY(launch_rescore(h, q_dev, B, n_seg, seg_cap, per_seg));
     RefineParams rp{};
     rp.seg_keys = (const uint64_t*)h->seg_keys.p; rp.seg_counts = (const uint32_t*)h->cand_cnt.p;
     rp.n_seg = n_seg; rp.seg_cap = seg_cap; rp.cap = cand_cap;
     rp.tau_check = (const uint64_t*)h->tau.p;
     rp.k = k; rp.k_out = k; rp.expect = (uint32_t)((uint64_t)k < h->E_rows ? (uint64_t)k : h->E_rows);
     rp.sort_cap = sort_cap; rp.out_keys = keys_out; rp.flags = (int32_t*)h->flags.p; rp.max_count = max_cnt;
-    StageScope span(h, ST_SELECT);
-    PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
-    refine_select_kernel<<<B, 1024, refine_smem, h->stream>>>(rp);
-    PRG_CUDA(cudaGetLastError());
-    count_launch(h);
+    PRG_TRY(launch_refine(h, rp, B, refine_smem));
   } else {
-  if (use_tc) PRG_TRY(launch_rescore());   // large k: the keys do not fit on chip
+  if (use_tc) PRG_TRY(launch_rescore(h, q_dev, B, n_seg, seg_cap, per_seg));   // large k: the keys do not fit on chip
   // 4. exact top-k of the candidates
   SelectParams se{};
   se.keys = (const uint64_t*)h->seg_keys.p; se.stride = cand_cap; se.counts = nullptr;
@@ -1102,7 +1289,7 @@ int recall_shard_sample_device(prg_handle* h, const float* q_dev, int Bg, int k,
   SelectParams st{};
   st.keys = (const uint64_t*)h->sample_keys.p; st.stride = pl.slots; st.fixed_m = (uint32_t)pl.slots;
   st.cap = st.fixed_m; st.k = (int)pl.r; st.k_out = (int)pl.r; st.out_keys = out;
-  return launch_select(h, SEL_TOPK, st, Bg);
+  return launch_sample_select(h, SEL_TOPK, st, Bg);
 }
 
 // tau[q] = r-th largest of the G*r gathered sample keys (0 = no threshold when fewer than r are valid)
@@ -1189,26 +1376,14 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
     PRG_TRY(launch_scan_tc(h, sc));
   }
   {
-    StageScope span(h, ST_SELECT);
-    if (dim == 64)
-      rescore_kernel<64><<<dim3(pl.n_seg, (unsigned)Bg), 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
-                                                                            (const uint32_t*)h->cand_cnt.p, pl.seg_cap, h->E,
-                                                                            q_dev, h->E_row_base, (uint64_t*)h->seg_keys.p);
-    else
-      rescore_kernel<128><<<dim3(pl.n_seg, (unsigned)Bg), 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p,
-                                                                             (const uint32_t*)h->cand_cnt.p, pl.seg_cap, h->E,
-                                                                             q_dev, h->E_row_base, (uint64_t*)h->seg_keys.p);
-    PRG_CUDA(cudaGetLastError());
-    count_launch(h);
+    PRG_TRY(launch_rescore(h, q_dev, Bg, pl.n_seg, pl.seg_cap, (double)pl.r * kShardSampleStride / (double)G / pl.n_seg));
     RefineParams rp{};
     rp.seg_keys = (const uint64_t*)h->seg_keys.p; rp.seg_counts = (const uint32_t*)h->cand_cnt.p;
     rp.n_seg = pl.n_seg; rp.seg_cap = pl.seg_cap; rp.cap = pl.cand_cap;
     rp.k = k; rp.k_out = k; rp.expect = 0; rp.sort_cap = pl.sort_cap;
     rp.out_keys = out; rp.flags = (int32_t*)h->flags.p; rp.max_count = max_cnt;
-    PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.refine_smem));
-    refine_select_kernel<<<Bg, 1024, pl.refine_smem, h->stream>>>(rp);
-    PRG_CUDA(cudaGetLastError());
-    count_launch(h);
+    PRG_TRY(launch_refine(h, rp, Bg, pl.refine_smem));
+    StageScope span(h, ST_SELECT);
     shard_status_kernel<<<(Bg + 255) / 256, 256, 0, h->stream>>>((const int32_t*)h->flags.p, Bg, status);
     PRG_CUDA(cudaGetLastError());
     count_launch(h);
@@ -1218,30 +1393,34 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
 
 // phase 3 check, identical on every rank: gathered = G blocks of [Bg*k keys | Bg status words]; a query needs the exact
 // protocol if a shard reported an overflow or fewer than k gathered keys reach its tau.  retry[0] |= 1, retry[1] += count.
-__global__ void shard_check_kernel(const uint64_t* __restrict__ gathered, int G, int Bg, int k, const uint64_t* __restrict__ tau,
-                                   int32_t* __restrict__ retry) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) shard_check_kernel(const uint64_t* __restrict__ gathered, int G, int Bg, int k,
+                                                          const uint64_t* __restrict__ tau, int32_t* __restrict__ retry) {
+  // one WARP per query, lane g walks shard g's list: the G binary searches (dependent loads through L2) run side by side
+  // instead of one after the other in a single thread (46 us -> a few us at G = 8, Bg = 512)
+  const int q = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (q >= Bg) return;
   const size_t blk = (size_t)Bg * k + Bg;
   const uint64_t t = tau[q];
+  const uint64_t lim = t ? t : 1ull;
   bool bad = false;
   uint32_t reach = 0;
-  for (int g = 0; g < G; ++g) {
+  for (int g = lane; g < G; g += 32) {
     const uint64_t* base = gathered + (size_t)g * blk;
     if (base[(size_t)Bg * k + q] != 0ull) bad = true;
     const uint64_t* list = base + (size_t)q * k;   // sorted descending, 0-padded: count keys >= max(t, 1)
-    const uint64_t lim = t ? t : 1ull;
     int lo = 0, hi = k;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (list[mid] >= lim) lo = mid + 1; else hi = mid; }
     reach += (uint32_t)lo;
   }
+  reach = __reduce_add_sync(0xffffffffu, reach);
+  bad = __any_sync(0xffffffffu, bad);
   if (t != 0ull && reach < (uint32_t)k) bad = true;
-  if (bad) { atomicOr(&retry[0], 1); atomicAdd(&retry[1], 1); }
+  if (bad && lane == 0) { atomicOr(&retry[0], 1); atomicAdd(&retry[1], 1); }
 }
 
 int shard_check_device(prg_handle* h, const uint64_t* gathered, int G, int Bg, int k, int32_t* retry_dev) {
   if (!h->tau.p) return fail(PRG_ESTATE, "prg_shard_candidates has not run on this handle");
-  shard_check_kernel<<<(Bg + 127) / 128, 128, 0, h->stream>>>(gathered, G, Bg, k, (const uint64_t*)h->tau.p, retry_dev);
+  shard_check_kernel<<<(Bg + 3) / 4, 128, 0, h->stream>>>(gathered, G, Bg, k, (const uint64_t*)h->tau.p, retry_dev);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;

@@ -67,6 +67,7 @@ struct SelectParams {
   uint64_t* tau;           // MODE_KTH: [q] the k-th largest key (0 if fewer than k valid keys)
   int32_t* flags;          // nullable; 0 ok, 1 overflow, 2 underflow
   uint32_t* max_count;     // nullable: atomicMax of the list lengths seen
+  const int32_t* skip;     // nullable: query q is skipped when skip[q] != 0 (already served by sample_topr_kernel)
 };
 enum { SEL_TOPK = 0, SEL_KTH = 1 };
 

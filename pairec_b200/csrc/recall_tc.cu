@@ -84,8 +84,19 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {  // SASS FMN
 // sample does not need exact scores, and the tensor cores score it in a fraction of the FFMA2 kernel's time.
 template <int DIM, int NQB, bool BF, int MODE = SCAN_THRESH>
 __global__ void __launch_bounds__(kTcThreads, 1)
-recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p) {
+recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p_in) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr bool kDenseMode = MODE == SCAN_DENSE;
+  // DENSE launches carry one grid row per block of 64 queries (the sample is a few dozen tiles: tiles x query blocks
+  // CTAs fill the machine, tiles alone do not); grid row y sees its own slice of the queries and of the output
+  ScanParams p_adj = p_in;
+  if constexpr (kDenseMode) {
+    const int y = (int)blockIdx.y;
+    p_adj.Q = p_in.Q + (size_t)y * kQB * DIM;
+    p_adj.nq = p_in.nq - y * kQB < kQB ? p_in.nq - y * kQB : kQB;
+    p_adj.dense = p_in.dense + (size_t)y * kQB * p_in.dense_stride;
+  }
+  const ScanParams& p = kDenseMode ? p_adj : p_in;
   constexpr int KH = BF ? 1 : DIM / 64;                    // stages per tile
   constexpr int kTcStages = tc_stages<DIM, NQB, BF>();
   constexpr int kStageB = tc_stage_bytes<DIM, BF>();
@@ -472,16 +483,18 @@ static int launch_tc(prg_handle* h, const ScanParams& p) {
   return PRG_OK;
 }
 
-// sample scoring on the tensor cores (bf16 index): nq <= 256 queries at dim 64, <= 64 at dim 128, per launch
-template <int DIM, int NQB>
+// sample scoring on the tensor cores (bf16 index): any number of queries per launch, one grid row per block of 64
+template <int DIM>
 static int launch_tc_dense(prg_handle* h, const ScanParams& p) {
-  const size_t smem = scan_tc_smem_bytes<DIM, NQB, true>();
-  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM, NQB, true, SCAN_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = scan_tc_smem_bytes<DIM, 1, true>();
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM, 1, true, SCAN_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem));
-  if (p.n_tiles == 0) return PRG_OK;
+  if (p.n_tiles == 0 || p.nq <= 0) return PRG_OK;
   StageScope span(h, ST_SCAN_DENSE);
-  const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
-  recall_scan_tc_kernel<DIM, NQB, true, SCAN_DENSE><<<grid, kTcThreads, smem, h->stream>>>(h->E16_map, p);
+  const unsigned gx = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
+  const unsigned gy = (unsigned)((p.nq + kQB - 1) / kQB);
+  if (gy > 65535u) return fail(PRG_EINVAL, "launch_scan_tc_dense: too many queries");
+  recall_scan_tc_kernel<DIM, 1, true, SCAN_DENSE><<<dim3(gx, gy), kTcThreads, smem, h->stream>>>(h->E16_map, p);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;
@@ -491,13 +504,8 @@ bool scan_tc_dense_available(const prg_handle* h) { return h->scan_filter == SCA
 
 int launch_scan_tc_dense(prg_handle* h, const ScanParams& p) {
   if (!scan_tc_dense_available(h)) return fail(PRG_ESTATE, "bf16 filter index not built");
-  if (h->E_dim == 64) {
-    if (p.nq <= 64) return launch_tc_dense<64, 1>(h, p);
-    if (p.nq <= 128) return launch_tc_dense<64, 2>(h, p);
-    if (p.nq <= 256) return launch_tc_dense<64, 4>(h, p);
-    return fail(PRG_EINVAL, "launch_scan_tc_dense: more than 256 queries per launch");
-  }
-  if (h->E_dim == 128 && p.nq <= 64) return launch_tc_dense<128, 1>(h, p);
+  if (h->E_dim == 64) return launch_tc_dense<64>(h, p);
+  if (h->E_dim == 128) return launch_tc_dense<128>(h, p);
   return fail(PRG_EINVAL, "launch_scan_tc_dense: unsupported shape");
 }
 
