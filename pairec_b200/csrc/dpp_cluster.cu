@@ -454,12 +454,12 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   const double diag = active ? __dmul_rn(__dmul_rn(qi, pick_own()), qi) : CUDART_NAN;
   DPP_CLK(3);
 
-  // cluster-wide first-maximum argmax over the owners; every CTA ends up with the winner's record in pub[par][w].
+  // cluster-wide first-maximum argmax over the owners; every CTA ends up with the winner's record (pub[par][w], or its own srec[par]).
   // Two CTA barriers (per-warp maxima -> every warp reduces them redundantly; record staged) + one mbarrier wait.
   int par = 0;
   uint32_t mb_phase = 0;      // bit p: parity to wait for on mbar[p]
   cluster.barrier_wait();     // every CTA's mbarriers are initialised (arrive was before phase 2a)
-  auto cluster_argmax = [&](double v, int krows) -> int {
+  auto cluster_argmax = [&](double v, int krows) -> const CandRec* {
     uint64_t wk;
     int wi;
     warp_first_max(owner ? d2_key(v) : 0ull, it, &wk, &wi);
@@ -506,23 +506,26 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
     __syncthreads();
     if (tid == 0) {
       fence_proxy_async_smem();
-      mbar_arrive_expect_tx(&mbar[par], (uint32_t)(kClCtas * sizeof(CandRec)));
+      // three PEERS receive the record; this CTA reads its own straight from srec[par] (a shared::cluster bulk copy
+      // addressed to the issuing CTA itself is flagged by compute-sanitizer: "not located in remote CTA")
+      mbar_arrive_expect_tx(&mbar[par], (uint32_t)((kClCtas - 1) * sizeof(CandRec)));
       const uint32_t src = smem_u32(mine), dst = smem_u32(&pub[par * kClCtas + rank]), bar = smem_u32(&mbar[par]);
 #pragma unroll
       for (int r = 0; r < kClCtas; ++r)
-        bulk_copy_to_peer(mapa_u32(dst, r), src, (uint32_t)sizeof(CandRec), mapa_u32(bar, r));
+        if (r != (int)rank) bulk_copy_to_peer(mapa_u32(dst, r), src, (uint32_t)sizeof(CandRec), mapa_u32(bar, r));
     }
     mbar_wait_bounded(&mbar[par], (mb_phase >> par) & 1);
     mb_phase ^= 1u << par;
     DPP_CLK(9);
-    uint64_t best_k = pub[par * kClCtas].key;
+    auto rec_of = [&](int r) -> const CandRec* { return r == (int)rank ? mine : &pub[par * kClCtas + r]; };
+    uint64_t best_k = rec_of(0)->key;
     int best_r = 0;
 #pragma unroll
     for (int r = 1; r < kClCtas; ++r) {
-      const uint64_t rk = pub[par * kClCtas + r].key;
+      const uint64_t rk = rec_of(r)->key;
       if (rk > best_k) { best_k = rk; best_r = r; }  // lower rank == lower index wins ties
     }
-    const int used = par * kClCtas + best_r;
+    const CandRec* used = rec_of(best_r);
     par ^= 1;
     return used;
   };
@@ -534,13 +537,13 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
     int top = (T_out <= window) ? T_out : ((call < T_out / window) ? window : T_out % window);
     if (top > m) top = m;
     double d2 = (active && !existed[gi]) ? diag : CUDART_NAN;
-    int wrec = cluster_argmax(d2, 0);
-    int j = isnan(pub[wrec].v) ? 0 : pub[wrec].idx;
+    const CandRec* wrec = cluster_argmax(d2, 0);
+    int j = isnan(wrec->v) ? 0 : wrec->idx;
     if (tid == 0) res[total] = j;
     int ny = 1;
     bool broke = false;
     while (ny < top) {
-      const CandRec& W = pub[wrec];
+      const CandRec& W = *wrec;
       double dj = W.v;  // == d2[j]; NaN when every candidate is used up (the reference then repeats index 0)
       if (dj < 1e-10) { broke = true; break; }
       const int k = ny - 1;
@@ -583,7 +586,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
       }
       DPP_CLK(5);
       wrec = cluster_argmax(d2, ny);  // its CTA barrier also orders the C[k] writes before the column reads
-      j = isnan(pub[wrec].v) ? 0 : pub[wrec].idx;
+      j = isnan(wrec->v) ? 0 : wrec->idx;
       if (tid == 0) res[total + ny] = j;
       ++ny;
     }
