@@ -395,6 +395,8 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
 #pragma unroll
         for (int u = 0; u < LPI; ++u) {
           const int l = (t / 2) * LPI + u;
+          // rows l >= k are read although the owners write row k in this very step; the value is discarded (tm == 0)
+          // — racecheck reports this read/write pair as a warning; predicating the load costs 4 % of the kernel
           const double tm = (l < k) ? wcj[l] : 0.0;
           const double pr = __dmul_rn(tm, C[l * kClItems + c_it]);
           ss = (tm != 0) ? __dadd_rn(ss, pr) : ss;

@@ -105,7 +105,9 @@ struct prg_handle {
   prg::DevBuf mlp_W[prg::kMaxLayers];  // bf16, layout chosen by mlp.cu
   prg::DevBuf mlp_b[prg::kMaxLayers];
   CUtensorMap mlp_Wmap[prg::kMaxLayers];
+  CUtensorMap mlp_Wmap_half[prg::kMaxLayers];  // boxes of half a W block (one CTA's share of a multicast pair load)
   float mlp_b_last = 0.f;
+  bool mlp_no_pair = false;           // config "mlp_no_pair": single-CTA persistent kernel without W multicast (A/B measurements)
   bool mlp_one_tile_per_cta = false;  // config "mlp_one_tile": the non-persistent layer kernel (A/B measurements)
   prg::DevBuf act[2];   // activations ping-pong (bf16)
   prg::DevBuf fm_logit; // B*n f32

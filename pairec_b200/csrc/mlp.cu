@@ -10,10 +10,14 @@
 // The hi/lo split is what makes the result reproducible to 1e-5 against oracle/oracle.c orc_mlp_forward: with plain
 // bf16 activations a 1e-6 accumulation-order difference flips whole bf16 ulps of hidden units.
 //
-// One CTA per 128 x BN output tile, 6 warps: warp 0 = TMA producer (SWIZZLE_128B boxes, 4-stage mbarrier ring),
-// warp 1 = TMEM allocator + the single MMA-issuing thread (tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16),
-// warps 2-5 = epilogue (tcgen05.ld 32x32b.x32 -> bias + ReLU -> hi/lo split -> global, or for the last hidden layer
-// the fused N=1 output layer: logit = b + sum_j w_j * a_j in fp32).
+// Default kernel (mlp_layer_persistent_kernel<BN, FINAL, PAIR = true>): persistent 2-CTA clusters, one per SM pair, each
+// computing 256 x BN tiles with tcgen05.mma.cta_group::2 (M = 256, N = BN, K = 16): warp 0 = TMA producer (SWIZZLE_128B
+// boxes, 3-stage mbarrier ring; a stage = the hi and the lo block of a 64-wide K slice + this CTA's half of the W block),
+// warp 1 = TMEM allocator + (leader CTA only) the single MMA-issuing thread, warps 2-9 = epilogue (tcgen05.ld
+// 32x32b.x32 -> bias + ReLU -> hi/lo split -> shared-memory staging -> TMA tensor stores; for the last hidden layer the
+// fused N = 1 output layer: logit = b + sum_j w_j * a_j in fp32).  Accumulators are double buffered in TMEM.
+// Fallbacks: the same kernel with PAIR = false (single CTA, M = 128, direct stores) for an odd number of row blocks,
+// and the one-tile-per-CTA mlp_layer_kernel (config "mlp_one_tile", A/B measurements).
 #include "handle.h"
 #include <cuda_bf16.h>
 #include <cstring>
@@ -175,25 +179,85 @@ mlp_layer_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // both are multiplied with (a = hi + lo, so hi*W and lo*W use the same weights): per slice the CTA pulls
 // 16 + 16 + BN/8 KiB instead of 2 x (16 + BN/8) KiB.  Layer 1 at 128 x 256 tiles ran at the L2 bandwidth limit
 // (768 MB of operand reads in 92 us = 8.3 TB/s, tensor pipe 39 % active); this takes a third of that traffic away.
-constexpr int kMlpPThreads = 320;
-constexpr int kMlpEpiWarps = 8;
-constexpr int kMlpPStages = 3;
-
-template <int BN>
-constexpr size_t mlp_p_smem_bytes() {
-  return (size_t)kMlpPStages * (2 * kMlpBM * 128 + BN * 128) + 2 * 1024 * 4 /*bias, w_last*/ + 2 * 2 * kMlpBM * 4 /*partials*/ +
-         (2 * kMlpPStages + 4) * 8 + 16;
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t cta_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_smem_addr), "r"(cta_rank));
+  return r;
+}
+// TMA 2-D load into OUR shared memory whose completion is signalled on an mbarrier of the CTA pair's leader
+// (`bar_cluster_addr` is a shared::cluster address); .cta_group::2 is what allows the barrier to live in the peer
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t bar_cluster_addr,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar_cluster_addr), "l"(policy)
+      : "memory");
+}
+// D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, half of the N rows per CTA]^T: one instruction, two SMs
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives (once the pair MMAs issued so far have completed) on the barrier at this offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// TMA tensor store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 
-template <int BN, bool FINAL>
+constexpr int kMlpPThreads = 320;
+constexpr int kMlpEpiWarps = 8;
+template <bool PAIR>
+constexpr int mlp_p_stages() { return 3; }
+constexpr int kMlpOutStage = 8192;   // per epilogue warp: two buffers of (32 x 32 bf16 hi block | lo block) staged for the TMA stores
+
+template <int BN, bool PAIR>
+constexpr size_t mlp_p_smem_bytes() {
+  return (size_t)mlp_p_stages<PAIR>() * (2 * kMlpBM * 128 + (PAIR ? BN / 2 : BN) * 128) +
+         (PAIR ? (size_t)kMlpEpiWarps * kMlpOutStage : 0) + 2 * 1024 * 4 /*bias, w_last*/ +
+         2 * 2 * kMlpBM * 4 /*partials*/ + (2 * mlp_p_stages<PAIR>() + 4) * 8 + 16;
+}
+
+// PAIR: a 2-CTA cluster computes a 256 x BN tile with tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128
+// rows of activations and HALF of the W block (BN/2 rows); the leader's MMA thread issues one instruction for both SMs
+// and each SM's accumulator (its 128 rows x BN columns) lands in its own TMEM.  A single-CTA M = 128 MMA reads
+// (128 + BN) x 32 B of operands from shared memory per K = 16 step — at BN = 256 that is 12 KiB per 136 tensor-pipe
+// cycles, 90 B/clk of the SM's 128 B/clk with the TMA writes of the next stage on top: the tensor pipe idled 60 % of
+// the time.  The pair halves the W bytes each SM reads and stages.
+// Protocol: every TMA load of both CTAs signals the LEADER's full[s] (.cta_group::2 barrier in the peer); the leader's
+// commits are multicast to empty[s] / tfull[b] of both CTAs; the peer's epilogue warps arrive on the leader's tempty[b].
+template <int BN, bool FINAL, bool PAIR>
 __global__ void __launch_bounds__(kMlpPThreads, 1)
 mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-                            const MlpLayerParams p, const int n_mblk) {
+                            const __grid_constant__ CUtensorMap mapOut, const MlpLayerParams p, const int n_mblk) {
   extern __shared__ __align__(1024) uint8_t msm[];
-  constexpr int kABytes = kMlpBM * 128, kBBytes = BN * 128, kStageBytes = 2 * kABytes + kBBytes;  // A_hi | A_lo | W
-  constexpr int kMlpStages = kMlpPStages;
+  constexpr int kABytes = kMlpBM * 128, kBBytes = (PAIR ? BN / 2 : BN) * 128;   // W rows staged by this CTA
+  constexpr int kStageBytes = 2 * kABytes + kBBytes;                               // A_hi | A_lo | W
+  constexpr int kMlpStages = mlp_p_stages<PAIR>();
   constexpr uint32_t kTmemCols = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
-  float* bias_s = reinterpret_cast<float*>(msm + (size_t)kMlpStages * kStageBytes);  // [1024]
+  uint8_t* out_stage = msm + (size_t)kMlpStages * kStageBytes;                       // PAIR: [8 warps][2 buffers][hi 2 KiB | lo 2 KiB]
+  float* bias_s = reinterpret_cast<float*>(out_stage + (PAIR ? kMlpEpiWarps * kMlpOutStage : 0));  // [1024]
   float* wl_s = bias_s + 1024;                                                       // [1024]
   float* part_s = wl_s + 1024;                                                       // [2 buf][2 halves][128]
   uint64_t* full = reinterpret_cast<uint64_t*>(part_s + 4 * kMlpBM);
@@ -204,9 +268,20 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_nblk = p.N / BN;
-  const int n_tiles = n_mblk * n_nblk;
+  uint32_t cta_rank = 0;
+  if constexpr (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  // work units: output tiles, or (PAIR) pairs of vertically adjacent tiles; unit u -> row block(s), column block
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_tiles = (PAIR ? n_mblk / 2 : n_mblk) * n_nblk;
   const int num_kb = p.K / kMlpBK;   // 64-wide slices of K; each brings its hi and its lo activations
-  const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int my_tiles = (n_tiles > unit0) ? (n_tiles - unit0 + n_workers - 1) / n_workers : 0;
+  auto tile_of = [&](int i, int& m_blk, int& n_blk) {
+    const int t = unit0 + i * n_workers;
+    const int mu = t / n_nblk;
+    n_blk = t - mu * n_nblk;
+    m_blk = PAIR ? 2 * mu + (int)cta_rank : mu;
+  };
 
   for (int i = tid; i < p.N; i += kMlpPThreads) {
     bias_s[i] = p.bias ? p.bias[i] : 0.f;
@@ -216,16 +291,23 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapW);
     for (int s = 0; s < kMlpStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kMlpEpiWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], PAIR ? 2 * kMlpEpiWarps : kMlpEpiWarps); }
     mbar_fence_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(kTmemCols));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything of ours can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -233,22 +315,33 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
     if (lane == 0) {
       uint32_t it = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int t = (int)blockIdx.x + i * (int)gridDim.x;
-        const int m_blk = t / n_nblk, n_blk = t - m_blk * n_nblk;
+        int m_blk, n_blk;
+        tile_of(i, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % kMlpStages, ph = (it / kMlpStages) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], kStageBytes);
           uint8_t* a_dst = msm + (size_t)s * kStageBytes;
-          tma_load_2d(a_dst, &mapA, kb * kMlpBK, m_blk * kMlpBM, &full[s], kEvictNormal);
-          tma_load_2d(a_dst + kABytes, &mapA, p.K + kb * kMlpBK, m_blk * kMlpBM, &full[s], kEvictNormal);
-          tma_load_2d(a_dst + 2 * kABytes, &mapW, kb * kMlpBK, n_blk * BN, &full[s], kEvictLast);
+          if constexpr (PAIR) {
+            // both CTAs' loads complete on the leader's full[s]; the leader expects the bytes of both
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], 2 * kStageBytes);
+            const uint32_t lbar = mapa_cluster(smem_u32(&full[s]), 0);
+            tma_load_2d_pair(a_dst, &mapA, kb * kMlpBK, m_blk * kMlpBM, lbar, kEvictNormal);
+            tma_load_2d_pair(a_dst + kABytes, &mapA, p.K + kb * kMlpBK, m_blk * kMlpBM, lbar, kEvictNormal);
+            tma_load_2d_pair(a_dst + 2 * kABytes, &mapW, kb * kMlpBK, n_blk * BN + (int)cta_rank * (BN / 2), lbar,
+                             kEvictLast);   // our half of the W block (mapW boxes are BN/2 rows here)
+          } else {
+            mbar_arrive_expect_tx(&full[s], kStageBytes);
+            tma_load_2d(a_dst, &mapA, kb * kMlpBK, m_blk * kMlpBM, &full[s], kEvictNormal);
+            tma_load_2d(a_dst + kABytes, &mapA, p.K + kb * kMlpBK, m_blk * kMlpBM, &full[s], kEvictNormal);
+            tma_load_2d(a_dst + 2 * kABytes, &mapW, kb * kMlpBK, n_blk * BN, &full[s], kEvictLast);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kMlpBM >> 4) << 24);
+    if (lane == 0 && cta_rank == 0) {   // PAIR: only the leader issues (for both SMs)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                 ((uint32_t)((PAIR ? 2 * kMlpBM : kMlpBM) >> 4) << 24);
       uint32_t it = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const uint32_t buf = (uint32_t)i & 1u;
@@ -265,12 +358,18 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
           for (int part = 0; part < 2; ++part) {   // hi, then lo, against the same W block
             const uint64_t adesc = umma_desc_k_sw128(a_addr + (uint32_t)part * kABytes);
 #pragma unroll
-            for (int k = 0; k < kMlpBK / 16; ++k)
-              umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | part | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kMlpBK / 16; ++k) {
+              if constexpr (PAIR)
+                umma_bf16_pair(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | part | k) != 0 ? 1u : 0u);
+              else
+                umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | part | k) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(&empty[s]);
+          if constexpr (PAIR) umma_commit_pair(&empty[s]);
+          else umma_commit(&empty[s]);
         }
-        umma_commit(&tfull[buf]);
+        if constexpr (PAIR) umma_commit_pair(&tfull[buf]);
+        else umma_commit(&tfull[buf]);
       }
     }
   } else {
@@ -279,8 +378,8 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
     constexpr int kHalf = BN / 2;
     for (int i = 0; i < my_tiles; ++i) {
       const uint32_t buf = (uint32_t)i & 1u;
-      const int t = (int)blockIdx.x + i * (int)gridDim.x;
-      const int m_blk = t / n_nblk, n_blk = t - m_blk * n_nblk;
+      int m_blk, n_blk;
+      tile_of(i, m_blk, n_blk);
       const int row = m_blk * kMlpBM + quarter * 32 + lane;
       mbar_wait(&tfull[buf], ((uint32_t)i >> 1) & 1u);
       tc_fence_after();
@@ -292,7 +391,10 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
         if (c0 + 32 >= (chalf + 1) * kHalf) {  // last read of this tile by this warp: hand the buffer back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[buf]);
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(mapa_cluster(smem_u32(&tempty[buf]), 0));   // the leader's barrier
+            else mbar_arrive(&tempty[buf]);
+          }
         }
         const int nb = n_blk * BN + c0;  // column in the layer's output
         uint32_t hi_w[16], lo_w[16];
@@ -318,10 +420,35 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
           uint16_t* o = p.out + (size_t)row * (2 * p.N) + (size_t)nb;
           uint4* oh = reinterpret_cast<uint4*>(o);
           uint4* ol = reinterpret_cast<uint4*>(o + p.N);
+          if constexpr (PAIR) {
+            // The accumulator layout gives every lane one ROW: direct stores are 32 scattered 16-B pieces per
+            // instruction, half a sector each (measured: the layer kernels spent 60 us of 160 in these stores).  The
+            // 32 x 32 block goes through shared memory (SWIZZLE_64B, conflict free) and out as two TMA tensor stores.
+            uint8_t* stg = out_stage + (size_t)ew * kMlpOutStage + ((c0 >> 5) & 1) * 4096;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the stores of two chunks ago have read it
+            __syncwarp();
+            const int sw = (lane >> 1) & 3;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            oh[w] = make_uint4(hi_w[4 * w], hi_w[4 * w + 1], hi_w[4 * w + 2], hi_w[4 * w + 3]);
-            ol[w] = make_uint4(lo_w[4 * w], lo_w[4 * w + 1], lo_w[4 * w + 2], lo_w[4 * w + 3]);
+            for (int w = 0; w < 4; ++w) {
+              *reinterpret_cast<uint4*>(stg + lane * 64 + ((w ^ sw) << 4)) =
+                  make_uint4(hi_w[4 * w], hi_w[4 * w + 1], hi_w[4 * w + 2], hi_w[4 * w + 3]);
+              *reinterpret_cast<uint4*>(stg + 2048 + lane * 64 + ((w ^ sw) << 4)) =
+                  make_uint4(lo_w[4 * w], lo_w[4 * w + 1], lo_w[4 * w + 2], lo_w[4 * w + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              const int r0 = m_blk * kMlpBM + quarter * 32;
+              tma_store_2d(&mapOut, nb, r0, stg);
+              tma_store_2d(&mapOut, p.N + nb, r0, stg + 2048);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              oh[w] = make_uint4(hi_w[4 * w], hi_w[4 * w + 1], hi_w[4 * w + 2], hi_w[4 * w + 3]);
+              ol[w] = make_uint4(lo_w[4 * w], lo_w[4 * w + 1], lo_w[4 * w + 2], lo_w[4 * w + 3]);
+            }
           }
         }
       }
@@ -335,24 +462,30 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
     }
   }
 
+  if constexpr (PAIR && !FINAL) {   // the staged output blocks must have left shared memory before the CTA retires
+    if (warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still signal / use it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
   }
 }
 
 // ------------------------------------------------------------------ host side
-static int encode_bf16_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+static int encode_bf16_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint32_t box_rows,
+                           uint32_t box_cols = kMlpBK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kMlpBK, box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled(bf16) failed: " + std::to_string((int)r));
   return PRG_OK;
@@ -364,14 +497,39 @@ static int tile_n(uint32_t N) {
 }
 
 template <int BN, bool FINAL>
-static int launch_layer(prg_handle* h, const CUtensorMap& mapA, const CUtensorMap& mapW, const MlpLayerParams& p, int Mp) {
+static int launch_layer(prg_handle* h, const CUtensorMap& mapA, const CUtensorMap& mapW, const CUtensorMap& mapWhalf,
+                        const CUtensorMap& mapOut, const MlpLayerParams& p, int Mp) {
   if (!h->mlp_one_tile_per_cta && p.N <= 1024) {
-    const size_t smem = mlp_p_smem_bytes<BN>();
-    PRG_CUDA(cudaFuncSetAttribute(mlp_layer_persistent_kernel<BN, FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const int n_mblk = Mp / kMlpBM;
+    if (!h->mlp_no_pair && n_mblk % 2 == 0 && BN % 32 == 0 && h->sm_count >= 2) {
+      // CTA pairs (tcgen05 cta_group::2, 256 x BN tiles): units = pairs of row blocks
+      const size_t smem = mlp_p_smem_bytes<BN, true>();
+      PRG_CUDA(cudaFuncSetAttribute(mlp_layer_persistent_kernel<BN, FINAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+      const int units = (n_mblk / 2) * (p.N / BN);
+      const int pairs = units < h->sm_count / 2 ? units : h->sm_count / 2;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)(2 * pairs));
+      cfg.blockDim = dim3(kMlpPThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = h->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      PRG_CUDA(cudaLaunchKernelEx(&cfg, mlp_layer_persistent_kernel<BN, FINAL, true>, mapA, mapWhalf, mapOut, p, n_mblk));
+      count_launch(h);
+      return PRG_OK;
+    }
+    const size_t smem = mlp_p_smem_bytes<BN, false>();
+    PRG_CUDA(cudaFuncSetAttribute(mlp_layer_persistent_kernel<BN, FINAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    const int n_mblk = Mp / kMlpBM, tiles = n_mblk * (p.N / BN);
+    const int tiles = n_mblk * (p.N / BN);
     const unsigned grid = (unsigned)(tiles < h->sm_count ? tiles : h->sm_count);
-    mlp_layer_persistent_kernel<BN, FINAL><<<grid, kMlpPThreads, smem, h->stream>>>(mapA, mapW, p, n_mblk);
+    mlp_layer_persistent_kernel<BN, FINAL, false><<<grid, kMlpPThreads, smem, h->stream>>>(mapA, mapW, mapOut, p, n_mblk);
     PRG_CUDA(cudaGetLastError());
     count_launch(h);
     return PRG_OK;
@@ -386,12 +544,13 @@ static int launch_layer(prg_handle* h, const CUtensorMap& mapA, const CUtensorMa
 }
 
 template <bool FINAL>
-static int launch_layer_bn(prg_handle* h, int BN, const CUtensorMap& a, const CUtensorMap& w, const MlpLayerParams& p, int Mp) {
+static int launch_layer_bn(prg_handle* h, int BN, const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& wh,
+                           const CUtensorMap& o, const MlpLayerParams& p, int Mp) {
   switch (BN) {
-    case 64: return launch_layer<64, FINAL>(h, a, w, p, Mp);
-    case 128: return launch_layer<128, FINAL>(h, a, w, p, Mp);
-    case 192: return launch_layer<192, FINAL>(h, a, w, p, Mp);
-    case 256: return launch_layer<256, FINAL>(h, a, w, p, Mp);
+    case 64: return launch_layer<64, FINAL>(h, a, w, wh, o, p, Mp);
+    case 128: return launch_layer<128, FINAL>(h, a, w, wh, o, p, Mp);
+    case 192: return launch_layer<192, FINAL>(h, a, w, wh, o, p, Mp);
+    case 256: return launch_layer<256, FINAL>(h, a, w, wh, o, p, Mp);
     default: return fail(PRG_EUNSUPPORTED, "MLP hidden width must be 64, 128, 192, 256 or a multiple of 256");
   }
 }
@@ -415,11 +574,13 @@ int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit
       p.w_last = (const float*)h->mlp_W[L - 1].p;
       p.b_last = h->mlp_b_last;
       p.logit_out = logit_dev;
-      PRG_TRY(launch_layer_bn<true>(h, BN, mapA, h->mlp_Wmap[l], p, Mp));
+      PRG_TRY(launch_layer_bn<true>(h, BN, mapA, h->mlp_Wmap[l], h->mlp_Wmap_half[l], mapA, p, Mp));
     } else {
       uint16_t* out = (uint16_t*)h->act[(l + 1) & 1].p;
       p.out = out;
-      PRG_TRY(launch_layer_bn<false>(h, BN, mapA, h->mlp_Wmap[l], p, Mp));
+      CUtensorMap mapOut;   // 32 x 32 blocks of the [Mp][2N] output for the epilogue's TMA stores
+      PRG_TRY(encode_bf16_map(&mapOut, out, 2ull * N, (uint64_t)Mp, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B));
+      PRG_TRY(launch_layer_bn<false>(h, BN, mapA, h->mlp_Wmap[l], h->mlp_Wmap_half[l], mapOut, p, Mp));
       in = out;
     }
   }
@@ -463,6 +624,7 @@ extern "C" int prg_set_mlp(prg_handle* h, int n_layers, const uint32_t* dims, co
       if (bias[l]) PRG_CUDA(cudaMemcpy(h->mlp_b[l].p, bias[l], N * 4, cudaMemcpyHostToDevice));
       else PRG_CUDA(cudaMemset(h->mlp_b[l].p, 0, N * 4));
       PRG_TRY(encode_bf16_map(&h->mlp_Wmap[l], h->mlp_W[l].p, K, N, (uint32_t)tile_n((uint32_t)N)));
+      PRG_TRY(encode_bf16_map(&h->mlp_Wmap_half[l], h->mlp_W[l].p, K, N, (uint32_t)tile_n((uint32_t)N) / 2));
     } else {
       std::vector<float> wl(K);
       for (size_t i = 0; i < K; ++i) {

@@ -22,14 +22,17 @@ def _setup(engine, n_items, n_fields, dims, seed=6):
     return fields, factors, linear, W, b
 
 
+# shape (3, 333): 999 rows = 8 row blocks -> the CTA-pair kernel (tcgen05 cta_group::2, TMA-stored activations);
+# shape (2, 320): 640 rows = 5 row blocks (odd) -> the single-CTA persistent kernel
+@pytest.mark.parametrize("shape", [(3, 333), (2, 320)])
 @pytest.mark.parametrize("dims,n_fields", [([512, 512, 256, 128, 1], 32), ([64, 64, 1], 4), ([256, 192, 64, 1], 16)])
-def test_mlp_scores_within_tolerance(engine, oracle_lib, dims, n_fields):
+def test_mlp_scores_within_tolerance(engine, oracle_lib, dims, n_fields, shape):
     from pairec_b200.binding import MODEL_MLP, MODEL_FM_MLP
     n_items = 3000
     fields, factors, linear, W, b = _setup(engine, n_items, n_fields, dims)
     rng = np.random.default_rng(1)
-    rows = rng.integers(0, n_items, size=(3, 333)).astype(np.uint32)   # 999 rows: not a multiple of the 128-row tile
-    rows[2, -3:] = 0xFFFFFFFF
+    rows = rng.integers(0, n_items, size=shape).astype(np.uint32)   # not a multiple of the 128-row tile
+    rows[-1, -3:] = 0xFFFFFFFF
     got = engine.rank(MODEL_MLP, rows)
     fm_logit, x = oracle_lib.gather_fm(fields, factors, linear, 0.02, rows.reshape(-1), want_x=True)
     mlp_logit = oracle_lib.mlp_forward(x, dims, W, b)
