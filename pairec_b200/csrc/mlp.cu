@@ -179,6 +179,10 @@ mlp_layer_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // both are multiplied with (a = hi + lo, so hi*W and lo*W use the same weights): per slice the CTA pulls
 // 16 + 16 + BN/8 KiB instead of 2 x (16 + BN/8) KiB.  Layer 1 at 128 x 256 tiles ran at the L2 bandwidth limit
 // (768 MB of operand reads in 92 us = 8.3 TB/s, tensor pipe 39 % active); this takes a third of that traffic away.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo_half, hi_half);   // .x (low 16 bits) = lo_half, .y = hi_half
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -402,18 +406,18 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
         for (int c = 0; c < 32; c += 2) {
           float r0 = fmaxf(__fadd_rn(__uint_as_float(v[c]), bias_s[nb + c]), 0.f);
           float r1 = fmaxf(__fadd_rn(__uint_as_float(v[c + 1]), bias_s[nb + c + 1]), 0.f);
-          const uint16_t h0 = __bfloat16_as_ushort(__float2bfloat16_rn(r0)), h1 = __bfloat16_as_ushort(__float2bfloat16_rn(r1));
-          const float h0f = __uint_as_float((uint32_t)h0 << 16), h1f = __uint_as_float((uint32_t)h1 << 16);
-          const uint16_t l0 = __bfloat16_as_ushort(__float2bfloat16_rn(__fsub_rn(r0, h0f)));
-          const uint16_t l1 = __bfloat16_as_ushort(__float2bfloat16_rn(__fsub_rn(r1, h1f)));
+          // packed conversions (cvt.rn.bf16x2.f32: one XU instruction per PAIR of values; the XU pipe was 32 % busy)
+          const uint32_t hp = pack_bf16x2(r0, r1);                       // low half = bf16(r0), high half = bf16(r1)
+          const float h0f = __uint_as_float(hp << 16), h1f = __uint_as_float(hp & 0xFFFF0000u);
+          const uint32_t lp = pack_bf16x2(__fsub_rn(r0, h0f), __fsub_rn(r1, h1f));
           if (FINAL) {
-            const float a0 = __fadd_rn(h0f, __uint_as_float((uint32_t)l0 << 16));
-            const float a1 = __fadd_rn(h1f, __uint_as_float((uint32_t)l1 << 16));
+            const float a0 = __fadd_rn(h0f, __uint_as_float(lp << 16));
+            const float a1 = __fadd_rn(h1f, __uint_as_float(lp & 0xFFFF0000u));
             logit = __fmaf_rn(wl_s[nb + c], a0, logit);
             logit = __fmaf_rn(wl_s[nb + c + 1], a1, logit);
           } else {
-            hi_w[c >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-            lo_w[c >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            hi_w[c >> 1] = hp;
+            lo_w[c >> 1] = lp;
           }
         }
         if (!FINAL) {
