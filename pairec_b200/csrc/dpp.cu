@@ -358,6 +358,8 @@ __global__ void __launch_bounds__(kDppMaxItems, 1) dpp_kernel(const DppArgs a) {
   if (tid == 0) { a.out_n[b] = total; a.status[b] = 0; }
 }
 
+int dpp_lazy_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
+                    int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled);
 int dpp_cluster_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n,
                        const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled);
 
@@ -381,7 +383,12 @@ int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev,
   int c_rows = p.top_n <= window ? p.top_n : window;
   if (c_rows < 6) c_rows = 6;  // the region doubles as presort staging (4096 x 12 B)
   if (c_rows > 24) return fail(PRG_EUNSUPPORTED, "prg_dpp: window (or top_n when <= window) > 24");
-  if (!h->dpp_generic) {  // fast path: 4-CTA cluster per request, embeddings in registers (dpp_cluster.cu)
+  if (!h->dpp_generic && h->dpp_lazy) {  // config "dpp_lazy": one CTA per request, lazy evaluation of the greedy step (dpp_lazy.cu)
+    bool handled = false;
+    PRG_TRY(dpp_lazy_device(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, &handled));
+    if (handled) return PRG_OK;
+  }
+  if (!h->dpp_generic) {  // default: 4-CTA cluster per request, features resident on chip (dpp_cluster.cu)
     bool handled = false;
     PRG_TRY(dpp_cluster_device(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, &handled));
     if (handled) return PRG_OK;

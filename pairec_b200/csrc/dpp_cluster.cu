@@ -20,49 +20,13 @@
 // Per step each CTA publishes its local arg-max candidate TOGETHER with everything the others need about it
 // (d2, quality, its features, its column of C) into every CTA's shared memory (DSMEM); the records are
 // double buffered so a fast CTA never overwrites what a slow one still reads.
-#include "handle.h"
+#include "dpp_common.cuh"
 #include <cooperative_groups.h>
-#include <math_constants.h>
 #include <type_traits>
 
 namespace cg = cooperative_groups;
 
 namespace prg {
-
-constexpr int kClCtas = 4;
-constexpr int kClItems = 256;                      // candidates per CTA
-constexpr int kClThreads = 2 * kClItems;           // two threads per candidate (k blocks split)
-constexpr int kClMaxItems = kClCtas * kClItems;    // 1024
-constexpr int kClMaxN = 4096;
-constexpr int kClCRows = 24;
-constexpr double kInvSqrt2c = 0.70710678118654752440;
-
-struct DppClArgs {
-  const uint32_t* rows;
-  const double* score;
-  int n;
-  const float* D;
-  const double* D_inv;  // 1 / ||row|| per table row (dpp_inv_norm_kernel)
-  uint64_t D_rows;
-  prg_dpp_params p;
-  int32_t* out_idx;
-  int32_t* out_n;
-  int32_t* status;
-};
-
-template <int D>
-struct ClCfg {
-  static constexpr int kBlocks = (D + 63) / 64;             // gonum 64-wide k blocks that hold embedding features
-  static constexpr int kLPC = 4 * kBlocks;                  // lanes per candidate group: one per (block, DotUnitary chain)
-  static constexpr int kR = kLPC / 2;                       // candidates per group (and per thread)
-  static constexpr int kCL = D >= 64 ? 16 : D / 4;          // chain length: features per (candidate, lane)
-  static constexpr int kTR = (D == 128) ? 8 : kCL;          // of those, kept in registers
-  static constexpr int kSlots = kR * (kCL - kTR);           // shared-memory feature slots per thread ([slot][512] doubles)
-  static constexpr int kFDoubles = (kSlots * 512 > 128 * D) ? kSlots * 512 : 128 * D;  // F region; first holds the f32 staging [256][D]
-  static constexpr int kFS = kCL + 2;                       // lane stride (doubles) of a feature record: 16-B accesses of the
-                                                            // 4 / 8 lanes of a group fall into distinct banks
-  static constexpr bool kConstOwnBlock = (D % 64) == 0;     // the constant feature D opens a block of its own
-};
 
 template <int D>
 struct __align__(16) CandRecT {
@@ -77,32 +41,6 @@ struct __align__(16) CandRecT {
   double f[ClCfg<D>::kLPC * ClCfg<D>::kFS];  // features by (lane of the group, chain position); the constant feature is implied
 };
 
-__device__ __forceinline__ uint64_t f64_ord_c(double d) {
-  uint64_t u = (uint64_t)__double_as_longlong(d);
-  if ((u & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return 0ull;
-  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
-// order key of a d2 value for the first-maximum search: NaN -> 0 (never wins), -0 == +0 (gonum compares with >)
-__device__ __forceinline__ uint64_t d2_key(double d) {
-  uint64_t u = (uint64_t)__double_as_longlong(d);
-  if ((u << 1) == 0) u = 0;
-  if ((u & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return 0ull;
-  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double d2_from_key(uint64_t k) {
-  if (k == 0) return CUDART_NAN;
-  const uint64_t u = (k >> 63) ? (k ^ 0x8000000000000000ull) : ~k;
-  return __longlong_as_double((long long)u);
-}
-// warp-wide (max key, lowest index among equals) with three REDUX ops instead of five 64-bit shuffle rounds
-__device__ __forceinline__ void warp_first_max(uint64_t key, int idx, uint64_t* kout, int* iout) {
-  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-  const unsigned H = __reduce_max_sync(0xffffffffu, hi);
-  const unsigned L = __reduce_max_sync(0xffffffffu, hi == H ? lo : 0u);
-  const unsigned I = __reduce_min_sync(0xffffffffu, (hi == H && lo == L) ? (unsigned)idx : 0x7FFFFFFFu);
-  *kout = ((uint64_t)H << 32) | L;
-  *iout = (int)I;
-}
 // cluster publication primitives: smem -> peer smem bulk copy (async proxy) completing on the PEER's mbarrier
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_smem_addr, uint32_t cta_rank) {
   uint32_t r;
@@ -131,9 +69,6 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
         : "memory");
     if (!done && spins > (1ll << 26)) __trap();
   }
-}
-__device__ __forceinline__ double shfl_xor_f64(double v, int m) {
-  return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
 #ifdef PRG_DPP_PROFILE

@@ -120,6 +120,7 @@ struct prg_handle {
   prg::DevBuf D_inv;        // D_rows f64: 1 / ||row|| (gonum floats.Norm order) of an f32 diversity table, built once at set time
   uint32_t D_dim = 0;
   int D_dtype = PRG_F32;
+  bool dpp_lazy = false;     // config "dpp_lazy": the lazy-evaluation kernel (dpp_lazy.cu) instead of the cluster kernel
   bool dpp_generic = false;  // config "dpp_generic": force the one-CTA-per-request kernel (A/B measurements)
   prg::DevBuf dpp_scratch, dpp_rows, dpp_score, dpp_idx, dpp_n, dpp_status;
 

@@ -21,14 +21,16 @@ def test_sort_desc_matches_stable_oracle_and_go_order(engine, oracle_lib):
         assert (perm[b] == oracle_lib.go_sort(score[b])).all()
 
 
-def _dpp_case(engine, oracle_lib, n, dim, top_n, dtype=np.float32, **kw):
+def _dpp_case(engine, oracle_lib, n, dim, top_n, dtype=np.float32, score_fn=None, dup=False, **kw):
     from pairec_b200 import DppParams
     D = synth.diversity(n_items=3000, dim=dim, dtype=dtype)
+    if dup:
+        D[1500:] = D[:1500]              # every embedding twice: exact ties in d2 between a row and its twin
     engine.set_diversity_matrix(D)
     rng = np.random.default_rng(n + top_n)
     B = 4
     rows = np.stack([rng.choice(3000, size=n, replace=False) for _ in range(B)]).astype(np.uint32)
-    score = rng.random((B, n))
+    score = rng.random((B, n)) if score_fn is None else score_fn(rng, B, n)
     if kw.get("norm_mode", 0) == 2 or kw.get("candidate_count", 0) > 0:
         score = -np.sort(-score, axis=1)
     p = DppParams(top_n=top_n, **kw)
@@ -82,6 +84,44 @@ def test_dpp_generic_kernel_still_matches(oracle_lib):
     try:
         _dpp_case(eng, oracle_lib, n=700, dim=128, top_n=30, alpha=1.0, window_size=10)
         _dpp_case(eng, oracle_lib, n=200, dim=24, top_n=12, alpha=1.0, window_size=5)
+    finally:
+        eng.close()
+
+
+def _hard_cases(eng, oracle_lib, dim):
+    # what stresses the arg-max logic: equal scores, quantised scores with twin embeddings (exact ties: the
+    # first-maximum rule decides), saturated scores (the bench's distribution), and a descending list (the fused path)
+    equal = lambda rng, B, n: np.full((B, n), 0.5)
+    quant = lambda rng, B, n: np.round(rng.random((B, n)) * 4) / 4
+    sat = lambda rng, B, n: np.clip(rng.standard_normal((B, n)) * 2 + 0.3, 0.0, 1.0)
+    desc = lambda rng, B, n: -np.sort(-rng.random((B, n)), axis=1)
+    _dpp_case(eng, oracle_lib, n=1000, dim=dim, top_n=50, score_fn=equal, alpha=1.0, window_size=10)
+    _dpp_case(eng, oracle_lib, n=1000, dim=dim, top_n=50, score_fn=quant, dup=True, alpha=1.0, window_size=10)
+    _dpp_case(eng, oracle_lib, n=1000, dim=dim, top_n=50, score_fn=sat, alpha=1.0, window_size=10)
+    _dpp_case(eng, oracle_lib, n=777, dim=dim, top_n=33, score_fn=desc, alpha=3.0, window_size=8)
+    _dpp_case(eng, oracle_lib, n=600, dim=dim, top_n=40, score_fn=quant, dup=True, alpha=1.0, window_size=10, normalize_emb=0)
+
+
+@pytest.mark.parametrize("dim", [32, 128])
+def test_dpp_hard_cases(engine, oracle_lib, dim):
+    _hard_cases(engine, oracle_lib, dim)
+
+
+def test_dpp_lazy_kernel_matches(oracle_lib):
+    # the lazy-evaluation kernel behind config dpp_lazy (one CTA per request; only candidates whose stale bound can still
+    # win are brought up to date): same selection sequences, bit for bit
+    from pairec_b200 import Engine
+    eng = Engine(0, dpp_lazy=1)
+    try:
+        for dim in (32, 64, 128):
+            _dpp_case(eng, oracle_lib, n=1000, dim=dim, top_n=50, alpha=1.0, window_size=10)
+        for kw in (dict(alpha=2.0, window_size=7), dict(alpha=1.0, window_size=10, norm_mode=1),
+                   dict(alpha=1.0, window_size=10, norm_mode=2), dict(alpha=1.0, window_size=10, candidate_count=300, min_score_percent=0.6)):
+            _dpp_case(eng, oracle_lib, n=400, dim=32, top_n=23, **kw)
+        _dpp_case(eng, oracle_lib, n=25, dim=32, top_n=50, alpha=1.0, window_size=10)   # candidates run out: index 0 repeats
+        _dpp_case(eng, oracle_lib, n=5, dim=32, top_n=3, alpha=1.0, window_size=10)
+        _hard_cases(eng, oracle_lib, 128)
+        _hard_cases(eng, oracle_lib, 32)
     finally:
         eng.close()
 
