@@ -27,13 +27,25 @@ __device__ __forceinline__ float bf16_val(uint16_t h) { return __uint_as_float((
 // X layout: [M][2*F*16] bf16: hi at column f*16+k, lo at F*16 + f*16+k.
 template <int F_UNROLL>
 __global__ void __launch_bounds__(256)
-gather_fm_kernel(const uint32_t* __restrict__ rows, int M, const uint32_t* __restrict__ fields, uint64_t field_rows,
+gather_fm_kernel(const uint32_t* __restrict__ rows, const uint64_t* __restrict__ keys, uint32_t* __restrict__ rows_out,
+                 int M, const uint32_t* __restrict__ fields, uint64_t field_rows,
                  int F, const __grid_constant__ TableSet ts, float w0, float* __restrict__ logit_out,
                  uint16_t* __restrict__ x_out) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int item = gid >> 2, sub = gid & 3, lane = threadIdx.x & 31;
   const bool in_range = item < M;
-  uint32_t row = in_range ? rows[item] : 0xFFFFFFFFu;
+  // candidates arrive as item rows, or (fused path) as the recall's order keys: the row is unpacked here and written
+  // out for the later stages instead of by a launch of its own
+  uint32_t row = 0xFFFFFFFFu;
+  if (in_range) {
+    if (keys) {
+      const uint64_t key = keys[item];
+      row = key ? key_row(key) : 0xFFFFFFFFu;
+      if (sub == 0) rows_out[item] = row;
+    } else {
+      row = rows[item];
+    }
+  }
   const bool live = row != 0xFFFFFFFFu && (uint64_t)row < field_rows;
   const uint32_t* idp = fields + (size_t)(live ? row : 0) * F;
   const int K = F * 16;
@@ -105,7 +117,8 @@ __global__ void logit_to_score_kernel(const float* a, const float* b, const uint
   out[i] = (rows[i] == 0xFFFFFFFFu) ? 0.0 : (double)sc;
 }
 
-int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logit_dev, uint16_t* x_dev) {
+int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logit_dev, uint16_t* x_dev,
+                     const uint64_t* keys_dev, uint32_t* rows_out) {
   if (!h->fields) return fail(PRG_ESTATE, "item fields not set (prg_set_item_fields)");
   if (h->fdim != 16) return fail(PRG_EUNSUPPORTED, "feature tables must have fdim == 16");
   TableSet ts{};
@@ -119,7 +132,7 @@ int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logi
   const int threads = 256;
   const long long total = (long long)M * 4;
   const unsigned grid = (unsigned)((total + threads - 1) / threads);
-  gather_fm_kernel<8><<<grid, threads, 0, h->stream>>>(rows_dev, M, h->fields, h->fields_rows, (int)h->n_fields, ts,
+  gather_fm_kernel<8><<<grid, threads, 0, h->stream>>>(rows_dev, keys_dev, rows_out, M, h->fields, h->fields_rows, (int)h->n_fields, ts,
                                                         h->fm_w0, logit_dev, x_dev);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);

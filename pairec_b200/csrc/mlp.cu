@@ -42,6 +42,10 @@ struct MlpLayerParams {
   const float* w_last;   // [N] f32 (bf16 values widened)           (FINAL)
   float b_last;          //                                         (FINAL)
   float* logit_out;      // [M]                                     (FINAL)
+  // fused score epilogue (FINAL, optional): score = rows[i] == pad ? 0 : (double)(float)sigmoid((fm_logit[i] +) logit)
+  const float* fm_logit;  // nullable: logit of the FM part, added first (DeepFM-shaped model)
+  const uint32_t* rows;   // candidate rows (0xFFFFFFFF = padding)
+  double* score_out;      // nullable: when set, scores are written instead of logits
 };
 
 template <int BN>
@@ -179,6 +183,17 @@ mlp_layer_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 // both are multiplied with (a = hi + lo, so hi*W and lo*W use the same weights): per slice the CTA pulls
 // 16 + 16 + BN/8 KiB instead of 2 x (16 + BN/8) KiB.  Layer 1 at 128 x 256 tiles ran at the L2 bandwidth limit
 // (768 MB of operand reads in 92 us = 8.3 TB/s, tensor pipe 39 % active); this takes a third of that traffic away.
+// last step of the tower for one candidate: the logit, or (fused path) the rank score of gather_fm.cu's
+// logit_to_score_kernel — same operations in the same order, so the score is bit-identical to the unfused path
+__device__ __forceinline__ void mlp_write_result(const MlpLayerParams& p, int row, float mlp_logit) {
+  if (p.score_out) {
+    float l = p.fm_logit ? __fadd_rn(p.fm_logit[row], mlp_logit) : mlp_logit;
+    const float sc = (float)(1.0 / (1.0 + exp(-(double)l)));
+    p.score_out[row] = (p.rows[row] == 0xFFFFFFFFu) ? 0.0 : (double)sc;
+  } else {
+    p.logit_out[row] = mlp_logit;
+  }
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
   const __nv_bfloat162 v = __floats2bfloat162_rn(lo_half, hi_half);   // .x (low 16 bits) = lo_half, .y = hi_half
   return *reinterpret_cast<const uint32_t*>(&v);
@@ -460,8 +475,8 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
         part_s[(buf * 2 + chalf) * kMlpBM + quarter * 32 + lane] = logit;
         asm volatile("bar.sync 1, %0;" ::"n"(kMlpEpiWarps * 32) : "memory");
         if (chalf == 0 && row < p.M)
-          p.logit_out[row] = __fadd_rn(__fadd_rn(part_s[(buf * 2) * kMlpBM + quarter * 32 + lane],
-                                                 part_s[(buf * 2 + 1) * kMlpBM + quarter * 32 + lane]), p.b_last);
+          mlp_write_result(p, row, __fadd_rn(__fadd_rn(part_s[(buf * 2) * kMlpBM + quarter * 32 + lane],
+                                                       part_s[(buf * 2 + 1) * kMlpBM + quarter * 32 + lane]), p.b_last));
       }
     }
   }
@@ -560,7 +575,11 @@ static int launch_layer_bn(prg_handle* h, int BN, const CUtensorMap& a, const CU
 }
 
 // x_dev: [Mp][2*dims[0]] bf16 hi|lo in h->act[0];  logit_dev: [M]
-int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit_dev) {
+// score_dev != nullptr: the last layer writes rank scores (sigmoid of fm_logit + tower logit, 0 for padding rows)
+// instead of logits — only the persistent kernels do that; *fused_score tells the caller whether it happened
+int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit_dev, const float* fm_logit_dev,
+                       const uint32_t* rows_dev, double* score_dev, bool* fused_score) {
+  if (fused_score) *fused_score = false;
   const int L = h->mlp_layers;
   if (L < 2) return fail(PRG_ESTATE, "MLP weights not set (prg_set_mlp)");
   const int Mp = (M + kMlpBM - 1) / kMlpBM * kMlpBM;
@@ -578,6 +597,10 @@ int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit
       p.w_last = (const float*)h->mlp_W[L - 1].p;
       p.b_last = h->mlp_b_last;
       p.logit_out = logit_dev;
+      if (score_dev && fused_score && !h->mlp_one_tile_per_cta && N <= 1024) {
+        p.fm_logit = fm_logit_dev; p.rows = rows_dev; p.score_out = score_dev;
+        *fused_score = true;
+      }
       PRG_TRY(launch_layer_bn<true>(h, BN, mapA, h->mlp_Wmap[l], h->mlp_Wmap_half[l], mapA, p, Mp));
     } else {
       uint16_t* out = (uint16_t*)h->act[(l + 1) & 1].p;

@@ -4,13 +4,16 @@
 
 namespace prg {
 // gather_fm.cu
-int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logit_dev, uint16_t* x_dev);
+int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logit_dev, uint16_t* x_dev,
+                     const uint64_t* keys_dev, uint32_t* rows_out);
 int logits_to_scores_device(prg_handle* h, const float* a, const float* b, const uint32_t* rows_dev, int M, double* out);
 // mlp.cu
-int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit_dev);
+int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit_dev, const float* fm_logit_dev,
+                       const uint32_t* rows_dev, double* score_dev, bool* fused_score);
 size_t mlp_act_bytes(const prg_handle* h, int M);
 // sort.cu
-int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32_t* perm_dev);
+int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32_t* perm_dev, const uint32_t* rows_dev,
+                     uint32_t* rows_sorted, double* scores_sorted);
 // dpp.cu
 int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
                int32_t* out_idx, int32_t* out_n, int32_t* status);
@@ -44,8 +47,10 @@ static int adopt(const void* src, size_t bytes, int mem, const void** dst, bool*
   return PRG_OK;
 }
 
-// rank on device buffers: rows_dev [M] -> score_dev [M] f64
-static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int M, double* score_dev) {
+// rank on device buffers: rows_dev [M] -> score_dev [M] f64.  keys_dev != nullptr (fused path): the candidates come as
+// the recall's order keys; the gather unpacks the rows into rows_dev (which is then an OUTPUT).
+static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int M, double* score_dev,
+                       const uint64_t* keys_dev = nullptr) {
   if (model != PRG_MODEL_FM && model != PRG_MODEL_MLP && model != PRG_MODEL_FM_MLP)
     return fail(PRG_EINVAL, "unknown rank model");
   const bool need_mlp = model != PRG_MODEL_FM;
@@ -62,21 +67,16 @@ static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int M
     PRG_TRY(h->act[1].ensure(mlp_act_bytes(h, M)));
     x = (uint16_t*)h->act[0].p;
   }
-  PRG_TRY(gather_fm_device(h, rows_dev, M, fm_logit, x));
-  if (need_mlp) PRG_TRY(mlp_forward_device(h, x, M, mlp_logit));
+  PRG_TRY(gather_fm_device(h, rows_dev, M, fm_logit, x, keys_dev, keys_dev ? const_cast<uint32_t*>(rows_dev) : nullptr));
+  if (need_mlp) {
+    bool fused_score = false;   // the tower's last layer writes the scores itself when it can
+    PRG_TRY(mlp_forward_device(h, x, M, mlp_logit, need_fm ? fm_logit : nullptr, rows_dev, score_dev, &fused_score));
+    if (fused_score) return PRG_OK;
+  }
   return logits_to_scores_device(h, need_fm ? fm_logit : mlp_logit, (need_fm && need_mlp) ? mlp_logit : nullptr, rows_dev,
                                  M, score_dev);
 }
 
-__global__ void apply_perm_kernel(const uint32_t* rows, const double* scores, const int32_t* perm, int total,
-                                  uint32_t* rows_o, double* scores_o, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int b = i / n;
-  const int src = b * n + perm[i];
-  rows_o[i] = rows[src];
-  scores_o[i] = scores[src];
-}
 __global__ void final_gather_kernel(const uint32_t* rows, const double* scores, const int32_t* idx, const int32_t* cnt,
                                     const int32_t* status, int B, int n, int T, uint32_t* out_row, double* out_score,
                                     int32_t* out_n) {
@@ -130,18 +130,11 @@ static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_
   PRG_TRY(h->dpp_idx.ensure((size_t)B * p.top_n * 4));
   PRG_TRY(h->dpp_n.ensure((size_t)B * 4));
   PRG_TRY(h->dpp_status.ensure((size_t)B * 4));
-  PRG_TRY(keys_to_outputs(h, (const uint64_t*)h->topk_keys.p, B, k, (uint32_t*)h->rec_rows.p, (float*)h->out_score.p,
-                          (int32_t*)h->out_n.p));
-  // 2. gather + rank
-  PRG_TRY(rank_device(h, model, (const uint32_t*)h->rec_rows.p, M, (double*)h->rec_scores.p));
-  // 3. ItemRankScore sort
-  PRG_TRY(sort_desc_device(h, (const double*)h->rec_scores.p, B, k, (int32_t*)h->rec_perm.p));
-  apply_perm_kernel<<<(M + 255) / 256, 256, 0, h->stream>>>((const uint32_t*)h->rec_rows.p, (const double*)h->rec_scores.p,
-                                                            (const int32_t*)h->rec_perm.p, M,
-                                                            (uint32_t*)h->rec_sorted_rows.p,
-                                                            (double*)h->rec_sorted_scores.p, k);
-  PRG_CUDA(cudaGetLastError());
-  count_launch(h);
+  // 2. gather + rank (the gather unpacks the recall keys into rec_rows on the way)
+  PRG_TRY(rank_device(h, model, (const uint32_t*)h->rec_rows.p, M, (double*)h->rec_scores.p, (const uint64_t*)h->topk_keys.p));
+  // 3. ItemRankScore sort; the sort writes the sorted list for DPP itself
+  PRG_TRY(sort_desc_device(h, (const double*)h->rec_scores.p, B, k, (int32_t*)h->rec_perm.p, (const uint32_t*)h->rec_rows.p,
+                           (uint32_t*)h->rec_sorted_rows.p, (double*)h->rec_sorted_scores.p));
   // 4. DPP
   PRG_TRY(dpp_device(h, (const uint32_t*)h->rec_sorted_rows.p, (const double*)h->rec_sorted_scores.p, B, k, p,
                      (int32_t*)h->dpp_idx.p, (int32_t*)h->dpp_n.p, (int32_t*)h->dpp_status.p));

@@ -151,7 +151,11 @@ __device__ __forceinline__ uint64_t f64_ord(double d) {
 }
 
 // One CTA per list.  smem: P2 u64 keys + P2 i32 indices.  perm[i] = input index at output position i.
-__global__ void __launch_bounds__(1024) sort_desc_kernel(const double* __restrict__ score, int n, int32_t* __restrict__ perm) {
+// Optionally also writes the list in sorted order (rows_o / scores_o: what the fused path feeds to DPP; saves the
+// separate apply-permutation launch).
+__global__ void __launch_bounds__(1024) sort_desc_kernel(const double* __restrict__ score, int n, int32_t* __restrict__ perm,
+                                                         const uint32_t* __restrict__ rows, uint32_t* __restrict__ rows_o,
+                                                         double* __restrict__ scores_o) {
   extern __shared__ __align__(16) uint8_t sort_smem[];
   uint32_t P2 = 32;
   while (P2 < (uint32_t)n) P2 <<= 1;
@@ -177,10 +181,18 @@ __global__ void __launch_bounds__(1024) sort_desc_kernel(const double* __restric
     }
   }
   int32_t* o = perm + (size_t)blockIdx.x * n;
-  for (uint32_t i = threadIdx.x; i < (uint32_t)n; i += blockDim.x) o[i] = idx[i];
+  for (uint32_t i = threadIdx.x; i < (uint32_t)n; i += blockDim.x) {
+    const int32_t src = idx[i];
+    o[i] = src;
+    if (rows_o) {
+      rows_o[(size_t)blockIdx.x * n + i] = rows[(size_t)blockIdx.x * n + src];
+      scores_o[(size_t)blockIdx.x * n + i] = s[src];
+    }
+  }
 }
 
-int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32_t* perm_dev) {
+int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32_t* perm_dev, const uint32_t* rows_dev,
+                     uint32_t* rows_sorted, double* scores_sorted) {
   if (n > 8192) return fail(PRG_EUNSUPPORTED, "prg_sort_desc: n > 8192");
   uint32_t P2 = 32;
   while (P2 < (uint32_t)n) P2 <<= 1;
@@ -188,7 +200,8 @@ int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32
   StageScope span(h, ST_SORT);
   if (smem > 48 * 1024)
     PRG_CUDA(cudaFuncSetAttribute(sort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sort_desc_kernel<<<B, P2 / 2 < 1024 ? (P2 / 2 < 32 ? 32 : P2 / 2) : 1024, smem, h->stream>>>(score_dev, n, perm_dev);
+  sort_desc_kernel<<<B, P2 / 2 < 1024 ? (P2 / 2 < 32 ? 32 : P2 / 2) : 1024, smem, h->stream>>>(score_dev, n, perm_dev, rows_dev,
+                                                                                                rows_sorted, scores_sorted);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;
@@ -215,12 +228,12 @@ int prg_sort_desc(prg_handle* h, const double* score, int B, int n, int32_t* out
   std::lock_guard<std::mutex> lk(h->mu);
   PRG_CUDA(cudaSetDevice(h->device));
   prg::resolve_pending(h);
-  if (mem == PRG_MEM_DEVICE) return sort_desc_device(h, score, B, n, out_perm);
+  if (mem == PRG_MEM_DEVICE) return sort_desc_device(h, score, B, n, out_perm, nullptr, nullptr, nullptr);
   const size_t cnt = (size_t)B * n;
   PRG_TRY(h->sort_in.ensure(cnt * 8));
   PRG_TRY(h->sort_perm.ensure(cnt * 4));
   PRG_CUDA(cudaMemcpyAsync(h->sort_in.p, score, cnt * 8, cudaMemcpyHostToDevice, h->stream));
-  PRG_TRY(sort_desc_device(h, (const double*)h->sort_in.p, B, n, (int32_t*)h->sort_perm.p));
+  PRG_TRY(sort_desc_device(h, (const double*)h->sort_in.p, B, n, (int32_t*)h->sort_perm.p, nullptr, nullptr, nullptr));
   PRG_CUDA(cudaMemcpyAsync(out_perm, h->sort_perm.p, cnt * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaStreamSynchronize(h->stream));
   return PRG_OK;
