@@ -142,6 +142,8 @@ int prg_init(const char* json_cfg, prg_handle** out) {
   if (json_int(json_cfg, "dpp_lazy", &v) && v != 0) h->dpp_lazy = true;
   if (json_int(json_cfg, "mlp_one_tile", &v) && v != 0) h->mlp_one_tile_per_cta = true;
   if (json_int(json_cfg, "mlp_no_pair", &v) && v != 0) h->mlp_no_pair = true;
+  if (json_int(json_cfg, "pdl", &v)) h->pdl = v != 0;
+  if (const char* ev = getenv("PRG_PDL")) h->pdl = atoi(ev) != 0;   // A/B measurements without a config change
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete h;

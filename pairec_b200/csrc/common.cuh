@@ -158,6 +158,15 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Programmatic dependent launch (launch_chained in handle.h): a kernel of the per-batch chain is launched while its
+// predecessor in the stream is still draining; everything before pdl_wait() — barrier initialisation, TMEM allocation,
+// loads of tables that no kernel of the chain writes — overlaps the predecessor's tail.  pdl_wait() returns when the
+// predecessor grid has completed and its writes are visible (a no-op for a launch without the attribute); EVERY
+// kernel launched through launch_chained calls it before it exits, so completion is transitive along the chain.
+// pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as every CTA of this grid has issued it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // L2 cache-hint policy words (createpolicy equivalents)
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;

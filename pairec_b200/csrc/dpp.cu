@@ -361,7 +361,8 @@ __global__ void __launch_bounds__(kDppMaxItems, 1) dpp_kernel(const DppArgs a) {
 int dpp_lazy_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
                     int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled);
 int dpp_cluster_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n,
-                       const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled);
+                       const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled,
+                       DppFinal* fin);
 
 static size_t dpp_smem_bytes(int c_rows, int top_n) {
   return (size_t)c_rows * kDppMaxItems * 8 + 2 * kDppMaxItems * 8 + 520 * 8 + 32 * 8 + 32 * 4 + kDppMaxItems * 4 +
@@ -369,7 +370,8 @@ static size_t dpp_smem_bytes(int c_rows, int top_n) {
 }
 
 int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
-               int32_t* out_idx, int32_t* out_n, int32_t* status) {
+               int32_t* out_idx, int32_t* out_n, int32_t* status, DppFinal* fin) {
+  if (fin) fin->done = false;
   if (!h->D) return fail(PRG_ESTATE, "diversity matrix not set (prg_set_diversity_matrix)");
   if (B <= 0 || n <= 0 || p.top_n <= 0) return fail(PRG_EINVAL, "B, n, top_n must be positive");
   if (n > kDppMaxN) return fail(PRG_EUNSUPPORTED, "prg_dpp: n > 4096");
@@ -390,7 +392,7 @@ int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev,
   }
   if (!h->dpp_generic) {  // default: 4-CTA cluster per request, features resident on chip (dpp_cluster.cu)
     bool handled = false;
-    PRG_TRY(dpp_cluster_device(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, &handled));
+    PRG_TRY(dpp_cluster_device(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, &handled, fin));
     if (handled) return PRG_OK;
   }
   const size_t esz = h->D_dtype == PRG_F64 ? 8 : 4;

@@ -80,8 +80,33 @@ __device__ long long g_dpp_clk[16];
 #define DPP_CLK(slot) do { } while (0)
 #endif
 
+// Final outputs of the fused request path for request b, by all threads of the cluster's leader CTA: the picks' rows
+// and rank scores, or — status != 0, the reference returns the list unchanged (sort/dpp_sort.go:317-320) — the first
+// top_n entries of the sorted list.  Same result as pipeline.cu's final_gather_kernel, without its launch.
+__device__ __forceinline__ void dpp_write_final(const DppClArgs& a, int b, int tid, int st, int total, const int32_t* order,
+                                                const int32_t* res) {
+  if (!a.fin_row) return;
+  const int T = a.p.top_n, n = a.n;
+  const bool unchanged = st != 0;
+  const int c = unchanged ? (n < T ? n : T) : total;
+  for (int t = tid; t < T; t += kClThreads) {
+    const size_t o = (size_t)b * T + t;
+    if (t < c) {
+      const size_t src = (size_t)b * n + (unchanged ? t : order[res[t]]);
+      a.fin_row[o] = a.rows[src];
+      a.fin_score[o] = a.score[src];
+    } else {
+      a.fin_row[o] = 0xFFFFFFFFu;
+      a.fin_score[o] = 0.0;
+    }
+  }
+  if (tid == 0) a.fin_n[b] = c;
+}
+
 template <int D>
 __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClArgs a) {
+  pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
+  pdl_launch_dependents();
   using CandRec = CandRecT<D>;
   using Cfg = ClCfg<D>;
   constexpr int LPC = Cfg::kLPC, R = Cfg::kR, CL = Cfg::kCL, TR = Cfg::kTR, FS = Cfg::kFS;
@@ -182,6 +207,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   }
   if (nv == 0 || m > kClMaxItems) {  // uniform across the cluster: every CTA sees the same request
     if (rank == 0 && tid == 0) { a.out_n[b] = 0; a.status[b] = (nv == 0) ? 0 : 2; }
+    if (rank == 0) dpp_write_final(a, b, tid, (nv == 0) ? 0 : 2, 0, nullptr, nullptr);
     return;
   }
   __syncthreads();
@@ -215,6 +241,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   }
   if (s_err) {
     if (rank == 0 && tid == 0) { a.out_n[b] = 0; a.status[b] = 1; }
+    if (rank == 0) dpp_write_final(a, b, tid, 1, 0, nullptr, nullptr);
     return;
   }
   DPP_CLK(0);
@@ -555,6 +582,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   if (rank == 0) {
     for (int t = tid; t < total; t += kClThreads) a.out_idx[(size_t)b * T_out + t] = order[res[t]];
     if (tid == 0) { a.out_n[b] = total; a.status[b] = 0; }
+    dpp_write_final(a, b, tid, 0, total, order, res);
   }
   cluster.sync();  // no CTA may exit while peers can still write into its shared memory
 }
@@ -609,26 +637,15 @@ static int launch_cluster(prg_handle* h, const DppClArgs& a, int B) {
   const int window = a.p.window_size > 0 ? a.p.window_size : 10;
   const size_t smem = dpp_cluster_smem<D>(a.p.top_n, a.p.top_n <= window ? a.p.top_n : window);
   PRG_CUDA(cudaFuncSetAttribute(dpp_cluster_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(B * kClCtas));
-  cfg.blockDim = dim3(kClThreads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = h->stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kClCtas;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  PRG_CUDA(cudaLaunchKernelEx(&cfg, dpp_cluster_kernel<D>, a));
+  PRG_CUDA(launch_chained(h, dpp_cluster_kernel<D>, dim3((unsigned)(B * kClCtas)), dim3(kClThreads), smem, kClCtas, a));
   count_launch(h);
   return PRG_OK;
 }
 
 // returns PRG_OK and sets *handled when the request shape is served by the cluster kernel
 int dpp_cluster_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n,
-                       const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled) {
+                       const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled,
+                       DppFinal* fin) {
   *handled = false;
   if (h->D_dtype != PRG_F32) return PRG_OK;
   if (h->D_dim != 32 && h->D_dim != 64 && h->D_dim != 128) return PRG_OK;
@@ -640,12 +657,14 @@ int dpp_cluster_device(prg_handle* h, const uint32_t* rows_dev, const double* sc
   DppClArgs a{};
   a.rows = rows_dev; a.score = score_dev; a.n = n; a.D = (const float*)h->D; a.D_inv = (const double*)h->D_inv.p; a.D_rows = h->D_rows; a.p = p;
   a.out_idx = out_idx; a.out_n = out_n; a.status = status;
+  if (fin) { a.fin_row = fin->row; a.fin_score = fin->score; a.fin_n = fin->n; }
   StageScope span(h, ST_DPP);
   int rc = PRG_OK;
   if (h->D_dim == 32) rc = launch_cluster<32>(h, a, B);
   else if (h->D_dim == 64) rc = launch_cluster<64>(h, a, B);
   else rc = launch_cluster<128>(h, a, B);
   if (rc == PRG_OK) *handled = true;
+  if (rc == PRG_OK && fin) fin->done = true;
   return rc;
 }
 

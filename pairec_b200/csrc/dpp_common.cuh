@@ -25,6 +25,10 @@ struct DppClArgs {
   int32_t* out_idx;
   int32_t* out_n;
   int32_t* status;
+  // fused path (nullable): final outputs, written by the kernel itself (pipeline.cu final_gather_kernel semantics)
+  uint32_t* fin_row;
+  double* fin_score;
+  int32_t* fin_n;
 };
 
 template <int D>

@@ -31,6 +31,8 @@ gather_fm_kernel(const uint32_t* __restrict__ rows, const uint64_t* __restrict__
                  int M, const uint32_t* __restrict__ fields, uint64_t field_rows,
                  int F, const __grid_constant__ TableSet ts, float w0, float* __restrict__ logit_out,
                  uint16_t* __restrict__ x_out) {
+  pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
+  pdl_launch_dependents();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int item = gid >> 2, sub = gid & 3, lane = threadIdx.x & 31;
   const bool in_range = item < M;
@@ -132,9 +134,8 @@ int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logi
   const int threads = 256;
   const long long total = (long long)M * 4;
   const unsigned grid = (unsigned)((total + threads - 1) / threads);
-  gather_fm_kernel<8><<<grid, threads, 0, h->stream>>>(rows_dev, keys_dev, rows_out, M, h->fields, h->fields_rows, (int)h->n_fields, ts,
-                                                        h->fm_w0, logit_dev, x_dev);
-  PRG_CUDA(cudaGetLastError());
+  PRG_CUDA(launch_chained(h, gather_fm_kernel<8>, dim3(grid), dim3(threads), 0, 1, rows_dev, keys_dev, rows_out, M, h->fields,
+                          h->fields_rows, (int)h->n_fields, ts, h->fm_w0, logit_dev, x_dev));
   count_launch(h);
   return PRG_OK;
 }

@@ -29,6 +29,7 @@ struct prg_handle {
   cudaStream_t stream = nullptr;
   std::mutex mu;
   uint64_t launches = 0;
+  bool pdl = true;   // config "pdl": programmatic dependent launch along the per-batch kernel chain (launch_chained)
 
   // optional per-stage device timing (CUDA events on this handle's stream around each stage's launches)
   int timing = 0;  // 0 off, 1 every stage, 2 only the recall scan (least perturbation of the step)
@@ -137,6 +138,33 @@ namespace prg {
 // launch bookkeeping
 inline void count_launch(prg_handle* h, int n = 1) { h->launches += (uint64_t)n; }
 
+#ifdef __CUDACC__
+// Launch of a kernel of the per-batch chain.  With h->pdl the launch carries the programmatic-stream-serialization
+// attribute: the grid may start while its predecessor in the stream drains and orders itself behind it with
+// pdl_wait() (common.cuh).  Only kernels that call pdl_wait() before touching anything an earlier kernel wrote — and
+// before they exit — may be launched through here.  cluster_x > 1 adds the cluster dimension.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(prg_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                  unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (h->pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 enum { SCAN_FILTER_BF16 = 0, SCAN_FILTER_TF32 = 1 };
 enum Stage { ST_SCAN = 0, ST_SCAN_DENSE = 1, ST_SELECT = 2, ST_GATHER_FM = 3, ST_MLP = 4, ST_SORT = 5, ST_DPP = 6, ST_OTHER = 7 };
 // RAII span: records an event before and after the enclosed launches when timing is on
@@ -156,6 +184,15 @@ struct StageScope {
   ~StageScope() {
     if (a) { cudaEvent_t b = get(h); cudaEventRecord(b, h->stream); h->spans.push_back({stage, a, b}); }
   }
+};
+
+// The fused request path's final outputs (the picks' rows and rank scores, [B][top_n], and the per-request counts):
+// a DPP kernel that can write them itself does so and sets `done`; otherwise pipeline.cu's final_gather_kernel runs.
+struct DppFinal {
+  uint32_t* row = nullptr;
+  double* score = nullptr;
+  int32_t* n = nullptr;
+  bool done = false;
 };
 
 // recall.cu

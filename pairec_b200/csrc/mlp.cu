@@ -329,6 +329,10 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
   if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything of ours can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // chained launch: weights and biases above are static; the activations (and everything this layer writes) are
+  // touched only from here on, when the previous kernel of the chain has completed
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -527,19 +531,8 @@ static int launch_layer(prg_handle* h, const CUtensorMap& mapA, const CUtensorMa
                                     (int)smem));
       const int units = (n_mblk / 2) * (p.N / BN);
       const int pairs = units < h->sm_count / 2 ? units : h->sm_count / 2;
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)(2 * pairs));
-      cfg.blockDim = dim3(kMlpPThreads);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = h->stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      PRG_CUDA(cudaLaunchKernelEx(&cfg, mlp_layer_persistent_kernel<BN, FINAL, true>, mapA, mapWhalf, mapOut, p, n_mblk));
+      PRG_CUDA(launch_chained(h, mlp_layer_persistent_kernel<BN, FINAL, true>, dim3((unsigned)(2 * pairs)), dim3(kMlpPThreads),
+                              smem, 2, mapA, mapWhalf, mapOut, p, n_mblk));
       count_launch(h);
       return PRG_OK;
     }
@@ -548,8 +541,8 @@ static int launch_layer(prg_handle* h, const CUtensorMap& mapA, const CUtensorMa
                                   (int)smem));
     const int tiles = n_mblk * (p.N / BN);
     const unsigned grid = (unsigned)(tiles < h->sm_count ? tiles : h->sm_count);
-    mlp_layer_persistent_kernel<BN, FINAL, false><<<grid, kMlpPThreads, smem, h->stream>>>(mapA, mapW, mapOut, p, n_mblk);
-    PRG_CUDA(cudaGetLastError());
+    PRG_CUDA(launch_chained(h, mlp_layer_persistent_kernel<BN, FINAL, false>, dim3(grid), dim3(kMlpPThreads), smem, 1, mapA, mapW,
+                            mapOut, p, n_mblk));
     count_launch(h);
     return PRG_OK;
   }

@@ -16,7 +16,7 @@ int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32
                      uint32_t* rows_sorted, double* scores_sorted);
 // dpp.cu
 int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
-               int32_t* out_idx, int32_t* out_n, int32_t* status);
+               int32_t* out_idx, int32_t* out_n, int32_t* status, DppFinal* fin = nullptr);
 
 // dpp_cluster.cu
 int dpp_cluster_prepare(prg_handle* h);
@@ -80,6 +80,8 @@ static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int M
 __global__ void final_gather_kernel(const uint32_t* rows, const double* scores, const int32_t* idx, const int32_t* cnt,
                                     const int32_t* status, int B, int n, int T, uint32_t* out_row, double* out_score,
                                     int32_t* out_n) {
+  pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
+  pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * T) return;
   const int b = i / T, t = i - b * T;
@@ -135,14 +137,17 @@ static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_
   // 3. ItemRankScore sort; the sort writes the sorted list for DPP itself
   PRG_TRY(sort_desc_device(h, (const double*)h->rec_scores.p, B, k, (int32_t*)h->rec_perm.p, (const uint32_t*)h->rec_rows.p,
                            (uint32_t*)h->rec_sorted_rows.p, (double*)h->rec_sorted_scores.p));
-  // 4. DPP
+  // 4. DPP; the cluster kernel writes the final outputs itself, the other kernels leave them to final_gather_kernel
+  DppFinal fin;
+  fin.row = out_row; fin.score = out_score; fin.n = out_n;
   PRG_TRY(dpp_device(h, (const uint32_t*)h->rec_sorted_rows.p, (const double*)h->rec_sorted_scores.p, B, k, p,
-                     (int32_t*)h->dpp_idx.p, (int32_t*)h->dpp_n.p, (int32_t*)h->dpp_status.p));
+                     (int32_t*)h->dpp_idx.p, (int32_t*)h->dpp_n.p, (int32_t*)h->dpp_status.p, &fin));
+  if (fin.done) return PRG_OK;
   const int tot = B * p.top_n;
-  final_gather_kernel<<<(tot + 255) / 256, 256, 0, h->stream>>>(
-      (const uint32_t*)h->rec_sorted_rows.p, (const double*)h->rec_sorted_scores.p, (const int32_t*)h->dpp_idx.p,
-      (const int32_t*)h->dpp_n.p, (const int32_t*)h->dpp_status.p, B, k, p.top_n, out_row, out_score, out_n);
-  PRG_CUDA(cudaGetLastError());
+  PRG_CUDA(launch_chained(h, final_gather_kernel, dim3((tot + 255) / 256), dim3(256), 0, 1,
+                          (const uint32_t*)h->rec_sorted_rows.p, (const double*)h->rec_sorted_scores.p,
+                          (const int32_t*)h->dpp_idx.p, (const int32_t*)h->dpp_n.p, (const int32_t*)h->dpp_status.p, B, k,
+                          p.top_n, out_row, out_score, out_n));
   count_launch(h);
   return PRG_OK;
 }

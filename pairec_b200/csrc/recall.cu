@@ -402,6 +402,8 @@ __global__ void __launch_bounds__(1024, 1) select_kernel(const SelectParams p) {
 // typically 2 passes over the keys instead of the 9 of the generic radix select.  Exact (keys are distinct).
 constexpr uint32_t kKthCap = 4096;
 __global__ void __launch_bounds__(1024, 1) select_kth_kernel(const SelectParams p) {
+  pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
+  pdl_launch_dependents();
   __shared__ uint32_t hist[2048];
   __shared__ uint64_t s_prefix, s_mask;
   __shared__ uint32_t s_want, s_bucket, s_fill;
@@ -501,6 +503,8 @@ __global__ void __launch_bounds__(32) rescore_kernel(const uint32_t* __restrict_
                                                      uint32_t n_seg, uint32_t seg_cap, uint32_t seg_group,
                                                      const float* __restrict__ E, const float* __restrict__ Q,
                                                      uint64_t row_base, uint64_t* __restrict__ seg_keys) {
+  pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
+  pdl_launch_dependents();
   constexpr int F4 = DIM / 4;            // 16-B pieces per row
   constexpr int RPI = 32 / F4;           // rows fetched per load instruction (2 at dim 64, 1 at dim 128)
   constexpr int PITCH = DIM + 4;         // floats; keeps both the row-wise stores and the lane-per-row loads conflict free
@@ -593,6 +597,8 @@ struct RefineParams {
 // (G times the queries, 1/G of the survivors each: several CTAs per SM instead of 3.5 waves of one).
 template <int NT>
 __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) refine_select_kernel(const RefineParams p) {
+  pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
+  pdl_launch_dependents();
   extern __shared__ uint64_t rs_keys[];          // [cap] exact keys, then [sort_cap] sort buffer
   __shared__ uint32_t seg_off[520];
   __shared__ uint32_t hist[256];
@@ -826,6 +832,8 @@ struct TopRParams {
 };
 template <int NT>
 __global__ void __launch_bounds__(NT) sample_topr_kernel(const TopRParams p) {
+  pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
+  pdl_launch_dependents();
   __shared__ uint64_t mx[256];
   __shared__ uint64_t cand[kTopRCap];
   __shared__ uint64_t s_t0;
@@ -932,11 +940,13 @@ static int launch_rescore(prg_handle* h, const float* q_dev, int nq, uint32_t n_
   while (group < 32 && per_seg * group < 24.0) group <<= 1;
   const dim3 grid((n_seg + group - 1) / group, (unsigned)nq);
   if (h->E_dim == 64)
-    rescore_kernel<64><<<grid, 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p, (const uint32_t*)h->cand_cnt.p, n_seg, seg_cap,
-                                                   group, h->E, q_dev, h->E_row_base, (uint64_t*)h->seg_keys.p);
+    PRG_CUDA(launch_chained(h, rescore_kernel<64>, grid, dim3(32), 0, 1, (const uint32_t*)h->seg_rows.p,
+                            (const uint32_t*)h->cand_cnt.p, n_seg, seg_cap, group, h->E, q_dev, h->E_row_base,
+                            (uint64_t*)h->seg_keys.p));
   else
-    rescore_kernel<128><<<grid, 32, 0, h->stream>>>((const uint32_t*)h->seg_rows.p, (const uint32_t*)h->cand_cnt.p, n_seg, seg_cap,
-                                                    group, h->E, q_dev, h->E_row_base, (uint64_t*)h->seg_keys.p);
+    PRG_CUDA(launch_chained(h, rescore_kernel<128>, grid, dim3(32), 0, 1, (const uint32_t*)h->seg_rows.p,
+                            (const uint32_t*)h->cand_cnt.p, n_seg, seg_cap, group, h->E, q_dev, h->E_row_base,
+                            (uint64_t*)h->seg_keys.p));
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;
@@ -948,10 +958,10 @@ static int launch_refine(prg_handle* h, const RefineParams& rp, int nq, size_t s
   StageScope span(h, ST_SELECT);
   if (nq > h->sm_count && smem <= 100 * 1024) {
     PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    refine_select_kernel<256><<<nq, 256, smem, h->stream>>>(rp);
+    PRG_CUDA(launch_chained(h, refine_select_kernel<256>, dim3(nq), dim3(256), smem, 1, rp));
   } else {
     PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    refine_select_kernel<1024><<<nq, 1024, smem, h->stream>>>(rp);
+    PRG_CUDA(launch_chained(h, refine_select_kernel<1024>, dim3(nq), dim3(1024), smem, 1, rp));
   }
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
@@ -961,7 +971,7 @@ static int launch_refine(prg_handle* h, const RefineParams& rp, int nq, size_t s
 static int launch_select(prg_handle* h, int mode, const SelectParams& p, int nq) {
   StageScope span(h, ST_SELECT);
   if (mode == SEL_KTH) {
-    select_kth_kernel<<<nq, 1024, kKthCap * 8, h->stream>>>(p);
+    PRG_CUDA(launch_chained(h, select_kth_kernel, dim3(nq), dim3(1024), kKthCap * 8, 1, p));
   } else {
     uint32_t K2 = 32;
     while (K2 < (uint32_t)p.k) K2 <<= 1;
@@ -988,9 +998,9 @@ static int launch_sample_select(prg_handle* h, int mode, SelectParams st, int nq
     tp.done = (int32_t*)h->topr_done.p;
     static const int force_nt = getenv("PRG_TOPR_NT") ? atoi(getenv("PRG_TOPR_NT")) : 0;   // experiments only
     const int nt = force_nt ? force_nt : (((uint64_t)st.fixed_m >= 32768 && nq <= 2 * h->sm_count) ? 1024 : 256);
-    if (nt == 1024) sample_topr_kernel<1024><<<nq, 1024, 0, h->stream>>>(tp);
-    else if (nt == 512) sample_topr_kernel<512><<<nq, 512, 0, h->stream>>>(tp);
-    else sample_topr_kernel<256><<<nq, 256, 0, h->stream>>>(tp);
+    if (nt == 1024) PRG_CUDA(launch_chained(h, sample_topr_kernel<1024>, dim3(nq), dim3(1024), 0, 1, tp));
+    else if (nt == 512) PRG_CUDA(launch_chained(h, sample_topr_kernel<512>, dim3(nq), dim3(512), 0, 1, tp));
+    else PRG_CUDA(launch_chained(h, sample_topr_kernel<256>, dim3(nq), dim3(256), 0, 1, tp));
     PRG_CUDA(cudaGetLastError());
     count_launch(h);
   }
@@ -1089,6 +1099,9 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
 
   // All query blocks go through each phase together: the scans run once per block of <= 64 queries, the selects
   // and the re-score once for the whole batch (one CTA per query), and there is ONE status read-back.
+  // (the survivor-count maximum is cleared up front: no memset between the kernels of the chain, see launch_chained)
+  uint32_t* max_cnt = (uint32_t*)h->cand_cnt.p + QT * n_seg;
+  PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
   // 1. sample
   PRG_TRY(score_sample(h, q_dev, B, sample_tiles, tile_stride, slots, use_tc));
   // 2. threshold = r-th largest sample key
@@ -1097,8 +1110,6 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   st.cap = st.fixed_m; st.k = (int)r_rank; st.tau = (uint64_t*)h->tau.p;
   PRG_TRY(launch_sample_select(h, SEL_KTH, st, B));
   // 3. full pass with the threshold test fused into the tile epilogue
-  uint32_t* max_cnt = (uint32_t*)h->cand_cnt.p + QT * n_seg;
-  PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
   const int pass_q = use_tc ? scan_tc_max_queries(h) : kQB;  // queries per pass over the matrix
   for (int q0 = 0; q0 < B; q0 += pass_q) {
     ScanParams sc{};

@@ -137,19 +137,6 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kTcEpiWarps); }
     mbar_fence_init();
   }
-  int bad = 0;
-  for (int q = tid; q < QTOT; q += kTcThreads) {
-    float sc = 0.f;
-    if (kDense) bad = 1;
-    else if (q < p.nq) {
-      const uint64_t t = p.tau[q];
-      const float tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
-      if (tf > 0x1p-60f && tf < 0x1p60f) sc = 1.0f / tf; else bad = 1;
-    }
-    s_scale[q] = sc;
-  }
-  const bool scaled = __syncthreads_or(bad) == 0 && !kDense;   // (also publishes the mbarrier initialisation)
-
   const uint32_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   // one tile = KH stages of data + its row norms
   auto issue_tile = [&](uint32_t i, uint32_t it) {
@@ -172,11 +159,27 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       }
     }
   };
-  // the first tiles are requested before the query operands are staged: the ring fills while the prologue runs
+  // The first tiles are requested at once, by the thread that initialised the barriers: the matrix and its norms are
+  // tables no kernel of the per-batch chain writes, so on a chained launch the ring fills while the previous kernel
+  // drains (everything below pdl_wait() reads what that kernel wrote: thresholds, queries) and while the query
+  // operands are staged.
   constexpr uint32_t kPrefetchTiles = kTcStages / KH;
   const uint32_t n_pre = my_tiles < kPrefetchTiles ? my_tiles : kPrefetchTiles;
   if (tid == 0)
     for (uint32_t i = 0; i < n_pre; ++i) issue_tile(i, i * KH);
+  pdl_wait();
+  int bad = 0;
+  for (int q = tid; q < QTOT; q += kTcThreads) {
+    float sc = 0.f;
+    if (kDense) bad = 1;
+    else if (q < p.nq) {
+      const uint64_t t = p.tau[q];
+      const float tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
+      if (tf > 0x1p-60f && tf < 0x1p60f) sc = 1.0f / tf; else bad = 1;
+    }
+    s_scale[q] = sc;
+  }
+  const bool scaled = __syncthreads_or(bad) == 0 && !kDense;   // (also publishes the mbarrier initialisation)
 
   // query blocks -> K-major SWIZZLE_128B B operands (16-B chunk index XOR row-in-group); padded queries are zero rows
   for (int i = tid; i < DIM * QTOT; i += kTcThreads) {
@@ -220,8 +223,12 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0)
+    if (lane == 0) {
       for (uint32_t i = n_pre; i < my_tiles; ++i) issue_tile(i, i * KH);
+      // every tile of this CTA is requested: the next kernel of the chain may start its prologue (it orders itself
+      // behind this grid with pdl_wait)
+      pdl_launch_dependents();
+    }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
@@ -477,8 +484,8 @@ static int launch_tc(prg_handle* h, const ScanParams& p) {
   if (BF && !h->E16_map_ok) return fail(PRG_ESTATE, "bf16 filter index not built");
   StageScope span(h, ST_SCAN);
   const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
-  recall_scan_tc_kernel<DIM, NQB, BF><<<grid, kTcThreads, smem, h->stream>>>(BF ? h->E16_map : h->E_map, p);
-  PRG_CUDA(cudaGetLastError());
+  PRG_CUDA(launch_chained(h, recall_scan_tc_kernel<DIM, NQB, BF>, dim3(grid), dim3(kTcThreads), smem, 1,
+                          BF ? h->E16_map : h->E_map, p));
   count_launch(h);
   return PRG_OK;
 }
@@ -494,8 +501,8 @@ static int launch_tc_dense(prg_handle* h, const ScanParams& p) {
   const unsigned gx = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
   const unsigned gy = (unsigned)((p.nq + kQB - 1) / kQB);
   if (gy > 65535u) return fail(PRG_EINVAL, "launch_scan_tc_dense: too many queries");
-  recall_scan_tc_kernel<DIM, 1, true, SCAN_DENSE><<<dim3(gx, gy), kTcThreads, smem, h->stream>>>(h->E16_map, p);
-  PRG_CUDA(cudaGetLastError());
+  PRG_CUDA(launch_chained(h, recall_scan_tc_kernel<DIM, 1, true, SCAN_DENSE>, dim3(gx, gy), dim3(kTcThreads), smem, 1,
+                          h->E16_map, p));
   count_launch(h);
   return PRG_OK;
 }

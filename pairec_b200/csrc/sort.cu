@@ -156,6 +156,8 @@ __device__ __forceinline__ uint64_t f64_ord(double d) {
 __global__ void __launch_bounds__(1024) sort_desc_kernel(const double* __restrict__ score, int n, int32_t* __restrict__ perm,
                                                          const uint32_t* __restrict__ rows, uint32_t* __restrict__ rows_o,
                                                          double* __restrict__ scores_o) {
+  pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
+  pdl_launch_dependents();
   extern __shared__ __align__(16) uint8_t sort_smem[];
   uint32_t P2 = 32;
   while (P2 < (uint32_t)n) P2 <<= 1;
@@ -200,9 +202,9 @@ int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32
   StageScope span(h, ST_SORT);
   if (smem > 48 * 1024)
     PRG_CUDA(cudaFuncSetAttribute(sort_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  sort_desc_kernel<<<B, P2 / 2 < 1024 ? (P2 / 2 < 32 ? 32 : P2 / 2) : 1024, smem, h->stream>>>(score_dev, n, perm_dev, rows_dev,
-                                                                                                rows_sorted, scores_sorted);
-  PRG_CUDA(cudaGetLastError());
+  const unsigned threads = P2 / 2 < 1024 ? (P2 / 2 < 32 ? 32 : P2 / 2) : 1024;
+  PRG_CUDA(launch_chained(h, sort_desc_kernel, dim3(B), dim3(threads), smem, 1, score_dev, n, perm_dev, rows_dev, rows_sorted,
+                          scores_sorted));
   count_launch(h);
   return PRG_OK;
 }
