@@ -77,6 +77,16 @@ void* prg_stream(prg_handle* h);
  * id of local row 0 (non-zero on a row shard).  Replaces the index held by the remote faiss server. */
 int prg_set_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_t dim, uint64_t row_base, int mem);
 
+/* Snapshot swap of the item matrix without stopping the service — the reference's vector DAO switches to the newest
+ * partition table in the background, once a minute (module/vector_hologres_dao.go:40-61).
+ * prg_stage_item_matrix uploads the new matrix and builds everything recall needs for it (bf16 filter index, row
+ * norms, tensor maps) on a side stream WITHOUT taking the handle's lock: calls on the handle keep being served from the
+ * live snapshot (both are resident meanwhile).  prg_commit_item_matrix swaps the snapshots between two batches and
+ * frees the old one; PRG_ESTATE if nothing is staged.  Staging again before a commit drops the earlier staged
+ * snapshot.  A PRG_MEM_DEVICE matrix is adopted, not copied, and must stay valid while it is staged or live. */
+int prg_stage_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_t dim, uint64_t row_base, int mem);
+int prg_commit_item_matrix(prg_handle* h);
+
 /* Per-item categorical field ids, rows x n_fields u32 row-major (what FeatureDao.FeatureFetch would have written
  * into item.Properties, module/feature_hologres_dao.go:644-675, already id-encoded). */
 int prg_set_item_fields(prg_handle* h, const uint32_t* ids, uint64_t rows, uint32_t n_fields, int mem);

@@ -17,6 +17,7 @@ _lib = None
 
 EXPORTS = [
     "prg_init", "prg_destroy", "prg_last_error", "prg_version", "prg_sync", "prg_stream", "prg_set_item_matrix",
+    "prg_stage_item_matrix", "prg_commit_item_matrix",
     "prg_set_item_fields", "prg_set_feature_table", "prg_set_fm_bias", "prg_set_mlp", "prg_set_diversity_matrix",
     "prg_recall_topk", "prg_recall_local_keys", "prg_merge_keys", "prg_shard_sample_len", "prg_shard_sample",
     "prg_shard_candidates", "prg_shard_check", "prg_rank", "prg_sort_desc_host", "prg_sort_desc",
@@ -166,6 +167,19 @@ class Engine:
         self._ck(self._lib.prg_set_item_matrix(self._h, _ptr(data), C.c_uint64(rows), C.c_uint32(dim),
                                                C.c_uint64(row_base), C.c_int(mem)))
         self.dim = dim
+
+    def stage_item_matrix(self, data, rows=None, dim=None, row_base=0, mem=MEM_HOST):
+        """Upload + index a new item matrix beside the live one (no handle lock held); commit_item_matrix swaps."""
+        if mem == MEM_HOST:
+            data = _np(data, np.float32)
+            rows, dim = data.shape
+        self._ck(self._lib.prg_stage_item_matrix(self._h, _ptr(data), C.c_uint64(rows), C.c_uint32(dim),
+                                                 C.c_uint64(row_base), C.c_int(mem)))
+        self._staged_dim = dim
+
+    def commit_item_matrix(self):
+        self._ck(self._lib.prg_commit_item_matrix(self._h))
+        self.dim = self._staged_dim
 
     def set_item_fields(self, ids, rows=None, n_fields=None, mem=MEM_HOST):
         if mem == MEM_HOST:

@@ -2,10 +2,12 @@
 // host-buffer / device-buffer wrappers around the kernels.  No CPU compute path exists here: without a CUDA device
 // prg_init fails with PRG_ENODEVICE.
 #include "handle.h"
+#include "recall.h"
 #include <cstring>
 #include <cstdlib>
 #include <cmath>
 #include <new>
+#include <utility>
 
 namespace prg {
 
@@ -99,6 +101,18 @@ static int take_table(const void* src, size_t bytes, int mem, const void** dst, 
   return PRG_OK;
 }
 
+// A staged item-matrix snapshot lives in a bare prg_handle of its own (only the item-matrix fields and a side stream are
+// used): the index builders of recall.cu / recall_tc.cu run on it unchanged while the live handle keeps serving.
+static void free_snapshot(prg_handle* s) {
+  if (!s) return;
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->E_owned && s->E) cudaFree(const_cast<float*>(s->E));
+  s->E16.release();
+  s->row_norm.release();
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
 }  // namespace prg
 
 using namespace prg;
@@ -158,6 +172,8 @@ void prg_destroy(prg_handle* h) {
   {
     Guard g(h);
     cudaStreamSynchronize(h->stream);
+    free_snapshot(h->staged);
+    h->staged = nullptr;
     if (h->E_owned && h->E) cudaFree(const_cast<float*>(h->E));
     if (h->fields_owned && h->fields) cudaFree(const_cast<uint32_t*>(h->fields));
     if (h->D_owned && h->D) cudaFree(const_cast<void*>(h->D));
@@ -245,6 +261,62 @@ int prg_set_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_
   h->row_norm.release();  // norms and the bf16 filter index are rebuilt lazily for the new matrix
   h->E16_map_ok = false;
   return recall_build_map(h);
+}
+
+// Snapshot swap (the reference's VectorHologresDao switches to a new partition table once a minute
+// without stopping the service, module/vector_hologres_dao.go:40-61).  Stage: upload + bf16 filter index + row norms +
+// tensor maps of the NEW matrix on a side stream, without the handle's lock — requests keep running on the live
+// snapshot (both are resident meanwhile: size for 2 x (6 B per element + 4 B per row)).  Commit: between two batches,
+// under the lock, the two snapshots change places and the old one is freed; the first request after the commit pays
+// nothing extra (prg_set_item_matrix rebuilds the index lazily inside the first recall instead).
+int prg_stage_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_t dim, uint64_t row_base, int mem) {
+  CHECK_H(h);
+  if (!data || rows == 0) return fail(PRG_EINVAL, "empty item matrix");
+  if (dim != 64 && dim != 128) return fail(PRG_EUNSUPPORTED, "item matrix dim must be 64 or 128");
+  if ((reinterpret_cast<uintptr_t>(data) & 15) && mem == PRG_MEM_DEVICE)
+    return fail(PRG_EINVAL, "device item matrix must be 16-byte aligned");
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != h->device) cudaSetDevice(h->device);
+  struct Restore { int prev, dev; ~Restore() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); } } restore{prev, h->device};
+  prg_handle* s = new (std::nothrow) prg_handle();
+  if (!s) return fail(PRG_ENOMEM, "snapshot allocation failed");
+  s->device = h->device; s->sm_count = h->sm_count;
+  s->scan_filter = h->scan_filter; s->scan_ffma2 = h->scan_ffma2; s->pdl = false;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete s; return fail(PRG_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+  const void* d = nullptr;
+  int rc = take_table(data, (size_t)rows * dim * 4, mem, &d, &s->E_owned);
+  if (rc == PRG_OK) {
+    s->E = (const float*)d; s->E_rows = rows; s->E_dim = dim; s->E_row_base = row_base;
+    rc = recall_build_map(s);
+  }
+  if (rc == PRG_OK && !s->scan_ffma2) rc = build_row_norms(s);   // norms + bf16 index + its map; waits for s->stream
+  if (rc != PRG_OK) { free_snapshot(s); return rc; }
+  prg_handle* old = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    old = h->staged;         // a snapshot staged earlier and never committed is dropped
+    h->staged = s;
+  }
+  free_snapshot(old);
+  return PRG_OK;
+}
+
+int prg_commit_item_matrix(prg_handle* h) {
+  CHECK_H(h);
+  Guard g(h);                // also settles a deferred recall check — against the snapshot it ran on
+  if (!h->staged) return fail(PRG_ESTATE, "no staged item matrix (prg_stage_item_matrix)");
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  prg_handle* s = h->staged;
+  h->staged = nullptr;
+  std::swap(h->E, s->E); std::swap(h->E_owned, s->E_owned); std::swap(h->E_rows, s->E_rows);
+  std::swap(h->E_dim, s->E_dim); std::swap(h->E_row_base, s->E_row_base);
+  std::swap(h->E_map, s->E_map); std::swap(h->E_map_ok, s->E_map_ok);
+  std::swap(h->E16, s->E16); std::swap(h->E16_map, s->E16_map); std::swap(h->E16_map_ok, s->E16_map_ok);
+  std::swap(h->row_norm, s->row_norm);
+  free_snapshot(s);          // the previous snapshot
+  return PRG_OK;
 }
 
 // ------------------------------------------------------------------ recall

@@ -11,6 +11,7 @@
 // candidate read one 64-B row in a single request); fields are walked in order, 8 independent loads in flight per
 // lane.  HBM-bound: algorithmic bytes per candidate = F*4 (ids) + F*fdim*4 (rows) + F*4 (linear) + 4 (logit).
 #include "handle.h"
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 namespace prg {
@@ -25,8 +26,8 @@ __device__ __forceinline__ uint16_t bf16_bits(float f) { return __bfloat16_as_us
 __device__ __forceinline__ float bf16_val(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
 
 // X layout: [M][2*F*16] bf16: hi at column f*16+k, lo at F*16 + f*16+k.
-template <int F_UNROLL>
-__global__ void __launch_bounds__(256)
+template <int F_UNROLL, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS)
 gather_fm_kernel(const uint32_t* __restrict__ rows, const uint64_t* __restrict__ keys, uint32_t* __restrict__ rows_out,
                  int M, const uint32_t* __restrict__ fields, uint64_t field_rows,
                  int F, const __grid_constant__ TableSet ts, float w0, float* __restrict__ logit_out,
@@ -134,8 +135,14 @@ int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logi
   const int threads = 256;
   const long long total = (long long)M * 4;
   const unsigned grid = (unsigned)((total + threads - 1) / threads);
-  PRG_CUDA(launch_chained(h, gather_fm_kernel<8>, dim3(grid), dim3(threads), 0, 1, rows_dev, keys_dev, rows_out, M, h->fields,
-                          h->fields_rows, (int)h->n_fields, ts, h->fm_w0, logit_dev, x_dev));
+  static const int min_ctas = getenv("PRG_GATHER_MINB") ? atoi(getenv("PRG_GATHER_MINB")) : 4;   // A/B measurements
+  // 4 CTAs per SM (64 registers) instead of 3: the kernel is bound by the row loads it keeps in flight (0.097 -> 0.090 ms)
+  if (min_ctas == 4)
+    PRG_CUDA(launch_chained(h, gather_fm_kernel<8, 4>, dim3(grid), dim3(threads), 0, 1, rows_dev, keys_dev, rows_out, M, h->fields,
+                            h->fields_rows, (int)h->n_fields, ts, h->fm_w0, logit_dev, x_dev));
+  else
+    PRG_CUDA(launch_chained(h, gather_fm_kernel<8, 3>, dim3(grid), dim3(threads), 0, 1, rows_dev, keys_dev, rows_out, M, h->fields,
+                            h->fields_rows, (int)h->n_fields, ts, h->fm_w0, logit_dev, x_dev));
   count_launch(h);
   return PRG_OK;
 }

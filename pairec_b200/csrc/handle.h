@@ -51,6 +51,10 @@ struct prg_handle {
   CUtensorMap E_map;
   bool E_map_ok = false;
 
+  // a second, fully built snapshot of the item matrix (fp32 rows, bf16 filter index, row norms, tensor maps) staged by
+  // prg_stage_item_matrix while this one serves; prg_commit_item_matrix swaps the two between batches (capi.cu)
+  prg_handle* staged = nullptr;
+
   prg::DevBuf q_dev;        // B x dim f32 (host-call staging)
   prg::DevBuf sample_keys;  // QB x sample_slots u64
   prg::DevBuf cand_keys;    // QB x cand_cap u64 (packed candidates)

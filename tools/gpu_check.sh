@@ -6,7 +6,7 @@ TAG=${1:-check}
 timeout 420 python -m pytest tests -m gpu -q --timeout 180 2>&1 | tail -15 > gpurun_out/${TAG}_pytest.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1
 timeout 300 python bench.py --steps 200 --warmup 5 > gpurun_out/${TAG}_bench.log 2>&1
-PRG_PDL=0 timeout 200 python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-batcher > gpurun_out/${TAG}_bench_nopdl.log 2>&1
+[ -n "${SKIP_NOPDL:-}" ] || PRG_PDL=0 timeout 200 python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-batcher > gpurun_out/${TAG}_bench_nopdl.log 2>&1
 NCU="ncu --clock-control none --kernel-name-base demangled -k regex:prg::"
 timeout 300 $NCU --metrics gpu__time_duration.sum -s 40 -c 100 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-batcher > gpurun_out/${TAG}_launches_bench.log 2>&1
