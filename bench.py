@@ -511,8 +511,10 @@ def main():
                    "unloaded_request_p50_ms": float(np.percentile(lat1, 50)) / 1e3,
                    "unloaded_request_p99_ms": float(np.percentile(lat1, 99)) / 1e3,
                    "answers_equal_direct_batch_call": same,
-                   "note": "prg_batcher_recommend: one request per host thread, coalesced into prg_recommend batches "
-                           "(host buffers, copies inside); latency = per request, queueing included"}
+                   "pipelined": os.environ.get("PRG_BATCHER_PIPELINE", "1") != "0",
+                   "note": "prg_batcher_recommend: one request per host thread, coalesced into batches of the fused path "
+                           "(host buffers, copies inside; a full batch is enqueued behind the running one when "
+                           "pipelined); latency = per request, queueing included"}
 
     shard_retries = None
     if world > 1 and protocol == "global":

@@ -11,11 +11,16 @@
 // Policy (continuous batching): the worker dispatches as soon as the GPU is free and at least one request waits, so
 // an idle server adds no queueing delay; while a batch runs (≈ 1 ms) the next one fills.  `max_wait_us` > 0 lets a
 // batch that is not yet full wait that long (measured from its first request) for more requests to join.
+// Pipelining (default; PRG_BATCHER_PIPELINE=0 restores the one-batch-at-a-time turn taking): a FULL batch does not
+// wait for the GPU to free up — it is enqueued behind the running one (recommend_begin / recommend_end, pipeline.cu),
+// so under load the device never idles between batches (≈ 60 µs per batch of host wake-up, H2D and launch latency
+// otherwise); at most two batches are in flight, and a batch that is not full still forms at the last moment.
 // Requests wait in ONE FIFO queue (arrival order == service order); each caller sleeps on its own condition variable,
 // so finishing a batch wakes exactly its callers.
 #include "handle.h"
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <thread>
@@ -61,8 +66,13 @@ struct prg_batcher {
   std::string last_err[2];
   uint64_t n_requests = 0, n_batches = 0;
   uint64_t hist[9] = {0};  // batch sizes: 1, 2, 3-4, 5-8, 9-16, 17-32, 33-64, 65-128, 129+
+  bool pipeline = true;    // a full batch is enqueued behind the running one
+  int gpu_busy = 0;        // batches enqueued and not yet finished (pipelined mode; guarded by mu)
+  cudaEvent_t done[2] = {nullptr, nullptr};
 
   void run(int w);
+  void run_pipelined(int w);
+  void deliver(int w, std::vector<Request*>& batch, int rc);
 };
 
 // Two workers take turns: the one holding `gpu_turn` forms its batch at the last moment (when the previous batch has
@@ -71,7 +81,6 @@ struct prg_batcher {
 void prg_batcher::run(int w) {
   cudaSetDevice(h->device);
   Staging& st = stage[w];
-  const size_t T = (size_t)cfg.dpp.top_n;
   std::vector<Request*> batch;
   batch.reserve((size_t)cfg.max_batch);
   for (;;) {
@@ -95,25 +104,82 @@ void prg_batcher::run(int w) {
     const int rc = prg_recommend(h, st.q, B, cfg.recall_k, cfg.model, &cfg.dpp, st.rows, st.scores, st.n, PRG_MEM_HOST);
     if (rc != PRG_OK) last_err[w] = prg_last_error();
     turn.unlock();
-    if (rc == PRG_OK) {  // the callers are blocked: their output buffers are ours to fill
-      for (int i = 0; i < B; ++i) {
-        std::memcpy(batch[i]->out_row, st.rows + (size_t)i * T, T * 4);
-        std::memcpy(batch[i]->out_score, st.scores + (size_t)i * T, T * 8);
-        *batch[i]->out_n = st.n[i];
+    deliver(w, batch, rc);
+  }
+}
+
+// results of worker w's staging buffers -> the callers' buffers; statistics; wake the callers
+void prg_batcher::deliver(int w, std::vector<Request*>& batch, int rc) {
+  Staging& st = stage[w];
+  const size_t T = (size_t)cfg.dpp.top_n;
+  const int B = (int)batch.size();
+  if (rc == PRG_OK) {  // the callers are blocked: their output buffers are ours to fill
+    for (int i = 0; i < B; ++i) {
+      std::memcpy(batch[i]->out_row, st.rows + (size_t)i * T, T * 4);
+      std::memcpy(batch[i]->out_score, st.scores + (size_t)i * T, T * 8);
+      *batch[i]->out_n = st.n[i];
+    }
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  n_batches += 1;
+  n_requests += (uint64_t)B;
+  int bin = 0;
+  for (int v = B - 1; v > 0 && bin < 8; v >>= 1) ++bin;
+  hist[bin] += 1;
+  for (int i = 0; i < B; ++i) {  // notify under the lock: a Request may be destroyed as soon as its owner sees `done`
+    batch[i]->rc = rc;
+    if (rc != PRG_OK) batch[i]->err = last_err[w];
+    batch[i]->done = true;
+    batch[i]->cv.notify_one();
+  }
+}
+
+// Pipelined turn taking: the worker holding `gpu_turn` forms a batch when the device is idle (gpu_busy == 0: exactly
+// the policy of run()) OR when a full batch waits and at most one batch is in flight; it ENQUEUES the batch
+// (recommend_begin returns once the copies and launches are in the stream), passes the turn on, and only then waits
+// for its results.  The other worker's full batch therefore sits in the stream behind this one.
+void prg_batcher::run_pipelined(int w) {
+  cudaSetDevice(h->device);
+  Staging& st = stage[w];
+  std::vector<Request*> batch;
+  batch.reserve((size_t)cfg.max_batch);
+  for (;;) {
+    std::unique_lock<std::mutex> turn(gpu_turn);
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      auto ready = [&] {
+        if (queue.empty()) return stop;
+        return gpu_busy == 0 || (gpu_busy < 2 && (int)queue.size() >= cfg.max_batch);
+      };
+      cv_worker.wait(lk, ready);
+      if (queue.empty()) return;  // stop, and nothing left to serve
+      if (cfg.max_wait_us > 0 && (int)queue.size() < cfg.max_batch && !stop) {
+        const auto deadline = queue.front()->arrived + std::chrono::microseconds(cfg.max_wait_us);
+        cv_worker.wait_until(lk, deadline, [&] { return stop || (int)queue.size() >= cfg.max_batch; });
       }
+      batch.clear();
+      while (!queue.empty() && (int)batch.size() < cfg.max_batch) {
+        batch.push_back(queue.front());
+        queue.pop_front();
+      }
+      ++gpu_busy;
     }
-    std::lock_guard<std::mutex> lk(mu);
-    n_batches += 1;
-    n_requests += (uint64_t)B;
-    int bin = 0;
-    for (int v = B - 1; v > 0 && bin < 8; v >>= 1) ++bin;
-    hist[bin] += 1;
-    for (int i = 0; i < B; ++i) {  // notify under the lock: a Request may be destroyed as soon as its owner sees `done`
-      batch[i]->rc = rc;
-      if (rc != PRG_OK) batch[i]->err = last_err[w];
-      batch[i]->done = true;
-      batch[i]->cv.notify_one();
+    const int B = (int)batch.size();
+    for (int i = 0; i < B; ++i) std::memcpy(st.q + (size_t)i * dim, batch[i]->q, (size_t)dim * 4);
+    uint64_t seq = 0;
+    int rc = recommend_begin(h, st.q, B, cfg.recall_k, cfg.model, cfg.dpp, st.rows, st.scores, st.n, done[w], &seq);
+    if (rc != PRG_OK) last_err[w] = prg_last_error();
+    turn.unlock();
+    if (rc == PRG_OK) {
+      rc = recommend_end(h, seq, done[w]);
+      if (rc != PRG_OK) last_err[w] = prg_last_error();
     }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      --gpu_busy;
+    }
+    cv_worker.notify_all();   // the device has one batch less: a waiting worker may form a partial batch now
+    deliver(w, batch, rc);
   }
 }
 
@@ -146,7 +212,17 @@ int prg_batcher_start(prg_handle* h, const prg_batcher_config* cfg, prg_batcher*
       return fail(PRG_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
     }
   }
-  for (int w = 0; w < 2; ++w) b->worker[w] = std::thread([b, w] { b->run(w); });
+  if (const char* ev = getenv("PRG_BATCHER_PIPELINE")) b->pipeline = atoi(ev) != 0;
+  for (int w = 0; w < 2; ++w) {
+    if (cudaEventCreateWithFlags(&b->done[w], cudaEventDisableTiming) != cudaSuccess) {
+      for (Staging& t : b->stage) t.release();
+      for (cudaEvent_t e : b->done) if (e) cudaEventDestroy(e);
+      delete b;
+      return fail(PRG_ECUDA, "cudaEventCreate failed");
+    }
+  }
+  for (int w = 0; w < 2; ++w)
+    b->worker[w] = std::thread([b, w] { if (b->pipeline) b->run_pipelined(w); else b->run(w); });
   *out = b;
   return PRG_OK;
 }
@@ -228,6 +304,7 @@ void prg_batcher_stop(prg_batcher* b) {
   }
   cudaSetDevice(b->h->device);
   for (Staging& t : b->stage) t.release();
+  for (cudaEvent_t e : b->done) if (e) cudaEventDestroy(e);
   delete b;
 }
 

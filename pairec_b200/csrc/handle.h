@@ -87,7 +87,17 @@ struct prg_handle {
     uint32_t* out_row = nullptr;
     double* out_score = nullptr;
     int32_t* out_n = nullptr;
+    // asynchronous host call (recommend_begin): where the results were copied to — a repair copies them again and
+    // re-records `done`
+    uint32_t* host_row = nullptr;
+    double* host_score = nullptr;
+    int32_t* host_n = nullptr;
+    cudaEvent_t done = nullptr;
+    uint64_t seq = 0;
   } pending;
+  uint64_t call_seq = 0;            // asynchronous host calls issued so far
+  uint64_t repaired_seq[4] = {0};   // the most recent asynchronous calls whose results were repaired (ring)
+  uint32_t repaired_pos = 0;
   cudaEvent_t flags_ev = nullptr;
   int32_t* host_flags = nullptr;  // pinned, host_flags_cap + 1 ints
   size_t host_flags_cap = 0;
@@ -204,6 +214,13 @@ int recall_build_map(prg_handle* h);
 int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t* keys_out /*B x k*/, bool defer = false);
 int recall_resolve(prg_handle* h, bool* repaired);   // waits for the deferred status, redoes failed queries densely
 int resolve_pending(prg_handle* h);                  // pipeline.cu: recall_resolve + re-run of the fused downstream
+// pipeline.cu — the fused request path as an asynchronous pair (batcher.cu): `begin` enqueues H2D of the queries, all
+// stages and the D2H of the results into pinned buffers, records `done` and returns; `end` waits for `done`, settles
+// the recall's deferred check if nobody has yet and returns the call's status.  Several calls may be in flight on a
+// handle (stream order); the handle's lock is held only while a call is being enqueued.
+int recommend_begin(prg_handle* h, const float* q_pinned, int B, int recall_k, int model, const prg_dpp_params& p,
+                    uint32_t* out_row, double* out_score, int32_t* out_n, cudaEvent_t done, uint64_t* seq);
+int recommend_end(prg_handle* h, uint64_t seq, cudaEvent_t done);
 int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint32_t* out_row, float* out_score,
                     int32_t* out_n);
 int shard_sample_len(int k);

@@ -152,16 +152,79 @@ static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_
   return PRG_OK;
 }
 
+// D2H of a fused call's results (device staging -> the caller's pinned buffers), then `done`
+static int copy_results_to_host(prg_handle* h, int B, int top_n, const uint32_t* row_dev, const double* score_dev,
+                                const int32_t* n_dev, uint32_t* row, double* score, int32_t* n, cudaEvent_t done) {
+  const size_t TT = (size_t)B * top_n;
+  PRG_CUDA(cudaMemcpyAsync(row, row_dev, TT * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(score, score_dev, TT * 8, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(n, n_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (done) PRG_CUDA(cudaEventRecord(done, h->stream));
+  return PRG_OK;
+}
+
 int resolve_pending(prg_handle* h) {
   if (!h->pending.active) return PRG_OK;
   const bool fused = h->pending.fused;
   bool repaired = false;
   int rc = recall_resolve(h, &repaired);
-  if (rc == PRG_OK && repaired && fused)
+  if (rc == PRG_OK && repaired && fused) {
     rc = post_recall_device(h, h->pending.B, h->pending.k, h->pending.model, h->pending.p, h->pending.out_row,
                             h->pending.out_score, h->pending.out_n);
+    if (rc == PRG_OK && h->pending.host_row) {   // an asynchronous call: its first copies carried the unrepaired results
+      rc = copy_results_to_host(h, h->pending.B, h->pending.p.top_n, h->pending.out_row, h->pending.out_score,
+                                h->pending.out_n, h->pending.host_row, h->pending.host_score, h->pending.host_n,
+                                h->pending.done);
+      h->repaired_seq[h->repaired_pos++ & 3u] = h->pending.seq;
+    }
+  }
   if (rc != PRG_OK) { h->deferred_status = rc; h->deferred_msg = prg_last_error(); }
   return rc;
+}
+
+int recommend_begin(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params& p,
+                    uint32_t* out_row, double* out_score, int32_t* out_n, cudaEvent_t done, uint64_t* seq) {
+  DevGuard g(h);   // settles the previous call's deferred check first (its scratch is about to be reused)
+  if (!h->E) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
+  if (h->deferred_status != PRG_OK) { const int rc = h->deferred_status; h->deferred_status = PRG_OK; return fail(rc, "deferred: " + h->deferred_msg); }
+  const size_t TT = (size_t)B * p.top_n;
+  PRG_TRY(h->q_dev.ensure((size_t)B * h->E_dim * 4));
+  PRG_TRY(h->out_row.ensure(TT * 4 > (size_t)B * recall_k * 4 ? TT * 4 : (size_t)B * recall_k * 4));
+  PRG_TRY(h->rank_out.ensure(TT * 8));
+  PRG_TRY(h->flags.ensure((size_t)(B > 64 ? B : 64) * 4));
+  PRG_TRY(h->sort_perm.ensure((size_t)B * 4));
+  PRG_CUDA(cudaMemcpyAsync(h->q_dev.p, q, (size_t)B * h->E_dim * 4, cudaMemcpyHostToDevice, h->stream));
+  PRG_TRY(recommend_device(h, (const float*)h->q_dev.p, B, recall_k, model, p, (uint32_t*)h->out_row.p,
+                           (double*)h->rank_out.p, (int32_t*)h->sort_perm.p, /*resolve_now=*/false));
+  PRG_TRY(copy_results_to_host(h, B, p.top_n, (const uint32_t*)h->out_row.p, (const double*)h->rank_out.p,
+                               (const int32_t*)h->sort_perm.p, out_row, out_score, out_n, done));
+  *seq = ++h->call_seq;
+  if (h->pending.active) {
+    h->pending.host_row = out_row; h->pending.host_score = out_score; h->pending.host_n = out_n;
+    h->pending.done = done; h->pending.seq = *seq;
+  }
+  return PRG_OK;
+}
+
+int recommend_end(prg_handle* h, uint64_t seq, cudaEvent_t done) {
+  cudaSetDevice(h->device);
+  PRG_CUDA(cudaEventSynchronize(done));
+  int rc = PRG_OK;
+  bool repaired = false;
+  {
+    // the plain lock, not DevGuard: a LATER call's deferred check is not ours to wait for
+    std::unique_lock<std::mutex> lk(h->mu);
+    if (h->pending.active && h->pending.seq == seq) rc = resolve_pending(h);
+    for (uint64_t r : h->repaired_seq) repaired |= (r == seq);
+    if (rc == PRG_OK && h->deferred_status != PRG_OK) {
+      rc = h->deferred_status;
+      h->deferred_status = PRG_OK;
+      fail(rc, "deferred: " + h->deferred_msg);
+    }
+  }
+  if (rc != PRG_OK) return rc;
+  if (repaired) PRG_CUDA(cudaEventSynchronize(done));   // re-recorded behind the repaired results' copies
+  return PRG_OK;
 }
 
 }  // namespace prg

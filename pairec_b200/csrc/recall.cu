@@ -1167,6 +1167,8 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   PRG_CUDA(cudaEventRecord(h->flags_ev, h->stream));
   h->pending.active = true;
   h->pending.fused = false;
+  h->pending.host_row = nullptr; h->pending.host_score = nullptr; h->pending.host_n = nullptr;
+  h->pending.done = nullptr; h->pending.seq = 0;
   h->pending.B = B; h->pending.k = k; h->pending.q_dev = q_dev; h->pending.keys_out = keys_out;
   if (defer) return PRG_OK;
   bool repaired = false;

@@ -95,3 +95,54 @@ def test_batcher_reports_errors_to_every_caller_and_stops_cleanly():
         bat.close()   # idempotent
     finally:
         eng.close()
+
+
+def test_batched_requests_survive_a_repaired_recall():
+    """Adversarial row order (the sampled threshold fails for one query of the batch): the batcher's asynchronous call
+    has already copied the unrepaired results to the host when the deferred check trips; the repair must copy them
+    again before any caller is woken.  Every request still gets what the direct call returns."""
+    from pairec_b200 import DppParams, Engine
+    from pairec_b200.binding import MODEL_FM, Batcher
+    n, d, k, T = 400_000, 64, 500, 12
+    rng = np.random.default_rng(11)
+    E = (rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    n_tiles = (n + 255) // 256
+    stride = n_tiles // max(64, n_tiles // 128)
+    tile = np.arange(n) // 256
+    E[:, 0] = np.where(tile % stride == 0, 0.0, 1.0 + rng.random(n) * 0.5).astype(np.float32)
+    Q = (rng.standard_normal((24, d)) * 0.01).astype(np.float32)
+    Q[::3] = 0
+    Q[::3, 0] = 1.0                      # every third request defeats the strided sample
+    fields, factors, linear = synth.rank_tables(n_items=n, n_fields=32)
+    D = synth.diversity(n_items=n, dim=32)
+    eng = Engine(0)
+    try:
+        eng.set_item_matrix(E)
+        eng.set_item_fields(fields)
+        for t, (f, l) in enumerate(zip(factors, linear)):
+            eng.set_feature_table(t, f, l)
+        eng.set_fm_bias(0.05)
+        eng.set_diversity_matrix(D)
+        p = DppParams(top_n=T, alpha=1.0, window_size=10)
+        want_rows, want_scores, want_n = eng.recommend(Q, k, MODEL_FM, p)
+        assert eng.recall_stats()["fallback_queries"] >= 1
+        bat = Batcher(eng, k, MODEL_FM, p, max_batch=8, max_wait_us=0)
+        errors = []
+
+        def client(i):
+            try:
+                for _ in range(3):
+                    rows, scores = bat.recommend(Q[i])
+                    assert len(rows) == want_n[i]
+                    assert (rows == want_rows[i, :want_n[i]]).all(), f"request {i}: rows differ"
+                    assert (scores.view(np.uint64) == want_scores[i, :want_n[i]].view(np.uint64)).all()
+            except Exception as ex:  # noqa: BLE001
+                errors.append(ex)
+
+        th = [threading.Thread(target=client, args=(i,)) for i in range(Q.shape[0])]
+        [t.start() for t in th]
+        [t.join(timeout=120) for t in th]
+        assert not errors, errors[0]
+        bat.close()
+    finally:
+        eng.close()
