@@ -364,6 +364,10 @@ int dpp_cluster_device(prg_handle* h, const uint32_t* rows_dev, const double* sc
                        const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled,
                        DppFinal* fin);
 
+int dpp_pair_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n,
+                    const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled,
+                    DppFinal* fin);
+
 static size_t dpp_smem_bytes(int c_rows, int top_n) {
   return (size_t)c_rows * kDppMaxItems * 8 + 2 * kDppMaxItems * 8 + 520 * 8 + 32 * 8 + 32 * 4 + kDppMaxItems * 4 +
          (size_t)((top_n + 3) & ~3) * 4 + kDppMaxItems + 64;
@@ -388,6 +392,11 @@ int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev,
   if (!h->dpp_generic && h->dpp_lazy) {  // config "dpp_lazy": one CTA per request, lazy evaluation of the greedy step (dpp_lazy.cu)
     bool handled = false;
     PRG_TRY(dpp_lazy_device(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, &handled));
+    if (handled) return PRG_OK;
+  }
+  if (!h->dpp_generic && h->dpp_pair) {  // config "dpp_pair" (experimental): 2-CTA cluster per request, one wave per batch (dpp_pair.cu)
+    bool handled = false;
+    PRG_TRY(dpp_pair_device(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, &handled, fin));
     if (handled) return PRG_OK;
   }
   if (!h->dpp_generic) {  // default: 4-CTA cluster per request, features resident on chip (dpp_cluster.cu)

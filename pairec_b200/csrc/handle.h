@@ -136,6 +136,7 @@ struct prg_handle {
   uint32_t D_dim = 0;
   int D_dtype = PRG_F32;
   bool dpp_lazy = false;     // config "dpp_lazy": the lazy-evaluation kernel (dpp_lazy.cu) instead of the cluster kernel
+  bool dpp_pair = false;     // config "dpp_pair" (experimental, dpp_pair.cu): 2-CTA clusters with features in tensor memory
   bool dpp_generic = false;  // config "dpp_generic": force the one-CTA-per-request kernel (A/B measurements)
   prg::DevBuf dpp_scratch, dpp_rows, dpp_score, dpp_idx, dpp_n, dpp_status;
 

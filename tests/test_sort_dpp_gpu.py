@@ -126,6 +126,29 @@ def test_dpp_lazy_kernel_matches(oracle_lib):
         eng.close()
 
 
+@pytest.mark.skipif(__import__("os").environ.get("PRG_TEST_EXPERIMENTAL") != "1",
+                    reason="dpp_pair.cu is experimental (not yet run on a B200): PRG_TEST_EXPERIMENTAL=1 enables its tests")
+def test_dpp_pair_kernel_matches(oracle_lib):
+    # config dpp_pair: 2-CTA clusters, 512 candidates per CTA, features in registers + shared + TENSOR memory
+    # (csrc/dpp_pair.cu): same selection sequences, bit for bit; other shapes fall through to the cluster kernel
+    from pairec_b200 import Engine
+    eng = Engine(0, dpp_pair=1)
+    try:
+        _dpp_case(eng, oracle_lib, n=1000, dim=128, top_n=50, alpha=1.0, window_size=10)
+        _dpp_case(eng, oracle_lib, n=1024, dim=128, top_n=24, alpha=0.7, window_size=8)
+        _dpp_case(eng, oracle_lib, n=513, dim=128, top_n=50, alpha=1.0, window_size=10)    # second CTA nearly empty
+        _dpp_case(eng, oracle_lib, n=400, dim=128, top_n=23, alpha=1.0, window_size=10, norm_mode=1)
+        _dpp_case(eng, oracle_lib, n=400, dim=128, top_n=23, alpha=1.0, window_size=10, norm_mode=2)
+        _dpp_case(eng, oracle_lib, n=400, dim=128, top_n=23, alpha=1.0, window_size=10, candidate_count=300, min_score_percent=0.6)
+        _dpp_case(eng, oracle_lib, n=400, dim=128, top_n=23, alpha=0.5, window_size=10, normalize_emb=0)
+        _dpp_case(eng, oracle_lib, n=25, dim=128, top_n=50, alpha=1.0, window_size=10)   # candidates run out: index 0 repeats
+        _dpp_case(eng, oracle_lib, n=5, dim=128, top_n=3, alpha=1.0, window_size=10)
+        _hard_cases(eng, oracle_lib, 128)
+        _dpp_case(eng, oracle_lib, n=1000, dim=64, top_n=50, alpha=1.0, window_size=10)  # falls through
+    finally:
+        eng.close()
+
+
 def test_dpp_cluster_dims(engine, oracle_lib):
     for dim in (32, 64, 128):
         _dpp_case(engine, oracle_lib, n=1000, dim=dim, top_n=50, alpha=1.0, window_size=10)
