@@ -152,6 +152,24 @@ long long ph_recommend(ph_server* s, const char* request_json, char* out, unsign
   return need;
 }
 
+// doSort's head (DoSortHead / EmbeddingMissAboveThreshold) as a pure function, for the CPU tests: scores[n] and
+// has_emb[n] in, the indices of the list the reference holds when it loads the embeddings out (returns their count);
+// *missed = 1 when the share of items without an embedding exceeds the threshold (doSort then returns that list).
+long long ph_dosort_head(const double* scores, const unsigned char* has_emb, int n, int size, int candidate_cnt,
+                         double min_score_percent, double miss_threshold, int always_sort, int* out_idx, int* missed) {
+  if (!scores || !has_emb || !out_idx || !missed || n < 0) { g_err = "null argument"; return -1; }
+  std::vector<module::ItemPtr> items;
+  for (int i = 0; i < n; ++i) { auto it = module::NewItem(std::to_string(i)); it->Score = scores[i]; items.push_back(it); }
+  auto head = sort::DoSortHead(items, size, candidate_cnt, min_score_percent, always_sort != 0);
+  size_t missing = 0;
+  for (size_t i = 0; i < head.size(); ++i) {
+    out_idx[i] = std::stoi(head[i]->Id);
+    missing += has_emb[out_idx[i]] == 0;
+  }
+  *missed = sort::EmbeddingMissAboveThreshold(missing, head.size(), miss_threshold > 0 ? miss_threshold : 0.5) ? 1 : 0;
+  return (long long)head.size();
+}
+
 // sort/dpp_sort.go:224-233 embedding text -> doubles; returns the element count (writes up to cap)
 long long ph_parse_embedding(const char* text, const char* sep, double* out, unsigned long long cap) {
   auto v = ingest::ParseEmbeddingText(text ? text : "", sep ? sep : "");

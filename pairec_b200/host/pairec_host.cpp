@@ -65,6 +65,7 @@ Error LoadConfig(const std::string& json, RecommendConfig* out) {
     c.DPPConf.AbortRunCount = d["AbortRunCount"].as_int();
     c.DPPConf.CandidateCount = d["CandidateCount"].as_int();
     c.DPPConf.MinScorePercent = d["MinScorePercent"].as_number();
+    c.DPPConf.EmbMissedThreshold = d["EmbMissedThreshold"].as_number();
     c.DPPConf.NormalizeEmb = d["NormalizeEmb"].as_string();
     c.DPPConf.EnsurePositiveSim = d["EnsurePositiveSim"].as_string();
     c.DPPConf.FilterRetrieveIds = str_list(d["FilterRetrieveIds"]);
@@ -76,6 +77,7 @@ Error LoadConfig(const std::string& json, RecommendConfig* out) {
     c.SSDConf.AbortRunCount = sd["AbortRunCount"].as_int();
     c.SSDConf.CandidateCount = sd["CandidateCount"].as_int();
     c.SSDConf.MinScorePercent = sd["MinScorePercent"].as_number();
+    c.SSDConf.EmbMissedThreshold = sd["EmbMissedThreshold"].as_number();
     c.SSDConf.NormalizeEmb = sd["NormalizeEmb"].as_string();
     c.SSDConf.FilterRetrieveIds = str_list(sd["FilterRetrieveIds"]);
     out->SortConfs.push_back(c);
@@ -620,8 +622,37 @@ Error AlgoScoreSort::Sort(SortData* d) {
   return "";
 }
 
+std::vector<module::ItemPtr> DoSortHead(std::vector<module::ItemPtr> items, int size, int candidateCnt,
+                                        double minScorePercent, bool alwaysSort) {
+  if (items.empty()) return items;
+  const bool truncates = (candidateCnt > 0 || minScorePercent > 0) && (int)items.size() > size;
+  if (alwaysSort || truncates) {   // ssd_sort.go:301 sorts first, always; dpp_sort.go:281 only when it truncates
+    std::vector<double> key(items.size());
+    for (size_t i = 0; i < items.size(); ++i) key[i] = items[i]->Score;
+    go_sort_desc(items, key);
+  }
+  if (truncates) {
+    if (candidateCnt > 0) {
+      const int cnt = std::max(size, candidateCnt);
+      if (cnt < (int)items.size()) items.resize((size_t)cnt);
+    }
+    if (minScorePercent > 0 && (int)items.size() > size) {
+      int idx = size;
+      const double maxScore = items[0]->Score;
+      for (; idx < (int)items.size(); ++idx)
+        if (items[(size_t)idx]->Score / maxScore < minScorePercent) break;
+      items.resize((size_t)idx);
+    }
+  }
+  return items;
+}
+bool EmbeddingMissAboveThreshold(size_t missing, size_t total, double threshold) {
+  return total > 0 && (double)missing / (double)total > threshold;
+}
+
 GpuDPPSort::GpuDPPSort(const recconf::DPPSortConfig& c, std::shared_ptr<GpuCatalog> cat) : conf_(c), cat_(std::move(cat)) {
   if (conf_.WindowSize <= 0) conf_.WindowSize = 10;  // dpp_sort.go:89-91
+  if (conf_.EmbMissedThreshold <= 0) conf_.EmbMissedThreshold = 0.5;  // :85, :101-103
 }
 Error GpuDPPSort::Sort(SortData* d) {
   auto& candidates = d->Data;
@@ -646,6 +677,19 @@ Error GpuDPPSort::Sort(SortData* d) {
       rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFEu : r->second;  // unknown id: out-of-table row -> zero embedding
       score[i] = selected[i]->Score;
     }
+    // what doSort holds when it loads the embeddings, and returns on every error path (:280-300, :304-307, :317-320)
+    const std::vector<module::ItemPtr> head = DoSortHead(selected, ctx->Size, conf_.CandidateCount, conf_.MinScorePercent, false);
+    size_t missing = 0;
+    for (auto& it : head) missing += cat_->row_of.find(it->Id) == cat_->row_of.end();
+    if (EmbeddingMissAboveThreshold(missing, head.size(), conf_.EmbMissedThreshold)) {  // :246-249
+      ctx->LogError("load embedding table cache failed the number of items missing embedding is above threshold");
+      result = head;
+      result.insert(result.end(), backup.begin(), backup.end());
+      candidates.swap(result);
+      return "";
+    }
+    // (items without an embedding below the threshold: the reference draws UNSEEDED random unit vectors, :250-262 —
+    // not reproducible by construction; here they get a zero embedding and are never picked before the fill)
     prg_dpp_params p{};
     p.alpha = conf_.Alpha;
     p.top_n = ctx->Size;
@@ -657,8 +701,12 @@ Error GpuDPPSort::Sort(SortData* d) {
     std::vector<int32_t> idx((size_t)std::max(1, ctx->Size), -1);
     int32_t n = 0, st = 0;
     if (prg_dpp(cat_->h, rows.data(), score.data(), 1, (int)rows.size(), &p, idx.data(), &n, &st, PRG_MEM_HOST) != PRG_OK) {
-      ctx->LogError(std::string("build kernel matrix failed ") + prg_last_error());  // :317-320: items unchanged
-    } else if (st == 0) {
+      ctx->LogError(std::string("build kernel matrix failed ") + prg_last_error());  // :317-320: `return items`
+      result = head;
+    } else if (st != 0) {
+      ctx->LogError("build kernel matrix failed all item score is zero");                 // :385-388, :397-400
+      result = head;
+    } else {
       result.clear();
       for (int i = 0; i < n; ++i) {
         selected[(size_t)idx[(size_t)i]]->AddAlgoScore("dpp_relevance_score", score[(size_t)idx[(size_t)i]]);  // :411
@@ -672,6 +720,7 @@ Error GpuDPPSort::Sort(SortData* d) {
 }
 GpuSSDSort::GpuSSDSort(const recconf::SSDSortConfig& c, std::shared_ptr<GpuCatalog> cat) : conf_(c), cat_(std::move(cat)) {
   if (conf_.Gamma <= 0) conf_.Gamma = 0.25;     // ssd_sort.go:62,81-83
+  if (conf_.EmbMissedThreshold <= 0) conf_.EmbMissedThreshold = 0.5;  // :77, :96-98
   if (conf_.WindowSize <= 0) conf_.WindowSize = 5;  // :84-86
 }
 Error GpuSSDSort::Sort(SortData* d) {
@@ -697,6 +746,16 @@ Error GpuSSDSort::Sort(SortData* d) {
       rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFEu : r->second;
       score[i] = selected[i]->Score;
     }
+    const std::vector<module::ItemPtr> head = DoSortHead(selected, ctx->Size, conf_.CandidateCount, conf_.MinScorePercent, true);
+    size_t missing = 0;
+    for (auto& it : head) missing += cat_->row_of.find(it->Id) == cat_->row_of.end();
+    if (EmbeddingMissAboveThreshold(missing, head.size(), conf_.EmbMissedThreshold)) {  // ssd_sort.go:270-273, :334-337
+      ctx->LogError("load embedding table cache failed the number of items missing embedding is above threshold");
+      result = head;
+      result.insert(result.end(), backup.begin(), backup.end());
+      candidates.swap(result);
+      return "";
+    }
     prg_ssd_params p{};
     p.gamma = conf_.Gamma;
     p.top_n = ctx->Size;
@@ -709,7 +768,8 @@ Error GpuSSDSort::Sort(SortData* d) {
     std::vector<int32_t> idx((size_t)std::max(1, ctx->Size), -1);
     int32_t n = 0, st = 0;
     if (prg_ssd(cat_->h, rows.data(), score.data(), 1, (int)rows.size(), &p, idx.data(), &n, &st, PRG_MEM_HOST) != PRG_OK) {
-      ctx->LogError(std::string("module=SSDSort\terror=") + prg_last_error());  // items unchanged, as upstream on errors
+      ctx->LogError(std::string("module=SSDSort\terror=") + prg_last_error());  // `return items`: the sorted, cut list
+      result = head;
     } else {
       result.clear();
       for (int i = 0; i < n; ++i) result.push_back(selected[(size_t)idx[(size_t)i]]);

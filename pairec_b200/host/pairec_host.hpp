@@ -45,13 +45,13 @@ struct RecallConfig { std::string Name, RecallType, RecallAlgo, ItemType; int Re
 struct RankConfig { std::vector<std::string> RankAlgoList; std::string RankScore, Processor; int BatchCount = 0; };
 struct DPPSortConfig {
   std::string Name, NormalizeEmb, EnsurePositiveSim;
-  double Alpha = 0, MinScorePercent = 0;
+  double Alpha = 0, MinScorePercent = 0, EmbMissedThreshold = 0;   // recconf.go:960-979
   int WindowSize = 0, AbortRunCount = 0, CandidateCount = 0;
   std::vector<std::string> FilterRetrieveIds;
 };
 struct SSDSortConfig {  // recconf/recconf.go:980-1000
   std::string Name, NormalizeEmb;
-  double Gamma = 0, MinScorePercent = 0;
+  double Gamma = 0, MinScorePercent = 0, EmbMissedThreshold = 0;
   bool UseSSDStar = false;
   int WindowSize = 0, AbortRunCount = 0, CandidateCount = 0;
   std::vector<std::string> FilterRetrieveIds;
@@ -288,6 +288,14 @@ class AlgoScoreSort : public ISort {  // sort/algo_score_sort.go
   std::string sortByField_;
   double switchThreshold_;
 };
+// The head of doSort (sort/dpp_sort.go:271-300, sort/ssd_sort.go:298-331): the list the reference holds at the moment
+// it loads the embeddings — optionally sorted by score (Go sort order) and cut to max(size, CandidateCount), then to
+// the MinScorePercent prefix.  It is also what doSort RETURNS on every error path ("return items").
+std::vector<module::ItemPtr> DoSortHead(std::vector<module::ItemPtr> items, int size, int candidateCnt,
+                                        double minScorePercent, bool alwaysSort);
+// loadEmbeddingCache's guard (dpp_sort.go:246-249, ssd_sort.go:270-273): more than `threshold` of the items have no
+// embedding -> error -> doSort returns the head list unchanged
+bool EmbeddingMissAboveThreshold(size_t missing, size_t total, double threshold);
 // DPPSort.Sort (sort/dpp_sort.go:108-167) with the kernel-matrix + greedy part on the GPU (prg_dpp)
 class GpuDPPSort : public ISort {
  public:

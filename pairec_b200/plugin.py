@@ -111,3 +111,22 @@ def recall_cache_roundtrip(ids, scores, model):
     lib.ph_recall_cache_roundtrip(arr, sc, C.c_int(len(ids)), model.encode(), out, C.c_ulonglong(1 << 20), cache,
                                   C.c_ulonglong(1 << 20))
     return cache.value.decode(), json.loads(out.value.decode())
+
+
+def dosort_head(scores, has_emb, size, candidate_count=0, min_score_percent=0.0, miss_threshold=0.5, always_sort=False):
+    """The head of DPPSort/SSDSort.doSort (sort/dpp_sort.go:280-300, sort/ssd_sort.go:301-331) plus the embedding-miss
+    guard (:246-249): returns (indices of the list the reference holds when it loads embeddings, missed flag)."""
+    import numpy as np
+    lib = load_host_library()
+    lib.ph_dosort_head.restype = C.c_longlong
+    sc = np.ascontiguousarray(scores, dtype=np.float64)
+    he = np.ascontiguousarray(has_emb, dtype=np.uint8)
+    n = int(sc.shape[0])
+    out = np.empty(max(n, 1), dtype=np.int32)
+    missed = C.c_int(0)
+    cnt = lib.ph_dosort_head(sc.ctypes.data_as(C.c_void_p), he.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(size),
+                             C.c_int(candidate_count), C.c_double(min_score_percent), C.c_double(miss_threshold),
+                             C.c_int(1 if always_sort else 0), out.ctypes.data_as(C.c_void_p), C.byref(missed))
+    if cnt < 0:
+        raise HostError(lib.ph_last_error().decode())
+    return out[:cnt].copy(), bool(missed.value)

@@ -152,3 +152,50 @@ def test_ingest_formats():
     assert cache == "a:u2i:0.5,b:u2i:0.123456789,c:u2i:1e-07"             # fmt %v of float64 (vector_recall.go:107)
     assert [(d["item_id"], d["score"], d["retrieve_id"]) for d in back] == [("a", 0.5, "u2i"), ("b", 0.123456789, "u2i"),
                                                                            ("c", 1e-7, "u2i")]
+
+
+def test_dosort_head_truncation_and_embedding_miss_threshold(oracle_lib):
+    """DPPSort/SSDSort.doSort before the embeddings are needed (sort/dpp_sort.go:280-300, sort/ssd_sort.go:301-331) and
+    loadEmbeddingCache's guard (:246-249): the list doSort holds — and returns unchanged on every error path."""
+    from pairec_b200.plugin import dosort_head
+    rng = np.random.default_rng(3)
+    n, size = 300, 20
+    scores = np.round(rng.random(n), 2)          # ties on purpose: the order must be Go's sort order
+    all_emb = np.ones(n, dtype=np.uint8)
+
+    def want(cc, msp, always):
+        idx = np.arange(n)
+        trunc = (cc > 0 or msp > 0) and n > size
+        if always or trunc:
+            idx = np.asarray(oracle_lib.go_sort(scores))
+        if trunc:
+            if cc > 0 and max(size, cc) < len(idx):
+                idx = idx[:max(size, cc)]
+            if msp > 0 and len(idx) > size:
+                j = size
+                while j < len(idx) and scores[idx[j]] / scores[idx[0]] >= msp:
+                    j += 1
+                idx = idx[:j]
+        return idx
+
+    for cc, msp, always in [(0, 0.0, False), (0, 0.0, True), (100, 0.0, False), (10, 0.0, False), (0, 0.8, False),
+                            (150, 0.9, True), (1000, 0.5, False)]:
+        got, missed = dosort_head(scores, all_emb, size, cc, msp, always_sort=always)
+        assert (got == want(cc, msp, always)).all(), (cc, msp, always)
+        assert not missed
+    # the guard looks at the TRUNCATED list: 60 % of the best 100 have no embedding -> above the default 0.5
+    best100 = want(100, 0.0, False)
+    has = np.ones(n, dtype=np.uint8)
+    has[best100[:60]] = 0
+    got, missed = dosort_head(scores, has, size, 100, 0.0)
+    assert missed and (got == best100).all()
+    _, missed = dosort_head(scores, has, size, 100, 0.0, miss_threshold=0.7)      # EmbMissedThreshold raised
+    assert not missed
+    _, missed = dosort_head(scores, has, size, 0, 0.0)                            # 60 of 300 overall: below
+    assert not missed
+    has[:] = 0
+    has[best100[:50]] = 1                                                         # exactly half missing: not ABOVE
+    _, missed = dosort_head(scores, has, size, 100, 0.0)
+    assert not missed
+    got, missed = dosort_head(np.zeros(0), np.zeros(0, dtype=np.uint8), size)
+    assert len(got) == 0 and not missed
