@@ -19,6 +19,7 @@
 // epilogue, so the only HBM traffic is the matrix itself (algorithmic bytes = rows*dim*4 per <=64-query block).
 #include "handle.h"
 #include "recall.h"
+#include "bitonic.cuh"
 #include <cstdlib>
 #include <vector>
 
@@ -595,7 +596,7 @@ struct RefineParams {
 
 // NT threads per CTA: 1024 for the single-GPU shape (64 queries x ~4.6 k survivors, one CTA per SM), 256 for row shards
 // (G times the queries, 1/G of the survivors each: several CTAs per SM instead of 3.5 waves of one).
-template <int NT>
+template <int NT, bool FAST = false>   // FAST (experimental, PRG_FAST_SORT=1): the final sort by bitonic.cuh
 __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) refine_select_kernel(const RefineParams p) {
   pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
   pdl_launch_dependents();
@@ -736,6 +737,17 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) refine_select_kernel(c
   uint32_t K2 = 32;
   while (K2 < filled) K2 <<= 1;
   // ---- 4. bitonic sort, descending
+  bool sorted = false;
+  if constexpr (FAST && NT == 1024) {
+    if (K2 <= 1024u && p.cap >= 1024u) {   // one key per thread; the packed-key region is free and serves as exchange buffer
+      uint64_t e = (uint32_t)tid < p.sort_cap ? sk[tid] : 0ull;
+      e = bitonic_sort_1024(e, keys, [](uint64_t a, uint64_t b) { return a > b; });
+      if ((uint32_t)tid < p.sort_cap) sk[tid] = e;
+      __syncthreads();
+      sorted = true;
+    }
+  }
+  if (!sorted) {
   for (uint32_t size = 2; size <= K2; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
       for (uint32_t i = tid; i < (K2 >> 1); i += NT) {
@@ -746,6 +758,7 @@ __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) refine_select_kernel(c
       }
       __syncthreads();
     }
+  }
   }
   const uint32_t n_out = m < k ? m : k;
   for (uint32_t i = tid; i < (uint32_t)p.k_out; i += NT)
@@ -960,8 +973,14 @@ static int launch_refine(prg_handle* h, const RefineParams& rp, int nq, size_t s
     PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PRG_CUDA(launch_chained(h, refine_select_kernel<256>, dim3(nq), dim3(256), smem, 1, rp));
   } else {
+    static const bool fast = getenv("PRG_FAST_SORT") && atoi(getenv("PRG_FAST_SORT")) != 0;   // experimental
+    if (fast) {
+      PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PRG_CUDA(launch_chained(h, refine_select_kernel<1024, true>, dim3(nq), dim3(1024), smem, 1, rp));
+    } else {
     PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PRG_CUDA(launch_chained(h, refine_select_kernel<1024>, dim3(nq), dim3(1024), smem, 1, rp));
+    }
   }
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
