@@ -20,6 +20,7 @@
 #include "handle.h"
 #include "recall.h"
 #include "bitonic.cuh"
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -1027,6 +1028,38 @@ static int launch_sample_select(prg_handle* h, int mode, SelectParams st, int nq
   return launch_select(h, mode, st, nq);
 }
 
+// EXPERIMENTAL (config "recall_tilemax"): threshold from tile maxima.  The sample scan leaves ONE value per (sample tile,
+// query): the largest approximate score of the tile's 256 rows (recall_tc.cu, SCAN_TILEMAX).  tau = the r-th largest of a
+// query's T tile maxima: at least r sampled rows reach it, and the share of tiles whose maximum reaches it, r / T,
+// estimates the share of ROWS that do: -ln(1 - r/T) / 256 — the same statistic the r-th largest of all sample keys
+// gives, from T values per query instead of 256 T keys (C4: 40 MB of keys written and read twice per batch).  tau is a
+// pruning hint only; the refine step's check keeps the result exact for any tau.
+// One CTA per query: rank counting in shared memory (T <= 2048).
+__global__ void __launch_bounds__(256) tilemax_tau_kernel(const uint32_t* __restrict__ tile_max, uint64_t stride, uint32_t T,
+                                                          uint32_t r, uint64_t* __restrict__ tau) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ uint32_t v[2048];
+  __shared__ uint32_t s_pick;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const uint32_t* src = tile_max + (size_t)q * stride;
+  for (uint32_t i = tid; i < T; i += 256) v[i] = src[i];
+  if (tid == 0) s_pick = 0u;
+  __syncthreads();
+  for (uint32_t i = tid; i < T; i += 256) {
+    const uint32_t mine = v[i];
+    uint32_t rank = 0;   // values that come before `mine` in (value desc, index asc) order; exact only below r
+    for (uint32_t u = 0; u < T && rank < r; ++u) {
+      const uint32_t o = v[u];
+      rank += (o > mine || (o == mine && u < i)) ? 1u : 0u;
+    }
+    if (rank == r - 1) s_pick = mine;   // exactly one element has rank r - 1 (if T >= r)
+  }
+  __syncthreads();
+  // ordered score in the key's high word, row bits zero: a row whose exact score equals the threshold still reaches it
+  if (tid == 0) tau[q] = (T >= r && s_pick > 1u) ? ((uint64_t)s_pick << 32) : 0ull;
+}
+
 // Scores of the strided tile sample for B queries -> h->sample_keys [B][slots].  With the bf16 filter index the
 // tensor-core kernel scores it (approximate keys: tau is only a pruning hint); otherwise the exact FFMA2 kernel, one
 // launch with one grid row per block of 64 queries.
@@ -1121,6 +1154,27 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   // (the survivor-count maximum is cleared up front: no memset between the kernels of the chain, see launch_chained)
   uint32_t* max_cnt = (uint32_t*)h->cand_cnt.p + QT * n_seg;
   PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
+  // share of a tile's rows expected above the threshold, x = 256 * target / rows: the tile-maximum estimate needs x << 1
+  const double tile_x = (double)kTileRows * target / (double)h->E_rows;
+  if (h->recall_tilemax && use_tc && scan_tc_dense_available(h) && tile_x <= 0.35 && sample_tiles <= 2048) {
+    // 1'. one maximum per (sample tile, query);  2'. threshold = r_t-th largest tile maximum (experimental, see above)
+    uint32_t r_t = (uint32_t)((double)sample_tiles * (1.0 - exp(-tile_x)) + 0.999);
+    if (r_t < 24) r_t = 24;
+    ScanParams sp{};
+    sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
+    sp.n_tiles = sample_tiles; sp.tile_stride = tile_stride;
+    sp.row_norm = (const float*)h->row_norm.p;
+    sp.Q = q_dev; sp.nq = B;
+    sp.dense = (uint64_t*)h->sample_keys.p;   // used as u32 [B][sample_tiles]
+    sp.dense_stride = sample_tiles;
+    PRG_TRY(launch_scan_tc_tilemax(h, sp));
+    {
+      StageScope span(h, ST_SELECT);
+      PRG_CUDA(launch_chained(h, tilemax_tau_kernel, dim3(B), dim3(256), 0, 1, (const uint32_t*)h->sample_keys.p,
+                              (uint64_t)sample_tiles, sample_tiles, r_t, (uint64_t*)h->tau.p));
+      count_launch(h);
+    }
+  } else {
   // 1. sample
   PRG_TRY(score_sample(h, q_dev, B, sample_tiles, tile_stride, slots, use_tc));
   // 2. threshold = r-th largest sample key
@@ -1128,6 +1182,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   st.keys = (const uint64_t*)h->sample_keys.p; st.stride = slots; st.fixed_m = (uint32_t)slots;
   st.cap = st.fixed_m; st.k = (int)r_rank; st.tau = (uint64_t*)h->tau.p;
   PRG_TRY(launch_sample_select(h, SEL_KTH, st, B));
+  }
   // 3. full pass with the threshold test fused into the tile epilogue
   const int pass_q = use_tc ? scan_tc_max_queries(h) : kQB;  // queries per pass over the matrix
   for (int q0 = 0; q0 < B; q0 += pass_q) {

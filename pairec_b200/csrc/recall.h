@@ -15,7 +15,7 @@ constexpr int kStageBytes = kStageFloats * 4;        // 64 KiB
 constexpr int kStages = 3;
 constexpr int kSubTileFloats = kTileRows * 32;       // one TMA box: 256 rows x 32 floats (128 B)
 
-enum { SCAN_THRESH = 0, SCAN_DENSE = 1 };
+enum { SCAN_THRESH = 0, SCAN_DENSE = 1, SCAN_TILEMAX = 2 };   // TILEMAX: recall_tc.cu only (experimental)
 #ifndef SCAN_UNROLL
 #define SCAN_UNROLL 2
 #endif
@@ -78,5 +78,6 @@ int scan_tc_max_queries(const prg_handle* h);
 int build_row_norms(prg_handle* h);
 bool scan_tc_dense_available(const prg_handle* h);
 int launch_scan_tc_dense(prg_handle* h, const ScanParams& p);   // sample scoring (approximate keys) on the tensor cores
+int launch_scan_tc_tilemax(prg_handle* h, const ScanParams& p); // sample scoring reduced to one maximum per (tile, query)
 
 }  // namespace prg

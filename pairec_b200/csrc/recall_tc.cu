@@ -86,7 +86,7 @@ template <int DIM, int NQB, bool BF, int MODE = SCAN_THRESH>
 __global__ void __launch_bounds__(kTcThreads, 1)
 recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p_in) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr bool kDenseMode = MODE == SCAN_DENSE;
+  constexpr bool kDenseMode = MODE != SCAN_THRESH;   // DENSE and TILEMAX: no thresholds, one grid row per query block
   // DENSE launches carry one grid row per block of 64 queries (the sample is a few dozen tiles: tiles x query blocks
   // CTAs fill the machine, tiles alone do not); grid row y sees its own slice of the queries and of the output
   ScanParams p_adj = p_in;
@@ -94,7 +94,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     const int y = (int)blockIdx.y;
     p_adj.Q = p_in.Q + (size_t)y * kQB * DIM;
     p_adj.nq = p_in.nq - y * kQB < kQB ? p_in.nq - y * kQB : kQB;
-    p_adj.dense = p_in.dense + (size_t)y * kQB * p_in.dense_stride;
+    if constexpr (MODE == SCAN_DENSE) p_adj.dense = p_in.dense + (size_t)y * kQB * p_in.dense_stride;
   }
   const ScanParams& p = kDenseMode ? p_adj : p_in;
   constexpr int KH = BF ? 1 : DIM / 64;                    // stages per tile
@@ -105,7 +105,8 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   constexpr uint32_t kTmemCols = NQB == 1 ? 256 : 512;
   constexpr int QTOT = NQB * kQB;
   constexpr float kMargin = BF ? kTcMarginBf16 : kTcMarginTf32;
-  constexpr bool kDense = MODE == SCAN_DENSE;
+  constexpr bool kDense = MODE != SCAN_THRESH;
+  constexpr bool kTileMax = MODE == SCAN_TILEMAX;
   uint8_t* stage_base = smem;
   uint8_t* Qb = smem + (size_t)kTcStages * kStageB;  // B operands, K-major SWIZZLE_128B: tf32 [NQB][DIM/32][64 q][32 f32],
                                                      // bf16 [NQB][DIM/64][64 q][64 bf16]
@@ -209,6 +210,12 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     }
     tq[q] = make_float2(tf, nq2);
     s_cnt[q] = 0;
+  }
+  // TILEMAX: per-query maxima of the current tile, two buffers of 64 ordered scores, over tq (2 x 64 words, unused here)
+  uint32_t* tmax = reinterpret_cast<uint32_t*>(tq);
+  if constexpr (kTileMax) {
+    __syncthreads();   // the loop above wrote tq
+    for (int i = tid; i < 2 * kQB; i += kTcThreads) tmax[i] = 0u;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols));
@@ -317,7 +324,34 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
         const int nqb = p.nq - blk * kQB;  // queries of this block (may exceed 64; <= 0 for an unused block)
         uint32_t* scb = s_cnt + blk * kQB;
         const uint32_t qoff = (uint32_t)(blk * kQB);
-        if constexpr (kDense) {
+        if constexpr (kTileMax) {
+          // Sample for the threshold estimate, reduced on the spot: only the MAXIMUM score of each (tile, query) leaves
+          // the kernel (recall.cu: the r-th largest tile maximum is the threshold) — 4 bytes per tile and query instead
+          // of 8 per row and query.  Warp maximum per query (REDUX on the ordered score), lane q % 32 keeps query q's.
+          static_assert(!kTileMax || NQB == 1, "TILEMAX is launched with one query block per grid row");
+          uint32_t keep0 = 0u, keep1 = 0u;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const uint32_t o0 = __reduce_max_sync(0xffffffffu, valid ? f32_ord(__uint_as_float(v0[q])) : 0u);
+            const uint32_t o1 = __reduce_max_sync(0xffffffffu, valid ? f32_ord(__uint_as_float(v1[q])) : 0u);
+            if (lane == q) { keep0 = o0; keep1 = o1; }
+          }
+          uint32_t* tm = tmax + (i & 1u) * kQB;
+          atomicMax(&tm[lane], keep0);
+          atomicMax(&tm[32 + lane], keep1);
+          asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");   // the 8 epilogue warps: tile complete
+          if (ew == 0) {
+            const uint32_t tile = blockIdx.x + i * gridDim.x;      // launch tile index (< p.n_tiles)
+            uint32_t* out = reinterpret_cast<uint32_t*>(p_in.dense);
+            const uint32_t qg0 = (uint32_t)blockIdx.y * kQB;
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+              const int q = hq * 32 + lane;
+              if (q < nqb) out[(size_t)(qg0 + (uint32_t)q) * p.dense_stride + tile] = tm[q];
+              tm[q] = 0u;   // free for tile i + 2: the other warps get there only through the barrier of tile i + 1
+            }
+          }
+        } else if constexpr (kDense) {
           // lanes of a warp hold consecutive rows: for a fixed query the 32 keys are one contiguous 256-B store
           const uint64_t slot = (uint64_t)(blockIdx.x + i * gridDim.x) * kTileRows + (uint64_t)row_local;
 #pragma unroll
@@ -505,6 +539,30 @@ static int launch_tc_dense(prg_handle* h, const ScanParams& p) {
                           h->E16_map, p));
   count_launch(h);
   return PRG_OK;
+}
+
+// EXPERIMENTAL (config "recall_tilemax"): sample scoring that emits one maximum per (tile, query):
+// p.dense = u32 [nq][dense_stride], slot = launch tile
+template <int DIM>
+static int launch_tc_tilemax(prg_handle* h, const ScanParams& p) {
+  const size_t smem = scan_tc_smem_bytes<DIM, 1, true>();
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM, 1, true, SCAN_TILEMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
+  if (p.n_tiles == 0 || p.nq <= 0) return PRG_OK;
+  StageScope span(h, ST_SCAN_DENSE);
+  const unsigned gx = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
+  const unsigned gy = (unsigned)((p.nq + kQB - 1) / kQB);
+  if (gy > 65535u) return fail(PRG_EINVAL, "launch_scan_tc_tilemax: too many queries");
+  PRG_CUDA(launch_chained(h, recall_scan_tc_kernel<DIM, 1, true, SCAN_TILEMAX>, dim3(gx, gy), dim3(kTcThreads), smem, 1,
+                          h->E16_map, p));
+  count_launch(h);
+  return PRG_OK;
+}
+int launch_scan_tc_tilemax(prg_handle* h, const ScanParams& p) {
+  if (!scan_tc_dense_available(h)) return fail(PRG_ESTATE, "bf16 filter index not built");
+  if (h->E_dim == 64) return launch_tc_tilemax<64>(h, p);
+  if (h->E_dim == 128) return launch_tc_tilemax<128>(h, p);
+  return fail(PRG_EINVAL, "launch_scan_tc_tilemax: unsupported shape");
 }
 
 bool scan_tc_dense_available(const prg_handle* h) { return h->scan_filter == SCAN_FILTER_BF16 && h->E16_map_ok; }
