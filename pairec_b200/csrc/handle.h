@@ -61,6 +61,7 @@ struct prg_handle {
   prg::DevBuf seg_keys;     // QB x n_seg x seg_cap u64 keys (FFMA2 scan) or u32 rows (tensor-core filter)
   prg::DevBuf seg_rows;     // QB x n_seg x seg_cap u32 survivor rows of the tensor-core filter
   prg::DevBuf row_norm;     // rows f32: upper bounds of the item row norms (tensor-core filter margin)
+  bool scan128_nqb = false;     // config "scan128_nqb" (experimental): up to 256 queries per filter pass at dim 128
   bool recall_tilemax = false;  // config "recall_tilemax" (experimental): threshold from per-tile maxima of the sample
   bool scan_ffma2 = false;  // config "scan_ffma2": use the exact FFMA2 scan for the full pass as well
   int scan_filter = 0;      // config "scan_filter": 0 = bf16 shadow index (default), 1 = tf32 on the fp32 rows

@@ -44,7 +44,7 @@ constexpr float kTcMarginBf16 = 1.05f / 256.f;  // c = 1.05 * 2^-8
 template <int DIM, bool BF>
 constexpr int tc_stage_bytes() { return BF ? kTileRows * DIM * 2 : kStageBytes; }
 template <int DIM, int NQB, bool BF>
-constexpr int tc_stages() { return BF ? (DIM == 64 ? (NQB <= 2 ? 5 : 4) : 3) : ((NQB == 1 && DIM == 64) ? 3 : 2); }
+constexpr int tc_stages() { return BF ? (DIM == 64 ? (NQB <= 2 ? 5 : 4) : (NQB == 1 ? 3 : 2)) : ((NQB == 1 && DIM == 64) ? 3 : 2); }
 // The row norms of a tile travel with it (one 1 KiB bulk copy completing on the tile's `full` barrier) into a ring of
 // S + 3 slots: the producer may run S tiles ahead of the MMA warp and the MMA warp 2 tiles (accumulator buffers) ahead
 // of the epilogue, which reads the norms.
@@ -575,7 +575,12 @@ int launch_scan_tc_dense(prg_handle* h, const ScanParams& p) {
 }
 
 // queries per pass the kernel is built for: 64/128/256 at dim 64, 64 at dim 128 (shared-memory budget)
-int scan_tc_max_queries(const prg_handle* h) { return h->E_dim == 64 ? 256 : 64; }
+// EXPERIMENTAL (config "scan128_nqb", not yet run): 128/256 queries per pass at dim 128 over the bf16 index with a
+// 2-stage ring (C5: 1024 queries per shard are 4 passes over the index instead of 16)
+int scan_tc_max_queries(const prg_handle* h) {
+  if (h->E_dim == 64) return 256;
+  return (h->scan128_nqb && h->scan_filter == SCAN_FILTER_BF16) ? 256 : 64;
+}
 
 template <bool BF>
 static int launch_scan_tc_t(prg_handle* h, const ScanParams& p) {
@@ -587,6 +592,10 @@ static int launch_scan_tc_t(prg_handle* h, const ScanParams& p) {
   }
   if (h->E_dim == 128) {
     if (p.nq <= 64) return launch_tc<128, 1, BF>(h, p);
+    if constexpr (BF) {
+      if (h->scan128_nqb && p.nq <= 128) return launch_tc<128, 2, true>(h, p);
+      if (h->scan128_nqb && p.nq <= 256) return launch_tc<128, 4, true>(h, p);
+    }
     return fail(PRG_EINVAL, "launch_scan_tc: more than 64 queries per pass at dim 128");
   }
   return fail(PRG_EUNSUPPORTED, "item matrix dim must be 64 or 128");
