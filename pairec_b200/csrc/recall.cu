@@ -1156,10 +1156,11 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
   // share of a tile's rows expected above the threshold, x = 256 * target / rows: the tile-maximum estimate needs x << 1
   const double tile_x = (double)kTileRows * target / (double)h->E_rows;
-  if (h->recall_tilemax && use_tc && scan_tc_dense_available(h) && tile_x <= 0.35 && sample_tiles <= 2048) {
+  // tiles of the sample expected to hold a row above the threshold; below 24 the estimate is too noisy (small catalogs)
+  const double tile_r = (double)sample_tiles * (1.0 - exp(-tile_x));
+  if (h->recall_tilemax && use_tc && scan_tc_dense_available(h) && tile_x <= 0.35 && tile_r >= 24.0 && sample_tiles <= 2048) {
     // 1'. one maximum per (sample tile, query);  2'. threshold = r_t-th largest tile maximum (experimental, see above)
-    uint32_t r_t = (uint32_t)((double)sample_tiles * (1.0 - exp(-tile_x)) + 0.999);
-    if (r_t < 24) r_t = 24;
+    const uint32_t r_t = (uint32_t)(tile_r + 0.999);
     ScanParams sp{};
     sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
     sp.n_tiles = sample_tiles; sp.tile_stride = tile_stride;
