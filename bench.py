@@ -36,6 +36,10 @@ WORKLOADS = {
     # name: (items, dim, k, batch, n_fields, table_rows, mlp dims, div_dim, top_n, window)
     "c4": dict(items=10_000_000, dim=64, k=1000, batch=64, n_fields=32, table_rows=1_000_000,
                mlp=[512, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
+    # BASELINE.json config 5 (not yet run: needs 8 GPUs): 100 M x 128-d row-sharded, 128 requests per GPU = 1024 at N = 8;
+    # ~90 GB per GPU while the tables are generated (replicated fields / diversity tables)
+    "c5": dict(items=100_000_000, dim=128, k=1000, batch=128, n_fields=32, table_rows=1_000_000,
+               mlp=[512, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
     "small": dict(items=400_000, dim=64, k=1000, batch=64, n_fields=32, table_rows=50_000,
                   mlp=[512, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
 }
@@ -310,7 +314,8 @@ def main():
                            if os.environ.get("PRG_SHARD_PROTOCOL", "global") == "local" else
                            "global threshold: all-gather of per-shard sample keys, then all-gather of the candidates "
                            "that reach it") if world > 1 else "none"),
-              "l2": "inputs larger than L2 (item matrix / its 1.28 GB bf16 filter index streamed per step)"}
+              "l2": f"inputs larger than L2 (item matrix / its {w['items'] // world * w['dim'] * 2 / 1e9:.2f} GB bf16 filter "
+                    f"index streamed per step)"}
 
     if args.impl == "reference":
         if rank != 0:
