@@ -37,16 +37,15 @@ void DevBuf::release() {
 }
 
 PFN_encodeTiled get_encode_tiled() {
-  static PFN_encodeTiled fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // resolved once; a function-local static's initialisation is thread-safe (snapshots are staged from other threads)
+  static const PFN_encodeTiled fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
         qr == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(p);
-  }
+      return reinterpret_cast<PFN_encodeTiled>(p);
+    return static_cast<PFN_encodeTiled>(nullptr);
+  }();
   return fn;
 }
 
