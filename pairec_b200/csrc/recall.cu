@@ -1035,8 +1035,11 @@ static int launch_sample_select(prg_handle* h, int mode, SelectParams st, int nq
 // gives, from T values per query instead of 256 T keys (C4: 40 MB of keys written and read twice per batch).  tau is a
 // pruning hint only; the refine step's check keeps the result exact for any tau.
 // One CTA per query: rank counting in shared memory (T <= 2048).
+// out_keys (nullable): the r largest as order keys [q][r], sorted descending, 0-padded — what a shard contributes to the
+// global threshold (recall_shard_sample_device).
 __global__ void __launch_bounds__(256) tilemax_tau_kernel(const uint32_t* __restrict__ tile_max, uint64_t stride, uint32_t T,
-                                                          uint32_t r, uint64_t* __restrict__ tau) {
+                                                          uint32_t r, uint64_t* __restrict__ tau,
+                                                          uint64_t* __restrict__ out_keys) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ uint32_t v[2048];
@@ -1045,6 +1048,8 @@ __global__ void __launch_bounds__(256) tilemax_tau_kernel(const uint32_t* __rest
   const uint32_t* src = tile_max + (size_t)q * stride;
   for (uint32_t i = tid; i < T; i += 256) v[i] = src[i];
   if (tid == 0) s_pick = 0u;
+  if (out_keys)
+    for (uint32_t j = tid; j < r; j += 256) out_keys[(size_t)q * r + j] = 0ull;
   __syncthreads();
   for (uint32_t i = tid; i < T; i += 256) {
     const uint32_t mine = v[i];
@@ -1053,11 +1058,12 @@ __global__ void __launch_bounds__(256) tilemax_tau_kernel(const uint32_t* __rest
       const uint32_t o = v[u];
       rank += (o > mine || (o == mine && u < i)) ? 1u : 0u;
     }
+    // ordered score in the key's high word, row bits zero: a row whose exact score equals the threshold still reaches it
+    if (rank < r && out_keys) out_keys[(size_t)q * r + rank] = mine > 1u ? ((uint64_t)mine << 32) : 0ull;
     if (rank == r - 1) s_pick = mine;   // exactly one element has rank r - 1 (if T >= r)
   }
   __syncthreads();
-  // ordered score in the key's high word, row bits zero: a row whose exact score equals the threshold still reaches it
-  if (tid == 0) tau[q] = (T >= r && s_pick > 1u) ? ((uint64_t)s_pick << 32) : 0ull;
+  if (tid == 0 && tau) tau[q] = (T >= r && s_pick > 1u) ? ((uint64_t)s_pick << 32) : 0ull;
 }
 
 // Scores of the strided tile sample for B queries -> h->sample_keys [B][slots].  With the bf16 filter index the
@@ -1172,7 +1178,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     {
       StageScope span(h, ST_SELECT);
       PRG_CUDA(launch_chained(h, tilemax_tau_kernel, dim3(B), dim3(256), 0, 1, (const uint32_t*)h->sample_keys.p,
-                              (uint64_t)sample_tiles, sample_tiles, r_t, (uint64_t*)h->tau.p));
+                              (uint64_t)sample_tiles, sample_tiles, r_t, (uint64_t*)h->tau.p, (uint64_t*)nullptr));
       count_launch(h);
     }
   } else {
@@ -1373,6 +1379,29 @@ int recall_shard_sample_device(prg_handle* h, const float* q_dev, int Bg, int k,
   const int nblk = (Bg + kQB - 1) / kQB;
   PRG_TRY(h->sample_keys.ensure((size_t)nblk * kQB * pl.slots * 8));
   if (!h->row_norm.p) PRG_TRY(build_row_norms(h));
+  {
+    // EXPERIMENTAL (config "recall_tilemax", same on every rank): the shard contributes its r largest TILE MAXIMA instead
+    // of its r largest sample keys; the r-th largest of the gathered maxima estimates the same row share (the share of
+    // the G * T sample tiles that hold a row above tau is r / (G T) ~ 256 * target / rows for small shares).
+    const double rows_all = (double)h->E_rows * G;
+    const double tile_x = (double)kTileRows * 4.0 * (k < 1024 ? 1024 : k) / rows_all;
+    const double tile_r = (double)pl.sample_tiles * G * (1.0 - exp(-tile_x));
+    if (h->recall_tilemax && scan_tc_dense_available(h) && tile_x <= 0.35 && tile_r >= 24.0 && pl.sample_tiles <= 2048) {
+      ScanParams sp{};
+      sp.n_rows = h->E_rows; sp.row_base = h->E_row_base;
+      sp.n_tiles = pl.sample_tiles; sp.tile_stride = pl.tile_stride;
+      sp.row_norm = (const float*)h->row_norm.p;
+      sp.Q = q_dev; sp.nq = Bg;
+      sp.dense = (uint64_t*)h->sample_keys.p;   // used as u32 [Bg][sample_tiles]
+      sp.dense_stride = pl.sample_tiles;
+      PRG_TRY(launch_scan_tc_tilemax(h, sp));
+      StageScope span(h, ST_SELECT);
+      PRG_CUDA(launch_chained(h, tilemax_tau_kernel, dim3(Bg), dim3(256), 0, 1, (const uint32_t*)h->sample_keys.p,
+                              (uint64_t)pl.sample_tiles, pl.sample_tiles, pl.r, (uint64_t*)nullptr, out));
+      count_launch(h);
+      return PRG_OK;
+    }
+  }
   PRG_TRY(score_sample(h, q_dev, Bg, pl.sample_tiles, pl.tile_stride, pl.slots, true));
   SelectParams st{};
   st.keys = (const uint64_t*)h->sample_keys.p; st.stride = pl.slots; st.fixed_m = (uint32_t)pl.slots;

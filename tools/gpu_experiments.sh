@@ -14,7 +14,7 @@ PRG_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_sort_dpp_gpu.py 
 tail -5 gpurun_out/${TAG}_pytest_pair.log
 PRG_FAST_SORT=1 timeout 400 python -m pytest tests/test_sort_dpp_gpu.py tests/test_recall_gpu.py tests/test_pipeline_gpu.py -m gpu -q --timeout 200 2>&1 | tail -12 > gpurun_out/${TAG}_pytest_fastsort.log
 tail -3 gpurun_out/${TAG}_pytest_fastsort.log
-PRG_RECALL_TILEMAX=1 timeout 500 python -m pytest tests/test_recall_gpu.py tests/test_pipeline_gpu.py tests/test_full_size_gpu.py -m gpu -q --timeout 300 2>&1 | tail -12 > gpurun_out/${TAG}_pytest_tilemax.log
+PRG_RECALL_TILEMAX=1 timeout 500 python -m pytest tests/test_recall_gpu.py tests/test_pipeline_gpu.py tests/test_full_size_gpu.py tests/test_shard_gpu.py -m gpu -q --timeout 300 2>&1 | tail -12 > gpurun_out/${TAG}_pytest_tilemax.log
 tail -3 gpurun_out/${TAG}_pytest_tilemax.log
 tools/gpu_knobs.sh ${TAG}_knob "PRG_RECALL_TILEMAX=1" "PRG_RECALL_TILEMAX=1 PRG_DPP_PAIR=1 PRG_GATHER_HINTS=1 PRG_FAST_SORT=1"
 tools/gpu_knobs.sh ${TAG}_knob2 "" "PRG_DPP_PAIR=1" "PRG_GATHER_HINTS=1" "PRG_FAST_SORT=1" "PRG_DPP_PAIR=1 PRG_GATHER_HINTS=1 PRG_FAST_SORT=1"
