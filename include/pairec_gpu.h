@@ -217,7 +217,9 @@ int prg_recommend_from_keys(prg_handle* h, const uint64_t* keys_dev, int G, uint
  * BatchCount-sized RPCs, service/rank/rank_service.go:163-166, :264-289); the kernels serve up to 256 queries with one
  * pass over the item matrix.  The batcher coalesces concurrent single-request calls into prg_recommend batches:
  * it dispatches as soon as the GPU is free and a request waits (no added delay on an idle server); while a batch
- * runs, the next one fills.  max_wait_us > 0 lets a non-full batch wait that long after its first request. */
+ * runs, the next one fills, and a FULL batch is enqueued at once behind the running one (at most two in flight), so
+ * the device does not idle between batches.  max_wait_us > 0 lets a non-full batch wait that long after its first
+ * request. */
 typedef struct prg_batcher prg_batcher;
 typedef struct prg_batcher_config {
   int32_t max_batch;    /* 1..256 requests per prg_recommend call */
