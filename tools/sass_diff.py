@@ -43,8 +43,8 @@ def main():
         old_obj = os.path.join(tmp, f[:-3] + ".o")
         subprocess.run(NVCC + [f, "-o", old_obj], cwd=src, check=True, stderr=subprocess.DEVNULL)
         a, b = sass(old_obj), sass(new_obj)
-        for k, v in strips:
-            b = {name.replace(k, v): body for name, body in b.items()}
+        for k, v in strips:   # a new function also answers to its name with the added template argument removed
+            b.update({name.replace(k, v): body for name, body in list(b.items()) if name.replace(k, v) not in b})
         diff = {}
         for name, body in a.items():
             if name not in b:
