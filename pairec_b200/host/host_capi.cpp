@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "pairec_host.hpp"
+#include <cmath>
 
 using namespace pairec;
 
@@ -168,6 +169,46 @@ long long ph_dosort_head(const double* scores, const unsigned char* has_emb, int
   }
   *missed = sort::EmbeddingMissAboveThreshold(missing, head.size(), miss_threshold > 0 ? miss_threshold : 0.5) ? 1 : 0;
   return (long long)head.size();
+}
+
+// Item-feature column sets -> id-encoded fields (ingest::FieldEncoder).  spec_json: [{"column": "...", "vocab": [...]} |
+// {"column": "...", "id": true}, ...]; rows_json: one object per item = the properties a FeatureDao fetched for it
+// (a NULL column is simply absent).  out: n_items x n_fields u32.  Returns n_items * n_fields, or -1.
+long long ph_encode_fields(const char* spec_json, const char* rows_json, unsigned int* out, unsigned long long cap) {
+  if (!spec_json || !rows_json) { g_err = "null argument"; return -1; }
+  Json spec, rows;
+  std::string err;
+  if (!Json::parse(spec_json, &spec, &err) || spec.type != Json::Array) { g_err = "bad field spec JSON: " + err; return -1; }
+  if (!Json::parse(rows_json, &rows, &err) || rows.type != Json::Array) { g_err = "bad rows JSON: " + err; return -1; }
+  std::vector<ingest::FieldSpec> specs;
+  for (const Json& e : spec.arr) {
+    ingest::FieldSpec fs;
+    fs.Column = e["column"].as_string();
+    fs.IsId = e["id"].as_bool(false);
+    for (const Json& v : e["vocab"].arr) {
+      if (v.type == Json::String) fs.Vocab.push_back(v.str);
+      else if (v.type == Json::Number)
+        fs.Vocab.push_back(ingest::ToString(v.num == std::floor(v.num) && std::fabs(v.num) < 9e15 ? module::Value((int64_t)v.num)
+                                                                                                : module::Value(v.num)));
+    }
+    specs.push_back(std::move(fs));
+  }
+  const ingest::FieldEncoder enc(std::move(specs));
+  const size_t F = enc.size(), N = rows.arr.size();
+  if (out && cap >= N * F) {
+    for (size_t i = 0; i < N; ++i) {
+      module::Features props;
+      for (auto& kv : rows.arr[i].obj) {
+        if (kv.second.type == Json::String) props[kv.first] = kv.second.str;
+        else if (kv.second.type == Json::Number) {
+          if (kv.second.num == std::floor(kv.second.num) && std::fabs(kv.second.num) < 9e15) props[kv.first] = (int64_t)kv.second.num;
+          else props[kv.first] = kv.second.num;
+        }   // null / other kinds: no property, like a NULL column
+      }
+      enc.Encode(props, out + i * F);
+    }
+  }
+  return (long long)(N * F);
 }
 
 // sort/dpp_sort.go:224-233 embedding text -> doubles; returns the element count (writes up to cap)

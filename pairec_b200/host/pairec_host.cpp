@@ -2,6 +2,7 @@
 #include "pairec_host.hpp"
 
 #include <algorithm>
+#include <charconv>
 #include <cmath>
 #include <cstring>
 #include <sstream>
@@ -901,6 +902,34 @@ std::vector<double> ParseEmbeddingText(const std::string& text, const std::strin
     pos = nx + sep.size();
   }
   return out;
+}
+std::string ToString(const module::Value& v) {
+  if (const auto* s = std::get_if<std::string>(&v)) return *s;
+  if (const auto* i = std::get_if<int64_t>(&v)) return std::to_string(*i);
+  char buf[400];   // 'f' format of a double needs up to 309 integer digits
+  const auto r = std::to_chars(buf, buf + sizeof buf, std::get<double>(v), std::chars_format::fixed);
+  return std::string(buf, r.ptr);
+}
+FieldEncoder::FieldEncoder(std::vector<FieldSpec> specs) : specs_(std::move(specs)), rows_(specs_.size()) {
+  for (size_t f = 0; f < specs_.size(); ++f)
+    for (size_t i = 0; i < specs_[f].Vocab.size(); ++i) rows_[f].emplace(specs_[f].Vocab[i], (uint32_t)i);  // first wins
+}
+void FieldEncoder::Encode(const module::Features& properties, uint32_t* out) const {
+  for (size_t f = 0; f < specs_.size(); ++f) {
+    out[f] = kAbsent;
+    const auto it = properties.find(specs_[f].Column);
+    if (it == properties.end()) continue;   // NULL column: ParseColumnValues returned nil, no property was written
+    if (specs_[f].IsId) {
+      int64_t id = -1;
+      if (const auto* i = std::get_if<int64_t>(&it->second)) id = *i;
+      else if (const auto* d = std::get_if<double>(&it->second)) { if (*d >= 0 && *d == std::floor(*d) && *d < 4294967295.0) id = (int64_t)*d; }
+      else { char* end = nullptr; const std::string& s = std::get<std::string>(it->second); const long long v = strtoll(s.c_str(), &end, 10); if (!s.empty() && end && *end == 0) id = v; }
+      if (id >= 0 && id < 0xFFFFFFFFll) out[f] = (uint32_t)id;
+    } else {
+      const auto r = rows_[f].find(ToString(it->second));
+      if (r != rows_[f].end()) out[f] = r->second;
+    }
+  }
 }
 std::string FormatRecallCache(const std::vector<module::ItemPtr>& items, const std::string& modelName) {
   std::string s;

@@ -336,6 +336,34 @@ std::vector<double> ParseEmbeddingText(const std::string& text, const std::strin
 // recall result cache "id:name:score,id:name:score" (service/recall/vector_recall.go:35-58 read, :103-110 write)
 std::string FormatRecallCache(const std::vector<module::ItemPtr>& items, const std::string& modelName);
 std::vector<module::ItemPtr> ParseRecallCache(const std::string& s, const std::string& modelName, const std::string& itemType);
+
+// utils.ToString (utils/type.go:120-140) for the value kinds a fetched column can hold: integers in decimal, floats as
+// strconv.FormatFloat(v, 'f', -1, 64) (shortest digits that round-trip, no exponent), strings unchanged.
+std::string ToString(const module::Value& v);
+
+// Item-feature column sets -> the id-encoded field matrix of prg_set_item_fields.  A FeatureDao writes one property per
+// non-NULL feature column of a fetched row into item.Properties (module/feature_hologres_dao.go:644-675,
+// sqlutil.ParseColumnValues); the reference then ships those VALUES to the remote model, which owns the
+// value -> embedding-row mapping.  With the tables in HBM that mapping is explicit, one rule per field:
+//   Vocab  the listed values, in order, are rows 0, 1, ... of the field's table (looked up by utils.ToString of the value)
+//   IsId   the column already holds the table row (a non-negative integer)
+// A NULL / missing column, a value outside the vocabulary and an invalid id encode as kAbsent (0xFFFFFFFF): the gather
+// treats an id beyond the table as "no contribution".
+struct FieldSpec {
+  std::string Column;
+  bool IsId = false;
+  std::vector<std::string> Vocab;
+};
+class FieldEncoder {
+ public:
+  static constexpr uint32_t kAbsent = 0xFFFFFFFFu;
+  explicit FieldEncoder(std::vector<FieldSpec> specs);
+  size_t size() const { return specs_.size(); }
+  void Encode(const module::Features& properties, uint32_t* out) const;   // out[size()]
+ private:
+  std::vector<FieldSpec> specs_;
+  std::vector<std::unordered_map<std::string, uint32_t>> rows_;
+};
 }
 
 // ------------------------------------------------------------------------------------------------ service

@@ -130,3 +130,22 @@ def dosort_head(scores, has_emb, size, candidate_count=0, min_score_percent=0.0,
     if cnt < 0:
         raise HostError(lib.ph_last_error().decode())
     return out[:cnt].copy(), bool(missed.value)
+
+
+def encode_fields(spec, rows):
+    """Item-feature column sets -> the u32 field matrix of Engine.set_item_fields (host mirror ingest::FieldEncoder).
+    spec: [{"column": name, "vocab": [values...]} | {"column": name, "id": True}, ...];
+    rows: one dict per item with the properties a FeatureDao fetched (module/feature_hologres_dao.go:644-675); a NULL
+    column is absent or None.  Absent / unknown values encode as 0xFFFFFFFF."""
+    import numpy as np
+    lib = load_host_library()
+    lib.ph_encode_fields.restype = C.c_longlong
+    sj = json.dumps(spec).encode()
+    rj = json.dumps(rows).encode()
+    n = lib.ph_encode_fields(sj, rj, None, C.c_ulonglong(0))
+    if n < 0:
+        raise HostError(lib.ph_last_error().decode())
+    out = np.empty(max(int(n), 1), dtype=np.uint32)
+    lib.ph_encode_fields(sj, rj, out.ctypes.data_as(C.c_void_p), C.c_ulonglong(n))
+    F = max(1, len(spec))
+    return out[:n].reshape(-1, F).copy()

@@ -199,3 +199,29 @@ def test_dosort_head_truncation_and_embedding_miss_threshold(oracle_lib):
     assert not missed
     got, missed = dosort_head(np.zeros(0), np.zeros(0, dtype=np.uint8), size)
     assert len(got) == 0 and not missed
+
+
+def test_item_feature_column_sets_encode_to_field_ids():
+    """what a FeatureDao fetches per item (feature_hologres_dao.go:644-675: one property per non-NULL
+    column; values int / float / string) -> the id-encoded field matrix the gather reads."""
+    from pairec_b200.plugin import encode_fields
+    spec = [{"column": "category", "vocab": ["news", "sport", "music"]},
+            {"column": "brand_id", "id": True},
+            {"column": "price_bucket", "vocab": [0, 10, 20.5]},       # numeric vocabulary: matched by utils.ToString
+            {"column": "city", "vocab": ["hz", "bj", "hz"]}]           # duplicate entry: the first row wins
+    rows = [{"item_id": "i1", "category": "sport", "brand_id": 17, "price_bucket": 10, "city": "hz"},
+            {"item_id": "i2", "category": "opera", "brand_id": "42", "price_bucket": 20.5, "city": None},
+            {"item_id": "i3", "brand_id": -1, "price_bucket": 10.0},                       # NULL category and city
+            {"item_id": "i4", "category": "news", "brand_id": 3.0, "price_bucket": 7, "city": "bj"},
+            {"item_id": "i5", "category": "music", "brand_id": 2.5, "price_bucket": "10", "city": "sh"}]
+    A = 0xFFFFFFFF
+    got = encode_fields(spec, rows)
+    want = np.array([[1, 17, 1, 0],
+                     [A, 42, 2, A],       # unknown category; id given as a decimal string; float value; NULL city
+                     [A, A, 1, A],        # negative id is invalid; 10.0 prints as "10" (FormatFloat 'f', -1)
+                     [0, 3, A, 1],        # 3.0 is a valid id; 7 is not in the vocabulary
+                     [2, A, 1, A]],       # 2.5 is not an id; the string "10" matches the numeric entry 10
+                    dtype=np.uint32)
+    assert got.shape == (5, 4)
+    assert (got == want).all(), got
+    assert encode_fields(spec, []).shape[0] == 0
