@@ -568,6 +568,9 @@ def main():
                                  "rows*dim*4 (tf32 / ffma2 over the fp32 rows) + rows*4 row norms + queries; the fp32 "
                                  "matrix is only touched for the ~5 k survivors per query (exact re-score); see DESIGN.md 3.1"},
             "e2e": e2e}
+    knobs = {k: v for k, v in sorted(os.environ.items()) if k.startswith("PRG_")}
+    if knobs:
+        line["knobs"] = knobs   # experiment switches read by the library (A/B lines describe themselves)
     if batcher is not None:
         line["e2e_batcher"] = batcher
     if shard_retries is not None:
