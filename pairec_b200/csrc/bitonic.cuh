@@ -1,5 +1,4 @@
-// bitonic.cuh — EXPERIMENTAL (opt-in: PRG_FAST_SORT=1; not yet run on a B200): 1024-element bitonic sort with ONE
-// element per thread.  The shared-memory version used by sort.cu and the recall's refine select pays a CTA barrier and
+// bitonic.cuh — 1024-element bitonic sort with ONE element per thread (used by the recall's refine select).  The shared-memory version used by sort.cu and the recall's refine select pays a CTA barrier and
 // a shared-memory round trip for each of its 55 compare-exchange stages (≈ 0.3 µs per stage); here the 40 stages whose
 // partner is in the same warp (stride < 32) are register shuffles and only the 15 with stride >= 32 go through shared
 // memory.  Same network, same strict total order, hence the same output.

@@ -153,11 +153,11 @@ int prg_init(const char* json_cfg, prg_handle** out) {
   if (json_int(json_cfg, "scan_tf32", &v) && v != 0) h->scan_filter = SCAN_FILTER_TF32;
   if (json_int(json_cfg, "dpp_generic", &v) && v != 0) h->dpp_generic = true;
   if (json_int(json_cfg, "dpp_lazy", &v) && v != 0) h->dpp_lazy = true;
-  if (json_int(json_cfg, "scan128_nqb", &v) && v != 0) h->scan128_nqb = true;
+  if (json_int(json_cfg, "scan128_nqb", &v)) h->scan128_nqb = v != 0;
   if (const char* ev = getenv("PRG_SCAN128_NQB")) h->scan128_nqb = atoi(ev) != 0;
-  if (json_int(json_cfg, "recall_tilemax", &v) && v != 0) h->recall_tilemax = true;
+  if (json_int(json_cfg, "recall_tilemax", &v)) h->recall_tilemax = v != 0;
   if (const char* ev = getenv("PRG_RECALL_TILEMAX")) h->recall_tilemax = atoi(ev) != 0;
-  if (json_int(json_cfg, "dpp_pair", &v) && v != 0) h->dpp_pair = true;
+  if (json_int(json_cfg, "dpp_pair", &v)) h->dpp_pair = v != 0;
   if (const char* ev = getenv("PRG_DPP_PAIR")) h->dpp_pair = atoi(ev) != 0;
   if (json_int(json_cfg, "mlp_one_tile", &v) && v != 0) h->mlp_one_tile_per_cta = true;
   if (json_int(json_cfg, "mlp_no_pair", &v) && v != 0) h->mlp_no_pair = true;

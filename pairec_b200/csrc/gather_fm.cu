@@ -26,22 +26,7 @@ __device__ __forceinline__ uint16_t bf16_bits(float f) { return __bfloat16_as_us
 __device__ __forceinline__ float bf16_val(uint16_t h) { return __uint_as_float((uint32_t)h << 16); }
 
 // X layout: [M][2*F*16] bf16: hi at column f*16+k, lo at F*16 + f*16+k.
-// L2 cache hints (HINTS, experimental: PRG_GATHER_HINTS=1): factor rows are touched once per candidate (evict_first),
-// the 4-byte linear weights cost a whole 64-byte DRAM access each and the linear tables are small (evict_last)
-__device__ __forceinline__ float4 ld_row_evict_first(const float* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p), "l"(kEvictFirst));
-  return v;
-}
-__device__ __forceinline__ float ld_weight_evict_last(const float* p) {
-  float v;
-  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(kEvictLast));
-  return v;
-}
-
-template <int F_UNROLL, int MIN_CTAS, bool HINTS = false>
+template <int F_UNROLL, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 gather_fm_kernel(const uint32_t* __restrict__ rows, const uint64_t* __restrict__ keys, uint32_t* __restrict__ rows_out,
                  int M, const uint32_t* __restrict__ fields, uint64_t field_rows,
@@ -80,14 +65,9 @@ gather_fm_kernel(const uint32_t* __restrict__ rows, const uint64_t* __restrict__
     for (int u = 0; u < F_UNROLL; ++u) {
       const int f = f0 + u;
       const bool ok = f < F && id[u] < ts.rows[f < F ? f : 0];
-      if constexpr (HINTS) {
-        v[u] = ok ? ld_row_evict_first(ts.factors[f] + (size_t)id[u] * 16 + sub * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        w[u] = (ok && ts.linear[f]) ? ld_weight_evict_last(ts.linear[f] + id[u]) : 0.f;
-      } else {
-        v[u] = ok ? *reinterpret_cast<const float4*>(ts.factors[f] + (size_t)id[u] * 16 + sub * 4)
-                  : make_float4(0.f, 0.f, 0.f, 0.f);
-        w[u] = (ok && ts.linear[f]) ? ts.linear[f][id[u]] : 0.f;
-      }
+      v[u] = ok ? *reinterpret_cast<const float4*>(ts.factors[f] + (size_t)id[u] * 16 + sub * 4)
+                : make_float4(0.f, 0.f, 0.f, 0.f);
+      w[u] = (ok && ts.linear[f]) ? ts.linear[f][id[u]] : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < F_UNROLL; ++u) {
@@ -157,11 +137,7 @@ int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logi
   const unsigned grid = (unsigned)((total + threads - 1) / threads);
   static const int min_ctas = getenv("PRG_GATHER_MINB") ? atoi(getenv("PRG_GATHER_MINB")) : 4;   // A/B measurements
   // 4 CTAs per SM (64 registers) instead of 3: the kernel is bound by the row loads it keeps in flight (0.097 -> 0.090 ms)
-  static const bool hints = getenv("PRG_GATHER_HINTS") && atoi(getenv("PRG_GATHER_HINTS")) != 0;      // experimental
-  if (hints)
-    PRG_CUDA(launch_chained(h, gather_fm_kernel<8, 4, true>, dim3(grid), dim3(threads), 0, 1, rows_dev, keys_dev, rows_out, M,
-                            h->fields, h->fields_rows, (int)h->n_fields, ts, h->fm_w0, logit_dev, x_dev));
-  else if (min_ctas == 4)
+  if (min_ctas == 4)
     PRG_CUDA(launch_chained(h, gather_fm_kernel<8, 4>, dim3(grid), dim3(threads), 0, 1, rows_dev, keys_dev, rows_out, M, h->fields,
                             h->fields_rows, (int)h->n_fields, ts, h->fm_w0, logit_dev, x_dev));
   else

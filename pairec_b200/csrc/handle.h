@@ -61,8 +61,8 @@ struct prg_handle {
   prg::DevBuf seg_keys;     // QB x n_seg x seg_cap u64 keys (FFMA2 scan) or u32 rows (tensor-core filter)
   prg::DevBuf seg_rows;     // QB x n_seg x seg_cap u32 survivor rows of the tensor-core filter
   prg::DevBuf row_norm;     // rows f32: upper bounds of the item row norms (tensor-core filter margin)
-  bool scan128_nqb = false;     // config "scan128_nqb" (experimental): up to 256 queries per filter pass at dim 128
-  bool recall_tilemax = false;  // config "recall_tilemax" (experimental): threshold from per-tile maxima of the sample
+  bool scan128_nqb = true;      // config "scan128_nqb": up to 256 queries per filter pass at dim 128 (2-stage ring); 0 = 64 per pass
+  bool recall_tilemax = true;   // config "recall_tilemax": threshold from per-tile maxima of the sample (0 = from sample keys)
   bool scan_ffma2 = false;  // config "scan_ffma2": use the exact FFMA2 scan for the full pass as well
   int scan_filter = 0;      // config "scan_filter": 0 = bf16 shadow index (default), 1 = tf32 on the fp32 rows
   prg::DevBuf E16;          // rows x dim bf16: round-to-nearest shadow of the item matrix (bf16 filter operand)
@@ -138,7 +138,7 @@ struct prg_handle {
   uint32_t D_dim = 0;
   int D_dtype = PRG_F32;
   bool dpp_lazy = false;     // config "dpp_lazy": the lazy-evaluation kernel (dpp_lazy.cu) instead of the cluster kernel
-  bool dpp_pair = false;     // config "dpp_pair" (experimental, dpp_pair.cu): 2-CTA clusters with features in tensor memory
+  bool dpp_pair = true;      // config "dpp_pair" (dpp_pair.cu, default for dim-128 tables): 2-CTA clusters, features partly in tensor memory; 0 = 4-CTA cluster kernel
   bool dpp_generic = false;  // config "dpp_generic": force the one-CTA-per-request kernel (A/B measurements)
   prg::DevBuf dpp_scratch, dpp_rows, dpp_score, dpp_idx, dpp_n, dpp_status;
 

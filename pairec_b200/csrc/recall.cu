@@ -597,7 +597,7 @@ struct RefineParams {
 
 // NT threads per CTA: 1024 for the single-GPU shape (64 queries x ~4.6 k survivors, one CTA per SM), 256 for row shards
 // (G times the queries, 1/G of the survivors each: several CTAs per SM instead of 3.5 waves of one).
-template <int NT, bool FAST = false>   // FAST (experimental, PRG_FAST_SORT=1): the final sort by bitonic.cuh
+template <int NT, bool FAST = false>   // FAST: the final sort by bitonic.cuh (NT == 1024)
 __global__ void __launch_bounds__(NT, NT == 1024 ? 1 : 2) refine_select_kernel(const RefineParams p) {
   pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
   pdl_launch_dependents();
@@ -974,14 +974,10 @@ static int launch_refine(prg_handle* h, const RefineParams& rp, int nq, size_t s
     PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PRG_CUDA(launch_chained(h, refine_select_kernel<256>, dim3(nq), dim3(256), smem, 1, rp));
   } else {
-    static const bool fast = getenv("PRG_FAST_SORT") && atoi(getenv("PRG_FAST_SORT")) != 0;   // experimental
-    if (fast) {
-      PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PRG_CUDA(launch_chained(h, refine_select_kernel<1024, true>, dim3(nq), dim3(1024), smem, 1, rp));
-    } else {
-    PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PRG_CUDA(launch_chained(h, refine_select_kernel<1024>, dim3(nq), dim3(1024), smem, 1, rp));
-    }
+    // FAST: the final 1024-element sort with one key per thread, intra-warp stages by shuffle (bitonic.cuh); measured
+    // on the C4 batch: select stage 0.0892 -> 0.0861 ms (profiles/r02_experiments_ab.txt)
+    PRG_CUDA(cudaFuncSetAttribute(refine_select_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PRG_CUDA(launch_chained(h, refine_select_kernel<1024, true>, dim3(nq), dim3(1024), smem, 1, rp));
   }
   PRG_CUDA(cudaGetLastError());
   count_launch(h);

@@ -8,7 +8,6 @@
 //    (score descending, input position ascending) — identical to the reference whenever scores are distinct, and the
 //    documented deviation (stable instead of pdqsort tie order) otherwise.
 #include "handle.h"
-#include "bitonic.cuh"
 #include <cstdlib>
 #include <vector>
 
@@ -195,40 +194,9 @@ __global__ void __launch_bounds__(1024) sort_desc_kernel(const double* __restric
   }
 }
 
-// EXPERIMENTAL (PRG_FAST_SORT=1): n <= 1024, one element per thread, intra-warp stages by shuffle (bitonic.cuh).
-// Same order as sort_desc_kernel: score descending, input position ascending, padding last.
-__global__ void __launch_bounds__(1024) sort_desc_fast_kernel(const double* __restrict__ score, int n, int32_t* __restrict__ perm,
-                                                              const uint32_t* __restrict__ rows, uint32_t* __restrict__ rows_o,
-                                                              double* __restrict__ scores_o) {
-  pdl_wait();
-  pdl_launch_dependents();
-  __shared__ KeyIdx xch[1024];
-  const uint32_t t = threadIdx.x;
-  const double* s = score + (size_t)blockIdx.x * n;
-  KeyIdx e;
-  e.k = (t < (uint32_t)n) ? f64_ord(s[t]) : 0ull;
-  e.i = (t < (uint32_t)n) ? (int32_t)t : 0x7FFFFFFF;   // padding sorts after every real element
-  e = bitonic_sort_1024(e, xch, [](const KeyIdx& a, const KeyIdx& b) { return a.k > b.k || (a.k == b.k && a.i < b.i); });
-  if (t < (uint32_t)n) {
-    perm[(size_t)blockIdx.x * n + t] = e.i;
-    if (rows_o) {
-      rows_o[(size_t)blockIdx.x * n + t] = rows[(size_t)blockIdx.x * n + e.i];
-      scores_o[(size_t)blockIdx.x * n + t] = s[e.i];
-    }
-  }
-}
-
 int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32_t* perm_dev, const uint32_t* rows_dev,
                      uint32_t* rows_sorted, double* scores_sorted) {
   if (n > 8192) return fail(PRG_EUNSUPPORTED, "prg_sort_desc: n > 8192");
-  static const bool fast = getenv("PRG_FAST_SORT") && atoi(getenv("PRG_FAST_SORT")) != 0;   // experimental
-  if (fast && n <= 1024) {
-    StageScope span(h, ST_SORT);
-    PRG_CUDA(launch_chained(h, sort_desc_fast_kernel, dim3(B), dim3(1024), 0, 1, score_dev, n, perm_dev, rows_dev, rows_sorted,
-                            scores_sorted));
-    count_launch(h);
-    return PRG_OK;
-  }
   uint32_t P2 = 32;
   while (P2 < (uint32_t)n) P2 <<= 1;
   const size_t smem = (size_t)P2 * 12;

@@ -77,6 +77,17 @@ def test_recall_full_size_properties(oracle_lib):
         eng.sync()
         assert torch.equal(rows, rows2) and torch.equal(sc.view(torch.int32), sc2.view(torch.int32))
 
+        # 4b. the threshold taken from sample KEYS (recall_tilemax=0, round 1's rule) instead of tile maxima: same bits
+        eng_keys = Engine(0, recall_tilemax=0)
+        try:
+            eng_keys.set_item_matrix(E.data_ptr(), rows=N, dim=D, mem=MEM_DEVICE)
+            eng_keys.recall_topk_dev(Q.data_ptr(), B, K, rows2.data_ptr(), sc2.data_ptr(), n.data_ptr())
+            eng_keys.sync()
+            assert eng_keys.recall_stats()["fallback_queries"] == 0
+            assert torch.equal(rows, rows2) and torch.equal(sc.view(torch.int32), sc2.view(torch.int32))
+        finally:
+            eng_keys.close()
+
         # 5. two row shards, global-threshold protocol, merged: same bits
         half = N // 2
         halves[0].set_item_matrix(E.data_ptr(), rows=half, dim=D, row_base=0, mem=MEM_DEVICE)

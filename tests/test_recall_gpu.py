@@ -121,13 +121,11 @@ def test_many_queries_per_pass(engine, oracle_lib, b):
     assert engine.recall_stats()["fallback_queries"] == 0
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PRG_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental (not yet run on a B200): PRG_TEST_EXPERIMENTAL=1 enables it")
 @pytest.mark.parametrize("b", [100, 200, 300])
 def test_many_queries_per_pass_dim128(oracle_lib, b):
     # config scan128_nqb: 2 / 4 query blocks per pass at dim 128 (2-stage ring), and more than one pass
     from pairec_b200 import Engine
-    eng = Engine(0, scan128_nqb=1)
+    eng = Engine(0, scan128_nqb=1 if b != 100 else 0)   # b == 100 also covers the 64-queries-per-pass form
     try:
         E, Q = _data(350_000, 128, b, seed=43 + b)
         _check(eng, oracle_lib, E, Q, 200)

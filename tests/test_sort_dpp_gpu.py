@@ -126,8 +126,6 @@ def test_dpp_lazy_kernel_matches(oracle_lib):
         eng.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PRG_TEST_EXPERIMENTAL") != "1",
-                    reason="dpp_pair.cu is experimental (not yet run on a B200): PRG_TEST_EXPERIMENTAL=1 enables its tests")
 def test_dpp_pair_kernel_matches(oracle_lib):
     # config dpp_pair: 2-CTA clusters, 512 candidates per CTA, features in registers + shared + TENSOR memory
     # (csrc/dpp_pair.cu): same selection sequences, bit for bit; other shapes fall through to the cluster kernel
@@ -145,6 +143,17 @@ def test_dpp_pair_kernel_matches(oracle_lib):
         _dpp_case(eng, oracle_lib, n=5, dim=128, top_n=3, alpha=1.0, window_size=10)
         _hard_cases(eng, oracle_lib, 128)
         _dpp_case(eng, oracle_lib, n=1000, dim=64, top_n=50, alpha=1.0, window_size=10)  # falls through
+    finally:
+        eng.close()
+
+
+def test_dpp_cluster_kernel_dim128_when_pair_is_off(oracle_lib):
+    # dpp_pair=0: the 4-CTA cluster kernel (dpp_cluster.cu) serves dim 128 as in round 1
+    from pairec_b200 import Engine
+    eng = Engine(0, dpp_pair=0)
+    try:
+        _dpp_case(eng, oracle_lib, n=1000, dim=128, top_n=50, alpha=1.0, window_size=10)
+        _hard_cases(eng, oracle_lib, 128)
     finally:
         eng.close()
 
