@@ -82,8 +82,13 @@ int prg_set_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_
  * prg_stage_item_matrix uploads the new matrix and builds everything recall needs for it (bf16 filter index, row
  * norms, tensor maps) on a side stream WITHOUT taking the handle's lock: calls on the handle keep being served from the
  * live snapshot (both are resident meanwhile).  prg_commit_item_matrix swaps the snapshots between two batches and
- * frees the old one; PRG_ESTATE if nothing is staged.  Staging again before a commit drops the earlier staged
- * snapshot.  A PRG_MEM_DEVICE matrix is adopted, not copied, and must stay valid while it is staged or live. */
+ * frees the old one; PRG_ESTATE if nothing is staged; PRG_EINVAL if the staged dim differs from the live one (callers
+ * and batchers hold query buffers of the live dim: use prg_set_item_matrix for that).  Staging again before a commit
+ * drops the earlier staged snapshot.  A PRG_MEM_DEVICE matrix is adopted, not copied, and must stay valid while it is staged or live. */
+/* dim of the live item matrix (0 before prg_set_item_matrix).  The recall entry points take no vector length: a host
+ * glue layer checks len(vector) == prg_item_dim() before passing &vector[0] (the reference parses user vectors from
+ * 'i:v i:v' text and silently skips malformed pairs, service/recall/vector_recall.go:72-82). */
+uint32_t prg_item_dim(prg_handle* h);
 int prg_stage_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_t dim, uint64_t row_base, int mem);
 int prg_commit_item_matrix(prg_handle* h);
 
@@ -97,10 +102,31 @@ int prg_set_feature_table(prg_handle* h, int table, const float* factors, const 
                           uint32_t fdim, int mem);
 int prg_set_fm_bias(prg_handle* h, float w0);
 
-/* Dense tower: n_layers weight matrices, dims[n_layers+1] (dims[0] == n_fields*fdim, dims[n_layers] == 1).
+/* User / context side of the rank features.  The reference merges, per candidate, features = userFeatures with the
+ * item's features on top (service/rank/algo_data.go:104-118; user map from user.MakeUserFeatures(),
+ * service/rank/rank_service.go:175-183) and sends the merged map to the remote model.  Id-encoded here like the item
+ * side: n_user_fields categorical user fields, whose embedding tables are feature tables n_fields ..
+ * n_fields + n_user_fields - 1 (prg_set_feature_table), plus n_user_dense numeric context values that only the dense
+ * tower sees.  FM sums run over the user fields first, then the item fields; the tower input row is
+ * [item factors | user factors | dense values], so dims[0] of prg_set_mlp == (n_fields + n_user_fields) * 16 +
+ * n_user_dense.  Call before prg_set_mlp (changing the counts drops the tower). */
+int prg_set_user_fields(prg_handle* h, uint32_t n_user_fields, uint32_t n_user_dense);
+typedef struct prg_user_features {
+  const uint32_t* ids;   /* B x n_user_fields u32; 0xFFFFFFFF (or >= table rows) = the user has no such feature; NULL = none */
+  const float* dense;    /* B x n_user_dense f32; NULL = zeros */
+} prg_user_features;
+
+/* Dense tower: n_layers weight matrices, dims[n_layers+1]; dims[0] == (n_fields + n_user_fields) * fdim + n_user_dense,
+ * dims[n_layers] == number of output heads, 1..4 (a multi-target EasyRec model returns one score per head,
+ * algorithm/eas/easyrec_response.go:35-70; TF-Serving Outputs rows, algorithm/tfserving/response.go:51-63).
  * W[l] is bf16 (raw uint16 bit patterns) [dims[l+1]][dims[l]] row-major (out-major), bias[l] f32 [dims[l+1]].
- * Host pointers only. */
+ * Arithmetic: the input is rounded to bf16 once; computed activations are carried as bf16 pairs (hi + lo); fp32
+ * accumulation; see oracle/oracle.c orc_mlp_forward.  Host pointers only. */
 int prg_set_mlp(prg_handle* h, int n_layers, const uint32_t* dims, const uint16_t* const* W, const float* const* bias);
+/* Item.Score = sum_o coef[o] * score_o over the tower's heads, evaluated left to right in fp64 — the RankScore
+ * expression (service/rank/rank_service.go:339-363, utils/ast) for the sums of products the device path folds into the
+ * last layer; any other expression is evaluated by the host from the score map of prg_rank_ex.  Default {1}. */
+int prg_set_rank_score(prg_handle* h, const double* coef, int n);
 
 /* Diversity embeddings read by DPP: rows x dim, f32 or f64 row-major (the table behind
  * sort/dpp_sort.go:169-269; rows are L2-normalised in fp64 at use when normalize != 0, :234-237). */
@@ -148,6 +174,12 @@ int prg_merge_keys(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k,
 /* rows: B x n u32 item rows (0xFFFFFFFF = padding, scored 0).  out_score: B x n f64 (the AlgoResponse.GetScore()
  * values, algorithm/response/resonse.go:3-7), f32 arithmetic widened exactly. */
 int prg_rank(prg_handle* h, int model, const uint32_t* rows, int B, int n, double* out_score, int mem);
+/* prg_rank with the requests' user / context features (request b's candidates are rows[b*n .. b*n+n-1]) and,
+ * optionally, every head's score: out_score_map B x n x heads f64 (AlgoResponse.GetScoreMap(); head 0 carries the FM
+ * part of PRG_MODEL_FM_MLP).  out_score (nullable when out_score_map is given) = sum_o coef_o * score_o.
+ * user == NULL: no user features (their tables contribute nothing). */
+int prg_rank_ex(prg_handle* h, int model, const uint32_t* rows, int B, int n, const prg_user_features* user,
+                double* out_score, double* out_score_map, int mem);
 
 /* ---------------------------------------------------------------- sort */
 
@@ -203,6 +235,13 @@ int prg_ssd(prg_handle* h, const uint32_t* rows, const double* score, int B, int
  * out_n: B i32.  This is what one /api/recommend costs below the four plugin call sites. */
 int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params* p,
                   uint32_t* out_row, double* out_score, int32_t* out_n, int mem);
+/* The same with each request's user / context features (prg_set_user_fields).
+ * PRG_MEM_DEVICE: the outputs are final when the work enqueued by the call has completed (prg_sync, or an event on
+ * prg_stream()); the call itself waits for the recall stage's exactness check and repairs a failed query before it
+ * returns.  A handle created with "defer_check":1 skips that wait: then a (rare) repair is enqueued by the NEXT call
+ * on the handle or by prg_sync, and the output / user buffers must stay valid until one of those has returned. */
+int prg_recommend_ex(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params* p,
+                     const prg_user_features* user, uint32_t* out_row, double* out_score, int32_t* out_n, int mem);
 
 /* Row-sharded variant: keys_dev points at this rank's slice of the all-gathered per-shard top-k keys —
  * G lists of B x k keys, list g at keys_dev + g*g_stride (u64 elements) — which are merged (same total order, so the
@@ -210,6 +249,9 @@ int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model,
  * diversity tables must hold every global row (replicated per GPU). */
 int prg_recommend_from_keys(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k, int model,
                             const prg_dpp_params* p, uint32_t* out_row, double* out_score, int32_t* out_n, int mem);
+int prg_recommend_from_keys_ex(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k, int model,
+                               const prg_dpp_params* p, const prg_user_features* user, uint32_t* out_row,
+                               double* out_score, int32_t* out_n, int mem);
 
 /* ---------------------------------------------------------------- cross-call request batcher */
 
@@ -233,6 +275,9 @@ int prg_batcher_start(prg_handle* h, const prg_batcher_config* cfg, prg_batcher*
  * entries, out_n: 1 entry (host).  Callable concurrently from any number of threads.  Results are those of
  * prg_recommend for the same query, whatever batch it lands in. */
 int prg_batcher_recommend(prg_batcher* b, const float* q, uint32_t* out_row, double* out_score, int32_t* out_n);
+/* The same with the request's user features: user_ids n_user_fields u32, user_dense n_user_dense f32 (either may be NULL). */
+int prg_batcher_recommend_ex(prg_batcher* b, const float* q, const uint32_t* user_ids, const float* user_dense,
+                             uint32_t* out_row, double* out_score, int32_t* out_n);
 /* size_hist9: batches by size 1, 2, 3-4, 5-8, 9-16, 17-32, 33-64, 65-128, 129+ (any pointer may be NULL). */
 int prg_batcher_stats(prg_batcher* b, uint64_t* n_requests, uint64_t* n_batches, uint64_t* size_hist9);
 /* Closed-loop load generator (measurement aid; what a pool of request goroutines does): n_threads host threads each

@@ -103,22 +103,31 @@ def merge_keys(keys):
 
 
 # ------------------------------------------------------------------ gather + FM / MLP
-def gather_fm(fields, factors, linear, w0, rows, want_x=True):
+def gather_fm(fields, factors, linear, w0, rows, want_x=True, user_ids=None, user_dense=None):
+    """One request's candidates.  user_ids [U] / user_dense [n_dense]: that request's user features
+    (service/rank/algo_data.go:104-118); the tables of the U user fields follow the F item tables in factors / linear."""
     fields = np.ascontiguousarray(fields, dtype=np.uint32)
     rows = np.ascontiguousarray(rows, dtype=np.uint32).reshape(-1)
     F = fields.shape[1]
+    U = 0 if user_ids is None else len(user_ids)
+    nd = 0 if user_dense is None else len(user_dense)
+    assert len(factors) == F + U
     fdim = factors[0].shape[1]
     fac = [np.ascontiguousarray(f, dtype=np.float32) for f in factors]
     lin = [None if l is None else np.ascontiguousarray(l, dtype=np.float32) for l in linear]
-    fp = (C.POINTER(C.c_float) * F)(*[_p(f, C.c_float) for f in fac])
-    lp = (C.POINTER(C.c_float) * F)(*[C.POINTER(C.c_float)() if l is None else _p(l, C.c_float) for l in lin])
+    fp = (C.POINTER(C.c_float) * (F + U))(*[_p(f, C.c_float) for f in fac])
+    lp = (C.POINTER(C.c_float) * (F + U))(*[C.POINTER(C.c_float)() if l is None else _p(l, C.c_float) for l in lin])
     tr = np.array([f.shape[0] for f in fac], dtype=np.uint64)
     n = rows.shape[0]
     logit = np.zeros(n, dtype=np.float32)
-    x = np.zeros((n, F * fdim), dtype=np.float32) if want_x else None
-    rc = lib().orc_gather_fm(_p(fields, C.c_uint32), C.c_uint64(fields.shape[0]), C.c_uint32(F), fp, lp,
-                             _p(tr, C.c_uint64), C.c_uint32(fdim), C.c_float(w0), _p(rows, C.c_uint32), C.c_int(n),
-                             _p(logit, C.c_float), _p(x, C.c_float) if want_x else None)
+    x = np.zeros((n, (F + U) * fdim + nd), dtype=np.float32) if want_x else None
+    uid = np.ascontiguousarray(user_ids, dtype=np.uint32) if U else None
+    ud = np.ascontiguousarray(user_dense, dtype=np.float32) if nd else None
+    rc = lib().orc_gather_fm_user(_p(fields, C.c_uint32), C.c_uint64(fields.shape[0]), C.c_uint32(F), fp, lp,
+                                  _p(tr, C.c_uint64), C.c_uint32(fdim), C.c_float(w0), _p(rows, C.c_uint32), C.c_int(n),
+                                  C.c_uint32(U), _p(uid, C.c_uint32) if U else None, C.c_uint32(nd),
+                                  _p(ud, C.c_float) if nd else None,
+                                  _p(logit, C.c_float), _p(x, C.c_float) if want_x else None)
     assert rc == 0
     return logit, x
 
@@ -148,10 +157,11 @@ def mlp_forward(x, dims, W, bias):
     wp = (C.POINTER(C.c_uint16) * L)(*[_p(w, C.c_uint16) for w in Wc])
     bp = (C.POINTER(C.c_float) * L)(*[_p(b, C.c_float) for b in bc])
     d = np.array(dims, dtype=np.uint32)
-    out = np.zeros(n, dtype=np.float32)
+    O = int(d[-1])
+    out = np.zeros((n, O), dtype=np.float32)
     rc = lib().orc_mlp_forward(_p(x, C.c_float), C.c_int(n), C.c_int(L), _p(d, C.c_uint32), wp, bp, _p(out, C.c_float))
     assert rc == 0
-    return out
+    return out[:, 0].copy() if O == 1 else out
 
 
 # ------------------------------------------------------------------ sort / lookup

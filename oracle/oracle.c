@@ -186,21 +186,37 @@ ORC_API int orc_merge_keys(const uint64_t* keys, int G, int B, int k, uint64_t* 
  */
 typedef struct { const uint32_t* fields; uint64_t field_rows; uint32_t F; const float* const* factors;
                  const float* const* linear; const uint64_t* table_rows; uint32_t fdim; float w0; const uint32_t* rows;
-                 int n; float* logit_out; float* x_out; } gfm_job;
+                 int n; float* logit_out; float* x_out;
+                 uint32_t U; const uint32_t* user_ids; uint32_t n_dense; const float* user_dense; } gfm_job;
 static void gfm_worker(void* arg, int tid, int nt) {
   const gfm_job* J = (const gfm_job*)arg;
-  const uint32_t F = J->F, fdim = J->fdim;
+  const uint32_t F = J->F, fdim = J->fdim, U = J->U;
+  const size_t xw = (size_t)(F + U) * fdim + J->n_dense;
   const int i0 = (int)((int64_t)J->n * tid / nt), i1 = (int)((int64_t)J->n * (tid + 1) / nt);
+  /* user prefix (service/rank/algo_data.go:110-112: the user's features enter the map first): tables F..F+U-1 */
+  float lin0 = J->w0, s0[64], ss0[64];
+  for (uint32_t k = 0; k < fdim; ++k) { s0[k] = 0.0f; ss0[k] = 0.0f; }
+  for (uint32_t u = 0; u < U; ++u) {
+    const uint32_t id = J->user_ids ? J->user_ids[u] : 0xFFFFFFFFu;
+    const int ok = id < J->table_rows[F + u];
+    const float w = (ok && J->linear[F + u]) ? J->linear[F + u][id] : 0.0f;
+    lin0 = lin0 + w;
+    for (uint32_t k = 0; k < fdim; ++k) {
+      const float v = ok ? J->factors[F + u][(size_t)id * fdim + k] : 0.0f;
+      s0[k] = s0[k] + v;
+      ss0[k] = __builtin_fmaf(v, v, ss0[k]);
+    }
+  }
   for (int i = i0; i < i1; ++i) {
     const uint32_t row = J->rows[i];
-    float* x = J->x_out ? J->x_out + (size_t)i * F * fdim : NULL;
+    float* x = J->x_out ? J->x_out + (size_t)i * xw : NULL;
     if (row == 0xFFFFFFFFu || row >= J->field_rows) {
       if (J->logit_out) J->logit_out[i] = 0.0f;
-      if (x) memset(x, 0, sizeof(float) * (size_t)F * fdim);
+      if (x) memset(x, 0, sizeof(float) * xw);
       continue;
     }
-    float lin = J->w0, s[64], ss[64];
-    for (uint32_t k = 0; k < fdim; ++k) { s[k] = 0.0f; ss[k] = 0.0f; }
+    float lin = lin0, s[64], ss[64];
+    for (uint32_t k = 0; k < fdim; ++k) { s[k] = s0[k]; ss[k] = ss0[k]; }
     for (uint32_t f = 0; f < F; ++f) {
       const uint32_t id = J->fields[(size_t)row * F + f];
       const int ok = id < J->table_rows[f];
@@ -213,6 +229,15 @@ static void gfm_worker(void* arg, int tid, int nt) {
         if (x) x[f * fdim + k] = v;
       }
     }
+    if (x) {
+      for (uint32_t u = 0; u < U; ++u) {
+        const uint32_t id = J->user_ids ? J->user_ids[u] : 0xFFFFFFFFu;
+        const int ok = id < J->table_rows[F + u];
+        for (uint32_t k = 0; k < fdim; ++k)
+          x[(F + u) * fdim + k] = ok ? J->factors[F + u][(size_t)id * fdim + k] : 0.0f;
+      }
+      for (uint32_t c = 0; c < J->n_dense; ++c) x[(F + U) * fdim + c] = J->user_dense ? J->user_dense[c] : 0.0f;
+    }
     float inter = 0.0f;
     for (uint32_t k = 0; k < fdim; ++k) inter = inter + __builtin_fmaf(s[k], s[k], -ss[k]);
     if (J->logit_out) J->logit_out[i] = __builtin_fmaf(0.5f, inter, lin);
@@ -222,7 +247,24 @@ ORC_API int orc_gather_fm(const uint32_t* fields, uint64_t field_rows, uint32_t 
                           const float* const* linear, const uint64_t* table_rows, uint32_t fdim, float w0,
                           const uint32_t* rows, int n, float* logit_out, float* x_out) {
   if (fdim > 64) return 1;
-  gfm_job job = {fields, field_rows, F, factors, linear, table_rows, fdim, w0, rows, n, logit_out, x_out};
+  gfm_job job = {fields, field_rows, F, factors, linear, table_rows, fdim, w0, rows, n, logit_out, x_out, 0, NULL, 0, NULL};
+  orc_parallel(n > 1024 ? orc_hw_threads() : 1, gfm_worker, &job);
+  return 0;
+}
+/* One request's candidates with that request's user / context features merged in.  The reference builds
+ *   features = userFeatures, then itemFeatures on top   (service/rank/algo_data.go:104-118)
+ * from user.MakeUserFeatures() (service/rank/rank_service.go:175-183) and item.GetFeatures() (module/item.go:229-248).
+ * Id-encoded here: U categorical user fields (tables F..F+U-1 of factors / linear / table_rows, ids user_ids[U],
+ * 0xFFFFFFFF = the user has no such feature) and n_dense numeric context values that only the tower sees.
+ * FM sums run over the user fields first, then the item fields, each in index order.
+ * x_out: [n][(F+U)*fdim + n_dense] = item factors | user factors | dense values. */
+ORC_API int orc_gather_fm_user(const uint32_t* fields, uint64_t field_rows, uint32_t F, const float* const* factors,
+                               const float* const* linear, const uint64_t* table_rows, uint32_t fdim, float w0,
+                               const uint32_t* rows, int n, uint32_t U, const uint32_t* user_ids, uint32_t n_dense,
+                               const float* user_dense, float* logit_out, float* x_out) {
+  if (fdim > 64) return 1;
+  gfm_job job = {fields, field_rows, F, factors, linear, table_rows, fdim, w0, rows, n, logit_out, x_out,
+                 U, user_ids, n_dense, user_dense};
   orc_parallel(n > 1024 ? orc_hw_threads() : 1, gfm_worker, &job);
   return 0;
 }
@@ -255,8 +297,11 @@ ORC_API float orc_bf16_to_f32(uint16_t h) { return bf16_to_f32(h); }
  *   the value carried is hi + lo (>= 16 significant bits), which keeps the result continuous under the 1e-6-level
  *   accumulation-order differences between implementations (plain bf16 activations flip whole bf16 ulps).
  *   z_j   = b_j + sum_i W[j][i] * (hi_i + lo_i)      W bf16, accumulation wide (oracle: fp64), z rounded to f32
- *   hidden: a = max(z, 0) -> split again;   last layer (width 1): logit = z (f32)
- * x: [n][dims[0]] f32.  W[l]: [dims[l+1]][dims[l]] bf16 bits.  logit_out: [n].
+ *   hidden: a = max(z, 0) -> split again;   last layer (width O >= 1, one column per model output:
+ *   easyrec_response.go:35-70 / tfserving/response.go:51-63): logit_o = z_o (f32)
+ *   The tower INPUT is carried as bf16(x) alone (lo = 0): gathered table values carry no accumulation-order noise, so
+ *   the single rounding is reproducible bit for bit; only COMPUTED activations need the second term.
+ * x: [n][dims[0]] f32.  W[l]: [dims[l+1]][dims[l]] bf16 bits.  logit_out: [n][O].
  */
 typedef struct { const float* x; int n, n_layers; const uint32_t* dims; double* const* Wt; const float* const* bias; float* logit_out; uint32_t maxd; } mlp_job;
 static void mlp_worker(void* arg, int tid, int nt) {
@@ -268,9 +313,7 @@ static void mlp_worker(void* arg, int tid, int nt) {
   for (int i = i0; i < i1; ++i) {
     for (uint32_t c = 0; c < dims[0]; ++c) {
       const float v = J->x[(size_t)i * dims[0] + c];
-      const float hi = bf16_to_f32(f32_to_bf16(v));
-      const float lo = bf16_to_f32(f32_to_bf16(v - hi));
-      a[c] = (double)hi + (double)lo;
+      a[c] = (double)bf16_to_f32(f32_to_bf16(v));
     }
     for (int l = 0; l < J->n_layers; ++l) {
       const uint32_t K = dims[l], N = dims[l + 1];
@@ -283,7 +326,8 @@ static void mlp_worker(void* arg, int tid, int nt) {
         for (uint32_t j = 0; j < N; ++j) acc[j] += w[j] * ac;
       }
       if (l == J->n_layers - 1) {
-        J->logit_out[i] = (float)(acc[0] + (double)(J->bias[l] ? J->bias[l][0] : 0.0f));
+        for (uint32_t j = 0; j < N; ++j)
+          J->logit_out[(size_t)i * N + j] = (float)(acc[j] + (double)(J->bias[l] ? J->bias[l][j] : 0.0f));
       } else {
         for (uint32_t j = 0; j < N; ++j) {
           const float z = (float)(acc[j] + (double)(J->bias[l] ? J->bias[l][j] : 0.0f));
@@ -304,7 +348,7 @@ ORC_API int orc_mlp_forward(const float* x, int n, int n_layers, const uint32_t*
   uint32_t maxd = 0;
   for (int l = 0; l <= n_layers; ++l)
     if (dims[l] > maxd) maxd = dims[l];
-  if (dims[n_layers] != 1) return 1;
+  if (dims[n_layers] < 1) return 1;
   double** Wt = (double**)malloc(sizeof(double*) * (size_t)n_layers);
   for (int l = 0; l < n_layers; ++l) {
     const uint32_t K = dims[l], N = dims[l + 1];

@@ -23,6 +23,8 @@ EXPORTS = [
     "prg_shard_candidates", "prg_shard_check", "prg_rank", "prg_sort_desc_host", "prg_sort_desc",
     "prg_dpp", "prg_ssd", "prg_recommend", "prg_recommend_from_keys", "prg_lookup", "prg_launch_count", "prg_recall_stats", "prg_timing",
     "prg_batcher_start", "prg_batcher_recommend", "prg_batcher_stats", "prg_batcher_stop", "prg_batcher_drive",
+    "prg_set_user_fields", "prg_set_rank_score", "prg_rank_ex", "prg_recommend_ex", "prg_recommend_from_keys_ex",
+    "prg_batcher_recommend_ex", "prg_item_dim",
 ]
 
 
@@ -54,6 +56,11 @@ class SsdParams(C.Structure):
                          min_score_percent)
 
 
+class UserFeatures(C.Structure):
+    """prg_user_features: a batch's user / context features (service/rank/algo_data.go:104-118)."""
+    _fields_ = [("ids", C.c_void_p), ("dense", C.c_void_p)]
+
+
 class BatcherConfig(C.Structure):
     """prg_batcher_config."""
     _fields_ = [("max_batch", C.c_int32), ("max_wait_us", C.c_int32), ("recall_k", C.c_int32), ("model", C.c_int32),
@@ -78,6 +85,7 @@ def load_library():
         _lib.prg_version.restype = C.c_char_p
         _lib.prg_stream.restype = C.c_void_p
         _lib.prg_launch_count.restype = C.c_uint64
+        _lib.prg_item_dim.restype = C.c_uint32
         _lib.prg_destroy.restype = None
         _lib.prg_batcher_stop.restype = None
         for name in EXPORTS:
@@ -197,6 +205,28 @@ class Engine:
                                                  C.c_uint32(fdim), C.c_int(mem)))
         self.fdim = fdim
 
+    def set_user_fields(self, n_user_fields, n_user_dense=0):
+        """User fields use feature tables n_fields .. n_fields + n_user_fields - 1; call before set_mlp."""
+        self._ck(self._lib.prg_set_user_fields(self._h, C.c_uint32(n_user_fields), C.c_uint32(n_user_dense)))
+        self.n_user_fields, self.n_user_dense = n_user_fields, n_user_dense
+
+    def set_rank_score(self, coef):
+        c = _np(coef, np.float64)
+        self._ck(self._lib.prg_set_rank_score(self._h, _ptr(c), C.c_int(c.shape[0])))
+
+    def _user(self, B, user_ids, user_dense):
+        """-> (prg_user_features*, keep-alive arrays)"""
+        if user_ids is None and user_dense is None:
+            return None, ()
+        ids = None if user_ids is None else _np(user_ids, np.uint32).reshape(B, -1)
+        dense = None if user_dense is None else _np(user_dense, np.float32).reshape(B, -1)
+        if ids is not None:
+            assert ids.shape[1] == getattr(self, "n_user_fields", 0), "user_ids must be [B, n_user_fields]"
+        if dense is not None:
+            assert dense.shape[1] == getattr(self, "n_user_dense", 0), "user_dense must be [B, n_user_dense]"
+        uf = UserFeatures(None if ids is None else ids.ctypes.data, None if dense is None else dense.ctypes.data)
+        return C.byref(uf), (uf, ids, dense)
+
     def set_fm_bias(self, w0):
         self._ck(self._lib.prg_set_fm_bias(self._h, C.c_float(w0)))
 
@@ -208,6 +238,7 @@ class Engine:
         bp = (C.c_void_p * L)(*[b.ctypes.data for b in bc])
         d = np.array(dims, dtype=np.uint32)
         self._ck(self._lib.prg_set_mlp(self._h, C.c_int(L), _ptr(d), wp, bp))
+        self.heads = int(dims[-1])
 
     def set_diversity_matrix(self, data, rows=None, dim=None, dtype=None, mem=MEM_HOST):
         if mem == MEM_HOST:
@@ -221,7 +252,7 @@ class Engine:
     # ---------------------------------------------------------------- recall
     def recall_topk(self, q, k):
         """Host buffers in/out (the e2e path).  Returns rows u32 [B,k], scores f32 [B,k], n i32 [B]."""
-        q = _np(q, np.float32)
+        q = self._queries(q)
         B = q.shape[0]
         rows = np.empty((B, k), dtype=np.uint32)
         scores = np.empty((B, k), dtype=np.float32)
@@ -229,6 +260,15 @@ class Engine:
         self._ck(self._lib.prg_recall_topk(self._h, _ptr(q), C.c_int(B), C.c_int(k), _ptr(rows), _ptr(scores), _ptr(n),
                                            C.c_int(MEM_HOST)))
         return rows, scores, n
+
+    def _queries(self, q):
+        """The C ABI takes no vector length: a query of the wrong width would be read past its end
+        (service/recall/vector_recall.go:72-82 silently skips malformed 'i:v' pairs, so short vectors do occur)."""
+        q = _np(q, np.float32)
+        dim = int(self._lib.prg_item_dim(self._h))
+        if q.ndim != 2 or q.shape[1] != dim:
+            raise PrgError(1, f"query vectors must be [B, {dim}], got {q.shape}")
+        return q
 
     def recall_topk_dev(self, q_ptr, B, k, rows_ptr, scores_ptr, n_ptr):
         self._ck(self._lib.prg_recall_topk(self._h, _ptr(q_ptr), C.c_int(B), C.c_int(k), _ptr(rows_ptr),
@@ -262,13 +302,16 @@ class Engine:
         return rows, scores, n
 
     # ---------------------------------------------------------------- rank
-    def rank(self, model, rows):
+    def rank(self, model, rows, user_ids=None, user_dense=None, score_map=False):
+        """rows [B, n] -> Item.Score [B, n] (and, score_map=True, every head's score [B, n, heads])."""
         rows = _np(rows, np.uint32)
         B, n = rows.shape
         out = np.empty((B, n), dtype=np.float64)
-        self._ck(self._lib.prg_rank(self._h, C.c_int(model), _ptr(rows), C.c_int(B), C.c_int(n), _ptr(out),
-                                    C.c_int(MEM_HOST)))
-        return out
+        uf, keep = self._user(B, user_ids, user_dense)
+        smap = np.empty((B, n, getattr(self, "heads", 1)), dtype=np.float64) if score_map else None
+        self._ck(self._lib.prg_rank_ex(self._h, C.c_int(model), _ptr(rows), C.c_int(B), C.c_int(n), uf, _ptr(out),
+                                       _ptr(smap), C.c_int(MEM_HOST)))
+        return (out, smap) if score_map else out
 
     def rank_dev(self, model, rows_ptr, B, n, out_ptr):
         self._ck(self._lib.prg_rank(self._h, C.c_int(model), _ptr(rows_ptr), C.c_int(B), C.c_int(n), _ptr(out_ptr),
@@ -308,27 +351,36 @@ class Engine:
         return idx, cnt, st
 
     # ---------------------------------------------------------------- fused
-    def recommend(self, q, recall_k, model, params):
-        q = _np(q, np.float32)
+    def recommend(self, q, recall_k, model, params, user_ids=None, user_dense=None):
+        q = self._queries(q)
         B = q.shape[0]
         T = params.top_n
         rows = np.empty((B, T), dtype=np.uint32)
         scores = np.empty((B, T), dtype=np.float64)
         n = np.empty(B, dtype=np.int32)
-        self._ck(self._lib.prg_recommend(self._h, _ptr(q), C.c_int(B), C.c_int(recall_k), C.c_int(model),
-                                         C.byref(params), _ptr(rows), _ptr(scores), _ptr(n), C.c_int(MEM_HOST)))
+        uf, keep = self._user(B, user_ids, user_dense)
+        self._ck(self._lib.prg_recommend_ex(self._h, _ptr(q), C.c_int(B), C.c_int(recall_k), C.c_int(model),
+                                            C.byref(params), uf, _ptr(rows), _ptr(scores), _ptr(n), C.c_int(MEM_HOST)))
         return rows, scores, n
 
-    def recommend_dev(self, q_ptr, B, recall_k, model, params, rows_ptr, scores_ptr, n_ptr):
-        self._ck(self._lib.prg_recommend(self._h, _ptr(q_ptr), C.c_int(B), C.c_int(recall_k), C.c_int(model),
-                                         C.byref(params), _ptr(rows_ptr), _ptr(scores_ptr), _ptr(n_ptr),
-                                         C.c_int(MEM_DEVICE)))
+    def recommend_dev(self, q_ptr, B, recall_k, model, params, rows_ptr, scores_ptr, n_ptr, user_ids_ptr=None,
+                      user_dense_ptr=None):
+        uf = None
+        if user_ids_ptr is not None or user_dense_ptr is not None:
+            uf = C.byref(UserFeatures(user_ids_ptr, user_dense_ptr))
+        self._ck(self._lib.prg_recommend_ex(self._h, _ptr(q_ptr), C.c_int(B), C.c_int(recall_k), C.c_int(model),
+                                            C.byref(params), uf, _ptr(rows_ptr), _ptr(scores_ptr), _ptr(n_ptr),
+                                            C.c_int(MEM_DEVICE)))
 
 
-def _engine_recommend_from_keys_dev(self, keys_ptr, G, g_stride, B, k, model, params, rows_ptr, scores_ptr, n_ptr):
-    self._ck(self._lib.prg_recommend_from_keys(self._h, _ptr(keys_ptr), C.c_int(G), C.c_uint64(g_stride), C.c_int(B),
-                                               C.c_int(k), C.c_int(model), C.byref(params), _ptr(rows_ptr),
-                                               _ptr(scores_ptr), _ptr(n_ptr), C.c_int(MEM_DEVICE)))
+def _engine_recommend_from_keys_dev(self, keys_ptr, G, g_stride, B, k, model, params, rows_ptr, scores_ptr, n_ptr,
+                                    user_ids_ptr=None, user_dense_ptr=None):
+    uf = None
+    if user_ids_ptr is not None or user_dense_ptr is not None:
+        uf = C.byref(UserFeatures(user_ids_ptr, user_dense_ptr))
+    self._ck(self._lib.prg_recommend_from_keys_ex(self._h, _ptr(keys_ptr), C.c_int(G), C.c_uint64(g_stride), C.c_int(B),
+                                                  C.c_int(k), C.c_int(model), C.byref(params), uf, _ptr(rows_ptr),
+                                                  _ptr(scores_ptr), _ptr(n_ptr), C.c_int(MEM_DEVICE)))
 
 
 Engine.recommend_from_keys_dev = _engine_recommend_from_keys_dev
@@ -371,14 +423,17 @@ class Batcher:
         if rc != 0:
             raise PrgError(rc, self._lib.prg_last_error().decode())
 
-    def recommend(self, q):
-        """One request: q [dim] f32 -> (rows [n] u32, scores [n] f64).  Blocks until served."""
+    def recommend(self, q, user_ids=None, user_dense=None):
+        """One request: q [dim] f32 (+ its user features) -> (rows [n] u32, scores [n] f64).  Blocks until served."""
         q = _np(q, np.float32)
         assert q.shape == (self.dim,)
         rows = np.empty(self.top_n, dtype=np.uint32)
         scores = np.empty(self.top_n, dtype=np.float64)
         n = C.c_int32(0)
-        rc = self._lib.prg_batcher_recommend(self._b, _ptr(q), _ptr(rows), _ptr(scores), C.byref(n))
+        ids = None if user_ids is None else _np(user_ids, np.uint32)
+        dense = None if user_dense is None else _np(user_dense, np.float32)
+        rc = self._lib.prg_batcher_recommend_ex(self._b, _ptr(q), _ptr(ids), _ptr(dense), _ptr(rows), _ptr(scores),
+                                                C.byref(n))
         if rc != 0:
             raise PrgError(rc, self._lib.prg_last_error().decode())
         return rows[:n.value], scores[:n.value]

@@ -31,6 +31,8 @@ namespace {
 // one blocked caller; lives on that caller's stack for the duration of prg_batcher_recommend
 struct Request {
   const float* q;
+  const uint32_t* user_ids = nullptr;   // [U] or null (every user feature absent)
+  const float* user_dense = nullptr;    // [n_dense] or null (zeros)
   uint32_t* out_row;
   double* out_score;
   int32_t* out_n;
@@ -46,7 +48,9 @@ struct Staging {  // pinned host buffers of one worker
   uint32_t* rows = nullptr;    // [max_batch][top_n]
   double* scores = nullptr;    // [max_batch][top_n]
   int32_t* n = nullptr;        // [max_batch]
-  void release() { cudaFreeHost(q); cudaFreeHost(rows); cudaFreeHost(scores); cudaFreeHost(n); }
+  uint32_t* uid = nullptr;     // [max_batch][U] user field ids
+  float* udense = nullptr;     // [max_batch][n_dense]
+  void release() { cudaFreeHost(q); cudaFreeHost(rows); cudaFreeHost(scores); cudaFreeHost(n); cudaFreeHost(uid); cudaFreeHost(udense); }
 };
 }  // namespace
 
@@ -54,6 +58,7 @@ struct prg_batcher {
   prg_handle* h = nullptr;
   prg_batcher_config cfg{};
   uint32_t dim = 0;
+  uint32_t n_user = 0, n_dense = 0;    // user / context features per request (prg_set_user_fields at start time)
   std::mutex mu;                       // queue, flags, statistics
   std::mutex gpu_turn;                 // held by the worker that forms and runs the next batch
   std::condition_variable cv_worker;   // a request arrived / stop
@@ -72,6 +77,26 @@ struct prg_batcher {
 
   void run(int w);
   void run_pipelined(int w);
+  // queries and user features of a batch -> worker w's pinned staging; returns the user block to pass on (or null)
+  const prg_user_features* stage_inputs(int w, const std::vector<Request*>& batch, prg_user_features* uf) {
+    Staging& st = stage[w];
+    const int B = (int)batch.size();
+    for (int i = 0; i < B; ++i) std::memcpy(st.q + (size_t)i * dim, batch[i]->q, (size_t)dim * 4);
+    if (n_user + n_dense == 0) return nullptr;
+    for (int i = 0; i < B; ++i) {
+      if (n_user) {
+        if (batch[i]->user_ids) std::memcpy(st.uid + (size_t)i * n_user, batch[i]->user_ids, (size_t)n_user * 4);
+        else std::memset(st.uid + (size_t)i * n_user, 0xFF, (size_t)n_user * 4);
+      }
+      if (n_dense) {
+        if (batch[i]->user_dense) std::memcpy(st.udense + (size_t)i * n_dense, batch[i]->user_dense, (size_t)n_dense * 4);
+        else std::memset(st.udense + (size_t)i * n_dense, 0, (size_t)n_dense * 4);
+      }
+    }
+    uf->ids = n_user ? st.uid : nullptr;
+    uf->dense = n_dense ? st.udense : nullptr;
+    return uf;
+  }
   void deliver(int w, std::vector<Request*>& batch, int rc);
 };
 
@@ -100,8 +125,9 @@ void prg_batcher::run(int w) {
       }
     }
     const int B = (int)batch.size();
-    for (int i = 0; i < B; ++i) std::memcpy(st.q + (size_t)i * dim, batch[i]->q, (size_t)dim * 4);
-    const int rc = prg_recommend(h, st.q, B, cfg.recall_k, cfg.model, &cfg.dpp, st.rows, st.scores, st.n, PRG_MEM_HOST);
+    prg_user_features uf{nullptr, nullptr};
+    const prg_user_features* user = stage_inputs(w, batch, &uf);
+    const int rc = prg_recommend_ex(h, st.q, B, cfg.recall_k, cfg.model, &cfg.dpp, user, st.rows, st.scores, st.n, PRG_MEM_HOST);
     if (rc != PRG_OK) last_err[w] = prg_last_error();
     turn.unlock();
     deliver(w, batch, rc);
@@ -165,9 +191,10 @@ void prg_batcher::run_pipelined(int w) {
       ++gpu_busy;
     }
     const int B = (int)batch.size();
-    for (int i = 0; i < B; ++i) std::memcpy(st.q + (size_t)i * dim, batch[i]->q, (size_t)dim * 4);
+    prg_user_features uf{nullptr, nullptr};
+    const prg_user_features* user = stage_inputs(w, batch, &uf);
     uint64_t seq = 0;
-    int rc = recommend_begin(h, st.q, B, cfg.recall_k, cfg.model, cfg.dpp, st.rows, st.scores, st.n, done[w], &seq);
+    int rc = recommend_begin(h, st.q, B, cfg.recall_k, cfg.model, cfg.dpp, user, st.rows, st.scores, st.n, done[w], &seq);
     if (rc != PRG_OK) last_err[w] = prg_last_error();
     turn.unlock();
     if (rc == PRG_OK) {
@@ -189,23 +216,29 @@ int prg_batcher_start(prg_handle* h, const prg_batcher_config* cfg, prg_batcher*
   if (!h || !cfg || !out) return fail(PRG_EINVAL, "null argument");
   if (cfg->max_batch <= 0 || cfg->max_batch > 256) return fail(PRG_EINVAL, "max_batch must be in 1..256");
   if (cfg->recall_k <= 0 || cfg->dpp.top_n <= 0 || cfg->max_wait_us < 0) return fail(PRG_EINVAL, "bad batcher config");
-  uint32_t dim;
+  uint32_t dim, n_user, n_dense;
   {
     std::lock_guard<std::mutex> g(h->mu);
     if (!h->E) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
     dim = h->E_dim;
+    n_user = h->n_user_fields;
+    n_dense = h->n_user_dense;
   }
   cudaSetDevice(h->device);
   prg_batcher* b = new prg_batcher();
   b->h = h;
   b->cfg = *cfg;
   b->dim = dim;
+  b->n_user = n_user;
+  b->n_dense = n_dense;
   const size_t T = (size_t)cfg->dpp.top_n, M = (size_t)cfg->max_batch;
   for (Staging& s : b->stage) {
     cudaError_t e = cudaHostAlloc((void**)&s.q, M * dim * 4, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.rows, M * T * 4, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.scores, M * T * 8, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s.n, M * 4, cudaHostAllocDefault);
+    if (e == cudaSuccess && n_user) e = cudaHostAlloc((void**)&s.uid, M * n_user * 4, cudaHostAllocDefault);
+    if (e == cudaSuccess && n_dense) e = cudaHostAlloc((void**)&s.udense, M * n_dense * 4, cudaHostAllocDefault);
     if (e != cudaSuccess) {
       for (Staging& t : b->stage) t.release();
       delete b;
@@ -228,9 +261,15 @@ int prg_batcher_start(prg_handle* h, const prg_batcher_config* cfg, prg_batcher*
 }
 
 int prg_batcher_recommend(prg_batcher* b, const float* q, uint32_t* out_row, double* out_score, int32_t* out_n) {
+  return prg_batcher_recommend_ex(b, q, nullptr, nullptr, out_row, out_score, out_n);
+}
+
+int prg_batcher_recommend_ex(prg_batcher* b, const float* q, const uint32_t* user_ids, const float* user_dense,
+                             uint32_t* out_row, double* out_score, int32_t* out_n) {
   if (!b || !q || !out_row || !out_score || !out_n) return fail(PRG_EINVAL, "null argument");
   Request r;
-  r.q = q; r.out_row = out_row; r.out_score = out_score; r.out_n = out_n;
+  r.q = q; r.user_ids = user_ids; r.user_dense = user_dense;
+  r.out_row = out_row; r.out_score = out_score; r.out_n = out_n;
   std::unique_lock<std::mutex> lk(b->mu);
   if (b->stop) return fail(PRG_ESTATE, "batcher stopped");
   ++b->inflight;

@@ -159,8 +159,8 @@ int prg_init(const char* json_cfg, prg_handle** out) {
   if (const char* ev = getenv("PRG_RECALL_TILEMAX")) h->recall_tilemax = atoi(ev) != 0;
   if (json_int(json_cfg, "dpp_pair", &v)) h->dpp_pair = v != 0;
   if (const char* ev = getenv("PRG_DPP_PAIR")) h->dpp_pair = atoi(ev) != 0;
-  if (json_int(json_cfg, "mlp_one_tile", &v) && v != 0) h->mlp_one_tile_per_cta = true;
   if (json_int(json_cfg, "mlp_no_pair", &v) && v != 0) h->mlp_no_pair = true;
+  if (json_int(json_cfg, "defer_check", &v)) h->defer_check = v != 0;
   if (json_int(json_cfg, "pdl", &v)) h->pdl = v != 0;
   if (const char* ev = getenv("PRG_PDL")) h->pdl = atoi(ev) != 0;   // A/B measurements without a config change
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
@@ -190,7 +190,7 @@ void prg_destroy(prg_handle* h) {
     }
     DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->row_norm, &h->E16, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
                       &h->out_row, &h->out_score, &h->out_n, &h->flags, &h->table_ptrs, &h->act[0], &h->act[1],
-                      &h->fm_logit, &h->rank_rows, &h->rank_out, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
+                      &h->fm_logit, &h->rank_rows, &h->rank_out, &h->mlp_Wu, &h->user_ids_dev, &h->user_dense_dev, &h->fm_state, &h->ubias, &h->rank_map, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
                       &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->ssd_E, &h->ssd_P, &h->sort_in, &h->sort_perm, &h->rec_rows,
                       &h->rec_scores, &h->rec_perm, &h->rec_sorted_rows, &h->rec_sorted_scores};
     for (DevBuf* b : bufs) b->release();
@@ -216,6 +216,7 @@ int prg_sync(prg_handle* h) {
   return PRG_OK;
 }
 void* prg_stream(prg_handle* h) { return h ? (void*)h->stream : nullptr; }
+uint32_t prg_item_dim(prg_handle* h) { return (h && h->E) ? h->E_dim : 0; }
 uint64_t prg_launch_count(prg_handle* h) { return h ? h->launches : 0; }
 
 int prg_timing(prg_handle* h, int enable, double* ms_out, uint64_t* n_out) {
@@ -312,6 +313,9 @@ int prg_commit_item_matrix(prg_handle* h) {
   CHECK_H(h);
   Guard g(h);                // also settles a deferred recall check — against the snapshot it ran on
   if (!h->staged) return fail(PRG_ESTATE, "no staged item matrix (prg_stage_item_matrix)");
+  if (h->E && h->staged->E_dim != h->E_dim)
+    return fail(PRG_EINVAL, "staged item matrix has dim " + std::to_string(h->staged->E_dim) + ", the live one " +
+                                std::to_string(h->E_dim) + ": a snapshot swap keeps the dim (use prg_set_item_matrix)");
   PRG_CUDA(cudaStreamSynchronize(h->stream));
   prg_handle* s = h->staged;
   h->staged = nullptr;

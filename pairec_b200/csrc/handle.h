@@ -29,6 +29,7 @@ struct prg_handle {
   cudaStream_t stream = nullptr;
   std::mutex mu;
   uint64_t launches = 0;
+  bool defer_check = false;   // config "defer_check": prg_recommend(PRG_MEM_DEVICE) leaves the recall's exactness check to the next call / prg_sync
   bool pdl = true;   // config "pdl": programmatic dependent launch along the per-batch kernel chain (launch_chained)
 
   // optional per-stage device timing (CUDA events on this handle's stream around each stage's launches)
@@ -86,6 +87,7 @@ struct prg_handle {
     const float* q_dev = nullptr;
     uint64_t* keys_out = nullptr;
     prg_dpp_params p{};
+    prg_user_features user{nullptr, nullptr};   // device pointers of the call's user features
     uint32_t* out_row = nullptr;
     double* out_score = nullptr;
     int32_t* out_n = nullptr;
@@ -123,12 +125,21 @@ struct prg_handle {
   prg::DevBuf mlp_b[prg::kMaxLayers];
   CUtensorMap mlp_Wmap[prg::kMaxLayers];
   CUtensorMap mlp_Wmap_half[prg::kMaxLayers];  // boxes of half a W block (one CTA's share of a multicast pair load)
-  float mlp_b_last = 0.f;
+  float mlp_b_last[4] = {0.f, 0.f, 0.f, 0.f};   // biases of the output heads
+  double rank_coef[4] = {1.0, 0.0, 0.0, 0.0};   // Item.Score = sum_o coef[o] * score_o (prg_set_rank_score)
+  uint32_t mlp_k_item = 0, mlp_k_user = 0;      // input columns from the item fields (tensor cores) / user + context (per request)
+  prg::DevBuf mlp_Wu;                           // [k_user][dims[1]] f32: first-layer weights of the user / context columns
   bool mlp_no_pair = false;           // config "mlp_no_pair": single-CTA persistent kernel without W multicast (A/B measurements)
-  bool mlp_one_tile_per_cta = false;  // config "mlp_one_tile": the non-persistent layer kernel (A/B measurements)
+
+  // ---- user / context features of a request (service/rank/algo_data.go:104-118)
+  uint32_t n_user_fields = 0;   // categorical user fields: feature tables n_fields .. n_fields + n_user_fields - 1
+  uint32_t n_user_dense = 0;    // numeric context values appended to the tower input
+  prg::DevBuf user_ids_dev, user_dense_dev;   // host-call staging: B x U u32, B x n_dense f32
+  prg::DevBuf fm_state;         // B x 36 f32: lin, s[16], ss[16] after the user fields (the gather continues from it)
+  prg::DevBuf ubias;            // B x dims[1] f32: b1 + W1[:, user columns] * x_user
   prg::DevBuf act[2];   // activations ping-pong (bf16)
   prg::DevBuf fm_logit; // B*n f32
-  prg::DevBuf rank_rows, rank_out;
+  prg::DevBuf rank_rows, rank_out, rank_map;   // rank_map: host-call staging of the per-head scores
 
   // ---- DPP
   const void* D = nullptr;
@@ -222,7 +233,8 @@ int resolve_pending(prg_handle* h);                  // pipeline.cu: recall_reso
 // the recall's deferred check if nobody has yet and returns the call's status.  Several calls may be in flight on a
 // handle (stream order); the handle's lock is held only while a call is being enqueued.
 int recommend_begin(prg_handle* h, const float* q_pinned, int B, int recall_k, int model, const prg_dpp_params& p,
-                    uint32_t* out_row, double* out_score, int32_t* out_n, cudaEvent_t done, uint64_t* seq);
+                    const prg_user_features* user_pinned, uint32_t* out_row, double* out_score, int32_t* out_n,
+                    cudaEvent_t done, uint64_t* seq);
 int recommend_end(prg_handle* h, uint64_t seq, cudaEvent_t done);
 int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint32_t* out_row, float* out_score,
                     int32_t* out_n);

@@ -5,11 +5,12 @@
 namespace prg {
 // gather_fm.cu
 int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logit_dev, uint16_t* x_dev,
-                     const uint64_t* keys_dev, uint32_t* rows_out);
+                     const uint64_t* keys_dev, uint32_t* rows_out, int rows_per_req);
+int user_prefix_device(prg_handle* h, const uint32_t* user_ids_dev, const float* user_dense_dev, int B, bool need_mlp);
 int logits_to_scores_device(prg_handle* h, const float* a, const float* b, const uint32_t* rows_dev, int M, double* out);
 // mlp.cu
 int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit_dev, const float* fm_logit_dev,
-                       const uint32_t* rows_dev, double* score_dev, bool* fused_score);
+                       const uint32_t* rows_dev, double* score_dev, double* score_map, const float* ubias, int rows_per_req);
 size_t mlp_act_bytes(const prg_handle* h, int M);
 // sort.cu
 int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32_t* perm_dev, const uint32_t* rows_dev,
@@ -47,34 +48,59 @@ static int adopt(const void* src, size_t bytes, int mem, const void** dst, bool*
   return PRG_OK;
 }
 
-// rank on device buffers: rows_dev [M] -> score_dev [M] f64.  keys_dev != nullptr (fused path): the candidates come as
-// the recall's order keys; the gather unpacks the rows into rows_dev (which is then an OUTPUT).
-static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int M, double* score_dev,
-                       const uint64_t* keys_dev = nullptr) {
+// rank on device buffers: rows_dev [B*n] -> score_dev [B*n] f64 (Item.Score = sum_o coef_o * score_o) and, optionally,
+// map_dev [B*n][heads].  keys_dev != nullptr (fused path): the candidates come as the recall's order keys; the gather
+// unpacks the rows into rows_dev (which is then an OUTPUT).  user: device pointers (ids [B][U], dense [B][n_dense]) or
+// nulls = every user feature absent (service/rank/algo_data.go:104-118 with an empty user map).
+static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int B, int n, double* score_dev,
+                       const uint64_t* keys_dev = nullptr, const prg_user_features* user = nullptr,
+                       double* map_dev = nullptr) {
   if (model != PRG_MODEL_FM && model != PRG_MODEL_MLP && model != PRG_MODEL_FM_MLP)
     return fail(PRG_EINVAL, "unknown rank model");
+  const int M = B * n;
   const bool need_mlp = model != PRG_MODEL_FM;
   const bool need_fm = model != PRG_MODEL_MLP;
   if (need_mlp && h->mlp_layers == 0) return fail(PRG_ESTATE, "MLP weights not set (prg_set_mlp)");
-  PRG_TRY(h->fm_logit.ensure((size_t)M * 4 * 2));
+  if (map_dev && !need_mlp) return fail(PRG_EINVAL, "per-head scores need a tower model");
+  PRG_TRY(h->fm_logit.ensure((size_t)M * 4 * (1 + 4)));
   float* fm_logit = (float*)h->fm_logit.p;
   float* mlp_logit = fm_logit + M;
   uint16_t* x = nullptr;
+  const bool has_user = h->n_user_fields + h->n_user_dense > 0;
   if (need_mlp) {
-    if ((size_t)h->n_fields * 16 != h->mlp_dims[0])
-      return fail(PRG_ESTATE, "MLP input width != n_fields * 16");
+    if ((size_t)h->n_fields * 16 != h->mlp_k_item || h->mlp_k_user != h->n_user_fields * 16 + h->n_user_dense)
+      return fail(PRG_ESTATE, "MLP input width != (n_fields + n_user_fields) * 16 + n_user_dense");
     PRG_TRY(h->act[0].ensure(mlp_act_bytes(h, M)));
     PRG_TRY(h->act[1].ensure(mlp_act_bytes(h, M)));
     x = (uint16_t*)h->act[0].p;
   }
-  PRG_TRY(gather_fm_device(h, rows_dev, M, fm_logit, x, keys_dev, keys_dev ? const_cast<uint32_t*>(rows_dev) : nullptr));
-  if (need_mlp) {
-    bool fused_score = false;   // the tower's last layer writes the scores itself when it can
-    PRG_TRY(mlp_forward_device(h, x, M, mlp_logit, need_fm ? fm_logit : nullptr, rows_dev, score_dev, &fused_score));
-    if (fused_score) return PRG_OK;
+  if (has_user) PRG_TRY(user_prefix_device(h, user ? user->ids : nullptr, user ? user->dense : nullptr, B, need_mlp));
+  PRG_TRY(gather_fm_device(h, rows_dev, M, fm_logit, x, keys_dev, keys_dev ? const_cast<uint32_t*>(rows_dev) : nullptr,
+                           has_user ? n : 0));
+  if (need_mlp)
+    return mlp_forward_device(h, x, M, mlp_logit, need_fm ? fm_logit : nullptr, rows_dev, score_dev, map_dev,
+                              has_user ? (const float*)h->ubias.p : nullptr, n);
+  return logits_to_scores_device(h, fm_logit, nullptr, rows_dev, M, score_dev);
+}
+
+// host-call staging of a batch's user features: *dev receives device pointers (nulls stay null)
+static int stage_user(prg_handle* h, const prg_user_features* user, int B, int mem, prg_user_features* dev) {
+  dev->ids = nullptr; dev->dense = nullptr;
+  if (!user) return PRG_OK;
+  if (mem == PRG_MEM_DEVICE) { *dev = *user; return PRG_OK; }
+  if (user->ids && h->n_user_fields) {
+    const size_t bytes = (size_t)B * h->n_user_fields * 4;
+    PRG_TRY(h->user_ids_dev.ensure(bytes));
+    PRG_CUDA(cudaMemcpyAsync(h->user_ids_dev.p, user->ids, bytes, cudaMemcpyHostToDevice, h->stream));
+    dev->ids = (const uint32_t*)h->user_ids_dev.p;
   }
-  return logits_to_scores_device(h, need_fm ? fm_logit : mlp_logit, (need_fm && need_mlp) ? mlp_logit : nullptr, rows_dev,
-                                 M, score_dev);
+  if (user->dense && h->n_user_dense) {
+    const size_t bytes = (size_t)B * h->n_user_dense * 4;
+    PRG_TRY(h->user_dense_dev.ensure(bytes));
+    PRG_CUDA(cudaMemcpyAsync(h->user_dense_dev.p, user->dense, bytes, cudaMemcpyHostToDevice, h->stream));
+    dev->dense = (const float*)h->user_dense_dev.p;
+  }
+  return PRG_OK;
 }
 
 __global__ void final_gather_kernel(const uint32_t* rows, const double* scores, const int32_t* idx, const int32_t* cnt,
@@ -101,26 +127,27 @@ __global__ void final_gather_kernel(const uint32_t* rows, const double* scores, 
 
 // stages after recall: topk_keys [B][k] (sorted, merged) -> rank -> sort -> DPP -> outputs
 static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
-                              double* out_score, int32_t* out_n);
+                              double* out_score, int32_t* out_n, const prg_user_features& user);
 
 // The recall's per-query status is validated AFTER the downstream stages have been enqueued (resolve_pending): in the
 // steady state the host never waits in the middle of a step; a failed query (adversarial row order) is redone densely
 // and the downstream stages are simply run again.
 static int recommend_device(prg_handle* h, const float* q_dev, int B, int k, int model, const prg_dpp_params& p,
-                            uint32_t* out_row, double* out_score, int32_t* out_n, bool resolve_now) {
+                            uint32_t* out_row, double* out_score, int32_t* out_n, bool resolve_now,
+                            const prg_user_features& user) {
   PRG_TRY(h->topk_keys.ensure((size_t)B * k * 8));
   PRG_TRY(recall_topk_device(h, q_dev, B, k, (uint64_t*)h->topk_keys.p, /*defer=*/true));
-  PRG_TRY(post_recall_device(h, B, k, model, p, out_row, out_score, out_n));
+  PRG_TRY(post_recall_device(h, B, k, model, p, out_row, out_score, out_n, user));
   if (h->pending.active) {
     h->pending.fused = true;
-    h->pending.model = model; h->pending.p = p;
+    h->pending.model = model; h->pending.p = p; h->pending.user = user;
     h->pending.out_row = out_row; h->pending.out_score = out_score; h->pending.out_n = out_n;
   }
   return resolve_now ? resolve_pending(h) : PRG_OK;
 }
 
 static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
-                              double* out_score, int32_t* out_n) {
+                              double* out_score, int32_t* out_n, const prg_user_features& user) {
   const int M = B * k;
   PRG_TRY(h->rec_rows.ensure((size_t)M * 4));
   PRG_TRY(h->out_score.ensure((size_t)M * 4));
@@ -133,7 +160,8 @@ static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_
   PRG_TRY(h->dpp_n.ensure((size_t)B * 4));
   PRG_TRY(h->dpp_status.ensure((size_t)B * 4));
   // 2. gather + rank (the gather unpacks the recall keys into rec_rows on the way)
-  PRG_TRY(rank_device(h, model, (const uint32_t*)h->rec_rows.p, M, (double*)h->rec_scores.p, (const uint64_t*)h->topk_keys.p));
+  PRG_TRY(rank_device(h, model, (const uint32_t*)h->rec_rows.p, B, k, (double*)h->rec_scores.p, (const uint64_t*)h->topk_keys.p,
+                      &user));
   // 3. ItemRankScore sort; the sort writes the sorted list for DPP itself
   PRG_TRY(sort_desc_device(h, (const double*)h->rec_scores.p, B, k, (int32_t*)h->rec_perm.p, (const uint32_t*)h->rec_rows.p,
                            (uint32_t*)h->rec_sorted_rows.p, (double*)h->rec_sorted_scores.p));
@@ -170,7 +198,7 @@ int resolve_pending(prg_handle* h) {
   int rc = recall_resolve(h, &repaired);
   if (rc == PRG_OK && repaired && fused) {
     rc = post_recall_device(h, h->pending.B, h->pending.k, h->pending.model, h->pending.p, h->pending.out_row,
-                            h->pending.out_score, h->pending.out_n);
+                            h->pending.out_score, h->pending.out_n, h->pending.user);
     if (rc == PRG_OK && h->pending.host_row) {   // an asynchronous call: its first copies carried the unrepaired results
       rc = copy_results_to_host(h, h->pending.B, h->pending.p.top_n, h->pending.out_row, h->pending.out_score,
                                 h->pending.out_n, h->pending.host_row, h->pending.host_score, h->pending.host_n,
@@ -183,9 +211,12 @@ int resolve_pending(prg_handle* h) {
 }
 
 int recommend_begin(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params& p,
-                    uint32_t* out_row, double* out_score, int32_t* out_n, cudaEvent_t done, uint64_t* seq) {
+                    const prg_user_features* user, uint32_t* out_row, double* out_score, int32_t* out_n, cudaEvent_t done,
+                    uint64_t* seq) {
   DevGuard g(h);   // settles the previous call's deferred check first (its scratch is about to be reused)
   if (!h->E) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
+  prg_user_features udev;
+  PRG_TRY(stage_user(h, user, B, PRG_MEM_HOST, &udev));
   if (h->deferred_status != PRG_OK) { const int rc = h->deferred_status; h->deferred_status = PRG_OK; return fail(rc, "deferred: " + h->deferred_msg); }
   const size_t TT = (size_t)B * p.top_n;
   PRG_TRY(h->q_dev.ensure((size_t)B * h->E_dim * 4));
@@ -195,7 +226,7 @@ int recommend_begin(prg_handle* h, const float* q, int B, int recall_k, int mode
   PRG_TRY(h->sort_perm.ensure((size_t)B * 4));
   PRG_CUDA(cudaMemcpyAsync(h->q_dev.p, q, (size_t)B * h->E_dim * 4, cudaMemcpyHostToDevice, h->stream));
   PRG_TRY(recommend_device(h, (const float*)h->q_dev.p, B, recall_k, model, p, (uint32_t*)h->out_row.p,
-                           (double*)h->rank_out.p, (int32_t*)h->sort_perm.p, /*resolve_now=*/false));
+                           (double*)h->rank_out.p, (int32_t*)h->sort_perm.p, /*resolve_now=*/false, udev));
   PRG_TRY(copy_results_to_host(h, B, p.top_n, (const uint32_t*)h->out_row.p, (const double*)h->rank_out.p,
                                (const int32_t*)h->sort_perm.p, out_row, out_score, out_n, done));
   *seq = ++h->call_seq;
@@ -299,19 +330,53 @@ int prg_set_diversity_matrix(prg_handle* h, const void* data, uint64_t rows, uin
   return PRG_OK;
 }
 
-int prg_rank(prg_handle* h, int model, const uint32_t* rows, int B, int n, double* out_score, int mem) {
+int prg_set_user_fields(prg_handle* h, uint32_t n_user_fields, uint32_t n_user_dense) {
   if (!h) return fail(PRG_EINVAL, "null handle");
-  if (!rows || !out_score || B <= 0 || n <= 0) return fail(PRG_EINVAL, "bad arguments");
+  if (n_user_fields > (uint32_t)kMaxFields || n_user_dense > 64) return fail(PRG_EINVAL, "n_user_fields <= 64, n_user_dense <= 64");
+  DevGuard g(h);
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  if (n_user_fields != h->n_user_fields || n_user_dense != h->n_user_dense) h->mlp_layers = 0;   // prg_set_mlp splits W1 by these
+  h->n_user_fields = n_user_fields;
+  h->n_user_dense = n_user_dense;
+  return PRG_OK;
+}
+
+int prg_set_rank_score(prg_handle* h, const double* coef, int n) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!coef || n < 1 || n > 4) return fail(PRG_EINVAL, "1..4 coefficients");
+  DevGuard g(h);
+  for (int o = 0; o < 4; ++o) h->rank_coef[o] = o < n ? coef[o] : 0.0;
+  return PRG_OK;
+}
+
+int prg_rank_ex(prg_handle* h, int model, const uint32_t* rows, int B, int n, const prg_user_features* user,
+                double* out_score, double* out_score_map, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!rows || (!out_score && !out_score_map) || B <= 0 || n <= 0) return fail(PRG_EINVAL, "bad arguments");
   DevGuard g(h);
   const int M = B * n;
-  if (mem == PRG_MEM_DEVICE) return rank_device(h, model, rows, M, out_score);
+  const int heads = h->mlp_layers ? (int)h->mlp_dims[h->mlp_layers] : 1;
+  prg_user_features udev;
+  PRG_TRY(stage_user(h, user, B, mem, &udev));
+  if (mem == PRG_MEM_DEVICE) {
+    if (!out_score) { PRG_TRY(h->rank_out.ensure((size_t)M * 8)); out_score = (double*)h->rank_out.p; }
+    return rank_device(h, model, rows, B, n, out_score, nullptr, &udev, out_score_map);
+  }
   PRG_TRY(h->rank_rows.ensure((size_t)M * 4));
   PRG_TRY(h->rank_out.ensure((size_t)M * 8));
+  if (out_score_map) PRG_TRY(h->rank_map.ensure((size_t)M * heads * 8));
   PRG_CUDA(cudaMemcpyAsync(h->rank_rows.p, rows, (size_t)M * 4, cudaMemcpyHostToDevice, h->stream));
-  PRG_TRY(rank_device(h, model, (const uint32_t*)h->rank_rows.p, M, (double*)h->rank_out.p));
-  PRG_CUDA(cudaMemcpyAsync(out_score, h->rank_out.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  PRG_TRY(rank_device(h, model, (const uint32_t*)h->rank_rows.p, B, n, (double*)h->rank_out.p, nullptr, &udev,
+                      out_score_map ? (double*)h->rank_map.p : nullptr));
+  if (out_score) PRG_CUDA(cudaMemcpyAsync(out_score, h->rank_out.p, (size_t)M * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (out_score_map)
+    PRG_CUDA(cudaMemcpyAsync(out_score_map, h->rank_map.p, (size_t)M * heads * 8, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaStreamSynchronize(h->stream));
   return PRG_OK;
+}
+
+int prg_rank(prg_handle* h, int model, const uint32_t* rows, int B, int n, double* out_score, int mem) {
+  return prg_rank_ex(h, model, rows, B, n, nullptr, out_score, nullptr, mem);
 }
 
 int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_dpp_params* p,
@@ -364,20 +429,58 @@ int prg_ssd(prg_handle* h, const uint32_t* rows, const double* score, int B, int
   return PRG_OK;
 }
 
-int prg_recommend_from_keys(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k, int model,
-                            const prg_dpp_params* p, uint32_t* out_row, double* out_score, int32_t* out_n, int mem) {
+int prg_recommend_from_keys_ex(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k, int model,
+                               const prg_dpp_params* p, const prg_user_features* user, uint32_t* out_row,
+                               double* out_score, int32_t* out_n, int mem) {
   if (!h) return fail(PRG_EINVAL, "null handle");
   if (!keys_dev || !p || !out_row || !out_score || !out_n) return fail(PRG_EINVAL, "null buffer");
   if (G <= 0 || B <= 0 || k <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "G, B, k, top_n must be positive");
   DevGuard g(h);
+  prg_user_features udev;
+  PRG_TRY(stage_user(h, user, B, mem, &udev));
   PRG_TRY(h->topk_keys.ensure((size_t)B * k * 8));
   PRG_TRY(merge_keys_device(h, keys_dev, G, g_stride, B, k, (uint64_t*)h->topk_keys.p));
-  if (mem == PRG_MEM_DEVICE) return post_recall_device(h, B, k, model, *p, out_row, out_score, out_n);
+  if (mem == PRG_MEM_DEVICE) return post_recall_device(h, B, k, model, *p, out_row, out_score, out_n, udev);
   const size_t TT = (size_t)B * p->top_n;
   PRG_TRY(h->out_row.ensure(TT * 4 > (size_t)B * k * 4 ? TT * 4 : (size_t)B * k * 4));
   PRG_TRY(h->rank_out.ensure(TT * 8));
   PRG_TRY(h->sort_perm.ensure((size_t)B * 4));
-  PRG_TRY(post_recall_device(h, B, k, model, *p, (uint32_t*)h->out_row.p, (double*)h->rank_out.p, (int32_t*)h->sort_perm.p));
+  PRG_TRY(post_recall_device(h, B, k, model, *p, (uint32_t*)h->out_row.p, (double*)h->rank_out.p, (int32_t*)h->sort_perm.p, udev));
+  PRG_CUDA(cudaMemcpyAsync(out_row, h->out_row.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_score, h->rank_out.p, TT * 8, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaMemcpyAsync(out_n, h->sort_perm.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  PRG_CUDA(cudaStreamSynchronize(h->stream));
+  return PRG_OK;
+}
+
+int prg_recommend_from_keys(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k, int model,
+                            const prg_dpp_params* p, uint32_t* out_row, double* out_score, int32_t* out_n, int mem) {
+  return prg_recommend_from_keys_ex(h, keys_dev, G, g_stride, B, k, model, p, nullptr, out_row, out_score, out_n, mem);
+}
+
+int prg_recommend_ex(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params* p,
+                     const prg_user_features* user, uint32_t* out_row, double* out_score, int32_t* out_n, int mem) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (!q || !p || !out_row || !out_score || !out_n) return fail(PRG_EINVAL, "null buffer");
+  if (B <= 0 || recall_k <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "B, recall_k, top_n must be positive");
+  DevGuard g(h);
+  if (!h->E) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
+  if (h->deferred_status != PRG_OK) { const int rc = h->deferred_status; h->deferred_status = PRG_OK; return fail(rc, "deferred: " + h->deferred_msg); }
+  prg_user_features udev;
+  PRG_TRY(stage_user(h, user, B, mem, &udev));
+  // PRG_MEM_DEVICE: the recall's exactness check is settled before the call returns (the host waits for the recall
+  // part only; everything downstream is already enqueued) unless the handle was created with "defer_check":1
+  if (mem == PRG_MEM_DEVICE)
+    return recommend_device(h, q, B, recall_k, model, *p, out_row, out_score, out_n, /*resolve_now=*/!h->defer_check, udev);
+  const size_t TT = (size_t)B * p->top_n;
+  PRG_TRY(h->q_dev.ensure((size_t)B * h->E_dim * 4));
+  PRG_TRY(h->out_row.ensure(TT * 4 > (size_t)B * recall_k * 4 ? TT * 4 : (size_t)B * recall_k * 4));
+  PRG_TRY(h->rank_out.ensure(TT * 8));
+  PRG_TRY(h->flags.ensure((size_t)(B > 64 ? B : 64) * 4));
+  PRG_CUDA(cudaMemcpyAsync(h->q_dev.p, q, (size_t)B * h->E_dim * 4, cudaMemcpyHostToDevice, h->stream));
+  PRG_TRY(h->sort_perm.ensure((size_t)B * 4));
+  PRG_TRY(recommend_device(h, (const float*)h->q_dev.p, B, recall_k, model, *p, (uint32_t*)h->out_row.p,
+                           (double*)h->rank_out.p, (int32_t*)h->sort_perm.p, /*resolve_now=*/true, udev));
   PRG_CUDA(cudaMemcpyAsync(out_row, h->out_row.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaMemcpyAsync(out_score, h->rank_out.p, TT * 8, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaMemcpyAsync(out_n, h->sort_perm.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -387,27 +490,7 @@ int prg_recommend_from_keys(prg_handle* h, const uint64_t* keys_dev, int G, uint
 
 int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params* p,
                   uint32_t* out_row, double* out_score, int32_t* out_n, int mem) {
-  if (!h) return fail(PRG_EINVAL, "null handle");
-  if (!q || !p || !out_row || !out_score || !out_n) return fail(PRG_EINVAL, "null buffer");
-  if (B <= 0 || recall_k <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "B, recall_k, top_n must be positive");
-  DevGuard g(h);
-  if (!h->E) return fail(PRG_ESTATE, "item matrix not set (prg_set_item_matrix)");
-  if (h->deferred_status != PRG_OK) { const int rc = h->deferred_status; h->deferred_status = PRG_OK; return fail(rc, "deferred: " + h->deferred_msg); }
-  if (mem == PRG_MEM_DEVICE) return recommend_device(h, q, B, recall_k, model, *p, out_row, out_score, out_n, /*resolve_now=*/false);
-  const size_t TT = (size_t)B * p->top_n;
-  PRG_TRY(h->q_dev.ensure((size_t)B * h->E_dim * 4));
-  PRG_TRY(h->out_row.ensure(TT * 4 > (size_t)B * recall_k * 4 ? TT * 4 : (size_t)B * recall_k * 4));
-  PRG_TRY(h->rank_out.ensure(TT * 8));
-  PRG_TRY(h->flags.ensure((size_t)(B > 64 ? B : 64) * 4));
-  PRG_CUDA(cudaMemcpyAsync(h->q_dev.p, q, (size_t)B * h->E_dim * 4, cudaMemcpyHostToDevice, h->stream));
-  PRG_TRY(h->sort_perm.ensure((size_t)B * 4));
-  PRG_TRY(recommend_device(h, (const float*)h->q_dev.p, B, recall_k, model, *p, (uint32_t*)h->out_row.p,
-                           (double*)h->rank_out.p, (int32_t*)h->sort_perm.p, /*resolve_now=*/true));
-  PRG_CUDA(cudaMemcpyAsync(out_row, h->out_row.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
-  PRG_CUDA(cudaMemcpyAsync(out_score, h->rank_out.p, TT * 8, cudaMemcpyDeviceToHost, h->stream));
-  PRG_CUDA(cudaMemcpyAsync(out_n, h->sort_perm.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
-  PRG_CUDA(cudaStreamSynchronize(h->stream));
-  return PRG_OK;
+  return prg_recommend_ex(h, q, B, recall_k, model, p, nullptr, out_row, out_score, out_n, mem);
 }
 
 }  // extern "C"

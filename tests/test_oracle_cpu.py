@@ -85,11 +85,47 @@ def test_mlp_against_numpy_float64(oracle_lib):
     rng = np.random.default_rng(3)
     x = (rng.standard_normal((40, 64)) * 0.5).astype(np.float32)
     got = oracle_lib.mlp_forward(x, dims, W, b)
-    a = x.astype(np.float64)
+    a = oracle_lib.bf16_to_f32(oracle_lib.f32_to_bf16(x)).astype(np.float64)   # the tower input is bf16(x)
     a = np.maximum(a @ oracle_lib.bf16_to_f32(W[0]).astype(np.float64).T + b[0], 0)
     want = a @ oracle_lib.bf16_to_f32(W[1]).astype(np.float64).T + b[1]
     # bf16x2 activations carry >= 16 significant bits
     assert np.allclose(got, want[:, 0], rtol=0, atol=2e-5)
+
+
+def test_user_features_against_numpy_float64(oracle_lib):
+    """features = userFeatures, then itemFeatures (service/rank/algo_data.go:104-118): FM over user + item fields,
+    tower input [item | user | dense]; multi-head output."""
+    F, U, nd = 5, 2, 3
+    fields, factors, linear = synth.rank_tables(n_items=200, n_fields=F + U, max_rows=100)
+    fields = np.ascontiguousarray(fields[:, :F])
+    rows = np.arange(200, dtype=np.uint32)
+    uid = np.array([7, 0xFFFFFFFF], dtype=np.uint32)
+    dense = np.array([0.25, -1.5, 3.0], dtype=np.float32)
+    logit, x = oracle_lib.gather_fm(fields, factors, linear, 0.1, rows, user_ids=uid, user_dense=dense)
+    v_item = np.stack([factors[f][fields[:, f]] for f in range(F)], axis=1).astype(np.float64)
+    v_user = np.zeros((200, U, 16))
+    v_user[:, 0] = factors[F][7]
+    v = np.concatenate([v_user, v_item], axis=1)
+    lin = 0.1 + float(linear[F][7]) + sum(linear[f][fields[:, f]].astype(np.float64) for f in range(F))
+    want = lin + 0.5 * ((v.sum(1) ** 2) - (v ** 2).sum(1)).sum(1)
+    assert np.allclose(logit, want, rtol=0, atol=1e-6)
+    assert x.shape == (200, (F + U) * 16 + nd)
+    assert (x[:, :F * 16].reshape(200, F, 16) == v_item.astype(np.float32)).all()
+    assert (x[:, F * 16:(F + 1) * 16] == factors[F][7]).all() and (x[:, (F + 1) * 16:(F + 2) * 16] == 0).all()
+    assert (x[:, (F + U) * 16:] == dense).all()
+    # without user features the two entry points agree bit for bit
+    a, _ = oracle_lib.gather_fm(fields, factors[:F], linear[:F], 0.1, rows)
+    b, _ = oracle_lib.gather_fm(fields, factors, linear, 0.1, rows, user_ids=np.full(U, 0xFFFFFFFF, dtype=np.uint32))
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    # three heads
+    dims = [x.shape[1] + 13, 64, 3]      # any input width
+    dims[0] = x.shape[1]
+    W, bs = synth.mlp_weights(dims)
+    got = oracle_lib.mlp_forward(x, dims, W, bs)
+    a0 = oracle_lib.bf16_to_f32(oracle_lib.f32_to_bf16(x)).astype(np.float64)
+    a1 = np.maximum(a0 @ oracle_lib.bf16_to_f32(W[0]).astype(np.float64).T + bs[0], 0)
+    want = a1 @ oracle_lib.bf16_to_f32(W[1]).astype(np.float64).T + bs[1]
+    assert got.shape == (200, 3) and np.allclose(got, want, rtol=0, atol=2e-5)
 
 
 def test_bf16_round_to_nearest_even(oracle_lib):
