@@ -55,7 +55,7 @@ func b200CheckIdx(t *testing.T, name string, got []int, want []int) {
 // DPPWithWindow / DPP (dpp_sort.go:477-551) on an L assembled with gonum exactly as KernelMatrix does
 // (:428-431 features, :463-472 the three dense products) — needs nothing but gonum and the two exported functions.
 func TestB200DPPFromGonumKernel(t *testing.T) {
-	for _, name := range b200Glob(t, "dpp_[!h]*.json") {
+	for _, name := range b200Glob(t, "dpp_[^h]*.json") {
 		var f b200DPPFixture
 		b200Load(t, name, &f)
 		if f.NormMode != 0 || f.ExpectStatus != 0 {

@@ -200,6 +200,9 @@ typedef struct prg_dpp_params {
   int32_t normalize_emb;    /* NormalizeEmb (dpp_sort.go:234-237) */
   int32_t candidate_count;  /* DPPConf.CandidateCount (dpp_sort.go:280-287) */
   double min_score_percent; /* DPPConf.MinScorePercent (dpp_sort.go:288-298) */
+  int32_t no_positive_sim;  /* 1 = DPPConf.EnsurePositiveSim == "false" (hook-only embeddings, dpp_sort.go:440-445): the
+                               feature row is [v ; 0] without the 1/sqrt2 scaling.  0 (default) = [v ; 1] / sqrt2 */
+  int32_t reserved;
 } prg_dpp_params;
 
 /* rows: B x n item rows into the diversity matrix; score: B x n f64 relevance (Item.Score) in the order the items
@@ -208,6 +211,17 @@ typedef struct prg_dpp_params {
  * unchanged, e.g. "all item score is zero", dpp_sort.go:385-388,397-400).  0xFFFFFFFF rows are padding. */
 int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_dpp_params* p,
             int32_t* out_idx, int32_t* out_n, int32_t* status, int mem);
+/* A candidate whose row is outside the diversity table (>= rows, e.g. 0xFFFFFFFE for an id the host could not map)
+ * has no embedding: the reference gives it a random unit vector (dpp_sort.go:250-262, unseeded); here it takes row
+ * (position in the request's list & 1023) of a fixed table of pseudo-random directions, so it competes like any other
+ * item and results are reproducible.
+ *
+ * prg_dpp_ex: embeddings from registered hooks (sort/dpp_sort.go:56-58, :362-370).  hook: B x n x hook_dim f64, the
+ * concatenated GenerateEmbedding output per candidate.  use_table != 0: concat(hook, table row) re-normalised as a whole
+ * (:416-421; rows indexes the f32 diversity table); use_table == 0: hook only (:432-447; rows may be NULL; NormalizeEmb
+ * and EnsurePositiveSim as in p).  hook == NULL is prg_dpp. */
+int prg_dpp_ex(prg_handle* h, const uint32_t* rows, const double* score, const double* hook, int hook_dim, int use_table,
+               int B, int n, const prg_dpp_params* p, int32_t* out_idx, int32_t* out_n, int32_t* status, int mem);
 
 /* ---------------------------------------------------------------- SSD re-rank (sort/ssd_sort.go) */
 

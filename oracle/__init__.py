@@ -216,6 +216,40 @@ def dpp_request(emb, score, top_n, alpha=1.0, window_size=10, norm_mode=0, norma
     return out[:ny].copy(), int(st.value)
 
 
+def dpp_substitute(sub_row, dim):
+    """The fixed direction a candidate without an embedding receives (oracle.c orc_dpp_substitute)."""
+    fn = lib().orc_dpp_substitute
+    fn.restype = C.c_float
+    fn.argtypes = [C.c_uint32, C.c_uint32]
+    return np.array([fn(sub_row, d) for d in range(dim)], dtype=np.float32)
+
+
+def dpp_request_ex(emb, score, top_n, present=None, hook=None, use_table=True, no_positive_sim=0, alpha=1.0,
+                   window_size=10, norm_mode=0, normalize_emb=1, candidate_count=0, min_score_percent=0.0, want_L=False):
+    """orc_dpp_request_ex: missing embeddings (present mask), hook embeddings [n, hook_dim], hook-only path."""
+    score = np.ascontiguousarray(score, dtype=np.float64)
+    n = score.shape[0]
+    emb = None if emb is None else np.ascontiguousarray(emb, dtype=np.float64)
+    D = 0 if emb is None else emb.shape[1]
+    hook = None if hook is None else np.ascontiguousarray(hook, dtype=np.float64)
+    present = None if present is None else np.ascontiguousarray(present, dtype=np.uint8)
+    p = DppParams(alpha, top_n, window_size, norm_mode, normalize_emb, candidate_count, min_score_percent)
+    out = np.full(max(top_n, n), -1, dtype=np.int32)
+    st = C.c_int32(0)
+    Ld = np.full(n, np.nan) if want_L else None
+    L0 = np.full(n, np.nan) if want_L else None
+    ny = lib().orc_dpp_request_ex(None if emb is None else _p(emb, C.c_double),
+                                  None if present is None else _p(present, C.c_uint8),
+                                  None if hook is None else _p(hook, C.c_double),
+                                  C.c_int(0 if hook is None else hook.shape[1]), C.c_int(1 if use_table else 0),
+                                  C.c_int(no_positive_sim), _p(score, C.c_double), C.c_int(n), C.c_int(D), C.byref(p),
+                                  _p(out, C.c_int32), C.byref(st), None if Ld is None else _p(Ld, C.c_double),
+                                  None if L0 is None else _p(L0, C.c_double))
+    if want_L:
+        return out[:ny].copy(), int(st.value), Ld, L0
+    return out[:ny].copy(), int(st.value)
+
+
 class SsdParams(C.Structure):
     _fields_ = [("gamma", C.c_double), ("top_n", C.c_int32), ("window_size", C.c_int32), ("norm_mode", C.c_int32),
                 ("normalize_emb", C.c_int32), ("use_ssd_star", C.c_int32), ("candidate_count", C.c_int32),

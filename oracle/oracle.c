@@ -689,8 +689,28 @@ static int dpp_once(const double* F, const double* r, int n, int D1, int top_n, 
  * when that repeats index 0 — the reference does, :477-491 with :497-499).  *status = 1 when the reference logs an
  * error and returns the items unchanged (out_idx = identity over the truncated list).
  */
-ORC_API int orc_dpp_request(const double* emb, const double* score, int n, int D, const orc_dpp_params* p,
-                            int32_t* out_idx, int32_t* status) {
+/* the fixed pseudo-random direction a candidate WITHOUT an embedding receives (the reference draws an unseeded random
+ * unit vector, dpp_sort.go:250-262): splitmix64 of (substitute row, dimension) -> 24-bit dyadic value in [-1, 1).
+ * Same function as pairec_b200/csrc/dpp_common.cuh dpp_substitute_value. */
+ORC_API float orc_dpp_substitute(uint32_t sub_row, uint32_t d) {
+  uint64_t z = (((uint64_t)sub_row << 32) | d) + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)((int32_t)(z >> 40) - (1 << 23)) * (1.0f / (float)(1 << 23));
+}
+
+/*
+ * General form.  present: n bytes (NULL = every candidate has a table embedding); a candidate without one takes
+ * substitute row (input position & 1023).  hook: n x hook_dim (NULL = no hooks), the concatenated GenerateEmbedding
+ * output (:362-370).  use_table = 0: hook-only path (:432-447) with p->normalize_emb and no_positive_sim
+ * (EnsurePositiveSim == "false": append 0, no 1/sqrt2).  hooks + table (:416-421): concat(hook, table row as cached),
+ * re-normalised as a whole whatever NormalizeEmb says.  The cached table row is normalised at load when
+ * p->normalize_emb (:234-237).  L_diag / L_row0 (nullable, n_trunc values each): diag(L) and row 0 of L.
+ */
+ORC_API int orc_dpp_request_ex(const double* emb, const uint8_t* present, const double* hook, int hook_dim, int use_table,
+                               int no_positive_sim, const double* score, int n, int D, const orc_dpp_params* p,
+                               int32_t* out_idx, int32_t* status, double* L_diag, double* L_row0) {
   *status = 0;
   if (n == 0) return 0;
   int window = p->window_size > 0 ? p->window_size : 10;
@@ -737,20 +757,51 @@ ORC_API int orc_dpp_request(const double* emb, const double* score, int n, int D
     for (int i = 0; i < m; ++i) out_idx[i] = order[i];
     ny = m;
   } else {
-    const int D1 = D + 1;
+    const int Dh = hook ? hook_dim : 0, Dt = use_table ? D : 0;
+    const int W = Dh + Dt, D1 = W + 1;
     double* F = (double*)malloc(sizeof(double) * (size_t)m * D1);
     double* r = (double*)malloc(sizeof(double) * (size_t)m);
     const double inv_sqrt2 = 0.70710678118654752440; /* 1/math.Sqrt2 as a Go constant expression */
     for (int i = 0; i < m; ++i) {
       double* f = F + (size_t)i * D1;
-      memcpy(f, emb + (size_t)order[i] * D, sizeof(double) * (size_t)D);
-      if (p->normalize_emb) { /* :234-237 floats.Scale(1/normV, vector) */
-        const double s = 1 / g_norm2(f, D);
-        for (int d = 0; d < D; ++d) f[d] *= s;
+      double* t = f + Dh; /* the table part */
+      if (Dh) memcpy(f, hook + (size_t)order[i] * Dh, sizeof(double) * (size_t)Dh);
+      if (Dt) {
+        if (!present || present[order[i]]) memcpy(t, emb + (size_t)order[i] * D, sizeof(double) * (size_t)D);
+        else for (int d = 0; d < D; ++d) t[d] = (double)orc_dpp_substitute((uint32_t)order[i] & 1023u, (uint32_t)d);
+        if (p->normalize_emb) { /* :234-237 floats.Scale(1/normV, vector) at load */
+          const double s = 1 / g_norm2(t, D);
+          for (int d = 0; d < D; ++d) t[d] *= s;
+        }
       }
-      f[D] = 1;
-      for (int d = 0; d < D1; ++d) f[d] *= inv_sqrt2; /* :428-429 */
+      int pos = 1;
+      if (Dt && Dh) {                 /* :416-421 concat re-normalised */
+        const double s = 1 / g_norm2(f, W);
+        for (int d = 0; d < W; ++d) f[d] *= s;
+      } else if (!Dt) {               /* :432-447 hook only */
+        if (p->normalize_emb) {
+          const double s = 1 / g_norm2(f, W);
+          for (int d = 0; d < W; ++d) f[d] *= s;
+        }
+        pos = !no_positive_sim;
+      }
+      if (pos) {
+        f[W] = 1;
+        for (int d = 0; d < D1; ++d) f[d] *= inv_sqrt2; /* :428-429 / :441-442 */
+      } else {
+        f[W] = 0;                                       /* :444 */
+      }
       r[i] = exp(p->alpha * rel[i]);                  /* :431 */
+    }
+    if (L_diag || L_row0) {
+      double* row = (double*)malloc(sizeof(double) * (size_t)m);
+      if (L_row0) { dpp_L_row(F, r, m, D1, 0, row); memcpy(L_row0, row, sizeof(double) * (size_t)m); }
+      if (L_diag)
+        for (int i = 0; i < m; ++i) {
+          const double sii = g_gemm_nt_elem(F + (size_t)i * D1, F + (size_t)i * D1, D1);
+          L_diag[i] = (r[i] * sii) * r[i];
+        }
+      free(row);
     }
     int32_t* res = (int32_t*)malloc(sizeof(int32_t) * (size_t)(T > 0 ? T : 1));
     if (T <= window) {
@@ -774,6 +825,11 @@ ORC_API int orc_dpp_request(const double* emb, const double* score, int n, int D
   }
   free(rel); free(order);
   return ny;
+}
+
+ORC_API int orc_dpp_request(const double* emb, const double* score, int n, int D, const orc_dpp_params* p,
+                            int32_t* out_idx, int32_t* status) {
+  return orc_dpp_request_ex(emb, NULL, NULL, 0, 1, 0, score, n, D, p, out_idx, status, NULL, NULL);
 }
 
 /* Dense kernel matrix exactly as KernelMatrix materialises it (for tests of the row-on-demand form). */

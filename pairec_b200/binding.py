@@ -24,7 +24,7 @@ EXPORTS = [
     "prg_dpp", "prg_ssd", "prg_recommend", "prg_recommend_from_keys", "prg_lookup", "prg_launch_count", "prg_recall_stats", "prg_timing",
     "prg_batcher_start", "prg_batcher_recommend", "prg_batcher_stats", "prg_batcher_stop", "prg_batcher_drive",
     "prg_set_user_fields", "prg_set_rank_score", "prg_rank_ex", "prg_recommend_ex", "prg_recommend_from_keys_ex",
-    "prg_batcher_recommend_ex", "prg_item_dim",
+    "prg_batcher_recommend_ex", "prg_item_dim", "prg_dpp_ex",
 ]
 
 
@@ -37,11 +37,13 @@ class PrgError(RuntimeError):
 class DppParams(C.Structure):
     """prg_dpp_params (DPPSortConfig / abtest knobs of sort/dpp_sort.go)."""
     _fields_ = [("alpha", C.c_double), ("top_n", C.c_int32), ("window_size", C.c_int32), ("norm_mode", C.c_int32),
-                ("normalize_emb", C.c_int32), ("candidate_count", C.c_int32), ("min_score_percent", C.c_double)]
+                ("normalize_emb", C.c_int32), ("candidate_count", C.c_int32), ("min_score_percent", C.c_double),
+                ("no_positive_sim", C.c_int32), ("reserved", C.c_int32)]
 
     def __init__(self, alpha=1.0, top_n=50, window_size=10, norm_mode=0, normalize_emb=1, candidate_count=0,
-                 min_score_percent=0.0):
-        super().__init__(alpha, top_n, window_size, norm_mode, normalize_emb, candidate_count, min_score_percent)
+                 min_score_percent=0.0, no_positive_sim=0):
+        super().__init__(alpha, top_n, window_size, norm_mode, normalize_emb, candidate_count, min_score_percent,
+                         no_positive_sim, 0)
 
 
 class SsdParams(C.Structure):
@@ -326,16 +328,19 @@ class Engine:
         return perm
 
     # ---------------------------------------------------------------- DPP
-    def dpp(self, rows, score, params):
-        rows = _np(rows, np.uint32)
+    def dpp(self, rows, score, params, hook=None, use_table=True):
+        """hook [B, n, hook_dim] f64: embeddings from registered hooks (sort/dpp_sort.go:362-370); use_table=False = hooks only."""
         score = _np(score, np.float64)
-        B, n = rows.shape
+        B, n = score.shape
+        rows = None if rows is None else _np(rows, np.uint32)
+        hook = None if hook is None else _np(hook, np.float64)
         T = params.top_n
         idx = np.full((B, T), -1, dtype=np.int32)
         cnt = np.zeros(B, dtype=np.int32)
         st = np.zeros(B, dtype=np.int32)
-        self._ck(self._lib.prg_dpp(self._h, _ptr(rows), _ptr(score), C.c_int(B), C.c_int(n), C.byref(params), _ptr(idx),
-                                   _ptr(cnt), _ptr(st), C.c_int(MEM_HOST)))
+        self._ck(self._lib.prg_dpp_ex(self._h, _ptr(rows), _ptr(score), _ptr(hook), C.c_int(0 if hook is None else hook.shape[2]),
+                                      C.c_int(1 if use_table else 0), C.c_int(B), C.c_int(n), C.byref(params), _ptr(idx),
+                                      _ptr(cnt), _ptr(st), C.c_int(MEM_HOST)))
         return idx, cnt, st
 
     def ssd(self, rows, score, params):

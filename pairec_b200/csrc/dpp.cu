@@ -9,8 +9,7 @@
 //
 // Embeddings are staged once per request into a transposed scratch Et[d][i] (coalesced per-dim reads in the
 // selection loop); normalisation (1/||e||, 1/sqrt2) is applied on the fly so the scratch stays at the table's width.
-#include "handle.h"
-#include <math_constants.h>
+#include "dpp_common.cuh"
 
 namespace prg {
 
@@ -31,6 +30,9 @@ struct DppArgs {
   int32_t* out_n;    // [B]
   int32_t* status;   // [B]
   int c_rows;        // rows of C held in shared memory
+  const float* D_sub;  // substitute directions for candidates without a table row (dpp_common.cuh)
+  int force_norm;      // hook + table path: the concatenated vector is always re-normalised (dpp_sort.go:418-421)
+  int no_pos;          // EnsurePositiveSim == "false" (hook-only path, :440-445): append 0, no 1/sqrt2 scaling
 };
 
 __device__ __forceinline__ uint64_t f64_ord_dev(double d) {
@@ -192,10 +194,11 @@ __global__ void __launch_bounds__(kDppMaxItems, 1) dpp_kernel(const DppArgs a) {
     const uint32_t row = rows[my_in];
     const bool have = (uint64_t)row < a.D_rows;
     const T* src = reinterpret_cast<const T*>(a.D) + (size_t)(have ? row : 0) * D;
+    const float* sub = a.D_sub + (size_t)((uint32_t)my_in & (kDppSubRows - 1)) * D;   // no table row: substitute direction
     // gonum floats.Norm(v, 2): scaled sum of squares, sequential
     double scale = 0.0, sumsq = 1.0;
     for (int d = 0; d < D; ++d) {
-      const T xv = have ? src[d] : (T)0;
+      const T xv = have ? src[d] : (T)sub[d];
       Et[(size_t)d * kDppMaxItems + tid] = xv;
       const double v = (double)xv;
       if (v != 0.0) {
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(kDppMaxItems, 1) dpp_kernel(const DppArgs a) {
         }
       }
     }
-    if (a.p.normalize_emb) inv = 1.0 / __dmul_rn(scale, sqrt(sumsq));
+    if (a.p.normalize_emb || a.force_norm) inv = 1.0 / __dmul_rn(scale, sqrt(sumsq));
     inv_s[tid] = inv;
     q_s[tid] = exp(__dmul_rn(a.p.alpha, rel));
   } else {
@@ -220,13 +223,16 @@ __global__ void __launch_bounds__(kDppMaxItems, 1) dpp_kernel(const DppArgs a) {
   existed[tid] = 0;
   __syncthreads();
   const double qi = q_s[tid];
-  const bool do_norm = a.p.normalize_emb != 0;
+  const bool do_norm = a.p.normalize_emb != 0 || a.force_norm != 0;
+  const bool pos = a.no_pos == 0;
 
-  // f_i[d] as the reference rounds it: (x * inv) * (1/sqrt2), or x * (1/sqrt2) without normalisation; f_i[D] = 1/sqrt2
+  // f_i[d] as the reference rounds it: (x * inv) * (1/sqrt2), or x * (1/sqrt2) without normalisation; f_i[D] = 1/sqrt2.
+  // EnsurePositiveSim == false: no 1/sqrt2 scaling and f_i[D] = 0 (:440-445)
   auto feat = [&](int d, int i, double invn) -> double {
-    if (d == D) return kInvSqrt2;
+    if (d == D) return pos ? kInvSqrt2 : 0.0;
     const double x = (double)Et[(size_t)d * kDppMaxItems + i];
-    return do_norm ? __dmul_rn(__dmul_rn(x, invn), kInvSqrt2) : __dmul_rn(x, kInvSqrt2);
+    const double t = do_norm ? __dmul_rn(x, invn) : x;
+    return pos ? __dmul_rn(t, kInvSqrt2) : t;
   };
   // S[j][i] in gonum Dgemm(NoTrans,Trans) order: 64-wide k blocks, DotUnitary = 4 partial sums, (s0+s2)+(s1+s3).
   // other[] holds f_j (shared memory) or nullptr for the diagonal (f_j == f_i).
@@ -368,6 +374,10 @@ int dpp_pair_device(prg_handle* h, const uint32_t* rows_dev, const double* score
                     const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status, bool* handled,
                     DppFinal* fin);
 
+int dpp_generic_launch(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
+                       int32_t* out_idx, int32_t* out_n, int32_t* status, int c_rows, const void* D, uint64_t D_rows,
+                       int D_dim, int dtype, int force_norm, int no_pos);
+
 static size_t dpp_smem_bytes(int c_rows, int top_n) {
   return (size_t)c_rows * kDppMaxItems * 8 + 2 * kDppMaxItems * 8 + 520 * 8 + 32 * 8 + 32 * 4 + kDppMaxItems * 4 +
          (size_t)((top_n + 3) & ~3) * 4 + kDppMaxItems + 64;
@@ -404,14 +414,23 @@ int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev,
     PRG_TRY(dpp_cluster_device(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, &handled, fin));
     if (handled) return PRG_OK;
   }
-  const size_t esz = h->D_dtype == PRG_F64 ? 8 : 4;
-  PRG_TRY(h->dpp_scratch.ensure((size_t)B * h->D_dim * kDppMaxItems * esz));
+  return dpp_generic_launch(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, c_rows, h->D, h->D_rows, (int)h->D_dim,
+                            h->D_dtype, 0, 0);
+}
+
+// the one-CTA-per-request kernel over any table (D, D_rows, D_dim, dtype)
+int dpp_generic_launch(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
+                       int32_t* out_idx, int32_t* out_n, int32_t* status, int c_rows, const void* D, uint64_t D_rows,
+                       int D_dim, int dtype, int force_norm, int no_pos) {
+  const size_t esz = dtype == PRG_F64 ? 8 : 4;
+  PRG_TRY(h->dpp_scratch.ensure((size_t)B * D_dim * kDppMaxItems * esz));
   DppArgs a{};
-  a.rows = rows_dev; a.score = score_dev; a.n = n; a.D = h->D; a.D_rows = h->D_rows; a.D_dim = (int)h->D_dim;
+  a.rows = rows_dev; a.score = score_dev; a.n = n; a.D = D; a.D_rows = D_rows; a.D_dim = D_dim;
   a.p = p; a.Et = h->dpp_scratch.p; a.out_idx = out_idx; a.out_n = out_n; a.status = status; a.c_rows = c_rows;
+  a.D_sub = (const float*)h->D_sub.p; a.force_norm = force_norm; a.no_pos = no_pos;
   const size_t smem = dpp_smem_bytes(c_rows, p.top_n);
   StageScope span(h, ST_DPP);
-  if (h->D_dtype == PRG_F64) {
+  if (dtype == PRG_F64) {
     PRG_CUDA(cudaFuncSetAttribute(dpp_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dpp_kernel<double><<<B, kDppMaxItems, smem, h->stream>>>(a);
   } else {
@@ -421,6 +440,68 @@ int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev,
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;
+}
+
+// ---------------------------------------------------------------- hook embeddings (sort/dpp_sort.go:362-370, :412-447)
+// RegisterEmbeddingHook functions return a []float64 per item; the host passes their concatenation per candidate as
+// hook[B][n][hook_dim] f64.  Three shapes of KernelMatrix:
+//   table only             (:422-431)  f = [e_table ; 1] / sqrt2                        -> the fast kernels above
+//   hooks + table          (:416-421)  v = concat(hook, e_table); v /= ||v||; f = [v ; 1] / sqrt2
+//   hooks only             (:432-447)  v = hook; v /= ||v|| if NormalizeEmb; f = [v ; 1] / sqrt2, or [v ; 0] when
+//                                      EnsurePositiveSim == "false"
+// e_table is the row as the cache holds it: normalised at load when NormalizeEmb (:234-237).  The per-call vectors are
+// assembled in fp64 by dpp_hook_concat_kernel and the generic kernel runs over them.
+__global__ void dpp_hook_concat_kernel(const uint32_t* __restrict__ rows, const double* __restrict__ hook, int hook_dim, int M,
+                                       int n, const float* __restrict__ D, const double* __restrict__ D_inv, uint64_t D_rows,
+                                       int D_dim, const float* __restrict__ D_sub, const double* __restrict__ D_sub_inv,
+                                       int normalize_emb, double* __restrict__ out, uint32_t* __restrict__ rows_out) {
+  const int i = blockIdx.x;            // candidate (b * n + position)
+  if (i >= M) return;
+  const int W = hook_dim + D_dim;
+  const uint32_t row = rows ? rows[i] : (uint32_t)i;
+  if (threadIdx.x == 0) rows_out[i] = (rows && row == 0xFFFFFFFFu) ? 0xFFFFFFFFu : (uint32_t)i;
+  for (int d = threadIdx.x; d < hook_dim; d += blockDim.x) out[(size_t)i * W + d] = hook[(size_t)i * hook_dim + d];
+  if (D_dim > 0) {
+    const bool have = (uint64_t)row < D_rows;
+    const uint32_t srow = (uint32_t)(i % n) & (kDppSubRows - 1);
+    const float* src = have ? D + (size_t)row * D_dim : D_sub + (size_t)srow * D_dim;
+    const double inv = !normalize_emb ? 1.0 : (have ? D_inv[row] : D_sub_inv[srow]);
+    for (int d = threadIdx.x; d < D_dim; d += blockDim.x) {
+      const double x = (double)src[d];
+      out[(size_t)i * W + hook_dim + d] = normalize_emb ? __dmul_rn(x, inv) : x;   // floats.Scale(1/normV, vector) at load
+    }
+  }
+}
+
+int dpp_hook_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, const double* hook_dev, int hook_dim,
+                    int use_table, int B, int n, const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status) {
+  if (hook_dim <= 0 || !hook_dev) return fail(PRG_EINVAL, "hook embeddings missing");
+  if (use_table && (!h->D || h->D_dtype != PRG_F32)) return fail(PRG_EUNSUPPORTED, "hooks + table need an f32 diversity table");
+  const int Dt = use_table ? (int)h->D_dim : 0;
+  const int W = hook_dim + Dt;
+  if (W > 512) return fail(PRG_EUNSUPPORTED, "prg_dpp_ex: hook_dim + table dim > 512");
+  if (n > kDppMaxN) return fail(PRG_EUNSUPPORTED, "prg_dpp: n > 4096");
+  const int window = p.window_size > 0 ? p.window_size : 10;
+  int c_rows = p.top_n <= window ? p.top_n : window;
+  if (c_rows < 6) c_rows = 6;
+  if (c_rows > 24) return fail(PRG_EUNSUPPORTED, "prg_dpp: window (or top_n when <= window) > 24");
+  const int M = B * n;
+  if (!h->D_sub.p) {   // no table was ever set: the substitutes are only touched when use_table
+    PRG_TRY(h->D_sub.ensure(16));
+  }
+  PRG_TRY(h->dpp_hook_E.ensure((size_t)M * W * 8));
+  PRG_TRY(h->dpp_hook_rows.ensure((size_t)M * 4));
+  dpp_hook_concat_kernel<<<M, 128, 0, h->stream>>>(rows_dev, hook_dev, hook_dim, M, n, (const float*)h->D,
+                                                   (const double*)h->D_inv.p, h->D_rows, Dt, (const float*)h->D_sub.p,
+                                                   (const double*)h->D_sub_inv.p, p.normalize_emb,
+                                                   (double*)h->dpp_hook_E.p, (uint32_t*)h->dpp_hook_rows.p);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  prg_dpp_params q = p;
+  int force_norm = 0;
+  if (use_table) { force_norm = 1; q.no_positive_sim = 0; }   // :416-431: always re-normalised, always [v ; 1] / sqrt2
+  return dpp_generic_launch(h, (const uint32_t*)h->dpp_hook_rows.p, score_dev, B, n, q, out_idx, out_n, status, c_rows,
+                            h->dpp_hook_E.p, (uint64_t)M, W, PRG_F64, force_norm, use_table ? 0 : (p.no_positive_sim != 0));
 }
 
 }  // namespace prg

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
     const int c = (int)rank * kClItems + tid;
     const bool act = c < m;
     const uint32_t r = act ? rows[order[c]] : 0u;
-    row_s[tid] = (act && (uint64_t)r < a.D_rows) ? r : 0xFFFFFFFFu;
+    row_s[tid] = dpp_row_code(act, r, a.D_rows, act ? order[c] : 0);
   }
   for (int i = tid; i < kClMaxItems; i += kClThreads) existed[i] = 0;
   __syncthreads();
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
   for (int g = tid; g < kClItems * CH; g += kClThreads) {
     const int row = g / CH, c = g % CH;
     const uint32_t rw = row_s[row];
-    const float4 v = (rw != 0xFFFFFFFFu) ? reinterpret_cast<const float4*>(a.D + (size_t)rw * D)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = (rw != 0xFFFFFFFFu) ? reinterpret_cast<const float4*>(dpp_row_ptr(a, rw, D))[c] : make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(XS + (size_t)row * D + 4 * (c ^ (row & (CH - 1)))) = v;
   }
   __syncthreads();
@@ -283,10 +283,10 @@ __global__ void __launch_bounds__(kClThreads, 1) dpp_cluster_kernel(const DppClA
     else if (a.p.norm_mode == 2) rel = __dadd_rn(__dmul_rn(__dsub_rn(rel, s_p0) / s_p1, 1 - 1e-6), 1e-6);
     // 1 / ||e|| comes from the per-row table built when the matrix was set (dpp_inv_norm_kernel: gonum floats.Norm in
     // its exact operation order).  Computing it here cost 44k cycles per request — 128 dependent divide/accumulate steps
-    // per candidate with only half the warps busy — for a value that is a pure function of the table row.  A row
-    // outside the table stands for a zero embedding: norm 0, inverse +inf, NaN features, exactly as computed before.
+    // per candidate with only half the warps busy — for a value that is a pure function of the table row.  A candidate
+    // without a table row takes a substitute direction (dpp_common.cuh) and its norm.
     const uint32_t rw = row_s[tid];
-    const double inv = !a.p.normalize_emb ? 1.0 : (rw != 0xFFFFFFFFu ? a.D_inv[rw] : 1.0 / __dmul_rn(0.0, 1.0));
+    const double inv = !a.p.normalize_emb ? 1.0 : (rw != 0xFFFFFFFFu ? dpp_row_inv(a, rw) : 1.0);
     inv_s[tid] = inv;
     q_s[tid] = act ? exp(__dmul_rn(a.p.alpha, rel)) : 0.0;
   }
@@ -612,8 +612,24 @@ __global__ void dpp_inv_norm_kernel(const float* __restrict__ D, uint64_t rows, 
   out[r] = 1.0 / __dmul_rn(scale, sqrt(sumsq));
 }
 
+__global__ void dpp_substitute_kernel(float* __restrict__ out, int dim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int)kDppSubRows * dim) out[i] = dpp_substitute_value((uint32_t)(i / dim), (uint32_t)(i % dim));
+}
+
 int dpp_cluster_prepare(prg_handle* h) {
-  if (h->D_dtype != PRG_F32) return PRG_OK;  // f64 tables take the generic kernel, which normalises on the fly
+  if (h->D_rows > (uint64_t)kDppMissBase) return fail(PRG_EUNSUPPORTED, "diversity table has more than 0xFFFFF000 rows");
+  // substitute directions for candidates without a table row (any table dtype; the values are f32)
+  PRG_TRY(h->D_sub.ensure((size_t)kDppSubRows * h->D_dim * 4));
+  PRG_TRY(h->D_sub_inv.ensure((size_t)kDppSubRows * 8));
+  dpp_substitute_kernel<<<(kDppSubRows * h->D_dim + 255) / 256, 256, 0, h->stream>>>((float*)h->D_sub.p, (int)h->D_dim);
+  dpp_inv_norm_kernel<<<(kDppSubRows + 255) / 256, 256, 0, h->stream>>>((const float*)h->D_sub.p, kDppSubRows, (int)h->D_dim,
+                                                                      (double*)h->D_sub_inv.p);
+  PRG_CUDA(cudaGetLastError());
+  if (h->D_dtype != PRG_F32) {  // f64 tables take the generic kernel, which normalises on the fly
+    PRG_CUDA(cudaStreamSynchronize(h->stream));
+    return PRG_OK;
+  }
   PRG_TRY(h->D_inv.ensure((size_t)h->D_rows * 8));
   const unsigned blocks = (unsigned)((h->D_rows + 255) / 256);
   dpp_inv_norm_kernel<<<blocks, 256, 0, h->stream>>>((const float*)h->D, h->D_rows, (int)h->D_dim, (double*)h->D_inv.p);
@@ -656,6 +672,7 @@ int dpp_cluster_device(prg_handle* h, const uint32_t* rows_dev, const double* sc
   if (c_rows > kClCRows) return PRG_OK;
   DppClArgs a{};
   a.rows = rows_dev; a.score = score_dev; a.n = n; a.D = (const float*)h->D; a.D_inv = (const double*)h->D_inv.p; a.D_rows = h->D_rows; a.p = p;
+  a.D_sub = (const float*)h->D_sub.p; a.D_sub_inv = (const double*)h->D_sub_inv.p;
   a.out_idx = out_idx; a.out_n = out_n; a.status = status;
   if (fin) { a.fin_row = fin->row; a.fin_score = fin->score; a.fin_n = fin->n; }
   StageScope span(h, ST_DPP);

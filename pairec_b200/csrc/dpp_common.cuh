@@ -14,12 +14,33 @@ constexpr int kClMaxN = 4096;
 constexpr int kClCRows = 24;
 constexpr double kInvSqrt2c = 0.70710678118654752440;
 
+// A candidate WITHOUT a row in the diversity table: the reference gives it an (unseeded) random unit vector
+// (sort/dpp_sort.go:250-262) — not reproducible by construction.  Here it gets row (input position & 1023) of a fixed
+// table of 1024 pseudo-random directions built when the diversity matrix is set (dpp_substitute_kernel: 24-bit dyadic
+// values from splitmix64, the same on the CPU oracle), so it competes like any other item and the result is
+// deterministic.  Row codes: < D_rows a table row, kDppMissBase + s a substitute row, 0xFFFFFFFF not a candidate.
+constexpr uint32_t kDppSubRows = 1024;
+constexpr uint32_t kDppMissBase = 0xFFFFF000u;
+__host__ __device__ __forceinline__ float dpp_substitute_value(uint32_t sub_row, uint32_t d) {
+  uint64_t z = (((uint64_t)sub_row << 32) | d) + 0x9E3779B97F4A7C15ull;   // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)((int32_t)(z >> 40) - (1 << 23)) * (1.0f / (float)(1 << 23));   // [-1, 1), exact in f32
+}
+__device__ __forceinline__ uint32_t dpp_row_code(bool act, uint32_t r, uint64_t D_rows, int in_idx) {
+  if (!act) return 0xFFFFFFFFu;
+  return (uint64_t)r < D_rows ? r : kDppMissBase + ((uint32_t)in_idx & (kDppSubRows - 1));
+}
+
 struct DppClArgs {
   const uint32_t* rows;
   const double* score;
   int n;
   const float* D;
   const double* D_inv;  // 1 / ||row|| per table row (dpp_inv_norm_kernel)
+  const float* D_sub;       // [kDppSubRows][D] substitute directions for candidates without a table row
+  const double* D_sub_inv;  // their 1 / ||row||
   uint64_t D_rows;
   prg_dpp_params p;
   int32_t* out_idx;
@@ -30,6 +51,13 @@ struct DppClArgs {
   double* fin_score;
   int32_t* fin_n;
 };
+
+__device__ __forceinline__ const float* dpp_row_ptr(const DppClArgs& a, uint32_t code, int D) {
+  return code >= kDppMissBase ? a.D_sub + (size_t)(code - kDppMissBase) * D : a.D + (size_t)code * D;
+}
+__device__ __forceinline__ double dpp_row_inv(const DppClArgs& a, uint32_t code) {
+  return code >= kDppMissBase ? a.D_sub_inv[code - kDppMissBase] : a.D_inv[code];
+}
 
 template <int D>
 struct ClCfg {

@@ -198,12 +198,12 @@ __global__ void __launch_bounds__(kLzThreads, 1) dpp_lazy_kernel(const DppClArgs
     const bool act = p < m;
     const int li = act ? lidx[p] : 0;
     const uint32_t r = act ? rows[order[li]] : 0xFFFFFFFFu;
-    const uint32_t rw = (act && (uint64_t)r < a.D_rows) ? r : 0xFFFFFFFFu;
+    const uint32_t rw = dpp_row_code(act, r, a.D_rows, act ? order[li] : 0);
     row_s[p] = rw;
     double rel = act ? score[order[li]] : 0.0;
     if (a.p.norm_mode == 1) rel = __dsub_rn(rel, s_p0) / s_p1;
     else if (a.p.norm_mode == 2) rel = __dadd_rn(__dmul_rn(__dsub_rn(rel, s_p0) / s_p1, 1 - 1e-6), 1e-6);
-    inv_s[p] = !a.p.normalize_emb ? 1.0 : (rw != 0xFFFFFFFFu ? a.D_inv[rw] : 1.0 / __dmul_rn(0.0, 1.0));
+    inv_s[p] = !a.p.normalize_emb ? 1.0 : (rw != 0xFFFFFFFFu ? dpp_row_inv(a, rw) : 1.0);
     q_s[p] = act ? exp(__dmul_rn(a.p.alpha, rel)) : 0.0;
     existed[p] = 0;
   }
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kLzThreads, 1) dpp_lazy_kernel(const DppClArgs
   auto build = [&](int p, double (&f)[CL]) {
     const uint32_t rw = row_s[p];
     const double inv = inv_s[p];
-    const float* src = a.D + (size_t)(rw != 0xFFFFFFFFu ? rw : 0) * D + 64 * bb + q;
+    const float* src = dpp_row_ptr(a, rw != 0xFFFFFFFFu ? rw : 0u, D) + 64 * bb + q;
 #pragma unroll
     for (int t = 0; t < CL; ++t) {
       const double x = (rw != 0xFFFFFFFFu) ? (double)__ldg(src + 4 * t) : 0.0;
@@ -452,6 +452,7 @@ int dpp_lazy_device(prg_handle* h, const uint32_t* rows_dev, const double* score
   if (c_rows > kLzCRows) return PRG_OK;
   DppClArgs a{};
   a.rows = rows_dev; a.score = score_dev; a.n = n; a.D = (const float*)h->D; a.D_inv = (const double*)h->D_inv.p; a.D_rows = h->D_rows; a.p = p;
+  a.D_sub = (const float*)h->D_sub.p; a.D_sub_inv = (const double*)h->D_sub_inv.p;
   a.out_idx = out_idx; a.out_n = out_n; a.status = status;
   StageScope span(h, ST_DPP);
   int rc = PRG_OK;

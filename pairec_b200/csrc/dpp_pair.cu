@@ -284,14 +284,14 @@ __global__ void __launch_bounds__(kPrThreads, 1) dpp_pair_kernel(const DppClArgs
     const int c = (int)rank * kPrItems + i;
     const bool act = c < m;
     const uint32_t r = act ? rows[order[c]] : 0u;
-    const uint32_t rw = (act && (uint64_t)r < a.D_rows) ? r : 0xFFFFFFFFu;
+    const uint32_t rw = dpp_row_code(act, r, a.D_rows, act ? order[c] : 0);
     row_s[i] = rw;
     double rel = act ? score[order[c]] : 0.0;
     if (a.p.norm_mode == 1) rel = __dsub_rn(rel, s_p0) / s_p1;
     else if (a.p.norm_mode == 2) rel = __dadd_rn(__dmul_rn(__dsub_rn(rel, s_p0) / s_p1, 1 - 1e-6), 1e-6);
-    // 1 / ||e|| from the per-row table built when the matrix was set; a row outside the table stands for a zero
-    // embedding: norm 0, inverse +inf, NaN features (dpp_cluster.cu)
-    inv_s[i] = !a.p.normalize_emb ? 1.0 : (rw != 0xFFFFFFFFu ? a.D_inv[rw] : 1.0 / __dmul_rn(0.0, 1.0));
+    // 1 / ||e|| from the per-row table built when the matrix was set; a candidate without a table row takes a
+    // substitute direction and its norm (dpp_common.cuh)
+    inv_s[i] = !a.p.normalize_emb ? 1.0 : (rw != 0xFFFFFFFFu ? dpp_row_inv(a, rw) : 1.0);
     q_s[i] = act ? exp(__dmul_rn(a.p.alpha, rel)) : 0.0;
   }
   for (int i = tid; i < kPrMaxItems; i += kPrThreads) existed[i] = 0;
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(kPrThreads, 1) dpp_pair_kernel(const DppClArgs
     for (int g = tid; g < 256 * CH; g += kPrThreads) {
       const int row = g / CH, c = g % CH;
       const uint32_t rw = row_s[hh * 256 + row];
-      const float4 v = (rw != 0xFFFFFFFFu) ? reinterpret_cast<const float4*>(a.D + (size_t)rw * D)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v = (rw != 0xFFFFFFFFu) ? reinterpret_cast<const float4*>(dpp_row_ptr(a, rw, D))[c] : make_float4(0.f, 0.f, 0.f, 0.f);
       *reinterpret_cast<float4*>(XS + (size_t)row * D + 4 * (c ^ (row & (CH - 1)))) = v;
     }
     __syncthreads();
@@ -639,6 +639,7 @@ int dpp_pair_device(prg_handle* h, const uint32_t* rows_dev, const double* score
   DppClArgs a{};
   a.rows = rows_dev; a.score = score_dev; a.n = n; a.D = (const float*)h->D; a.D_inv = (const double*)h->D_inv.p;
   a.D_rows = h->D_rows; a.p = p;
+  a.D_sub = (const float*)h->D_sub.p; a.D_sub_inv = (const double*)h->D_sub_inv.p;
   a.out_idx = out_idx; a.out_n = out_n; a.status = status;
   if (fin) { a.fin_row = fin->row; a.fin_score = fin->score; a.fin_n = fin->n; }
   StageScope span(h, ST_DPP);

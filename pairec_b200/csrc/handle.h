@@ -146,12 +146,14 @@ struct prg_handle {
   bool D_owned = false;
   uint64_t D_rows = 0;
   prg::DevBuf D_inv;        // D_rows f64: 1 / ||row|| (gonum floats.Norm order) of an f32 diversity table, built once at set time
+  prg::DevBuf D_sub, D_sub_inv;   // 1024 substitute directions (f32 [1024][D_dim]) + inverse norms for candidates without a table row
   uint32_t D_dim = 0;
   int D_dtype = PRG_F32;
   bool dpp_lazy = false;     // config "dpp_lazy": the lazy-evaluation kernel (dpp_lazy.cu) instead of the cluster kernel
   bool dpp_pair = true;      // config "dpp_pair" (dpp_pair.cu, default for dim-128 tables): 2-CTA clusters, features partly in tensor memory; 0 = 4-CTA cluster kernel
   bool dpp_generic = false;  // config "dpp_generic": force the one-CTA-per-request kernel (A/B measurements)
   prg::DevBuf dpp_scratch, dpp_rows, dpp_score, dpp_idx, dpp_n, dpp_status;
+  prg::DevBuf dpp_hook_E, dpp_hook_rows, dpp_hook_in;   // hook path: per-call fp64 vectors [B*n][hook_dim + D_dim], identity rows, staged hooks
 
   prg::DevBuf ssd_E, ssd_P;  // SSD: mutable fp64 embeddings [B][D][1024], projection history [B][w][1024]
 

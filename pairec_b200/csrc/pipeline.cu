@@ -19,6 +19,8 @@ int sort_desc_device(prg_handle* h, const double* score_dev, int B, int n, int32
 int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, int B, int n, const prg_dpp_params& p,
                int32_t* out_idx, int32_t* out_n, int32_t* status, DppFinal* fin = nullptr);
 
+int dpp_hook_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev, const double* hook_dev, int hook_dim,
+                    int use_table, int B, int n, const prg_dpp_params& p, int32_t* out_idx, int32_t* out_n, int32_t* status);
 // dpp_cluster.cu
 int dpp_cluster_prepare(prg_handle* h);
 // ssd.cu
@@ -379,29 +381,46 @@ int prg_rank(prg_handle* h, int model, const uint32_t* rows, int B, int n, doubl
   return prg_rank_ex(h, model, rows, B, n, nullptr, out_score, nullptr, mem);
 }
 
-int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_dpp_params* p,
-            int32_t* out_idx, int32_t* out_n, int32_t* status, int mem) {
+int prg_dpp_ex(prg_handle* h, const uint32_t* rows, const double* score, const double* hook, int hook_dim, int use_table,
+               int B, int n, const prg_dpp_params* p, int32_t* out_idx, int32_t* out_n, int32_t* status, int mem) {
   if (!h) return fail(PRG_EINVAL, "null handle");
-  if (!rows || !score || !p || !out_idx || !out_n || !status) return fail(PRG_EINVAL, "null buffer");
+  const bool hooks = hook != nullptr && hook_dim > 0;
+  if (!hooks) use_table = 1;
+  if ((use_table && !rows) || !score || !p || !out_idx || !out_n || !status) return fail(PRG_EINVAL, "null buffer");
   if (B <= 0 || n <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "B, n, top_n must be positive");
   DevGuard g(h);
-  if (mem == PRG_MEM_DEVICE) return dpp_device(h, rows, score, B, n, *p, out_idx, out_n, status);
+  if (use_table && !h->D) return fail(PRG_ESTATE, "diversity matrix not set (prg_set_diversity_matrix)");
+  auto run = [&](const uint32_t* r, const double* s, const double* hk, int32_t* oi, int32_t* on, int32_t* st) {
+    if (hooks) return dpp_hook_device(h, r, s, hk, hook_dim, use_table, B, n, *p, oi, on, st);
+    return dpp_device(h, r, s, B, n, *p, oi, on, st);
+  };
+  if (mem == PRG_MEM_DEVICE) return run(rows, score, hook, out_idx, out_n, status);
   const size_t M = (size_t)B * n, TT = (size_t)B * p->top_n;
   PRG_TRY(h->dpp_rows.ensure(M * 4));
   PRG_TRY(h->dpp_score.ensure(M * 8));
   PRG_TRY(h->dpp_idx.ensure(TT * 4));
   PRG_TRY(h->dpp_n.ensure((size_t)B * 4));
   PRG_TRY(h->dpp_status.ensure((size_t)B * 4));
-  PRG_CUDA(cudaMemcpyAsync(h->dpp_rows.p, rows, M * 4, cudaMemcpyHostToDevice, h->stream));
+  if (rows) PRG_CUDA(cudaMemcpyAsync(h->dpp_rows.p, rows, M * 4, cudaMemcpyHostToDevice, h->stream));
   PRG_CUDA(cudaMemcpyAsync(h->dpp_score.p, score, M * 8, cudaMemcpyHostToDevice, h->stream));
+  if (hooks) {
+    PRG_TRY(h->dpp_hook_in.ensure(M * hook_dim * 8));
+    PRG_CUDA(cudaMemcpyAsync(h->dpp_hook_in.p, hook, M * hook_dim * 8, cudaMemcpyHostToDevice, h->stream));
+  }
   PRG_CUDA(cudaMemsetAsync(h->dpp_idx.p, 0xFF, TT * 4, h->stream));
-  PRG_TRY(dpp_device(h, (const uint32_t*)h->dpp_rows.p, (const double*)h->dpp_score.p, B, n, *p, (int32_t*)h->dpp_idx.p,
-                     (int32_t*)h->dpp_n.p, (int32_t*)h->dpp_status.p));
+  PRG_TRY(run(rows ? (const uint32_t*)h->dpp_rows.p : nullptr, (const double*)h->dpp_score.p,
+              hooks ? (const double*)h->dpp_hook_in.p : nullptr, (int32_t*)h->dpp_idx.p, (int32_t*)h->dpp_n.p,
+              (int32_t*)h->dpp_status.p));
   PRG_CUDA(cudaMemcpyAsync(out_idx, h->dpp_idx.p, TT * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaMemcpyAsync(out_n, h->dpp_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaMemcpyAsync(status, h->dpp_status.p, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
   PRG_CUDA(cudaStreamSynchronize(h->stream));
   return PRG_OK;
+}
+
+int prg_dpp(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_dpp_params* p,
+            int32_t* out_idx, int32_t* out_n, int32_t* status, int mem) {
+  return prg_dpp_ex(h, rows, score, nullptr, 0, 1, B, n, p, out_idx, out_n, status, mem);
 }
 
 int prg_ssd(prg_handle* h, const uint32_t* rows, const double* score, int B, int n, const prg_ssd_params* p,

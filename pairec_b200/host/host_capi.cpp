@@ -93,8 +93,14 @@ int ph_register_gpu_plugins(ph_server* s, const char* recall_algo, const char* r
   if (!s || !s->catalog->h) { g_err = "no engine attached"; return 1; }
   if (recall_algo && *recall_algo)
     algorithm::RegisterAlgorithm(recall_algo, std::make_shared<algorithm::GpuVectorAlgorithm>(s->catalog));
-  if (rank_algo && *rank_algo)
+  if (rank_algo && *rank_algo) {
     algorithm::RegisterAlgorithm(rank_algo, std::make_shared<algorithm::GpuRankAlgorithm>(s->catalog, model));
+    // the IAlgorithm route sees only feature maps: the scenes that name the algorithm get the LoadFeatureFunc that writes
+    // the item id into the item's properties (feature.RegisterLoadFeatureFunc, service/feature/feature_service.go:36-38)
+    for (auto& rc : s->conf.RankConf)
+      for (auto& a : rc.second.RankAlgoList)
+        if (a == rank_algo) feature::RegisterLoadFeatureFunc(rc.first, feature::ItemIdProperty());
+  }
   if (dpp_sort && *dpp_sort) {
     recconf::DPPSortConfig dc;
     dc.Alpha = 1.0;
@@ -107,6 +113,50 @@ int ph_register_gpu_plugins(ph_server* s, const char* recall_algo, const char* r
   for (auto& rc : s->conf.RecallConfs)
     if (rc.RecallType == "VectorRecall") recall::RegisterRecall(rc.Name, std::make_shared<recall::VectorRecall>(rc, s->vectors));
   sort::Load(s->conf);
+  return 0;
+}
+static std::vector<ingest::FieldSpec> parse_field_specs(const Json& spec) {
+  std::vector<ingest::FieldSpec> specs;
+  for (const Json& e : spec.arr) {
+    ingest::FieldSpec fs;
+    fs.Column = e["column"].as_string();
+    fs.IsId = e["id"].as_bool(false);
+    for (const Json& v : e["vocab"].arr) {
+      if (v.type == Json::String) fs.Vocab.push_back(v.str);
+      else if (v.type == Json::Number)
+        fs.Vocab.push_back(ingest::ToString(v.num == std::floor(v.num) && std::fabs(v.num) < 9e15 ? module::Value((int64_t)v.num)
+                                                                                                : module::Value(v.num)));
+    }
+    specs.push_back(std::move(fs));
+  }
+  return specs;
+}
+// The GPU rank as a rank.IRank of `scene` (rank.RegisterRank, service/rank/rank_service.go:45-60): one prg_rank_ex call
+// per request with the Items and the User.  user_fields_json: field specs as in ph_encode_fields, applied to the
+// request's user features; dense_columns_json: ["col", ...] numeric user features for the tower.
+int ph_register_gpu_rank(ph_server* s, const char* scene, const char* name, int model, const char* user_fields_json,
+                         const char* dense_columns_json, int heads) {
+  if (!s || !s->catalog->h || !scene || !name) { g_err = "no engine attached / null argument"; return 1; }
+  Json spec, dense;
+  std::string err;
+  if (!Json::parse(user_fields_json ? user_fields_json : "[]", &spec, &err) || spec.type != Json::Array) { g_err = "bad user field spec JSON: " + err; return 1; }
+  if (!Json::parse(dense_columns_json ? dense_columns_json : "[]", &dense, &err) || dense.type != Json::Array) { g_err = "bad dense column JSON: " + err; return 1; }
+  std::vector<std::string> cols;
+  for (const Json& v : dense.arr) cols.push_back(v.as_string());
+  rank::RegisterRank(scene, std::make_shared<rank::GpuRank>(s->catalog, name, model, parse_field_specs(spec), std::move(cols), heads));
+  return 0;
+}
+// An embedding hook (sort.RegisterEmbeddingHook, sort/dpp_sort.go:56-58) backed by a host table: item id -> row of
+// emb[n_ids][dim] (ids without a row get zeros).  Stands for a user-registered Go function in the tests.
+int ph_register_embedding_hook(ph_server* s, const char* hook_name, const char* const* ids, const double* emb,
+                               unsigned long long n_ids, int dim) {
+  if (!s || !hook_name || (!ids && n_ids) || !emb || dim <= 0) { g_err = "null argument"; return 1; }
+  auto table = std::make_shared<std::unordered_map<std::string, std::vector<double>>>();
+  for (unsigned long long i = 0; i < n_ids; ++i) (*table)[ids[i]] = std::vector<double>(emb + i * dim, emb + (i + 1) * dim);
+  sort::RegisterEmbeddingHook(hook_name, [table, dim](context::RecommendContext*, const module::ItemPtr& it) {
+    auto f = table->find(it->Id);
+    return f == table->end() ? std::vector<double>((size_t)dim, 0.0) : f->second;
+  });
   return 0;
 }
 int ph_set_user_vector(ph_server* s, const char* uid, const char* vector_string) {

@@ -69,6 +69,8 @@ Error LoadConfig(const std::string& json, RecommendConfig* out) {
     c.DPPConf.EmbMissedThreshold = d["EmbMissedThreshold"].as_number();
     c.DPPConf.NormalizeEmb = d["NormalizeEmb"].as_string();
     c.DPPConf.EnsurePositiveSim = d["EnsurePositiveSim"].as_string();
+    c.DPPConf.TableName = d["TableName"].as_string();
+    for (auto& v : d["EmbeddingHookNames"].arr) c.DPPConf.EmbeddingHookNames.push_back(v.as_string());
     c.DPPConf.FilterRetrieveIds = str_list(d["FilterRetrieveIds"]);
     const Json& sd = s["SSDConf"];
     c.SSDConf.Name = sd["Name"].as_string();
@@ -216,6 +218,10 @@ Error GpuVectorAlgorithm::Run(const AlgoData& algoData, AlgoResult* out) {
   if (!pp || !*pp) return "GpuVectorAlgorithm: algoData is not *pai_web.VectorRequest";
   const pai_web::VectorRequest& req = **pp;
   if (req.K == 0 || req.Vector.empty()) return "GpuVectorAlgorithm: empty request";
+  // the C ABI takes no vector length; vector_recall.go:72-82 silently skips malformed "i:v" pairs, so short vectors occur
+  if (req.Vector.size() != (size_t)prg_item_dim(cat_->h))
+    return "GpuVectorAlgorithm: user vector has " + std::to_string(req.Vector.size()) + " elements, the item matrix " +
+           std::to_string(prg_item_dim(cat_->h));
   const int k = (int)req.K;
   std::vector<uint32_t> rows((size_t)k);
   std::vector<float> scores((size_t)k);
@@ -494,11 +500,43 @@ void Rank(module::User* user, std::vector<module::ItemPtr>& items, context::Reco
   if (rc == ctx->Config->RankConf.end()) return;  // rank_service.go:153-157: no config -> no rank
   RankWithConfig(rc->second, user, items, ctx);
 }
-void RankWithConfig(const recconf::RankConfig& rankConfig, module::User* user, std::vector<module::ItemPtr>& items,
+namespace {
+std::map<std::string, std::vector<std::shared_ptr<IRank>>>& rank_inters() {
+  static std::map<std::string, std::vector<std::shared_ptr<IRank>>> m;
+  return m;
+}
+}  // namespace
+void RegisterRank(const std::string& scene, std::shared_ptr<IRank> r) { rank_inters()[scene].push_back(std::move(r)); }
+void ResetRanks() { rank_inters().clear(); }
+
+void RankWithConfig(const recconf::RankConfig& rankConfig, module::User* user, std::vector<module::ItemPtr>& all_items,
                     context::RecommendContext* ctx) {
   int batchCount = rankConfig.BatchCount > 0 ? rankConfig.BatchCount : 100;  // :163-166
-  if (rankConfig.RankAlgoList.empty() && rankConfig.RankScore.empty()) return;
+  if (rankConfig.RankAlgoList.empty() && rankConfig.RankScore.empty()) return;  // :168-171 (before any custom rank runs)
   const module::Features userFeatures = user ? user->MakeUserFeatures() : module::Features();
+  // custom ranks (rank_service.go:131-137, :185-204): the first IRank whose Filter claims an item takes it, with
+  // features = item.GetFeatures() overlaid by the user's (custom_rank.go:33-43); the rest goes to the algorithms
+  std::vector<module::ItemPtr> items;
+  {
+    auto ri = rank_inters().find(ctx->GetParameter("scene"));
+    struct Claimed { std::vector<module::ItemPtr> items; algorithm::FeatureList data; };
+    std::vector<Claimed> claimed(ri == rank_inters().end() ? 0 : ri->second.size());
+    for (auto& it : all_items) {
+      bool taken = false;
+      for (size_t r = 0; r < claimed.size() && !taken; ++r) {
+        if (!ri->second[r]->Filter(user, it, ctx)) continue;
+        module::Features f = it->GetFeatures();
+        for (auto& kv : userFeatures) f[kv.first] = kv.second;
+        claimed[r].data.push_back(std::move(f));
+        claimed[r].items.push_back(it);
+        taken = true;
+      }
+      if (!taken) items.push_back(it);
+    }
+    for (size_t r = 0; r < claimed.size(); ++r)   // :237-246 (one goroutine per custom rank upstream)
+      if (!claimed[r].items.empty()) ri->second[r]->Rank(user, claimed[r].items, claimed[r].data, ctx);
+    if (items.empty()) return;   // :248-253
+  }
   std::shared_ptr<ast::Expr> exprAst;
   if (!rankConfig.RankScore.empty()) {
     Error e = ast::Parse(rankConfig.RankScore, &exprAst);
@@ -511,7 +549,6 @@ void RankWithConfig(const recconf::RankConfig& rankConfig, module::User* user, s
     for (size_t i = b0; i < b1; ++i) {  // AlgoDataGenerator.AddFeatures (algo_data.go:104-118): user ∪ item features
       module::Features f = userFeatures;
       for (auto& kv : items[i]->GetFeatures()) f[kv.first] = kv.second;
-      f["item_id"] = items[i]->Id;
       feats.push_back(std::move(f));
     }
     for (auto& algoName : rankConfig.RankAlgoList) {  // :264-289 (one goroutine per batch x algo upstream)
@@ -538,11 +575,76 @@ void RankWithConfig(const recconf::RankConfig& rankConfig, module::User* user, s
     }
   }
 }
+
+GpuRank::GpuRank(std::shared_ptr<GpuCatalog> cat, std::string name, int model, std::vector<ingest::FieldSpec> user_fields,
+                 std::vector<std::string> dense_columns, int heads)
+    : cat_(std::move(cat)), name_(std::move(name)), model_(model), heads_(heads < 1 ? 1 : heads),
+      user_enc_(std::make_shared<ingest::FieldEncoder>(std::move(user_fields))), dense_(std::move(dense_columns)) {}
+
+void GpuRank::Rank(module::User* user, std::vector<module::ItemPtr>& items, const algorithm::FeatureList&,
+                   context::RecommendContext* ctx) {
+  if (items.empty()) return;
+  std::vector<uint32_t> rows(items.size());
+  for (size_t i = 0; i < items.size(); ++i) {
+    auto r = cat_->row_of.find(items[i]->Id);
+    rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFFu : r->second;   // unknown id: padding row, score 0
+  }
+  const module::Features uf = user ? user->MakeUserFeatures() : module::Features();
+  std::vector<uint32_t> uid(user_enc_->size());
+  if (!uid.empty()) user_enc_->Encode(uf, uid.data());
+  std::vector<float> dense(dense_.size(), 0.f);
+  for (size_t c = 0; c < dense_.size(); ++c) {
+    auto it = uf.find(dense_[c]);
+    if (it == uf.end()) continue;
+    if (auto d = std::get_if<double>(&it->second)) dense[c] = (float)*d;
+    else if (auto i64 = std::get_if<int64_t>(&it->second)) dense[c] = (float)*i64;
+  }
+  prg_user_features u{uid.empty() ? nullptr : uid.data(), dense.empty() ? nullptr : dense.data()};
+  std::vector<double> sc(items.size()), smap(heads_ > 1 ? items.size() * (size_t)heads_ : 0);
+  if (prg_rank_ex(cat_->h, model_, rows.data(), 1, (int)rows.size(), &u, sc.data(), smap.empty() ? nullptr : smap.data(),
+                  PRG_MEM_HOST) != PRG_OK) {
+    ctx->LogError(std::string("module=rank\terror=run algorithm error(prg_rank_ex: ") + prg_last_error() + ")");  // :274-277
+    return;   // scores stay as they are, as when algorithm.Run fails upstream
+  }
+  for (size_t i = 0; i < items.size(); ++i) {
+    if (heads_ > 1)
+      for (int o = 0; o < heads_; ++o) items[i]->AddAlgoScore(name_ + "_" + std::to_string(o), smap[i * (size_t)heads_ + o]);
+    items[i]->AddAlgoScore(name_, sc[i]);
+    items[i]->Score = sc[i];
+  }
+}
 }  // namespace rank
+
+// ================================================================================================ feature
+namespace feature {
+namespace {
+std::map<std::string, LoadFeatureFunc>& load_funcs() {
+  static std::map<std::string, LoadFeatureFunc> m;
+  return m;
+}
+}  // namespace
+void RegisterLoadFeatureFunc(const std::string& scene, LoadFeatureFunc f) { load_funcs()[scene] = std::move(f); }
+void LoadFeatures(module::User* user, std::vector<module::ItemPtr>& items, context::RecommendContext* ctx) {
+  // feature_service.go:77-131.  The reference runs the scene's FeatureDaos first (replaced by the HBM tables) and the
+  // LoadFeatureFunc beside them; upstream additionally requires a FeatureConfs entry for the scene (:87)
+  auto it = load_funcs().find(ctx->GetParameter("scene"));
+  if (it != load_funcs().end() && it->second) it->second(user, items, ctx);
+}
+LoadFeatureFunc ItemIdProperty() {
+  return [](module::User*, std::vector<module::ItemPtr>& items, context::RecommendContext*) {
+    for (auto& it : items) it->AddProperty("item_id", it->Id);
+  };
+}
+void ResetLoadFuncs() { load_funcs().clear(); }
+}  // namespace feature
 
 // ================================================================================================ sort
 namespace sort {
 namespace {
+std::map<std::string, EmbeddingHookFunc>& embedding_hooks() {
+  static std::map<std::string, EmbeddingHookFunc> m;
+  return m;
+}
 std::map<std::string, std::shared_ptr<ISort>>& mapping() {
   static std::map<std::string, std::shared_ptr<ISort>> m;
   return m;
@@ -655,6 +757,8 @@ bool EmbeddingMissAboveThreshold(size_t missing, size_t total, double threshold)
   return total > 0 && (double)missing / (double)total > threshold;
 }
 
+void RegisterEmbeddingHook(const std::string& name, EmbeddingHookFunc fn) { embedding_hooks()[name] = std::move(fn); }
+
 GpuDPPSort::GpuDPPSort(const recconf::DPPSortConfig& c, std::shared_ptr<GpuCatalog> cat) : conf_(c), cat_(std::move(cat)) {
   if (conf_.WindowSize <= 0) conf_.WindowSize = 10;  // dpp_sort.go:89-91
   if (conf_.EmbMissedThreshold <= 0) conf_.EmbMissedThreshold = 0.5;  // :85, :101-103
@@ -675,48 +779,72 @@ Error GpuDPPSort::Sort(SortData* d) {
   }
   std::vector<module::ItemPtr> result = selected;
   if (!selected.empty()) {
-    std::vector<uint32_t> rows(selected.size());
-    std::vector<double> score(selected.size());
-    for (size_t i = 0; i < selected.size(); ++i) {
-      auto r = cat_->row_of.find(selected[i]->Id);
-      rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFEu : r->second;  // unknown id: out-of-table row -> zero embedding
-      score[i] = selected[i]->Score;
-    }
-    // what doSort holds when it loads the embeddings, and returns on every error path (:280-300, :304-307, :317-320)
+    // what doSort holds when it loads the embeddings, and returns on every error path (:280-300, :304-307, :317-320):
+    // already in Go's sort order and cut — the device gets exactly this list (no second presort / cut there)
     const std::vector<module::ItemPtr> head = DoSortHead(selected, ctx->Size, conf_.CandidateCount, conf_.MinScorePercent, false);
+    // hooks (:352-370): hasHookFunc = any configured name is registered; hasTable = TableName set (an attached catalog
+    // with a diversity table stands for it when the config names no hooks at all)
+    std::vector<EmbeddingHookFunc> hooks;
+    for (auto& name : conf_.EmbeddingHookNames) {
+      auto h = embedding_hooks().find(name);
+      if (h != embedding_hooks().end()) hooks.push_back(h->second);
+    }
+    const bool hasTable = !conf_.TableName.empty() || hooks.empty();
+    std::vector<uint32_t> rows(head.size());
+    std::vector<double> score(head.size());
     size_t missing = 0;
-    for (auto& it : head) missing += cat_->row_of.find(it->Id) == cat_->row_of.end();
-    if (EmbeddingMissAboveThreshold(missing, head.size(), conf_.EmbMissedThreshold)) {  // :246-249
+    for (size_t i = 0; i < head.size(); ++i) {
+      auto r = cat_->row_of.find(head[i]->Id);
+      rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFEu : r->second;  // no embedding: a substitute direction (prg_dpp)
+      missing += r == cat_->row_of.end();
+      score[i] = head[i]->Score;
+    }
+    if (hasTable && EmbeddingMissAboveThreshold(missing, head.size(), conf_.EmbMissedThreshold)) {  // :246-249
       ctx->LogError("load embedding table cache failed the number of items missing embedding is above threshold");
       result = head;
       result.insert(result.end(), backup.begin(), backup.end());
       candidates.swap(result);
       return "";
     }
-    // (items without an embedding below the threshold: the reference draws UNSEEDED random unit vectors, :250-262 —
-    // not reproducible by construction; here they get a zero embedding and are never picked before the fill)
+    std::vector<double> hook;
+    int hook_dim = 0;
+    bool hook_error = false;
+    if (!hooks.empty()) {
+      for (size_t i = 0; i < head.size() && !hook_error; ++i) {
+        std::vector<double> e;                                       // GenerateEmbedding (:362-370): concatenation
+        for (auto& fn : hooks) { auto part = fn(ctx, head[i]); e.insert(e.end(), part.begin(), part.end()); }
+        if (i == 0) { hook_dim = (int)e.size(); hook.reserve(head.size() * e.size()); }
+        if ((int)e.size() != hook_dim || hook_dim == 0) hook_error = true;   // :423-425 / :433-435
+        hook.insert(hook.end(), e.begin(), e.end());
+      }
+    }
     prg_dpp_params p{};
     p.alpha = conf_.Alpha;
     p.top_n = ctx->Size;
     p.window_size = conf_.WindowSize;
     p.norm_mode = 0;
     p.normalize_emb = (conf_.NormalizeEmb == "false" || conf_.NormalizeEmb == "False") ? 0 : 1;
-    p.candidate_count = conf_.CandidateCount;
-    p.min_score_percent = conf_.MinScorePercent;
+    p.no_positive_sim = (conf_.EnsurePositiveSim == "false" || conf_.EnsurePositiveSim == "False") ? 1 : 0;
     std::vector<int32_t> idx((size_t)std::max(1, ctx->Size), -1);
     int32_t n = 0, st = 0;
-    if (prg_dpp(cat_->h, rows.data(), score.data(), 1, (int)rows.size(), &p, idx.data(), &n, &st, PRG_MEM_HOST) != PRG_OK) {
-      ctx->LogError(std::string("build kernel matrix failed ") + prg_last_error());  // :317-320: `return items`
+    int rc = PRG_OK;
+    if (hook_error) {
+      ctx->LogError("build kernel matrix failed the length of user-defined function is not equal");
+      rc = PRG_EINVAL;
+    } else {
+      rc = prg_dpp_ex(cat_->h, rows.data(), score.data(), hook.empty() ? nullptr : hook.data(), hook_dim, hasTable ? 1 : 0, 1,
+                      (int)rows.size(), &p, idx.data(), &n, &st, PRG_MEM_HOST);
+      if (rc != PRG_OK) ctx->LogError(std::string("build kernel matrix failed ") + prg_last_error());  // :317-320: `return items`
+    }
+    if (rc != PRG_OK) {
       result = head;
     } else if (st != 0) {
       ctx->LogError("build kernel matrix failed all item score is zero");                 // :385-388, :397-400
       result = head;
     } else {
+      for (size_t i = 0; i < head.size(); ++i) head[i]->AddAlgoScore("dpp_relevance_score", score[i]);  // :411: every item
       result.clear();
-      for (int i = 0; i < n; ++i) {
-        selected[(size_t)idx[(size_t)i]]->AddAlgoScore("dpp_relevance_score", score[(size_t)idx[(size_t)i]]);  // :411
-        result.push_back(selected[(size_t)idx[(size_t)i]]);
-      }
+      for (int i = 0; i < n; ++i) result.push_back(head[(size_t)idx[(size_t)i]]);
     }
   }
   result.insert(result.end(), backup.begin(), backup.end());
@@ -744,16 +872,17 @@ Error GpuSSDSort::Sort(SortData* d) {
   }
   std::vector<module::ItemPtr> result = selected;
   if (!selected.empty()) {
-    std::vector<uint32_t> rows(selected.size());
-    std::vector<double> score(selected.size());
-    for (size_t i = 0; i < selected.size(); ++i) {
-      auto r = cat_->row_of.find(selected[i]->Id);
-      rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFEu : r->second;
-      score[i] = selected[i]->Score;
-    }
+    // doSort's list: sorted in Go's order and cut (ssd_sort.go:301-331); the device gets exactly this list
     const std::vector<module::ItemPtr> head = DoSortHead(selected, ctx->Size, conf_.CandidateCount, conf_.MinScorePercent, true);
+    std::vector<uint32_t> rows(head.size());
+    std::vector<double> score(head.size());
     size_t missing = 0;
-    for (auto& it : head) missing += cat_->row_of.find(it->Id) == cat_->row_of.end();
+    for (size_t i = 0; i < head.size(); ++i) {
+      auto r = cat_->row_of.find(head[i]->Id);
+      rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFEu : r->second;
+      missing += r == cat_->row_of.end();
+      score[i] = head[i]->Score;
+    }
     if (EmbeddingMissAboveThreshold(missing, head.size(), conf_.EmbMissedThreshold)) {  // ssd_sort.go:270-273, :334-337
       ctx->LogError("load embedding table cache failed the number of items missing embedding is above threshold");
       result = head;
@@ -768,8 +897,6 @@ Error GpuSSDSort::Sort(SortData* d) {
     p.norm_mode = 0;
     p.normalize_emb = (conf_.NormalizeEmb == "false" || conf_.NormalizeEmb == "False") ? 0 : 1;
     p.use_ssd_star = conf_.UseSSDStar ? 1 : 0;
-    p.candidate_count = conf_.CandidateCount;
-    p.min_score_percent = conf_.MinScorePercent;
     std::vector<int32_t> idx((size_t)std::max(1, ctx->Size), -1);
     int32_t n = 0, st = 0;
     if (prg_ssd(cat_->h, rows.data(), score.data(), 1, (int)rows.size(), &p, idx.data(), &n, &st, PRG_MEM_HOST) != PRG_OK) {
@@ -777,7 +904,7 @@ Error GpuSSDSort::Sort(SortData* d) {
       result = head;
     } else {
       result.clear();
-      for (int i = 0; i < n; ++i) result.push_back(selected[(size_t)idx[(size_t)i]]);
+      for (int i = 0; i < n; ++i) result.push_back(head[(size_t)idx[(size_t)i]]);
     }
   }
   result.insert(result.end(), backup.begin(), backup.end());
@@ -1017,6 +1144,7 @@ std::vector<module::ItemPtr> Recommend(module::User* user, context::RecommendCon
     }
   }
   items = general_rank::Rank(user, items, ctx);   // user_recommend.go:116
+  feature::LoadFeatures(user, items, ctx);        // :129
   rank::Rank(user, items, ctx);                   // :137
   sort::SortData sd;
   sd.Data = items;
@@ -1030,8 +1158,12 @@ std::vector<module::ItemPtr> Recommend(module::User* user, context::RecommendCon
 }  // namespace service
 
 namespace filter { void ResetFilters(); }
+namespace feature { void ResetLoadFuncs(); }
 void ResetRegistries() {
   filter::ResetFilters();
+  feature::ResetLoadFuncs();
+  rank::ResetRanks();
+  sort::embedding_hooks().clear();
   sort::mapping().clear();
   sort::strategies().clear();
   recall::registry().clear();

@@ -44,7 +44,8 @@ struct AlgoConfig { std::string Name, Type; LookupConfig LookupConf; };
 struct RecallConfig { std::string Name, RecallType, RecallAlgo, ItemType; int RecallCount = 0; };
 struct RankConfig { std::vector<std::string> RankAlgoList; std::string RankScore, Processor; int BatchCount = 0; };
 struct DPPSortConfig {
-  std::string Name, NormalizeEmb, EnsurePositiveSim;
+  std::string Name, NormalizeEmb, EnsurePositiveSim, TableName;
+  std::vector<std::string> EmbeddingHookNames;
   double Alpha = 0, MinScorePercent = 0, EmbMissedThreshold = 0;   // recconf.go:960-979
   int WindowSize = 0, AbortRunCount = 0, CandidateCount = 0;
   std::vector<std::string> FilterRetrieveIds;
@@ -192,7 +193,11 @@ class GpuVectorAlgorithm : public IAlgorithm {
  private:
   std::shared_ptr<GpuCatalog> cat_;
 };
-// IAlgorithm behind a RankAlgoList name: feature maps (carrying "item_id") -> scores through prg_rank
+// IAlgorithm behind a RankAlgoList name: feature maps -> scores through prg_rank.  The stock feature maps
+// (service/rank/algo_data.go:104-118 over module/item.go:229-248) carry NO item id: this adapter needs the "item_id"
+// property that feature::ItemIdProperty() (a LoadFeatureFunc, service/feature/feature_service.go:36-38) writes; a map
+// without it scores 0 (comma-ok lookup, never a panic).  It cannot see which request a batch belongs to, so user
+// features do not reach the model through it — rank::GpuRank (the IRank plugin) is the full-featured drop-in.
 class GpuRankAlgorithm : public IAlgorithm {
  public:
   GpuRankAlgorithm(std::shared_ptr<GpuCatalog> c, int model) : cat_(std::move(c)), model_(model) {}
@@ -246,11 +251,50 @@ struct Expr;
 Error Parse(const std::string& src, std::shared_ptr<Expr>* out);
 Error Eval(const Expr& e, const std::function<bool(const std::string&, double*)>& param, double* out);
 }  // namespace ast
+namespace ingest { struct FieldSpec; class FieldEncoder; }
+namespace feature {
+// service/feature/feature_service.go:20-38: the user-defined feature loader of a scene, run before rank
+// (service/user_recommend.go:129).  The FeatureDaos themselves are replaced by the HBM-resident tables.
+using LoadFeatureFunc = std::function<void(module::User*, std::vector<module::ItemPtr>&, context::RecommendContext*)>;
+void RegisterLoadFeatureFunc(const std::string& scene, LoadFeatureFunc f);
+void LoadFeatures(module::User* user, std::vector<module::ItemPtr>& items, context::RecommendContext* ctx);
+LoadFeatureFunc ItemIdProperty();   // item.AddProperty("item_id", item.Id)
+}
 namespace rank {
+// service/rank/custom_rank.go:8-13.  Items a custom rank claims (Filter) bypass the BatchCount-sized algorithm.Run
+// fan-out and reach Rank() in ONE call per request, as Items, together with the User (rank_service.go:185-200,237-246)
+struct IRank {
+  virtual ~IRank() = default;
+  virtual bool Filter(module::User* user, const module::ItemPtr& item, context::RecommendContext* ctx) = 0;
+  virtual void Rank(module::User* user, std::vector<module::ItemPtr>& items, const algorithm::FeatureList& requestData,
+                    context::RecommendContext* ctx) = 0;
+};
+void RegisterRank(const std::string& scene, std::shared_ptr<IRank> r);   // rank_service.go:45-60
+void ResetRanks();
 void Rank(module::User* user, std::vector<module::ItemPtr>& items, context::RecommendContext* ctx);  // RankService.Rank
 // the shared core: batches -> algorithm.Run -> AddAlgoScore -> RankScore expression (rank_service.go:163-363)
 void RankWithConfig(const recconf::RankConfig& rankConfig, module::User* user, std::vector<module::ItemPtr>& items,
                     context::RecommendContext* ctx);
+}
+namespace rank {
+// The GPU rank as an IRank: every item of the request in one prg_rank_ex call, the user's categorical features encoded
+// by `user_fields` (ingest::FieldEncoder over user.MakeUserFeatures()) and numeric context features by `dense_columns`.
+// Writes algoScores[name] (and name_<head> for a multi-head tower) and Item.Score, as RankService does for its own
+// algorithms (rank_service.go:313-363 with RankScore = "${name}").
+class GpuRank : public IRank {
+ public:
+  GpuRank(std::shared_ptr<GpuCatalog> cat, std::string name, int model, std::vector<ingest::FieldSpec> user_fields,
+          std::vector<std::string> dense_columns, int heads);
+  bool Filter(module::User*, const module::ItemPtr&, context::RecommendContext*) override { return true; }
+  void Rank(module::User* user, std::vector<module::ItemPtr>& items, const algorithm::FeatureList& requestData,
+            context::RecommendContext* ctx) override;
+ private:
+  std::shared_ptr<GpuCatalog> cat_;
+  std::string name_;
+  int model_, heads_;
+  std::shared_ptr<ingest::FieldEncoder> user_enc_;
+  std::vector<std::string> dense_;
+};
 }
 namespace general_rank {
 // GeneralRankService.Rank (service/general_rank/general_rank.go:216) -> BaseGeneralRank.DoRank
@@ -305,6 +349,9 @@ class GpuDPPSort : public ISort {
   recconf::DPPSortConfig conf_;
   std::shared_ptr<GpuCatalog> cat_;
 };
+// sort/dpp_sort.go:52-58: hooks return a []float64 per item; DPPConf.EmbeddingHookNames selects them (:362-370)
+using EmbeddingHookFunc = std::function<std::vector<double>(context::RecommendContext*, const module::ItemPtr&)>;
+void RegisterEmbeddingHook(const std::string& name, EmbeddingHookFunc fn);
 // SSDSort.Sort (sort/ssd_sort.go:108-190) with doSort + SSDWithSlidingWindow on the GPU (prg_ssd)
 class GpuSSDSort : public ISort {
  public:

@@ -63,6 +63,20 @@ class HostServer:
         self._ck(self._lib.ph_register_gpu_plugins(self._h, recall_algo.encode(), rank_algo.encode(), C.c_int(model),
                                                    dpp_sort.encode()))
 
+    def register_gpu_rank(self, scene, name, model, user_fields=(), dense_columns=(), heads=1):
+        """The GPU rank as the scene's rank.IRank (service/rank/custom_rank.go:8-13): Items + User in one call per request."""
+        self._ck(self._lib.ph_register_gpu_rank(self._h, scene.encode(), name.encode(), C.c_int(model),
+                                                json.dumps(list(user_fields)).encode(),
+                                                json.dumps(list(dense_columns)).encode(), C.c_int(heads)))
+
+    def register_embedding_hook(self, hook_name, ids, emb):
+        """sort.RegisterEmbeddingHook(hook_name, fn) with fn = lookup of the item id in emb [len(ids), dim] (f64)."""
+        import numpy as np
+        emb = np.ascontiguousarray(emb, dtype=np.float64)
+        arr = (C.c_char_p * len(ids))(*[s.encode() for s in ids])
+        self._ck(self._lib.ph_register_embedding_hook(self._h, hook_name.encode(), arr, emb.ctypes.data_as(C.c_void_p),
+                                                      C.c_ulonglong(len(ids)), C.c_int(emb.shape[1])))
+
     def set_user_vector(self, uid, vector):
         s = " ".join(f"{i}:{float(v)!r}" for i, v in enumerate(vector))
         self._ck(self._lib.ph_set_user_vector(self._h, uid.encode(), s.encode()))

@@ -203,3 +203,130 @@ def test_ssd_variants(engine, oracle_lib, kw):
 def test_ssd_f64_table_and_small_inputs(engine, oracle_lib):
     _ssd_case(engine, oracle_lib, n=200, dim=24, top_n=10, dtype=np.float64, gamma=0.25, window_size=5)
     _ssd_case(engine, oracle_lib, n=7, dim=16, top_n=20, gamma=0.25, window_size=5)   # ctx.Size > n: T = n
+
+
+# ---------------------------------------------------------------- a11: missing embeddings, hook embeddings
+def _missing_case(eng, oracle_lib, n, dim, top_n, n_missing, dtype=np.float32, **kw):
+    from pairec_b200 import DppParams
+    D = synth.diversity(n_items=3000, dim=dim, dtype=dtype)
+    eng.set_diversity_matrix(D)
+    rng = np.random.default_rng(n + n_missing)
+    B = 3
+    rows = np.stack([rng.choice(3000, size=n, replace=False) for _ in range(B)]).astype(np.uint32)
+    present = np.ones((B, n), dtype=np.uint8)
+    for b in range(B):
+        miss = rng.choice(n, size=n_missing, replace=False)
+        present[b, miss] = 0
+        rows[b, miss[::2]] = 0xFFFFFFFE          # the id the host mirror uses for an unknown item
+        rows[b, miss[1::2]] = 3000 + 5           # or any row outside the table
+    score = rng.random((B, n))
+    p = DppParams(top_n=top_n, **kw)
+    idx, cnt, st = eng.dpp(rows, score, p)
+    for b in range(B):
+        emb = D[np.minimum(rows[b], 2999)].astype(np.float64)
+        want, wst = oracle_lib.dpp_request_ex(emb, score[b], top_n, present=present[b], alpha=p.alpha,
+                                              window_size=p.window_size, normalize_emb=p.normalize_emb)
+        assert st[b] == wst == 0
+        assert cnt[b] == len(want) and (idx[b, :cnt[b]] == want).all(), f"request {b}: selection sequence differs"
+        assert len(set(idx[b, :cnt[b]].tolist())) == cnt[b], "picks must be distinct items"
+    return idx, cnt, present
+
+
+@pytest.mark.parametrize("dim,cfg", [(128, {}), (128, {"dpp_pair": 0}), (32, {}), (64, {"dpp_lazy": 1}), (24, {})])
+def test_dpp_candidates_without_embedding_take_substitute_directions(oracle_lib, dim, cfg):
+    """The reference gives an item without a table embedding a random unit vector and keeps ranking
+    (sort/dpp_sort.go:250-262); here a fixed pseudo-random direction: the item competes, picks stay distinct, and the
+    sequence equals the oracle's — on every kernel (pair, 4-CTA cluster, lazy, generic)."""
+    from pairec_b200 import Engine
+    eng = Engine(0, **cfg)
+    try:
+        idx, cnt, present = _missing_case(eng, oracle_lib, n=600, dim=dim, top_n=40, n_missing=200, alpha=1.0, window_size=10)
+        picked_missing = sum(int((present[b][idx[b, :cnt[b]]] == 0).sum()) for b in range(3))
+        assert picked_missing > 0, "embedding-less items must be able to win"
+        # fewer items WITH an embedding than top_n: the rest of the list is still made of distinct items
+        _missing_case(eng, oracle_lib, n=60, dim=dim, top_n=50, n_missing=45, alpha=1.0, window_size=10)
+        _missing_case(eng, oracle_lib, n=300, dim=dim, top_n=20, n_missing=100, alpha=0.5, window_size=10, normalize_emb=0)
+    finally:
+        eng.close()
+
+
+def test_dpp_substitute_table_matches_oracle(oracle_lib):
+    a = oracle_lib.dpp_substitute(7, 128)
+    assert a.dtype == np.float32 and np.abs(a).max() < 1.0 and np.unique(a).size > 100
+
+
+@pytest.mark.parametrize("mode", ["hook+table", "hook", "hook-raw", "hook-nopos"])
+def test_dpp_hook_embeddings(engine, oracle_lib, mode):
+    """RegisterEmbeddingHook embeddings (sort/dpp_sort.go:362-370): concat(hook, table) re-normalised (:416-421), hook only
+    with / without NormalizeEmb and with EnsurePositiveSim == false (:432-447)."""
+    from pairec_b200 import DppParams
+    dim, hd, n, top_n, B = 64, 12, 500, 30, 3
+    D = synth.diversity(n_items=3000, dim=dim)
+    engine.set_diversity_matrix(D)
+    rng = np.random.default_rng(11)
+    rows = np.stack([rng.choice(3000, size=n, replace=False) for _ in range(B)]).astype(np.uint32)
+    score = rng.random((B, n))
+    hook = rng.standard_normal((B, n, hd)) * 0.7
+    use_table = mode == "hook+table"
+    p = DppParams(top_n=top_n, alpha=1.0, window_size=10, normalize_emb=0 if mode == "hook-raw" else 1,
+                  no_positive_sim=1 if mode == "hook-nopos" else 0)
+    if mode == "hook-raw":
+        hook = hook / np.linalg.norm(hook, axis=2, keepdims=True) * 0.9
+    idx, cnt, st = engine.dpp(rows if use_table else None, score, p, hook=hook, use_table=use_table)
+    for b in range(B):
+        want, wst = oracle_lib.dpp_request_ex(D[rows[b]].astype(np.float64) if use_table else None, score[b], top_n,
+                                              hook=hook[b], use_table=use_table, no_positive_sim=p.no_positive_sim,
+                                              alpha=1.0, window_size=10, normalize_emb=p.normalize_emb)
+        assert st[b] == wst == 0
+        assert cnt[b] == len(want) and (idx[b, :cnt[b]] == want).all(), f"{mode}: request {b} differs"
+    # the hooks matter: the table-only sequence is a different one
+    if use_table:
+        idx0, _, _ = engine.dpp(rows, score, p)
+        assert not (idx0 == idx).all()
+
+
+def test_gpu_replays_the_go_fixtures(engine, oracle_lib):
+    """baseline/go/testdata/dpp_*.json are what baseline/go/sort/b200_dpp_test.go feeds to the reference's own
+    KernelMatrix + DPPWithWindow; the CUDA path must give the expected sequences on the same inputs."""
+    import glob
+    import json
+    import os
+    from pairec_b200 import DppParams
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "baseline", "go", "testdata", "dpp_*.json")))
+    assert len(files) >= 10
+    for path in files:
+        fx = json.load(open(path))
+        score = np.array(fx["score"], dtype=np.float64).reshape(1, -1)
+        n = score.shape[1]
+        use_table = len(fx["emb"]) > 0
+        hook = np.array(fx["hook"], dtype=np.float64).reshape(1, n, -1) if fx["hook"] else None
+        rows = None
+        if use_table:
+            engine.set_diversity_matrix(np.array(fx["emb"], dtype=np.float32))   # fixture embeddings are f32 values
+            rows = np.arange(n, dtype=np.uint32).reshape(1, -1)
+        p = DppParams(top_n=fx["top_n"], alpha=fx["alpha"], window_size=fx["window"], norm_mode=fx["norm_mode"],
+                      normalize_emb=1 if fx["normalize_emb"] else 0, no_positive_sim=0 if fx["ensure_positive_sim"] else 1)
+        idx, cnt, st = engine.dpp(rows, score, p, hook=hook, use_table=use_table)
+        assert st[0] == fx["expect_status"], fx["name"]
+        if fx["expect_status"] == 0:
+            assert idx[0, :cnt[0]].tolist() == fx["expect_idx"], fx["name"]
+
+
+def test_gpu_replays_the_go_ssd_fixtures(engine):
+    import glob
+    import json
+    import os
+    from pairec_b200 import SsdParams
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "baseline", "go", "testdata", "ssd_*.json")))
+    assert len(files) >= 3
+    for path in files:
+        fx = json.load(open(path))
+        emb = np.array(fx["emb"], dtype=np.float64)
+        engine.set_diversity_matrix(emb)
+        n = emb.shape[0]
+        p = SsdParams(gamma=fx["gamma"], top_n=fx["top_n"], window_size=fx["window"], norm_mode=fx["norm_mode"],
+                      normalize_emb=0, use_ssd_star=1 if fx["use_ssd_star"] else 0)
+        idx, cnt, st = engine.ssd(np.arange(n, dtype=np.uint32).reshape(1, -1), np.array(fx["score"]).reshape(1, -1), p)
+        assert idx[0, :cnt[0]].tolist() == fx["expect_idx"], fx["name"]
