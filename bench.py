@@ -5,19 +5,22 @@ One "step" = one pass of the hot path over one batch of synthetic requests.
 
   python bench.py --gpus 1 --steps K --warmup W            the CUDA path (libpairec_gpu.so through its C ABI)
   python bench.py --impl reference --gpus N ...            the reference's CPU path (oracle port) on the host cores
+  python bench.py --workload c2|c3|c4|c5|small             BASELINE.json configs[1..4] (default c4 = the metric's config)
 
-N=1 workload ("c4"): BASELINE.json configs[3] — 10 M items x 64-d f32 recall top-1000, 32 categorical tables
-(1 M rows x 16-d) gather + FM + MLP 512-512-256-128-1 (bf16 tensor cores) rank, score sort, DPP top-50 (window 10) on
-128-d diversity embeddings, batch 64 requests.  The recall stage alone is configs[1]; it is the dominant kernel and
-the one the roofline object describes.
-
-N>1 (torchrun, one rank per GPU): the item matrix is row-sharded (10 M / N rows per rank), every rank scans its shard
-for the global batch of 64*N queries, ONE all-gather (NCCL) exchanges the per-shard top-k keys, and each rank merges,
-ranks and re-ranks its own 64 requests with replicated feature/diversity tables: per-GPU work is constant -> "weak".
+Workloads (BASELINE.json `configs`):
+  c2  configs[1]: 10 M items x 64-d f32, vector recall top-1000 + ItemRankScore sort, batch 64        (recall + sort)
+  c3  configs[2]: 32 categorical tables (1 M rows x 16-d) gather + FM rank of 1000 candidates, batch 256 (gather + FM)
+  c4  configs[3]: recall -> 32 item tables + 8 user tables gather + FM + MLP (item 512 + user 128)-512-256-128-1 ->
+      score sort -> DPP top-50 (window 10) on 128-d diversity embeddings, batch 64     (the metric's config; default)
+  c5  configs[4]: 100 M items x 128-d row-sharded across the ranks, 128 requests per GPU (1024 at 8 GPUs), rest as c4
+N>1 (torchrun, one rank per GPU): the item matrix is row-sharded, every rank scans its shard for the global batch,
+the shards' candidates are exchanged over NCCL (global-threshold protocol) and each rank merges, ranks and
+re-ranks its own requests with replicated feature/diversity tables: per-GPU work is constant -> "weak".  After the
+timed region rank 0's results are compared, untimed, with the unsharded path (c4) and with the exact-local protocol.
 
 Timing: W >= 3 warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the library's
-stream, max over ranks.  The 2.56 GB item matrix is far larger than the 126 MB L2, so every step streams it from
-HBM (config.l2 = "inputs larger than L2").
+stream, max over ranks.  The item matrix (2.56 GB / its 1.28 GB bf16 index) is far larger than the 126 MB L2, so every
+step streams it from HBM; the timed loop rotates through 8 distinct request batches (queries, users, candidates).
 """
 import argparse
 import json
@@ -32,19 +35,34 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+N_ROT = 8   # distinct request batches the timed loop rotates through
+
 WORKLOADS = {
-    # name: (items, dim, k, batch, n_fields, table_rows, mlp dims, div_dim, top_n, window)
-    "c4": dict(items=10_000_000, dim=64, k=1000, batch=64, n_fields=32, table_rows=1_000_000,
-               mlp=[512, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
-    # BASELINE.json config 5 (not yet run: needs 8 GPUs): 100 M x 128-d row-sharded, 128 requests per GPU = 1024 at N = 8;
-    # ~90 GB per GPU while the tables are generated (replicated fields / diversity tables)
-    "c5": dict(items=100_000_000, dim=128, k=1000, batch=128, n_fields=32, table_rows=1_000_000,
-               mlp=[512, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
-    "small": dict(items=400_000, dim=64, k=1000, batch=64, n_fields=32, table_rows=50_000,
-                  mlp=[512, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
+    "c2": dict(kind="recall_sort", items=10_000_000, dim=64, k=1000, batch=64, n_fields=0, table_rows=0, user_fields=0,
+               mlp=None, div_dim=0, top_n=0, window=0),
+    "c3": dict(kind="fm", items=10_000_000, dim=64, k=1000, batch=256, n_fields=32, table_rows=1_000_000, user_fields=0,
+               mlp=None, div_dim=0, top_n=0, window=0),
+    "c4": dict(kind="full", items=10_000_000, dim=64, k=1000, batch=64, n_fields=32, table_rows=1_000_000, user_fields=8,
+               user_rows=100_000, mlp=[640, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
+    # BASELINE.json configs[4]: 100 M x 128-d row-sharded, 128 requests per GPU = 1024 at N = 8
+    "c5": dict(kind="full", items=100_000_000, dim=128, k=1000, batch=128, n_fields=32, table_rows=1_000_000, user_fields=8,
+               user_rows=100_000, mlp=[640, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
+    "small": dict(kind="full", items=400_000, dim=64, k=1000, batch=64, n_fields=32, table_rows=50_000, user_fields=8,
+                  user_rows=10_000, mlp=[640, 512, 256, 128, 1], div_dim=128, top_n=50, window=10),
 }
 METRIC = "requests/sec (10M-item recall->rank->DPP)"
 UNIT = "requests/s"
+
+
+def describe(name, w):
+    if w["kind"] == "recall_sort":
+        return (f"{name}: {w['items']} items x {w['dim']}-d f32 vector recall top-{w['k']} -> ItemRankScore sort")
+    if w["kind"] == "fm":
+        return (f"{name}: {w['n_fields']}-table ({w['table_rows']} rows x 16-d f32) gather + FM rank of {w['k']} candidates "
+                f"per request out of {w['items']} items")
+    return (f"{name}: {w['items']} items x {w['dim']}-d f32 recall top-{w['k']} -> {w['n_fields']} item + {w['user_fields']} "
+            f"user tables gather + FM + MLP {'-'.join(map(str, w['mlp']))} (bf16 input, bf16x2 hidden act, bf16 W) rank -> "
+            f"score sort -> DPP top-{w['top_n']} (window {w['window']}, {w['div_dim']}-d f32 table, fp64 arithmetic)")
 
 
 def peaks():
@@ -167,7 +185,8 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- synthetic tables
 def make_tables_torch(w, dev, rank, world):
-    """Synthetic tables generated ON the device with torch (plumbing).  Seeds follow SURVEY §8d."""
+    """Synthetic tables generated ON the device with torch (plumbing), in row chunks so that the 100 M-item workload
+    never holds more than one chunk of temporaries.  Seeds follow SURVEY §8d."""
     import torch
     g = torch.Generator(device=dev)
     items, dim = w["items"], w["dim"]
@@ -175,31 +194,41 @@ def make_tables_torch(w, dev, rank, world):
     row_base = rank * shard
     if rank == world - 1:
         shard = items - row_base
+    CH = 5_000_000
+    E = torch.empty(shard, dim, device=dev)
     g.manual_seed(2 + 1000 * rank)
-    E = torch.randn(shard, dim, device=dev, generator=g) / dim ** 0.5
-    g.manual_seed(5)
+    for c0 in range(0, shard, CH):
+        c1 = min(shard, c0 + CH)
+        E[c0:c1] = torch.randn(c1 - c0, dim, device=dev, generator=g) / dim ** 0.5
+    T = dict(E=E, row_base=row_base)
     F, R = w["n_fields"], w["table_rows"]
-    u = torch.rand(items, F, device=dev, generator=g)
-    fields = (u * u * u * R).to(torch.int32).clamp_(0, R - 1)  # skewed ids (hot head), replicated on every rank
-    del u
-    g.manual_seed(4)
-    factors = torch.randn(F, R, 16, device=dev, generator=g) * 0.4
-    linear = torch.randn(F, R, device=dev, generator=g) * 0.05
-    g.manual_seed(7)
-    D = torch.randn(items, w["div_dim"], device=dev, generator=g)
-    D /= D.norm(dim=1, keepdim=True)
-    return dict(E=E, row_base=row_base, fields=fields, factors=factors, linear=linear, D=D)
-
-
-def mlp_weights(dims, seed=6):
-    import oracle
-    rng = np.random.default_rng(seed)
-    W, b = [], []
-    for l in range(len(dims) - 1):
-        lim = np.sqrt(6.0 / (dims[l] + dims[l + 1]))
-        W.append(oracle.f32_to_bf16(rng.uniform(-lim, lim, size=(dims[l + 1], dims[l])).astype(np.float32)))
-        b.append((rng.standard_normal(dims[l + 1]) * 0.01).astype(np.float32))
-    return W, b
+    if F:
+        fields = torch.empty(items, F, dtype=torch.int32, device=dev)
+        g.manual_seed(5)
+        for c0 in range(0, items, CH):
+            c1 = min(items, c0 + CH)
+            u = torch.rand(c1 - c0, F, device=dev, generator=g)
+            fields[c0:c1] = (u * u * u * R).to(torch.int32).clamp_(0, R - 1)  # skewed ids (hot head), replicated on every rank
+            del u
+        g.manual_seed(4)
+        T["fields"] = fields
+        T["factors"] = torch.randn(F, R, 16, device=dev, generator=g) * 0.4
+        T["linear"] = torch.randn(F, R, device=dev, generator=g) * 0.05
+    U = w.get("user_fields", 0)
+    if U:
+        g.manual_seed(9)
+        T["ufactors"] = torch.randn(U, w["user_rows"], 16, device=dev, generator=g) * 0.4
+        T["ulinear"] = torch.randn(U, w["user_rows"], device=dev, generator=g) * 0.05
+    if w["div_dim"]:
+        D = torch.empty(items, w["div_dim"], device=dev)
+        g.manual_seed(7)
+        for c0 in range(0, items, CH):
+            c1 = min(items, c0 + CH)
+            d = torch.randn(c1 - c0, w["div_dim"], device=dev, generator=g)
+            D[c0:c1] = d / d.norm(dim=1, keepdim=True)
+            del d
+        T["D"] = D
+    return T
 
 
 def bf16_bits(a):
@@ -217,75 +246,136 @@ def mlp_weights_np(dims, seed=6):
     return W, b
 
 
+def load_engine(eng, w, T, mem):
+    eng.set_item_matrix(T["E"].data_ptr(), rows=T["E"].shape[0], dim=w["dim"], row_base=T["row_base"], mem=mem)
+    F, U = w["n_fields"], w.get("user_fields", 0)
+    if F:
+        eng.set_item_fields(T["fields"].data_ptr(), rows=w["items"], n_fields=F, mem=mem)
+        for t in range(F):
+            eng.set_feature_table(t, T["factors"][t].data_ptr(), T["linear"][t].data_ptr(), rows=w["table_rows"], fdim=16, mem=mem)
+        for u in range(U):
+            eng.set_feature_table(F + u, T["ufactors"][u].data_ptr(), T["ulinear"][u].data_ptr(), rows=w["user_rows"], fdim=16,
+                                  mem=mem)
+        eng.set_fm_bias(0.05)
+        if U:
+            eng.set_user_fields(U, 0)
+    if w["mlp"]:
+        W, b = mlp_weights_np(w["mlp"])
+        eng.set_mlp(w["mlp"], W, b)
+    if w["div_dim"]:
+        eng.set_diversity_matrix(T["D"].data_ptr(), rows=w["items"], dim=w["div_dim"], dtype=0, mem=mem)
+
+
 # ---------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_pipeline(w, T, Q, sample_rows, threads):
-    """The oracle port of the path on the host cores, over the first `sample_rows` catalog rows; returns seconds per
-    stage for one batch.  Recall time scales linearly with rows, the other stages do not depend on the catalog size."""
+def cpu_tables(w):
+    """Host tables for the CPU arm at the workload's FULL sizes (numpy, same distributions as the device tables)."""
+    rng = np.random.default_rng(2)
+    n, F, R, U = w["items"], w["n_fields"], w["table_rows"], w.get("user_fields", 0)
+    T = {}
+    if w["kind"] != "fm":
+        T["E"] = (rng.standard_normal((n, w["dim"]), dtype=np.float32) / np.float32(w["dim"] ** 0.5))
+    if F:
+        fields = np.empty((n, F), dtype=np.uint32)
+        for c0 in range(0, n, 2_000_000):
+            u = rng.random((min(n, c0 + 2_000_000) - c0, F), dtype=np.float32)
+            fields[c0:c0 + u.shape[0]] = np.minimum((u * u * u * R).astype(np.uint32), R - 1)
+        T["fields"] = fields
+        T["factors"] = [(rng.standard_normal((R, 16), dtype=np.float32) * np.float32(0.4)) for _ in range(F)]
+        T["linear"] = [(rng.standard_normal(R, dtype=np.float32) * np.float32(0.05)) for _ in range(F)]
+        for _ in range(U):
+            T["factors"].append(rng.standard_normal((w["user_rows"], 16), dtype=np.float32) * np.float32(0.4))
+            T["linear"].append(rng.standard_normal(w["user_rows"], dtype=np.float32) * np.float32(0.05))
+    if w["div_dim"]:
+        D = rng.standard_normal((n, w["div_dim"]), dtype=np.float32)
+        D /= np.linalg.norm(D, axis=1, keepdims=True)
+        T["D"] = D
+    if w["mlp"]:
+        T["W"], T["b"] = mlp_weights_np(w["mlp"])
+    return T
+
+
+def cpu_step(w, T, Q, rows_in, uids, threads):
+    """The oracle port of the workload's path on the host cores for the requests given; seconds per stage."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
-    B, k = Q.shape[0], w["k"]
-    E = T["E"][:sample_rows]
+    k = w["k"]
+    st = {}
+    if w["kind"] != "fm":
+        B = Q.shape[0]
+        t0 = time.perf_counter()
+        keys = oracle.recall_topk(T["E"], Q, k, n_threads=threads)
+        st["recall"] = time.perf_counter() - t0
+        rows, scores, _ = oracle.keys_split(keys)
+    else:
+        rows, B = rows_in, rows_in.shape[0]
+    if w["kind"] == "recall_sort":
+        t0 = time.perf_counter()
+        for b in range(B):
+            oracle.go_sort(scores[b].astype(np.float64))   # Item.Score = float64(score) (vector_recall.go:99), ItemRankScore
+        st["sort"] = time.perf_counter() - t0
+        return st
+    U = w.get("user_fields", 0)
     t0 = time.perf_counter()
-    keys = oracle.recall_topk(E, Q, k, n_threads=threads)
-    t_recall = time.perf_counter() - t0
-    rows, _, _ = oracle.keys_split(keys)
+    fm, xs = [], []
+    for b in range(B):   # per request: its user's features are merged into every candidate's feature map
+        f, x = oracle.gather_fm(T["fields"], T["factors"], T["linear"], 0.05, rows[b], want_x=w["mlp"] is not None,
+                                user_ids=uids[b] if U else None)
+        fm.append(f)
+        xs.append(x)
+    st["gather_fm"] = time.perf_counter() - t0
+    if w["kind"] == "fm":
+        oracle.sigmoid(np.concatenate(fm))
+        return st
     t0 = time.perf_counter()
-    fm, x = oracle.gather_fm(T["fields"], T["factors"], T["linear"], 0.05, rows.reshape(-1), want_x=True)
-    t_gather = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    ml = oracle.mlp_forward(x, w["mlp"], T["W"], T["b"])
-    sc = oracle.sigmoid((fm + ml).astype(np.float32)).astype(np.float64).reshape(B, k)
-    t_mlp = time.perf_counter() - t0
+    ml = oracle.mlp_forward(np.concatenate(xs), w["mlp"], T["W"], T["b"])
+    sc = oracle.sigmoid((np.concatenate(fm) + ml).astype(np.float32)).astype(np.float64).reshape(B, k)
+    st["mlp"] = time.perf_counter() - t0
 
     def one(b):
         perm = oracle.stable_sort_desc(sc[b])
         r = rows[b][perm]
-        idx, st = oracle.dpp_request(T["D"][r].astype(np.float64), sc[b][perm], w["top_n"], alpha=1.0,
-                                     window_size=w["window"])
+        idx, _ = oracle.dpp_request(T["D"][r].astype(np.float64), sc[b][perm], w["top_n"], alpha=1.0, window_size=w["window"])
         return r[idx]
     t0 = time.perf_counter()
     with ThreadPoolExecutor(max_workers=max(1, min(threads, B))) as ex:
-        out = list(ex.map(one, range(B)))
-    t_dpp = time.perf_counter() - t0
-    return dict(recall=t_recall, gather_fm=t_gather, mlp=t_mlp, sort_dpp=t_dpp), out
+        list(ex.map(one, range(B)))
+    st["sort_dpp"] = time.perf_counter() - t0
+    return st
 
 
-def cpu_tables(w, sample_rows):
-    """Host tables for the CPU arm (numpy, same distributions as the device tables; the CPU arm is a timing arm)."""
-    rng = np.random.default_rng(2)
-    F, R = w["n_fields"], min(w["table_rows"], 200_000)
-    E = (rng.standard_normal((sample_rows, w["dim"]), dtype=np.float32) / np.float32(w["dim"] ** 0.5))
-    u = rng.random((sample_rows, F), dtype=np.float32)
-    fields = np.minimum((u * u * u * R).astype(np.uint32), R - 1)
-    factors = [(rng.standard_normal((R, 16), dtype=np.float32) * np.float32(0.4)) for _ in range(F)]
-    linear = [(rng.standard_normal(R, dtype=np.float32) * np.float32(0.05)) for _ in range(F)]
-    D = rng.standard_normal((sample_rows, w["div_dim"]), dtype=np.float32)
-    D /= np.linalg.norm(D, axis=1, keepdims=True)
-    W, b = mlp_weights_np(w["mlp"])
-    return dict(E=E, fields=fields, factors=factors, linear=linear, D=D, W=W, b=b)
-
-
-def cpu_measure(w, steps, warmup, sample_rows):
+def cpu_measure(w, steps, warmup, reqs_per_step):
+    """`steps` timed steps of `reqs_per_step` requests each (a bounded sample of the workload's batch) at FULL table
+    sizes, distinct requests every step."""
     import oracle
     oracle.build()
     threads = oracle.num_threads()
-    T = cpu_tables(w, sample_rows)
+    scale = 1.0
+    if w["items"] > 20_000_000:   # c5: 115 GB of host tables do not fit every box: recall over 10 M rows, time scaled
+        scale = w["items"] / 10_000_000
+        w = dict(w, items=10_000_000)
+    T = cpu_tables(w)
     rng = np.random.default_rng(3)
-    Q = (rng.standard_normal((w["batch"], w["dim"]), dtype=np.float32) / np.float32(w["dim"] ** 0.5))
+    U = w.get("user_fields", 0)
     per = []
     for i in range(warmup + steps):
-        st, _ = cpu_pipeline(w, T, Q, sample_rows, threads)
+        Q = (rng.standard_normal((reqs_per_step, w["dim"]), dtype=np.float32) / np.float32(w["dim"] ** 0.5))
+        rows_in = rng.integers(0, w["items"], size=(reqs_per_step, w["k"])).astype(np.uint32) if w["kind"] == "fm" else None
+        uids = rng.integers(0, w["user_rows"], size=(reqs_per_step, U)).astype(np.uint32) if U else None
+        t0 = time.perf_counter()
+        st = cpu_step(w, T, Q, rows_in, uids, threads)
+        st["total"] = time.perf_counter() - t0
+        if scale != 1.0:
+            st["total"] += st["recall"] * (scale - 1.0)
+            st["recall_scaled_to_full_catalog"] = st["recall"] * scale
         if i >= warmup:
             per.append(st)
-    scale = w["items"] / sample_rows
-    tot = [p["recall"] * scale + p["gather_fm"] + p["mlp"] + p["sort_dpp"] for p in per]
-    med = float(np.median(tot))
+    tot = [p["total"] for p in per]
+    mean = float(np.mean(tot))
     stages = {k: float(np.median([p[k] for p in per])) for k in per[0]}
-    stages["recall_scaled_to_full_catalog"] = stages["recall"] * scale
-    return dict(value=w["batch"] / med, ms_per_step=med * 1e3, cores=threads, stages_s=stages,
-                sample=f"batch {w['batch']} requests; recall over the first {sample_rows} of {w['items']} rows "
-                       f"(time scaled x{scale:.1f}), gather+FM / MLP / sort+DPP at full size on tables of "
-                       f"{min(w['table_rows'], 200_000)} rows; oracle port (C, AVX2 FMA), all host threads")
+    return dict(value=reqs_per_step / mean, ms_per_step=mean * 1e3, cores=threads, stages_s=stages,
+                sample=f"{steps} steps of {reqs_per_step} requests (of the workload's batch of {w['batch']}) at full table "
+                       f"sizes ({w['items']} items); oracle port (C, AVX2 FMA, pthreads) on all {threads} host threads; "
+                       f"distinct requests per step" + (f"; catalog capped at 10 M rows, recall time scaled x{scale:.0f}" if scale != 1.0 else ""))
 
 
 # ---------------------------------------------------------------------------------------------- main
@@ -296,34 +386,39 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PRG_WORKLOAD", "c4"), choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--cpu-requests", type=int, default=8, help="requests per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batcher", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the untimed N>1 parity checks")
+    ap.add_argument("--items", type=int, default=0, help="override the catalog size (e.g. c5's per-GPU shard shape on fewer GPUs)")
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.items:
+        w["items"] = args.items
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(args.warmup, 3)
-    config = {"workload": f"{args.workload}: {w['items']} items x {w['dim']}-d f32 recall top-{w['k']} -> "
-                          f"{w['n_fields']}-table gather + FM + MLP {'-'.join(map(str, w['mlp']))} (bf16x2 act, bf16 W) "
-                          f"rank -> score sort -> DPP top-{w['top_n']} (window {w['window']}, {w['div_dim']}-d f32 table, "
-                          f"fp64 arithmetic)",
+    kind = w["kind"]
+    if world > 1 and kind != "full":
+        raise SystemExit("c2 / c3 are single-GPU workloads (parity-test configs)")
+    config = {"workload": describe(args.workload, w),
               "batch_per_gpu": w["batch"], "global_batch": w["batch"] * world,
               "sharding": ("item matrix row-sharded; " + ("all-gather of per-shard top-k keys"
                            if os.environ.get("PRG_SHARD_PROTOCOL", "global") == "local" else
                            "global threshold: all-gather of per-shard sample keys, then all-gather of the candidates "
                            "that reach it") if world > 1 else "none"),
-              "l2": f"inputs larger than L2 (item matrix / its {w['items'] // world * w['dim'] * 2 / 1e9:.2f} GB bf16 filter "
-                    f"index streamed per step)"}
+              "l2": (f"inputs larger than L2 (item matrix / its {w['items'] // world * w['dim'] * 2 / 1e9:.2f} GB bf16 filter "
+                     f"index streamed per step)" if kind != "fm" else
+                     "inputs larger than L2 (2.2 GB of feature tables + 1.28 GB of item fields, random rows)"),
+              "request_batches_rotated": N_ROT}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        sample_rows = min(args.cpu_sample_rows, w["items"])
-        r = cpu_measure(w, max(1, min(args.steps, 3)), 1, sample_rows)
+        r = cpu_measure(w, max(1, args.steps), max(0, args.warmup), args.cpu_requests)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": r["ms_per_step"],
+                "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 recall/FM, f64 MLP-acc/DPP",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
@@ -332,69 +427,99 @@ def main():
         print(json.dumps(line))
         return
 
+    import ctypes as C
     import torch
     import torch.distributed as dist
     from pairec_b200 import DppParams, Engine
-    from pairec_b200.binding import MEM_DEVICE, MODEL_FM_MLP
+    from pairec_b200.binding import MEM_DEVICE, MODEL_FM, MODEL_FM_MLP, UserFeatures
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine(local_rank)
     T = make_tables_torch(w, dev, rank, world)
-    eng.set_item_matrix(T["E"].data_ptr(), rows=T["E"].shape[0], dim=w["dim"], row_base=T["row_base"], mem=MEM_DEVICE)
-    eng.set_item_fields(T["fields"].data_ptr(), rows=w["items"], n_fields=w["n_fields"], mem=MEM_DEVICE)
-    for t in range(w["n_fields"]):
-        eng.set_feature_table(t, T["factors"][t].data_ptr(), T["linear"][t].data_ptr(), rows=w["table_rows"], fdim=16,
-                              mem=MEM_DEVICE)
-    eng.set_fm_bias(0.05)
-    W, b = mlp_weights_np(w["mlp"])
-    eng.set_mlp(w["mlp"], W, b)
-    eng.set_diversity_matrix(T["D"].data_ptr(), rows=w["items"], dim=w["div_dim"], dtype=0, mem=MEM_DEVICE)
-    p = DppParams(top_n=w["top_n"], alpha=1.0, window_size=w["window"])
+    load_engine(eng, w, T, MEM_DEVICE)
+    p = DppParams(top_n=max(1, w["top_n"]), alpha=1.0, window_size=max(1, w["window"]))
 
-    B, k, Tn = w["batch"], w["k"], w["top_n"]
+    B, k, Tn, U = w["batch"], w["k"], w["top_n"], w.get("user_fields", 0)
     Bg = B * world
     gq = torch.Generator(device=dev)
     gq.manual_seed(3)
-    Qg = torch.randn(Bg, w["dim"], device=dev, generator=gq) / w["dim"] ** 0.5   # same global batch on every rank
-    out_rows = torch.empty(B, Tn, dtype=torch.int32, device=dev)
-    out_scores = torch.empty(B, Tn, dtype=torch.float64, device=dev)
-    out_n = torch.empty(B, dtype=torch.int32, device=dev)
+    # N_ROT distinct global request batches (the same on every rank): queries, user ids
+    Qs = [torch.randn(Bg, w["dim"], device=dev, generator=gq) / w["dim"] ** 0.5 for _ in range(N_ROT)]
+    Us = [torch.randint(0, w["user_rows"], (Bg, U), device=dev, generator=gq, dtype=torch.int32) for _ in range(N_ROT)] if U else None
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
-    protocol = os.environ.get("PRG_SHARD_PROTOCOL", "global")   # "global": one threshold per query across shards
-    if world > 1 and protocol == "local":
-        keys_local = torch.empty(Bg, k, dtype=torch.int64, device=dev)
-        keys_all = torch.empty(world, Bg, k, dtype=torch.int64, device=dev)
-    elif world > 1:
-        r_s = eng.shard_sample_len(k)
-        samp_local = torch.empty(Bg, r_s, dtype=torch.int64, device=dev)
-        samp_all = torch.empty(world, Bg, r_s, dtype=torch.int64, device=dev)
-        blk = Bg * k + Bg                                        # per rank: Bg x k keys + Bg status words
-        cand_local = torch.empty(blk, dtype=torch.int64, device=dev)
-        cand_all = torch.empty(world, blk, dtype=torch.int64, device=dev)
-        retry = torch.zeros(2, dtype=torch.int32, device=dev)
+    lib, h = eng._lib, eng._h
 
-    def step_device():
-        if world == 1:
-            eng.recommend_dev(Qg.data_ptr(), B, k, MODEL_FM_MLP, p, out_rows.data_ptr(), out_scores.data_ptr(),
-                              out_n.data_ptr())
-        elif protocol == "local":
+    def uptr(i, local=True):   # this rank's requests' user ids of batch i
+        if not U:
+            return None
+        return Us[i].data_ptr() + (rank * B * U * 4 if local else 0)
+
+    launches_extra = 0
+    if kind == "recall_sort":
+        r_rows = torch.empty(B, k, dtype=torch.int32, device=dev)
+        r_sc = torch.empty(B, k, dtype=torch.float32, device=dev)
+        r_n = torch.empty(B, dtype=torch.int32, device=dev)
+        r_perm = torch.empty(B, k, dtype=torch.int32, device=dev)
+        out_rows = r_rows
+
+        def step_device(i):
+            eng.recall_topk_dev(Qs[i % N_ROT].data_ptr(), B, k, r_rows.data_ptr(), r_sc.data_ptr(), r_n.data_ptr())
+            with torch.cuda.stream(stream):
+                sc64 = r_sc.to(torch.float64)   # Item.Score = float64(score), vector_recall.go:99 (a torch cast: plumbing)
+            eng.sort_desc_dev(sc64.data_ptr(), B, k, r_perm.data_ptr())
+    elif kind == "fm":
+        # candidates: N_ROT sets of B x k item rows (what C2's recall hands over), drawn once, untimed
+        cand = [torch.randint(0, w["items"], (B, k), device=dev, generator=gq, dtype=torch.int32) for _ in range(N_ROT)]
+        fm_out = torch.empty(B, k, dtype=torch.float64, device=dev)
+        out_rows = fm_out
+
+        def step_device(i):
+            eng.rank_dev(MODEL_FM, cand[i % N_ROT].data_ptr(), B, k, fm_out.data_ptr())
+    else:
+        out_rows = torch.empty(B, Tn, dtype=torch.int32, device=dev)
+        out_scores = torch.empty(B, Tn, dtype=torch.float64, device=dev)
+        out_n = torch.empty(B, dtype=torch.int32, device=dev)
+        protocol = os.environ.get("PRG_SHARD_PROTOCOL", "global")   # "global": one threshold per query across shards
+        if world > 1 and protocol == "local":
+            keys_local = torch.empty(Bg, k, dtype=torch.int64, device=dev)
+            keys_all = torch.empty(world, Bg, k, dtype=torch.int64, device=dev)
+        elif world > 1:
+            r_s = eng.shard_sample_len(k)
+            samp_local = torch.empty(Bg, r_s, dtype=torch.int64, device=dev)
+            samp_all = torch.empty(world, Bg, r_s, dtype=torch.int64, device=dev)
+            blk = Bg * k + Bg                                        # per rank: Bg x k keys + Bg status words
+            cand_local = torch.empty(blk, dtype=torch.int64, device=dev)
+            cand_all = torch.empty(world, blk, dtype=torch.int64, device=dev)
+            retry = torch.zeros(2, dtype=torch.int32, device=dev)
+
+        def step_local_protocol(i, rows_t, scores_t, n_t):
+            Qg = Qs[i % N_ROT]
             eng.recall_local_keys_dev(Qg.data_ptr(), Bg, k, keys_local.data_ptr())
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(keys_all, keys_local)
             eng.recommend_from_keys_dev(keys_all.data_ptr() + rank * B * k * 8, world, Bg * k, B, k, MODEL_FM_MLP, p,
-                                        out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr())
-        else:
-            eng.shard_sample_dev(Qg.data_ptr(), Bg, k, world, samp_local.data_ptr())
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(samp_all, samp_local)          # exchange 1: G x Bg x r sample keys
-            eng.shard_candidates_dev(Qg.data_ptr(), Bg, k, world, samp_all.data_ptr(), cand_local.data_ptr())
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(cand_all, cand_local)          # exchange 2: candidates that reach tau
-            eng.shard_check_dev(cand_all.data_ptr(), world, Bg, k, retry.data_ptr())
-            eng.recommend_from_keys_dev(cand_all.data_ptr() + rank * B * k * 8, world, blk, B, k, MODEL_FM_MLP, p,
-                                        out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr())
+                                        rows_t.data_ptr(), scores_t.data_ptr(), n_t.data_ptr(), user_ids_ptr=uptr(i % N_ROT))
+
+        def step_device(i):
+            Qg = Qs[i % N_ROT]
+            if world == 1:
+                eng.recommend_dev(Qg.data_ptr(), B, k, MODEL_FM_MLP, p, out_rows.data_ptr(), out_scores.data_ptr(),
+                                  out_n.data_ptr(), user_ids_ptr=uptr(i % N_ROT))
+            elif protocol == "local":
+                step_local_protocol(i, out_rows, out_scores, out_n)
+            else:
+                eng.shard_sample_dev(Qg.data_ptr(), Bg, k, world, samp_local.data_ptr())
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(samp_all, samp_local)          # exchange 1: G x Bg x r sample keys
+                eng.shard_candidates_dev(Qg.data_ptr(), Bg, k, world, samp_all.data_ptr(), cand_local.data_ptr())
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(cand_all, cand_local)          # exchange 2: candidates that reach tau
+                eng.shard_check_dev(cand_all.data_ptr(), world, Bg, k, retry.data_ptr())
+                eng.recommend_from_keys_dev(cand_all.data_ptr() + rank * B * k * 8, world, blk, B, k, MODEL_FM_MLP, p,
+                                            out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr(),
+                                            user_ids_ptr=uptr(i % N_ROT))
 
     def sync_all():
         eng.sync()
@@ -406,11 +531,12 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()   # the poller process needs a moment to come up: start it before the warm-up
-    for _ in range(warmup):
-        step_device()
+    for i in range(max(warmup, N_ROT)):   # every rotated batch is touched once before timing
+        step_device(i)
     sync_all()
-    eng.timing(2)             # CUDA-event spans around the recall scan only while the step is timed
-    eng.timing(2, read=True)  # reset accumulators
+    roof_stage = "gather_fm" if kind == "fm" else "scan"
+    eng.timing(1 if kind == "fm" else 2)   # CUDA-event spans around the roofline kernel only while the step is timed
+    eng.timing(1 if kind == "fm" else 2, read=True)  # reset accumulators
     launches0 = eng.launches
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     sync_all()
@@ -419,16 +545,16 @@ def main():
     with torch.cuda.stream(stream):
         ev[0].record(stream)
         for i in range(args.steps):
-            step_device()
+            step_device(i)
             ev[i + 1].record(stream)
     sync_all()
     if rank == 0:
         sampler.end()
     clocks = sampler.stop() if rank == 0 else None
-    stage = eng.timing(1, read=True)   # scan spans of the timed region; now switch to all stages
+    stage = eng.timing(1, read=True)   # spans of the timed region; now switch to all stages
     launches = eng.launches - launches0
-    for _ in range(20):                # untimed: per-stage breakdown (the extra events perturb the step slightly)
-        step_device()
+    for i in range(20):                # untimed: per-stage breakdown (the extra events perturb the step slightly)
+        step_device(i)
     sync_all()
     stage_all = eng.timing(0, read=True)
     total_ms = ev[0].elapsed_time(ev[-1])
@@ -439,48 +565,75 @@ def main():
     total_ms = float(tt.item())
     value = Bg * args.steps / (total_ms * 1e-3)
 
-    # ---- e2e: the same step with HOST buffers: pinned host queries in, results out, copies inside the timed region
-    e2e = None
-    rows_h = torch.empty(B, Tn, dtype=torch.int32).pin_memory()
-    sc_h = torch.empty(B, Tn, dtype=torch.float64).pin_memory()
-    n_h = torch.empty(B, dtype=torch.int32).pin_memory()
-    if world == 1:
-        q_host = torch.empty(B, w["dim"], dtype=torch.float32).pin_memory()
-        q_host.copy_(Qg.cpu())
-        import ctypes as C
-        lib, h = eng._lib, eng._h
+    # ---- e2e: the same step through the C ABI with HOST buffers: pinned host inputs, results out, copies inside
+    def pinned(t):
+        return t.cpu().pin_memory()
+    q_host = [pinned(Qs[i] if world > 1 else Qs[i][:B]) for i in range(N_ROT)]
+    u_host = [pinned(Us[i]) for i in range(N_ROT)] if U else None
+    if kind == "recall_sort":
+        rows_h = torch.empty(B, k, dtype=torch.int32).pin_memory()
+        sc_h = torch.empty(B, k, dtype=torch.float32).pin_memory()
+        n_h = torch.empty(B, dtype=torch.int32).pin_memory()
+        sc64_h = torch.empty(B, k, dtype=torch.float64).pin_memory()
+        perm_h = torch.empty(B, k, dtype=torch.int32).pin_memory()
 
-        def step_host():   # prg_recommend(PRG_MEM_HOST): H2D, all stages, D2H inside the C ABI call
-            rc = lib.prg_recommend(h, C.c_void_p(q_host.data_ptr()), B, k, MODEL_FM_MLP, C.byref(p),
-                                   C.c_void_p(rows_h.data_ptr()), C.c_void_p(sc_h.data_ptr()),
-                                   C.c_void_p(n_h.data_ptr()), 0)
+        def step_host(i):   # prg_recall_topk + prg_sort_desc, PRG_MEM_HOST
+            rc = lib.prg_recall_topk(h, C.c_void_p(q_host[i % N_ROT].data_ptr()), B, k, C.c_void_p(rows_h.data_ptr()),
+                                     C.c_void_p(sc_h.data_ptr()), C.c_void_p(n_h.data_ptr()), 0)
             assert rc == 0, lib.prg_last_error()
-        h2d = B * w["dim"] * 4
-        note = "prg_recommend with host buffers: H2D of the queries, all stages, D2H of rows/scores/counts, per step"
-    else:
-        q_host = torch.empty(Bg, w["dim"], dtype=torch.float32).pin_memory()
-        q_host.copy_(Qg.cpu())
+            sc64_h.copy_(sc_h)          # Item.Score = float64(score): what the Go glue does per item
+            rc = lib.prg_sort_desc(h, C.c_void_p(sc64_h.data_ptr()), B, k, C.c_void_p(perm_h.data_ptr()), 0)
+            assert rc == 0, lib.prg_last_error()
+        h2d, d2h = B * w["dim"] * 4 + B * k * 8, B * k * 8 + B * 4 + B * k * 4
+        note = "prg_recall_topk + prg_sort_desc with host buffers: H2D queries / scores, D2H rows, scores, counts, permutation"
+    elif kind == "fm":
+        cand_h = [pinned(c) for c in cand]
+        fm_h = torch.empty(B, k, dtype=torch.float64).pin_memory()
 
-        def step_host():   # sharded path: every rank receives the global query batch from its host, returns its 64 results
-            with torch.cuda.stream(stream):
-                Qg.copy_(q_host, non_blocking=True)
-            step_device()
-            with torch.cuda.stream(stream):
-                rows_h.copy_(out_rows, non_blocking=True)
-                sc_h.copy_(out_scores, non_blocking=True)
-                n_h.copy_(out_n, non_blocking=True)
-            eng.sync()
-        h2d = Bg * w["dim"] * 4
-        note = ("pinned host queries -> device, sharded recall + all-gather + rank/sort/DPP, results -> pinned host, "
-                "per step and per rank")
-    for _ in range(3):
-        step_host()
+        def step_host(i):   # prg_rank(PRG_MEM_HOST)
+            rc = lib.prg_rank(h, MODEL_FM, C.c_void_p(cand_h[i % N_ROT].data_ptr()), B, k, C.c_void_p(fm_h.data_ptr()), 0)
+            assert rc == 0, lib.prg_last_error()
+        h2d, d2h = B * k * 4, B * k * 8
+        note = "prg_rank(PRG_MODEL_FM) with host buffers: H2D candidate rows, gather + FM, D2H f64 scores, per step"
+    else:
+        rows_h = torch.empty(B, Tn, dtype=torch.int32).pin_memory()
+        sc_h = torch.empty(B, Tn, dtype=torch.float64).pin_memory()
+        n_h = torch.empty(B, dtype=torch.int32).pin_memory()
+        if world == 1:
+            def step_host(i):   # prg_recommend_ex(PRG_MEM_HOST): H2D, all stages, D2H inside the C ABI call
+                uf = UserFeatures(u_host[i % N_ROT].data_ptr(), None) if U else None
+                rc = lib.prg_recommend_ex(h, C.c_void_p(q_host[i % N_ROT].data_ptr()), B, k, MODEL_FM_MLP, C.byref(p),
+                                          C.byref(uf) if U else None, C.c_void_p(rows_h.data_ptr()),
+                                          C.c_void_p(sc_h.data_ptr()), C.c_void_p(n_h.data_ptr()), 0)
+                assert rc == 0, lib.prg_last_error()
+            h2d = B * w["dim"] * 4 + B * U * 4
+            note = ("prg_recommend_ex with host buffers: H2D of the queries and user ids, all stages, D2H of "
+                    "rows/scores/counts, per step")
+        else:
+            def step_host(i):   # sharded path: every rank receives the global request batch from its host, returns its results
+                j = i % N_ROT
+                with torch.cuda.stream(stream):
+                    Qs[j].copy_(q_host[j], non_blocking=True)
+                    if U:
+                        Us[j].copy_(u_host[j], non_blocking=True)
+                step_device(i)
+                with torch.cuda.stream(stream):
+                    rows_h.copy_(out_rows, non_blocking=True)
+                    sc_h.copy_(out_scores, non_blocking=True)
+                    n_h.copy_(out_n, non_blocking=True)
+                eng.sync()
+            h2d = Bg * w["dim"] * 4 + Bg * U * 4
+            note = ("pinned host queries + user ids -> device, sharded recall + exchanges + rank/sort/DPP, results -> pinned "
+                    "host, per step and per rank")
+        d2h = B * Tn * 12 + B * 4
+    for i in range(3):
+        step_host(i)
     sync_all()
     lat = []
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         t1 = time.perf_counter()
-        step_host()
+        step_host(i)
         lat.append((time.perf_counter() - t1) * 1e3)
     sync_all()
     e2e_s = time.perf_counter() - t0
@@ -488,25 +641,28 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    e2e = {"value": Bg * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": B * Tn * 12 + B * 4, "p50_ms": float(np.percentile(lat, 50)),
-           "p99_ms": float(np.percentile(lat, 99)), "note": note}
+    e2e = {"value": Bg * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "note": note}
 
     # ---- the same path entered ONE REQUEST PER HOST THREAD (what the reference's request goroutines do) through the
     #      cross-call batcher: closed loop of 3*B native client threads, each a blocking prg_batcher_recommend call
     batcher = None
-    if world == 1 and not args.no_batcher:
+    if world == 1 and kind == "full" and not args.no_batcher:
         from pairec_b200.binding import Batcher
+        if U:
+            eng.set_user_fields(0, 0)          # the native load generator drives query-only requests
+            W0, b0 = mlp_weights_np([w["n_fields"] * 16] + w["mlp"][1:])
+            eng.set_mlp([w["n_fields"] * 16] + w["mlp"][1:], W0, b0)
         bat = Batcher(eng, k, MODEL_FM_MLP, p, max_batch=B, max_wait_us=0)
-        q_pool = q_host.numpy().copy()
+        q_pool = q_host[0].numpy().copy()
         n_thr = 3 * B
         per = max(4, (args.steps * B) // n_thr)
         bat.drive(q_pool, n_thr, 2)                      # warm-up
         st0 = bat.stats()
         lat_us, wall, rows_b, n_b = bat.drive(q_pool, n_thr, per)
         st1 = bat.stats()
-        step_host()                                       # the direct batch call on the same queries, for the check
-        same = bool((rows_b.view(np.int32)[:, :] == rows_h.numpy()).all() and (n_b == n_h.numpy()).all())
+        rows_d, _, n_d = eng.recommend(q_pool, k, MODEL_FM_MLP, p)   # the direct batch call on the same queries
+        same = bool((rows_b == rows_d).all() and (n_b == n_d).all())
         lat1, _, _, _ = bat.drive(q_pool, 1, 50)          # one caller at a time: unloaded single-request latency
         bat.close()
         nb = st1["batches"] - st0["batches"]
@@ -519,65 +675,131 @@ def main():
                    "pipelined": os.environ.get("PRG_BATCHER_PIPELINE", "1") != "0",
                    "note": "prg_batcher_recommend: one request per host thread, coalesced into batches of the fused path "
                            "(host buffers, copies inside; a full batch is enqueued behind the running one when "
-                           "pipelined); latency = per request, queueing included"}
+                           "pipelined); item-side features only (the load generator sends no user block); latency = "
+                           "per request, queueing included"}
 
+    # ---- N>1, untimed: what the sharded NCCL path produced against (a) the exact-local protocol on the same ranks and
+    #      (b) the unsharded path over the gathered matrix (c4: it fits beside the shard)
     shard_retries = None
-    if world > 1 and protocol == "global":
-        eng.sync()
-        shard_retries = int(retry.cpu()[1].item())   # queries that asked for the exact protocol (expected: 0)
+    verify = None
+    if world > 1 and kind == "full":
+        if protocol == "global":
+            eng.sync()
+            shard_retries = int(retry.cpu()[1].item())   # queries that asked for the exact protocol (expected: 0)
+        if not args.no_verify:
+            step_device(0)
+            eng.sync()
+            got = (out_rows.clone(), out_scores.clone(), out_n.clone())
+            verify = {}
+            if protocol == "global":
+                keys_local = torch.empty(Bg, k, dtype=torch.int64, device=dev)
+                keys_all = torch.empty(world, Bg, k, dtype=torch.int64, device=dev)
+                a_rows, a_sc, a_n = torch.empty_like(got[0]), torch.empty_like(got[1]), torch.empty_like(got[2])
+                step_local_protocol(0, a_rows, a_sc, a_n)
+                eng.sync()
+                ok = bool(torch.equal(a_rows, got[0]) and torch.equal(a_sc, got[1]) and torch.equal(a_n, got[2]))
+                verify["equals_exact_local_protocol"] = ok
+            full_bytes = w["items"] * w["dim"] * 4
+            if full_bytes <= 8e9:
+                shard_rows = w["items"] // world
+                parts = [torch.empty(shard_rows, w["dim"], device=dev) for _ in range(world)]
+                if w["items"] % world == 0:
+                    dist.all_gather(parts, T["E"])
+                    if rank == 0:
+                        full = torch.cat(parts)
+                        del parts
+                        eng1 = Engine(local_rank)
+                        T1 = dict(T)
+                        T1["E"], T1["row_base"] = full, 0
+                        load_engine(eng1, w, T1, MEM_DEVICE)
+                        b_rows, b_sc, b_n = torch.empty_like(got[0]), torch.empty_like(got[1]), torch.empty_like(got[2])
+                        eng1.recommend_dev(Qs[0].data_ptr(), B, k, MODEL_FM_MLP, p, b_rows.data_ptr(), b_sc.data_ptr(),
+                                           b_n.data_ptr(), user_ids_ptr=uptr(0))
+                        eng1.sync()
+                        verify["rank0_equals_unsharded_path"] = bool(torch.equal(b_rows, got[0]) and
+                                                                     torch.equal(b_sc, got[1]) and torch.equal(b_n, got[2]))
+                        eng1.close()
+            vt = torch.tensor([1 if all(verify.values()) else 0], device=dev)
+            dist.all_reduce(vt, op=dist.ReduceOp.MIN)
+            verify["all_ranks_ok"] = bool(vt.item())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     pk, pk_kind = peaks()
-    scan = stage["scan"]
-    scan_ms = scan["ms"] / max(1, scan["spans"])
-    rows_local = T["E"].shape[0]
-    # the full-matrix pass: tensor-core filter over the bf16 shadow index (default), the fp32 rows (scan_tf32) or the
-    # exact FFMA2 scan (scan_ffma2); algorithmic bytes per launch = the operand the pass must stream + the row norms
+    rs = stage[roof_stage]
+    roof_ms = rs["ms"] / max(1, rs["spans"])
     cfg_env = json.loads(os.environ.get("PRG_CFG", "{}"))
-    filt = "ffma2" if cfg_env.get("scan_ffma2") else ("tf32" if cfg_env.get("scan_tf32") else "bf16")
-    q_pass = min(Bg, 256 if filt != "ffma2" else 64)
-    elem = 2 if filt == "bf16" else 4
-    alg_bytes = rows_local * w["dim"] * elem + (rows_local * 4 if filt != "ffma2" else 0) + q_pass * w["dim"] * 4
-    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-    kernel = {"bf16": f"recall_scan_tc_kernel<{w['dim']},NQB,bf16 shadow index>",
-              "tf32": f"recall_scan_tc_kernel<{w['dim']},NQB,tf32 on fp32 rows>",
-              "ffma2": f"recall_scan_kernel<{w['dim']},THRESH>"}[filt]
+    if kind == "fm":
+        M = B * k
+        F = w["n_fields"]
+        alg_bytes = M * (F * 4 + F * 64 + F * 4 + 8)      # ids + 64-B factor rows + linear weights + f64 score
+        kernel = "gather_fm_kernel<8,4>"
+        note = ("algorithmic bytes per candidate = F*4 (field ids) + F*64 (factor rows) + F*4 (linear weights) + 8 (score); "
+                "SURVEY §8(d) C3")
+        extra = {}
+    else:
+        rows_local = T["E"].shape[0]
+        filt = "ffma2" if cfg_env.get("scan_ffma2") else ("tf32" if cfg_env.get("scan_tf32") else "bf16")
+        q_pass = min(Bg, 256 if filt != "ffma2" else 64)
+        elem = 2 if filt == "bf16" else 4
+        alg_bytes = rows_local * w["dim"] * elem + (rows_local * 4 if filt != "ffma2" else 0) + q_pass * w["dim"] * 4
+        kernel = {"bf16": f"recall_scan_tc_kernel<{w['dim']},NQB,bf16 shadow index>",
+                  "tf32": f"recall_scan_tc_kernel<{w['dim']},NQB,tf32 on fp32 rows>",
+                  "ffma2": f"recall_scan_kernel<{w['dim']},THRESH>"}[filt]
+        note = ("algorithmic bytes = what one pass must stream: rows*dim*2 (bf16 filter index) or rows*dim*4 (tf32 / ffma2 "
+                "over the fp32 rows) + rows*4 row norms + queries; the fp32 matrix is only touched for the ~5 k survivors "
+                "per query (exact re-score); see DESIGN.md 3.1")
+        extra = {"queries_per_pass": q_pass, "passes_per_step": -(-Bg // q_pass),
+                 "fp32_matrix_bytes_per_ms": rows_local * w["dim"] * 4 / roof_ms if roof_ms > 0 else 0.0}
+    achieved = alg_bytes / (roof_ms * 1e-3) / 1e9 if roof_ms > 0 else 0.0
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp) and world == 1:
         try:
-            tj = json.load(open(tp))
-            traffic = tj.get("dram_bytes_per_launch") if tj.get("filter", "tf32") == filt else None
+            traffic = json.load(open(tp)).get(args.workload if kind == "fm" else f"scan_dim{w['dim']}")
         except Exception:
             traffic = None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": total_ms / args.steps, "p50_ms_per_step": float(np.percentile(step_ms, 50)),
             "p99_ms_per_step": float(np.percentile(step_ms, 99)), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (recall, FM), bf16x2/bf16->f32 (MLP), f64 (sort, DPP)",
+            "vs_baseline": None,
+            "dtype": {"recall_sort": "f32 (recall), f64 (sort)", "fm": "f32 (FM)",
+                      "full": "f32 (recall, FM), bf16 / bf16x2 -> f32 (MLP), f64 (sort, DPP)"}[kind],
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
             "stage_ms_per_step": {s: stage_all[s]["ms"] / 20 for s in stage_all},
-            "roofline": {"kernel": kernel, "bound": "hbm", "achieved": achieved,
-                         "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
-                         "peak_source": f"MEASURED_PEAKS.json ({pk_kind})", "launch_ms": scan_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes, "queries_per_pass": q_pass,
-                         "fp32_matrix_bytes_per_ms": rows_local * w["dim"] * 4 / scan_ms if scan_ms > 0 else 0.0,
-                         "note": "algorithmic bytes = what this pass must stream: rows*dim*2 (bf16 filter index) or "
-                                 "rows*dim*4 (tf32 / ffma2 over the fp32 rows) + rows*4 row norms + queries; the fp32 "
-                                 "matrix is only touched for the ~5 k survivors per query (exact re-score); see DESIGN.md 3.1"},
+            "roofline": dict({"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                              "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                              "peak_source": f"MEASURED_PEAKS.json ({pk_kind})", "launch_ms": roof_ms,
+                              "algorithmic_bytes_per_launch": alg_bytes, "note": note}, **extra),
             "e2e": e2e}
-    knobs = {k: v for k, v in sorted(os.environ.items()) if k.startswith("PRG_")}
+    if kind == "full":
+        # DPP is not HBM- or tensor-bound: per selection step a CTA of the pair kernel re-reads the fp64 features of
+        # its 512 candidates from shared memory (positions 4-7 of 16) and tensor memory (positions 8-15)
+        steps_dpp = w["top_n"]
+        feat = 512 * 129 * 8
+        smem_b, tmem_b = feat * 4 // 16, feat * 8 // 16
+        clk = (clocks or {}).get("sm_mhz") or 1900.0
+        t_bound = steps_dpp * (smem_b / 128.0 + tmem_b / 128.0) / (clk * 1e6) * 1e3
+        line["dpp_bound"] = {"kernel": "dpp_pair_kernel", "bound": "on-chip feature re-read (shared + tensor memory)",
+                             "bytes_per_step_per_cta": {"shared": smem_b, "tensor_memory": tmem_b},
+                             "assumed_bytes_per_clk_per_sm": {"shared": 128, "tensor_memory": 128},
+                             "bound_ms": t_bound, "measured_ms": stage_all["dpp"]["ms"] / 20,
+                             "frac": t_bound / max(1e-9, stage_all["dpp"]["ms"] / 20),
+                             "note": "one wave (64 requests x 2 CTAs <= 148 SMs); see DESIGN.md 3.6"}
+    knobs = {kk: v for kk, v in sorted(os.environ.items()) if kk.startswith("PRG_")}
     if knobs:
         line["knobs"] = knobs   # experiment switches read by the library (A/B lines describe themselves)
     if batcher is not None:
         line["e2e_batcher"] = batcher
     if shard_retries is not None:
         line["shard_retry_queries"] = shard_retries
+    if verify is not None:
+        line["multi_gpu_parity"] = verify
     if not args.no_cpu_baseline and world == 1:
         try:
-            r = cpu_measure(w, 1, 0, min(args.cpu_sample_rows, w["items"]))
+            r = cpu_measure(w, 1, 0, args.cpu_requests)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"], "stages_s": r["stages_s"]}
         except Exception as ex:  # the baseline must not take the bench line down

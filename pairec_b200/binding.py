@@ -315,9 +315,12 @@ class Engine:
                                        _ptr(smap), C.c_int(MEM_HOST)))
         return (out, smap) if score_map else out
 
-    def rank_dev(self, model, rows_ptr, B, n, out_ptr):
-        self._ck(self._lib.prg_rank(self._h, C.c_int(model), _ptr(rows_ptr), C.c_int(B), C.c_int(n), _ptr(out_ptr),
-                                    C.c_int(MEM_DEVICE)))
+    def rank_dev(self, model, rows_ptr, B, n, out_ptr, user_ids_ptr=None, user_dense_ptr=None):
+        uf = None
+        if user_ids_ptr is not None or user_dense_ptr is not None:
+            uf = C.byref(UserFeatures(user_ids_ptr, user_dense_ptr))
+        self._ck(self._lib.prg_rank_ex(self._h, C.c_int(model), _ptr(rows_ptr), C.c_int(B), C.c_int(n), uf, _ptr(out_ptr),
+                                       None, C.c_int(MEM_DEVICE)))
 
     # ---------------------------------------------------------------- sort
     def sort_desc(self, score):
@@ -326,6 +329,9 @@ class Engine:
         perm = np.empty((B, n), dtype=np.int32)
         self._ck(self._lib.prg_sort_desc(self._h, _ptr(score), C.c_int(B), C.c_int(n), _ptr(perm), C.c_int(MEM_HOST)))
         return perm
+
+    def sort_desc_dev(self, score_ptr, B, n, perm_ptr):
+        self._ck(self._lib.prg_sort_desc(self._h, _ptr(score_ptr), C.c_int(B), C.c_int(n), _ptr(perm_ptr), C.c_int(MEM_DEVICE)))
 
     # ---------------------------------------------------------------- DPP
     def dpp(self, rows, score, params, hook=None, use_table=True):

@@ -43,41 +43,72 @@ user_prefix_kernel(const uint32_t* __restrict__ ids, const float* __restrict__ d
                    const float* __restrict__ Wu, const float* __restrict__ b1, int N1, float* __restrict__ ubias) {
   pdl_wait();
   pdl_launch_dependents();
+  __shared__ float xv[kMaxFields * 16];        // the user's factor values [u][k]
+  __shared__ float xw[kMaxFields];             // the user's linear weights [u]
   __shared__ float xu[kMaxFields * 16 + 64];   // bf16-rounded user input columns of the tower
   const int b = blockIdx.x, tid = threadIdx.x;
   const uint32_t* idp = ids ? ids + (size_t)b * U : nullptr;
+  // all loads of the request at once (one thread per factor value / linear weight / dense value), the sequential sums after
+  for (int i = tid; i < U * 16; i += 256) {
+    const int u = i >> 4, k = i & 15;
+    const uint32_t id = idp ? idp[u] : 0xFFFFFFFFu;
+    const float v = id < ts.rows[F + u] ? ts.factors[F + u][(size_t)id * 16 + k] : 0.f;
+    xv[i] = v;
+    xu[i] = bf16_val(bf16_bits(v));
+  }
+  for (int u = tid; u < U; u += 256) {
+    const uint32_t id = idp ? idp[u] : 0xFFFFFFFFu;
+    xw[u] = (id < ts.rows[F + u] && ts.linear[F + u]) ? ts.linear[F + u][id] : 0.f;
+  }
+  for (int c = tid; c < n_dense; c += 256) xu[U * 16 + c] = bf16_val(bf16_bits(dense ? dense[(size_t)b * n_dense + c] : 0.f));
+  __syncthreads();
   if (tid < 16) {          // factor dim k: running sums over the user fields, in field order
     float s = 0.f, ss = 0.f;
     for (int u = 0; u < U; ++u) {
-      const uint32_t id = idp ? idp[u] : 0xFFFFFFFFu;
-      const float v = id < ts.rows[F + u] ? ts.factors[F + u][(size_t)id * 16 + tid] : 0.f;
+      const float v = xv[u * 16 + tid];
       s = __fadd_rn(s, v);
       ss = __fmaf_rn(v, v, ss);
-      xu[u * 16 + tid] = bf16_val(bf16_bits(v));
     }
     state[(size_t)b * kFmState + 4 + tid] = s;
     state[(size_t)b * kFmState + 20 + tid] = ss;
   } else if (tid == 16) {
     float lin = w0;
-    for (int u = 0; u < U; ++u) {
-      const uint32_t id = idp ? idp[u] : 0xFFFFFFFFu;
-      const float w = (id < ts.rows[F + u] && ts.linear[F + u]) ? ts.linear[F + u][id] : 0.f;
-      lin = __fadd_rn(lin, w);
-    }
+    for (int u = 0; u < U; ++u) lin = __fadd_rn(lin, xw[u]);
     state[(size_t)b * kFmState] = lin;
-  } else if (tid >= 32 && tid < 32 + n_dense) {
-    const int c = tid - 32;
-    xu[U * 16 + c] = bf16_val(bf16_bits(dense ? dense[(size_t)b * n_dense + c] : 0.f));
   }
-  __syncthreads();
   if (!ubias) return;
   const int Ku = U * 16 + n_dense;
-  for (int j = tid; j < N1; j += 256) {   // fp64 accumulation, c ascending (the oracle's order; rounding once at the end)
-    double acc = 0.0;
-    for (int c = 0; c < Ku; ++c) acc = fma((double)Wu[(size_t)c * N1 + j], (double)xu[c], acc);
-    ubias[(size_t)b * N1 + j] = (float)(acc + (double)b1[j]);
+  // fp64 accumulation, rounded once at the end.  Two output columns per thread and 16 rows of Wu per batch: 32 independent
+  // L2 loads in flight per thread (the kernel is pure load latency: 52 us with one load in flight, r2d launch list)
+  for (int j0 = tid; j0 < N1; j0 += 512) {
+    const int j1 = j0 + 256;
+    const bool two = j1 < N1;
+    double a0 = 0.0, a1 = 0.0;
+    int c = 0;
+    for (; c + 16 <= Ku; c += 16) {
+      float w0v[16], w1v[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        w0v[t] = __ldg(Wu + (size_t)(c + t) * N1 + j0);
+        w1v[t] = two ? __ldg(Wu + (size_t)(c + t) * N1 + j1) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const double x = (double)xu[c + t];
+        a0 = fma((double)w0v[t], x, a0);
+        a1 = fma((double)w1v[t], x, a1);
+      }
+    }
+    for (; c < Ku; ++c) {
+      const double x = (double)xu[c];
+      a0 = fma((double)__ldg(Wu + (size_t)c * N1 + j0), x, a0);
+      if (two) a1 = fma((double)__ldg(Wu + (size_t)c * N1 + j1), x, a1);
+    }
+    ubias[(size_t)b * N1 + j0] = (float)(a0 + (double)b1[j0]);
+    if (two) ubias[(size_t)b * N1 + j1] = (float)(a1 + (double)b1[j1]);
   }
 }
+
 template <int F_UNROLL, int MIN_CTAS>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 gather_fm_kernel(const uint32_t* __restrict__ rows, const uint64_t* __restrict__ keys, uint32_t* __restrict__ rows_out,

@@ -1,6 +1,7 @@
 // handle.h — the per-GPU state behind a prg_handle.
 #pragma once
 #include "common.cuh"
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost nothing unless a tool (nsys / ncu --nvtx) is attached
 
 namespace prg {
 
@@ -197,7 +198,13 @@ inline cudaError_t launch_chained(prg_handle* h, void (*kernel)(KArgs...), dim3 
 
 enum { SCAN_FILTER_BF16 = 0, SCAN_FILTER_TF32 = 1 };
 enum Stage { ST_SCAN = 0, ST_SCAN_DENSE = 1, ST_SELECT = 2, ST_GATHER_FM = 3, ST_MLP = 4, ST_SORT = 5, ST_DPP = 6, ST_OTHER = 7 };
-// RAII span: records an event before and after the enclosed launches when timing is on
+// RAII span: an NVTX range named after the stage around the enclosed launches (host side: where the launches are
+// issued), plus an event before and after them when timing is on
+inline const char* stage_name(int st) {
+  static const char* const names[8] = {"prg:recall_scan", "prg:recall_sample", "prg:recall_select", "prg:gather_fm",
+                                       "prg:mlp", "prg:sort", "prg:dpp", "prg:other"};
+  return names[st & 7];
+}
 struct StageScope {
   prg_handle* h;
   int stage;
@@ -209,10 +216,12 @@ struct StageScope {
     return e;
   }
   StageScope(prg_handle* hh, int st) : h(hh), stage(st) {
+    nvtxRangePushA(stage_name(st));
     if (h->timing == 1 || (h->timing == 2 && st == ST_SCAN)) { a = get(h); cudaEventRecord(a, h->stream); }
   }
   ~StageScope() {
     if (a) { cudaEvent_t b = get(h); cudaEventRecord(b, h->stream); h->spans.push_back({stage, a, b}); }
+    nvtxRangePop();
   }
 };
 

@@ -316,11 +316,30 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
       float logit[NOUT];
 #pragma unroll
       for (int o = 0; o < NOUT; ++o) logit[o] = 0.f;
-#pragma unroll 1
-      for (int c0 = chalf * kHalf; c0 < (chalf + 1) * kHalf; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)BN + (uint32_t)c0, v);
-        if (c0 + 32 >= (chalf + 1) * kHalf) {  // last read of this tile by this warp: hand the buffer back
+      // The accumulator chunks of this warp are read through two register buffers: the tcgen05.ld of chunk i + 1 is in
+      // flight while chunk i goes through bias / ReLU / split / staging (with one buffer the two epilogue warps of a
+      // scheduler spent most of their time waiting for the load: ncu r2d, layer 1 at 35 % tensor-pipe activity after
+      // its MMA count had been halved)
+      constexpr int kChunks = kHalf / 32;
+      uint32_t va[32], vb[32];
+      const uint32_t t_tile = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * (uint32_t)BN + (uint32_t)(chalf * kHalf);
+      tmem_ld32_nowait(t_tile, va);
+#pragma unroll
+      for (int ci = 0; ci < kChunks; ++ci) {
+        const int c0 = chalf * kHalf + ci * 32;
+        uint32_t (&v)[32] = (ci & 1) ? vb : va;
+        uint32_t (&vn)[32] = (ci & 1) ? va : vb;
+        // the request's bias row for this chunk is requested BEFORE the wait for the accumulators, so the two latencies
+        // overlap (ncu r2d: the add that consumed these loads was the top stall of layer 1, 14 % of all samples)
+        float4 bq[8];
+        if (ub) {
+#pragma unroll
+          for (int w = 0; w < 8; ++w) bq[w] = __ldg(reinterpret_cast<const float4*>(ub + n_blk * BN + c0) + w);
+        }
+        tmem_ld_wait32(v);
+        if (ci + 1 < kChunks) {
+          tmem_ld32_nowait(t_tile + (uint32_t)((ci + 1) * 32), vn);
+        } else {  // last read of this tile by this warp: hand the buffer back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -334,7 +353,7 @@ mlp_layer_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __gr
                     // address per warp); the shared-memory bias is then skipped below by adding 0
 #pragma unroll
           for (int w = 0; w < 8; ++w) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(ub + nb) + w);
+            const float4 t = bq[w];
             v[4 * w] = __float_as_uint(__fadd_rn(__uint_as_float(v[4 * w]), t.x));
             v[4 * w + 1] = __float_as_uint(__fadd_rn(__uint_as_float(v[4 * w + 1]), t.y));
             v[4 * w + 2] = __float_as_uint(__fadd_rn(__uint_as_float(v[4 * w + 2]), t.z));

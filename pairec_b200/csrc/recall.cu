@@ -1024,7 +1024,7 @@ static int launch_sample_select(prg_handle* h, int mode, SelectParams st, int nq
   return launch_select(h, mode, st, nq);
 }
 
-// EXPERIMENTAL (config "recall_tilemax"): threshold from tile maxima.  The sample scan leaves ONE value per (sample tile,
+// Threshold from tile maxima (config "recall_tilemax", default on).  The sample scan leaves ONE value per (sample tile,
 // query): the largest approximate score of the tile's 256 rows (recall_tc.cu, SCAN_TILEMAX).  tau = the r-th largest of a
 // query's T tile maxima: at least r sampled rows reach it, and the share of tiles whose maximum reaches it, r / T,
 // estimates the share of ROWS that do: -ln(1 - r/T) / 256 — the same statistic the r-th largest of all sample keys
@@ -1049,8 +1049,18 @@ __global__ void __launch_bounds__(256) tilemax_tau_kernel(const uint32_t* __rest
   __syncthreads();
   for (uint32_t i = tid; i < T; i += 256) {
     const uint32_t mine = v[i];
-    uint32_t rank = 0;   // values that come before `mine` in (value desc, index asc) order; exact only below r
-    for (uint32_t u = 0; u < T && rank < r; ++u) {
+    uint32_t rank = 0;   // values that come before `mine` in (value desc, index asc) order
+    // no early exit: the loop is a stream of independent broadcast reads (8 in flight), not a chain of dependent ones
+    // (ncu launch list, r2d: 29 us for T = 305 with the data-dependent exit)
+    uint32_t u = 0;
+    for (; u + 8 <= T; u += 8) {
+#pragma unroll
+      for (uint32_t t = 0; t < 8; ++t) {
+        const uint32_t o = v[u + t];
+        rank += (o > mine || (o == mine && u + t < i)) ? 1u : 0u;
+      }
+    }
+    for (; u < T; ++u) {
       const uint32_t o = v[u];
       rank += (o > mine || (o == mine && u < i)) ? 1u : 0u;
     }
@@ -1376,7 +1386,7 @@ int recall_shard_sample_device(prg_handle* h, const float* q_dev, int Bg, int k,
   PRG_TRY(h->sample_keys.ensure((size_t)nblk * kQB * pl.slots * 8));
   if (!h->row_norm.p) PRG_TRY(build_row_norms(h));
   {
-    // EXPERIMENTAL (config "recall_tilemax", same on every rank): the shard contributes its r largest TILE MAXIMA instead
+    // config "recall_tilemax" (same on every rank): the shard contributes its r largest TILE MAXIMA instead
     // of its r largest sample keys; the r-th largest of the gathered maxima estimates the same row share (the share of
     // the G * T sample tiles that hold a row above tau is r / (G T) ~ 256 * target / rows for small shares).
     const double rows_all = (double)h->E_rows * G;

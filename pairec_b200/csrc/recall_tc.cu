@@ -541,7 +541,7 @@ static int launch_tc_dense(prg_handle* h, const ScanParams& p) {
   return PRG_OK;
 }
 
-// EXPERIMENTAL (config "recall_tilemax"): sample scoring that emits one maximum per (tile, query):
+// config "recall_tilemax": sample scoring that emits one maximum per (tile, query):
 // p.dense = u32 [nq][dense_stride], slot = launch tile
 template <int DIM>
 static int launch_tc_tilemax(prg_handle* h, const ScanParams& p) {
@@ -575,7 +575,7 @@ int launch_scan_tc_dense(prg_handle* h, const ScanParams& p) {
 }
 
 // queries per pass the kernel is built for: 64/128/256 at dim 64, 64 at dim 128 (shared-memory budget)
-// EXPERIMENTAL (config "scan128_nqb", not yet run): 128/256 queries per pass at dim 128 over the bf16 index with a
+// config "scan128_nqb" (default on): 128/256 queries per pass at dim 128 over the bf16 index with a
 // 2-stage ring (C5: 1024 queries per shard are 4 passes over the index instead of 16)
 int scan_tc_max_queries(const prg_handle* h) {
   if (h->E_dim == 64) return 256;

@@ -119,24 +119,20 @@ def test_fused_path_full_size_equals_staged_calls_and_oracle_spot_checks(oracle_
     T = bench.make_tables_torch(w, dev, 0, 1)
     eng = Engine(0)
     try:
-        eng.set_item_matrix(T["E"].data_ptr(), rows=w["items"], dim=w["dim"], mem=MEM_DEVICE)
-        eng.set_item_fields(T["fields"].data_ptr(), rows=w["items"], n_fields=w["n_fields"], mem=MEM_DEVICE)
-        for t in range(w["n_fields"]):
-            eng.set_feature_table(t, T["factors"][t].data_ptr(), T["linear"][t].data_ptr(), rows=w["table_rows"], fdim=16,
-                                  mem=MEM_DEVICE)
-        eng.set_fm_bias(0.05)
+        bench.load_engine(eng, w, T, MEM_DEVICE)     # item matrix, 32 item + 8 user tables, tower 640-512-256-128-1, diversity
         W, b = bench.mlp_weights_np(w["mlp"])
-        eng.set_mlp(w["mlp"], W, b)
-        eng.set_diversity_matrix(T["D"].data_ptr(), rows=w["items"], dim=w["div_dim"], dtype=0, mem=MEM_DEVICE)
+        U = w["user_fields"]
         Bq, k, Tn = w["batch"], w["k"], w["top_n"]
         p = DppParams(top_n=Tn, alpha=1.0, window_size=w["window"])
         g = torch.Generator(device=dev)
         g.manual_seed(3)
         Q = (torch.randn(Bq, w["dim"], device=dev, generator=g) / w["dim"] ** 0.5).cpu().numpy()
 
-        rows_f, scores_f, n_f = eng.recommend(Q, k, MODEL_FM_MLP, p)            # fused
+        uids = torch.randint(0, w["user_rows"], (Bq, U), device=dev, generator=g, dtype=torch.int32).cpu().numpy().astype(np.uint32)
+
+        rows_f, scores_f, n_f = eng.recommend(Q, k, MODEL_FM_MLP, p, user_ids=uids)   # fused
         rrows, rscores, rn = eng.recall_topk(Q, k)                               # staged: four calls
-        rank = eng.rank(MODEL_FM_MLP, rrows)
+        rank = eng.rank(MODEL_FM_MLP, rrows, user_ids=uids)
         perm = eng.sort_desc(rank)
         srows = np.take_along_axis(rrows, perm, axis=1)
         sscores = np.take_along_axis(rank, perm, axis=1)
@@ -149,12 +145,13 @@ def test_fused_path_full_size_equals_staged_calls_and_oracle_spot_checks(oracle_
             assert set(rows_f[bi].tolist()) <= set(rrows[bi].tolist())
 
         # oracle spot checks (two requests): rank scores from the same tables, DPP sequence from the GPU's scores
-        factors = [T["factors"][t].cpu().numpy() for t in range(w["n_fields"])]
-        linear = [T["linear"][t].cpu().numpy() for t in range(w["n_fields"])]
+        factors = [T["factors"][t].cpu().numpy() for t in range(w["n_fields"])] + [T["ufactors"][u].cpu().numpy() for u in range(U)]
+        linear = [T["linear"][t].cpu().numpy() for t in range(w["n_fields"])] + [T["ulinear"][u].cpu().numpy() for u in range(U)]
         for bi in (0, Bq - 1):
             r = torch.from_numpy(rrows[bi].astype(np.int64)).to(dev)
             fields_sub = T["fields"][r].cpu().numpy().astype(np.uint32)
-            fm, x = oracle_lib.gather_fm(fields_sub, factors, linear, 0.05, np.arange(k, dtype=np.uint32), want_x=True)
+            fm, x = oracle_lib.gather_fm(fields_sub, factors, linear, 0.05, np.arange(k, dtype=np.uint32), want_x=True,
+                                         user_ids=uids[bi])
             ml = oracle_lib.mlp_forward(x, w["mlp"], W, b)
             want = oracle_lib.sigmoid((fm + ml).astype(np.float32)).astype(np.float64)
             rel = np.abs(rank[bi] - want) / np.maximum(np.abs(want), 1e-30)
