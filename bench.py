@@ -722,10 +722,19 @@ def main():
             vt = torch.tensor([1 if all(verify.values()) else 0], device=dev)
             dist.all_reduce(vt, op=dist.ReduceOp.MIN)
             verify["all_ranks_ok"] = bool(vt.item())
-    if rank != 0:
+    def finish():
+        # Tensors that NCCL used on the library's stream are recorded against it by torch's allocator: freeing them after
+        # the Engine (and its stream) has gone aborts the interpreter at exit.  Leave in a defined order instead.
+        sys.stdout.flush()
+        torch.cuda.synchronize(dev)
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        os._exit(0)
+
+    if rank != 0:
+        finish()
 
     pk, pk_kind = peaks()
     rs = stage[roof_stage]
@@ -754,6 +763,20 @@ def main():
         extra = {"queries_per_pass": q_pass, "passes_per_step": -(-Bg // q_pass),
                  "fp32_matrix_bytes_per_ms": rows_local * w["dim"] * 4 / roof_ms if roof_ms > 0 else 0.0}
     achieved = alg_bytes / (roof_ms * 1e-3) / 1e9 if roof_ms > 0 else 0.0
+    roof = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / pk["hbm_gbs"]}
+    if kind != "fm" and roof_ms > 0:
+        # the same pass as tensor-core work: 2 * rows * dim * queries flops per launch against the sustained bf16 rate.
+        # Whichever fraction is larger names the bound: C4 (64-d, 64 queries per pass) streams, C5 (128-d, 256 queries per
+        # pass: 819 GFLOP per 3.2 GB) computes.
+        flops = 2.0 * rows_local * w["dim"] * q_pass
+        tf = flops / (roof_ms * 1e-3) / 1e12
+        tfrac = tf / pk["bf16_tflops_sustained"]
+        extra.update({"hbm": {"achieved_gbs": achieved, "peak_gbs": pk["hbm_gbs"], "frac": achieved / pk["hbm_gbs"]},
+                      "tensor": {"achieved_tflops": tf, "peak_tflops": pk["bf16_tflops_sustained"], "frac": tfrac,
+                                 "flops_per_launch": flops}})
+        if tfrac > roof["frac"]:
+            roof.update({"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tfrac})
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp) and world == 1:
@@ -769,25 +792,29 @@ def main():
                       "full": "f32 (recall, FM), bf16 / bf16x2 -> f32 (MLP), f64 (sort, DPP)"}[kind],
             "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
             "stage_ms_per_step": {s: stage_all[s]["ms"] / 20 for s in stage_all},
-            "roofline": dict({"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                              "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
-                              "peak_source": f"MEASURED_PEAKS.json ({pk_kind})", "launch_ms": roof_ms,
-                              "algorithmic_bytes_per_launch": alg_bytes, "note": note}, **extra),
+            "roofline": dict(roof, **{"traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({pk_kind})",
+                                      "launch_ms": roof_ms, "algorithmic_bytes_per_launch": alg_bytes, "note": note}, **extra),
             "e2e": e2e}
     if kind == "full":
         # DPP is not HBM- or tensor-bound: per selection step a CTA of the pair kernel re-reads the fp64 features of
         # its 512 candidates from shared memory (positions 4-7 of 16) and tensor memory (positions 8-15)
         steps_dpp = w["top_n"]
+        waves = -(-B * 2 // 148)                      # 2 CTAs per request
         feat = 512 * 129 * 8
         smem_b, tmem_b = feat * 4 // 16, feat * 8 // 16
+        dops = 512 * 129 * 2                          # one DMUL + one DADD per feature element and step
         clk = (clocks or {}).get("sm_mhz") or 1900.0
-        t_bound = steps_dpp * (smem_b / 128.0 + tmem_b / 128.0) / (clk * 1e6) * 1e3
-        line["dpp_bound"] = {"kernel": "dpp_pair_kernel", "bound": "on-chip feature re-read (shared + tensor memory)",
-                             "bytes_per_step_per_cta": {"shared": smem_b, "tensor_memory": tmem_b},
-                             "assumed_bytes_per_clk_per_sm": {"shared": 128, "tensor_memory": 128},
+        cyc = smem_b / 128.0 + tmem_b / 64.0 + dops / 64.0
+        t_bound = waves * steps_dpp * cyc / (clk * 1e6) * 1e3
+        line["dpp_bound"] = {"kernel": "dpp_pair_kernel", "bound": "on-chip feature re-read + fp64 issue, per selection step",
+                             "per_step_per_cta": {"shared_bytes": smem_b, "tensor_memory_bytes": tmem_b, "fp64_ops": dops},
+                             "rates_per_clk_per_sm": {"shared_bytes": 128, "tensor_memory_read_bytes": 64, "fp64_ops": 64},
+                             "cycles_per_step": cyc, "selection_steps": steps_dpp, "waves": waves,
                              "bound_ms": t_bound, "measured_ms": stage_all["dpp"]["ms"] / 20,
                              "frac": t_bound / max(1e-9, stage_all["dpp"]["ms"] / 20),
-                             "note": "one wave (64 requests x 2 CTAs <= 148 SMs); see DESIGN.md 3.6"}
+                             "note": "the three phases of a step run back to back (every warp is in the same phase), so the "
+                                     "bound is their sum; rates from the microarchitecture notes (TMEM read 64 B/clk/SM); "
+                                     "DESIGN.md 3.6"}
     knobs = {kk: v for kk, v in sorted(os.environ.items()) if kk.startswith("PRG_")}
     if knobs:
         line["knobs"] = knobs   # experiment switches read by the library (A/B lines describe themselves)
@@ -805,8 +832,7 @@ def main():
         except Exception as ex:  # the baseline must not take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {ex}"}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
