@@ -267,6 +267,24 @@ int prg_recommend_from_keys_ex(prg_handle* h, const uint64_t* keys_dev, int G, u
                                const prg_dpp_params* p, const prg_user_features* user, uint32_t* out_row,
                                double* out_score, int32_t* out_n, int mem);
 
+/* ---------------------------------------------------------------- all GPUs of a box behind one call */
+
+/* The reference is ONE Go process (pairec.Run, pairec.go:61-86).  A prg_group owns G handles of that process — handle g
+ * holds row shard g of the item matrix (prg_set_item_matrix with row_base = first global row of the shard) and replicas of
+ * the field / feature / diversity tables — and runs the row-sharded request path without NCCL and without a host round
+ * trip inside a batch: sample keys and candidate lists travel as stores into the peers' buffers over NVLink (P2P), the
+ * GPUs order themselves with events.  Request i is ranked / re-ranked by GPU i / ceil(n_requests / G).  Results are
+ * bit-identical to prg_recommend_ex over the unsharded matrix.  *out_redone (nullable) = 1 when a query failed the
+ * global-threshold check and the batch was redone with exact per-shard lists.  Host buffers only; one batch at a time
+ * per group; the member handles must not be destroyed before the group.  Members on the same device are allowed. */
+typedef struct prg_group prg_group;
+int prg_group_create(prg_handle* const* handles, int G, prg_group** out);
+int prg_group_size(prg_group* grp);
+int prg_group_recommend(prg_group* grp, const float* q, int n_requests, int recall_k, int model, const prg_dpp_params* p,
+                        const prg_user_features* user, uint32_t* out_row, double* out_score, int32_t* out_n,
+                        int32_t* out_redone);
+void prg_group_destroy(prg_group* grp);
+
 /* ---------------------------------------------------------------- cross-call request batcher */
 
 /* The reference handles ONE request per goroutine (service/user_recommend.go:46; the rank stage then fans out into

@@ -4,6 +4,6 @@ The product is pairec_b200/libpairec_gpu.so (hand-written sm_100a CUDA behind th
 This package only binds that library (binding.py) and mirrors the reference's operator/plugin interface for the
 path (plugin.py).  There is no CPU implementation in here: loading fails loudly when the library is missing.
 """
-from .binding import Batcher, Engine, DppParams, SsdParams, PrgError, lib_path, load_library  # noqa: F401
+from .binding import Batcher, Engine, Group, DppParams, SsdParams, PrgError, lib_path, load_library  # noqa: F401
 
-__all__ = ["Batcher", "Engine", "DppParams", "SsdParams", "PrgError", "lib_path", "load_library"]
+__all__ = ["Batcher", "Engine", "Group", "DppParams", "SsdParams", "PrgError", "lib_path", "load_library"]

@@ -25,6 +25,7 @@ EXPORTS = [
     "prg_batcher_start", "prg_batcher_recommend", "prg_batcher_stats", "prg_batcher_stop", "prg_batcher_drive",
     "prg_set_user_fields", "prg_set_rank_score", "prg_rank_ex", "prg_recommend_ex", "prg_recommend_from_keys_ex",
     "prg_batcher_recommend_ex", "prg_item_dim", "prg_dpp_ex",
+    "prg_group_create", "prg_group_size", "prg_group_recommend", "prg_group_destroy",
 ]
 
 
@@ -90,6 +91,7 @@ def load_library():
         _lib.prg_item_dim.restype = C.c_uint32
         _lib.prg_destroy.restype = None
         _lib.prg_batcher_stop.restype = None
+        _lib.prg_group_destroy.restype = None
         for name in EXPORTS:
             getattr(_lib, name)  # raises AttributeError if a declared symbol is not exported
     return _lib
@@ -417,6 +419,48 @@ def lookup(value, present):
     if rc != 0:
         raise PrgError(rc, lib.prg_last_error().decode())
     return out
+
+
+class Group:
+    """prg_group: G Engines of this process (one per GPU of the box, or several on one GPU in tests), each holding one row
+    shard of the item matrix and replicas of the other tables; one call serves a batch over all of them, the exchanges
+    run as peer stores over NVLink inside the library (no NCCL, no torch.distributed)."""
+
+    def __init__(self, engines):
+        self._lib = engines[0]._lib
+        self._engines = list(engines)   # keep the members alive
+        arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+        self._g = C.c_void_p(0)
+        rc = self._lib.prg_group_create(arr, C.c_int(len(engines)), C.byref(self._g))
+        if rc != 0:
+            raise PrgError(rc, self._lib.prg_last_error().decode())
+
+    def recommend(self, q, recall_k, model, params, user_ids=None, user_dense=None):
+        """q [n, dim] -> rows u32 [n, top_n], scores f64 [n, top_n], counts i32 [n], redone (bool)."""
+        q = self._engines[0]._queries(q)
+        n = q.shape[0]
+        T = params.top_n
+        rows = np.empty((n, T), dtype=np.uint32)
+        scores = np.empty((n, T), dtype=np.float64)
+        cnt = np.empty(n, dtype=np.int32)
+        redone = C.c_int32(0)
+        uf, keep = self._engines[0]._user(n, user_ids, user_dense)
+        rc = self._lib.prg_group_recommend(self._g, _ptr(q), C.c_int(n), C.c_int(recall_k), C.c_int(model), C.byref(params),
+                                           uf, _ptr(rows), _ptr(scores), _ptr(cnt), C.byref(redone))
+        if rc != 0:
+            raise PrgError(rc, self._lib.prg_last_error().decode())
+        return rows, scores, cnt, bool(redone.value)
+
+    def close(self):
+        if self._g:
+            self._lib.prg_group_destroy(self._g)
+            self._g = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Batcher:

@@ -253,7 +253,9 @@ int shard_sample_len(int k);
 int recall_shard_sample_device(prg_handle* h, const float* q_dev, int Bg, int k, int G, uint64_t* out);
 int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, int k, int G, const uint64_t* all_samples,
                                    uint64_t* out);
-int shard_check_device(prg_handle* h, const uint64_t* gathered, int G, int Bg, int k, int32_t* retry_dev);
+// tau (nullable): thresholds of the Bg queries checked (default: the handle's, from recall_shard_candidates_device)
+int shard_check_device(prg_handle* h, const uint64_t* gathered, int G, int Bg, int k, int32_t* retry_dev,
+                       const uint64_t* tau = nullptr);
 int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k,
                       uint64_t* keys_out);
 }  // namespace prg

@@ -127,9 +127,9 @@ __global__ void final_gather_kernel(const uint32_t* rows, const double* scores, 
   }
 }
 
-// stages after recall: topk_keys [B][k] (sorted, merged) -> rank -> sort -> DPP -> outputs
-static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
-                              double* out_score, int32_t* out_n, const prg_user_features& user);
+// stages after recall: topk_keys [B][k] (sorted, merged) -> rank -> sort -> DPP -> outputs (also called by group.cu)
+int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
+                       double* out_score, int32_t* out_n, const prg_user_features& user);
 
 // The recall's per-query status is validated AFTER the downstream stages have been enqueued (resolve_pending): in the
 // steady state the host never waits in the middle of a step; a failed query (adversarial row order) is redone densely
@@ -148,8 +148,8 @@ static int recommend_device(prg_handle* h, const float* q_dev, int B, int k, int
   return resolve_now ? resolve_pending(h) : PRG_OK;
 }
 
-static int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
-                              double* out_score, int32_t* out_n, const prg_user_features& user) {
+int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_params& p, uint32_t* out_row,
+                       double* out_score, int32_t* out_n, const prg_user_features& user) {
   const int M = B * k;
   PRG_TRY(h->rec_rows.ensure((size_t)M * 4));
   PRG_TRY(h->out_score.ensure((size_t)M * 4));

@@ -1541,9 +1541,9 @@ __global__ void __launch_bounds__(128) shard_check_kernel(const uint64_t* __rest
   if (bad && lane == 0) { atomicOr(&retry[0], 1); atomicAdd(&retry[1], 1); }
 }
 
-int shard_check_device(prg_handle* h, const uint64_t* gathered, int G, int Bg, int k, int32_t* retry_dev) {
+int shard_check_device(prg_handle* h, const uint64_t* gathered, int G, int Bg, int k, int32_t* retry_dev, const uint64_t* tau) {
   if (!h->tau.p) return fail(PRG_ESTATE, "prg_shard_candidates has not run on this handle");
-  shard_check_kernel<<<(Bg + 3) / 4, 128, 0, h->stream>>>(gathered, G, Bg, k, (const uint64_t*)h->tau.p, retry_dev);
+  shard_check_kernel<<<(Bg + 3) / 4, 128, 0, h->stream>>>(gathered, G, Bg, k, tau ? tau : (const uint64_t*)h->tau.p, retry_dev);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;
