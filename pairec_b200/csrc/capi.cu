@@ -196,6 +196,9 @@ void prg_destroy(prg_handle* h) {
     for (DevBuf* b : bufs) b->release();
     for (int l = 0; l < kMaxLayers; ++l) { h->mlp_W[l].release(); h->mlp_b[l].release(); }
     if (h->flags_ev) cudaEventDestroy(h->flags_ev);
+    if (h->side_stream) { cudaStreamSynchronize(h->side_stream); cudaStreamDestroy(h->side_stream); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->host_flags) cudaFreeHost(h->host_flags);
     for (auto& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);

@@ -214,7 +214,10 @@ static int fill_tables(prg_handle* h, TableSet* ts, uint32_t n_tables) {
 }
 
 // user_ids_dev [B][U] / user_dense_dev [B][n_dense] (nullable = every user feature absent) -> h->fm_state, h->ubias
-int user_prefix_device(prg_handle* h, const uint32_t* user_ids_dev, const float* user_dense_dev, int B, bool need_mlp) {
+// ahead: launch on the handle's side stream, forked from / joined to the main stream by events, so that the kernel (pure
+// load latency, a handful of CTAs) runs beside the recall instead of in front of the gather; the caller makes the main
+// stream wait for h->ev_join before the gather (rank_device)
+int user_prefix_device(prg_handle* h, const uint32_t* user_ids_dev, const float* user_dense_dev, int B, bool need_mlp, bool ahead) {
   const uint32_t U = h->n_user_fields, nd = h->n_user_dense;
   if (h->n_fields + U > (uint32_t)kMaxFields) return fail(PRG_EUNSUPPORTED, "item + user fields > 64");
   TableSet ts{};
@@ -227,6 +230,23 @@ int user_prefix_device(prg_handle* h, const uint32_t* user_ids_dev, const float*
     if (h->mlp_k_user != U * 16 + nd) return fail(PRG_ESTATE, "prg_set_mlp must follow prg_set_user_fields");
     PRG_TRY(h->ubias.ensure((size_t)B * N1 * 4));
     ubias = (float*)h->ubias.p;
+  }
+  if (ahead) {
+    if (!h->side_stream) {
+      PRG_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+      PRG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      PRG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    PRG_CUDA(cudaEventRecord(h->ev_fork, h->stream));            // behind the H2D of the user ids / the previous batch
+    PRG_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    user_prefix_kernel<<<(unsigned)B, 256, 0, h->side_stream>>>(user_ids_dev, user_dense_dev, (int)U, (int)nd, (int)h->n_fields, ts,
+                                                                h->fm_w0, (float*)h->fm_state.p, (const float*)h->mlp_Wu.p,
+                                                                (const float*)h->mlp_b[0].p, N1, ubias);
+    PRG_CUDA(cudaGetLastError());
+    PRG_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+    h->prefix_ahead = true;
+    count_launch(h);
+    return PRG_OK;
   }
   StageScope span(h, ST_GATHER_FM);
   PRG_CUDA(launch_chained(h, user_prefix_kernel, dim3((unsigned)B), dim3(256), 0, 1, user_ids_dev, user_dense_dev, (int)U, (int)nd,

@@ -317,26 +317,27 @@ int prg_group_recommend(prg_group* grp, const float* q, int n_requests, int reca
   if (n_requests <= 0 || recall_k <= 0 || p->top_n <= 0) return fail(PRG_EINVAL, "n_requests, recall_k, top_n must be positive");
   std::lock_guard<std::mutex> call(grp->call_mu);
   const int G = grp->G;
-  const int B = (n_requests + G - 1) / G, Bg = B * G;   // requests per GPU; the tail is padded with zero queries
+  const int B = (n_requests + G - 1) / G, Bg = B * G;   // requests per GPU; the tail repeats the last request (dropped again)
   prg_handle* h0 = grp->dev[0].h;
   const uint32_t dim = h0->E_dim, U = h0->n_user_fields, nd = h0->n_user_dense;
   const int r = shard_sample_len(recall_k);
   const size_t blk = (size_t)B * recall_k + B, TT = (size_t)B * p->top_n;
   // ---- pinned input staging (zero-padded), shared by the G copy engines
+  // (a zero query would tie every row of the catalog and fail the threshold check for the whole batch)
   PRG_TRY(ensure_pinned((void**)&grp->q_host, &grp->q_cap, (size_t)Bg * dim * 4));
-  memset(grp->q_host, 0, (size_t)Bg * dim * 4);
   memcpy(grp->q_host, q, (size_t)n_requests * dim * 4);
+  for (int i = n_requests; i < Bg; ++i) memcpy(grp->q_host + (size_t)i * dim, q + (size_t)(n_requests - 1) * dim, (size_t)dim * 4);
   grp->has_uid = user && user->ids && U;
   grp->has_dense = user && user->dense && nd;
   if (grp->has_uid) {
     PRG_TRY(ensure_pinned((void**)&grp->uid_host, &grp->uid_cap, (size_t)Bg * U * 4));
-    memset(grp->uid_host, 0xFF, (size_t)Bg * U * 4);
     memcpy(grp->uid_host, user->ids, (size_t)n_requests * U * 4);
+    for (int i = n_requests; i < Bg; ++i) memcpy(grp->uid_host + (size_t)i * U, user->ids + (size_t)(n_requests - 1) * U, (size_t)U * 4);
   }
   if (grp->has_dense) {
     PRG_TRY(ensure_pinned((void**)&grp->udense_host, &grp->udense_cap, (size_t)Bg * nd * 4));
-    memset(grp->udense_host, 0, (size_t)Bg * nd * 4);
     memcpy(grp->udense_host, user->dense, (size_t)n_requests * nd * 4);
+    for (int i = n_requests; i < Bg; ++i) memcpy(grp->udense_host + (size_t)i * nd, user->dense + (size_t)(n_requests - 1) * nd, (size_t)nd * 4);
   }
   // ---- per-GPU buffers and the tables of peer destinations
   std::vector<uint4*> p1((size_t)G);

@@ -136,6 +136,10 @@ struct prg_handle {
   uint32_t n_user_fields = 0;   // categorical user fields: feature tables n_fields .. n_fields + n_user_fields - 1
   uint32_t n_user_dense = 0;    // numeric context values appended to the tower input
   prg::DevBuf user_ids_dev, user_dense_dev;   // host-call staging: B x U u32, B x n_dense f32
+  // the fused path evaluates a batch's user prefix on a side stream while the recall runs (it depends on the request only)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool prefix_ahead = false;    // user_prefix_kernel of the current batch is in flight on side_stream; ev_join follows it
   prg::DevBuf fm_state;         // B x 36 f32: lin, s[16], ss[16] after the user fields (the gather continues from it)
   prg::DevBuf ubias;            // B x dims[1] f32: b1 + W1[:, user columns] * x_user
   prg::DevBuf act[2];   // activations ping-pong (bf16)

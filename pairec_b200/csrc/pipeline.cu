@@ -6,7 +6,7 @@ namespace prg {
 // gather_fm.cu
 int gather_fm_device(prg_handle* h, const uint32_t* rows_dev, int M, float* logit_dev, uint16_t* x_dev,
                      const uint64_t* keys_dev, uint32_t* rows_out, int rows_per_req);
-int user_prefix_device(prg_handle* h, const uint32_t* user_ids_dev, const float* user_dense_dev, int B, bool need_mlp);
+int user_prefix_device(prg_handle* h, const uint32_t* user_ids_dev, const float* user_dense_dev, int B, bool need_mlp, bool ahead);
 int logits_to_scores_device(prg_handle* h, const float* a, const float* b, const uint32_t* rows_dev, int M, double* out);
 // mlp.cu
 int mlp_forward_device(prg_handle* h, const uint16_t* x_dev, int M, float* logit_dev, const float* fm_logit_dev,
@@ -76,7 +76,14 @@ static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int B
     PRG_TRY(h->act[1].ensure(mlp_act_bytes(h, M)));
     x = (uint16_t*)h->act[0].p;
   }
-  if (has_user) PRG_TRY(user_prefix_device(h, user ? user->ids : nullptr, user ? user->dense : nullptr, B, need_mlp));
+  if (has_user) {
+    if (h->prefix_ahead) {   // the fused path launched it on the side stream before the recall: join here
+      h->prefix_ahead = false;
+      PRG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    } else {
+      PRG_TRY(user_prefix_device(h, user ? user->ids : nullptr, user ? user->dense : nullptr, B, need_mlp, /*ahead=*/false));
+    }
+  }
   PRG_TRY(gather_fm_device(h, rows_dev, M, fm_logit, x, keys_dev, keys_dev ? const_cast<uint32_t*>(rows_dev) : nullptr,
                            has_user ? n : 0));
   if (need_mlp)
@@ -138,7 +145,14 @@ static int recommend_device(prg_handle* h, const float* q_dev, int B, int k, int
                             uint32_t* out_row, double* out_score, int32_t* out_n, bool resolve_now,
                             const prg_user_features& user) {
   PRG_TRY(h->topk_keys.ensure((size_t)B * k * 8));
-  PRG_TRY(recall_topk_device(h, q_dev, B, k, (uint64_t*)h->topk_keys.p, /*defer=*/true));
+  // the user prefix depends on the request only: it runs on the side stream while the recall streams the item index
+  if (h->n_user_fields + h->n_user_dense > 0 && (model == PRG_MODEL_FM || h->mlp_layers > 0) &&
+      (model == PRG_MODEL_FM || h->mlp_k_user == h->n_user_fields * 16 + h->n_user_dense))
+    PRG_TRY(user_prefix_device(h, user.ids, user.dense, B, model != PRG_MODEL_FM, /*ahead=*/true));
+  {
+    const int rc = recall_topk_device(h, q_dev, B, k, (uint64_t*)h->topk_keys.p, /*defer=*/true);
+    if (rc != PRG_OK) { h->prefix_ahead = false; return rc; }   // nobody will join the side stream for this batch
+  }
   PRG_TRY(post_recall_device(h, B, k, model, p, out_row, out_score, out_n, user));
   if (h->pending.active) {
     h->pending.fused = true;
