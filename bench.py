@@ -378,6 +378,77 @@ def cpu_measure(w, steps, warmup, reqs_per_step):
                        f"distinct requests per step" + (f"; catalog capped at 10 M rows, recall time scaled x{scale:.0f}" if scale != 1.0 else ""))
 
 
+# ---------------------------------------------------------------------------------------------- prg_group (one process)
+def main_group(args, w, config):
+    """The row-sharded path of ONE process over G GPUs (prg_group_*: P2P exchanges inside the library, no NCCL): the call a
+    Go host makes.  Host buffers in and out, so every number here is end to end.  Not the driver's N>1 contract (that is
+    torchrun, one rank per GPU); an extra line for profiles/."""
+    import torch
+    from pairec_b200 import DppParams, Engine, Group
+    from pairec_b200.binding import MEM_DEVICE, MODEL_FM_MLP
+    G = args.group
+    assert w["kind"] == "full"
+    engs, tabs = [], []
+    for g in range(G):
+        torch.cuda.set_device(g)
+        dev = torch.device("cuda", g)
+        T = make_tables_torch(w, dev, g, G)
+        e = Engine(g)
+        load_engine(e, w, T, MEM_DEVICE)
+        engs.append(e)
+        tabs.append(T)
+    grp = Group(engs)
+    B, k, Tn, U = w["batch"], w["k"], w["top_n"], w.get("user_fields", 0)
+    Bg = B * G
+    rng = np.random.default_rng(3)
+    Qs = [(rng.standard_normal((Bg, w["dim"])) / w["dim"] ** 0.5).astype(np.float32) for _ in range(N_ROT)]
+    Us = [rng.integers(0, w["user_rows"], size=(Bg, U)).astype(np.uint32) for _ in range(N_ROT)] if U else [None] * N_ROT
+    p = DppParams(top_n=Tn, alpha=1.0, window_size=w["window"])
+    warm = max(args.warmup, N_ROT)
+    redone = 0
+    for i in range(warm):
+        grp.recommend(Qs[i % N_ROT], k, MODEL_FM_MLP, p, user_ids=Us[i % N_ROT])
+    l0 = sum(e.launches for e in engs)
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        t1 = time.perf_counter()
+        out = grp.recommend(Qs[i % N_ROT], k, MODEL_FM_MLP, p, user_ids=Us[i % N_ROT])
+        lat.append((time.perf_counter() - t1) * 1e3)
+        redone += int(out[3])
+    wall = time.perf_counter() - t0
+    launches = sum(e.launches for e in engs) - l0
+    parity = None
+    if w["items"] * w["dim"] * 4 <= 8e9 and not args.no_verify:   # the unsharded path over the gathered matrix on GPU 0
+        torch.cuda.set_device(0)
+        full = torch.cat([tabs[g]["E"].to("cuda:0") for g in range(G)])
+        T1 = dict(tabs[0])
+        T1["E"], T1["row_base"] = full, 0
+        e1 = Engine(0)
+        load_engine(e1, w, T1, MEM_DEVICE)
+        want = e1.recommend(Qs[0][:B * G], k, MODEL_FM_MLP, p, user_ids=Us[0])
+        got = grp.recommend(Qs[0], k, MODEL_FM_MLP, p, user_ids=Us[0])
+        parity = bool((got[0] == want[0]).all() and (got[1].view(np.uint64) == want[1].view(np.uint64)).all() and
+                      (got[2] == want[2]).all())
+        e1.close()
+    line = {"impl": "b200-group", "metric": METRIC, "value": Bg * args.steps / wall, "unit": UNIT, "n_gpus": G,
+            "steps": args.steps, "warmup": warm, "ms_per_step": wall / args.steps * 1e3,
+            "p50_ms_per_step": float(np.percentile(lat, 50)), "p99_ms_per_step": float(np.percentile(lat, 99)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (recall, FM), bf16 / bf16x2 -> f32 (MLP), f64 (sort, DPP)", "data": "synthetic",
+            "config": dict(config, global_batch=Bg,
+                           sharding="item matrix row-sharded over the GPUs of ONE process; prg_group_recommend: sample keys "
+                                    "and candidate prefixes travel as peer stores over NVLink, no NCCL"),
+            "gpu_launches": int(launches), "batches_redone_exactly": redone,
+            "e2e": {"value": Bg * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": G * (Bg * w["dim"] * 4 + Bg * U * 4),
+                    "d2h_bytes_per_step": Bg * Tn * 12 + Bg * 4,
+                    "note": "host buffers in and out: every GPU copies the whole request batch in, returns its own results"},
+            "equals_unsharded_path": parity}
+    print(json.dumps(line))
+    sys.stdout.flush()
+    os._exit(0)
+
+
 # ---------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -390,6 +461,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batcher", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed N>1 parity checks")
+    ap.add_argument("--group", type=int, default=0, help="ONE process driving this many GPUs through prg_group_recommend "
+                                                         "(the in-library multi-GPU path a Go host would call)")
     ap.add_argument("--items", type=int, default=0, help="override the catalog size (e.g. c5's per-GPU shard shape on fewer GPUs)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -413,6 +486,8 @@ def main():
                      "inputs larger than L2 (2.2 GB of feature tables + 1.28 GB of item fields, random rows)"),
               "request_batches_rotated": N_ROT}
 
+    if args.group:
+        return main_group(args, w, config)
     if args.impl == "reference":
         if rank != 0:
             return
