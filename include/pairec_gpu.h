@@ -257,6 +257,13 @@ int prg_recommend(prg_handle* h, const float* q, int B, int recall_k, int model,
 int prg_recommend_ex(prg_handle* h, const float* q, int B, int recall_k, int model, const prg_dpp_params* p,
                      const prg_user_features* user, uint32_t* out_row, double* out_score, int32_t* out_n, int mem);
 
+/* General (pre-)rank inside the fused path (service/general_rank/base_general_rank.go:66-109: GeneralRankConfs[scene] =
+ * {RankConf, ActionConfs}): the whole recall set is scored by `model` (normally the cheap PRG_MODEL_FM), sorted, and the
+ * Action keeps the best `keep` candidates per request (:183); only those reach the rank model of the call, the score
+ * sort and DPP.  Everything stays on the device.  keep == 0 (default) or keep >= recall_k: no pre-rank stage.  Applies to
+ * prg_recommend*, prg_recommend_from_keys*, the batcher and prg_group_recommend on this handle. */
+int prg_set_prerank(prg_handle* h, int model, int keep);
+
 /* Row-sharded variant: keys_dev points at this rank's slice of the all-gathered per-shard top-k keys —
  * G lists of B x k keys, list g at keys_dev + g*g_stride (u64 elements) — which are merged (same total order, so the
  * result is replica-identical) and then ranked / sorted / DPP-re-ranked as in prg_recommend.  Feature, field and

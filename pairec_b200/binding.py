@@ -25,7 +25,7 @@ EXPORTS = [
     "prg_batcher_start", "prg_batcher_recommend", "prg_batcher_stats", "prg_batcher_stop", "prg_batcher_drive",
     "prg_set_user_fields", "prg_set_rank_score", "prg_rank_ex", "prg_recommend_ex", "prg_recommend_from_keys_ex",
     "prg_batcher_recommend_ex", "prg_item_dim", "prg_dpp_ex",
-    "prg_group_create", "prg_group_size", "prg_group_recommend", "prg_group_destroy",
+    "prg_set_prerank", "prg_group_create", "prg_group_size", "prg_group_recommend", "prg_group_destroy",
 ]
 
 
@@ -213,6 +213,10 @@ class Engine:
         """User fields use feature tables n_fields .. n_fields + n_user_fields - 1; call before set_mlp."""
         self._ck(self._lib.prg_set_user_fields(self._h, C.c_uint32(n_user_fields), C.c_uint32(n_user_dense)))
         self.n_user_fields, self.n_user_dense = n_user_fields, n_user_dense
+
+    def set_prerank(self, model, keep):
+        """General (pre-)rank stage of the fused path: `model` scores the recall set, the best `keep` go on (0 = off)."""
+        self._ck(self._lib.prg_set_prerank(self._h, C.c_int(model), C.c_int(keep)))
 
     def set_rank_score(self, coef):
         c = _np(coef, np.float64)

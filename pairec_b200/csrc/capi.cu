@@ -190,7 +190,7 @@ void prg_destroy(prg_handle* h) {
     }
     DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->row_norm, &h->E16, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
                       &h->out_row, &h->out_score, &h->out_n, &h->flags, &h->table_ptrs, &h->act[0], &h->act[1],
-                      &h->fm_logit, &h->rank_rows, &h->rank_out, &h->mlp_Wu, &h->user_ids_dev, &h->user_dense_dev, &h->fm_state, &h->ubias, &h->rank_map, &h->D_sub, &h->D_sub_inv, &h->dpp_hook_E, &h->dpp_hook_rows, &h->dpp_hook_in, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
+                      &h->fm_logit, &h->rank_rows, &h->rank_out, &h->mlp_Wu, &h->user_ids_dev, &h->user_dense_dev, &h->fm_state, &h->ubias, &h->rank_map, &h->pre_rows, &h->D_sub, &h->D_sub_inv, &h->dpp_hook_E, &h->dpp_hook_rows, &h->dpp_hook_in, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
                       &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->ssd_E, &h->ssd_P, &h->sort_in, &h->sort_perm, &h->rec_rows,
                       &h->rec_scores, &h->rec_perm, &h->rec_sorted_rows, &h->rec_sorted_scores};
     for (DevBuf* b : bufs) b->release();

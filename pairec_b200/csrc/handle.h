@@ -166,6 +166,8 @@ struct prg_handle {
   prg::DevBuf sort_in, sort_perm;
 
   // ---- fused path
+  int prerank_model = 0, prerank_keep = 0;   // prg_set_prerank: general (pre-)rank stage of the fused path (0 = none)
+  prg::DevBuf pre_rows;                      // [B][keep] rows that survive the pre-rank Action
   prg::DevBuf rec_rows, rec_scores, rec_perm, rec_sorted_rows, rec_sorted_scores;
 };
 

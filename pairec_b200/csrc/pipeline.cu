@@ -56,7 +56,7 @@ static int adopt(const void* src, size_t bytes, int mem, const void** dst, bool*
 // nulls = every user feature absent (service/rank/algo_data.go:104-118 with an empty user map).
 static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int B, int n, double* score_dev,
                        const uint64_t* keys_dev = nullptr, const prg_user_features* user = nullptr,
-                       double* map_dev = nullptr) {
+                       double* map_dev = nullptr, bool reuse_prefix = false) {
   if (model != PRG_MODEL_FM && model != PRG_MODEL_MLP && model != PRG_MODEL_FM_MLP)
     return fail(PRG_EINVAL, "unknown rank model");
   const int M = B * n;
@@ -76,7 +76,7 @@ static int rank_device(prg_handle* h, int model, const uint32_t* rows_dev, int B
     PRG_TRY(h->act[1].ensure(mlp_act_bytes(h, M)));
     x = (uint16_t*)h->act[0].p;
   }
-  if (has_user) {
+  if (has_user && !reuse_prefix) {   // reuse_prefix: an earlier rank of the same batch left fm_state / ubias in place
     if (h->prefix_ahead) {   // the fused path launched it on the side stream before the recall: join here
       h->prefix_ahead = false;
       PRG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
@@ -148,7 +148,8 @@ static int recommend_device(prg_handle* h, const float* q_dev, int B, int k, int
   // the user prefix depends on the request only: it runs on the side stream while the recall streams the item index
   if (h->n_user_fields + h->n_user_dense > 0 && (model == PRG_MODEL_FM || h->mlp_layers > 0) &&
       (model == PRG_MODEL_FM || h->mlp_k_user == h->n_user_fields * 16 + h->n_user_dense))
-    PRG_TRY(user_prefix_device(h, user.ids, user.dense, B, model != PRG_MODEL_FM, /*ahead=*/true));
+    PRG_TRY(user_prefix_device(h, user.ids, user.dense, B,
+                               model != PRG_MODEL_FM || (h->prerank_keep > 0 && h->prerank_model != PRG_MODEL_FM), /*ahead=*/true));
   {
     const int rc = recall_topk_device(h, q_dev, B, k, (uint64_t*)h->topk_keys.p, /*defer=*/true);
     if (rc != PRG_OK) { h->prefix_ahead = false; return rc; }   // nobody will join the side stream for this batch
@@ -175,22 +176,47 @@ int post_recall_device(prg_handle* h, int B, int k, int model, const prg_dpp_par
   PRG_TRY(h->dpp_idx.ensure((size_t)B * p.top_n * 4));
   PRG_TRY(h->dpp_n.ensure((size_t)B * 4));
   PRG_TRY(h->dpp_status.ensure((size_t)B * 4));
-  // 2. gather + rank (the gather unpacks the recall keys into rec_rows on the way)
-  PRG_TRY(rank_device(h, model, (const uint32_t*)h->rec_rows.p, B, k, (double*)h->rec_scores.p, (const uint64_t*)h->topk_keys.p,
-                      &user));
-  // 3. ItemRankScore sort; the sort writes the sorted list for DPP itself
-  PRG_TRY(sort_desc_device(h, (const double*)h->rec_scores.p, B, k, (int32_t*)h->rec_perm.p, (const uint32_t*)h->rec_rows.p,
-                           (uint32_t*)h->rec_sorted_rows.p, (double*)h->rec_sorted_scores.p));
+  int n = k;   // candidates per request that reach rank / sort / DPP
+  if (h->prerank_keep > 0 && h->prerank_keep < k) {
+    // General (pre-)rank, device resident (service/general_rank/base_general_rank.go:66-109): a cheaper model scores the
+    // whole recall set, the Action keeps its best `keep` (:183, ActionType sort + truncation), and only those reach the
+    // full rank model — no host round trip between the two ranks.  Both ranks need the user prefix: tower share included
+    // when either model has a tower.
+    const int keep = h->prerank_keep;
+    PRG_TRY(h->pre_rows.ensure((size_t)B * keep * 4));
+    const bool need_mlp_any = h->prerank_model != PRG_MODEL_FM || model != PRG_MODEL_FM;
+    if (h->n_user_fields + h->n_user_dense > 0 && !h->prefix_ahead)
+      PRG_TRY(user_prefix_device(h, user.ids, user.dense, B, need_mlp_any && h->mlp_layers > 0, /*ahead=*/false));
+    else if (h->prefix_ahead) { h->prefix_ahead = false; PRG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0)); }
+    PRG_TRY(rank_device(h, h->prerank_model, (const uint32_t*)h->rec_rows.p, B, k, (double*)h->rec_scores.p,
+                        (const uint64_t*)h->topk_keys.p, &user, nullptr, /*reuse_prefix=*/true));
+    PRG_TRY(sort_desc_device(h, (const double*)h->rec_scores.p, B, k, (int32_t*)h->rec_perm.p, (const uint32_t*)h->rec_rows.p,
+                             (uint32_t*)h->rec_sorted_rows.p, (double*)h->rec_sorted_scores.p));
+    PRG_CUDA(cudaMemcpy2DAsync(h->pre_rows.p, (size_t)keep * 4, h->rec_sorted_rows.p, (size_t)k * 4, (size_t)keep * 4, (size_t)B,
+                               cudaMemcpyDeviceToDevice, h->stream));
+    n = keep;
+    PRG_TRY(rank_device(h, model, (const uint32_t*)h->pre_rows.p, B, n, (double*)h->rec_scores.p, nullptr, &user, nullptr,
+                        /*reuse_prefix=*/true));
+    PRG_TRY(sort_desc_device(h, (const double*)h->rec_scores.p, B, n, (int32_t*)h->rec_perm.p, (const uint32_t*)h->pre_rows.p,
+                             (uint32_t*)h->rec_sorted_rows.p, (double*)h->rec_sorted_scores.p));
+  } else {
+    // 2. gather + rank (the gather unpacks the recall keys into rec_rows on the way)
+    PRG_TRY(rank_device(h, model, (const uint32_t*)h->rec_rows.p, B, k, (double*)h->rec_scores.p, (const uint64_t*)h->topk_keys.p,
+                        &user));
+    // 3. ItemRankScore sort; the sort writes the sorted list for DPP itself
+    PRG_TRY(sort_desc_device(h, (const double*)h->rec_scores.p, B, k, (int32_t*)h->rec_perm.p, (const uint32_t*)h->rec_rows.p,
+                             (uint32_t*)h->rec_sorted_rows.p, (double*)h->rec_sorted_scores.p));
+  }
   // 4. DPP; the cluster kernel writes the final outputs itself, the other kernels leave them to final_gather_kernel
   DppFinal fin;
   fin.row = out_row; fin.score = out_score; fin.n = out_n;
-  PRG_TRY(dpp_device(h, (const uint32_t*)h->rec_sorted_rows.p, (const double*)h->rec_sorted_scores.p, B, k, p,
+  PRG_TRY(dpp_device(h, (const uint32_t*)h->rec_sorted_rows.p, (const double*)h->rec_sorted_scores.p, B, n, p,
                      (int32_t*)h->dpp_idx.p, (int32_t*)h->dpp_n.p, (int32_t*)h->dpp_status.p, &fin));
   if (fin.done) return PRG_OK;
   const int tot = B * p.top_n;
   PRG_CUDA(launch_chained(h, final_gather_kernel, dim3((tot + 255) / 256), dim3(256), 0, 1,
                           (const uint32_t*)h->rec_sorted_rows.p, (const double*)h->rec_sorted_scores.p,
-                          (const int32_t*)h->dpp_idx.p, (const int32_t*)h->dpp_n.p, (const int32_t*)h->dpp_status.p, B, k,
+                          (const int32_t*)h->dpp_idx.p, (const int32_t*)h->dpp_n.p, (const int32_t*)h->dpp_status.p, B, n,
                           p.top_n, out_row, out_score, out_n));
   count_launch(h);
   return PRG_OK;
@@ -354,6 +380,16 @@ int prg_set_user_fields(prg_handle* h, uint32_t n_user_fields, uint32_t n_user_d
   if (n_user_fields != h->n_user_fields || n_user_dense != h->n_user_dense) h->mlp_layers = 0;   // prg_set_mlp splits W1 by these
   h->n_user_fields = n_user_fields;
   h->n_user_dense = n_user_dense;
+  return PRG_OK;
+}
+
+int prg_set_prerank(prg_handle* h, int model, int keep) {
+  if (!h) return fail(PRG_EINVAL, "null handle");
+  if (keep < 0 || (keep > 0 && model != PRG_MODEL_FM && model != PRG_MODEL_MLP && model != PRG_MODEL_FM_MLP))
+    return fail(PRG_EINVAL, "bad pre-rank model / keep");
+  DevGuard g(h);
+  h->prerank_model = model;
+  h->prerank_keep = keep;
   return PRG_OK;
 }
 

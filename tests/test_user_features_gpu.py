@@ -183,3 +183,45 @@ def test_fused_path_and_batcher_carry_user_features(oracle_lib):
             bt.close()
     finally:
         eng.close()
+
+
+def test_device_resident_prerank_equals_staged_calls(oracle_lib):
+    """general (pre-)rank with Action truncation (service/general_rank/base_general_rank.go:66-109,183) as a
+    stage of the fused path: FM over the whole recall set, the best 150 go to the DeepFM-shaped rank, sort, DPP."""
+    from pairec_b200 import DppParams
+    from pairec_b200.binding import MODEL_FM, MODEL_FM_MLP
+    F, U, nd = 8, 2, 0
+    dims = [(F + U) * 16, 128, 64, 1]
+    n_items = 300_000
+    eng, fields, factors, linear, W, b = _setup(F, U, nd, dims, n_items=n_items)
+    try:
+        rng = np.random.default_rng(5)
+        E = (rng.standard_normal((n_items, 64)) / 8).astype(np.float32)
+        eng.set_item_matrix(E)
+        eng.set_diversity_matrix(synth.diversity(n_items=n_items, dim=128))
+        B, k, keep, T = 5, 600, 150, 20
+        Q = (rng.standard_normal((B, 64)) / 8).astype(np.float32)
+        ids, _ = _users(rng, B, U, factors, F, 0)
+        p = DppParams(top_n=T, alpha=1.0, window_size=10)
+        eng.set_prerank(MODEL_FM, keep)
+        rows, scores, n = eng.recommend(Q, k, MODEL_FM_MLP, p, user_ids=ids)
+        eng.set_prerank(MODEL_FM, 0)                                   # staged calls without the stage
+        rr, _, _ = eng.recall_topk(Q, k)
+        pre = eng.rank(MODEL_FM, rr, user_ids=ids)
+        perm = eng.sort_desc(pre)
+        kept = np.ascontiguousarray(np.take_along_axis(rr, perm, axis=1)[:, :keep])
+        rs = eng.rank(MODEL_FM_MLP, kept, user_ids=ids)
+        perm2 = eng.sort_desc(rs)
+        srows = np.take_along_axis(kept, perm2, axis=1)
+        sscore = np.take_along_axis(rs, perm2, axis=1)
+        idx, cnt, st = eng.dpp(srows, sscore, p)
+        for bi in range(B):
+            assert n[bi] == cnt[bi] == T
+            assert (rows[bi] == srows[bi][idx[bi]]).all() and (scores[bi] == sscore[bi][idx[bi]]).all()
+        # the pre-rank order is the oracle's: FM scores bit-exact, stable order
+        logit, _ = oracle_lib.gather_fm(fields, factors, linear, 0.03, rr[0], want_x=False, user_ids=ids[0])
+        want = oracle_lib.sigmoid(logit).astype(np.float64)
+        assert (pre[0].view(np.uint64) == want.view(np.uint64)).all()
+        assert (perm[0] == oracle_lib.stable_sort_desc(want)).all()
+    finally:
+        eng.close()
