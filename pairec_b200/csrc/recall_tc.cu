@@ -102,6 +102,12 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   constexpr int kStageB = tc_stage_bytes<DIM, BF>();
   constexpr int kQBytes = DIM * kQB * (BF ? 2 : 4);        // one query block as a B operand
   constexpr int NBUF = NQB <= 2 ? 2 : 1;                   // accumulator buffers (128 TMEM columns per block and buffer)
+  // NQB = 4 fills all 512 TMEM columns with ONE tile's accumulators (256 rows x 256 queries), so whole tiles cannot be
+  // double buffered.  The two 128-row HALVES of a tile are independent though (own MMAs, own TMEM columns, own four
+  // epilogue warps): with one full / empty barrier pair per half the MMAs of a half run while the other half is being
+  // read, and the next tile's first half starts as soon as its four warps are through.  Measured before (C5 shard shape,
+  // 12.5 M x 128, 256 queries per pass): 1.10 ms per pass = MMA (2 x 1024 clk) + TMEM read (4096 clk) per tile back to back.
+  constexpr bool kHalfBars = NBUF == 1 && BF;              // (bf16 index: one stage per tile)
   constexpr uint32_t kTmemCols = NQB == 1 ? 256 : 512;
   constexpr int QTOT = NQB * kQB;
   constexpr float kMargin = BF ? kTcMarginBf16 : kTcMarginTf32;
@@ -135,7 +141,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     s_cmax = 0u;
     tma_prefetch_desc(&emap);
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kTcEpiWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kHalfBars ? kTcEpiWarps / 2 : kTcEpiWarps); }
     mbar_fence_init();
   }
   const uint32_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -245,6 +251,33 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       constexpr int kSubs = BF ? DIM / 64 : 2;           // 128-B-wide sub-tiles per stage
       const uint32_t qb_addr = smem_u32(Qb);
       uint32_t it = 0;
+      if constexpr (kHalfBars) {
+        for (uint32_t i = 0; i < my_tiles; ++i, ++it) {
+          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st_addr = smem_u32(stage_base + (size_t)s * kStageB);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(&tempty[half], (i & 1u) ^ 1u);        // this half's four epilogue warps have drained the previous tile
+            tc_fence_after();
+#pragma unroll
+            for (int blk = 0; blk < NQB; ++blk) {
+              const uint32_t d_addr = tmem_base + (uint32_t)blk * 128u + (uint32_t)half * 64u;
+#pragma unroll
+              for (int sub = 0; sub < kSubs; ++sub) {
+                const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kTileRows * 128) + (uint32_t)half * (128 * 128));
+                const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)blk * kQBytes + (uint32_t)sub * (kQB * 128));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (sub | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&tfull[half]);
+          }
+          umma_commit(&empty[s]);
+        }
+      } else {
       for (uint32_t i = 0; i < my_tiles; ++i) {
         const uint32_t buf = (NBUF == 2) ? (i & 1u) : 0u;
         const uint32_t use = (NBUF == 2) ? (i >> 1) : i;  // how often this buffer has been used before
@@ -280,6 +313,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
         }
         umma_commit(&tfull[buf]);
       }
+      }
     }
   } else {
     // ---------------------------------------------------------------- epilogue: 8 warps, 256 rows
@@ -296,12 +330,13 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     auto run = [&](auto scaled_tag) {
     constexpr bool kScaled = decltype(scaled_tag)::value;
     for (uint32_t i = 0; i < my_tiles; ++i) {
-      const uint32_t buf = (NBUF == 2) ? (i & 1u) : 0u;
+      const uint32_t buf = (NBUF == 2) ? (i & 1u) : 0u;          // TMEM buffer (column offset)
       const uint32_t use = (NBUF == 2) ? (i >> 1) : i;
+      const uint32_t bar = kHalfBars ? (uint32_t)half : buf;     // barrier pair: per half-tile, or per buffer
       const uint64_t lrow = tile_row(i);
       const bool valid = lrow < p.n_rows;
       const uint32_t grow = (uint32_t)(p.row_base + lrow);
-      mbar_wait(&tfull[buf], use & 1u);
+      mbar_wait(&tfull[bar], use & 1u);
       tc_fence_after();
       // The norms landed before the tile's `full` barrier completed, which the MMA thread observed before it issued the
       // MMAs whose commit completes `tfull`: reading them after the tfull wait is ordered behind the copy.  (Waiting on
@@ -319,7 +354,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
         if (blk == NQB - 1) {  // last accumulator read of this tile: the MMA warp may overwrite the buffer
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[buf]);
+          if (lane == 0) mbar_arrive(&tempty[bar]);
         }
         const int nqb = p.nq - blk * kQB;  // queries of this block (may exceed 64; <= 0 for an unused block)
         uint32_t* scb = s_cnt + blk * kQB;
