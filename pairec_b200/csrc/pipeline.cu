@@ -508,7 +508,15 @@ int prg_recommend_from_keys_ex(prg_handle* h, const uint64_t* keys_dev, int G, u
   prg_user_features udev;
   PRG_TRY(stage_user(h, user, B, mem, &udev));
   PRG_TRY(h->topk_keys.ensure((size_t)B * k * 8));
-  PRG_TRY(merge_keys_device(h, keys_dev, G, g_stride, B, k, (uint64_t*)h->topk_keys.p));
+  // the user prefix runs on the side stream beside the merge of the G lists (it depends on the request only)
+  if (h->n_user_fields + h->n_user_dense > 0 && (model == PRG_MODEL_FM || h->mlp_layers > 0) &&
+      (model == PRG_MODEL_FM || h->mlp_k_user == h->n_user_fields * 16 + h->n_user_dense))
+    PRG_TRY(user_prefix_device(h, udev.ids, udev.dense, B,
+                               model != PRG_MODEL_FM || (h->prerank_keep > 0 && h->prerank_model != PRG_MODEL_FM), /*ahead=*/true));
+  {
+    const int rc = merge_keys_device(h, keys_dev, G, g_stride, B, k, (uint64_t*)h->topk_keys.p);
+    if (rc != PRG_OK) { h->prefix_ahead = false; return rc; }
+  }
   if (mem == PRG_MEM_DEVICE) return post_recall_device(h, B, k, model, *p, out_row, out_score, out_n, udev);
   const size_t TT = (size_t)B * p->top_n;
   PRG_TRY(h->out_row.ensure(TT * 4 > (size_t)B * k * 4 ? TT * 4 : (size_t)B * k * 4));
