@@ -141,6 +141,11 @@ int prg_group::run_dev(int g) {
     if (has_dense) PRG_CUDA(cudaMemcpyAsync(d.udense.p, udense_host, (size_t)Bg * nd * 4, cudaMemcpyHostToDevice, st));
     PRG_CUDA(cudaMemsetAsync(d.cand_in.p, 0, (size_t)G * blk * 8, st));
     PRG_CUDA(cudaMemsetAsync(d.retry.p, 0, 8, st));
+    // the user prefix of this GPU's own B requests runs on the side stream beside the whole recall (joined in phase 3)
+    if (U + nd > 0 && (model == PRG_MODEL_FM || (h->mlp_layers > 0 && h->mlp_k_user == U * 16 + nd)))
+      PRG_TRY(user_prefix_device(h, has_uid ? (const uint32_t*)d.uid.p + (size_t)g * B * U : nullptr,
+                                 has_dense ? (const float*)d.udense.p + (size_t)g * B * nd : nullptr, B,
+                                 model != PRG_MODEL_FM || (h->prerank_keep > 0 && h->prerank_model != PRG_MODEL_FM), /*ahead=*/true));
     if (!exact) {   // sample keys of this shard -> slot g of every GPU's gather buffer
       PRG_TRY(recall_shard_sample_device(h, q_dev, Bg, k, G, (uint64_t*)d.samp_local.p));
       const size_t n16 = (size_t)Bg * r * 8 / 16;
@@ -223,7 +228,9 @@ void prg_group::worker(int g) {
     {
       std::lock_guard<std::mutex> hl(d.h->mu);   // calls on the member handle from elsewhere wait for the batch
       d.h->pending.active = false;
+      d.h->prefix_ahead = false;
       rc = run_dev(g);
+      if (rc != PRG_OK) d.h->prefix_ahead = false;   // nobody will join the side stream for this batch
       if (rc != PRG_OK && d.err.empty()) d.err = prg_last_error();
     }
     d.rc = rc;

@@ -253,6 +253,9 @@ int recommend_begin(prg_handle* h, const float* q_pinned, int B, int recall_k, i
                     const prg_user_features* user_pinned, uint32_t* out_row, double* out_score, int32_t* out_n,
                     cudaEvent_t done, uint64_t* seq);
 int recommend_end(prg_handle* h, uint64_t seq, cudaEvent_t done);
+// gather_fm.cu: a batch's user prefix (FM running sums after the user fields + the user share of the tower's first layer);
+// ahead = on the handle's side stream, joined by the next rank of the batch (pipeline.cu rank_device)
+int user_prefix_device(prg_handle* h, const uint32_t* user_ids_dev, const float* user_dense_dev, int B, bool need_mlp, bool ahead);
 int keys_to_outputs(prg_handle* h, const uint64_t* keys_dev, int B, int k, uint32_t* out_row, float* out_score,
                     int32_t* out_n);
 int shard_sample_len(int k);
