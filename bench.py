@@ -457,7 +457,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("PRG_WORKLOAD", "c4"), choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-requests", type=int, default=8, help="requests per step of the CPU arm (bounded sample)")
+    ap.add_argument("--cpu-requests", type=int, default=0,
+                    help="requests per step of the CPU arm (0 = the workload's whole batch; a smaller bounded sample "
+                         "under-uses the cache reuse of the CPU recall across queries)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batcher", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed N>1 parity checks")
@@ -468,6 +470,8 @@ def main():
     w = dict(WORKLOADS[args.workload])
     if args.items:
         w["items"] = args.items
+    if args.cpu_requests <= 0:
+        args.cpu_requests = min(w["batch"], 64)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
