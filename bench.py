@@ -481,10 +481,12 @@ def main():
         raise SystemExit("c2 / c3 are single-GPU workloads (parity-test configs)")
     config = {"workload": describe(args.workload, w),
               "batch_per_gpu": w["batch"], "global_batch": w["batch"] * world,
-              "sharding": ("item matrix row-sharded; " + ("all-gather of per-shard top-k keys"
-                           if os.environ.get("PRG_SHARD_PROTOCOL", "global") == "local" else
-                           "global threshold: all-gather of per-shard sample keys, then all-gather of the candidates "
-                           "that reach it") if world > 1 else "none"),
+              "sharding": ("item matrix row-sharded; " + {"local": "all-gather of per-shard top-k keys",
+                           "global": "global threshold: all-gather of per-shard sample keys, then all-gather of the "
+                                     "candidates that reach it",
+                           "a2a": "global threshold: all-gather of per-shard sample keys, then ONE all-to-all of the candidates "
+                                  "that reach it (a rank receives its own requests' lists only)"}[
+                               os.environ.get("PRG_SHARD_PROTOCOL", "a2a")] if world > 1 else "none"),
               "l2": (f"inputs larger than L2 (item matrix / its {w['items'] // world * w['dim'] * 2 / 1e9:.2f} GB bf16 filter "
                      f"index streamed per step)" if kind != "fm" else
                      "inputs larger than L2 (2.2 GB of feature tables + 1.28 GB of item fields, random rows)"),
@@ -560,7 +562,9 @@ def main():
         out_rows = torch.empty(B, Tn, dtype=torch.int32, device=dev)
         out_scores = torch.empty(B, Tn, dtype=torch.float64, device=dev)
         out_n = torch.empty(B, dtype=torch.int32, device=dev)
-        protocol = os.environ.get("PRG_SHARD_PROTOCOL", "global")   # "global": one threshold per query across shards
+        # "a2a" (default): one global threshold per query, candidates exchanged with ONE all-to-all (each rank receives only
+        # its own requests' lists); "global": the same with an all-gather of everything; "local": exact per-shard top-k lists
+        protocol = os.environ.get("PRG_SHARD_PROTOCOL", "a2a")
         if world > 1 and protocol == "local":
             keys_local = torch.empty(Bg, k, dtype=torch.int64, device=dev)
             keys_all = torch.empty(world, Bg, k, dtype=torch.int64, device=dev)
@@ -570,8 +574,13 @@ def main():
             samp_all = torch.empty(world, Bg, r_s, dtype=torch.int64, device=dev)
             blk = Bg * k + Bg                                        # per rank: Bg x k keys + Bg status words
             cand_local = torch.empty(blk, dtype=torch.int64, device=dev)
-            cand_all = torch.empty(world, blk, dtype=torch.int64, device=dev)
             retry = torch.zeros(2, dtype=torch.int32, device=dev)
+            if protocol == "a2a":
+                chunk = B * k + B                                    # what one rank needs of one shard: its B lists + B status words
+                cand_packed = torch.empty(world, chunk, dtype=torch.int64, device=dev)
+                cand_recv = torch.empty(world, chunk, dtype=torch.int64, device=dev)
+            else:
+                cand_all = torch.empty(world, blk, dtype=torch.int64, device=dev)
 
         def step_local_protocol(i, rows_t, scores_t, n_t):
             Qg = Qs[i % N_ROT]
@@ -593,12 +602,21 @@ def main():
                 with torch.cuda.stream(stream):
                     dist.all_gather_into_tensor(samp_all, samp_local)          # exchange 1: G x Bg x r sample keys
                 eng.shard_candidates_dev(Qg.data_ptr(), Bg, k, world, samp_all.data_ptr(), cand_local.data_ptr())
-                with torch.cuda.stream(stream):
-                    dist.all_gather_into_tensor(cand_all, cand_local)          # exchange 2: candidates that reach tau
-                eng.shard_check_dev(cand_all.data_ptr(), world, Bg, k, retry.data_ptr())
-                eng.recommend_from_keys_dev(cand_all.data_ptr() + rank * B * k * 8, world, blk, B, k, MODEL_FM_MLP, p,
-                                            out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr(),
-                                            user_ids_ptr=uptr(i % N_ROT))
+                if protocol == "a2a":
+                    eng.shard_pack_owner_dev(cand_local.data_ptr(), Bg, B, k, cand_packed.data_ptr())
+                    with torch.cuda.stream(stream):
+                        dist.all_to_all_single(cand_recv, cand_packed)         # exchange 2: each rank gets ITS requests' lists
+                    eng.shard_check_owner_dev(cand_recv.data_ptr(), world, B, k, rank * B, retry.data_ptr())
+                    eng.recommend_from_keys_dev(cand_recv.data_ptr(), world, chunk, B, k, MODEL_FM_MLP, p,
+                                                out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr(),
+                                                user_ids_ptr=uptr(i % N_ROT))
+                else:
+                    with torch.cuda.stream(stream):
+                        dist.all_gather_into_tensor(cand_all, cand_local)      # exchange 2: candidates that reach tau
+                    eng.shard_check_dev(cand_all.data_ptr(), world, Bg, k, retry.data_ptr())
+                    eng.recommend_from_keys_dev(cand_all.data_ptr() + rank * B * k * 8, world, blk, B, k, MODEL_FM_MLP, p,
+                                                out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr(),
+                                                user_ids_ptr=uptr(i % N_ROT))
 
     def sync_all():
         eng.sync()
@@ -762,15 +780,18 @@ def main():
     shard_retries = None
     verify = None
     if world > 1 and kind == "full":
-        if protocol == "global":
+        if protocol in ("global", "a2a"):
             eng.sync()
-            shard_retries = int(retry.cpu()[1].item())   # queries that asked for the exact protocol (expected: 0)
+            rt = retry.clone()
+            if protocol == "a2a":   # the check ran per owner: the ranks' counts add up
+                dist.all_reduce(rt, op=dist.ReduceOp.SUM)
+            shard_retries = int(rt.cpu()[1].item())   # queries that asked for the exact protocol (expected: 0)
         if not args.no_verify:
             step_device(0)
             eng.sync()
             got = (out_rows.clone(), out_scores.clone(), out_n.clone())
             verify = {}
-            if protocol == "global":
+            if protocol in ("global", "a2a"):
                 keys_local = torch.empty(Bg, k, dtype=torch.int64, device=dev)
                 keys_all = torch.empty(world, Bg, k, dtype=torch.int64, device=dev)
                 a_rows, a_sc, a_n = torch.empty_like(got[0]), torch.empty_like(got[1]), torch.empty_like(got[2])

@@ -165,6 +165,14 @@ int prg_shard_sample(prg_handle* h, const float* q_dev, int Bg, int k, int G, ui
 int prg_shard_candidates(prg_handle* h, const float* q_dev, int Bg, int k, int G, const uint64_t* all_samples_dev,
                          uint64_t* out_keys_dev);
 int prg_shard_check(prg_handle* h, const uint64_t* gathered_dev, int G, int Bg, int k, int32_t* retry_dev);
+/* All-to-all form of exchange #2 (what bench.py uses at N > 1): a rank only ranks its OWN B = Bg / G queries
+ * [rank*B, rank*B + B), so it only needs their lists.  prg_shard_pack_owner regroups prg_shard_candidates' output into G
+ * chunks of [B*k keys | B status words] (chunk o = the part rank o needs); ONE ncclAllToAll (chunk size B*k + B) replaces
+ * the all-gather (G x less data received); prg_shard_check_owner runs the check on the received G chunks for the owned
+ * queries (q0 = rank*B) — the retry flag is then per rank, so the ranks agree on a redo through one integer all-reduce
+ * (or per batch of batches); prg_recommend_from_keys(_ex) merges the received chunks with g_stride = B*k + B. */
+int prg_shard_pack_owner(prg_handle* h, const uint64_t* cand_dev, int Bg, int B, int k, uint64_t* out_dev);
+int prg_shard_check_owner(prg_handle* h, const uint64_t* received_dev, int G, int B, int k, int q0, int32_t* retry_dev);
 /* Merge G gathered key lists (keys_dev: G x B x k, the all-gather output) into the global top-k. */
 int prg_merge_keys(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint32_t* out_row,
                    float* out_score, int32_t* out_n, int mem);

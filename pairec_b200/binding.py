@@ -25,7 +25,7 @@ EXPORTS = [
     "prg_batcher_start", "prg_batcher_recommend", "prg_batcher_stats", "prg_batcher_stop", "prg_batcher_drive",
     "prg_set_user_fields", "prg_set_rank_score", "prg_rank_ex", "prg_recommend_ex", "prg_recommend_from_keys_ex",
     "prg_batcher_recommend_ex", "prg_item_dim", "prg_dpp_ex",
-    "prg_set_prerank", "prg_group_create", "prg_group_size", "prg_group_recommend", "prg_group_destroy",
+    "prg_set_prerank", "prg_shard_pack_owner", "prg_shard_check_owner", "prg_group_create", "prg_group_size", "prg_group_recommend", "prg_group_destroy",
 ]
 
 
@@ -299,6 +299,13 @@ class Engine:
     def shard_check_dev(self, gathered_ptr, G, Bg, k, retry_ptr):
         self._ck(self._lib.prg_shard_check(self._h, _ptr(gathered_ptr), C.c_int(G), C.c_int(Bg), C.c_int(k),
                                            _ptr(retry_ptr)))
+
+    def shard_pack_owner_dev(self, cand_ptr, Bg, B, k, out_ptr):
+        self._ck(self._lib.prg_shard_pack_owner(self._h, _ptr(cand_ptr), C.c_int(Bg), C.c_int(B), C.c_int(k), _ptr(out_ptr)))
+
+    def shard_check_owner_dev(self, received_ptr, G, B, k, q0, retry_ptr):
+        self._ck(self._lib.prg_shard_check_owner(self._h, _ptr(received_ptr), C.c_int(G), C.c_int(B), C.c_int(k), C.c_int(q0),
+                                                 _ptr(retry_ptr)))
 
     def merge_keys(self, keys_ptr, G, B, k, rows=None, scores=None, n=None, mem=MEM_HOST):
         if mem == MEM_HOST:

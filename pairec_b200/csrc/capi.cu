@@ -392,6 +392,20 @@ int prg_shard_check(prg_handle* h, const uint64_t* gathered_dev, int G, int Bg, 
   return shard_check_device(h, gathered_dev, G, Bg, k, retry_dev);
 }
 
+int prg_shard_pack_owner(prg_handle* h, const uint64_t* cand_dev, int Bg, int B, int k, uint64_t* out_dev) {
+  CHECK_H(h);
+  if (!cand_dev || !out_dev || Bg <= 0 || k <= 0) return fail(PRG_EINVAL, "bad arguments");
+  Guard g(h);
+  return shard_pack_owner_device(h, cand_dev, Bg, B, k, out_dev);
+}
+
+int prg_shard_check_owner(prg_handle* h, const uint64_t* received_dev, int G, int B, int k, int q0, int32_t* retry_dev) {
+  CHECK_H(h);
+  if (!received_dev || !retry_dev || G <= 0 || B <= 0 || k <= 0 || q0 < 0) return fail(PRG_EINVAL, "bad arguments");
+  Guard g(h);
+  return shard_check_owner_device(h, received_dev, G, B, k, q0, retry_dev);
+}
+
 int prg_merge_keys(prg_handle* h, const uint64_t* keys_dev, int G, int B, int k, uint32_t* out_row, float* out_score,
                    int32_t* out_n, int mem) {
   CHECK_H(h);

@@ -265,6 +265,8 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
 // tau (nullable): thresholds of the Bg queries checked (default: the handle's, from recall_shard_candidates_device)
 int shard_check_device(prg_handle* h, const uint64_t* gathered, int G, int Bg, int k, int32_t* retry_dev,
                        const uint64_t* tau = nullptr);
+int shard_pack_owner_device(prg_handle* h, const uint64_t* in, int Bg, int B, int k, uint64_t* out);
+int shard_check_owner_device(prg_handle* h, const uint64_t* received, int G, int B, int k, int q0, int32_t* retry_dev);
 int merge_keys_device(prg_handle* h, const uint64_t* keys_dev, int G, uint64_t g_stride, int B, int k,
                       uint64_t* keys_out);
 }  // namespace prg

@@ -1516,21 +1516,22 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
 
 // phase 3 check, identical on every rank: gathered = G blocks of [Bg*k keys | Bg status words]; a query needs the exact
 // protocol if a shard reported an overflow or fewer than k gathered keys reach its tau.  retry[0] |= 1, retry[1] += count.
-__global__ void __launch_bounds__(128) shard_check_kernel(const uint64_t* __restrict__ gathered, int G, int Bg, int k,
-                                                          const uint64_t* __restrict__ tau, int32_t* __restrict__ retry) {
+__global__ void __launch_bounds__(128) shard_check_kernel(const uint64_t* __restrict__ keys, uint64_t key_stride,
+                                                          const uint64_t* __restrict__ status, uint64_t status_stride, int G,
+                                                          int Bq, int k, const uint64_t* __restrict__ tau,
+                                                          int32_t* __restrict__ retry) {
   // one WARP per query, lane g walks shard g's list: the G binary searches (dependent loads through L2) run side by side
-  // instead of one after the other in a single thread (46 us -> a few us at G = 8, Bg = 512)
+  // instead of one after the other in a single thread (46 us -> a few us at G = 8, Bg = 512).
+  // Shard g's lists: keys + g * key_stride ([Bq][k], sorted descending, 0-padded); its status words: status + g * status_stride.
   const int q = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-  if (q >= Bg) return;
-  const size_t blk = (size_t)Bg * k + Bg;
+  if (q >= Bq) return;
   const uint64_t t = tau[q];
   const uint64_t lim = t ? t : 1ull;
   bool bad = false;
   uint32_t reach = 0;
   for (int g = lane; g < G; g += 32) {
-    const uint64_t* base = gathered + (size_t)g * blk;
-    if (base[(size_t)Bg * k + q] != 0ull) bad = true;
-    const uint64_t* list = base + (size_t)q * k;   // sorted descending, 0-padded: count keys >= max(t, 1)
+    if (status[(size_t)g * status_stride + q] != 0ull) bad = true;
+    const uint64_t* list = keys + (size_t)g * key_stride + (size_t)q * k;   // count keys >= max(t, 1)
     int lo = 0, hi = k;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (list[mid] >= lim) lo = mid + 1; else hi = mid; }
     reach += (uint32_t)lo;
@@ -1543,7 +1544,40 @@ __global__ void __launch_bounds__(128) shard_check_kernel(const uint64_t* __rest
 
 int shard_check_device(prg_handle* h, const uint64_t* gathered, int G, int Bg, int k, int32_t* retry_dev, const uint64_t* tau) {
   if (!h->tau.p) return fail(PRG_ESTATE, "prg_shard_candidates has not run on this handle");
-  shard_check_kernel<<<(Bg + 3) / 4, 128, 0, h->stream>>>(gathered, G, Bg, k, tau ? tau : (const uint64_t*)h->tau.p, retry_dev);
+  const uint64_t blk = (uint64_t)Bg * k + Bg;
+  shard_check_kernel<<<(Bg + 3) / 4, 128, 0, h->stream>>>(gathered, blk, gathered + (size_t)Bg * k, blk, G, Bg, k,
+                                                         tau ? tau : (const uint64_t*)h->tau.p, retry_dev);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+// [Bg][k] lists + [Bg] status words (prg_shard_candidates' output) -> G owner-major chunks of [B][k] lists + [B] status words:
+// chunk o is what rank o needs of this shard (its own B queries), so ONE all-to-all moves B*k + B words per pair of ranks
+// instead of an all-gather of everything to everybody
+__global__ void shard_pack_owner_kernel(const uint64_t* __restrict__ in, int Bg, int B, int k, uint64_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t chunk = (size_t)B * k + B, total = (size_t)(Bg / B) * chunk;
+  if (i >= total) return;
+  const size_t o = i / chunk, r = i - o * chunk;
+  out[i] = r < (size_t)B * k ? in[o * (size_t)B * k + r] : in[(size_t)Bg * k + o * B + (r - (size_t)B * k)];
+}
+
+int shard_pack_owner_device(prg_handle* h, const uint64_t* in, int Bg, int B, int k, uint64_t* out) {
+  if (B <= 0 || Bg % B != 0) return fail(PRG_EINVAL, "Bg must be a multiple of B");
+  const size_t total = (size_t)Bg * k + Bg;
+  shard_pack_owner_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(in, Bg, B, k, out);
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+
+// the check for the B queries [q0, q0 + B) this rank owns, on what the all-to-all delivered: G chunks of [B*k | B]
+int shard_check_owner_device(prg_handle* h, const uint64_t* received, int G, int B, int k, int q0, int32_t* retry_dev) {
+  if (!h->tau.p) return fail(PRG_ESTATE, "prg_shard_candidates has not run on this handle");
+  const uint64_t blk = (uint64_t)B * k + B;
+  shard_check_kernel<<<(B + 3) / 4, 128, 0, h->stream>>>(received, blk, received + (size_t)B * k, blk, G, B, k,
+                                                        (const uint64_t*)h->tau.p + q0, retry_dev);
   PRG_CUDA(cudaGetLastError());
   count_launch(h);
   return PRG_OK;

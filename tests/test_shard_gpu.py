@@ -152,3 +152,75 @@ def test_global_threshold_protocol_flags_adversarial_order(oracle_lib):
     finally:
         for e in engs:
             e.close()
+
+
+def test_all_to_all_exchange_form_equals_unsharded_path(oracle_lib):
+    """Exchange #2 as ONE all-to-all (bench.py's default at N > 1): prg_shard_pack_owner regroups a shard's candidates into
+    per-owner chunks, each owner checks and merges only its own B requests (prg_shard_check_owner, g_stride = B*k + B).
+    Emulated on one GPU: chunk o of shard g lands in slot g of owner o's receive buffer."""
+    import torch
+    from pairec_b200 import DppParams, Engine
+    from pairec_b200.binding import MODEL_FM
+    G, d, B, k, T = 4, 64, 9, 300, 12
+    Bg = G * B
+    n = 1_200_000
+    rng = np.random.default_rng(61)
+    E = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    Q = (rng.standard_normal((Bg, d)) / np.sqrt(d)).astype(np.float32)
+    fields, factors, linear = synth.rank_tables(n_items=n, n_fields=6)
+    Dm = synth.diversity(n_items=n, dim=32)
+    dev = torch.device("cuda:0")
+    p = DppParams(top_n=T, alpha=1.0, window_size=10)
+
+    def load_rank(e):
+        e.set_item_fields(fields)
+        for t, (f, l) in enumerate(zip(factors, linear)):
+            e.set_feature_table(t, f, l)
+        e.set_fm_bias(0.05)
+        e.set_diversity_matrix(Dm)
+    ref = Engine(0)
+    ref.set_item_matrix(E)
+    load_rank(ref)
+    want = ref.recommend(Q, k, MODEL_FM, p)
+    ref.close()
+    bounds = [g * (n // G) for g in range(G)] + [n]
+    engs = [Engine(0) for _ in range(G)]
+    try:
+        for g, e in enumerate(engs):
+            e.set_item_matrix(E[bounds[g]:bounds[g + 1]], row_base=bounds[g])
+            load_rank(e)
+        r = engs[0].shard_sample_len(k)
+        q_dev = torch.from_numpy(Q).to(dev)
+        samples = torch.zeros(G, Bg, r, dtype=torch.int64, device=dev)
+        for g, e in enumerate(engs):
+            e.shard_sample_dev(q_dev.data_ptr(), Bg, k, G, samples[g].data_ptr())
+            e.sync()
+        chunk = B * k + B
+        recv = torch.zeros(G, G, chunk, dtype=torch.int64, device=dev)          # [owner][source shard][chunk]
+        for g, e in enumerate(engs):
+            cand = torch.zeros(Bg * k + Bg, dtype=torch.int64, device=dev)
+            packed = torch.zeros(G, chunk, dtype=torch.int64, device=dev)
+            e.shard_candidates_dev(q_dev.data_ptr(), Bg, k, G, samples.data_ptr(), cand.data_ptr())
+            e.shard_pack_owner_dev(cand.data_ptr(), Bg, B, k, packed.data_ptr())
+            e.sync()
+            # the pack is a pure regrouping of the lists and the status words
+            assert torch.equal(packed[:, :B * k].reshape(-1), cand[:Bg * k])
+            assert torch.equal(packed[:, B * k:].reshape(-1), cand[Bg * k:])
+            recv[:, g] = packed                                                  # the all-to-all
+        for o, e in enumerate(engs):
+            retry = torch.zeros(2, dtype=torch.int32, device=dev)
+            e.shard_check_owner_dev(recv[o].data_ptr(), G, B, k, o * B, retry.data_ptr())
+            out_rows = torch.empty(B, T, dtype=torch.int32, device=dev)
+            out_sc = torch.empty(B, T, dtype=torch.float64, device=dev)
+            out_n = torch.empty(B, dtype=torch.int32, device=dev)
+            e.recommend_from_keys_dev(recv[o].data_ptr(), G, chunk, B, k, MODEL_FM, p, out_rows.data_ptr(), out_sc.data_ptr(),
+                                      out_n.data_ptr())
+            e.sync()
+            assert retry.cpu().numpy().tolist() == [0, 0]
+            sl = slice(o * B, (o + 1) * B)
+            assert (out_rows.cpu().numpy().view(np.uint32) == want[0][sl]).all(), f"owner {o}: rows differ from the unsharded path"
+            assert (out_sc.cpu().numpy().view(np.uint64) == want[1][sl].view(np.uint64)).all()
+            assert (out_n.cpu().numpy() == want[2][sl]).all()
+    finally:
+        for e in engs:
+            e.close()
