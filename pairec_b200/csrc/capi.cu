@@ -157,6 +157,8 @@ int prg_init(const char* json_cfg, prg_handle** out) {
   if (const char* ev = getenv("PRG_SCAN128_NQB")) h->scan128_nqb = atoi(ev) != 0;
   if (json_int(json_cfg, "recall_tilemax", &v)) h->recall_tilemax = v != 0;
   if (const char* ev = getenv("PRG_RECALL_TILEMAX")) h->recall_tilemax = atoi(ev) != 0;
+  if (json_int(json_cfg, "scan_groups", &v)) h->scan_groups = v < 0 ? -1 : (v != 0);
+  if (const char* ev = getenv("PRG_SCAN_GROUPS")) h->scan_groups = atoi(ev) < 0 ? -1 : (atoi(ev) != 0);
   if (json_int(json_cfg, "dpp_pair", &v)) h->dpp_pair = v != 0;
   if (const char* ev = getenv("PRG_DPP_PAIR")) h->dpp_pair = atoi(ev) != 0;
   if (json_int(json_cfg, "mlp_no_pair", &v) && v != 0) h->mlp_no_pair = true;
@@ -188,7 +190,7 @@ void prg_destroy(prg_handle* h) {
         if (h->tables[t].linear) cudaFree(const_cast<float*>(h->tables[t].linear));
       }
     }
-    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->row_norm, &h->E16, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
+    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->grp_cnt, &h->row_norm, &h->E16, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
                       &h->out_row, &h->out_score, &h->out_n, &h->flags, &h->table_ptrs, &h->act[0], &h->act[1],
                       &h->fm_logit, &h->rank_rows, &h->rank_out, &h->mlp_Wu, &h->user_ids_dev, &h->user_dense_dev, &h->fm_state, &h->ubias, &h->rank_map, &h->pre_rows, &h->D_sub, &h->D_sub_inv, &h->dpp_hook_E, &h->dpp_hook_rows, &h->dpp_hook_in, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
                       &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->ssd_E, &h->ssd_P, &h->sort_in, &h->sort_perm, &h->rec_rows,
@@ -325,7 +327,7 @@ int prg_commit_item_matrix(prg_handle* h) {
   std::swap(h->E, s->E); std::swap(h->E_owned, s->E_owned); std::swap(h->E_rows, s->E_rows);
   std::swap(h->E_dim, s->E_dim); std::swap(h->E_row_base, s->E_row_base);
   std::swap(h->E_map, s->E_map); std::swap(h->E_map_ok, s->E_map_ok);
-  std::swap(h->E16, s->E16); std::swap(h->E16_map, s->E16_map); std::swap(h->E16_map_ok, s->E16_map_ok);
+  std::swap(h->E16, s->E16); std::swap(h->E16_map, s->E16_map); std::swap(h->E16_map_h, s->E16_map_h); std::swap(h->E16_map_ok, s->E16_map_ok);
   std::swap(h->row_norm, s->row_norm);
   free_snapshot(s);          // the previous snapshot
   return PRG_OK;

@@ -62,6 +62,8 @@ struct prg_handle {
   prg::DevBuf cand_keys;    // QB x cand_cap u64 (packed candidates)
   prg::DevBuf seg_keys;     // QB x n_seg x seg_cap u64 keys (FFMA2 scan) or u32 rows (tensor-core filter)
   prg::DevBuf seg_rows;     // QB x n_seg x seg_cap u32 survivor rows of the tensor-core filter
+  prg::DevBuf grp_cnt;      // GROUP mode of the filter: [groups of 16 queries][n_seg] u32 list lengths
+  int scan_groups = -1;     // config "scan_groups" (-1 = by dim, see recall.cu scan_groups_on): passes of more than 64 queries record survivors per (row, group of 16 queries) and the exact re-score resolves the queries; 0 = per (row, query) as for <= 64 queries
   prg::DevBuf row_norm;     // rows f32: upper bounds of the item row norms (tensor-core filter margin)
   bool scan128_nqb = true;      // config "scan128_nqb": up to 256 queries per filter pass at dim 128 (2-stage ring); 0 = 64 per pass
   bool recall_tilemax = true;   // config "recall_tilemax": threshold from per-tile maxima of the sample (0 = from sample keys)
@@ -69,6 +71,7 @@ struct prg_handle {
   int scan_filter = 0;      // config "scan_filter": 0 = bf16 shadow index (default), 1 = tf32 on the fp32 rows
   prg::DevBuf E16;          // rows x dim bf16: round-to-nearest shadow of the item matrix (bf16 filter operand)
   CUtensorMap E16_map;
+  CUtensorMap E16_map_h;    // the same index with boxes of half a tile (128 rows): stages of the 256-queries-per-pass filter
   bool E16_map_ok = false;
   prg::DevBuf cand_cnt;     // B u32
   prg::DevBuf tau;          // B u64

@@ -573,6 +573,102 @@ __global__ void __launch_bounds__(32) rescore_kernel(const uint32_t* __restrict_
   }
 }
 
+// GROUP mode of the tensor-core filter (ScanParams::grp_rows, passes of more than 64 queries): the filter recorded a
+// surviving row once per group of 16 queries.  One warp takes the list of one (group, filter CTA): rows are fetched
+// coalesced into the shared-memory tile as above, every lane then scores its row against the group's 16 queries — 16
+// independent fmaf chains of the arithmetic contract (dims ascending, one accumulator each) — and the keys that reach
+// the query's threshold are appended to the (query, CTA) segment the refine step reads (ballot + prefix count: the warp
+// owns those 16 segments).  Keys below tau are dropped here: every row whose exact key reaches tau is in the list
+// (filter guarantee), and the refine step's check needs nothing else.
+// A list that overflowed its capacity poisons the 16 segment counts (> seg_cap), which the refine step reports as an
+// overflow of those queries (dense redo).
+template <int DIM>
+__global__ void __launch_bounds__(32) rescore_group_kernel(const uint32_t* __restrict__ grp_rows, const uint32_t* __restrict__ grp_cnt,
+                                                           uint32_t n_seg, uint32_t grp_cap, uint32_t seg_cap, int nq,
+                                                           const float* __restrict__ E, const float* __restrict__ Q,
+                                                           uint64_t row_base, const uint64_t* __restrict__ tau,
+                                                           uint64_t* __restrict__ seg_keys, uint32_t* __restrict__ seg_cnt) {
+  pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
+  pdl_launch_dependents();
+  constexpr int F4 = DIM / 4;            // 16-B pieces per row
+  constexpr int RPI = 32 / F4;           // rows fetched per load instruction (2 at dim 64, 1 at dim 128)
+  constexpr int PITCH = DIM + 4;
+  constexpr int QP = DIM + 4;            // pitch of a staged query (floats)
+  __shared__ __align__(16) float tile[32 * PITCH];
+  __shared__ __align__(16) float qs[kGrpQ * QP];
+  const uint32_t seg = blockIdx.x, gi = blockIdx.y, lane = threadIdx.x;
+  const int q0 = (int)gi * kGrpQ;
+  const bool own_q = lane < (uint32_t)kGrpQ && q0 + (int)lane < nq;   // lane j < 16 keeps query q0 + j's threshold and count
+  const size_t my_seg = ((size_t)(q0 + (int)(lane & (kGrpQ - 1))) * n_seg + seg);
+  const uint32_t total = grp_cnt[(size_t)gi * n_seg + seg];
+  if (total > grp_cap) {
+    if (own_q) seg_cnt[my_seg] = 0xFFFFFFFFu;
+    return;
+  }
+  if (total == 0) {
+    if (own_q) seg_cnt[my_seg] = 0u;
+    return;
+  }
+  // a query slot past nq gets the impossible threshold: nothing is ever appended for it
+  const uint64_t my_tau = own_q ? tau[q0 + (int)lane] : ~0ull;
+  for (uint32_t i = lane; i < (uint32_t)(kGrpQ * DIM); i += 32) {
+    const uint32_t j = i / DIM, d = i - j * DIM;
+    qs[j * QP + d] = (q0 + (int)j < nq) ? Q[(size_t)(q0 + (int)j) * DIM + d] : 0.f;
+  }
+  const uint32_t* src = grp_rows + ((size_t)gi * n_seg + seg) * grp_cap;
+  const uint32_t sub = lane / F4, piece = lane % F4;
+  uint32_t cnt = 0;   // lane j: keys of query q0 + j so far
+  for (uint32_t base = 0; base < total; base += 32) {
+    const uint32_t n = total - base < 32 ? total - base : 32;
+    const uint32_t my_row = lane < n ? src[base + lane] : 0u;
+    __syncwarp();
+    float4 xv[32 / RPI];
+#pragma unroll
+    for (int r = 0; r < 32 / RPI; ++r) {
+      const uint32_t row_in_chunk = r * RPI + sub;
+      const uint32_t grow = __shfl_sync(0xffffffffu, my_row, row_in_chunk);
+      xv[r] = row_in_chunk < n ? __ldg(reinterpret_cast<const float4*>(E + ((size_t)grow - row_base) * DIM) + piece)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < 32 / RPI; ++r)
+      *reinterpret_cast<float4*>(&tile[(r * RPI + sub) * PITCH + piece * 4]) = xv[r];
+    __syncwarp();
+    float acc[kGrpQ];
+#pragma unroll
+    for (int j = 0; j < kGrpQ; ++j) acc[j] = 0.f;
+    const float4* x = reinterpret_cast<const float4*>(&tile[lane * PITCH]);
+#pragma unroll 4
+    for (int d4 = 0; d4 < F4; ++d4) {
+      const float4 v = x[d4];
+#pragma unroll
+      for (int j = 0; j < kGrpQ; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(&qs[j * QP + 4 * d4]);   // same address in every lane: broadcast
+        acc[j] = __fmaf_rn(v.x, w.x, acc[j]);
+        acc[j] = __fmaf_rn(v.y, w.y, acc[j]);
+        acc[j] = __fmaf_rn(v.z, w.z, acc[j]);
+        acc[j] = __fmaf_rn(v.w, w.w, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kGrpQ; ++j) {
+      const uint64_t key = make_key(acc[j], my_row);
+      const uint64_t tj = __shfl_sync(0xffffffffu, my_tau, j);
+      const bool pass = lane < n && key >= tj;
+      const uint32_t b = __ballot_sync(0xffffffffu, pass);
+      if (b) {   // warp-uniform
+        const uint32_t cj = __shfl_sync(0xffffffffu, cnt, j);
+        if (pass) {
+          const uint32_t pos = cj + __popc(b & ((1u << lane) - 1u));
+          if (pos < seg_cap) seg_keys[((size_t)(q0 + j) * n_seg + seg) * seg_cap + pos] = key;
+        }
+        if (lane == (uint32_t)j) cnt += __popc(b);
+      }
+    }
+  }
+  if (own_q) seg_cnt[my_seg] = cnt;
+}
+
 // Select step of the tensor-core filter: one CTA per query packs the query's exact (re-scored) survivor keys into
 // SHARED memory, selects and sorts the top k there.  Replaces select_kernel<TOPK> on that path (ncu r5: 35 us per 64
 // queries: a tid-0 serial walk over the 148 segment counts, ten passes over the keys through L2, and an 8-pass radix
@@ -966,6 +1062,37 @@ static int launch_rescore(prg_handle* h, const float* q_dev, int nq, uint32_t n_
   return PRG_OK;
 }
 
+// config "scan_groups": 1 / 0 force GROUP mode on / off; default (-1) = on at dim 64, where the epilogue of a 256-query
+// pass is the limit, off at dim 128, where the MMAs and the loads are (the re-score of a group costs 16 dot products per
+// recorded row instead of one).
+static bool scan_groups_on(const prg_handle* h) { return h->scan_groups < 0 ? h->E_dim == 64 : h->scan_groups != 0; }
+
+// GROUP mode: exact scores of the recorded (row, group of 16 queries) pairs -> the (query, segment) key lists + counts
+static int launch_rescore_groups(prg_handle* h, const float* q_dev, int nq, uint32_t n_seg, uint32_t seg_cap) {
+  StageScope span(h, ST_SELECT);
+  const dim3 grid(n_seg, (unsigned)((nq + kGrpQ - 1) / kGrpQ));
+  const uint32_t grp_cap = kGrpQ * seg_cap;
+  if (h->E_dim == 64)
+    PRG_CUDA(launch_chained(h, rescore_group_kernel<64>, grid, dim3(32), 0, 1, (const uint32_t*)h->seg_rows.p,
+                            (const uint32_t*)h->grp_cnt.p, n_seg, grp_cap, seg_cap, nq, h->E, q_dev, h->E_row_base,
+                            (const uint64_t*)h->tau.p, (uint64_t*)h->seg_keys.p, (uint32_t*)h->cand_cnt.p));
+  else
+    PRG_CUDA(launch_chained(h, rescore_group_kernel<128>, grid, dim3(32), 0, 1, (const uint32_t*)h->seg_rows.p,
+                            (const uint32_t*)h->grp_cnt.p, n_seg, grp_cap, seg_cap, nq, h->E, q_dev, h->E_row_base,
+                            (const uint64_t*)h->tau.p, (uint64_t*)h->seg_keys.p, (uint32_t*)h->cand_cnt.p));
+  PRG_CUDA(cudaGetLastError());
+  count_launch(h);
+  return PRG_OK;
+}
+// the filter pass [q0, q0 + nq) of a GROUP-mode call: where its groups' lists and lengths live (h->seg_rows is shared with
+// the per-query mode: 16 queries x seg_cap rows per (group, segment) = the same bytes)
+static void scan_group_outputs(prg_handle* h, ScanParams& sc, int q0, uint32_t n_seg, uint32_t seg_cap) {
+  const size_t g0 = (size_t)q0 / kGrpQ;
+  sc.grp_cap = kGrpQ * seg_cap;
+  sc.grp_rows = (uint32_t*)h->seg_rows.p + g0 * n_seg * sc.grp_cap;
+  sc.grp_cnt = (uint32_t*)h->grp_cnt.p + g0 * n_seg;
+}
+
 // Top-k of the exact keys, one CTA per query: 1024 threads when every query gets an SM of its own, 256 (several CTAs
 // per SM) when there are more queries than SMs.
 static int launch_refine(prg_handle* h, const RefineParams& rp, int nq, size_t smem) {
@@ -1110,6 +1237,13 @@ static int recall_dense(prg_handle* h, const float* q_dev, int nq, int k, int k_
   return PRG_OK;
 }
 
+static size_t refine_smem_bytes(uint32_t cand_cap, int k) {
+  uint32_t k_pow2 = 32;
+  while (k_pow2 < (uint32_t)k) k_pow2 <<= 1;
+  const uint32_t sort_cap = (k_pow2 - (uint32_t)k >= 16) ? k_pow2 : 2 * k_pow2;
+  return ((size_t)cand_cap + sort_cap) * 8;
+}
+
 constexpr uint64_t kSampledMinRows = 1u << 18;  // below this the dense path is cheaper than sampling
 
 int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t* keys_out, bool defer) {
@@ -1198,6 +1332,10 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   }
   // 3. full pass with the threshold test fused into the tile epilogue
   const int pass_q = use_tc ? scan_tc_max_queries(h) : kQB;  // queries per pass over the matrix
+  // GROUP mode (config "scan_groups", default on): more than 64 queries and the on-chip refine below
+  const bool grouped = use_tc && scan_groups_on(h) && B > kQB && n_seg <= 512 && refine_smem_bytes(cand_cap, k) <= 200 * 1024 &&
+                       (uint64_t)QT * n_seg * seg_cap < (1ull << 32);
+  if (grouped) PRG_TRY(h->grp_cnt.ensure(QT / kGrpQ * n_seg * 4));
   for (int q0 = 0; q0 < B; q0 += pass_q) {
     ScanParams sc{};
     sc.Q = q_dev + (size_t)q0 * dim; sc.nq = (B - q0 < pass_q) ? (B - q0) : pass_q;
@@ -1207,6 +1345,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     sc.seg_cnt = (uint32_t*)h->cand_cnt.p + (size_t)q0 * n_seg;
     sc.row_norm = (const float*)h->row_norm.p;
     sc.cand_rows = use_tc ? (uint32_t*)h->seg_rows.p + (size_t)q0 * seg_q : nullptr;
+    if (grouped) scan_group_outputs(h, sc, q0, n_seg, seg_cap);
     if (use_tc) PRG_TRY(launch_scan_tc(h, sc));
     else PRG_TRY(scan(h, SCAN_THRESH, sc));
   }
@@ -1217,7 +1356,8 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   const double per_seg = ((double)r_rank / f) / n_seg;   // expected survivors per (segment, query)
   if (use_tc && n_seg <= 512 && refine_smem <= 200 * 1024) {
     // 4. exact re-score, then the top-k of the exact keys in shared memory
-    PRG_TRY(launch_rescore(h, q_dev, B, n_seg, seg_cap, per_seg));
+    if (grouped) PRG_TRY(launch_rescore_groups(h, q_dev, B, n_seg, seg_cap));
+    else PRG_TRY(launch_rescore(h, q_dev, B, n_seg, seg_cap, per_seg));
     RefineParams rp{};
     rp.seg_keys = (const uint64_t*)h->seg_keys.p; rp.seg_counts = (const uint32_t*)h->cand_cnt.p;
     rp.n_seg = n_seg; rp.seg_cap = seg_cap; rp.cap = cand_cap;
@@ -1487,6 +1627,8 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
   uint32_t* max_cnt = (uint32_t*)h->cand_cnt.p + QT * pl.n_seg;
   PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
   const int pass_q = scan_tc_max_queries(h);
+  const bool grouped = scan_groups_on(h) && Bg > kQB && (uint64_t)QT * seg_q < (1ull << 32);   // GROUP mode, as in recall_topk_device
+  if (grouped) PRG_TRY(h->grp_cnt.ensure(QT / kGrpQ * pl.n_seg * 4));
   for (int q0 = 0; q0 < Bg; q0 += pass_q) {
     ScanParams sc{};
     sc.Q = q_dev + (size_t)q0 * dim; sc.nq = (Bg - q0 < pass_q) ? (Bg - q0) : pass_q;
@@ -1496,10 +1638,12 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
     sc.seg_cnt = (uint32_t*)h->cand_cnt.p + (size_t)q0 * pl.n_seg;
     sc.row_norm = (const float*)h->row_norm.p;
     sc.cand_rows = (uint32_t*)h->seg_rows.p + (size_t)q0 * seg_q;
+    if (grouped) scan_group_outputs(h, sc, q0, pl.n_seg, pl.seg_cap);
     PRG_TRY(launch_scan_tc(h, sc));
   }
   {
-    PRG_TRY(launch_rescore(h, q_dev, Bg, pl.n_seg, pl.seg_cap, (double)pl.r * kShardSampleStride / (double)G / pl.n_seg));
+    if (grouped) PRG_TRY(launch_rescore_groups(h, q_dev, Bg, pl.n_seg, pl.seg_cap));
+    else PRG_TRY(launch_rescore(h, q_dev, Bg, pl.n_seg, pl.seg_cap, (double)pl.r * kShardSampleStride / (double)G / pl.n_seg));
     RefineParams rp{};
     rp.seg_keys = (const uint64_t*)h->seg_keys.p; rp.seg_counts = (const uint32_t*)h->cand_cnt.p;
     rp.n_seg = pl.n_seg; rp.seg_cap = pl.seg_cap; rp.cap = pl.cand_cap;

@@ -37,7 +37,15 @@ struct ScanParams {
   uint64_t* dense;         // DENSE: [nq][dense_stride], slot = t*256 + r
   uint64_t dense_stride;
   int q_blocks;            // DENSE: > 1 = nq spans that many blocks of 64 queries, one grid row (blockIdx.y) each
+  // TC filter, GROUP mode (grp_rows != nullptr; passes of more than 64 queries): a surviving row is recorded once per
+  // GROUP of 16 queries in which it may reach a threshold, not once per query — [group][gridDim.x][grp_cap] global rows,
+  // lengths in grp_cnt[group][gridDim.x] (group = query / 16 within the pass).  rescore_group_kernel then scores the row
+  // exactly against the group's 16 queries and keeps the keys that reach tau.
+  uint32_t* grp_rows;
+  uint32_t* grp_cnt;
+  uint32_t grp_cap;
 };
+constexpr int kGrpQ = 16;   // queries per group
 
 struct SelectParams {
   const uint64_t* keys;    // query q reads keys + q*stride

@@ -41,10 +41,18 @@ constexpr float kTcMarginBf16 = 1.05f / 256.f;  // c = 1.05 * 2^-8
 // every block (the shard of a G-GPU run sees 64*G queries per step: one pass instead of G).
 // A stage is 256 rows x 64 dims of fp32 (64 KiB, two 32-float TMA boxes) for the tf32 filter and 256 rows x DIM of
 // bf16 (DIM/64 boxes of 32 KiB) for the bf16 filter.
-template <int DIM, bool BF>
-constexpr int tc_stage_bytes() { return BF ? kTileRows * DIM * 2 : kStageBytes; }
+// 256 queries per pass over the bf16 index (NQB == 4): a stage is HALF a tile (128 rows, the unit of the per-half
+// accumulator barriers below) — the ring then turns over at half-tile granularity: a half's buffer is requested again as
+// soon as its own MMAs are through, not when the whole tile's are.  With whole-tile stages the dim-128 pass had two
+// 64-KiB stages and ran at (MMA + load latency) / 2 per tile: tensor pipe 51 % busy, DRAM 49 % (ncu r3d, C5 shard shape).
+template <int NQB, bool BF>
+constexpr bool tc_half_stages() { return BF && NQB == 4; }
 template <int DIM, int NQB, bool BF>
-constexpr int tc_stages() { return BF ? (DIM == 64 ? (NQB <= 2 ? 5 : 4) : (NQB == 1 ? 3 : 2)) : ((NQB == 1 && DIM == 64) ? 3 : 2); }
+constexpr int tc_stage_bytes() { return BF ? (tc_half_stages<NQB, BF>() ? kTileRows / 2 : kTileRows) * DIM * 2 : kStageBytes; }
+template <int DIM, int NQB, bool BF>
+constexpr int tc_stages() {
+  return BF ? (DIM == 64 ? (NQB <= 2 ? 5 : 8) : (NQB == 1 ? 3 : (NQB == 2 ? 2 : 4))) : ((NQB == 1 && DIM == 64) ? 3 : 2);
+}
 // The row norms of a tile travel with it (one 1 KiB bulk copy completing on the tile's `full` barrier) into a ring of
 // S + 3 slots: the producer may run S tiles ahead of the MMA warp and the MMA warp 2 tiles (accumulator buffers) ahead
 // of the epilogue, which reads the norms.
@@ -52,7 +60,7 @@ template <int DIM, int NQB, bool BF>
 constexpr int tc_norm_ring() { return tc_stages<DIM, NQB, BF>() + 3; }
 template <int DIM, int NQB, bool BF>
 constexpr size_t scan_tc_smem_bytes() {
-  return (size_t)tc_stages<DIM, NQB, BF>() * tc_stage_bytes<DIM, BF>() + (size_t)NQB * DIM * kQB * (BF ? 2 : 4) /*Q operands*/ +
+  return (size_t)tc_stages<DIM, NQB, BF>() * tc_stage_bytes<DIM, NQB, BF>() + (size_t)NQB * DIM * kQB * (BF ? 2 : 4) /*Q operands*/ +
          (size_t)NQB * 3 * kQB * 4 /*tauf, qn, s_cnt*/ + (2 * tc_stages<DIM, NQB, BF>() + 4) * 8 + 16 +
          (size_t)tc_norm_ring<DIM, NQB, BF>() * kTileRows * 4 /*row-norm ring*/;
 }
@@ -99,7 +107,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   const ScanParams& p = kDenseMode ? p_adj : p_in;
   constexpr int KH = BF ? 1 : DIM / 64;                    // stages per tile
   constexpr int kTcStages = tc_stages<DIM, NQB, BF>();
-  constexpr int kStageB = tc_stage_bytes<DIM, BF>();
+  constexpr int kStageB = tc_stage_bytes<DIM, NQB, BF>();
   constexpr int kQBytes = DIM * kQB * (BF ? 2 : 4);        // one query block as a B operand
   constexpr int NBUF = NQB <= 2 ? 2 : 1;                   // accumulator buffers (128 TMEM columns per block and buffer)
   // NQB = 4 fills all 512 TMEM columns with ONE tile's accumulators (256 rows x 256 queries), so whole tiles cannot be
@@ -114,8 +122,9 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   constexpr bool kDense = MODE != SCAN_THRESH;
   constexpr bool kTileMax = MODE == SCAN_TILEMAX;
   uint8_t* stage_base = smem;
-  uint8_t* Qb = smem + (size_t)kTcStages * kStageB;  // B operands, K-major SWIZZLE_128B: tf32 [NQB][DIM/32][64 q][32 f32],
-                                                     // bf16 [NQB][DIM/64][64 q][64 bf16]
+  uint8_t* Qb = smem + (size_t)kTcStages * kStageB;  // B operand, K-major SWIZZLE_128B: tf32 [DIM/32][QTOT q][32 f32],
+                                                     // bf16 [DIM/64][QTOT q][64 bf16] — ALL queries of the pass are the N
+                                                     // dimension of one MMA (N = 64 / 128 / 256)
   float2* tq = reinterpret_cast<float2*>(Qb + (size_t)NQB * kQBytes);           // [NQB*64] {tau_f, c*||q||}
   uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tq + QTOT);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + QTOT);
@@ -136,6 +145,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   // c||q'|| for all queries only lets a few more rows through.  Otherwise (a threshold <= 0, none, or extreme) the
   // per-query form below is used for the whole pass.
   __shared__ float s_scale[NQB * kQB];
+  __shared__ float s_ss[NQB * kQB];     // squared norms of the staged (scaled) queries
   __shared__ uint32_t s_cmax;
   if (tid == 0) {
     s_cmax = 0u;
@@ -145,11 +155,14 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     mbar_fence_init();
   }
   const uint32_t my_tiles = (p.n_tiles > blockIdx.x) ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  // one tile = KH stages of data + its row norms
+  // one tile = SPT stages of data + its row norms
+  constexpr bool kHalfStage = tc_half_stages<NQB, BF>();
+  constexpr int SPT = kHalfStage ? 2 : KH;               // stages per tile
+  constexpr int kStageRows = kHalfStage ? kTileRows / 2 : kTileRows;
   auto issue_tile = [&](uint32_t i, uint32_t it) {
     const uint32_t t = blockIdx.x + i * gridDim.x;
     const int row0 = (int)(t * p.tile_stride * (uint32_t)kTileRows);
-    for (int h = 0; h < KH; ++h, ++it) {
+    for (int h = 0; h < SPT; ++h, ++it) {
       const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
       mbar_wait(&empty[s], ph ^ 1u);
       mbar_arrive_expect_tx(&full[s], kStageB + (h == 0 ? kTileRows * 4 : 0));
@@ -158,8 +171,8 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
         bulk_load_1d(nrm + (size_t)(i % kNormRing) * kTileRows, p.row_norm + (size_t)row0, kTileRows * 4, &full[s]);
       if constexpr (BF) {
 #pragma unroll
-        for (int sub = 0; sub < DIM / 64; ++sub)   // one box = 256 rows x 64 bf16 (128 B)
-          tma_load_2d(dst + sub * (kTileRows * 128), &emap, sub * 64, row0, &full[s], kEvictFirst);
+        for (int sub = 0; sub < DIM / 64; ++sub)   // one box = kStageRows rows x 64 bf16 (128 B); half stages: rows [128 h, +128)
+          tma_load_2d(dst + sub * (kStageRows * 128), &emap, sub * 64, row0 + (kHalfStage ? h * kStageRows : 0), &full[s], kEvictFirst);
       } else {
         tma_load_2d(dst, &emap, h * 64, row0, &full[s], kEvictFirst);
         tma_load_2d(dst + kSubTileFloats * 4, &emap, h * 64 + 32, row0, &full[s], kEvictFirst);
@@ -170,10 +183,10 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   // tables no kernel of the per-batch chain writes, so on a chained launch the ring fills while the previous kernel
   // drains (everything below pdl_wait() reads what that kernel wrote: thresholds, queries) and while the query
   // operands are staged.
-  constexpr uint32_t kPrefetchTiles = kTcStages / KH;
+  constexpr uint32_t kPrefetchTiles = kTcStages / SPT;
   const uint32_t n_pre = my_tiles < kPrefetchTiles ? my_tiles : kPrefetchTiles;
   if (tid == 0)
-    for (uint32_t i = 0; i < n_pre; ++i) issue_tile(i, i * KH);
+    for (uint32_t i = 0; i < n_pre; ++i) issue_tile(i, i * SPT);
   pdl_wait();
   int bad = 0;
   for (int q = tid; q < QTOT; q += kTcThreads) {
@@ -188,30 +201,51 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   }
   const bool scaled = __syncthreads_or(bad) == 0 && !kDense;   // (also publishes the mbarrier initialisation)
 
-  // query blocks -> K-major SWIZZLE_128B B operands (16-B chunk index XOR row-in-group); padded queries are zero rows
-  for (int i = tid; i < DIM * QTOT; i += kTcThreads) {
-    const int q = i / DIM, dd = i - q * DIM;
-    float v = (q < p.nq) ? p.Q[(size_t)q * DIM + dd] : 0.f;
-    if (scaled) v *= s_scale[q];
-    const int blk = q >> 6, ql = q & 63;
-    if constexpr (BF) {
-      const int sub = dd >> 6, e = dd & 63, ch = e >> 3;
-      reinterpret_cast<__nv_bfloat16*>(Qb)[(size_t)blk * DIM * kQB + sub * (kQB * 64) + ql * 64 + ((ch ^ (ql & 7)) << 3) + (e & 7)] =
-          __float2bfloat16_rn(v);
-    } else {
-      const int sub = dd >> 5, ch = (dd & 31) >> 2;
-      reinterpret_cast<float*>(Qb)[(size_t)blk * DIM * kQB + sub * (kQB * 32) + ql * 32 + ((ch ^ (ql & 7)) << 2) + (dd & 3)] = v;
+  // query blocks -> K-major SWIZZLE_128B B operands (16-B chunk index XOR row-in-group); padded queries are zero rows.
+  // 16 bytes per thread and iteration, four iterations' loads in flight: the element-wise form of this loop and a
+  // per-query serial norm loop cost 15-20 us per pass at 256 queries (ncu r3d: a quarter of a c4-shard pass).  The squared
+  // norm of the (scaled) query is summed on the way: the DIM/4 pieces of a query are held by consecutive lanes.
+  {
+    constexpr int C4 = DIM / 4;                       // 16-B pieces per query: 16 or 32 (<= one warp)
+    constexpr int kIters = (C4 * QTOT + kTcThreads - 1) / kTcThreads;
+#pragma unroll 4
+    for (int itq = 0; itq < kIters; ++itq) {
+      const int i4 = tid + itq * kTcThreads;
+      const bool in = i4 < C4 * QTOT;
+      const int q = in ? i4 / C4 : 0, c4 = i4 - q * C4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in && q < p.nq) v = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)q * DIM) + c4);
+      if (scaled) { const float sc = s_scale[q]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+      float ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+      for (int off = 1; off < C4; off <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // lanes of one query only
+      if (in) {
+        const int dd = c4 * 4;
+        if constexpr (BF) {
+          const int sub = dd >> 6, e = dd & 63, ch = e >> 3;     // 4 bf16 = half of a 16-B chunk
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(Qb) + (size_t)sub * (QTOT * 64) + q * 64 +
+                                    ((ch ^ (q & 7)) << 3) + (e & 7)) = pk;
+        } else {
+          const int sub = dd >> 5, ch = (dd & 31) >> 2;          // 4 f32 = one 16-B chunk
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(Qb) + (size_t)sub * (QTOT * 32) + q * 32 +
+                                     ((ch ^ (q & 7)) << 2)) = v;
+        }
+        if (c4 == 0) s_ss[q] = ss;
+      }
     }
   }
+  __syncthreads();
   for (int q = tid; q < QTOT; q += kTcThreads) {
     float tf = __int_as_float(0x7F800000), nq2 = 0.f;
     if (q < p.nq && !kDense) {
       const uint64_t t = p.tau[q];
       tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
-      const float sc = scaled ? s_scale[q] : 1.0f;
-      float ss = 0.f;
-      for (int dd = 0; dd < DIM; ++dd) { const float v = p.Q[(size_t)q * DIM + dd] * sc; ss = fmaf(v, v, ss); }
-      nq2 = (sqrtf(ss) * 1.0001f + 1e-30f) * kMargin;
+      // (the pairwise order of the sum differs from a serial one by a few ulp; the bound is inflated by 1e-4)
+      nq2 = (sqrtf(s_ss[q]) * 1.0001f + 1e-30f) * kMargin;
       if (scaled) atomicMax(&s_cmax, __float_as_uint(nq2));  // non-negative floats order like their bit patterns
     }
     tq[q] = make_float2(tf, nq2);
@@ -237,7 +271,7 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      for (uint32_t i = n_pre; i < my_tiles; ++i) issue_tile(i, i * KH);
+      for (uint32_t i = n_pre; i < my_tiles; ++i) issue_tile(i, i * SPT);
       // every tile of this CTA is requested: the next kernel of the chain may start its prologue (it orders itself
       // behind this grid with pdl_wait)
       pdl_launch_dependents();
@@ -247,35 +281,38 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     if (lane == 0) {
       // D=f32, A=B=tf32 (format 2) or bf16 (format 1), both K-major, N=64, M=128
       constexpr uint32_t fmt = BF ? 1u : 2u;
-      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kQB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // One MMA covers every query block of the pass: N = QTOT.  With one N = 64 MMA per block (round 2's form) a tile at
+      // 256 queries per pass took 32 (dim 64) / 64 (dim 128) instructions of 32 tensor-pipe cycles each, and the pass ran
+      // at the rate the issuing thread could feed them: tensor pipe 24 % / 51 % busy, DRAM 24 % / 49 % (ncu r3d), the
+      // loads themselves good for 7 TB/s at this ring depth (tools/ubench_tma_stream.cu).
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(QTOT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       constexpr int kSubs = BF ? DIM / 64 : 2;           // 128-B-wide sub-tiles per stage
+      constexpr uint32_t kQSubBytes = (uint32_t)QTOT * 128u;   // one 128-B-wide K slice of all queries
       const uint32_t qb_addr = smem_u32(Qb);
       uint32_t it = 0;
       if constexpr (kHalfBars) {
-        for (uint32_t i = 0; i < my_tiles; ++i, ++it) {
-          const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
-          const uint32_t st_addr = smem_u32(stage_base + (size_t)s * kStageB);
+        static_assert(!kHalfBars || kHalfStage, "per-half accumulator barriers come with half-tile stages");
+        for (uint32_t i = 0; i < my_tiles; ++i) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          for (int half = 0; half < 2; ++half, ++it) {
+            const uint32_t s = it % kTcStages, ph = (it / kTcStages) & 1u;
+            mbar_wait(&full[s], ph);                        // this half's 128 rows (and, with half 0, the tile's norms)
+            tc_fence_after();
+            const uint32_t st_addr = smem_u32(stage_base + (size_t)s * kStageB);
             mbar_wait(&tempty[half], (i & 1u) ^ 1u);        // this half's four epilogue warps have drained the previous tile
             tc_fence_after();
+            const uint32_t d_addr = tmem_base + (uint32_t)half * (uint32_t)QTOT;
 #pragma unroll
-            for (int blk = 0; blk < NQB; ++blk) {
-              const uint32_t d_addr = tmem_base + (uint32_t)blk * 128u + (uint32_t)half * 64u;
+            for (int sub = 0; sub < kSubs; ++sub) {
+              const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kStageRows * 128));
+              const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)sub * kQSubBytes);
 #pragma unroll
-              for (int sub = 0; sub < kSubs; ++sub) {
-                const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kTileRows * 128) + (uint32_t)half * (128 * 128));
-                const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)blk * kQBytes + (uint32_t)sub * (kQB * 128));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (sub | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (sub | k) != 0 ? 1u : 0u);
             }
             umma_commit(&tfull[half]);
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
         }
       } else {
       for (uint32_t i = 0; i < my_tiles; ++i) {
@@ -289,23 +326,20 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
           tc_fence_after();
           const uint32_t st_addr = smem_u32(stage_base + (size_t)s * kStageB);
 #pragma unroll
-          for (int blk = 0; blk < NQB; ++blk) {
+          for (int half = 0; half < 2; ++half) {
+            const uint32_t d_addr = tmem_base + (buf * 2u + (uint32_t)half) * (uint32_t)QTOT;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint32_t d_addr = tmem_base + (buf * (uint32_t)NQB + (uint32_t)blk) * 128u + (uint32_t)half * 64u;
+            for (int sub = 0; sub < kSubs; ++sub) {
+              // a sub-tile is 256 rows of 128 B; rows [128*half, +128) start 16 KiB in; the matching K slice of the
+              // queries is QTOT rows of 128 B
+              const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kTileRows * 128) + (uint32_t)half * (128 * 128));
+              const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)(h * kSubs + sub) * kQSubBytes);
 #pragma unroll
-              for (int sub = 0; sub < kSubs; ++sub) {
-                // a sub-tile is 256 rows of 128 B; rows [128*half, +128) start 16 KiB in; the matching slice of the
-                // query block is 64 rows of 128 B (8 KiB)
-                const uint64_t adesc = umma_desc_k_sw128(st_addr + (uint32_t)sub * (kTileRows * 128) + (uint32_t)half * (128 * 128));
-                const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)blk * kQBytes + (uint32_t)(h * kSubs + sub) * (kQB * 128));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {  // UMMA_K = 32 B (8 tf32 / 16 bf16) -> +2 in 16-B units
-                  if constexpr (BF)
-                    umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (sub | k) != 0 ? 1u : 0u);
-                  else
-                    umma_tf32(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (h | sub | k) != 0 ? 1u : 0u);
-                }
+              for (int k = 0; k < 4; ++k) {  // UMMA_K = 32 B (8 tf32 / 16 bf16) -> +2 in 16-B units
+                if constexpr (BF)
+                  umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (sub | k) != 0 ? 1u : 0u);
+                else
+                  umma_tf32(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (h | sub | k) != 0 ? 1u : 0u);
               }
             }
           }
@@ -327,8 +361,25 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
     const float cmax = __uint_as_float(s_cmax);
     // the tile loop is instantiated once per threshold form (the choice is uniform for the launch), so that neither
     // form pays registers for the other
-    auto run = [&](auto scaled_tag) {
+    auto run = [&](auto scaled_tag, auto group_tag) {
     constexpr bool kScaled = decltype(scaled_tag)::value;
+    // GROUP mode (ScanParams::grp_rows): a survivor is appended once per group of 16 queries — a shared-memory atomic and a
+    // store per (row, group) — instead of walking the group's 16 accumulators again to append it per query.  With 128 / 256
+    // queries per pass the per-query walk (entered by 60 % of the warps for every block of 64 queries: one lane with a
+    // survivor is enough) made the epilogue, not HBM or the MMAs, the limit of the pass (~200 instructions per warp and
+    // block; ~60 here).  The exact re-score (recall.cu rescore_group_kernel) sorts out which of the 16 queries it was.
+    constexpr bool kGroup = decltype(group_tag)::value && !kDense;
+    const uint32_t grp_stride = gridDim.x * p.grp_cap;                       // slots between two groups' lists
+    uint32_t* const grp_base = p.grp_rows + (size_t)blockIdx.x * p.grp_cap;  // this CTA's list of group 0
+    auto append_groups = [&](int blk, uint32_t* scb, uint32_t grow, bool a0, bool a1, bool a2, bool a3) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g == 0 ? a0 : g == 1 ? a1 : g == 2 ? a2 : a3) {
+          const uint32_t pos = atomicAdd(&scb[g], 1u);
+          if (pos < p.grp_cap) grp_base[(uint32_t)(blk * 4 + g) * grp_stride + pos] = grow;   // 32-bit offsets (< 2^32 slots)
+        }
+      }
+    };
     for (uint32_t i = 0; i < my_tiles; ++i) {
       const uint32_t buf = (NBUF == 2) ? (i & 1u) : 0u;          // TMEM buffer (column offset)
       const uint32_t use = (NBUF == 2) ? (i >> 1) : i;
@@ -345,8 +396,8 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       const float nr = nrm[(size_t)(i % kNormRing) * kTileRows + row_local];
 #pragma unroll 1
       for (int blk = 0; blk < NQB; ++blk) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * (uint32_t)NQB + (uint32_t)blk) * 128u +
-                               (uint32_t)half * 64u;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * 2u + (uint32_t)half) * (uint32_t)QTOT +
+                               (uint32_t)blk * 64u;
         uint32_t v0[32], v1[32];
         tmem_ld32_nowait(taddr, v0);
         tmem_ld32_nowait(taddr + 32u, v1);
@@ -411,6 +462,9 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
             m[g] = fmaxf(a, __uint_as_float(v[o + 15]));
           }
           const bool any0 = !(m[0] < t_r), any1 = !(m[1] < t_r), any2 = !(m[2] < t_r), any3 = !(m[3] < t_r);
+          if constexpr (kGroup) {
+            if (valid && (any0 || any1 || any2 || any3)) append_groups(blk, scb, grow, any0, any1, any2, any3);
+          } else
           if (valid && (any0 || any1 || any2 || any3)) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -450,6 +504,9 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
             any[2 + (q >> 4)] |= !(__uint_as_float(v1[q]) < fmaf(-nr, b4.y, b4.x));
             any[2 + (q >> 4)] |= !(__uint_as_float(v1[q + 1]) < fmaf(-nr, b4.w, b4.z));
           }
+          if constexpr (kGroup) {
+            if (valid && (any[0] || any[1] || any[2] || any[3])) append_groups(blk, scb, grow, any[0], any[1], any[2], any[3]);
+          } else
           if (valid && (any[0] || any[1] || any[2] || any[3])) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -476,9 +533,14 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       }
     }
     };
-    if (scaled) run(std::true_type{}); else run(std::false_type{});
+    const bool grouped = !kDense && p.grp_rows != nullptr;
+    if (grouped) { if (scaled) run(std::true_type{}, std::true_type{}); else run(std::false_type{}, std::true_type{}); }
+    else { if (scaled) run(std::true_type{}, std::false_type{}); else run(std::false_type{}, std::false_type{}); }
     asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
-    if (!kDense)
+    if (grouped) {   // every group of the pass gets its length (0 for the padding groups of the last block)
+      for (int i = tid - 64; i < NQB * 4; i += kTcEpiWarps * 32)
+        p.grp_cnt[(size_t)i * gridDim.x + blockIdx.x] = s_cnt[(i >> 2) * kQB + (i & 3)];
+    } else if (!kDense)
       for (int q = tid - 64; q < p.nq; q += kTcEpiWarps * 32) p.seg_cnt[(size_t)q * gridDim.x + blockIdx.x] = s_cnt[q];
   }
 
@@ -540,6 +602,11 @@ int build_row_norms(prg_handle* h) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled (bf16 shadow) failed: " + std::to_string((int)r));
+    box[1] = (cuuint32_t)(kTileRows / 2);   // half-tile boxes: the 256-queries-per-pass kernels' stages (tc_half_stages)
+    r = enc(&h->E16_map_h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->E16.p, gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled (bf16 shadow, half tiles) failed: " + std::to_string((int)r));
     h->E16_map_ok = true;
   }
   return PRG_OK;
@@ -554,7 +621,7 @@ static int launch_tc(prg_handle* h, const ScanParams& p) {
   StageScope span(h, ST_SCAN);
   const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
   PRG_CUDA(launch_chained(h, recall_scan_tc_kernel<DIM, NQB, BF>, dim3(grid), dim3(kTcThreads), smem, 1,
-                          BF ? h->E16_map : h->E_map, p));
+                          BF ? (tc_half_stages<NQB, BF>() ? h->E16_map_h : h->E16_map) : h->E_map, p));
   count_launch(h);
   return PRG_OK;
 }

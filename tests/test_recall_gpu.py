@@ -200,3 +200,66 @@ def test_clustered_scores_refine_select(engine, oracle_lib):
     E = (base + rng.standard_normal((n, d)).astype(np.float32) * np.float32(1e-4)).astype(np.float32)
     Q = (base * np.float32(1.0) + rng.standard_normal((3, d)).astype(np.float32) * np.float32(1e-3)).astype(np.float32)
     _check(engine, oracle_lib, E, Q, 1000)
+
+
+# ---- GROUP mode of the tensor-core filter (passes of more than 64 queries: survivors recorded per (row, group of 16
+# queries), exact re-score against the group; recall_tc.cu / recall.cu rescore_group_kernel)
+
+def test_group_mode_equals_per_query_mode(oracle_lib):
+    from pairec_b200 import Engine
+    E, Q = _data(500_000, 64, 150, seed=101)
+    out = []
+    for groups in (1, 0):
+        eng = Engine(0, scan_groups=groups)
+        try:
+            eng.set_item_matrix(E, row_base=777)
+            out.append(eng.recall_topk(Q, 1000))
+            assert eng.recall_stats()["fallback_queries"] == 0
+        finally:
+            eng.close()
+    for a, b in zip(out[0], out[1]):
+        assert (np.asarray(a).view(np.uint32) == np.asarray(b).view(np.uint32)).all()
+    keys = oracle_lib.recall_topk(E, Q, 1000, row_base=777)
+    orows, oscores, on = oracle_lib.keys_split(keys)
+    assert (out[0][0] == orows).all() and (out[0][1].view(np.uint32) == oscores.view(np.uint32)).all()
+
+
+def test_group_mode_negative_thresholds_nan_and_padding(engine, oracle_lib):
+    # 70 queries = one full block + 6 queries in a block whose other groups are padding; negative thresholds force the
+    # per-query form of the filter test; one query and some rows carry NaN / inf
+    n, d = 400_000, 64
+    rng = np.random.default_rng(103)
+    E = rng.random((n, d), dtype=np.float32) + np.float32(0.1)
+    Q = -(rng.random((70, d), dtype=np.float32) + np.float32(0.1))
+    Q[5] = -Q[5]
+    Q[66] = -Q[66]
+    E[1234, 3] = np.inf
+    E[99_999, 7] = np.nan
+    E[200_000] = 0
+    _check(engine, oracle_lib, E, Q, 300)
+
+
+def test_group_mode_adversarial_order_falls_back_exactly(engine, oracle_lib):
+    # as test_adversarial_order_falls_back_exactly, with 96 queries: the group lists overflow, the affected queries are
+    # flagged through their segment counts and redone densely
+    n, d = 400_000, 64
+    rng = np.random.default_rng(107)
+    E = (rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    n_tiles = (n + 255) // 256
+    stride = n_tiles // max(64, n_tiles // 128)
+    tile = np.arange(n) // 256
+    E[:, 0] = np.where(tile % stride == 0, 0.0, 1.0 + rng.random(n) * 0.5).astype(np.float32)
+    Q = (rng.standard_normal((96, d)) * 0.01).astype(np.float32)
+    Q[:, 0] = 0          # the other queries do not see the adversarial column
+    Q[0] = 0
+    Q[0, 0] = 1.0
+    Q[70] = 0
+    Q[70, 0] = 2.0
+    _check(engine, oracle_lib, E, Q, 1000)
+    assert engine.recall_stats()["fallback_queries"] >= 2
+
+
+def test_group_mode_large_k_keeps_the_split_path(engine, oracle_lib):
+    E, Q = _data(400_000, 64, 80, seed=109)
+    _check(engine, oracle_lib, E, Q, 3000)
+    assert engine.recall_stats()["fallback_queries"] == 0

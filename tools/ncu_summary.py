@@ -26,9 +26,9 @@ if len(sys.argv) > 2:
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
-    hdr, data = rows[hi], rows[hi + 1:]
+    hdr, data = rows[hi], [r for r in rows[hi + 1:] if len(r) > 3]
     ix = {h: i for i, h in enumerate(hdr)}
-    g = lambda r, k: float(r[ix[k]] or 0) if r[ix[k]].replace(".", "").isdigit() else 0.0
+    g = lambda r, k: (float(r[ix[k]] or 0) if r[ix[k]].replace(".", "").isdigit() else 0.0) if ix[k] < len(r) else 0.0
     tot = sum(g(r, "# Samples") for r in data)
     c = Counter()
     for r in data:
