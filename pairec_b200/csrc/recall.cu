@@ -592,9 +592,16 @@ __global__ void __launch_bounds__(32) rescore_group_kernel(const uint32_t* __res
   pdl_launch_dependents();
   constexpr int F4 = DIM / 4;            // 16-B pieces per row
   constexpr int RPI = 32 / F4;           // rows fetched per load instruction (2 at dim 64, 1 at dim 128)
+  constexpr int NLD = 32 / RPI;          // load instructions per 32 rows
   constexpr int PITCH = DIM + 4;
   constexpr int QP = DIM + 4;            // pitch of a staged query (floats)
-  __shared__ __align__(16) float tile[32 * PITCH];
+  constexpr int QL = kGrpQ * F4 / 32;    // 16-B pieces of the group's queries per lane (8 / 16)
+  // Rows per lane.  Two (lane and lane + 32 of a chunk of 64: every broadcast read of a query piece feeds 8 FMAs instead of
+  // 4) was measured at dim 64 and lost: select stage of a c4 shard pass 0.119 -> 0.128 ms (gpurun r3h / r3i), the larger
+  // tile costs more resident warps than the saved shared-memory reads give back.
+  constexpr int RL = 1;
+  constexpr int CH = 32 * RL;            // rows per chunk
+  __shared__ __align__(16) float tile[CH * PITCH];
   __shared__ __align__(16) float qs[kGrpQ * QP];
   const uint32_t seg = blockIdx.x, gi = blockIdx.y, lane = threadIdx.x;
   const int q0 = (int)gi * kGrpQ;
@@ -609,60 +616,94 @@ __global__ void __launch_bounds__(32) rescore_group_kernel(const uint32_t* __res
     if (own_q) seg_cnt[my_seg] = 0u;
     return;
   }
+  // every load that depends on nothing but `total` is issued before the first wait: the first rows' ids, the thresholds
+  // and the group's queries (one round trip instead of three)
+  const uint32_t* src = grp_rows + ((size_t)gi * n_seg + seg) * grp_cap;
+  uint32_t my_row[RL];
+#pragma unroll
+  for (int r = 0; r < RL; ++r) my_row[r] = lane + 32u * r < total ? src[lane + 32u * r] : 0u;
   // a query slot past nq gets the impossible threshold: nothing is ever appended for it
   const uint64_t my_tau = own_q ? tau[q0 + (int)lane] : ~0ull;
-  for (uint32_t i = lane; i < (uint32_t)(kGrpQ * DIM); i += 32) {
-    const uint32_t j = i / DIM, d = i - j * DIM;
-    qs[j * QP + d] = (q0 + (int)j < nq) ? Q[(size_t)(q0 + (int)j) * DIM + d] : 0.f;
-  }
-  const uint32_t* src = grp_rows + ((size_t)gi * n_seg + seg) * grp_cap;
-  const uint32_t sub = lane / F4, piece = lane % F4;
-  uint32_t cnt = 0;   // lane j: keys of query q0 + j so far
-  for (uint32_t base = 0; base < total; base += 32) {
-    const uint32_t n = total - base < 32 ? total - base : 32;
-    const uint32_t my_row = lane < n ? src[base + lane] : 0u;
-    __syncwarp();
-    float4 xv[32 / RPI];
 #pragma unroll
-    for (int r = 0; r < 32 / RPI; ++r) {
-      const uint32_t row_in_chunk = r * RPI + sub;
-      const uint32_t grow = __shfl_sync(0xffffffffu, my_row, row_in_chunk);
-      xv[r] = row_in_chunk < n ? __ldg(reinterpret_cast<const float4*>(E + ((size_t)grow - row_base) * DIM) + piece)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int u0 = 0; u0 < QL; u0 += 8) {   // eight 16-B pieces per lane in flight
+    float4 qv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t idx = lane + 32u * (uint32_t)(u0 + u), j = idx / F4, c = idx - j * F4;
+      qv[u] = (q0 + (int)j < nq) ? __ldg(reinterpret_cast<const float4*>(Q + (size_t)(q0 + (int)j) * DIM) + c)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int r = 0; r < 32 / RPI; ++r)
-      *reinterpret_cast<float4*>(&tile[(r * RPI + sub) * PITCH + piece * 4]) = xv[r];
-    __syncwarp();
-    float acc[kGrpQ];
+    for (int u = 0; u < 8; ++u) {
+      const uint32_t idx = lane + 32u * (uint32_t)(u0 + u), j = idx / F4, c = idx - j * F4;
+      *reinterpret_cast<float4*>(&qs[j * QP + 4 * c]) = qv[u];
+    }
+  }
+  const uint32_t sub = lane / F4, piece = lane % F4;
+  uint32_t cnt = 0;   // lane j: keys of query q0 + j so far
+  for (uint32_t base = 0; base < total; base += CH) {
+    const uint32_t n = total - base < (uint32_t)CH ? total - base : (uint32_t)CH;
+    if (base) {
 #pragma unroll
-    for (int j = 0; j < kGrpQ; ++j) acc[j] = 0.f;
-    const float4* x = reinterpret_cast<const float4*>(&tile[lane * PITCH]);
-#pragma unroll 4
-    for (int d4 = 0; d4 < F4; ++d4) {
-      const float4 v = x[d4];
+      for (int r = 0; r < RL; ++r) my_row[r] = lane + 32u * r < n ? src[base + lane + 32u * r] : 0u;
+    }
+    __syncwarp();                                               // the previous chunk's tile has been consumed
+    // coalesced fetch (RPI rows per instruction) of up to CH rows; all loads of the chunk in flight, then parked in the tile
+    float4 xv[RL][NLD];
 #pragma unroll
-      for (int j = 0; j < kGrpQ; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(&qs[j * QP + 4 * d4]);   // same address in every lane: broadcast
-        acc[j] = __fmaf_rn(v.x, w.x, acc[j]);
-        acc[j] = __fmaf_rn(v.y, w.y, acc[j]);
-        acc[j] = __fmaf_rn(v.z, w.z, acc[j]);
-        acc[j] = __fmaf_rn(v.w, w.w, acc[j]);
+    for (int r = 0; r < RL; ++r) {
+#pragma unroll
+      for (int l = 0; l < NLD; ++l) {
+        const uint32_t row_in_half = l * RPI + sub;
+        const uint32_t grow = __shfl_sync(0xffffffffu, my_row[r], row_in_half);
+        xv[r][l] = 32u * r + row_in_half < n ? __ldg(reinterpret_cast<const float4*>(E + ((size_t)grow - row_base) * DIM) + piece)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
-    for (int j = 0; j < kGrpQ; ++j) {
-      const uint64_t key = make_key(acc[j], my_row);
-      const uint64_t tj = __shfl_sync(0xffffffffu, my_tau, j);
-      const bool pass = lane < n && key >= tj;
-      const uint32_t b = __ballot_sync(0xffffffffu, pass);
-      if (b) {   // warp-uniform
-        const uint32_t cj = __shfl_sync(0xffffffffu, cnt, j);
-        if (pass) {
-          const uint32_t pos = cj + __popc(b & ((1u << lane) - 1u));
-          if (pos < seg_cap) seg_keys[((size_t)(q0 + j) * n_seg + seg) * seg_cap + pos] = key;
+    for (int r = 0; r < RL; ++r)
+#pragma unroll
+      for (int l = 0; l < NLD; ++l)
+        *reinterpret_cast<float4*>(&tile[(32 * r + l * RPI + sub) * PITCH + piece * 4]) = xv[r][l];
+    __syncwarp();
+    float acc[RL][kGrpQ];
+#pragma unroll
+    for (int r = 0; r < RL; ++r)
+#pragma unroll
+      for (int j = 0; j < kGrpQ; ++j) acc[r][j] = 0.f;
+#pragma unroll 2
+    for (int d4 = 0; d4 < F4; ++d4) {
+      float4 v[RL];
+#pragma unroll
+      for (int r = 0; r < RL; ++r) v[r] = *reinterpret_cast<const float4*>(&tile[(32 * r + lane) * PITCH + 4 * d4]);
+#pragma unroll
+      for (int j = 0; j < kGrpQ; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(&qs[j * QP + 4 * d4]);   // same address in every lane: broadcast
+#pragma unroll
+        for (int r = 0; r < RL; ++r) {
+          acc[r][j] = __fmaf_rn(v[r].x, w.x, acc[r][j]);
+          acc[r][j] = __fmaf_rn(v[r].y, w.y, acc[r][j]);
+          acc[r][j] = __fmaf_rn(v[r].z, w.z, acc[r][j]);
+          acc[r][j] = __fmaf_rn(v[r].w, w.w, acc[r][j]);
         }
-        if (lane == (uint32_t)j) cnt += __popc(b);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+#pragma unroll
+      for (int j = 0; j < kGrpQ; ++j) {
+        const uint64_t key = make_key(acc[r][j], my_row[r]);
+        const uint64_t tj = __shfl_sync(0xffffffffu, my_tau, j);
+        const bool pass = lane + 32u * r < n && key >= tj;
+        const uint32_t b = __ballot_sync(0xffffffffu, pass);
+        if (b) {   // warp-uniform
+          const uint32_t cj = __shfl_sync(0xffffffffu, cnt, j);
+          if (pass) {
+            const uint32_t pos = cj + __popc(b & ((1u << lane) - 1u));
+            if (pos < seg_cap) seg_keys[((size_t)(q0 + j) * n_seg + seg) * seg_cap + pos] = key;
+          }
+          if (lane == (uint32_t)j) cnt += __popc(b);
+        }
       }
     }
   }
@@ -1063,9 +1104,13 @@ static int launch_rescore(prg_handle* h, const float* q_dev, int nq, uint32_t n_
 }
 
 // config "scan_groups": 1 / 0 force GROUP mode on / off; default (-1) = on at dim 64, where the epilogue of a 256-query
-// pass is the limit, off at dim 128, where the MMAs and the loads are (the re-score of a group costs 16 dot products per
-// recorded row instead of one).
-static bool scan_groups_on(const prg_handle* h) { return h->scan_groups < 0 ? h->E_dim == 64 : h->scan_groups != 0; }
+// pass is the limit (c4 shard pass 0.320 -> 0.298 ms), off at dim 128, where the MMAs and the loads are and the two forms
+// measure within the run-to-run spread of each other (c5 shard pass 2.94 / 3.11 ms in gpurun r3g, 3.18 / 3.02 ms in r3i;
+// the re-score of a group costs 16 dot products per recorded row instead of one).
+static bool scan_groups_on(const prg_handle* h) {
+  if (h->scan_filter != SCAN_FILTER_BF16) return false;   // the group form of the filter exists over the bf16 index only
+  return h->scan_groups < 0 ? h->E_dim == 64 : h->scan_groups != 0;
+}
 
 // GROUP mode: exact scores of the recorded (row, group of 16 queries) pairs -> the (query, segment) key lists + counts
 static int launch_rescore_groups(prg_handle* h, const float* q_dev, int nq, uint32_t n_seg, uint32_t seg_cap) {

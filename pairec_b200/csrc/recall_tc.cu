@@ -90,7 +90,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {  // SASS FMN
 // p.dense[q][launch tile * 256 + r].  Used for the strided SAMPLE from which the threshold is estimated: tau is a pruning
 // hint only (the filter keeps a superset of {exact >= tau} for any tau and the refine step checks that set), so the
 // sample does not need exact scores, and the tensor cores score it in a fraction of the FFMA2 kernel's time.
-template <int DIM, int NQB, bool BF, int MODE = SCAN_THRESH>
+template <int DIM, int NQB, bool BF, int MODE = SCAN_THRESH, bool GROUP = false>   // GROUP: ScanParams::grp_rows form
 __global__ void __launch_bounds__(kTcThreads, 1)
 recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p_in) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -394,6 +394,59 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       // `full` itself from here would be wrong: that barrier may already be a whole phase further, the epilogue being
       // up to two tiles behind the MMA warp.)
       const float nr = nrm[(size_t)(i % kNormRing) * kTileRows + row_local];
+      if constexpr (kGroup && kScaled) {
+        // GROUP mode, uniform threshold — the form every well-scaled batch takes: the blocks' accumulators go through two
+        // register buffers (block b + 1 travels from tensor memory while block b is reduced to its four group maxima), the
+        // survivor test leaves one bit per (block, group), and the appends of the whole tile are made at the end: their
+        // shared-memory atomics are independent and go out back to back instead of one latency after the other per block.
+        const float t_r = fmaf(-nr, cmax, 1.0f - 1e-6f);
+        const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * 2u + (uint32_t)half) * (uint32_t)QTOT;
+        uint32_t a0[32], a1[32], b0[32], b1[32];
+        uint32_t hits = 0u;
+        tmem_ld32_nowait(tcol, a0);
+        tmem_ld32_nowait(tcol + 32u, a1);
+        tmem_ld_wait32(a0);
+        tmem_ld_wait32(a1);
+#pragma unroll
+        for (int blk = 0; blk < NQB; ++blk) {
+          uint32_t (&c0)[32] = (blk & 1) ? b0 : a0;
+          uint32_t (&c1)[32] = (blk & 1) ? b1 : a1;
+          uint32_t (&n0)[32] = (blk & 1) ? a0 : b0;
+          uint32_t (&n1)[32] = (blk & 1) ? a1 : b1;
+          if (blk + 1 < NQB) {
+            tmem_ld32_nowait(tcol + (uint32_t)(blk + 1) * 64u, n0);
+            tmem_ld32_nowait(tcol + (uint32_t)(blk + 1) * 64u + 32u, n1);
+          } else {             // every accumulator of this tile is in registers: the MMA warp may overwrite the buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[bar]);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t* v = g < 2 ? c0 : c1;
+            const int o = (g & 1) * 16;
+            float a = fmax3(__uint_as_float(v[o]), __uint_as_float(v[o + 1]), __uint_as_float(v[o + 2]));
+#pragma unroll
+            for (int j = 3; j < 15; j += 2) a = fmax3(a, __uint_as_float(v[o + j]), __uint_as_float(v[o + j + 1]));
+            a = fmaxf(a, __uint_as_float(v[o + 15]));
+            hits |= !(a < t_r) ? (1u << (blk * 4 + g)) : 0u;   // (NaN maxima and t_r = -inf / NaN survive, as above)
+          }
+          if (blk + 1 < NQB) {
+            tmem_ld_wait32(n0);
+            tmem_ld_wait32(n1);
+          }
+        }
+        if (valid && hits) {
+          uint32_t pos[NQB * 4];
+#pragma unroll
+          for (int b = 0; b < NQB * 4; ++b)
+            pos[b] = (hits >> b & 1u) ? atomicAdd(&s_cnt[(b >> 2) * kQB + (b & 3)], 1u) : 0xFFFFFFFFu;
+#pragma unroll
+          for (int b = 0; b < NQB * 4; ++b)
+            if (pos[b] < p.grp_cap) grp_base[(uint32_t)b * grp_stride + pos[b]] = grow;
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int blk = 0; blk < NQB; ++blk) {
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * 2u + (uint32_t)half) * (uint32_t)QTOT +
@@ -533,9 +586,9 @@ recall_scan_tc_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
       }
     }
     };
-    const bool grouped = !kDense && p.grp_rows != nullptr;
-    if (grouped) { if (scaled) run(std::true_type{}, std::true_type{}); else run(std::false_type{}, std::true_type{}); }
-    else { if (scaled) run(std::true_type{}, std::false_type{}); else run(std::false_type{}, std::false_type{}); }
+    constexpr bool grouped = !kDense && GROUP;   // (an instantiation of its own: the per-query form keeps its registers)
+    if (scaled) run(std::true_type{}, std::integral_constant<bool, grouped>{});
+    else run(std::false_type{}, std::integral_constant<bool, grouped>{});
     asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
     if (grouped) {   // every group of the pass gets its length (0 for the padding groups of the last block)
       for (int i = tid - 64; i < NQB * 4; i += kTcEpiWarps * 32)
@@ -612,18 +665,28 @@ int build_row_norms(prg_handle* h) {
   return PRG_OK;
 }
 
-template <int DIM, int NQB, bool BF>
-static int launch_tc(prg_handle* h, const ScanParams& p) {
+template <int DIM, int NQB, bool BF, bool GROUP>
+static int launch_tc_g(prg_handle* h, const ScanParams& p) {
   const size_t smem = scan_tc_smem_bytes<DIM, NQB, BF>();
-  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM, NQB, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_tc_kernel<DIM, NQB, BF, SCAN_THRESH, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)smem));
   if (p.n_tiles == 0) return PRG_OK;
   if (BF && !h->E16_map_ok) return fail(PRG_ESTATE, "bf16 filter index not built");
   StageScope span(h, ST_SCAN);
   const unsigned grid = p.n_tiles < (uint32_t)h->sm_count ? p.n_tiles : (unsigned)h->sm_count;
-  PRG_CUDA(launch_chained(h, recall_scan_tc_kernel<DIM, NQB, BF>, dim3(grid), dim3(kTcThreads), smem, 1,
+  PRG_CUDA(launch_chained(h, recall_scan_tc_kernel<DIM, NQB, BF, SCAN_THRESH, GROUP>, dim3(grid), dim3(kTcThreads), smem, 1,
                           BF ? (tc_half_stages<NQB, BF>() ? h->E16_map_h : h->E16_map) : h->E_map, p));
   count_launch(h);
   return PRG_OK;
+}
+template <int DIM, int NQB, bool BF>
+static int launch_tc(prg_handle* h, const ScanParams& p) {
+  if constexpr (BF) {   // GROUP mode exists over the bf16 index only (recall.cu asks for it there)
+    if (p.grp_rows) return launch_tc_g<DIM, NQB, BF, true>(h, p);
+  } else {
+    if (p.grp_rows) return fail(PRG_EINVAL, "launch_scan_tc: group mode needs the bf16 filter index");
+  }
+  return launch_tc_g<DIM, NQB, BF, false>(h, p);
 }
 
 // sample scoring on the tensor cores (bf16 index): any number of queries per launch, one grid row per block of 64
