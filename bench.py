@@ -487,8 +487,8 @@ def main():
                            "a2a": "global threshold: all-gather of per-shard sample keys, then ONE all-to-all of the candidates "
                                   "that reach it (a rank receives its own requests' lists only)"}[
                                os.environ.get("PRG_SHARD_PROTOCOL", "a2a")] if world > 1 else "none"),
-              "l2": (f"inputs larger than L2 (item matrix / its {w['items'] // world * w['dim'] * 2 / 1e9:.2f} GB bf16 filter "
-                     f"index streamed per step)" if kind != "fm" else
+              "l2": (f"inputs larger than L2 (item matrix: its {w['items'] // world * w['dim'] * 2 / 1e9:.2f} GB bf16 or "
+                     f"{w['items'] // world * (w['dim'] + 8) / 1e9:.2f} GB int8 filter index streamed per step)" if kind != "fm" else
                      "inputs larger than L2 (2.2 GB of feature tables + 1.28 GB of item fields, random rows)"),
               "request_batches_rotated": N_ROT}
 
@@ -851,15 +851,23 @@ def main():
     else:
         rows_local = T["E"].shape[0]
         filt = "ffma2" if cfg_env.get("scan_ffma2") else ("tf32" if cfg_env.get("scan_tf32") else "bf16")
+        try:   # what the last full pass actually ran (prg_recall_filter): int8 index at dim 64 and <= 64 queries per pass
+            used = eng.recall_stats()["filter"]
+            if used in ("ffma2", "tf32", "bf16", "int8"):
+                filt = used
+        except Exception:
+            pass
         q_pass = min(Bg, 256 if filt != "ffma2" else 64)
-        elem = 2 if filt == "bf16" else 4
-        alg_bytes = rows_local * w["dim"] * elem + (rows_local * 4 if filt != "ffma2" else 0) + q_pass * w["dim"] * 4
-        kernel = {"bf16": f"recall_scan_tc_kernel<{w['dim']},NQB,bf16 shadow index>",
+        elem = {"int8": 1, "bf16": 2}.get(filt, 4)
+        row_side = {"int8": 8, "ffma2": 0}.get(filt, 4)          # per-row filter parameters: {a_r, hl_r} / norm bound
+        alg_bytes = rows_local * w["dim"] * elem + rows_local * row_side + q_pass * w["dim"] * 4
+        kernel = {"int8": f"recall_scan_i8_kernel (dim {w['dim']}, int8 shadow index)",
+                  "bf16": f"recall_scan_tc_kernel<{w['dim']},NQB,bf16 shadow index>",
                   "tf32": f"recall_scan_tc_kernel<{w['dim']},NQB,tf32 on fp32 rows>",
                   "ffma2": f"recall_scan_kernel<{w['dim']},THRESH>"}[filt]
-        note = ("algorithmic bytes = what one pass must stream: rows*dim*2 (bf16 filter index) or rows*dim*4 (tf32 / ffma2 "
-                "over the fp32 rows) + rows*4 row norms + queries; the fp32 matrix is only touched for the ~5 k survivors "
-                "per query (exact re-score); see DESIGN.md 3.1")
+        note = ("algorithmic bytes = what one pass must stream: rows*dim (int8 filter index) + rows*8 (row scale and bound), "
+                "rows*dim*2 (bf16 filter index) or rows*dim*4 (tf32 / ffma2 over the fp32 rows) + rows*4 row norms, + queries; "
+                "the fp32 matrix is only touched for the ~5-7 k survivors per query (exact re-score); see DESIGN.md 3.1")
         extra = {"queries_per_pass": q_pass, "passes_per_step": -(-Bg // q_pass),
                  "fp32_matrix_bytes_per_ms": rows_local * w["dim"] * 4 / roof_ms if roof_ms > 0 else 0.0}
     achieved = alg_bytes / (roof_ms * 1e-3) / 1e9 if roof_ms > 0 else 0.0
@@ -881,7 +889,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp) and world == 1:
         try:
-            traffic = json.load(open(tp)).get(args.workload if kind == "fm" else f"scan_dim{w['dim']}")
+            traffic = json.load(open(tp)).get(args.workload if kind == "fm" else
+                                              (f"scan_dim{w['dim']}_int8" if filt == "int8" else f"scan_dim{w['dim']}"))
         except Exception:
             traffic = None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,

@@ -352,6 +352,11 @@ uint64_t prg_launch_count(prg_handle* h);
 int prg_timing(prg_handle* h, int enable, double* ms_out, uint64_t* n_out);
 /* Last recall: how many queries took the dense re-scan path, and candidates collected per query (max). */
 int prg_recall_stats(prg_handle* h, int32_t* n_fallback, int32_t* max_candidates);
+/* Last recall: which filter the full pass over the item matrix used — PRG_FILTER_NONE (dense path: every key
+ * materialised), _FFMA2 (exact fp32 scan), _TF32 (tensor cores over the fp32 rows), _BF16 (bf16 index), _INT8 (int8
+ * index: dim 64, at most 64 queries per pass; config "scan_int8", default on).  Results do not depend on it. */
+enum { PRG_FILTER_NONE = 0, PRG_FILTER_FFMA2 = 1, PRG_FILTER_TF32 = 2, PRG_FILTER_BF16 = 3, PRG_FILTER_INT8 = 4 };
+int prg_recall_filter(prg_handle* h, int32_t* kind);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ EXPORTS = [
     "prg_set_item_fields", "prg_set_feature_table", "prg_set_fm_bias", "prg_set_mlp", "prg_set_diversity_matrix",
     "prg_recall_topk", "prg_recall_local_keys", "prg_merge_keys", "prg_shard_sample_len", "prg_shard_sample",
     "prg_shard_candidates", "prg_shard_check", "prg_rank", "prg_sort_desc_host", "prg_sort_desc",
-    "prg_dpp", "prg_ssd", "prg_recommend", "prg_recommend_from_keys", "prg_lookup", "prg_launch_count", "prg_recall_stats", "prg_timing",
+    "prg_dpp", "prg_ssd", "prg_recommend", "prg_recommend_from_keys", "prg_lookup", "prg_launch_count", "prg_recall_stats", "prg_recall_filter", "prg_timing",
     "prg_batcher_start", "prg_batcher_recommend", "prg_batcher_stats", "prg_batcher_stop", "prg_batcher_drive",
     "prg_set_user_fields", "prg_set_rank_score", "prg_rank_ex", "prg_recommend_ex", "prg_recommend_from_keys_ex",
     "prg_batcher_recommend_ex", "prg_item_dim", "prg_dpp_ex",
@@ -157,7 +157,10 @@ class Engine:
     def recall_stats(self):
         a, b = C.c_int32(0), C.c_int32(0)
         self._ck(self._lib.prg_recall_stats(self._h, C.byref(a), C.byref(b)))
-        return {"fallback_queries": a.value, "max_candidates": b.value}
+        f = C.c_int32(0)
+        self._ck(self._lib.prg_recall_filter(self._h, C.byref(f)))
+        return {"fallback_queries": a.value, "max_candidates": b.value,
+                "filter": ("none", "ffma2", "tf32", "bf16", "int8")[f.value]}
 
     STAGES = ("scan", "scan_dense", "select", "gather_fm", "mlp", "sort", "dpp", "other")
 

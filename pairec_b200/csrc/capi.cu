@@ -107,6 +107,8 @@ static void free_snapshot(prg_handle* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->E_owned && s->E) cudaFree(const_cast<float*>(s->E));
   s->E16.release();
+  s->E8.release();
+  s->E8_prm.release();
   s->row_norm.release();
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -157,6 +159,8 @@ int prg_init(const char* json_cfg, prg_handle** out) {
   if (const char* ev = getenv("PRG_SCAN128_NQB")) h->scan128_nqb = atoi(ev) != 0;
   if (json_int(json_cfg, "recall_tilemax", &v)) h->recall_tilemax = v != 0;
   if (const char* ev = getenv("PRG_RECALL_TILEMAX")) h->recall_tilemax = atoi(ev) != 0;
+  if (json_int(json_cfg, "scan_int8", &v)) h->scan_int8 = v != 0;
+  if (const char* ev = getenv("PRG_SCAN_INT8")) h->scan_int8 = atoi(ev) != 0;
   if (json_int(json_cfg, "scan_groups", &v)) h->scan_groups = v < 0 ? -1 : (v != 0);
   if (const char* ev = getenv("PRG_SCAN_GROUPS")) h->scan_groups = atoi(ev) < 0 ? -1 : (atoi(ev) != 0);
   if (json_int(json_cfg, "dpp_pair", &v)) h->dpp_pair = v != 0;
@@ -190,7 +194,7 @@ void prg_destroy(prg_handle* h) {
         if (h->tables[t].linear) cudaFree(const_cast<float*>(h->tables[t].linear));
       }
     }
-    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->grp_cnt, &h->row_norm, &h->E16, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
+    DevBuf* bufs[] = {&h->q_dev, &h->sample_keys, &h->cand_keys, &h->seg_keys, &h->seg_rows, &h->grp_cnt, &h->row_norm, &h->E16, &h->E8, &h->E8_prm, &h->cand_cnt, &h->tau, &h->dense_keys, &h->topk_keys,
                       &h->out_row, &h->out_score, &h->out_n, &h->flags, &h->table_ptrs, &h->act[0], &h->act[1],
                       &h->fm_logit, &h->rank_rows, &h->rank_out, &h->mlp_Wu, &h->user_ids_dev, &h->user_dense_dev, &h->fm_state, &h->ubias, &h->rank_map, &h->pre_rows, &h->D_sub, &h->D_sub_inv, &h->dpp_hook_E, &h->dpp_hook_rows, &h->dpp_hook_in, &h->dpp_scratch, &h->dpp_rows, &h->dpp_score,
                       &h->dpp_idx, &h->dpp_n, &h->dpp_status, &h->ssd_E, &h->ssd_P, &h->sort_in, &h->sort_perm, &h->rec_rows,
@@ -254,6 +258,13 @@ int prg_recall_stats(prg_handle* h, int32_t* n_fallback, int32_t* max_candidates
   return PRG_OK;
 }
 
+int prg_recall_filter(prg_handle* h, int32_t* kind) {
+  CHECK_H(h);
+  if (!kind) return fail(PRG_EINVAL, "null buffer");
+  *kind = h->last_filter;
+  return PRG_OK;
+}
+
 // ------------------------------------------------------------------ tables
 int prg_set_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_t dim, uint64_t row_base, int mem) {
   CHECK_H(h);
@@ -271,6 +282,8 @@ int prg_set_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint32_
   h->E_row_base = row_base;
   h->row_norm.release();  // norms and the bf16 filter index are rebuilt lazily for the new matrix
   h->E16_map_ok = false;
+  h->E8_map_ok = false;
+  h->i8_backoff = 0;
   return recall_build_map(h);
 }
 
@@ -293,7 +306,7 @@ int prg_stage_item_matrix(prg_handle* h, const float* data, uint64_t rows, uint3
   prg_handle* s = new (std::nothrow) prg_handle();
   if (!s) return fail(PRG_ENOMEM, "snapshot allocation failed");
   s->device = h->device; s->sm_count = h->sm_count;
-  s->scan_filter = h->scan_filter; s->scan_ffma2 = h->scan_ffma2; s->pdl = false;
+  s->scan_filter = h->scan_filter; s->scan_ffma2 = h->scan_ffma2; s->scan_int8 = h->scan_int8; s->pdl = false;
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete s; return fail(PRG_ECUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
   const void* d = nullptr;
@@ -329,6 +342,8 @@ int prg_commit_item_matrix(prg_handle* h) {
   std::swap(h->E_map, s->E_map); std::swap(h->E_map_ok, s->E_map_ok);
   std::swap(h->E16, s->E16); std::swap(h->E16_map, s->E16_map); std::swap(h->E16_map_h, s->E16_map_h); std::swap(h->E16_map_ok, s->E16_map_ok);
   std::swap(h->row_norm, s->row_norm);
+  std::swap(h->E8, s->E8); std::swap(h->E8_prm, s->E8_prm); std::swap(h->E8_map, s->E8_map); std::swap(h->E8_map_ok, s->E8_map_ok);
+  h->i8_backoff = 0;
   free_snapshot(s);          // the previous snapshot
   return PRG_OK;
 }

@@ -73,6 +73,13 @@ struct prg_handle {
   CUtensorMap E16_map;
   CUtensorMap E16_map_h;    // the same index with boxes of half a tile (128 rows): stages of the 256-queries-per-pass filter
   bool E16_map_ok = false;
+  bool scan_int8 = true;    // config "scan_int8": dim-64 passes of <= 64 queries stream an int8 index (recall_i8.cu) instead of the bf16 one
+  prg::DevBuf E8;           // rows (padded to 512) x 64 int8: per-row-scaled shadow of the item matrix
+  prg::DevBuf E8_prm;       // rows (padded) x {s_r, hl_r} f32
+  CUtensorMap E8_map;
+  bool E8_map_ok = false;
+  int i8_backoff = 0;       // recalls that skip the int8 index after one whose candidate lists overflowed (its bound is wider than the
+                            // bf16 one: matrices whose scores barely differ, e.g. all-positive rows, overflow it first); reset with the matrix
   prg::DevBuf cand_cnt;     // B u32
   prg::DevBuf tau;          // B u64
   prg::DevBuf dense_keys;   // fallback / small-N: nq x slots u64
@@ -81,6 +88,7 @@ struct prg_handle {
   prg::DevBuf flags;        // B i32 per-query status from select
   prg::DevBuf topr_done;    // B i32: sample_topr_kernel served the query (else the generic select runs for it)
   int32_t last_fallback = 0;
+  int32_t last_filter = 0;  // PRG_FILTER_* of the last recall's full pass
   int32_t last_max_cand = 0;
   // deferred validation of the sampled recall (fused path): the per-query status is copied to pinned host memory
   // asynchronously and checked later, so the steady state has no host round trip in the middle of a step

@@ -1300,6 +1300,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   const uint32_t dim = h->E_dim;
   h->last_fallback = 0;
   h->last_max_cand = 0;
+  h->last_filter = PRG_FILTER_NONE;
 
   const uint32_t n_tiles = (uint32_t)((h->E_rows + kTileRows - 1) / kTileRows);
   const bool sampled = h->E_rows >= kSampledMinRows && (uint64_t)k * 64 <= h->E_rows;
@@ -1381,6 +1382,8 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   const bool grouped = use_tc && scan_groups_on(h) && B > kQB && n_seg <= 512 && refine_smem_bytes(cand_cap, k) <= 200 * 1024 &&
                        (uint64_t)QT * n_seg * seg_cap < (1ull << 32);
   if (grouped) PRG_TRY(h->grp_cnt.ensure(QT / kGrpQ * n_seg * 4));
+  bool i8_ok = use_tc && !grouped && scan_i8_available(h);
+  if (i8_ok && h->i8_backoff > 0) { --h->i8_backoff; i8_ok = false; }
   for (int q0 = 0; q0 < B; q0 += pass_q) {
     ScanParams sc{};
     sc.Q = q_dev + (size_t)q0 * dim; sc.nq = (B - q0 < pass_q) ? (B - q0) : pass_q;
@@ -1391,8 +1394,16 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     sc.row_norm = (const float*)h->row_norm.p;
     sc.cand_rows = use_tc ? (uint32_t*)h->seg_rows.p + (size_t)q0 * seg_q : nullptr;
     if (grouped) scan_group_outputs(h, sc, q0, n_seg, seg_cap);
-    if (use_tc) PRG_TRY(launch_scan_tc(h, sc));
-    else PRG_TRY(scan(h, SCAN_THRESH, sc));
+    if (i8_ok && sc.nq <= kQB) {
+      PRG_TRY(launch_scan_i8(h, sc, n_seg));
+      h->last_filter = PRG_FILTER_INT8;
+    } else if (use_tc) {
+      PRG_TRY(launch_scan_tc(h, sc));
+      h->last_filter = h->scan_filter == SCAN_FILTER_BF16 ? PRG_FILTER_BF16 : PRG_FILTER_TF32;
+    } else {
+      PRG_TRY(scan(h, SCAN_THRESH, sc));
+      h->last_filter = PRG_FILTER_FFMA2;
+    }
   }
   uint32_t k_pow2 = 32;
   while (k_pow2 < (uint32_t)k) k_pow2 <<= 1;
@@ -1462,6 +1473,8 @@ int recall_resolve(prg_handle* h, bool* repaired) {
       PRG_TRY(recall_dense(h, h->pending.q_dev + (size_t)q * h->E_dim, 1, k, k, h->pending.keys_out + (size_t)q * k));
     }
   }
+  // the int8 bound lets more rows through than the bf16 one: when a batch overflowed under it, the next batches use bf16
+  if (h->last_fallback > 0 && h->last_filter == PRG_FILTER_INT8) h->i8_backoff = 64;
   return PRG_OK;
 }
 

@@ -33,6 +33,7 @@ struct ScanParams {
   uint32_t seg_cap;
   uint32_t* seg_cnt;       // THRESH: [nq][gridDim.x], written once per CTA at kernel end
   const float* row_norm;   // TC filter: [n_rows] upper bounds of the row norms
+  const float2* row_q8;    // int8 filter (recall_i8.cu): [rows padded to 512] {a_r, hl_r}; set by launch_scan_i8
   uint32_t* cand_rows;     // TC filter: [nq][gridDim.x][seg_cap] surviving global rows (re-scored exactly by select)
   uint64_t* dense;         // DENSE: [nq][dense_stride], slot = t*256 + r
   uint64_t dense_stride;
@@ -87,5 +88,10 @@ int build_row_norms(prg_handle* h);
 bool scan_tc_dense_available(const prg_handle* h);
 int launch_scan_tc_dense(prg_handle* h, const ScanParams& p);   // sample scoring (approximate keys) on the tensor cores
 int launch_scan_tc_tilemax(prg_handle* h, const ScanParams& p); // sample scoring reduced to one maximum per (tile, query)
+
+// recall_i8.cu — int8 filter index (dim 64, <= 64 queries per pass)
+int build_i8_index(prg_handle* h);          // called by build_row_norms; a no-op unless scan_i8_wanted
+bool scan_i8_available(const prg_handle* h);
+int launch_scan_i8(prg_handle* h, const ScanParams& p, uint32_t n_seg);
 
 }  // namespace prg

@@ -661,6 +661,7 @@ int build_row_norms(prg_handle* h) {
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled (bf16 shadow, half tiles) failed: " + std::to_string((int)r));
     h->E16_map_ok = true;
+    PRG_TRY(build_i8_index(h));   // dim 64: the int8 index of the <= 64-query pass (recall_i8.cu)
   }
   return PRG_OK;
 }
