@@ -61,7 +61,11 @@ enum {
 
 /* ---------------------------------------------------------------- lifecycle */
 
-/* json_cfg: {"device":0,"max_batch":64,"max_k":1000,"max_candidates":1024} — all keys optional. */
+/* json_cfg: {"device":0,"max_batch":64,"max_k":1000,"max_candidates":1024} — all keys optional.
+ * Kernel-variant switches (integers; results never depend on them, only speed): "scan_int8" (1: int8 filter index for
+ * dim-64 passes of at most 64 queries, default), "scan_tf32" (1: filter over the fp32 rows, no shadow index), "scan_ffma2"
+ * (1: exact fp32 scan, no filter), "scan_groups", "scan128_nqb", "recall_tilemax", "dpp_pair", "dpp_generic", "dpp_lazy",
+ * "mlp_no_pair", "defer_check", "pdl", "sm_limit".  DESIGN.md names what each selects. */
 int prg_init(const char* json_cfg, prg_handle** out);
 void prg_destroy(prg_handle* h);
 const char* prg_last_error(void);
