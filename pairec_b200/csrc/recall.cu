@@ -574,14 +574,25 @@ __global__ void __launch_bounds__(32) rescore_kernel(const uint32_t* __restrict_
 }
 
 // GROUP mode of the tensor-core filter (ScanParams::grp_rows, passes of more than 64 queries): the filter recorded a
-// surviving row once per group of 16 queries.  One warp takes the list of one (group, filter CTA): rows are fetched
-// coalesced into the shared-memory tile as above, every lane then scores its row against the group's 16 queries — 16
-// independent fmaf chains of the arithmetic contract (dims ascending, one accumulator each) — and the keys that reach
-// the query's threshold are appended to the (query, CTA) segment the refine step reads (ballot + prefix count: the warp
-// owns those 16 segments).  Keys below tau are dropped here: every row whose exact key reaches tau is in the list
-// (filter guarantee), and the refine step's check needs nothing else.
-// A list that overflowed its capacity poisons the 16 segment counts (> seg_cap), which the refine step reports as an
-// overflow of those queries (dense redo).
+// surviving row once per group of 16 queries.  One warp takes the list of one (group, filter CTA): 32 rows at a time are
+// copied coalesced into a shared-memory tile (cp.async, no staging registers), the group's 16 queries sit beside it, and
+// the 32 x 16 exact scores of the chunk are computed as a 4 x 4 REGISTER TILE per lane — lane (r8, q4) owns rows
+// {r8 + 8 i} x queries {q4 + 4 j}: per four dims it reads four row pieces and four query pieces (eight conflict-free
+// 16-byte shared-memory loads) for 64 FMAs.  Each (row, query) score is still one fmaf chain of the arithmetic contract
+// (dims ascending, one accumulator).  The keys that reach the query's threshold are appended to the (query, CTA) segment
+// the refine step reads (ballot + prefix count among the lanes that share the query: the warp owns those 16 segments).
+// Keys below tau are dropped here: every row whose exact key reaches tau is in the list (filter guarantee), and the
+// refine step's check needs nothing else.  A list that overflowed its capacity poisons the 16 segment counts
+// (> seg_cap), which the refine step reports as an overflow of those queries (dense redo).
+// (First form: one row per lane against 16 broadcast query pieces — 17 shared-memory loads per 64 FMAs and 128 staging
+// registers at dim 128: 0.46 ms for the ~1 M records of a c5 shard step, ncu i8h, against ~0.08 ms of FMA issue.)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t src_bytes) {   // src_bytes 0: zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(32) rescore_group_kernel(const uint32_t* __restrict__ grp_rows, const uint32_t* __restrict__ grp_cnt,
                                                            uint32_t n_seg, uint32_t grp_cap, uint32_t seg_cap, int nq,
@@ -591,123 +602,92 @@ __global__ void __launch_bounds__(32) rescore_group_kernel(const uint32_t* __res
   pdl_wait();                 // chained launch: the predecessor's writes are visible from here on
   pdl_launch_dependents();
   constexpr int F4 = DIM / 4;            // 16-B pieces per row
-  constexpr int RPI = 32 / F4;           // rows fetched per load instruction (2 at dim 64, 1 at dim 128)
-  constexpr int NLD = 32 / RPI;          // load instructions per 32 rows
-  constexpr int PITCH = DIM + 4;
-  constexpr int QP = DIM + 4;            // pitch of a staged query (floats)
-  constexpr int QL = kGrpQ * F4 / 32;    // 16-B pieces of the group's queries per lane (8 / 16)
-  // Rows per lane.  Two (lane and lane + 32 of a chunk of 64: every broadcast read of a query piece feeds 8 FMAs instead of
-  // 4) was measured at dim 64 and lost: select stage of a c4 shard pass 0.119 -> 0.128 ms (gpurun r3h / r3i), the larger
-  // tile costs more resident warps than the saved shared-memory reads give back.
-  constexpr int RL = 1;
-  constexpr int CH = 32 * RL;            // rows per chunk
-  __shared__ __align__(16) float tile[CH * PITCH];
-  __shared__ __align__(16) float qs[kGrpQ * QP];
+  constexpr int RPI = 32 / F4;           // rows copied per instruction (2 at dim 64, 1 at dim 128)
+  constexpr int NLD = 32 / RPI;          // copy instructions per 32 rows
+  constexpr int PITCH = DIM + 4;         // floats; rows r, r + 1 are 4 banks apart: 8 rows x 16 B per load are conflict free
+  __shared__ __align__(16) float tile[32 * PITCH];
+  __shared__ __align__(16) float qs[kGrpQ * PITCH];
   const uint32_t seg = blockIdx.x, gi = blockIdx.y, lane = threadIdx.x;
   const int q0 = (int)gi * kGrpQ;
-  const bool own_q = lane < (uint32_t)kGrpQ && q0 + (int)lane < nq;   // lane j < 16 keeps query q0 + j's threshold and count
-  const size_t my_seg = ((size_t)(q0 + (int)(lane & (kGrpQ - 1))) * n_seg + seg);
   const uint32_t total = grp_cnt[(size_t)gi * n_seg + seg];
-  if (total > grp_cap) {
-    if (own_q) seg_cnt[my_seg] = 0xFFFFFFFFu;
+  if (total > grp_cap || total == 0) {   // lane j < 16: query q0 + j
+    if (lane < (uint32_t)kGrpQ && q0 + (int)lane < nq) seg_cnt[(size_t)(q0 + (int)lane) * n_seg + seg] = total ? 0xFFFFFFFFu : 0u;
     return;
   }
-  if (total == 0) {
-    if (own_q) seg_cnt[my_seg] = 0u;
-    return;
-  }
-  // every load that depends on nothing but `total` is issued before the first wait: the first rows' ids, the thresholds
-  // and the group's queries (one round trip instead of three)
   const uint32_t* src = grp_rows + ((size_t)gi * n_seg + seg) * grp_cap;
-  uint32_t my_row[RL];
+  uint32_t my_row = lane < total ? src[lane] : 0u;
+  const uint32_t r8 = lane >> 2, q4 = lane & 3u;
+  // thresholds of this lane's four queries (a query slot past nq gets the impossible threshold)
+  uint64_t tq[4];
 #pragma unroll
-  for (int r = 0; r < RL; ++r) my_row[r] = lane + 32u * r < total ? src[lane + 32u * r] : 0u;
-  // a query slot past nq gets the impossible threshold: nothing is ever appended for it
-  const uint64_t my_tau = own_q ? tau[q0 + (int)lane] : ~0ull;
-#pragma unroll
-  for (int u0 = 0; u0 < QL; u0 += 8) {   // eight 16-B pieces per lane in flight
-    float4 qv[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const uint32_t idx = lane + 32u * (uint32_t)(u0 + u), j = idx / F4, c = idx - j * F4;
-      qv[u] = (q0 + (int)j < nq) ? __ldg(reinterpret_cast<const float4*>(Q + (size_t)(q0 + (int)j) * DIM) + c)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const uint32_t idx = lane + 32u * (uint32_t)(u0 + u), j = idx / F4, c = idx - j * F4;
-      *reinterpret_cast<float4*>(&qs[j * QP + 4 * c]) = qv[u];
-    }
-  }
+  for (int j = 0; j < 4; ++j) tq[j] = (q0 + (int)q4 + 4 * j < nq) ? tau[q0 + (int)q4 + 4 * j] : ~0ull;
   const uint32_t sub = lane / F4, piece = lane % F4;
-  uint32_t cnt = 0;   // lane j: keys of query q0 + j so far
-  for (uint32_t base = 0; base < total; base += CH) {
-    const uint32_t n = total - base < (uint32_t)CH ? total - base : (uint32_t)CH;
-    if (base) {
 #pragma unroll
-      for (int r = 0; r < RL; ++r) my_row[r] = lane + 32u * r < n ? src[base + lane + 32u * r] : 0u;
-    }
+  for (int u = 0; u < kGrpQ / RPI; ++u) {   // the group's queries (zero rows past nq)
+    const uint32_t j = u * RPI + sub;
+    const bool in = q0 + (int)j < nq;
+    cp_async16(&qs[j * PITCH + piece * 4], Q + (in ? (size_t)(q0 + (int)j) * DIM + piece * 4 : 0), in ? 16u : 0u);
+  }
+  uint32_t cnt[4] = {0u, 0u, 0u, 0u};      // keys of query q0 + q4 + 4 j so far (the same in the eight lanes that share q4)
+  const uint32_t same_q = 0x11111111u << q4, below = (1u << lane) - 1u;
+  for (uint32_t base = 0; base < total; base += 32) {
+    const uint32_t n = total - base < 32u ? total - base : 32u;
     __syncwarp();                                               // the previous chunk's tile has been consumed
-    // coalesced fetch (RPI rows per instruction) of up to CH rows; all loads of the chunk in flight, then parked in the tile
-    float4 xv[RL][NLD];
 #pragma unroll
-    for (int r = 0; r < RL; ++r) {
-#pragma unroll
-      for (int l = 0; l < NLD; ++l) {
-        const uint32_t row_in_half = l * RPI + sub;
-        const uint32_t grow = __shfl_sync(0xffffffffu, my_row[r], row_in_half);
-        xv[r][l] = 32u * r + row_in_half < n ? __ldg(reinterpret_cast<const float4*>(E + ((size_t)grow - row_base) * DIM) + piece)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    for (int l = 0; l < NLD; ++l) {
+      const uint32_t row_in_chunk = l * RPI + sub;
+      const uint32_t grow = __shfl_sync(0xffffffffu, my_row, row_in_chunk);
+      const bool in = row_in_chunk < n;
+      cp_async16(&tile[row_in_chunk * PITCH + piece * 4], E + (in ? ((size_t)grow - row_base) * DIM + piece * 4 : 0), in ? 16u : 0u);
     }
-#pragma unroll
-    for (int r = 0; r < RL; ++r)
-#pragma unroll
-      for (int l = 0; l < NLD; ++l)
-        *reinterpret_cast<float4*>(&tile[(32 * r + l * RPI + sub) * PITCH + piece * 4]) = xv[r][l];
+    const uint32_t this_row = my_row;
+    if (base + 32 < total) my_row = base + 32 + lane < total ? src[base + 32 + lane] : 0u;   // the next chunk's ids meanwhile
+    cp_async_wait_all();
     __syncwarp();
-    float acc[RL][kGrpQ];
+    float acc[4][4];
 #pragma unroll
-    for (int r = 0; r < RL; ++r)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < kGrpQ; ++j) acc[r][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 2
     for (int d4 = 0; d4 < F4; ++d4) {
-      float4 v[RL];
+      float4 x[4], w[4];
 #pragma unroll
-      for (int r = 0; r < RL; ++r) v[r] = *reinterpret_cast<const float4*>(&tile[(32 * r + lane) * PITCH + 4 * d4]);
+      for (int i = 0; i < 4; ++i) x[i] = *reinterpret_cast<const float4*>(&tile[(r8 + 8 * i) * PITCH + 4 * d4]);
 #pragma unroll
-      for (int j = 0; j < kGrpQ; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(&qs[j * QP + 4 * d4]);   // same address in every lane: broadcast
+      for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(&qs[(q4 + 4 * j) * PITCH + 4 * d4]);
 #pragma unroll
-        for (int r = 0; r < RL; ++r) {
-          acc[r][j] = __fmaf_rn(v[r].x, w.x, acc[r][j]);
-          acc[r][j] = __fmaf_rn(v[r].y, w.y, acc[r][j]);
-          acc[r][j] = __fmaf_rn(v[r].z, w.z, acc[r][j]);
-          acc[r][j] = __fmaf_rn(v[r].w, w.w, acc[r][j]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = __fmaf_rn(x[i].x, w[j].x, acc[i][j]);
+          acc[i][j] = __fmaf_rn(x[i].y, w[j].y, acc[i][j]);
+          acc[i][j] = __fmaf_rn(x[i].z, w[j].z, acc[i][j]);
+          acc[i][j] = __fmaf_rn(x[i].w, w[j].w, acc[i][j]);
         }
-      }
     }
 #pragma unroll
-    for (int r = 0; r < RL; ++r) {
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t row_in_chunk = r8 + 8 * i;
+      const uint32_t grow = __shfl_sync(0xffffffffu, this_row, row_in_chunk);
 #pragma unroll
-      for (int j = 0; j < kGrpQ; ++j) {
-        const uint64_t key = make_key(acc[r][j], my_row[r]);
-        const uint64_t tj = __shfl_sync(0xffffffffu, my_tau, j);
-        const bool pass = lane + 32u * r < n && key >= tj;
-        const uint32_t b = __ballot_sync(0xffffffffu, pass);
-        if (b) {   // warp-uniform
-          const uint32_t cj = __shfl_sync(0xffffffffu, cnt, j);
-          if (pass) {
-            const uint32_t pos = cj + __popc(b & ((1u << lane) - 1u));
-            if (pos < seg_cap) seg_keys[((size_t)(q0 + j) * n_seg + seg) * seg_cap + pos] = key;
-          }
-          if (lane == (uint32_t)j) cnt += __popc(b);
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t key = make_key(acc[i][j], grow);
+        const bool pass = row_in_chunk < n && key >= tq[j];
+        const uint32_t b = __ballot_sync(0xffffffffu, pass) & same_q;   // the lanes that share this lane's query
+        if (pass) {
+          const uint32_t pos = cnt[j] + __popc(b & below);
+          if (pos < seg_cap) seg_keys[((size_t)(q0 + (int)q4 + 4 * j) * n_seg + seg) * seg_cap + pos] = key;
         }
+        cnt[j] += __popc(b);
       }
     }
   }
-  if (own_q) seg_cnt[my_seg] = cnt;
+  if (r8 == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (q0 + (int)q4 + 4 * j < nq) seg_cnt[(size_t)(q0 + (int)q4 + 4 * j) * n_seg + seg] = cnt[j];
+  }
 }
 
 // Select step of the tensor-core filter: one CTA per query packs the query's exact (re-scored) survivor keys into
@@ -1109,7 +1089,8 @@ static int launch_rescore(prg_handle* h, const float* q_dev, int nq, uint32_t n_
 // the re-score of a group costs 16 dot products per recorded row instead of one).
 static bool scan_groups_on(const prg_handle* h) {
   if (h->scan_filter != SCAN_FILTER_BF16) return false;   // the group form of the filter exists over the bf16 index only
-  return h->scan_groups < 0 ? h->E_dim == 64 : h->scan_groups != 0;
+  // (dim 128 with the int8 index: its pass of more than 64 queries exists in GROUP form only, recall_i8.cu)
+  return h->scan_groups < 0 ? (h->E_dim == 64 || scan_i8g_available(h)) : h->scan_groups != 0;
 }
 
 // GROUP mode: exact scores of the recorded (row, group of 16 queries) pairs -> the (query, segment) key lists + counts
@@ -1382,7 +1363,7 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   const bool grouped = use_tc && scan_groups_on(h) && B > kQB && n_seg <= 512 && refine_smem_bytes(cand_cap, k) <= 200 * 1024 &&
                        (uint64_t)QT * n_seg * seg_cap < (1ull << 32);
   if (grouped) PRG_TRY(h->grp_cnt.ensure(QT / kGrpQ * n_seg * 4));
-  bool i8_ok = use_tc && !grouped && scan_i8_available(h);
+  bool i8_ok = use_tc && ((!grouped && scan_i8_available(h)) || (grouped && scan_i8g_available(h)));
   if (i8_ok && h->i8_backoff > 0) { --h->i8_backoff; i8_ok = false; }
   for (int q0 = 0; q0 < B; q0 += pass_q) {
     ScanParams sc{};
@@ -1394,7 +1375,10 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
     sc.row_norm = (const float*)h->row_norm.p;
     sc.cand_rows = use_tc ? (uint32_t*)h->seg_rows.p + (size_t)q0 * seg_q : nullptr;
     if (grouped) scan_group_outputs(h, sc, q0, n_seg, seg_cap);
-    if (i8_ok && sc.nq <= kQB) {
+    if (i8_ok && grouped) {
+      PRG_TRY(launch_scan_i8g(h, sc, n_seg));
+      h->last_filter = PRG_FILTER_INT8;
+    } else if (i8_ok && sc.nq <= kQB) {
       PRG_TRY(launch_scan_i8(h, sc, n_seg));
       h->last_filter = PRG_FILTER_INT8;
     } else if (use_tc) {
@@ -1697,7 +1681,8 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
     sc.row_norm = (const float*)h->row_norm.p;
     sc.cand_rows = (uint32_t*)h->seg_rows.p + (size_t)q0 * seg_q;
     if (grouped) scan_group_outputs(h, sc, q0, pl.n_seg, pl.seg_cap);
-    PRG_TRY(launch_scan_tc(h, sc));
+    if (grouped && scan_i8g_available(h)) PRG_TRY(launch_scan_i8g(h, sc, pl.n_seg));   // dim 128: int8 index (recall_i8.cu)
+    else PRG_TRY(launch_scan_tc(h, sc));
   }
   {
     if (grouped) PRG_TRY(launch_rescore_groups(h, q_dev, Bg, pl.n_seg, pl.seg_cap));

@@ -93,5 +93,7 @@ int launch_scan_tc_tilemax(prg_handle* h, const ScanParams& p); // sample scorin
 int build_i8_index(prg_handle* h);          // called by build_row_norms; a no-op unless scan_i8_wanted
 bool scan_i8_available(const prg_handle* h);
 int launch_scan_i8(prg_handle* h, const ScanParams& p, uint32_t n_seg);
+bool scan_i8g_available(const prg_handle* h);   // dim 128: GROUP-mode passes of up to 256 queries
+int launch_scan_i8g(prg_handle* h, const ScanParams& p, uint32_t n_seg);
 
 }  // namespace prg

@@ -340,70 +340,371 @@ recall_scan_i8_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// dim 128, up to 256 queries per pass, GROUP output (ScanParams::grp_rows) — the pass of a C5 row shard (12.5 M x 128,
+// 1024 queries per step).  Over the bf16 index that pass is tensor-bound (one M 128 x N 256 x K 16 MMA = 128 clk, 2048 clk
+// per 256-row tile, 0.92 of the sustained bf16 rate); kind::i8 covers K = 32 per instruction in the same 128 clk — half the
+// tensor time per tile (1024 clk), below the HBM time of the tile's 32 KiB + 2 KiB (~1650 clk per SM).  An int8 row of dim
+// 128 is one 128-byte swizzle row: no pairing trick.  Stages are HALF tiles (128 rows, 16 KiB); the 2 x 256 accumulator
+// columns of a tile fill tensor memory as FOUR buffers (half tile x block of 128 queries, M 128 x N 128 MMAs) with a barrier
+// pair each: three are in front of the tensor core while one is read.  16 epilogue warps: (half, lane quarter, query
+// block) — a thread reduces 128 accumulators of its row to eight group maxima through two 32-register buffers (the next
+// tcgen05.ld in flight while a buffer is reduced), tests them against T_r and records the row once per surviving group of
+// 16 queries; rescore_group_kernel (recall.cu) then scores it exactly against the group's queries.
+constexpr int kG8Dim = 128;
+constexpr int kG8Q = 256;                        // accumulator columns per half tile (queries per pass, zero padded)
+constexpr int kG8HalfRows = 128;
+constexpr int kG8Stages = 8;                     // half-tile stages
+constexpr int kG8StageBytes = kG8HalfRows * 128; // 16 KiB
+constexpr int kG8PrmRing = 8;                   // >= kG8Stages / 2 + 3 tiles, a power of two
+constexpr int kG8QBytes = kG8Q * 128;            // B operand: 256 queries x 128 B
+constexpr int kG8Groups = kG8Q / kGrpQ;          // 16
+
+constexpr size_t scan_i8g_smem_bytes() {
+  return (size_t)kG8Stages * kG8StageBytes + kG8QBytes + kG8Q * 16 /*tq*/ + 64 /*s_cnt[16]*/ + (2 * kG8Stages + 8) * 8 + 16 +
+         (size_t)kG8PrmRing * kTileRows * 8;
+}
+
+__global__ void __launch_bounds__(kI8Threads, 1)
+recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p, const uint32_t n_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* stage_base = smem;
+  uint8_t* Qb = smem + (size_t)kG8Stages * kG8StageBytes;
+  float4* tq = reinterpret_cast<float4*>(Qb + kG8QBytes);      // [256] {tau_f, t_q, C_q, -}
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(tq + kG8Q);    // [16] records per group
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_cnt + 16);
+  uint64_t* empty = full + kG8Stages;
+  uint64_t* tfull = empty + kG8Stages;     // [4] per (half tile, block of 128 queries): accumulator buffer 2 half + block
+  uint64_t* tempty = tfull + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
+  float2* prm = reinterpret_cast<float2*>(tmem_slot + 4);      // [kG8PrmRing][256] {a_r, hl_r}
+  __shared__ float s_scale[kG8Q];
+  __shared__ float s_amax[kG8Q];
+  __shared__ uint32_t s_tmax, s_cmax;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    s_tmax = 0u; s_cmax = 0u;
+    tma_prefetch_desc(&emap);
+    for (int s = 0; s < kG8Stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 4; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kI8EpiWarps / 4); }
+    mbar_fence_init();
+  }
+  const uint32_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue_tile = [&](uint32_t i) {
+    const uint32_t t = blockIdx.x + i * gridDim.x;
+#pragma unroll
+    for (uint32_t hf = 0; hf < 2; ++hf) {
+      const uint32_t it = 2 * i + hf;
+      const uint32_t s = it % kG8Stages, ph = (it / kG8Stages) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      mbar_arrive_expect_tx(&full[s], kG8StageBytes + (hf == 0 ? kTileRows * 8 : 0));
+      if (hf == 0)   // (the parameter array is padded to whole tiles, build_i8_index)
+        bulk_load_1d(prm + (size_t)(i % kG8PrmRing) * kTileRows, p.row_q8 + (size_t)t * kTileRows, kTileRows * 8, &full[s]);
+      tma_load_2d(stage_base + (size_t)s * kG8StageBytes, &emap, 0, (int)(t * (uint32_t)kTileRows + hf * kG8HalfRows), &full[s],
+                  kEvictFirst);
+    }
+  };
+  const uint32_t n_pre = my_tiles < (uint32_t)(kG8Stages / 2) ? my_tiles : (uint32_t)(kG8Stages / 2);
+  if (tid == 0)
+    for (uint32_t i = 0; i < n_pre; ++i) issue_tile(i);
+  for (int i = tid; i < kG8QBytes / 16; i += kI8Threads) reinterpret_cast<uint4*>(Qb)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid < 16) s_cnt[tid] = 0u;
+  pdl_wait();
+
+  // ---- thresholds and queries, as in recall_scan_i8_kernel; a query is 32 float4 pieces = one warp, read twice
+  // (maxima first, quantisation second: 256 queries do not fit in registers across the block-wide decision)
+  int bad = 0;
+  for (int q = tid; q < kG8Q; q += kI8Threads) {
+    float sc = 0.f;
+    if (q < p.nq) {
+      const uint64_t t = p.tau[q];
+      const float tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
+      if (tf > 0x1p-60f && tf < 0x1p60f) sc = 1.0f / tf; else bad = 1;
+    }
+    s_scale[q] = sc;
+  }
+  constexpr int kWarps = kI8Threads / 32;   // 18
+  for (int q = warp; q < kG8Q; q += kWarps) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < p.nq) v = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)q * kG8Dim) + lane);
+    float am = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    float l1 = fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, off));
+      l1 += __shfl_xor_sync(0xffffffffu, l1, off);
+    }
+    if (!(l1 < __int_as_float(0x7F800000))) { bad = 1; am = __int_as_float(0x7FC00000); }   // NaN / inf element
+    if (lane == 0) s_amax[q] = am;
+  }
+  const bool scaled = __syncthreads_or(bad) == 0;
+  if (scaled)
+    for (int q = tid; q < p.nq && q < kG8Q; q += kI8Threads) atomicMax(&s_tmax, __float_as_uint(s_amax[q] * s_scale[q]));
+  __syncthreads();
+  const float t_pass = __fdiv_rn(__uint_as_float(s_tmax), 127.f);
+  for (int q = warp; q < kG8Q; q += kWarps) {
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < p.nq) w = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)q * kG8Dim) + lane);
+    const float am = s_amax[q];
+    float tqs;
+    if (scaled) { const float sc = s_scale[q]; w.x *= sc; w.y *= sc; w.z *= sc; w.w *= sc; tqs = t_pass; }
+    else tqs = __fdiv_rn(am, 127.f);
+    const bool usable = am == am && tqs >= 1e-30f;
+    int e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    if (usable) {
+      e0 = max(-127, min(127, __float2int_rn(__fdiv_rn(w.x, tqs))));
+      e1 = max(-127, min(127, __float2int_rn(__fdiv_rn(w.y, tqs))));
+      e2 = max(-127, min(127, __float2int_rn(__fdiv_rn(w.z, tqs))));
+      e3 = max(-127, min(127, __float2int_rn(__fdiv_rn(w.w, tqs))));
+    }
+    int l1q = abs(e0) + abs(e1) + abs(e2) + abs(e3);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) l1q += __shfl_xor_sync(0xffffffffu, l1q, off);
+    const uint32_t pk = (uint32_t)(e0 & 255) | ((uint32_t)(e1 & 255) << 8) | ((uint32_t)(e2 & 255) << 16) | ((uint32_t)(e3 & 255) << 24);
+    const int dd = lane * 4, ch = dd >> 4, within = dd & 15;     // SWIZZLE_128B: 16-B chunk index XOR row-in-group
+    *reinterpret_cast<uint32_t*>(Qb + (size_t)q * 128 + ((ch ^ (q & 7)) << 4) + within) = pk;
+    if (lane == 0) {
+      float tf = __int_as_float(0x7F800000), cq = 0.f;   // padded query slots: never reached
+      if (q < p.nq) {
+        const uint64_t t = p.tau[q];
+        tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
+        cq = (usable || am == 0.f) ? (0.5f * (float)l1q + (float)(kG8Dim / 4 + 1)) * kI8Slack : __int_as_float(0x7F800000);
+        if (scaled) atomicMax(&s_cmax, __float_as_uint(cq));
+      }
+      tq[q] = make_float4(tf, (usable ? tqs : 0.f), cq, 0.f);
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (uint32_t i = n_pre; i < my_tiles; ++i) issue_tile(i);
+      pdl_launch_dependents();
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = s32, A = B = signed int8, both K-major, N = 128, M = 128.  A half tile's 256 accumulator columns are TWO buffers
+      // of 128 queries with a barrier pair each: with one buffer per half (N = 256) the half's next MMAs waited for all of
+      // its 256 columns to be read — a load phase of ~700 clk behind every 600 clk of MMAs: 2560 clk per tile, tensor pipe
+      // 47 % busy (ncu i8h).  Four buffers in rotation keep three of them in front of the tensor core while one is read.
+      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t qb_addr = smem_u32(Qb);
+      uint32_t it = 0;
+      for (uint32_t i = 0; i < my_tiles; ++i) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half, ++it) {
+          const uint32_t s = it % kG8Stages, ph = (it / kG8Stages) & 1u;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_k_sw128(smem_u32(stage_base + (size_t)s * kG8StageBytes));
+#pragma unroll
+          for (int qb = 0; qb < 2; ++qb) {
+            const int buf = half * 2 + qb;
+            mbar_wait(&tempty[buf], (i & 1u) ^ 1u);   // this buffer's four epilogue warps have drained the previous tile
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + (uint32_t)buf * 128u;
+            const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)qb * (128u * 128u));   // queries [128 qb, +128)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_i8(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+            umma_commit(&tfull[buf]);
+          }
+          umma_commit(&empty[s]);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: 16 warps = 2 halves x 4 lane quarters x 2 column halves
+    const int ew = warp - 2;
+    const int quarter = warp & 3, half = (ew >> 2) & 1, cpart = ew >> 3;
+    const int row_local = half * 128 + quarter * 32 + lane;
+    const uint32_t grp_stride = gridDim.x * p.grp_cap;
+    uint32_t* const grp_base = p.grp_rows + (size_t)blockIdx.x * p.grp_cap + (size_t)(cpart * 8) * grp_stride;   // this warp's first group
+    const int n_grp = ((p.nq + kQB - 1) / kQB) * 4;                 // groups that have lists (whole blocks of 64 queries)
+    const int my_grp = n_grp - cpart * 8;                           // how many of this warp's eight groups exist
+    const uint32_t grp_mask = my_grp >= 8 ? 0xFFu : (my_grp > 0 ? ((1u << my_grp) - 1u) : 0u);
+    const float cmax = __uint_as_float(s_cmax);
+    const float inv_t = __fdiv_rn(1.0f, t_pass);
+    const float inf = __int_as_float(0x7F800000);
+    // (row indices in 32 bits: a shard holds fewer than 2^31 rows, recall_topk_device)
+    const uint32_t n_rows32 = (uint32_t)p.n_rows, row_base32 = (uint32_t)p.row_base, row_step = gridDim.x * (uint32_t)kTileRows;
+    const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * (uint32_t)kG8Q + (uint32_t)cpart * 128u;
+    uint64_t* const my_tfull = &tfull[half * 2 + cpart];
+    uint64_t* const my_tempty = &tempty[half * 2 + cpart];
+    uint32_t* const my_cnt = s_cnt + cpart * 8;
+    const uint32_t below = (1u << lane) - 1u;
+    auto run = [&](auto scaled_tag) {
+      constexpr bool kScaled = decltype(scaled_tag)::value;
+      uint32_t lrow = blockIdx.x * (uint32_t)kTileRows + (uint32_t)row_local;
+      for (uint32_t i = 0; i < my_tiles; ++i, lrow += row_step) {
+        mbar_wait(my_tfull, i & 1u);
+        tc_fence_after();
+        const float2 pr = prm[(i & (uint32_t)(kG8PrmRing - 1)) * (uint32_t)kTileRows + (uint32_t)row_local];
+        const float a_r = pr.x, hl_r = pr.y;
+        const bool valid = lrow < n_rows32;
+        const uint32_t grow = row_base32 + lrow;
+        int Ti = 0;
+        float s_r = 0.f;
+        if constexpr (kScaled) {
+          float T = a_r * inv_t;
+          T = (a_r < inf && !(T < 1e30f)) ? __int_as_float(0x7FC00000) : T - hl_r - cmax;
+          Ti = __float2int_ru(fminf(fmaxf(T, -2.0e9f), 2.0e9f));
+        } else {
+          s_r = __fdiv_rn(1.0f - 1e-6f, a_r);
+        }
+        uint32_t hits = 0u;
+        uint32_t x[32], y[32];
+        tmem_ld32_nowait(tcol, x);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {               // 32 columns = two groups per chunk
+          uint32_t (&cur)[32] = (c & 1) ? y : x;
+          uint32_t (&nxt)[32] = (c & 1) ? x : y;
+          tmem_ld_wait32(cur);
+          if (c + 1 < 4) tmem_ld32_nowait(tcol + (uint32_t)(c + 1) * 32u, nxt);
+          else {             // every accumulator of this warp is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(my_tempty);
+          }
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int o = g * 16;
+            if constexpr (kScaled) {
+              // a tree, not a chain: five independent maxima of three, then two levels (the chain's eight dependent
+              // VIMNMX3 were a fixed-latency stall each)
+              const int m0 = imax3((int)cur[o], (int)cur[o + 1], (int)cur[o + 2]);
+              const int m1 = imax3((int)cur[o + 3], (int)cur[o + 4], (int)cur[o + 5]);
+              const int m2 = imax3((int)cur[o + 6], (int)cur[o + 7], (int)cur[o + 8]);
+              const int m3 = imax3((int)cur[o + 9], (int)cur[o + 10], (int)cur[o + 11]);
+              const int m4 = imax3((int)cur[o + 12], (int)cur[o + 13], (int)cur[o + 14]);
+              const int m = imax3(imax3(m0, m1, m2), imax3(m3, m4, (int)cur[o + 15]), (int)0x80000000);
+              hits |= (m >= Ti) ? (1u << (c * 2 + g)) : 0u;
+            } else {
+              // per-query form: survive unless  u (I + hl_r + C_q) < tau_q,  u = s_r t_q  (a badly scaled batch; not tuned)
+              bool any = false;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 t4 = tq[cpart * 128 + c * 32 + o + j];
+                const float u = s_r * t4.y;
+                const bool under = s_r != 0.f && t4.y != 0.f && u < 1e-30f;
+                any |= under || !(u * ((float)(int)cur[o + j] + (hl_r + t4.z)) < t4.x);
+              }
+              hits |= any ? (1u << (c * 2 + g)) : 0u;
+            }
+          }
+        }
+        hits = valid ? hits & grp_mask : 0u;
+        // appends, warp-aggregated: one shared-memory atomic per group that has a survivor in this warp's 32 rows (most
+        // tiles have none, the rest usually one) instead of eight predicated atomics + stores per tile
+        uint32_t todo = __reduce_or_sync(0xffffffffu, hits);
+        while (todo) {   // warp-uniform
+          const int b = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const bool mine = (hits >> b) & 1u;
+          const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+          const int leader = __ffs(bal) - 1;
+          uint32_t start = 0;
+          if ((int)lane == leader) start = atomicAdd(&my_cnt[b], (uint32_t)__popc(bal));
+          start = __shfl_sync(0xffffffffu, start, leader);
+          const uint32_t pos = start + __popc(bal & below);
+          if (mine && pos < p.grp_cap) grp_base[(uint32_t)b * grp_stride + pos] = grow;
+        }
+      }
+    };
+    if (scaled) run(std::true_type{}); else run(std::false_type{});
+    asm volatile("bar.sync 1, %0;" ::"n"(kI8EpiWarps * 32) : "memory");
+    const int n_grp_w = ((p.nq + kQB - 1) / kQB) * 4;
+    for (int g = tid - 64; g < n_grp_w; g += kI8EpiWarps * 32) p.grp_cnt[(size_t)g * gridDim.x + blockIdx.x] = s_cnt[g];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
 // One thread per row: scale, int8 row, {a_r, hl_r}.  (Run once per matrix; the strided reads do not matter.)
+template <int DIM>
 __global__ void i8_index_kernel(const float* __restrict__ E, uint64_t rows, uint8_t* __restrict__ out8, float2* __restrict__ prm) {
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  const float4* x = reinterpret_cast<const float4*>(E + r * kI8Dim);
-  float4 v[kI8Dim / 4];
+  const float4* x = reinterpret_cast<const float4*>(E + r * DIM);
   float am = 0.f, l1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < kI8Dim / 4; ++i) {
-    v[i] = x[i];
-    am = fmaxf(am, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-    l1 += fabsf(v[i].x) + fabsf(v[i].y) + fabsf(v[i].z) + fabsf(v[i].w);
+#pragma unroll 8
+  for (int i = 0; i < DIM / 4; ++i) {
+    const float4 v = x[i];
+    am = fmaxf(am, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    l1 += fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
   }
-  float s = __fdiv_rn(am, 127.f);
+  const float s = __fdiv_rn(am, 127.f);
   const bool finite = l1 < __int_as_float(0x7F800000) || (am < __int_as_float(0x7F800000) && l1 == l1);   // l1 may overflow for finite rows
   // NaN / inf elements, or a scale that underflowed: no bound, the row always survives (a_r = NaN)
   const bool usable = finite && (am == 0.f || s >= 1e-30f);
-  uint32_t pk[kI8Dim / 4];
   int L1 = 0;
+  uint4* o = reinterpret_cast<uint4*>(out8 + r * DIM);
+#pragma unroll 2
+  for (int i4 = 0; i4 < DIM / 16; ++i4) {     // (the row is read a second time: L1 / L2 hits)
+    uint32_t pk[4];
 #pragma unroll
-  for (int i = 0; i < kI8Dim / 4; ++i) {
-    int e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-    if (usable && am != 0.f) {
-      e0 = max(-127, min(127, __float2int_rn(__fdiv_rn(v[i].x, s))));
-      e1 = max(-127, min(127, __float2int_rn(__fdiv_rn(v[i].y, s))));
-      e2 = max(-127, min(127, __float2int_rn(__fdiv_rn(v[i].z, s))));
-      e3 = max(-127, min(127, __float2int_rn(__fdiv_rn(v[i].w, s))));
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = x[i4 * 4 + i];
+      int e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+      if (usable && am != 0.f) {
+        e0 = max(-127, min(127, __float2int_rn(__fdiv_rn(v.x, s))));
+        e1 = max(-127, min(127, __float2int_rn(__fdiv_rn(v.y, s))));
+        e2 = max(-127, min(127, __float2int_rn(__fdiv_rn(v.z, s))));
+        e3 = max(-127, min(127, __float2int_rn(__fdiv_rn(v.w, s))));
+      }
+      L1 += abs(e0) + abs(e1) + abs(e2) + abs(e3);
+      pk[i] = (uint32_t)(e0 & 255) | ((uint32_t)(e1 & 255) << 8) | ((uint32_t)(e2 & 255) << 16) | ((uint32_t)(e3 & 255) << 24);
     }
-    L1 += abs(e0) + abs(e1) + abs(e2) + abs(e3);
-    pk[i] = (uint32_t)(e0 & 255) | ((uint32_t)(e1 & 255) << 8) | ((uint32_t)(e2 & 255) << 16) | ((uint32_t)(e3 & 255) << 24);
+    o[i4] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
-  uint4* o = reinterpret_cast<uint4*>(out8 + r * kI8Dim);
-#pragma unroll
-  for (int i = 0; i < kI8Dim / 16; ++i) o[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
   // {a_r, hl_r}: a_r = (1 - 1e-6) / s_r (+inf for an all-zero row), NaN = no usable bound, the row always survives
   const float nan = __int_as_float(0x7FC00000);
   prm[r] = usable ? make_float2(__fdiv_rn(1.0f - 1e-6f, s), 0.5f * (float)L1 * kI8Slack) : make_float2(nan, nan);
 }
 
-// config "scan_int8" (default on): the int8 index exists for dim-64 matrices large enough for the sampled path
+// config "scan_int8" (default on): the int8 index exists for matrices large enough for the sampled path — at dim 64 for
+// the passes of at most 64 queries, at dim 128 for the GROUP-mode passes of more than 64
 bool scan_i8_wanted(const prg_handle* h) {
-  return h->scan_int8 && h->scan_filter == SCAN_FILTER_BF16 && !h->scan_ffma2 && h->E_dim == kI8Dim &&
+  return h->scan_int8 && h->scan_filter == SCAN_FILTER_BF16 && !h->scan_ffma2 && (h->E_dim == kI8Dim || h->E_dim == kG8Dim) &&
          h->E_rows >= (uint64_t)kI8TileRows * (uint64_t)h->sm_count;
 }
-bool scan_i8_available(const prg_handle* h) { return h->E8_map_ok; }
+bool scan_i8_available(const prg_handle* h) { return h->E8_map_ok && h->E_dim == kI8Dim; }
+bool scan_i8g_available(const prg_handle* h) { return h->E8_map_ok && h->E_dim == kG8Dim; }
 
 int build_i8_index(prg_handle* h) {
   h->E8_map_ok = false;
   if (!scan_i8_wanted(h)) return PRG_OK;
   const size_t padded = (size_t)((h->E_rows + kI8TileRows - 1) / kI8TileRows) * kI8TileRows;
-  PRG_TRY(h->E8.ensure(padded * kI8Dim));
+  const size_t dim = h->E_dim;
+  PRG_TRY(h->E8.ensure(padded * dim));
   PRG_TRY(h->E8_prm.ensure(padded * 8));
-  PRG_CUDA(cudaMemsetAsync(h->E8.p, 0, padded * kI8Dim, h->stream));
+  PRG_CUDA(cudaMemsetAsync(h->E8.p, 0, padded * dim, h->stream));
   PRG_CUDA(cudaMemsetAsync(h->E8_prm.p, 0, padded * 8, h->stream));
   const unsigned grid = (unsigned)((h->E_rows + 127) / 128);
-  i8_index_kernel<<<grid, 128, 0, h->stream>>>(h->E, h->E_rows, (uint8_t*)h->E8.p, (float2*)h->E8_prm.p);
+  if (dim == kI8Dim) i8_index_kernel<kI8Dim><<<grid, 128, 0, h->stream>>>(h->E, h->E_rows, (uint8_t*)h->E8.p, (float2*)h->E8_prm.p);
+  else i8_index_kernel<kG8Dim><<<grid, 128, 0, h->stream>>>(h->E, h->E_rows, (uint8_t*)h->E8.p, (float2*)h->E8_prm.p);
   PRG_CUDA(cudaGetLastError());
   PRG_CUDA(cudaStreamSynchronize(h->stream));
   count_launch(h);
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) return fail(PRG_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[2] = {128, (cuuint64_t)(padded / 2)};
+  // dim 64: [rows / 2][128], boxes of 256 operand rows (512 matrix rows); dim 128: [rows][128], boxes of half a tile
+  cuuint64_t gdim[2] = {128, (cuuint64_t)(dim == kI8Dim ? padded / 2 : padded)};
   cuuint64_t gstride[1] = {128};
-  cuuint32_t box[2] = {128, (cuuint32_t)kI8BoxRows};
+  cuuint32_t box[2] = {128, (cuuint32_t)(dim == kI8Dim ? kI8BoxRows : kG8HalfRows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&h->E8_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->E8.p, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -415,7 +716,7 @@ int build_i8_index(prg_handle* h) {
 // One pass of <= 64 queries over the int8 index; same outputs as launch_scan_tc (cand_rows / seg_cnt, one segment per CTA
 // and query; the grid is the caller's number of segments)
 int launch_scan_i8(prg_handle* h, const ScanParams& p_in, uint32_t n_seg) {
-  if (!h->E8_map_ok) return fail(PRG_ESTATE, "int8 filter index not built");
+  if (!scan_i8_available(h)) return fail(PRG_ESTATE, "int8 filter index not built");
   if (p_in.nq > kQB || p_in.nq <= 0) return fail(PRG_EINVAL, "launch_scan_i8: 1..64 queries per pass");
   const uint32_t n_tiles = (uint32_t)((h->E_rows + kI8TileRows - 1) / kI8TileRows);
   if (n_seg == 0 || n_seg > n_tiles) return fail(PRG_EINVAL, "launch_scan_i8: more segments than tiles");
@@ -425,6 +726,23 @@ int launch_scan_i8(prg_handle* h, const ScanParams& p_in, uint32_t n_seg) {
   PRG_CUDA(cudaFuncSetAttribute(recall_scan_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   StageScope span(h, ST_SCAN);
   PRG_CUDA(launch_chained(h, recall_scan_i8_kernel, dim3(n_seg), dim3(kI8Threads), smem, 1, h->E8_map, p, n_tiles));
+  count_launch(h);
+  return PRG_OK;
+}
+
+// One GROUP-mode pass of <= 256 queries over the dim-128 int8 index; same outputs as launch_scan_tc with p.grp_rows set
+int launch_scan_i8g(prg_handle* h, const ScanParams& p_in, uint32_t n_seg) {
+  if (!scan_i8g_available(h)) return fail(PRG_ESTATE, "int8 filter index (dim 128) not built");
+  if (p_in.nq > kG8Q || p_in.nq <= 0) return fail(PRG_EINVAL, "launch_scan_i8g: 1..256 queries per pass");
+  if (!p_in.grp_rows || !p_in.grp_cnt) return fail(PRG_EINVAL, "launch_scan_i8g: group outputs missing");
+  const uint32_t n_tiles = (uint32_t)((h->E_rows + kTileRows - 1) / kTileRows);
+  if (n_seg == 0 || n_seg > n_tiles) return fail(PRG_EINVAL, "launch_scan_i8g: more segments than tiles");
+  ScanParams p = p_in;
+  p.row_q8 = (const float2*)h->E8_prm.p;
+  constexpr size_t smem = scan_i8g_smem_bytes();
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_i8g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  StageScope span(h, ST_SCAN);
+  PRG_CUDA(launch_chained(h, recall_scan_i8g_kernel, dim3(n_seg), dim3(kI8Threads), smem, 1, h->E8_map, p, n_tiles));
   count_launch(h);
   return PRG_OK;
 }

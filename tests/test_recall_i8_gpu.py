@@ -181,3 +181,88 @@ def test_snapshot_swap_rebuilds_the_int8_index(engine, oracle_lib):
     assert engine.recall_stats()["filter"] == "int8"
     orows, oscores, _ = oracle_lib.keys_split(oracle_lib.recall_topk(E2, Q, 100))
     assert (rows == orows).all() and (scores.view(np.uint32) == oscores.view(np.uint32)).all()
+
+
+# ---- dim 128: GROUP-mode passes of up to 256 queries over the int8 index (recall_scan_i8g_kernel; the C5 shard pass)
+
+def _data128(n, b, seed):
+    return _data(n, 128, b, seed)
+
+
+@pytest.mark.parametrize("n,b,k", [(350_000, 100, 200), (300_001, 256, 1000), (400_000, 300, 100), (262_144 + 255, 65, 50)])
+def test_dim128_group_passes_use_the_int8_index(engine, oracle_lib, n, b, k):
+    E, Q = _data128(n, b, seed=b)
+    st = _check(engine, oracle_lib, E, Q, k, row_base=99)
+    assert st["fallback_queries"] == 0
+
+
+def test_dim128_int8_and_bf16_give_the_same_bits(oracle_lib):
+    from pairec_b200 import Engine
+    E, Q = _data128(500_000, 150, seed=3)
+    out = {}
+    for name, cfg in (("int8", dict()), ("bf16", dict(scan_int8=0)), ("bf16g", dict(scan_int8=0, scan_groups=1))):
+        eng = Engine(0, **cfg)
+        try:
+            eng.set_item_matrix(E)
+            out[name] = eng.recall_topk(Q, 1000)
+            st = eng.recall_stats()
+            assert st["filter"] == name[:4] and st["fallback_queries"] == 0, st
+        finally:
+            eng.close()
+    for other in ("bf16", "bf16g"):
+        for a, b in zip(out["int8"], out[other]):
+            assert (np.asarray(a).view(np.uint32) == np.asarray(b).view(np.uint32)).all()
+
+
+def test_dim128_negative_thresholds_nan_rows_and_padding_groups(engine, oracle_lib):
+    # 70 queries: one full block of 64 + 6 in a block whose other groups are padding; negative thresholds force the
+    # per-query form; NaN / inf rows survive for every group that has a list and for none that has not
+    n, d = 400_000, 128
+    rng = np.random.default_rng(7)
+    E = rng.random((n, d), dtype=np.float32) + np.float32(0.1)
+    Q = -(rng.random((70, d), dtype=np.float32) + np.float32(0.1))
+    Q[5] = -Q[5]
+    Q[66] = -Q[66]
+    E[1234, 3] = np.inf
+    E[99_999, 7] = np.nan
+    E[200_000] = 0
+    _check(engine, oracle_lib, E, Q, 300)
+
+
+def test_dim128_positive_batch_with_nan_rows_and_zero_rows(engine, oracle_lib):
+    E, Q = _data128(400_000, 130, seed=11)
+    E[10, 0] = np.nan
+    E[20, 1] = np.inf
+    E[::9] = 0
+    Q[17] = 0
+    _check(engine, oracle_lib, E, Q, 500)
+
+
+def test_dim128_worst_case_quantisation_error(engine, oracle_lib):
+    n, d = 300_000, 128
+    rng = np.random.default_rng(13)
+    lvl = rng.integers(0, 126, size=(n, d)).astype(np.float32) + np.float32(0.5)
+    lvl[:, 0] = 127.0
+    E = (lvl * (2.0 ** rng.integers(-12, -6, size=(n, 1)))).astype(np.float32) / np.float32(127.0)
+    ql = rng.integers(0, 126, size=(80, d)).astype(np.float32) + np.float32(0.5)
+    ql[:, 1] = 127.0
+    Q = (ql / np.float32(127.0 * 8.0)).astype(np.float32)
+    _check(engine, oracle_lib, E, Q, 1000)
+
+
+def test_dim128_adversarial_order_falls_back_exactly(engine, oracle_lib):
+    n, d = 400_000, 128
+    rng = np.random.default_rng(17)
+    E = (rng.standard_normal((n, d)) * 0.01).astype(np.float32)
+    n_tiles = (n + 255) // 256
+    stride = n_tiles // max(64, n_tiles // 128)
+    tile = np.arange(n) // 256
+    E[:, 0] = np.where(tile % stride == 0, 0.0, 1.0 + rng.random(n) * 0.5).astype(np.float32)
+    Q = (rng.standard_normal((96, d)) * 0.01).astype(np.float32)
+    Q[:, 0] = 0
+    Q[0] = 0
+    Q[0, 0] = 1.0
+    Q[70] = 0
+    Q[70, 0] = 2.0
+    st = _check(engine, oracle_lib, E, Q, 1000)
+    assert st["fallback_queries"] >= 2
