@@ -160,6 +160,8 @@ int prg_init(const char* json_cfg, prg_handle** out) {
   if (json_int(json_cfg, "recall_tilemax", &v)) h->recall_tilemax = v != 0;
   if (const char* ev = getenv("PRG_RECALL_TILEMAX")) h->recall_tilemax = atoi(ev) != 0;
   if (json_int(json_cfg, "scan_int8", &v)) h->scan_int8 = v != 0;
+  if (json_int(json_cfg, "scan_grp16", &v)) h->scan_grp16 = v != 0;
+  if (const char* ev = getenv("PRG_SCAN_GRP16")) h->scan_grp16 = atoi(ev) != 0;
   if (const char* ev = getenv("PRG_SCAN_INT8")) h->scan_int8 = atoi(ev) != 0;
   if (json_int(json_cfg, "scan_groups", &v)) h->scan_groups = v < 0 ? -1 : (v != 0);
   if (const char* ev = getenv("PRG_SCAN_GROUPS")) h->scan_groups = atoi(ev) < 0 ? -1 : (atoi(ev) != 0);

@@ -73,6 +73,7 @@ struct prg_handle {
   CUtensorMap E16_map;
   CUtensorMap E16_map_h;    // the same index with boxes of half a tile (128 rows): stages of the 256-queries-per-pass filter
   bool E16_map_ok = false;
+  bool scan_grp16 = true;   // config "scan_grp16": dim-64 GROUP-mode passes run recall_i8.cu's 16-epilogue-warp kernel over the bf16 index (0: recall_tc.cu's)
   bool scan_int8 = true;    // config "scan_int8": dim-64 passes of <= 64 queries stream an int8 index (recall_i8.cu) instead of the bf16 one
   prg::DevBuf E8;           // rows (padded to 512) x 64 int8: per-row-scaled shadow of the item matrix
   prg::DevBuf E8_prm;       // rows (padded) x {s_r, hl_r} f32

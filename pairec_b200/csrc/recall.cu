@@ -1362,7 +1362,14 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
   // GROUP mode (config "scan_groups", default on): more than 64 queries and the on-chip refine below
   const bool grouped = use_tc && scan_groups_on(h) && B > kQB && n_seg <= 512 && refine_smem_bytes(cand_cap, k) <= 200 * 1024 &&
                        (uint64_t)QT * n_seg * seg_cap < (1ull << 32);
-  if (grouped) PRG_TRY(h->grp_cnt.ensure(QT / kGrpQ * n_seg * 4));
+  if (grouped) {
+    // a GROUP-mode pass writes the lists / lengths of every group of its kernel's query capacity (recall_tc.cu: NQB * 4
+    // groups — 16 for a last pass of 129..192 queries; a row whose norm bound is +inf survives for all of them): size
+    // both for whole passes, not for whole blocks of 64 queries
+    const size_t QTp = (QT + (size_t)pass_q - 1) / (size_t)pass_q * (size_t)pass_q;
+    PRG_TRY(h->grp_cnt.ensure(QTp / kGrpQ * n_seg * 4));
+    PRG_TRY(h->seg_rows.ensure(QTp * n_seg * seg_cap * 4));
+  }
   bool i8_ok = use_tc && ((!grouped && scan_i8_available(h)) || (grouped && scan_i8g_available(h)));
   if (i8_ok && h->i8_backoff > 0) { --h->i8_backoff; i8_ok = false; }
   for (int q0 = 0; q0 < B; q0 += pass_q) {
@@ -1382,7 +1389,10 @@ int recall_topk_device(prg_handle* h, const float* q_dev, int B, int k, uint64_t
       PRG_TRY(launch_scan_i8(h, sc, n_seg));
       h->last_filter = PRG_FILTER_INT8;
     } else if (use_tc) {
-      PRG_TRY(launch_scan_tc(h, sc));
+      // dim 64, 129..256 queries: the 16-epilogue-warp form of the GROUP pass (recall_i8.cu); up to 128 queries half of its
+      // warps would idle and recall_tc.cu's form is the faster one (c4 shard of a 2-GPU run: scan 0.110 against 0.134 ms)
+      if (grouped && h->scan_grp16 && dim == 64 && sc.nq > 128) PRG_TRY(launch_scan_g16(h, sc, n_seg));
+      else PRG_TRY(launch_scan_tc(h, sc));
       h->last_filter = h->scan_filter == SCAN_FILTER_BF16 ? PRG_FILTER_BF16 : PRG_FILTER_TF32;
     } else {
       PRG_TRY(scan(h, SCAN_THRESH, sc));
@@ -1670,7 +1680,11 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
   PRG_CUDA(cudaMemsetAsync(max_cnt, 0, 4, h->stream));
   const int pass_q = scan_tc_max_queries(h);
   const bool grouped = scan_groups_on(h) && Bg > kQB && (uint64_t)QT * seg_q < (1ull << 32);   // GROUP mode, as in recall_topk_device
-  if (grouped) PRG_TRY(h->grp_cnt.ensure(QT / kGrpQ * pl.n_seg * 4));
+  if (grouped) {   // whole passes (see recall_topk_device)
+    const size_t QTp = (QT + (size_t)pass_q - 1) / (size_t)pass_q * (size_t)pass_q;
+    PRG_TRY(h->grp_cnt.ensure(QTp / kGrpQ * pl.n_seg * 4));
+    PRG_TRY(h->seg_rows.ensure(QTp * seg_q * 4));
+  }
   for (int q0 = 0; q0 < Bg; q0 += pass_q) {
     ScanParams sc{};
     sc.Q = q_dev + (size_t)q0 * dim; sc.nq = (Bg - q0 < pass_q) ? (Bg - q0) : pass_q;
@@ -1682,6 +1696,7 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
     sc.cand_rows = (uint32_t*)h->seg_rows.p + (size_t)q0 * seg_q;
     if (grouped) scan_group_outputs(h, sc, q0, pl.n_seg, pl.seg_cap);
     if (grouped && scan_i8g_available(h)) PRG_TRY(launch_scan_i8g(h, sc, pl.n_seg));   // dim 128: int8 index (recall_i8.cu)
+    else if (grouped && h->scan_grp16 && dim == 64 && sc.nq > 128) PRG_TRY(launch_scan_g16(h, sc, pl.n_seg));
     else PRG_TRY(launch_scan_tc(h, sc));
   }
   {

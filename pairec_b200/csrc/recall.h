@@ -95,5 +95,6 @@ bool scan_i8_available(const prg_handle* h);
 int launch_scan_i8(prg_handle* h, const ScanParams& p, uint32_t n_seg);
 bool scan_i8g_available(const prg_handle* h);   // dim 128: GROUP-mode passes of up to 256 queries
 int launch_scan_i8g(prg_handle* h, const ScanParams& p, uint32_t n_seg);
+int launch_scan_g16(prg_handle* h, const ScanParams& p, uint32_t n_seg);   // dim 64, bf16 index: GROUP-mode passes, 16 epilogue warps
 
 }  // namespace prg

@@ -31,6 +31,7 @@
 // per tile, accumulators double buffered in 512 TMEM columns), 16 epilogue warps, one matrix row per thread (tcgen05.ld
 // 32x32b.x32; integer maximum per group of 16 queries, compare with T_r, append survivors to the per-CTA, per-query segments).
 #include "recall.h"
+#include <cuda_bf16.h>
 #include <type_traits>
 
 namespace prg {
@@ -69,6 +70,11 @@ __device__ __forceinline__ int i8_thr(float T) {
   return __float2int_ru(T);
 }
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(max(a, b), c); }
+__device__ __forceinline__ float fmax3f(float a, float b, float c) {  // SASS FMNMX3; NaN operands are ignored
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 
 __global__ void __launch_bounds__(kI8Threads, 1)
 recall_scan_i8_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p, const uint32_t n_tiles) {
@@ -365,8 +371,16 @@ constexpr size_t scan_i8g_smem_bytes() {
          (size_t)kG8PrmRing * kTileRows * 8;
 }
 
+// I8 = false: the same kernel over the BF16 index of a dim-64 matrix (a bf16 row of dim 64 is the same 128 bytes): the
+// GROUP-mode pass of a c4 row shard (64 G queries per rank).  recall_tc.cu's form of that pass has 8 epilogue warps with
+// 256 accumulators per thread and tile and ran at the speed of that serial chain (c4 shard of an 8-GPU run: 33 tiles per
+// SM in 63 us per pass, neither HBM- nor MMA-bound); here 16 warps take 128 each.  Filter test as in recall_tc.cu:
+// approx' < t_r = (1 - 1e-6) - ||x_r|| max_q(c ||q'_q||), c = 1.05 * 2^-8 (per-query form for badly scaled batches).
+constexpr float kG16Margin = 1.05f / 256.f;
+template <bool I8>
 __global__ void __launch_bounds__(kI8Threads, 1)
-recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p, const uint32_t n_tiles) {
+recall_scan_grp_kernel(const __grid_constant__ CUtensorMap emap, const ScanParams p, const uint32_t n_tiles) {
+  constexpr int kDim = I8 ? kG8Dim : 64;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* stage_base = smem;
   uint8_t* Qb = smem + (size_t)kG8Stages * kG8StageBytes;
@@ -377,7 +391,7 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
   uint64_t* tfull = empty + kG8Stages;     // [4] per (half tile, block of 128 queries): accumulator buffer 2 half + block
   uint64_t* tempty = tfull + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
-  float2* prm = reinterpret_cast<float2*>(tmem_slot + 4);      // [kG8PrmRing][256] {a_r, hl_r}
+  float2* prm = reinterpret_cast<float2*>(tmem_slot + 4);      // [kG8PrmRing][256] {a_r, hl_r} (bf16: 256 norm bounds f32)
   __shared__ float s_scale[kG8Q];
   __shared__ float s_amax[kG8Q];
   __shared__ uint32_t s_tmax, s_cmax;
@@ -398,9 +412,12 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
       const uint32_t it = 2 * i + hf;
       const uint32_t s = it % kG8Stages, ph = (it / kG8Stages) & 1u;
       mbar_wait(&empty[s], ph ^ 1u);
-      mbar_arrive_expect_tx(&full[s], kG8StageBytes + (hf == 0 ? kTileRows * 8 : 0));
-      if (hf == 0)   // (the parameter array is padded to whole tiles, build_i8_index)
-        bulk_load_1d(prm + (size_t)(i % kG8PrmRing) * kTileRows, p.row_q8 + (size_t)t * kTileRows, kTileRows * 8, &full[s]);
+      constexpr uint32_t kPrmBytes = kTileRows * (I8 ? 8 : 4);
+      mbar_arrive_expect_tx(&full[s], kG8StageBytes + (hf == 0 ? kPrmBytes : 0));
+      if (hf == 0) {   // (the parameter / norm arrays are padded to whole tiles: build_i8_index, build_row_norms)
+        if constexpr (I8) bulk_load_1d(prm + (size_t)(i % kG8PrmRing) * kTileRows, p.row_q8 + (size_t)t * kTileRows, kPrmBytes, &full[s]);
+        else bulk_load_1d(prm + (size_t)(i % kG8PrmRing) * kTileRows, p.row_norm + (size_t)t * kTileRows, kPrmBytes, &full[s]);
+      }
       tma_load_2d(stage_base + (size_t)s * kG8StageBytes, &emap, 0, (int)(t * (uint32_t)kTileRows + hf * kG8HalfRows), &full[s],
                   kEvictFirst);
     }
@@ -424,6 +441,9 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
     }
     s_scale[q] = sc;
   }
+  bool scaled;
+  float t_pass = 0.f;
+  if constexpr (I8) {
   constexpr int kWarps = kI8Threads / 32;   // 18
   for (int q = warp; q < kG8Q; q += kWarps) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -438,11 +458,11 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
     if (!(l1 < __int_as_float(0x7F800000))) { bad = 1; am = __int_as_float(0x7FC00000); }   // NaN / inf element
     if (lane == 0) s_amax[q] = am;
   }
-  const bool scaled = __syncthreads_or(bad) == 0;
+  scaled = __syncthreads_or(bad) == 0;
   if (scaled)
     for (int q = tid; q < p.nq && q < kG8Q; q += kI8Threads) atomicMax(&s_tmax, __float_as_uint(s_amax[q] * s_scale[q]));
   __syncthreads();
-  const float t_pass = __fdiv_rn(__uint_as_float(s_tmax), 127.f);
+  t_pass = __fdiv_rn(__uint_as_float(s_tmax), 127.f);
   for (int q = warp; q < kG8Q; q += kWarps) {
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q < p.nq) w = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)q * kG8Dim) + lane);
@@ -475,6 +495,46 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
       tq[q] = make_float4(tf, (usable ? tqs : 0.f), cq, 0.f);
     }
   }
+  } else {
+    // bf16 operands, as in recall_tc.cu: the queries (scaled by 1 / tau in a uniform pass) rounded to bf16 into the
+    // K-major SWIZZLE_128B B operand, c ||q'|| per query, its maximum for the uniform threshold
+    scaled = __syncthreads_or(bad) == 0;
+    constexpr int C4 = 16;                                  // 16-B pieces of a 64-d f32 query = lanes per query
+    constexpr int kIters = (C4 * kG8Q + kI8Threads - 1) / kI8Threads;
+    float* s_ss = s_amax;                                   // squared norms of the staged queries
+#pragma unroll 4
+    for (int itq = 0; itq < kIters; ++itq) {
+      const int i4 = tid + itq * kI8Threads;
+      const bool in = i4 < C4 * kG8Q;
+      const int q = in ? i4 / C4 : 0, c4 = i4 - q * C4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in && q < p.nq) v = __ldg(reinterpret_cast<const float4*>(p.Q + (size_t)q * 64) + c4);
+      if (scaled) { const float sc = s_scale[q]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+      float ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
+#pragma unroll
+      for (int off = 1; off < C4; off <<= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);   // lanes of one query only
+      if (in) {
+        const int e = c4 * 4, ch = e >> 3;                  // 4 bf16 = half of a 16-B chunk
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(Qb) + (size_t)q * 64 + ((ch ^ (q & 7)) << 3) + (e & 7)) = pk;
+        if (c4 == 0) s_ss[q] = ss;
+      }
+    }
+    __syncthreads();
+    for (int q = tid; q < kG8Q; q += kI8Threads) {
+      float tf = __int_as_float(0x7F800000), nq2 = 0.f;     // padded query slots: never reached
+      if (q < p.nq) {
+        const uint64_t t = p.tau[q];
+        tf = (t == 0) ? __int_as_float(0xFF800000) : key_score(t);
+        nq2 = (sqrtf(s_ss[q]) * 1.0001f + 1e-30f) * kG16Margin;
+        if (scaled) atomicMax(&s_cmax, __float_as_uint(nq2));   // non-negative floats order like their bit patterns
+      }
+      tq[q] = make_float4(tf, nq2, 0.f, 0.f);
+    }
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -496,8 +556,11 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
       // of 128 queries with a barrier pair each: with one buffer per half (N = 256) the half's next MMAs waited for all of
       // its 256 columns to be read — a load phase of ~700 clk behind every 600 clk of MMAs: 2560 clk per tile, tensor pipe
       // 47 % busy (ncu i8h).  Four buffers in rotation keep three of them in front of the tensor core while one is read.
-      constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // (bf16: D = f32 (1), A = B = bf16 (1), K = 16 per instruction — the same 32 bytes)
+      constexpr uint32_t idesc = I8 ? ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+                                    : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
       const uint32_t qb_addr = smem_u32(Qb);
+      const int n_qb = p.nq > 128 ? 2 : 1;   // a pass of at most 128 queries leaves the second block's buffers alone
       uint32_t it = 0;
       for (uint32_t i = 0; i < my_tiles; ++i) {
 #pragma unroll
@@ -508,13 +571,17 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
           const uint64_t adesc = umma_desc_k_sw128(smem_u32(stage_base + (size_t)s * kG8StageBytes));
 #pragma unroll
           for (int qb = 0; qb < 2; ++qb) {
+            if (qb >= n_qb) break;
             const int buf = half * 2 + qb;
             mbar_wait(&tempty[buf], (i & 1u) ^ 1u);   // this buffer's four epilogue warps have drained the previous tile
             tc_fence_after();
             const uint32_t d_addr = tmem_base + (uint32_t)buf * 128u;
             const uint64_t bdesc = umma_desc_k_sw128(qb_addr + (uint32_t)qb * (128u * 128u));   // queries [128 qb, +128)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_i8(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              if constexpr (I8) umma_i8(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+              else umma_bf16(d_addr, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+            }
             umma_commit(&tfull[buf]);
           }
           umma_commit(&empty[s]);
@@ -547,13 +614,20 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
       for (uint32_t i = 0; i < my_tiles; ++i, lrow += row_step) {
         mbar_wait(my_tfull, i & 1u);
         tc_fence_after();
-        const float2 pr = prm[(i & (uint32_t)(kG8PrmRing - 1)) * (uint32_t)kTileRows + (uint32_t)row_local];
-        const float a_r = pr.x, hl_r = pr.y;
+        float a_r, hl_r = 0.f;     // bf16: a_r = the row's norm bound
+        if constexpr (I8) {
+          const float2 pr = prm[(i & (uint32_t)(kG8PrmRing - 1)) * (uint32_t)kTileRows + (uint32_t)row_local];
+          a_r = pr.x; hl_r = pr.y;
+        } else {
+          a_r = reinterpret_cast<const float*>(prm + (i & (uint32_t)(kG8PrmRing - 1)) * (uint32_t)kTileRows)[row_local];
+        }
         const bool valid = lrow < n_rows32;
         const uint32_t grow = row_base32 + lrow;
         int Ti = 0;
-        float s_r = 0.f;
-        if constexpr (kScaled) {
+        float s_r = 0.f, t_r = 0.f;
+        if constexpr (!I8) {
+          t_r = fmaf(-a_r, cmax, 1.0f - 1e-6f);   // (a row whose norm bound is +inf has t_r = -inf or NaN and always survives)
+        } else if constexpr (kScaled) {
           float T = a_r * inv_t;
           T = (a_r < inf && !(T < 1e30f)) ? __int_as_float(0x7FC00000) : T - hl_r - cmax;
           Ti = __float2int_ru(fminf(fmaxf(T, -2.0e9f), 2.0e9f));
@@ -577,7 +651,24 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int o = g * 16;
-            if constexpr (kScaled) {
+            if constexpr (!I8 && kScaled) {
+              const float f0 = fmax3f(__uint_as_float(cur[o]), __uint_as_float(cur[o + 1]), __uint_as_float(cur[o + 2]));
+              const float f1 = fmax3f(__uint_as_float(cur[o + 3]), __uint_as_float(cur[o + 4]), __uint_as_float(cur[o + 5]));
+              const float f2 = fmax3f(__uint_as_float(cur[o + 6]), __uint_as_float(cur[o + 7]), __uint_as_float(cur[o + 8]));
+              const float f3 = fmax3f(__uint_as_float(cur[o + 9]), __uint_as_float(cur[o + 10]), __uint_as_float(cur[o + 11]));
+              const float f4 = fmax3f(__uint_as_float(cur[o + 12]), __uint_as_float(cur[o + 13]), __uint_as_float(cur[o + 14]));
+              const float f = fmaxf(fmax3f(f0, f1, f2), fmax3f(f3, f4, __uint_as_float(cur[o + 15])));
+              hits |= !(f < t_r) ? (1u << (c * 2 + g)) : 0u;   // (NaN accumulators are ignored by max; NaN maxima and t_r survive)
+            } else if constexpr (!I8) {
+              // per-query form: survive unless approx < tau_q - ||x_r|| c ||q||
+              bool any = false;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 t4 = tq[cpart * 128 + c * 32 + o + j];
+                any |= !(__uint_as_float(cur[o + j]) < fmaf(-a_r, t4.y, t4.x));
+              }
+              hits |= any ? (1u << (c * 2 + g)) : 0u;
+            } else if constexpr (kScaled) {
               // a tree, not a chain: five independent maxima of three, then two levels (the chain's eight dependent
               // VIMNMX3 were a fixed-latency stall each)
               const int m0 = imax3((int)cur[o], (int)cur[o + 1], (int)cur[o + 2]);
@@ -619,7 +710,8 @@ recall_scan_i8g_kernel(const __grid_constant__ CUtensorMap emap, const ScanParam
         }
       }
     };
-    if (scaled) run(std::true_type{}); else run(std::false_type{});
+    if (cpart == 1 && p.nq <= 128) { /* the MMA thread leaves the second query block alone */ }
+    else if (scaled) run(std::true_type{}); else run(std::false_type{});
     asm volatile("bar.sync 1, %0;" ::"n"(kI8EpiWarps * 32) : "memory");
     const int n_grp_w = ((p.nq + kQB - 1) / kQB) * 4;
     for (int g = tid - 64; g < n_grp_w; g += kI8EpiWarps * 32) p.grp_cnt[(size_t)g * gridDim.x + blockIdx.x] = s_cnt[g];
@@ -730,6 +822,21 @@ int launch_scan_i8(prg_handle* h, const ScanParams& p_in, uint32_t n_seg) {
   return PRG_OK;
 }
 
+// One GROUP-mode pass of <= 256 queries over the bf16 index of a dim-64 matrix (same kernel, bf16 operands)
+int launch_scan_g16(prg_handle* h, const ScanParams& p, uint32_t n_seg) {
+  if (h->E_dim != 64 || !h->E16_map_ok) return fail(PRG_ESTATE, "bf16 filter index (dim 64) not built");
+  if (p.nq > kG8Q || p.nq <= 0) return fail(PRG_EINVAL, "launch_scan_g16: 1..256 queries per pass");
+  if (!p.grp_rows || !p.grp_cnt || !p.row_norm) return fail(PRG_EINVAL, "launch_scan_g16: group outputs / norms missing");
+  const uint32_t n_tiles = (uint32_t)((h->E_rows + kTileRows - 1) / kTileRows);
+  if (n_seg == 0 || n_seg > n_tiles) return fail(PRG_EINVAL, "launch_scan_g16: more segments than tiles");
+  constexpr size_t smem = scan_i8g_smem_bytes();
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_grp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  StageScope span(h, ST_SCAN);
+  PRG_CUDA(launch_chained(h, recall_scan_grp_kernel<false>, dim3(n_seg), dim3(kI8Threads), smem, 1, h->E16_map_h, p, n_tiles));
+  count_launch(h);
+  return PRG_OK;
+}
+
 // One GROUP-mode pass of <= 256 queries over the dim-128 int8 index; same outputs as launch_scan_tc with p.grp_rows set
 int launch_scan_i8g(prg_handle* h, const ScanParams& p_in, uint32_t n_seg) {
   if (!scan_i8g_available(h)) return fail(PRG_ESTATE, "int8 filter index (dim 128) not built");
@@ -740,9 +847,9 @@ int launch_scan_i8g(prg_handle* h, const ScanParams& p_in, uint32_t n_seg) {
   ScanParams p = p_in;
   p.row_q8 = (const float2*)h->E8_prm.p;
   constexpr size_t smem = scan_i8g_smem_bytes();
-  PRG_CUDA(cudaFuncSetAttribute(recall_scan_i8g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PRG_CUDA(cudaFuncSetAttribute(recall_scan_grp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   StageScope span(h, ST_SCAN);
-  PRG_CUDA(launch_chained(h, recall_scan_i8g_kernel, dim3(n_seg), dim3(kI8Threads), smem, 1, h->E8_map, p, n_tiles));
+  PRG_CUDA(launch_chained(h, recall_scan_grp_kernel<true>, dim3(n_seg), dim3(kI8Threads), smem, 1, h->E8_map, p, n_tiles));
   count_launch(h);
   return PRG_OK;
 }

@@ -266,3 +266,39 @@ def test_dim128_adversarial_order_falls_back_exactly(engine, oracle_lib):
     Q[70, 0] = 2.0
     st = _check(engine, oracle_lib, E, Q, 1000)
     assert st["fallback_queries"] >= 2
+
+
+# ---- dim 64, more than 64 queries: the GROUP-mode pass over the bf16 index through the 16-epilogue-warp kernel
+# (recall_scan_grp_kernel<false>, config scan_grp16) against recall_tc.cu's form of the same pass
+
+@pytest.mark.parametrize("b", [70, 128, 129, 256, 300])
+def test_dim64_group_pass_kernels_agree(oracle_lib, b):
+    from pairec_b200 import Engine
+    E, Q = _data(500_000, 64, b, seed=200 + b)
+    E[77, 5] = np.nan
+    E[78] = 0
+    out = []
+    for grp16 in (1, 0):
+        eng = Engine(0, scan_grp16=grp16)
+        try:
+            eng.set_item_matrix(E, row_base=31)
+            out.append(eng.recall_topk(Q, 500))
+            st = eng.recall_stats()
+            assert st["filter"] == "bf16" and st["fallback_queries"] == 0, st
+        finally:
+            eng.close()
+    for a, c in zip(out[0], out[1]):
+        assert (np.asarray(a).view(np.uint32) == np.asarray(c).view(np.uint32)).all()
+    orows, oscores, _ = oracle_lib.keys_split(oracle_lib.recall_topk(E, Q, 500, row_base=31))
+    assert (out[0][0] == orows).all() and (out[0][1].view(np.uint32) == oscores.view(np.uint32)).all()
+
+
+def test_dim64_group_pass_negative_thresholds(engine, oracle_lib):
+    n, d = 400_000, 64
+    rng = np.random.default_rng(301)
+    E = rng.random((n, d), dtype=np.float32) + np.float32(0.1)
+    Q = -(rng.random((140, d), dtype=np.float32) + np.float32(0.1))
+    Q[5] = -Q[5]
+    Q[130] = -Q[130]
+    E[1234, 3] = np.inf
+    _check(engine, oracle_lib, E, Q, 300, want_filter="bf16")
