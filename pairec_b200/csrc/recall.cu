@@ -1695,6 +1695,7 @@ int recall_shard_candidates_device(prg_handle* h, const float* q_dev, int Bg, in
     sc.row_norm = (const float*)h->row_norm.p;
     sc.cand_rows = (uint32_t*)h->seg_rows.p + (size_t)q0 * seg_q;
     if (grouped) scan_group_outputs(h, sc, q0, pl.n_seg, pl.seg_cap);
+    h->last_filter = (grouped && scan_i8g_available(h)) ? PRG_FILTER_INT8 : (h->scan_filter == SCAN_FILTER_BF16 ? PRG_FILTER_BF16 : PRG_FILTER_TF32);
     if (grouped && scan_i8g_available(h)) PRG_TRY(launch_scan_i8g(h, sc, pl.n_seg));   // dim 128: int8 index (recall_i8.cu)
     else if (grouped && h->scan_grp16 && dim == 64 && sc.nq > 128) PRG_TRY(launch_scan_g16(h, sc, pl.n_seg));
     else PRG_TRY(launch_scan_tc(h, sc));
