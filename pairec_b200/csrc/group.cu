@@ -71,7 +71,7 @@ struct GroupDev {
   uint32_t* row_host = nullptr;    // pinned results of this GPU's B requests
   double* score_host = nullptr;
   int32_t* n_host = nullptr;
-  size_t res_cap = 0;
+  size_t res_cap = 0, n_cap = 0;   // capacities of row_host / score_host (results) and of n_host (requests)
   int rc = PRG_OK;
   std::string err;
 };
@@ -365,15 +365,15 @@ int prg_group_recommend(prg_group* grp, const float* q, int n_requests, int reca
     PRG_TRY(d.out_n.ensure((size_t)B * 4));
     PRG_TRY(d.peers1.ensure((size_t)G * sizeof(void*)));
     PRG_TRY(d.peers2.ensure((size_t)G * sizeof(void*)));
-    if (d.res_cap < TT) {
+    if (d.res_cap < TT || d.n_cap < (size_t)B) {   // (a later call may have fewer results per request but more requests)
       if (d.row_host) cudaFreeHost(d.row_host);
       if (d.score_host) cudaFreeHost(d.score_host);
       if (d.n_host) cudaFreeHost(d.n_host);
-      d.row_host = nullptr; d.score_host = nullptr; d.n_host = nullptr; d.res_cap = 0;
+      d.row_host = nullptr; d.score_host = nullptr; d.n_host = nullptr; d.res_cap = 0; d.n_cap = 0;
       PRG_CUDA(cudaHostAlloc((void**)&d.row_host, TT * 4, cudaHostAllocPortable));
       PRG_CUDA(cudaHostAlloc((void**)&d.score_host, TT * 8, cudaHostAllocPortable));
       PRG_CUDA(cudaHostAlloc((void**)&d.n_host, (size_t)B * 4 + 16, cudaHostAllocPortable));
-      d.res_cap = TT;
+      d.res_cap = TT; d.n_cap = (size_t)B;
     }
     p1[(size_t)g] = (uint4*)d.samp_all.p;
     p2[(size_t)g] = (uint64_t*)d.cand_in.p;

@@ -89,6 +89,21 @@ def test_group_equals_unsharded_path(G, d, n_req, k):
         finally:
             ref.close()
         assert (rows2 == w2[0]).all() and (scores2.view(np.uint64) == w2[1].view(np.uint64)).all() and (cnt2 == w2[2]).all()
+        # more requests than any call before but fewer results in total (3 x the requests, top_n 20 -> 5): the per-request
+        # count staging grows although the result staging does not
+        if 3 * n_req <= 100:
+            p3 = DppParams(top_n=5, alpha=1.0, window_size=10)
+            Q3 = np.ascontiguousarray(np.tile(Q, (3, 1)))
+            rows3, scores3, cnt3, _ = grp.recommend(Q3, k, MODEL_FM_MLP, p3)
+            ref = _reference(n, d, F, U, nd, dims, E, fields, factors, linear, D)
+            try:
+                w3 = ref.recommend(Q, k, MODEL_FM_MLP, p3)
+            finally:
+                ref.close()
+            for r in range(3):
+                s = slice(r * n_req, (r + 1) * n_req)
+                assert (rows3[s] == w3[0]).all() and (scores3[s].view(np.uint64) == w3[1].view(np.uint64)).all()
+                assert (cnt3[s] == w3[2]).all()
     finally:
         grp.close()
         for e in engs:
