@@ -587,9 +587,14 @@ static double g_dot_unitary(const double* x, const double* y, int n) {
   for (; i < n; ++i) s0 += x[i] * y[i];
   return (s0 + s2) + (s1 + s3);
 }
-/* gonum blas Dgemm(NoTrans, Trans) element: k is processed in blocks of 64, each block one DotUnitary, block
- * results added to C in order.  [UNVERIFIED-UPSTREAM] */
-static double g_gemm_nt_elem(const double* a, const double* b, int k) {
+/* gonum blas Dgemm(NoTrans, Trans) element of an (items x k) * (items x k)^T product.  dgemmParallel
+ * (blas/gonum/dgemm.go) cuts C into 64 x 64 blocks and walks k in blocks of 64 — each k block one DotUnitary, block
+ * results added to C in order — but when the product has fewer than minParBlock = 4 blocks of C, i.e. items <= 64, it
+ * calls dgemmSerial on the whole problem: ONE DotUnitary over all of k.  The two differ in the last bit once k > 64.
+ * [UNVERIFIED-UPSTREAM] */
+static int g_gemm_serial(int items) { return ((items + 63) / 64) * ((items + 63) / 64) < 4; }
+static double g_gemm_nt_elem(const double* a, const double* b, int k, int serial) {
+  if (serial) return 0.0 + g_dot_unitary(a, b, k);
   double c = 0.0;
   for (int k0 = 0; k0 < k; k0 += 64) {
     const int len = (k - k0 < 64) ? (k - k0) : 64;
@@ -623,7 +628,7 @@ typedef struct {
  * matrix of :372-475, element for element.  F: n x (D+1) features, r: n quality terms. */
 static void dpp_L_row(const double* F, const double* r, int n, int D1, int j, double* out) {
   for (int i = 0; i < n; ++i) {
-    const double s = g_gemm_nt_elem(F + (size_t)j * D1, F + (size_t)i * D1, D1); /* S[j][i] */
+    const double s = g_gemm_nt_elem(F + (size_t)j * D1, F + (size_t)i * D1, D1, g_gemm_serial(n)); /* S[j][i] */
     out[i] = (r[j] * s) * r[i];                                                   /* diag(r) S diag(r), :466-472 */
   }
 }
@@ -638,7 +643,7 @@ static int dpp_once(const double* F, const double* r, int n, int D1, int top_n, 
   int ny = 0;
   for (int i = 0; i < n; ++i) {
     if (index_of(existed, n_existed, i) < 0) {
-      const double s = g_gemm_nt_elem(F + (size_t)i * D1, F + (size_t)i * D1, D1);
+      const double s = g_gemm_nt_elem(F + (size_t)i * D1, F + (size_t)i * D1, D1, g_gemm_serial(n));
       d2[i] = (r[i] * s) * r[i];
     } else d2[i] = NAN;
   }
@@ -798,7 +803,7 @@ ORC_API int orc_dpp_request_ex(const double* emb, const uint8_t* present, const 
       if (L_row0) { dpp_L_row(F, r, m, D1, 0, row); memcpy(L_row0, row, sizeof(double) * (size_t)m); }
       if (L_diag)
         for (int i = 0; i < m; ++i) {
-          const double sii = g_gemm_nt_elem(F + (size_t)i * D1, F + (size_t)i * D1, D1);
+          const double sii = g_gemm_nt_elem(F + (size_t)i * D1, F + (size_t)i * D1, D1, g_gemm_serial(m));
           L_diag[i] = (r[i] * sii) * r[i];
         }
       free(row);

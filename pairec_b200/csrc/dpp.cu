@@ -236,10 +236,13 @@ __global__ void __launch_bounds__(kDppMaxItems, 1) dpp_kernel(const DppArgs a) {
   };
   // S[j][i] in gonum Dgemm(NoTrans,Trans) order: 64-wide k blocks, DotUnitary = 4 partial sums, (s0+s2)+(s1+s3).
   // other[] holds f_j (shared memory) or nullptr for the diagonal (f_j == f_i).
+  // At most 64 items: dgemmParallel (blas/gonum/dgemm.go) sees fewer than minParBlock = 4 blocks of C and calls dgemmSerial
+  // on the whole product — ONE DotUnitary over all of k, no k blocks (oracle.c g_gemm_serial).
+  const int kblk = (m <= 64) ? D1 : 64;
   auto gram = [&](const double* other) -> double {
     double acc = 0.0;
-    for (int k0 = 0; k0 < D1; k0 += 64) {
-      const int len = (D1 - k0 < 64) ? (D1 - k0) : 64;
+    for (int k0 = 0; k0 < D1; k0 += kblk) {
+      const int len = (D1 - k0 < kblk) ? (D1 - k0) : kblk;
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
       int t = 0;
       for (; t + 4 <= len; t += 4) {
@@ -399,6 +402,19 @@ int dpp_device(prg_handle* h, const uint32_t* rows_dev, const double* score_dev,
   int c_rows = p.top_n <= window ? p.top_n : window;
   if (c_rows < 6) c_rows = 6;  // the region doubles as presort staging (4096 x 12 B)
   if (c_rows > 24) return fail(PRG_EUNSUPPORTED, "prg_dpp: window (or top_n when <= window) > 24");
+  // The fast kernels below build S = F F^T in gonum's 64-wide k blocks (dgemmParallel).  With at most 64 items the
+  // reference takes dgemmSerial instead (one dot product over all D + 1 features, dpp_kernel's kblk): a different last
+  // bit once D + 1 > 64.  Where the host can see that no request of the call keeps more than 64 candidates, the generic
+  // kernel serves it; a request that falls to <= 64 only through MinScorePercent or padding rows stays on the blocked order.
+  int m_upper = n;
+  if (p.candidate_count > 0 && n > p.top_n) {
+    const int cnt = p.candidate_count > p.top_n ? p.candidate_count : p.top_n;
+    if (cnt < m_upper) m_upper = cnt;
+  }
+  const bool serial_gemm = (int)h->D_dim + 1 > 64 && m_upper <= 64;
+  if (serial_gemm)
+    return dpp_generic_launch(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, c_rows, h->D, h->D_rows, (int)h->D_dim,
+                              h->D_dtype, 0, 0);
   if (!h->dpp_generic && h->dpp_lazy) {  // config "dpp_lazy": one CTA per request, lazy evaluation of the greedy step (dpp_lazy.cu)
     bool handled = false;
     PRG_TRY(dpp_lazy_device(h, rows_dev, score_dev, B, n, p, out_idx, out_n, status, &handled));

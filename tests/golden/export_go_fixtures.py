@@ -82,6 +82,11 @@ def fixtures():
         "dpp_minmax.json": dpp_fixture("minmax", 100, 16, 20, 10, seed=106, norm_mode=2, sort_scores=True),
         "dpp_zero_scores.json": dpp_fixture("zero_scores", 50, 8, 10, 10, seed=107, norm_mode=1, zero_scores=True),
         "dpp_topn_gt_n.json": dpp_fixture("topn_gt_n", 25, 16, 50, 10, seed=108),
+        # both sides of gonum's serial / blocked Dgemm switch (at most 64 items: one DotUnitary over all of k; more: 64-wide
+        # k blocks) with D + 1 > 64, where the two orders round L differently (oracle.c g_gemm_serial)
+        "dpp_gemm_serial_48.json": dpp_fixture("gemm_serial_48", 48, 96, 12, 10, seed=113),
+        "dpp_gemm_serial_64.json": dpp_fixture("gemm_serial_64", 64, 80, 20, 10, seed=114),
+        "dpp_gemm_blocked_65.json": dpp_fixture("gemm_blocked_65", 65, 80, 20, 10, seed=115),
         "dpp_hook_table.json": dpp_fixture("hook_table", 200, 32, 30, 10, seed=109, hook_dim=6),
         "dpp_hook_only.json": dpp_fixture("hook_only", 200, 0, 30, 10, seed=110, hook_dim=12, use_table=False),
         "dpp_hook_raw.json": dpp_fixture("hook_raw", 200, 0, 30, 10, seed=111, hook_dim=12, use_table=False, normalize_emb=False),

@@ -34,7 +34,11 @@ def dot_unitary(x, y):
     return (s[0] + s[2]) + (s[1] + s[3])
 
 
-def gemm_nt(a, b):
+def gemm_nt(a, b, serial=False):
+    """One element of gonum Dgemm(NoTrans, Trans): k in blocks of 64 (dgemmParallel), or — when the product has fewer than
+    four 64 x 64 blocks of C, i.e. at most 64 items — one DotUnitary over all of k (dgemmSerial)."""
+    if serial:
+        return 0.0 + dot_unitary(a, b)
     c = 0.0
     for k0 in range(0, len(a), 64):
         c += dot_unitary(a[k0:k0 + 64], b[k0:k0 + 64])
@@ -64,7 +68,8 @@ def kernel_matrix(emb, rel, alpha, normalize=True):
         f = [v * c for v in f]
         F.append(f)
         r.append(math.exp(alpha * rel[i]))
-    return [[(r[i] * gemm_nt(F[i], F[j])) * r[j] for j in range(n)] for i in range(n)]
+    serial = ((n + 63) // 64) ** 2 < 4
+    return [[(r[i] * gemm_nt(F[i], F[j], serial)) * r[j] for j in range(n)] for i in range(n)]
 
 
 def dpp(L, top_n, existed):

@@ -151,6 +151,32 @@ def test_golden_dpp_and_python_restatement(oracle_lib):
     assert (np.array(L) == Lc).all(), "kernel matrix differs from the Python restatement"
 
 
+def test_dpp_kernel_matrix_small_products_take_the_serial_gemm(oracle_lib):
+    """gonum dgemmParallel hands a product with fewer than four 64 x 64 blocks of C (at most 64 items) to dgemmSerial: one
+    DotUnitary over all of k instead of k blocks of 64 — a different rounding once D + 1 > 64.  The C oracle and the
+    independent Python restatement agree bit for bit on both sides of the threshold, and the two forms really differ."""
+    rng = np.random.default_rng(64)
+    D = 96
+    for n in (40, 64, 65):
+        emb = rng.standard_normal((n, D))
+        rel = rng.random(n)
+        Lc = oracle_lib.dpp_kernel_matrix(emb, rel, alpha=1.0)
+        Lp = np.array(ref_py.kernel_matrix(emb.tolist(), rel.tolist(), 1.0))
+        assert (Lc.view(np.uint64) == Lp.view(np.uint64)).all(), n
+    b = rng.standard_normal(97).tolist()
+    n_diff = 0
+    for _ in range(50):
+        a = rng.standard_normal(97).tolist()
+        n_diff += ref_py.gemm_nt(a, b, True) != ref_py.gemm_nt(a, b, False)
+    assert n_diff > 0, "the serial and the blocked summation orders should round differently somewhere"
+    # the selection follows the same rule: 40 candidates, top 12
+    emb = rng.standard_normal((40, D))
+    score = rng.random(40)
+    idx, st = oracle_lib.dpp_request(emb, score, 12, alpha=1.0, window_size=10)
+    L = ref_py.kernel_matrix(emb.tolist(), score.tolist(), 1.0)
+    assert st == 0 and ref_py.dpp_with_window(L, 12, 10) == idx.tolist()
+
+
 def test_dpp_kernel_matrix_matches_closed_form(oracle_lib):
     rng = np.random.default_rng(5)
     emb = rng.standard_normal((30, 12))

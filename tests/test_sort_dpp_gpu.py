@@ -67,6 +67,48 @@ def test_dpp_top_n_larger_than_candidates(engine, oracle_lib):
     _dpp_case(engine, oracle_lib, n=25, dim=16, top_n=50, alpha=1.0, window_size=10)
 
 
+def _order_sensitive_pair(dim, seed=7):
+    """Two raw embeddings a and b = a permuted whose squared norms, summed the way gonum's Dgemm sums them, compare
+    differently under its two code paths: b > a with ONE DotUnitary over all dim + 1 features (dgemmSerial, at most 64
+    items), b <= a with 64-wide k blocks (dgemmParallel).  The first DPP pick then tells which order a kernel used."""
+    from tests import ref_py
+    rng = np.random.default_rng(seed)
+    c = 0.70710678118654752440
+    for _ in range(20000):
+        a = rng.standard_normal(dim).astype(np.float32)
+        b = a[rng.permutation(dim)]
+        fa = [float(v) * c for v in a] + [c]
+        fb = [float(v) * c for v in b] + [c]
+        if ref_py.gemm_nt(fb, fb, True) > ref_py.gemm_nt(fa, fa, True) and ref_py.gemm_nt(fb, fb, False) <= ref_py.gemm_nt(fa, fa, False):
+            return a, b
+    raise AssertionError("no order-sensitive pair found")
+
+
+@pytest.mark.parametrize("dim", [64, 128])
+def test_dpp_small_lists_use_the_serial_gemm_order(engine, oracle_lib, dim):
+    """At most 64 candidates: the reference's S = F F^T goes through dgemmSerial (one dot product over all of k), above
+    that through 64-wide k blocks — the last bit of L differs once dim + 1 > 64 (oracle.c g_gemm_serial).  Items 0 and 1
+    (score 0 -> quality exactly 1, raw embeddings) are built so that the first pick is 1 under the serial order and 0 under
+    the blocked one; the fillers score far lower."""
+    from pairec_b200 import DppParams
+    a, b = _order_sensitive_pair(dim)
+    rng = np.random.default_rng(dim)
+    D = (rng.standard_normal((200, dim)) * 0.5).astype(np.float32)
+    D[0], D[1] = a, b
+    engine.set_diversity_matrix(D)
+    p = DppParams(top_n=3, alpha=1.0, window_size=10, normalize_emb=0)
+    first = {}
+    for n in (40, 64, 65, 120):
+        rows = np.arange(n, dtype=np.uint32).reshape(1, -1)
+        score = np.concatenate([[0.0, 0.0], -3.0 - 2.0 * rng.random(n - 2)]).reshape(1, -1)
+        idx, cnt, st = engine.dpp(rows, score, p)
+        want, wst = oracle_lib.dpp_request(D[rows[0]].astype(np.float64), score[0], 3, alpha=1.0, window_size=10, normalize_emb=0)
+        assert st[0] == wst == 0 and cnt[0] == len(want)
+        assert (idx[0, :cnt[0]] == want).all(), f"n = {n}: selection sequence differs from the oracle"
+        first[n] = int(idx[0, 0])
+    assert first == {40: 1, 64: 1, 65: 0, 120: 0}, first
+
+
 def test_dpp_all_zero_scores_is_flagged(engine, oracle_lib):
     from pairec_b200 import DppParams
     D = synth.diversity(n_items=500, dim=16)
