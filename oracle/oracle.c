@@ -743,6 +743,10 @@ ORC_API int orc_dpp_request_ex(const double* emb, const uint8_t* present, const 
   for (int i = 0; i < m; ++i) rel[i] = score[order[i]];
   int err = 0;
   if (p->norm_mode == 1) { /* stat.PopMeanVariance + StdScore */
+    /* [UNVERIFIED-UPSTREAM] the mean is stat.Mean -> floats.Sum -> f64.Sum, which on amd64 is an SSE2 kernel with eight
+     * partial sums that first peels one element when the slice is not 16-byte aligned: its last bit depends on the
+     * address of the slice and cannot be pinned by any fixture.  Restated in the plain sequential (noasm) order; the
+     * z-scores that follow can differ from an amd64 run in the last bits (abtest mode dpp_norm_relevance_score = 1 only). */
     double mean = 0;
     for (int i = 0; i < m; ++i) mean += rel[i];
     mean /= (double)m;
