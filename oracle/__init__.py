@@ -35,6 +35,8 @@ def lib():
         _lib.orc_make_key.restype = C.c_uint64
         _lib.orc_make_key.argtypes = [C.c_float, C.c_uint32]
         _lib.orc_sigmoid.restype = C.c_float
+        _lib.orc_exp.restype = C.c_double
+        _lib.orc_exp.argtypes = [C.c_double]
         _lib.orc_sigmoid.argtypes = [C.c_float]
         _lib.orc_rank_score_expr.restype = C.c_double
         _lib.orc_bf16_to_f32.restype = C.c_float
@@ -130,6 +132,12 @@ def gather_fm(fields, factors, linear, w0, rows, want_x=True, user_ids=None, use
                                   _p(logit, C.c_float), _p(x, C.c_float) if want_x else None)
     assert rc == 0
     return logit, x
+
+
+def exp(x):
+    """libm exp exactly as oracle.c calls it (element by element; fixtures only)."""
+    f = lib().orc_exp
+    return np.array([f(float(v)) for v in np.asarray(x, dtype=np.float64).ravel()], dtype=np.float64)
 
 
 def sigmoid(logit):

@@ -271,6 +271,9 @@ ORC_API int orc_gather_fm_user(const uint32_t* fields, uint64_t field_rows, uint
 
 /* score = (float)(1 / (1 + exp(-(double)logit))): the f32 AlgoResponse score, evaluated through fp64 so that the
  * CPU and GPU libm differences (<= 1 ulp of fp64) vanish in the f32 rounding. */
+/* libm exp as this oracle calls it (Go's math.Exp has an assembly kernel of its own on amd64 / arm64 / s390x and can differ
+ * from it in the last bit: baseline/go injects these values where it pins gonum's summation order) */
+ORC_API double orc_exp(double x) { return exp(x); }
 ORC_API float orc_sigmoid(float logit) { return (float)(1.0 / (1.0 + exp(-(double)logit))); }
 
 /* ------------------------------------------------------------------------------------------------ MLP */

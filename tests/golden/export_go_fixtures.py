@@ -41,7 +41,10 @@ def dpp_fixture(name, n, dim, top_n, window, seed, alpha=1.0, norm_mode=0, norma
     return {"name": name, "emb": _m(emb) if use_table else [], "hook": _m(hook) if hook_dim else [], "score": _f(score),
             "alpha": alpha, "top_n": top_n, "window": window, "norm_mode": norm_mode, "normalize_emb": normalize_emb,
             "ensure_positive_sim": ensure_pos, "expect_idx": [int(i) for i in idx] if st == 0 else [],
-            "expect_l_diag": _f(Ld) if st == 0 else [], "expect_l_row0": _f(L0) if st == 0 else [], "expect_status": st}
+            "expect_l_diag": _f(Ld) if st == 0 else [], "expect_l_row0": _f(L0) if st == 0 else [], "expect_status": st,
+            # quality terms exp(alpha * score) as the oracle's libm gives them (norm_mode 0 only): Go's math.Exp can differ in
+            # the last bit, and the test that pins gonum's Dgemm order takes them from here
+            "expect_r": _f(oracle.exp(alpha * score)) if (st == 0 and norm_mode == 0) else []}
 
 
 def ssd_fixture(name, n, dim, top_n, window, seed, gamma=0.25, norm_mode=0, use_ssd_star=False):
