@@ -146,6 +146,103 @@ int ph_register_gpu_rank(ph_server* s, const char* scene, const char* name, int 
   rank::RegisterRank(scene, std::make_shared<rank::GpuRank>(s->catalog, name, model, parse_field_specs(spec), std::move(cols), heads));
   return 0;
 }
+// The GPU rank as an IAlgorithm for scenes whose RankConf.Processor is "EasyRec" (algorithm.RegisterAlgorithm): the stock
+// RankService hands it one easyrec.PBRequest per batch — item ids + the request's user features (algo_data.go:292-325).
+// outputs_json: the tower's head names in order (one name or none: single-score responses).
+int ph_register_gpu_easyrec(ph_server* s, const char* algo_name, int model, const char* user_fields_json,
+                            const char* dense_columns_json, const char* outputs_json) {
+  if (!s || !s->catalog->h || !algo_name) { g_err = "no engine attached / null argument"; return 1; }
+  Json spec, dense, outs;
+  std::string err;
+  if (!Json::parse(user_fields_json ? user_fields_json : "[]", &spec, &err) || spec.type != Json::Array) { g_err = "bad user field spec JSON: " + err; return 1; }
+  if (!Json::parse(dense_columns_json ? dense_columns_json : "[]", &dense, &err) || dense.type != Json::Array) { g_err = "bad dense column JSON: " + err; return 1; }
+  if (!Json::parse(outputs_json ? outputs_json : "[]", &outs, &err) || outs.type != Json::Array) { g_err = "bad outputs JSON: " + err; return 1; }
+  std::vector<std::string> cols, names;
+  for (const Json& v : dense.arr) cols.push_back(v.as_string());
+  for (const Json& v : outs.arr) names.push_back(v.as_string());
+  algorithm::RegisterAlgorithm(algo_name, std::make_shared<algorithm::GpuEasyrecAlgorithm>(s->catalog, model, parse_field_specs(spec),
+                                                                                         std::move(cols), std::move(names)));
+  return 0;
+}
+
+static void json_props(const Json& j, module::Features* out) {
+  for (auto& kv : j.obj) {
+    if (kv.second.type == Json::Number) {
+      if (kv.second.is_int) (*out)[kv.first] = (int64_t)kv.second.num;
+      else (*out)[kv.first] = kv.second.num;
+    } else if (kv.second.type == Json::String) (*out)[kv.first] = kv.second.str;
+  }
+}
+static std::string json_value(const module::Value& v) {
+  if (auto d = std::get_if<double>(&v)) return Json::number(*d);
+  if (auto i = std::get_if<int64_t>(&v)) return std::to_string(*i);
+  return Json::quote(std::get<std::string>(v));
+}
+// rank::EasyrecAlgoDataGenerator as a pure function, for the CPU tests: RankConf.ContextFeatures / ItemFeatures, the items
+// ([{"item_id": ..., "properties": {...}}, ...]) and the user's properties in, the PBRequests of the request's batches out
+// (JSON list of {"user_features", "item_ids", "context_features", "item_features"}), as RankService would hand them to
+// algorithm.Run.  Returns the bytes needed (incl. NUL); writes when it fits.
+long long ph_easyrec_requests(const char* context_features_json, const char* item_features_json, const char* items_json,
+                              const char* user_json, int batch_count, char* out, unsigned long long cap) {
+  Json cf, itf, items, user;
+  std::string err;
+  if (!Json::parse(context_features_json ? context_features_json : "[]", &cf, &err) || cf.type != Json::Array ||
+      !Json::parse(item_features_json ? item_features_json : "[]", &itf, &err) || itf.type != Json::Array ||
+      !Json::parse(items_json ? items_json : "[]", &items, &err) || items.type != Json::Array ||
+      !Json::parse(user_json ? user_json : "{}", &user, &err) || user.type != Json::Object) {
+    g_err = "bad JSON argument: " + err;
+    return -1;
+  }
+  std::vector<std::string> ctxNames, itemNames;
+  for (const Json& v : cf.arr) ctxNames.push_back(v.as_string());
+  for (const Json& v : itf.arr) itemNames.push_back(v.as_string());
+  module::User u;
+  json_props(user, &u.Properties);
+  const module::Features userFeatures = u.MakeUserFeatures2();
+  rank::EasyrecAlgoDataGenerator gen(ctxNames);
+  gen.SetItemFeatures(itemNames);
+  const bool want = !ctxNames.empty() || !itemNames.empty();
+  if (batch_count <= 0) batch_count = 100;
+  std::vector<rank::EasyrecAlgoDataGenerator::AlgoData> batches;
+  int i = 0;
+  for (const Json& e : items.arr) {
+    auto it = module::NewItem(e["item_id"].as_string());
+    json_props(e["properties"], &it->Properties);
+    module::Features f;
+    if (want) f = it->GetFeatures();
+    gen.AddFeatures(it, want ? &f : nullptr, userFeatures);
+    if (++i % batch_count == 0) batches.push_back(gen.GeneratorAlgoData());
+  }
+  if (gen.HasFeatures()) batches.push_back(gen.GeneratorAlgoData());
+  auto columns = [](const std::map<std::string, std::vector<module::Value>>& m) {
+    std::string o = "{";
+    bool first = true;
+    for (auto& kv : m) {
+      if (!first) o += ",";
+      first = false;
+      o += Json::quote(kv.first) + ":[";
+      for (size_t k = 0; k < kv.second.size(); ++k) { if (k) o += ","; o += json_value(kv.second[k]); }
+      o += "]";
+    }
+    return o + "}";
+  };
+  std::string o = "[";
+  for (size_t b = 0; b < batches.size(); ++b) {
+    const easyrec::PBRequest& r = batches[b].Request;
+    if (b) o += ",";
+    o += "{\"user_features\":{";
+    bool first = true;
+    for (auto& kv : r.UserFeatures) { if (!first) o += ","; first = false; o += Json::quote(kv.first) + ":" + json_value(kv.second); }
+    o += "},\"item_ids\":[";
+    for (size_t k = 0; k < r.ItemIds.size(); ++k) { if (k) o += ","; o += Json::quote(r.ItemIds[k]); }
+    o += "],\"context_features\":" + columns(r.ContextFeatures) + ",\"item_features\":" + columns(r.ItemFeatures) + "}";
+  }
+  o += "]";
+  const long long need = (long long)o.size() + 1;
+  if (out && cap >= (unsigned long long)need) memcpy(out, o.c_str(), (size_t)need);
+  return need;
+}
+
 // An embedding hook (sort.RegisterEmbeddingHook, sort/dpp_sort.go:56-58) backed by a host table: item id -> row of
 // emb[n_ids][dim] (ids without a row get zeros).  Stands for a user-registered Go function in the tests.
 int ph_register_embedding_hook(ph_server* s, const char* hook_name, const char* const* ids, const double* emb,

@@ -2,7 +2,9 @@
 #include "pairec_host.hpp"
 
 #include <algorithm>
+#include <cctype>
 #include <charconv>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <sstream>
@@ -48,6 +50,8 @@ Error LoadConfig(const std::string& json, RecommendConfig* out) {
     c.RankAlgoList = str_list(rc.second["RankAlgoList"]);
     c.RankScore = rc.second["RankScore"].as_string();
     c.Processor = rc.second["Processor"].as_string();
+    c.ContextFeatures = str_list(rc.second["ContextFeatures"]);
+    c.ItemFeatures = str_list(rc.second["ItemFeatures"]);
     c.BatchCount = rc.second["BatchCount"].as_int();
     out->RankConf[rc.first] = c;
   }
@@ -99,6 +103,8 @@ Error LoadConfig(const std::string& json, RecommendConfig* out) {
     c.RankConf.RankAlgoList = str_list(rc["RankAlgoList"]);
     c.RankConf.RankScore = rc["RankScore"].as_string();
     c.RankConf.Processor = rc["Processor"].as_string();
+    c.RankConf.ContextFeatures = str_list(rc["ContextFeatures"]);
+    c.RankConf.ItemFeatures = str_list(rc["ItemFeatures"]);
     c.RankConf.BatchCount = rc["BatchCount"].as_int();
     for (auto& a : g.second["ActionConfs"].arr) c.ActionConfs.push_back({a["ActionType"].as_string(), a["ActionName"].as_string()});
     out->GeneralRankConfs[g.first] = c;
@@ -151,6 +157,21 @@ Error Item::FloatExprData(const std::string& name, double* out) {
   if (pt != Properties.end()) { *out = ToFloat(pt->second, 0); return ""; }
   *out = 0;
   return "not found,name:" + name;
+}
+Features User::MakeUserFeatures() const {   // module/user.go:137-159
+  Features features;
+  for (auto& kv : Properties) {
+    if (kv.first == "type") continue;
+    if (auto str = std::get_if<std::string>(&kv.second)) {   // strconv.ParseFloat(str, 64) succeeds -> float64
+      const char* b = str->c_str();
+      char* e = nullptr;
+      const double v = std::strtod(b, &e);
+      // (ParseFloat takes the whole string or fails; it accepts no leading / trailing blanks)
+      if (!str->empty() && e == b + str->size() && !std::isspace((unsigned char)b[0])) { features[kv.first] = v; continue; }
+    }
+    features[kv.first] = kv.second;
+  }
+  return features;
 }
 }  // namespace module
 
@@ -513,7 +534,11 @@ void RankWithConfig(const recconf::RankConfig& rankConfig, module::User* user, s
                     context::RecommendContext* ctx) {
   int batchCount = rankConfig.BatchCount > 0 ? rankConfig.BatchCount : 100;  // :163-166
   if (rankConfig.RankAlgoList.empty() && rankConfig.RankScore.empty()) return;  // :168-171 (before any custom rank runs)
-  const module::Features userFeatures = user ? user->MakeUserFeatures() : module::Features();
+  // Processor "EasyRec" (eas.Eas_Processor_EASYREC, algorithm/eas/model.go:25): MakeUserFeatures2 and the columnar
+  // generator (rank_service.go:173-182)
+  const bool easyrecProcessor = rankConfig.Processor == "EasyRec";
+  const module::Features userFeatures =
+      !user ? module::Features() : (easyrecProcessor ? user->MakeUserFeatures2() : user->MakeUserFeatures());
   // custom ranks (rank_service.go:131-137, :185-204): the first IRank whose Filter claims an item takes it, with
   // features = item.GetFeatures() overlaid by the user's (custom_rank.go:33-43); the rest goes to the algorithms
   std::vector<module::ItemPtr> items;
@@ -542,18 +567,35 @@ void RankWithConfig(const recconf::RankConfig& rankConfig, module::User* user, s
     Error e = ast::Parse(rankConfig.RankScore, &exprAst);
     if (!e.empty()) { ctx->LogError("module=rank\trankscore=" + rankConfig.RankScore + "\terror=" + e); exprAst = nullptr; }
   }
+  // one generator per request (its column layout is fixed by the config or by the first item); it is emptied per batch
+  std::unique_ptr<EasyrecAlgoDataGenerator> egen;
+  if (easyrecProcessor) {
+    egen = std::make_unique<EasyrecAlgoDataGenerator>(rankConfig.ContextFeatures);
+    egen->SetItemFeatures(rankConfig.ItemFeatures);
+  }
+  const bool wantItemFeatures = !rankConfig.ContextFeatures.empty() || !rankConfig.ItemFeatures.empty();   // :207-212
   for (size_t b0 = 0; b0 < items.size(); b0 += (size_t)batchCount) {
     const size_t b1 = std::min(items.size(), b0 + (size_t)batchCount);
     algorithm::FeatureList feats;
-    feats.reserve(b1 - b0);
-    for (size_t i = b0; i < b1; ++i) {  // AlgoDataGenerator.AddFeatures (algo_data.go:104-118): user ∪ item features
-      module::Features f = userFeatures;
-      for (auto& kv : items[i]->GetFeatures()) f[kv.first] = kv.second;
-      feats.push_back(std::move(f));
+    EasyrecAlgoDataGenerator::AlgoData edata;
+    if (egen) {
+      for (size_t i = b0; i < b1; ++i) {
+        module::Features f;
+        if (wantItemFeatures) f = items[i]->GetFeatures();
+        egen->AddFeatures(items[i], wantItemFeatures ? &f : nullptr, userFeatures);
+      }
+      edata = egen->GeneratorAlgoData();
+    } else {
+      feats.reserve(b1 - b0);
+      for (size_t i = b0; i < b1; ++i) {  // AlgoDataGenerator.AddFeatures (algo_data.go:104-118): user ∪ item features
+        module::Features f = userFeatures;
+        for (auto& kv : items[i]->GetFeatures()) f[kv.first] = kv.second;
+        feats.push_back(std::move(f));
+      }
     }
     for (auto& algoName : rankConfig.RankAlgoList) {  // :264-289 (one goroutine per batch x algo upstream)
       algorithm::AlgoResult result;
-      Error e = algorithm::Run(algoName, &feats, &result);
+      Error e = egen ? algorithm::Run(algoName, &edata.Request, &result) : algorithm::Run(algoName, &feats, &result);
       if (!e.empty()) { ctx->LogError("module=rank\terror=run algorithm error(" + e + ")"); continue; }  // :274-277
       auto res = std::get_if<algorithm::AlgoResponses>(&result);
       if (!res) continue;
@@ -613,7 +655,115 @@ void GpuRank::Rank(module::User* user, std::vector<module::ItemPtr>& items, cons
     items[i]->Score = sc[i];
   }
 }
+
+// ---- Processor "EasyRec": service/rank/algo_data.go:173-350
+EasyrecAlgoDataGenerator::EasyrecAlgoDataGenerator(const std::vector<std::string>& contextFeatures) {
+  for (auto& name : contextFeatures) itemFeatures_.push_back({name, 2});   // reflect.TypeOf(""): a missing value is ""
+}
+void EasyrecAlgoDataGenerator::SetItemFeatures(const std::vector<std::string>& inputItemFeatures) {
+  if (!inputItemFeatures.empty()) {
+    hasInputItemFeatureMap_ = true;
+    if (inputItemFeatures[0] != "*") {
+      parseInputItemFeature_ = true;
+      for (auto& name : inputItemFeatures) inputItemFeatures_.push_back({name, 2});
+    }   // "*": every feature of the first item that is not a context feature (AddFeatures)
+  } else {
+    parseInputItemFeature_ = true;
+  }
+}
+module::Value EasyrecAlgoDataGenerator::DefaultValue(const Feature& f) {
+  if (f.kind == 0) return 0.0;
+  if (f.kind == 1) return (int64_t)0;
+  return std::string();
+}
+void EasyrecAlgoDataGenerator::AddFeatures(const module::ItemPtr& item, const module::Features* itemFeatures,
+                                           const module::Features& userFeatures) {
+  static const module::Features kNone;
+  const module::Features& feats = itemFeatures ? *itemFeatures : kNone;
+  if (item) requestItem_.push_back(item);
+  if (!parseFeature_) {   // (:243-254; the constructor above always sets parseFeature, as upstream's does)
+    for (auto& kv : feats) itemFeatures_.push_back({kv.first, kv.second.index()});
+    userFeatures_ = userFeatures;
+    parseFeature_ = true;
+  }
+  if (!parseInputItemFeature_) {   // ItemFeatures == ["*"]: the first item decides the input item feature columns
+    for (auto& kv : feats) {
+      bool isContext = false;
+      for (auto& cf : itemFeatures_) isContext |= cf.name == kv.first;
+      if (!isContext) inputItemFeatures_.push_back({kv.first, kv.second.index()});
+    }
+    parseInputItemFeature_ = true;
+  }
+  if (userFeatures_.empty()) userFeatures_ = userFeatures;
+  for (auto& f : itemFeatures_) {
+    auto it = feats.find(f.name);
+    contextFeatures_[f.name].push_back(it != feats.end() ? it->second : DefaultValue(f));
+  }
+  if (hasInputItemFeatureMap_)
+    for (auto& f : inputItemFeatures_) {
+      auto it = feats.find(f.name);
+      inputItemFeatureMap_[f.name].push_back(it != feats.end() ? it->second : DefaultValue(f));
+    }
+}
+EasyrecAlgoDataGenerator::AlgoData EasyrecAlgoDataGenerator::GeneratorAlgoData() {
+  AlgoData d;
+  d.Items = requestItem_;
+  d.Request.UserFeatures = userFeatures_;                                  // builder.AddUserFeature per entry
+  for (auto& it : requestItem_) d.Request.ItemIds.push_back(it->Id);       // builder.AddItemId
+  for (auto& kv : contextFeatures_) { d.Request.ContextFeatures[kv.first] = kv.second; kv.second.clear(); }
+  for (auto& kv : inputItemFeatureMap_) { d.Request.ItemFeatures[kv.first] = kv.second; kv.second.clear(); }
+  requestItem_.clear();
+  return d;
+}
 }  // namespace rank
+
+namespace algorithm {
+namespace {
+struct EasyrecResponse : response::AlgoResponse {   // algorithm/eas/easyrec_response.go:13-33, multiValModule = true
+  std::map<std::string, double> scoreArr;
+  double GetScore() const override { return 0; }
+  std::map<std::string, double> GetScoreMap() const override { return scoreArr; }
+  bool GetModuleType() const override { return true; }
+};
+}  // namespace
+GpuEasyrecAlgorithm::GpuEasyrecAlgorithm(std::shared_ptr<GpuCatalog> cat, int model, std::vector<ingest::FieldSpec> user_fields,
+                                         std::vector<std::string> dense_columns, std::vector<std::string> outputs)
+    : cat_(std::move(cat)), model_(model), user_enc_(std::make_shared<ingest::FieldEncoder>(std::move(user_fields))),
+      dense_(std::move(dense_columns)), outputs_(std::move(outputs)) {}
+
+Error GpuEasyrecAlgorithm::Run(const AlgoData& algoData, AlgoResult* out) {
+  auto pp = std::get_if<const easyrec::PBRequest*>(&algoData);
+  if (!pp || !*pp) return "GpuEasyrecAlgorithm: algoData is not *easyrec.PBRequest";
+  const easyrec::PBRequest& req = **pp;
+  if (req.ItemIds.empty()) { *out = std::monostate{}; return ""; }
+  const size_t n = req.ItemIds.size(), heads = outputs_.size() > 1 ? outputs_.size() : 1;
+  std::vector<uint32_t> rows(n);
+  for (size_t i = 0; i < n; ++i) {
+    auto r = cat_->row_of.find(req.ItemIds[i]);
+    rows[i] = r == cat_->row_of.end() ? 0xFFFFFFFFu : r->second;   // no such item: zeros (easyrec_response.go:56-61)
+  }
+  std::vector<uint32_t> uid(user_enc_->size());
+  if (!uid.empty()) user_enc_->Encode(req.UserFeatures, uid.data());
+  std::vector<float> dense(dense_.size(), 0.f);
+  for (size_t c = 0; c < dense_.size(); ++c) {
+    auto it = req.UserFeatures.find(dense_[c]);
+    if (it != req.UserFeatures.end()) dense[c] = (float)module::ToFloat(it->second, 0.0);
+  }
+  prg_user_features u{uid.empty() ? nullptr : uid.data(), dense.empty() ? nullptr : dense.data()};
+  std::vector<double> sc(n), smap(heads > 1 ? n * heads : 0);
+  if (prg_rank_ex(cat_->h, model_, rows.data(), 1, (int)n, &u, sc.data(), smap.empty() ? nullptr : smap.data(), PRG_MEM_HOST) != PRG_OK)
+    return std::string("prg_rank_ex: ") + prg_last_error();
+  AlgoResponses res(n);
+  for (size_t i = 0; i < n; ++i) {
+    if (heads == 1) { res[i] = std::make_shared<ScoreResponse>(sc[i]); continue; }
+    auto r = std::make_shared<EasyrecResponse>();
+    for (size_t o = 0; o < heads; ++o) r->scoreArr[outputs_[o]] = smap[i * heads + o];
+    res[i] = std::move(r);
+  }
+  *out = std::move(res);
+  return "";
+}
+}  // namespace algorithm
 
 // ================================================================================================ feature
 namespace feature {

@@ -12,13 +12,15 @@
 //   algorithm::IAlgorithm, factory  algorithm/algorithm.go:28-31,107-168 ; LookupPolicy algorithm/lookup.go:37-51
 //   pai_web::VectorRequest/Reply    algorithm/faiss/vectorretrieval.proto:11-20
 //   recall::Recall, VectorRecall    service/recall/recall.go:18-34 ; service/recall/vector_recall.go:32-123
-//   rank::RankService               service/rank/rank_service.go:102-372 (generic processor), utils/ast/ast.go:215-269
+//   rank::RankService               service/rank/rank_service.go:102-372 (generic and EasyRec processors), utils/ast/ast.go:215-269
+//   rank::EasyrecAlgoDataGenerator  service/rank/algo_data.go:173-350 (columnar easyrec.PBRequest: user features, item ids, columns)
 //   sort::ISort, SortService        sort/sort.go:27-35,65-150 ; ItemRankScoreSort sort/item_rank_score.go:26-32 ;
 //                                   AlgoScoreSort sort/algo_score_sort.go:38-66 ; DPPSort sort/dpp_sort.go:108-167
 //   filter::UniqueFilter            filter/unique_filter.go:26-49
 //   service::UserRecommendService   service/user_recommend.go:46-183 (recall -> filter -> rank -> sort -> truncate)
 //
-// GPU-backed plugins (GpuVectorAlgorithm, GpuRankAlgorithm, GpuDPPSort) call libpairec_gpu.so through its C ABI only.
+// GPU-backed plugins (GpuVectorAlgorithm, GpuRankAlgorithm, GpuEasyrecAlgorithm, rank::GpuRank, GpuDPPSort, GpuSSDSort)
+// call libpairec_gpu.so through its C ABI only.
 #pragma once
 #include <functional>
 #include <map>
@@ -42,7 +44,11 @@ namespace recconf {
 struct LookupConfig { std::string FieldName; };
 struct AlgoConfig { std::string Name, Type; LookupConfig LookupConf; };
 struct RecallConfig { std::string Name, RecallType, RecallAlgo, ItemType; int RecallCount = 0; };
-struct RankConfig { std::vector<std::string> RankAlgoList; std::string RankScore, Processor; int BatchCount = 0; };
+struct RankConfig {   // recconf.go:736-745
+  std::vector<std::string> RankAlgoList, ContextFeatures, ItemFeatures;
+  std::string RankScore, Processor;
+  int BatchCount = 0;
+};
 struct DPPSortConfig {
   std::string Name, NormalizeEmb, EnsurePositiveSim, TableName;
   std::vector<std::string> EmbeddingHookNames;
@@ -106,7 +112,8 @@ ItemPtr NewItem(const std::string& id);
 struct User {
   std::string Id;
   Features Properties;
-  Features MakeUserFeatures() const { return Properties; }
+  Features MakeUserFeatures() const;                          // module/user.go:137-159: no "type", numeric strings -> float64
+  Features MakeUserFeatures2() const { return Properties; }   // :161-167 (EasyRec processor): a clone
 };
 }  // namespace module
 
@@ -131,6 +138,17 @@ struct VectorRequest { uint32_t K = 0; std::vector<float> Vector; };
 struct VectorReply { std::vector<uint64_t> Retval; std::vector<float> Scores; std::vector<std::string> Labels; };
 }  // namespace pai_web
 
+namespace easyrec {   // algorithm/eas/easyrec/easyrec_predict.proto:150-212 — the fields the rank path fills
+using PBFeature = module::Value;   // the scalar kinds of the oneof (int / long / float / double / string feature)
+struct PBRequest {
+  std::map<std::string, PBFeature> UserFeatures;                    // user_features = 2
+  std::vector<std::string> ItemIds;                                 // item_ids = 3
+  std::map<std::string, std::vector<PBFeature>> ContextFeatures;    // context_features = 4: one value per item id
+  std::map<std::string, std::vector<PBFeature>> ItemFeatures;       // item_features = 6
+  std::map<std::string, std::string> MetaData;                      // meta_data = 7
+};
+}  // namespace easyrec
+
 namespace algorithm {
 namespace response {
 struct AlgoResponse {  // algorithm/response/resonse.go:3-7
@@ -142,8 +160,9 @@ struct AlgoResponse {  // algorithm/response/resonse.go:3-7
 }  // namespace response
 using FeatureList = std::vector<module::Features>;
 using AlgoResponses = std::vector<std::shared_ptr<response::AlgoResponse>>;
-// Go's interface{} payloads on this path: generic-processor feature maps or a faiss VectorRequest
-using AlgoData = std::variant<std::monostate, const FeatureList*, const pai_web::VectorRequest*>;
+// Go's interface{} payloads on this path: generic-processor feature maps, a faiss VectorRequest or (Processor "EasyRec")
+// the columnar easyrec.PBRequest
+using AlgoData = std::variant<std::monostate, const FeatureList*, const pai_web::VectorRequest*, const easyrec::PBRequest*>;
 using AlgoResult = std::variant<std::monostate, AlgoResponses, pai_web::VectorReply>;
 
 struct IAlgorithm {  // algorithm/algorithm.go:28-31
@@ -294,6 +313,52 @@ class GpuRank : public IRank {
   int model_, heads_;
   std::shared_ptr<ingest::FieldEncoder> user_enc_;
   std::vector<std::string> dense_;
+};
+}
+namespace rank {
+// service/rank/algo_data.go:173-350 — the generator RankService uses when RankConf.Processor == "EasyRec"
+// (CreateAlgoDataGenerator, :33-40): user features ONCE per request, the item ids, and one column per context / input item
+// feature (a value per item, the feature's default where an item lacks it) instead of one merged map per item.
+class EasyrecAlgoDataGenerator {
+ public:
+  struct AlgoData { std::vector<module::ItemPtr> Items; easyrec::PBRequest Request; };
+  explicit EasyrecAlgoDataGenerator(const std::vector<std::string>& contextFeatures);      // :200-218
+  void SetItemFeatures(const std::vector<std::string>& inputItemFeatures);                // :221-237 ("*": infer from the first item)
+  // itemFeatures == nullptr: rank_service.go:207-212 fetches item.GetFeatures() only when the config names features
+  void AddFeatures(const module::ItemPtr& item, const module::Features* itemFeatures, const module::Features& userFeatures);  // :239-290
+  bool HasFeatures() const { return !requestItem_.empty(); }                               // :348-350
+  AlgoData GeneratorAlgoData();                                                            // :292-325
+ private:
+  struct Feature { std::string name; size_t kind; };   // kind: alternative of module::Value (0 double, 1 int64, 2 string)
+  static module::Value DefaultValue(const Feature& f);  // :159-176: 0 of the numeric type, "" otherwise
+  std::vector<module::ItemPtr> requestItem_;
+  std::map<std::string, std::vector<module::Value>> contextFeatures_, inputItemFeatureMap_;
+  std::vector<Feature> itemFeatures_, inputItemFeatures_;
+  module::Features userFeatures_;
+  bool parseFeature_ = true, parseInputItemFeature_ = false, hasInputItemFeatureMap_ = false;
+};
+}
+namespace algorithm {
+// IAlgorithm behind a RankAlgoList name of a scene whose RankConf.Processor is "EasyRec": the stock RankService then
+// hands it ONE easyrec.PBRequest per batch (rank_service.go:273 with algo_data.go:84-86) that carries the item ids and the
+// request's user features — everything the device needs, with no plugin interface beyond IAlgorithm and no feature-load
+// hook.  ItemIds -> rows through the catalog (an unknown id scores 0 on every output, easyrec_response.go:56-61),
+// UserFeatures -> categorical user field ids (ingest::FieldEncoder) and dense context columns, then prg_rank_ex.  The
+// request's context / item feature columns are not read: item features live in the HBM tables, keyed by row.
+// One output: responses carry GetScore(); several (`outputs` names the tower's heads in order): multi-value responses
+// (GetModuleType() == true, GetScoreMap() = {output: score}) as easyrecMutValResponseFunc builds them (:35-70), which
+// RankService stores as algoScores[algo + "_" + output] (rank_service.go:313-334).
+class GpuEasyrecAlgorithm : public IAlgorithm {
+ public:
+  GpuEasyrecAlgorithm(std::shared_ptr<GpuCatalog> cat, int model, std::vector<ingest::FieldSpec> user_fields,
+                      std::vector<std::string> dense_columns, std::vector<std::string> outputs);
+  Error Init(const recconf::AlgoConfig*) override { return ""; }
+  Error Run(const AlgoData& algoData, AlgoResult* out) override;
+ private:
+  std::shared_ptr<GpuCatalog> cat_;
+  int model_;
+  std::shared_ptr<ingest::FieldEncoder> user_enc_;
+  std::vector<std::string> dense_, outputs_;
 };
 }
 namespace general_rank {

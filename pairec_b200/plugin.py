@@ -69,6 +69,14 @@ class HostServer:
                                                 json.dumps(list(user_fields)).encode(),
                                                 json.dumps(list(dense_columns)).encode(), C.c_int(heads)))
 
+    def register_gpu_easyrec(self, algo_name, model, user_fields=(), dense_columns=(), outputs=()):
+        """The GPU rank as an IAlgorithm for scenes with RankConf.Processor == "EasyRec": RankService hands it one
+        easyrec.PBRequest per batch (item ids + the request's user features, service/rank/algo_data.go:292-325)."""
+        self._ck(self._lib.ph_register_gpu_easyrec(self._h, algo_name.encode(), C.c_int(model),
+                                                   json.dumps(list(user_fields)).encode(),
+                                                   json.dumps(list(dense_columns)).encode(),
+                                                   json.dumps(list(outputs)).encode()))
+
     def register_embedding_hook(self, hook_name, ids, emb):
         """sort.RegisterEmbeddingHook(hook_name, fn) with fn = lookup of the item id in emb [len(ids), dim] (f64)."""
         import numpy as np
@@ -102,6 +110,22 @@ def eval_expr(expr, values):
     if lib.ph_eval_expr(expr.encode(), arr, vals, C.c_int(len(names)), C.byref(out)) != 0:
         raise HostError(lib.ph_last_error().decode())
     return out.value
+
+
+def easyrec_requests(items, user=None, context_features=(), item_features=(), batch_count=100):
+    """rank::EasyrecAlgoDataGenerator (service/rank/algo_data.go:173-350) over items [(item_id, properties), ...]: the
+    PBRequests RankService would hand to algorithm.Run for one request, one dict per batch."""
+    lib = load_host_library()
+    lib.ph_easyrec_requests.restype = C.c_longlong
+    args = (json.dumps(list(context_features)).encode(), json.dumps(list(item_features)).encode(),
+            json.dumps([{"item_id": i, "properties": p or {}} for i, p in items]).encode(),
+            json.dumps(user or {}).encode(), C.c_int(batch_count))
+    need = lib.ph_easyrec_requests(*args, None, C.c_ulonglong(0))
+    if need < 0:
+        raise HostError(lib.ph_last_error().decode())
+    buf = C.create_string_buffer(int(need))
+    lib.ph_easyrec_requests(*args, buf, C.c_ulonglong(need))
+    return json.loads(buf.value.decode())
 
 
 def parse_embedding(text, sep=","):

@@ -225,3 +225,65 @@ def test_item_feature_column_sets_encode_to_field_ids():
     assert got.shape == (5, 4)
     assert (got == want).all(), got
     assert encode_fields(spec, []).shape[0] == 0
+
+
+def test_easyrec_generator_builds_the_columnar_request():
+    """RankConf.Processor == "EasyRec" (service/rank/rank_service.go:173-213, algo_data.go:173-350): one PBRequest per
+    batch with the user features once, the item ids, and a column per configured context / input item feature — the
+    request a GPU IAlgorithm receives from the stock RankService (item ids and user features included)."""
+    from pairec_b200.plugin import easyrec_requests
+    items = [("a", {"brand": "x", "price": 3.5, "cnt": 7}), ("b", {"price": 1.25}), ("c", {"brand": "z", "cnt": 2})]
+    user = {"age": 31, "city": "hz", "type": "vip", "level": "3"}
+    # neither ContextFeatures nor ItemFeatures: item.GetFeatures() is not even fetched (:207-212)
+    r = easyrec_requests(items, user)
+    assert r == [{"user_features": user, "item_ids": ["a", "b", "c"], "context_features": {}, "item_features": {}}]
+    # (MakeUserFeatures2 is a clone: "type" stays and "3" stays a string, unlike MakeUserFeatures, module/user.go:137-167)
+    # configured context features are string typed: a missing value is "" (algo_data.go:159-176, :208-214)
+    r = easyrec_requests(items, user, context_features=["brand", "nope"])
+    assert r[0]["context_features"] == {"brand": ["x", "", "z"], "nope": ["", "", ""]} and r[0]["item_features"] == {}
+    # ItemFeatures ["*"]: the FIRST item's features that are not context features become the input item features, with the
+    # default of the type they had there; one request per BatchCount items, the user features in each
+    r = easyrec_requests(items, {"age": 31}, context_features=["brand"], item_features=["*"], batch_count=2)
+    assert [q["item_ids"] for q in r] == [["a", "b"], ["c"]]
+    assert r[0]["context_features"] == {"brand": ["x", ""]} and r[1]["context_features"] == {"brand": ["z"]}
+    assert r[0]["item_features"] == {"cnt": [7, 0], "price": [3.5, 1.25]}
+    assert r[1]["item_features"] == {"cnt": [2], "price": [0]}
+    assert all(q["user_features"] == {"age": 31} for q in r)
+    # named input item features are string typed too
+    r = easyrec_requests(items, {}, item_features=["price", "zzz"])
+    assert r[0]["item_features"] == {"price": [3.5, 1.25, ""], "zzz": ["", "", ""]} and r[0]["context_features"] == {}
+    assert easyrec_requests([], user) == []
+
+
+def test_user_features_reach_the_generic_processor_as_make_user_features_builds_them(server):
+    """module/user.go:137-159: a user property that is a numeric STRING reaches the algorithm as float64 and "type" is
+    dropped; an item feature of the same name wins the merge (service/rank/algo_data.go:104-118).  LOOKUP reads the merged
+    map: items without a "score" property take the user's."""
+    _catalog(server)
+    resp = server.recommend(scene_id="home_feed", uid="u1", size=1000, features={"score": "0.875", "type": "vip"})
+    by_id = {it["item_id"]: it["score"] for it in resp["items"]}
+    assert by_id["i%07d" % 97] == 0.875 and by_id["i%07d" % 194] == 0.875      # no item "score": the user's, parsed
+    assert by_id["i%07d" % 1] != 0.875                                          # the item's own score wins
+    # a non-numeric string stays a string: LOOKUP then fails the float64 assertion for those batches (the reference
+    # panics there, algorithm/lookup.go:45; the mirror logs and leaves the scores)
+    resp = server.recommend(scene_id="home_feed", uid="u1", size=5, features={"score": "n/a"})
+    assert any("not float64" in l for l in resp["log"]), resp["log"]
+
+
+def test_easyrec_processor_hands_the_algorithm_a_pbrequest_not_feature_maps():
+    """RankConf.Processor == "EasyRec": algorithm.Run receives *easyrec.PBRequest (rank_service.go:273 over
+    algo_data.go:84-86).  LOOKUP type-asserts []map[string]interface{} (algorithm/lookup.go:38; the reference panics), so
+    behind this processor it fails per batch and the items keep their scores — the error is logged, nothing aborts."""
+    from pairec_b200.plugin import HostServer
+    conf = json.loads(json.dumps(RECCONF))
+    conf["RankConf"]["home_feed"]["Processor"] = "EasyRec"
+    conf["RankConf"]["home_feed"]["BatchCount"] = 400
+    s = HostServer(conf)
+    try:
+        _catalog(s)
+        resp = s.recommend(scene_id="home_feed", uid="u1", size=10)
+        assert resp["size"] == 10
+        errs = [l for l in resp["log"] if "algoData is not []map" in l]
+        assert len(errs) == 3, resp["log"]          # 1000 unique items / 400 per batch
+    finally:
+        s.close()

@@ -137,6 +137,28 @@ def test_gpu_rank_as_custom_irank_with_user_features_and_hook_embeddings(oracle_
             idx, st = oracle_lib.dpp_request_ex(D[srows].astype(np.float64), ssc, 20, hook=hook[srows], alpha=1.0, window_size=10)
             assert st == 0 and got_rows.tolist() == srows[idx].tolist()
         assert [it["score"] for it in out["u1"]["items"]] != [it["score"] for it in out["u2"]["items"]]
+
+        # The same requests through the OTHER drop-in route: RankConf.Processor "EasyRec".  The stock RankService then
+        # builds one easyrec.PBRequest per batch — item ids + the request's user features (algo_data.go:173-325) — and
+        # hands it to the IAlgorithm registered under the algo name: no IRank, no feature-load hook.  64 items per batch
+        # (4 algorithm.Run calls per request): identical responses.
+        conf2 = dict(conf)
+        conf2["RankConf"] = {"home_feed": {"RankAlgoList": ["gpu_easyrec"], "RankScore": "${gpu_easyrec}",
+                                           "Processor": "EasyRec", "BatchCount": 64}}
+        srv2 = HostServer(conf2)
+        try:
+            srv2.attach_engine(eng, ids)
+            srv2.register_gpu_plugins(recall_algo="gpu_recall", dpp_sort="gpu_dpp")
+            srv2.register_gpu_easyrec("gpu_easyrec", MODEL_FM_MLP,
+                                      user_fields=[{"column": "age_bucket", "id": True}, {"column": "city", "vocab": vocab}],
+                                      dense_columns=["ctx_hour"])
+            srv2.register_embedding_hook("cat_emb", ids, hook)
+            for uid in ("u1", "u2"):
+                srv2.set_user_vector(uid, q)
+                resp2 = srv2.recommend(scene_id="home_feed", uid=uid, size=20, features=feats[uid])
+                assert resp2["code"] == 200 and resp2["items"] == out[uid]["items"], uid
+        finally:
+            srv2.close()
     finally:
         srv.close()
         eng.close()
