@@ -383,6 +383,16 @@ long long ph_recall_cache_roundtrip(const char* const* ids, const double* scores
   return (long long)o.size() + 1;
 }
 
+// alinkFMResponseFunc + GetScore (algorithm/eas/fm_response.go:28-53): response body in, one score per entry out.
+// Returns the number of entries (writes up to cap), or -1 with ph_last_error set.
+long long ph_alink_fm_scores(const char* body, double* out, unsigned long long cap) {
+  algorithm::AlgoResponses res;
+  Error e = algorithm::eas::AlinkFMResponseFunc(body ? body : "", &res);
+  if (!e.empty()) { g_err = e; return -1; }
+  for (size_t i = 0; i < res.size() && i < cap; ++i) out[i] = res[i]->GetScore();
+  return (long long)res.size();
+}
+
 // utils/ast known-answer entry: evaluates an expression over named values (names[i] -> values[i])
 int ph_eval_expr(const char* expr, const char* const* names, const double* values, int n, double* out) {
   std::shared_ptr<ast::Expr> e;

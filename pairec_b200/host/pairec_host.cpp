@@ -213,6 +213,21 @@ void AlgorithmFactory::RegisterAlgorithm(const std::string& name, std::shared_pt
   algorithms_[name] = std::move(a);
 }
 
+Error eas::AlinkFMResponseFunc(const std::string& body, AlgoResponses* out) {
+  Json j;
+  std::string err;
+  if (!Json::parse(body, &j, &err) || j.type != Json::Array)   // (bodyFormat, fm_response.go:55-61)
+    return "error:" + (err.empty() ? std::string("not a JSON list") : err) + ", body:" + body.substr(0, 512);
+  out->clear();
+  for (const Json& e : j.arr) {
+    auto r = std::make_shared<AlinkFMResponse>();
+    r->Result = e["prediction_result"].as_number();
+    r->Score = e["prediction_score"].as_number();
+    out->push_back(std::move(r));
+  }
+  return "";
+}
+
 Error LookupPolicy::Init(const recconf::AlgoConfig* conf) {
   conf_ = conf->LookupConf;
   return "";

@@ -184,6 +184,20 @@ inline void Load(const recconf::RecommendConfig& c) { Factory().Init(c.AlgoConfs
 inline Error Run(const std::string& name, const AlgoData& d, AlgoResult* out) { return Factory().Run(name, d, out); }
 inline void RegisterAlgorithm(const std::string& n, std::shared_ptr<IAlgorithm> a) { Factory().RegisterAlgorithm(n, std::move(a)); }
 
+namespace eas {
+// algorithm/eas/fm_response.go:13-53 — the ALINK_FM processor's wire form: per item the predicted LABEL
+// ("prediction_result") and the probability of THAT label ("prediction_score"); GetScore() turns the pair back into
+// P(label = 1): result == 0 ? 1 - score : score (:28-34).  The in-process FM (prg_rank, PRG_MODEL_FM) has no wire and
+// emits P(1) directly; this restatement is for replaying recorded ALINK responses beside it.
+struct AlinkFMResponse : response::AlgoResponse {
+  double Result = 0, Score = 0;
+  double GetScore() const override { return Result == 0.0 ? 1 - Score : Score; }
+};
+// alinkFMResponseFunc (:36-53): body = JSON list of {"prediction_result", "prediction_score"}; a body that does not parse
+// is an error that quotes its first 512 bytes
+Error AlinkFMResponseFunc(const std::string& body, AlgoResponses* out);
+}  // namespace eas
+
 class LookupPolicy : public IAlgorithm {  // algorithm/lookup.go
  public:
   Error Init(const recconf::AlgoConfig* conf) override;

@@ -128,6 +128,18 @@ def easyrec_requests(items, user=None, context_features=(), item_features=(), ba
     return json.loads(buf.value.decode())
 
 
+def alink_fm_scores(body):
+    """alinkFMResponseFunc + GetScore (algorithm/eas/fm_response.go:28-53): the ALINK_FM response body -> P(label 1) per item."""
+    lib = load_host_library()
+    lib.ph_alink_fm_scores.restype = C.c_longlong
+    n = lib.ph_alink_fm_scores(body.encode(), None, C.c_ulonglong(0))
+    if n < 0:
+        raise HostError(lib.ph_last_error().decode())
+    buf = (C.c_double * int(n))()
+    lib.ph_alink_fm_scores(body.encode(), buf, C.c_ulonglong(n))
+    return list(buf)
+
+
 def parse_embedding(text, sep=","):
     """sort/dpp_sort.go:224-233 embedding text ("{v1,v2,...}") -> list of float."""
     lib = load_host_library()

@@ -287,3 +287,17 @@ def test_easyrec_processor_hands_the_algorithm_a_pbrequest_not_feature_maps():
         assert len(errs) == 3, resp["log"]          # 1000 unique items / 400 per batch
     finally:
         s.close()
+
+
+def test_alink_fm_response_score_flip():
+    """algorithm/eas/fm_response.go:28-53: the ALINK_FM processor answers with the predicted label and the probability of
+    THAT label; GetScore() is result == 0 ? 1 - score : score.  (The in-process FM emits P(label 1) directly; note that the
+    wire form does not round-trip: 1 - 0.7 is 0.30000000000000004.)"""
+    from pairec_b200.plugin import HostError, alink_fm_scores
+    body = json.dumps([{"prediction_result": 1, "prediction_score": 0.8},
+                       {"prediction_result": 0.0, "prediction_score": 0.7, "prediction_detail": "{...}"},
+                       {"prediction_result": 0, "prediction_score": 1.0}])
+    assert alink_fm_scores(body) == [0.8, 1 - 0.7, 0.0]
+    assert alink_fm_scores("[]") == []
+    with pytest.raises(HostError, match="body:"):
+        alink_fm_scores('[{"prediction_result": 1,')
