@@ -348,6 +348,7 @@ static void mlp_worker(void* arg, int tid, int nt) {
 
 ORC_API int orc_mlp_forward(const float* x, int n, int n_layers, const uint32_t* dims, const uint16_t* const* W,
                             const float* const* bias, float* logit_out) {
+  if (n_layers < 1 || n_layers > 64) return 1;
   uint32_t maxd = 0;
   for (int l = 0; l <= n_layers; ++l)
     if (dims[l] > maxd) maxd = dims[l];
