@@ -358,6 +358,9 @@ long long ph_encode_fields(const char* spec_json, const char* rows_json, unsigne
   return (long long)(N * F);
 }
 
+// one "v" of the user-vector text (vector_recall.go:78-79): strconv.ParseFloat(v, 32), error ignored
+float ph_parse_float32(const char* text) { return ingest::ParseFloat32(text ? text : ""); }
+
 // sort/dpp_sort.go:224-233 embedding text -> doubles; returns the element count (writes up to cap)
 long long ph_parse_embedding(const char* text, const char* sep, double* out, unsigned long long cap) {
   auto v = ingest::ParseEmbeddingText(text ? text : "", sep ? sep : "");

@@ -346,7 +346,7 @@ std::vector<module::ItemPtr> VectorRecall::GetCandidateItems(module::User* user,
   while (std::getline(ss, vc, ' ')) {
     const size_t c = vc.find(':');
     if (c == std::string::npos || vc.find(':', c + 1) != std::string::npos) continue;
-    request.Vector.push_back((float)strtod(vc.c_str() + c + 1, nullptr));
+    request.Vector.push_back(ingest::ParseFloat32(vc.substr(c + 1)));
   }
   if (request.Vector.empty()) {
     ctx->LogError("module=VectorRecall\terror=user Vector empty");
@@ -1194,6 +1194,15 @@ std::vector<double> ParseEmbeddingText(const std::string& text, const std::strin
     pos = nx + sep.size();
   }
   return out;
+}
+float ParseFloat32(const std::string& s) {
+  // strconv.ParseFloat(s, 32): ONE rounding, decimal -> nearest float32 (strtof; going through a double first rounds
+  // twice and can land on the other neighbour); the whole string or nothing — on any error the reference's ignored
+  // error leaves 0 (vector_recall.go:78-79)
+  if (s.empty() || std::isspace((unsigned char)s[0])) return 0.f;
+  char* end = nullptr;
+  const float v = std::strtof(s.c_str(), &end);
+  return end == s.c_str() + s.size() ? v : 0.f;
 }
 std::string ToString(const module::Value& v) {
   if (const auto* s = std::get_if<std::string>(&v)) return *s;

@@ -463,6 +463,10 @@ std::vector<double> ParseEmbeddingText(const std::string& text, const std::strin
 std::string FormatRecallCache(const std::vector<module::ItemPtr>& items, const std::string& modelName);
 std::vector<module::ItemPtr> ParseRecallCache(const std::string& s, const std::string& modelName, const std::string& itemType);
 
+// One element of the user-vector text "i:v i:v" (service/recall/vector_recall.go:72-82): strconv.ParseFloat(v, 32) with
+// the error ignored — correctly rounded to float32 in one step, 0 when v does not parse as a whole.
+float ParseFloat32(const std::string& s);
+
 // utils.ToString (utils/type.go:120-140) for the value kinds a fetched column can hold: integers in decimal, floats as
 // strconv.FormatFloat(v, 'f', -1, 64) (shortest digits that round-trip, no exponent), strings unchanged.
 std::string ToString(const module::Value& v);

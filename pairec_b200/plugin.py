@@ -140,6 +140,13 @@ def alink_fm_scores(body):
     return list(buf)
 
 
+def parse_float32(text):
+    """strconv.ParseFloat(text, 32) with the error ignored, as vector_recall.go:78-79 reads a user-vector element."""
+    lib = load_host_library()
+    lib.ph_parse_float32.restype = C.c_float
+    return float(lib.ph_parse_float32(text.encode()))
+
+
 def parse_embedding(text, sep=","):
     """sort/dpp_sort.go:224-233 embedding text ("{v1,v2,...}") -> list of float."""
     lib = load_host_library()

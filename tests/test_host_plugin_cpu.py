@@ -301,3 +301,15 @@ def test_alink_fm_response_score_flip():
     assert alink_fm_scores("[]") == []
     with pytest.raises(HostError, match="body:"):
         alink_fm_scores('[{"prediction_result": 1,')
+
+
+def test_user_vector_elements_are_rounded_to_float32_once():
+    """service/recall/vector_recall.go:78-79: strconv.ParseFloat(v, 32) rounds the decimal text to float32 in ONE step (and
+    the ignored error leaves 0).  Going through a double first rounds twice: just below the midpoint of two floats the
+    double lands ON the midpoint and the tie then goes to the even neighbour — the wrong one."""
+    from pairec_b200.plugin import parse_float32
+    s = "1.000000178813934326171874999"                     # a hair below 1 + 1.5 * 2^-23
+    assert parse_float32(s) == float(np.float32(1 + 2.0 ** -23))
+    assert float(np.float32(float(s))) == float(np.float32(1 + 2.0 ** -22))     # what double rounding would give
+    assert parse_float32("0.25") == 0.25 and parse_float32("1e-3") == float(np.float32(1e-3))
+    assert parse_float32("abc") == 0.0 and parse_float32("1.5x") == 0.0 and parse_float32("") == 0.0
