@@ -1232,21 +1232,28 @@ void FieldEncoder::Encode(const module::Features& properties, uint32_t* out) con
     }
   }
 }
+// fmt's %v of a float64 = strconv.FormatFloat(v, 'g', -1, 64): the shortest digits that round-trip; %e form when the
+// decimal exponent is < -4 or >= 6 (strconv/ftoa.go: "if precision was the shortest possible, use precision 6 for this
+// decision"), at least two exponent digits; otherwise plain decimals.  C's %g decides with the digit count instead
+// (100.0 would print as 1e+02).
+std::string FormatFloatV(double v) {
+  if (std::isnan(v)) return "NaN";
+  if (std::isinf(v)) return v > 0 ? "+Inf" : "-Inf";
+  char buf[64];
+  const auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);   // shortest: d[.ddd]e[+-]XX
+  std::string sci(buf, r.ptr);
+  const size_t e = sci.find('e');
+  const int exp = atoi(sci.c_str() + e + 1);
+  if (exp < -4 || exp >= 6) return sci;   // (to_chars writes the exponent the way strconv does: sign, >= 2 digits)
+  const auto f = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);           // shortest, no exponent
+  return std::string(buf, f.ptr);
+}
 std::string FormatRecallCache(const std::vector<module::ItemPtr>& items, const std::string& modelName) {
   std::string s;
   for (size_t i = 0; i < items.size(); ++i) {
     if (i) s += ",";
-    char buf[64];
-    // fmt.Sprintf("%s:%s:%v", id, modelName, score): %v of a float64 is strconv 'g' with the shortest repr
-    snprintf(buf, sizeof buf, "%.17g", items[i]->Score);
-    double back = strtod(buf, nullptr);
-    for (int prec = 1; prec < 17; ++prec) {  // shortest round-tripping representation
-      char b2[64];
-      snprintf(b2, sizeof b2, "%.*g", prec, items[i]->Score);
-      if (strtod(b2, nullptr) == items[i]->Score) { snprintf(buf, sizeof buf, "%s", b2); break; }
-    }
-    (void)back;
-    s += items[i]->Id + ":" + modelName + ":" + buf;
+    // fmt.Sprintf("%s:%s:%v", id, modelName, score) (vector_recall.go:106)
+    s += items[i]->Id + ":" + modelName + ":" + FormatFloatV(items[i]->Score);
   }
   return s;
 }

@@ -460,6 +460,7 @@ namespace ingest {
 // the separator, ParseFloat each element (an unparsable element stays 0, as upstream logs and continues).
 std::vector<double> ParseEmbeddingText(const std::string& text, const std::string& sep);
 // recall result cache "id:name:score,id:name:score" (service/recall/vector_recall.go:35-58 read, :103-110 write)
+std::string FormatFloatV(double v);   // fmt's %v of a float64 (strconv 'g', shortest)
 std::string FormatRecallCache(const std::vector<module::ItemPtr>& items, const std::string& modelName);
 std::vector<module::ItemPtr> ParseRecallCache(const std::string& s, const std::string& modelName, const std::string& itemType);
 

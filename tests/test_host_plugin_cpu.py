@@ -152,6 +152,14 @@ def test_ingest_formats():
     assert cache == "a:u2i:0.5,b:u2i:0.123456789,c:u2i:1e-07"             # fmt %v of float64 (vector_recall.go:107)
     assert [(d["item_id"], d["score"], d["retrieve_id"]) for d in back] == [("a", 0.5, "u2i"), ("b", 0.123456789, "u2i"),
                                                                            ("c", 1e-7, "u2i")]
+    # %v = strconv 'g' with the shortest digits: exponent form below 1e-4 and from 1e6 on, whatever the digit count
+    # (C's %g would print 100.0 as 1e+02 and 1234567.0 as 1234567)
+    vals = [100.0, 20000.0, 999999.0, 1000000.0, 1234567.0, 0.0001, 0.00009, 12.5, -3.0, 0.0, 1e21, 123456789.125]
+    want = ["100", "20000", "999999", "1e+06", "1.234567e+06", "0.0001", "9e-05", "12.5", "-3", "0", "1e+21",
+            "1.23456789125e+08"]
+    cache, back = recall_cache_roundtrip(["i%d" % i for i in range(len(vals))], vals, "m")
+    assert cache == ",".join("i%d:m:%s" % (i, w) for i, w in enumerate(want))
+    assert [d["score"] for d in back] == vals
 
 
 def test_dosort_head_truncation_and_embedding_miss_threshold(oracle_lib):
