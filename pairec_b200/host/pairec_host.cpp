@@ -517,8 +517,13 @@ Error Eval(const Expr& e, const std::function<bool(const std::string&, double*)>
         if (r == 0) return "violation of arithmetic specification: a division by zero in ExprASTResult";  // panics upstream
         *out = l / r;
       } else if (op == "%") {
-        if ((long long)r == 0) return "integer divide by zero";
-        *out = (double)((long long)l % (long long)r);
+        // float64(int(l) % int(r)); Go's int() of a NaN / out-of-range float64 is the minimum int64 on amd64
+        auto to_int = [](double v) -> long long {
+          return (v >= -9223372036854775808.0 && v < 9223372036854775808.0) ? (long long)v : (long long)0x8000000000000000ull;
+        };
+        const long long li = to_int(l), ri = to_int(r);
+        if (ri == 0) return "integer divide by zero";
+        *out = ri == -1 ? 0.0 : (double)(li % ri);   // (x % -1 is 0; the machine instruction traps on MinInt64 % -1)
       } else *out = 0;
       return "";
     }
