@@ -299,3 +299,24 @@ def test_reciprocal_division_is_correctly_rounded_for_f32_operands():
         q0 = a * y
         q = fma(fma(-q0, b, a), y, q0)
         assert q == float(Fraction(a) / Fraction(b)), (a, b)
+
+
+def test_go_sort_order_three_restatements_agree(oracle_lib):
+    """Go's pdqsort (sort.Sort / sort.Slice, go1.19+) restated three times — oracle.c, the library's host entry
+    prg_sort_desc_host (csrc/sort.cu) and, written separately, tests/ref_py.go_sort_perm — must give the same permutation
+    on random, tied, sorted, reversed, organ-pipe, constant and periodic inputs (the tie order is part of "bit-exact final
+    ordering"; no Go toolchain here to ask the real thing: baseline/go/sort/b200_sort_test.go does that elsewhere)."""
+    from pairec_b200.binding import sort_desc_host
+    rng = np.random.default_rng(0)
+    n_cases = 0
+    for n in (2, 5, 12, 13, 49, 50, 51, 100, 333, 1000, 2000):
+        a = rng.random(n)
+        for s in (a, np.round(a, 1), np.sort(a), np.sort(a)[::-1].copy(), np.zeros(n), (np.arange(n) % 7).astype(float),
+                  np.concatenate([np.arange(n // 2), np.arange(n - n // 2)[::-1]]).astype(float)):
+            s = np.ascontiguousarray(s, dtype=np.float64)
+            want = oracle_lib.go_sort(s).tolist()
+            assert ref_py.go_sort_perm(s.tolist(), True) == want, n
+            assert sort_desc_host(s).tolist() == want, n
+            assert ref_py.go_sort_perm(s.tolist(), False) == oracle_lib.go_sort(s, descending=False).tolist(), n
+            n_cases += 1
+    assert n_cases == 77
