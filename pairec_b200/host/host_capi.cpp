@@ -396,6 +396,16 @@ long long ph_alink_fm_scores(const char* body, double* out, unsigned long long c
   return (long long)res.size();
 }
 
+// tfservingResponseFunc (algorithm/tfserving/response.go:51-63): outputs [rows][cols] -> one score per value, row-major
+long long ph_tfserving_scores(const double* outputs, int rows, int cols, double* out, unsigned long long cap) {
+  if (rows < 0 || cols < 0 || (!outputs && rows * cols > 0)) { g_err = "bad arguments"; return -1; }
+  std::vector<std::vector<double>> o((size_t)rows);
+  for (int r = 0; r < rows; ++r) o[(size_t)r].assign(outputs + (size_t)r * cols, outputs + (size_t)(r + 1) * cols);
+  auto res = algorithm::tfserving::TfservingResponseFunc(o);
+  for (size_t i = 0; i < res.size() && i < cap; ++i) out[i] = res[i]->GetScore();
+  return (long long)res.size();
+}
+
 // utils/ast known-answer entry: evaluates an expression over named values (names[i] -> values[i])
 int ph_eval_expr(const char* expr, const char* const* names, const double* values, int n, double* out) {
   std::shared_ptr<ast::Expr> e;

@@ -228,6 +228,13 @@ Error eas::AlinkFMResponseFunc(const std::string& body, AlgoResponses* out) {
   return "";
 }
 
+AlgoResponses tfserving::TfservingResponseFunc(const std::vector<std::vector<double>>& outputs) {
+  AlgoResponses ret;
+  for (auto& val : outputs)
+    for (double score : val) ret.push_back(std::make_shared<ScoreResponse>(score));
+  return ret;
+}
+
 Error LookupPolicy::Init(const recconf::AlgoConfig* conf) {
   conf_ = conf->LookupConf;
   return "";

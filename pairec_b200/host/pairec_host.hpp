@@ -198,6 +198,13 @@ struct AlinkFMResponse : response::AlgoResponse {
 Error AlinkFMResponseFunc(const std::string& body, AlgoResponses* out);
 }  // namespace eas
 
+namespace tfserving {
+// tfservingResponseFunc (algorithm/tfserving/response.go:51-63): PredictResponse.Outputs [][]float64 — one row per item,
+// one value per output — flattened row-major into one single-score response per VALUE.  prg_rank_ex's score map
+// ([items][heads]) has the same layout, so a one-head tower gives one response per item in item order.
+AlgoResponses TfservingResponseFunc(const std::vector<std::vector<double>>& outputs);
+}  // namespace tfserving
+
 class LookupPolicy : public IAlgorithm {  // algorithm/lookup.go
  public:
   Error Init(const recconf::AlgoConfig* conf) override;

@@ -140,6 +140,19 @@ def alink_fm_scores(body):
     return list(buf)
 
 
+def tfserving_scores(outputs):
+    """tfservingResponseFunc (algorithm/tfserving/response.go:51-63): Outputs [][]float64 -> one score per value."""
+    import numpy as np
+    lib = load_host_library()
+    lib.ph_tfserving_scores.restype = C.c_longlong
+    o = np.ascontiguousarray(outputs, dtype=np.float64).reshape(len(outputs), -1)
+    buf = (C.c_double * max(1, o.size))()
+    n = lib.ph_tfserving_scores(o.ctypes.data_as(C.c_void_p), C.c_int(o.shape[0]), C.c_int(o.shape[1]), buf, C.c_ulonglong(o.size))
+    if n < 0:
+        raise HostError(lib.ph_last_error().decode())
+    return list(buf)[:int(n)]
+
+
 def parse_float32(text):
     """strconv.ParseFloat(text, 32) with the error ignored, as vector_recall.go:78-79 reads a user-vector element."""
     lib = load_host_library()
