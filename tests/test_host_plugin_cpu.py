@@ -321,3 +321,11 @@ def test_user_vector_elements_are_rounded_to_float32_once():
     assert float(np.float32(float(s))) == float(np.float32(1 + 2.0 ** -22))     # what double rounding would give
     assert parse_float32("0.25") == 0.25 and parse_float32("1e-3") == float(np.float32(1e-3))
     assert parse_float32("abc") == 0.0 and parse_float32("1.5x") == 0.0 and parse_float32("") == 0.0
+
+
+def test_tfserving_response_flattens_row_major():
+    """algorithm/tfserving/response.go:51-63: one single-score response per VALUE of Outputs, rows first — the layout of
+    prg_rank_ex's score map, so a one-output tower yields one response per item in item order."""
+    from pairec_b200.plugin import tfserving_scores
+    assert tfserving_scores([[0.1], [0.7], [0.3]]) == [0.1, 0.7, 0.3]
+    assert tfserving_scores([[0.1, 0.9], [0.7, 0.2]]) == [0.1, 0.9, 0.7, 0.2]
