@@ -74,3 +74,19 @@ def test_batcher_entry_points_reject_bad_arguments_without_a_gpu():
     assert lib.prg_batcher_recommend(None, None, None, None, C.byref(n)) != 0
     assert lib.prg_batcher_stats(None, None, None, None) != 0
     lib.prg_batcher_stop(None)   # no-op
+
+
+def test_every_symbol_the_python_front_ends_call_is_exported():
+    """binding.py / plugin.py are ctypes: a misspelt entry point would only fail when its line runs (on the GPU box)."""
+    import ctypes
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for py, so, prefix in (("binding.py", "libpairec_gpu.so", "prg_"), ("plugin.py", "libpairec_host.so", "ph_")):
+        src = open(os.path.join(root, "pairec_b200", py)).read()
+        names = set(re.findall(r"\b(?:_lib|lib|self\._lib)\.(" + prefix + r"[a-z0-9_]+)", src))
+        names |= set(re.findall(r'"(' + prefix + r'[a-z0-9_]+)"', src))
+        assert len(names) >= 10, (py, names)
+        lib = ctypes.CDLL(os.path.join(root, "pairec_b200", so))
+        missing = [n for n in sorted(names) if not hasattr(lib, n)]
+        assert not missing, f"{py} calls symbols {so} does not export: {missing}"
