@@ -10,6 +10,13 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:          # a port nobody holds right now (two tests, or two checkouts, on one machine)
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -39,7 +46,7 @@ def test_sharded_recall_two_ranks_gloo():
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (os.getpid() % 2000)
+    port = _free_port()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world)) and len(ret) == world
 
@@ -122,7 +129,7 @@ def test_global_threshold_all_to_all_protocol_two_ranks_gloo(adversarial):
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 31500 + (os.getpid() % 2000) + (7 if adversarial else 0)
+    port = _free_port()
     mp.spawn(_a2a_worker, args=(world, port, adversarial, ret), nprocs=world, join=True)
     assert len(ret) == world
     assert all(ret[r][0] for r in range(world)), "a rank's merged lists differ from the unsharded top-k"
